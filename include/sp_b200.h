@@ -1,0 +1,269 @@
+/*
+ * sp_b200.h — C ABI of the B200-native neighbour-search / pair-sweep engine.
+ *
+ * This is the drop-in boundary for the hot path of SmoothedParticles.jl
+ * (reference = /root/reference, pure Julia).  Every entry point is `extern "C"`,
+ * takes plain pointers and sizes, returns an int32 status (0 = SP_OK) and never
+ * throws.  A Julia host binds these with `ccall` (see INTEGRATION.md and
+ * julia/SmoothedParticlesB200.jl); the Python host in
+ * smoothedparticles.jl_b200/ binds them with ctypes.
+ *
+ * Reference interface each group replaces (file:line relative to the reference):
+ *   sp_create / sp_key_params        ParticleSystem ctor          src/structs.jl:57-91
+ *   sp_add_field / sp_upload / ...   struct-of-arrays storage of  src/structs.jl:53 (particles::Vector{T})
+ *                                    and ParticleField            src/structs.jl:118-125
+ *   sp_create_cell_list              create_cell_list!            src/core.jl:51-90 (+ find_key structs.jl:97-106,
+ *                                                                 is_inside(Box) geometry.jl:24-30)
+ *   sp_apply                         apply! / apply_unary! /      src/core.jl:94-161
+ *                                    apply_binary!
+ *   sp_sum_at_points                 SmoothedParticles.sum(sys,f,x)  src/core.jl:240-260
+ *   sp_poisson_apply / sp_poisson_cg assemble_matrix + cg         src/core.jl:196-225,
+ *                                                                 examples/collapse_dry_implicit.jl:154-163,223-227
+ *   sp_reduce                        energy / get_globals loops   examples/collapse_dry.jl:166-187
+ *   sp_kernel_eval                   kernel functions             src/kernels.jl
+ *
+ * Because arbitrary Julia closures cannot run inside CUDA kernels, the per-pair
+ * and per-particle actions of the shipped examples are *registered operators*
+ * (SP_OP_*), each taking a list of field ids (the "binding": which device field
+ * plays x, v, rho, ...) and a block of Float64 parameters that the host computes
+ * exactly as the reference's `const` expressions are folded (e.g. 0.5*dt).
+ *
+ * Threading: a handle is not thread-safe; calls on one handle are ordered on one
+ * CUDA stream.  Calls that return host data synchronise; the others may return
+ * before the device finished (errors then surface at the next synchronising call).
+ */
+#ifndef SP_B200_H
+#define SP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SP_ABI_VERSION 1
+
+/* ---- status codes -------------------------------------------------------- */
+enum {
+    SP_OK = 0,
+    SP_ERR_INVALID = 1,   /* bad argument (null pointer, bad id, wrong field count ...) */
+    SP_ERR_CUDA = 2,      /* CUDA runtime error, text in sp_last_error */
+    SP_ERR_NO_DEVICE = 3, /* no usable CUDA device: there is NO CPU fallback */
+    SP_ERR_STATE = 4,     /* call out of order (e.g. sweep before create_cell_list) */
+    SP_ERR_NCCL = 5,
+    SP_ERR_NOT_CONVERGED = 6
+};
+
+/* ---- SPH kernel families (src/kernels.jl) -------------------------------- */
+enum {
+    SP_KERNEL_WENDLAND1 = 1, /* kernels.jl:206-228 */
+    SP_KERNEL_WENDLAND2 = 2, /* kernels.jl:108-147 */
+    SP_KERNEL_WENDLAND3 = 3, /* kernels.jl:156-204 */
+    SP_KERNEL_SPLINE23 = 4,  /* kernels.jl:14-60   */
+    SP_KERNEL_SPLINE24 = 5   /* kernels.jl:69-99   */
+};
+enum { SP_KFUN_W = 0, SP_KFUN_DW = 1, SP_KFUN_RDW = 2, SP_KFUN_DDW = 3 /* wendland3 only */ };
+
+/* ---- registered operators -------------------------------------------------
+ * `fields` lists field ids in the role order given; `params` in the order given.
+ * x_pq = p.x - q.x, v_pq = p.v - q.v, r = |x_pq| (IEEE, un-fused, core.jl:8-10).
+ * All binary operators visit exactly the reference's neighbour set:
+ * q in the 9/27 linear-offset cells, !(r > h), q !== p  (core.jl:94-112).
+ */
+enum {
+    /* WCSPH — examples/collapse_dry.jl, collapse3d.jl, cavity_flow.jl */
+    SP_OP_BALANCE_OF_MASS = 1,
+    /* binary. fields {x, v, rho, Drho}; params {kernel, m, h, two_nu}
+       Drho_p += (m*rDw(h,r)) * (dot(x_pq, v_pq) + two_nu*(rho_p - rho_q))
+       collapse_dry.jl:112-115, collapse3d.jl:87-90; cavity_flow.jl:92-94 is two_nu = 0 */
+    SP_OP_FIND_PRESSURE = 2,
+    /* unary. fields {rho, Drho, P}; params {dt, c2, rho0, P0}
+       rho += Drho*dt; Drho = 0; P = P0 + c2*(rho - rho0)   (P0 = 0 -> term skipped)
+       collapse_dry.jl:123-127, collapse3d.jl:92-96, cavity_flow.jl:96-100 */
+    SP_OP_INTERNAL_FORCE = 3,
+    /* binary. fields {x, v, P, rho, Dv, type}; params {kernel, m, h, mu, rho0}
+       if type_p == 0: ker = m*rDw(h,r);
+         Dv_p += (-ker*(P_p/rho_p^2 + P_q/rho_q^2))*x_pq;  Dv_p += (2*ker*mu/rho0^2)*v_pq
+       collapse_dry.jl:135-141; collapse3d.jl:98-104 with the correction named in DESIGN.md */
+    SP_OP_INTERNAL_FORCE_CAVITY = 4,
+    /* binary. fields {x, v, P, rho, Dv, type}; params {m, h, Re, vlid, ylid, lid_type}
+       cavity_flow.jl:102-114 (rDwendland2, lid extrapolation, Monaghan viscosity) */
+    SP_OP_MOVE = 5,
+    /* unary. fields {x, v, Dv, type}; params {dtm}   Dv = 0; if type == 0: x += dtm*v
+       collapse_dry.jl:148-153 (dtm = 0.5*dt), collapse3d.jl:106-111 (dtm = dt), cavity_flow.jl:117-122 */
+    SP_OP_ACCELERATE = 6,
+    /* unary. fields {v, Dv, type}; params {hdt, gx, gy, gz}   if type == 0: v += hdt*(Dv + g)
+       collapse_dry.jl:155-159, collapse3d.jl:113-117, cavity_flow.jl:124-128 (g = 0) */
+
+    /* operators of tests/test_collision_2d.jl */
+    SP_OP_DENSITY_SUM = 7,
+    /* binary, honours self. fields {x, out}; params {kernel, m, h}   out_p += m*w(h,r)
+       test_collision_2d.jl:63-69 (find_rho!, find_rho0!) */
+    SP_OP_PRESSURE_FROM_RHO = 8,
+    /* unary. fields {rho, rho0, P}; params {c2}   P = c2*(rho - rho0)   test_collision_2d.jl:71-73 */
+    SP_OP_INTERNAL_FORCE_SYM = 9,
+    /* binary. fields {x, P, a}; params {kernel, m, h, rho0}
+       a_p += (-(m*rDw)*(P_p/rho0^2 + P_q/rho0^2))*x_pq     test_collision_2d.jl:75-78 */
+    SP_OP_FILL = 10,
+    /* unary. fields {f}; params {value}   every component of f = value   test_collision_2d.jl:80-86 */
+    SP_OP_ADVECT = 11,
+    /* unary. fields {x, v}; params {dt}   x += dt*v   test_collision_2d.jl:88-90 */
+    SP_OP_KICK = 12,
+    /* unary. fields {v, a}; params {hdt}   v += hdt*a   test_collision_2d.jl:92-94 */
+
+    /* ISPH — examples/collapse_dry_implicit.jl */
+    SP_OP_ISPH_INITIALIZE = 20,
+    /* unary. fields {x, v, div, L, lambda, type}; params {dt, gx, gy, gz}   :118-126 */
+    SP_OP_ISPH_VISCOUS_FORCE = 21,
+    /* binary. fields {x, v, Dv}; params {kernel, m, h, mu, rho}   Dv_p += (2*m*mu*rDk/rho^2)*v_pq   :128-130 */
+    SP_OP_ISPH_DIV_L_LAMBDA = 22,
+    /* binary. fields {x, v, div, L, lambda}; params {kernel, m, h, rho, dim}   :147-152 */
+    SP_OP_ISPH_PROJECTION_VECTOR = 23,
+    /* unary (assemble_vector). fields {div, b}; params {h, dt}   b = -h^2*div/dt   :165-167 */
+    SP_OP_ISPH_INTERNAL_FORCE = 25,
+    /* binary. fields {x, P, Dv}; params {kernel, m, h, rho}   Dv_p -= (m*rDk*(P_p+P_q)/rho^2)*x_pq   :132-134 */
+    SP_OP_ISPH_ACCELERATE = 26
+    /* unary. fields {v, Dv, type}; params {dt}   if type == 0: v += dt*Dv;  Dv = 0   :136-141 */
+};
+
+/* sp_apply flags */
+enum {
+    SP_FLAG_SELF = 1,        /* apply!(...; self=true): add the (p,p,0.0) term after the sweep (core.jl:155-157) */
+    SP_FLAG_STRICT_ORDER = 2 /* accumulate in the reference's order: key_diff order x descending index */
+};
+
+/* reductions (diagnostic loops of the examples) */
+enum {
+    SP_RED_ENERGY_WCSPH = 1,
+    /* fields {x, v, rho}; params {m, c, rho0, gx, gy, gz}; out[1]
+       sum of 0.5 m v.v - m g.x + m c^2 (log|rho/rho0| + rho0/rho - 1)   collapse_dry.jl:166-171 */
+    SP_RED_FRONT = 2,
+    /* fields {x, type}; params {width, height, h, xmax}; out[2] = {X, H}   collapse_dry.jl:173-187 */
+    SP_RED_ENERGY_COLLISION = 3,
+    /* fields {v, rho, rho0}; params {m, c, rho0}; out[1]   test_collision_2d.jl:96-100 */
+    SP_RED_SUM = 4,
+    /* fields {f}; out[ncomp] plain sum of every component */
+    SP_RED_ENERGY_ISPH = 5
+    /* fields {x, v}; params {m, gx, gy, gz}; out[1]   collapse_dry_implicit.jl:173-177 */
+};
+
+/* point sums:  out[k] = sum_q func(q, |x_k - q.x|)  over !(r > h), no self exclusion (core.jl:240-260) */
+enum {
+    SP_SUM_MASS_W = 1,  /* fields {x, type}; params {kernel, m, h, type_sel}: [type==type_sel]*m*w(h,r)       cavity_flow.jl:169,173 */
+    SP_SUM_MASS_F_W = 2 /* fields {x, type, f}; params {kernel, m, h, type_sel, comp}: ... *f[comp]*w(h,r)   cavity_flow.jl:170,174 */
+};
+
+/* host array layout for upload/download of a field with ncomp components */
+enum {
+    SP_LAYOUT_AOS = 0, /* host[i*ncomp + c]  (a Julia Vector{SVector{3,Float64}} reinterpreted) */
+    SP_LAYOUT_SOA = 1  /* host[c*n + i] */
+};
+
+typedef struct sp_system sp_system;
+
+/* ---- library ------------------------------------------------------------- */
+int32_t sp_version(void);
+/* Text of the last error on this handle (or of the last failed sp_create when sys == NULL). */
+const char* sp_last_error(const sp_system* sys);
+int32_t sp_device_count(int32_t* count);
+
+/* ---- particle system (src/structs.jl:57-91) ------------------------------
+ * lo/hi = corners of boundarybox(domain); h = neighbour radius.  Computes key_phase,
+ * key_lim, key_max, key_diff exactly as the constructor does.  Field 0 "x" (3 comps)
+ * always exists. */
+int32_t sp_create(sp_system** out, const double lo[3], const double hi[3], double h, int32_t device);
+int32_t sp_destroy(sp_system* sys);
+int32_t sp_key_params(const sp_system* sys, int64_t key_phase[3], int64_t key_lim[3], int64_t* key_max,
+                      int32_t* n_key_diff, int64_t key_diff[27]);
+
+/* ---- fields (struct-of-arrays replacement of the particle struct) -------- */
+int32_t sp_add_field(sp_system* sys, const char* name, int32_t ncomp, int32_t* fid);
+int32_t sp_find_field(const sp_system* sys, const char* name, int32_t* fid);
+/* Set the particle count.  Growing appends zero-initialised particles at the end of the
+ * reference order (push!, src/grids.jl:256); shrinking drops the tail. */
+int32_t sp_resize(sp_system* sys, int64_t n);
+int32_t sp_num_particles(sp_system* sys, int64_t* n);
+/* Host data is always in REFERENCE ORDER (index i = sys.particles[i+1] of the reference),
+ * whatever order the device keeps internally.  n must equal the particle count. */
+int32_t sp_upload(sp_system* sys, int32_t fid, const double* host, int64_t n, int32_t layout);
+int32_t sp_download(sp_system* sys, int32_t fid, double* host, int64_t n, int32_t layout);
+int32_t sp_synchronize(sp_system* sys);
+
+/* ---- the hot path --------------------------------------------------------- */
+int32_t sp_create_cell_list(sp_system* sys);
+int32_t sp_apply(sp_system* sys, int32_t op, const int32_t* fields, int32_t nfields, const double* params,
+                 int32_t nparams, int32_t flags);
+int32_t sp_sum_at_points(sp_system* sys, int32_t sum_op, const int32_t* fields, int32_t nfields,
+                         const double* params, int32_t nparams, const double* xyz /* m x 3 AoS */, int64_t m,
+                         double* out /* m */);
+int32_t sp_reduce(sp_system* sys, int32_t red, const int32_t* fields, int32_t nfields, const double* params,
+                  int32_t nparams, double* out);
+
+/* ---- ISPH pressure-Poisson operator, matrix-free ---------------------------
+ * (A p)_i = A_ii p_i + sum_{j != i, r <= h} (2 h^2 m/rho) rDk(h,r_ij) p_j,
+ * A_ii = h^2 L_i + [type_i == 0] C_free max(lambda_i, 0)
+ * = the matrix assemble_matrix(sys, projection_matrix) builds (collapse_dry_implicit.jl:154-163).
+ * fields {x, L, lambda, type, p_in, y_out}; params {kernel, m, h, rho, C_free}. */
+int32_t sp_poisson_apply(sp_system* sys, const int32_t* fields, int32_t nfields, const double* params,
+                         int32_t nparams);
+/* Unpreconditioned CG from x0 = 0 on A P = b, stopping at |r| <= max(reltol*|b|, abstol) or maxiter
+ * (IterativeSolvers.cg defaults: reltol = sqrt(eps), abstol = 0, maxiter = N).
+ * fields {x, L, lambda, type, b, P}; the result is written to P.  maxiter <= 0 -> N. */
+int32_t sp_poisson_cg(sp_system* sys, const int32_t* fields, int32_t nfields, const double* params,
+                      int32_t nparams, double reltol, double abstol, int64_t maxiter, int64_t* iters,
+                      double* resid);
+
+/* ---- fused step programs (amortise launch latency; same arithmetic) ------ */
+enum {
+    SP_PROGRAM_WCSPH_3D = 1, /* examples/collapse3d.jl:136-150 — move, cell list, balance_of_mass,
+                                find_pressure, internal_force, accelerate, accelerate */
+    SP_PROGRAM_WCSPH_2D = 2  /* examples/collapse_dry.jl:203-211 */
+};
+/* fields {x, v, Dv, rho, Drho, P, type}; params {kernel, m, h, two_nu, dt, c2, rho0, mu, gx, gy, gz} */
+int32_t sp_run_program(sp_system* sys, int32_t program, const int32_t* fields, int32_t nfields,
+                       const double* params, int32_t nparams, int64_t nsteps);
+
+/* ---- kernel functions on the device (tests/test_kernels.jl parity) ------- */
+int32_t sp_kernel_eval(int32_t kernel, int32_t kfun, double h, const double* r, double* out, int64_t n,
+                       int32_t device);
+
+/* ---- parity / debug views (all in reference order, 1-based like the reference) */
+/* keys[i] = find_key(sys, particles[i].x) as stored by the last sp_create_cell_list */
+int32_t sp_get_cell_keys(sp_system* sys, int64_t* keys, int64_t n);
+/* CSR view of cell_list: cell k (1-based) holds members[offsets[k-1] .. offsets[k]) — 1-based particle
+ * indices in DESCENDING order, exactly the non-zero prefix of cell_list[k].entries (core.jl:26-41). */
+int32_t sp_get_cell_list(sp_system* sys, int64_t* offsets /* key_max+1 */, int64_t* members /* n */);
+/* Neighbour lists as visited by apply_binary!: for particle i (0-based slot in the arrays),
+ * ids[offsets[i] .. offsets[i+1]) = 1-based indices q in the reference's visiting order.
+ * Call with ids == NULL to get only offsets (offsets[n] = total). */
+int32_t sp_get_neighbour_lists(sp_system* sys, int64_t* offsets /* n+1 */, int64_t* ids, int64_t ids_cap);
+/* Number of particles removed by all sp_create_cell_list calls so far. */
+int32_t sp_num_removed(sp_system* sys, int64_t* n_removed);
+/* Device timing of the last call in ms (CUDA events on the handle's stream). */
+int32_t sp_last_call_ms(sp_system* sys, float* ms);
+/* Count of kernel launches issued by this handle since creation. */
+int32_t sp_launch_count(sp_system* sys, int64_t* launches);
+
+/* ---- slab decomposition over the GPUs of one node (no counterpart in the reference) ----
+ * One process per GPU.  The host exchanges an NCCL unique id out of band (128 bytes from
+ * sp_slab_unique_id on rank 0) and every rank calls sp_slab_init.  The global cell grid of
+ * sp_create is cut along `axis` into `nranks` slabs of whole cells; each rank owns the particles
+ * whose cell lies in its slab and keeps one ghost cell layer per side.  periodic != 0 wraps the
+ * slab axis (and ONLY that axis) with period = key_lim[axis]*h. */
+int32_t sp_slab_unique_id(uint8_t id[128]);
+int32_t sp_slab_init(sp_system* sys, const uint8_t id[128], int32_t rank, int32_t nranks, int32_t axis,
+                     int32_t periodic);
+/* Migration of owned particles that left the slab + rebuild of the local cell list + ghost exchange
+ * of every field.  Replaces sp_create_cell_list on a slab system. */
+int32_t sp_slab_create_cell_list(sp_system* sys);
+/* Refresh the ghost copies of the listed fields from their owners (e.g. P, rho after find_pressure). */
+int32_t sp_slab_halo_refresh(sp_system* sys, const int32_t* fields, int32_t nfields);
+/* Owned (non-ghost) particle count on this rank. */
+int32_t sp_slab_num_owned(sp_system* sys, int64_t* n_owned);
+/* Sum / max all-reduce of host doubles over the slab communicator (CG dots, diagnostics). */
+int32_t sp_slab_allreduce(sp_system* sys, double* inout, int32_t count, int32_t is_max);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SP_B200_H */

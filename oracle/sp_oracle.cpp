@@ -1,0 +1,942 @@
+// sp_oracle.cpp — CPU ORACLE.  TEST INFRASTRUCTURE ONLY, NOT PRODUCT CODE.
+//
+// A C++17/OpenMP restatement of the reference's algorithm for the hot path of
+// SmoothedParticles.jl v0.2.0 (pure Julia; the reference cannot run in this image because
+// no Julia runtime exists here or on the GPU box).  Only tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline / `--impl reference` leg may load this library; the product
+// (smoothedparticles.jl_b200/) never does.
+//
+// PARITY PINNING.  The reference ships no golden vectors for this path.  What pins this
+// restatement to the Julia code is (1) the reference's own assertions, ported 1:1 and run
+// against this file in tests/test_oracle_pins.py: tests/test_kernels.jl:20-61 (kernel
+// known-answer properties) and tests/test_collision_2d.jl:118-149 (particle count constant,
+// energy growth < 1e-2 over 4 167 Verlet steps); (2) an independent brute-force O(N^2) /
+// scipy cKDTree neighbour check.  No output of the Julia reference itself could be
+// generated, and that limitation is stated in DESIGN.md.
+//
+// Every function cites the reference file:line it follows (paths relative to the
+// reference root).  Compile with -ffp-contract=off and without fast-math so each
+// arithmetic operation is individually rounded, as Julia does outside @fastmath.
+//
+// Particle storage mirrors the reference's array of mutable structs: one record of NSLOT
+// Float64 per particle; an operator's "field binding" is the offset of a struct field in
+// the record (the C analogue of p.rho, p.Dv ...).
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <limits>
+#include <string>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../include/sp_b200.h"  // operator / kernel ids only
+
+#define NSLOT 20
+
+namespace {
+
+struct Particle {
+    double f[NSLOT];
+};
+
+struct OSys {
+    double h;
+    double lo[3], hi[3];  // domain == its bounding Box (structs.jl:63,87)
+    int64_t key_phase[3], key_lim[3], key_max;
+    std::vector<int64_t> key_diff;
+    std::vector<Particle> particles;
+    // cell_list as CSR: cell k (1-based) = entries[cell_start[k-1] .. cell_start[k]), 1-based particle
+    // indices in DESCENDING order == the non-zero prefix of Cell.entries after add_index! (core.jl:26-41).
+    std::vector<int64_t> cell_start;
+    std::vector<int64_t> entries;
+    bool have_cells = false;
+    int64_t n_removed = 0;
+    std::string err;
+};
+
+// ------------------------------------------------------------------ kernels.jl
+// @fastmath in the reference: only a tolerance (not bits) is meaningful against these.
+inline double pw2(double x) { return x * x; }
+inline double pw3(double x) { return x * x * x; }
+inline double pw4(double x) { return (x * x) * (x * x); }
+inline double pos(double x) { return x > 0.0 ? x : 0.0; }  // kernels.jl:3-5
+
+double spline23(double h, double r) {  // kernels.jl:14-24
+    double x = r / h;
+    if (x < 0.5) return 1.8189136353359467 * (1.0 - 6.0 * pw2(x) + 6.0 * pw3(x)) / pw2(h);
+    else if (x < 1.0) return 3.6378272706718935 * pw3(1.0 - x) / pw2(h);
+    return 0.0;
+}
+double Dspline23(double h, double r) {  // kernels.jl:33-42
+    double x = r / h;
+    if (x < 0.5) return -10.91348181201568 * (2.0 * x - 3.0 * pw2(x)) / pw3(h);
+    else if (x < 1.0) return -10.91348181201568 * pw2(1.0 - x) / pw3(h);
+    return 0.0;
+}
+double rDspline23(double h, double r) {  // kernels.jl:51-60
+    double x = r / h;
+    if (x < 0.5) return -10.91348181201568 * (2.0 - 3.0 * x) / pw4(h);
+    else if (x < 1.0) return -10.91348181201568 * pw2(1.0 - x) / (x * pw4(h));
+    return 0.0;
+}
+double spline24(double h, double r) {  // kernels.jl:69-72
+    double x = r / h;
+    return 6.222175110452539 * (pw4(pos(1.0 - x)) - 5 * pw4(pos(0.6 - x)) + 10 * pw4(pos(0.2 - x))) / pw2(h);
+}
+double Dspline24(double h, double r) {  // kernels.jl:81-84
+    double x = r / h;
+    return -24.888700441810155 * (pw3(pos(1.0 - x)) - 5 * pw3(pos(0.6 - x)) + 10 * pw3(pos(0.2 - x))) / pw3(h);
+}
+double rDspline24(double h, double r) {  // kernels.jl:93-99
+    double x = r / h;
+    if (x > 0.2) return -24.888700441810155 * (pw3(pos(1.0 - x)) - 5 * pw3(pos(0.6 - x))) / (x * pw4(h));
+    return -24.888700441810155 * (1.2 - 6.0 * pw2(x)) / pw4(h);
+}
+double wendland2(double h, double r) {  // kernels.jl:108-115
+    double x = r / h;
+    if (x > 1.0) return 0.0;
+    return 2.228169203286535 * pw4(1.0 - x) * (1.0 + 4.0 * x) / pw2(h);
+}
+double Dwendland2(double h, double r) {  // kernels.jl:124-131
+    double x = r / h;
+    if (x > 1.0) return 0.0;
+    return -44.563384065730695 * x * pw3(1.0 - x) / pw3(h);
+}
+double rDwendland2(double h, double r) {  // kernels.jl:140-147
+    double x = r / h;
+    if (x > 1.0) return 0.0;
+    return -44.563384065730695 * pw3(1.0 - x) / pw4(h);
+}
+double wendland3(double h, double r) {  // kernels.jl:156-163
+    double x = r / h;
+    if (x > 1.0) return 0.0;
+    return 3.3422538049298023 * pw4(1.0 - x) * (1.0 + 4.0 * x) / pw3(h);
+}
+double Dwendland3(double h, double r) {  // kernels.jl:172-179
+    double x = r / h;
+    if (x > 1.0) return 0.0;
+    return -66.84507609859604 * x * pw3(1.0 - x) / pw4(h);
+}
+double rDwendland3(double h, double r) {  // kernels.jl:188-195
+    double x = r / h;
+    if (x > 1.0) return 0.0;
+    return -66.84507609859604 * pw3(1.0 - x) / (pw4(h) * h);
+}
+double DDwendland3(double h, double r) {  // kernels.jl:197-204
+    double x = r / h;
+    if (x > 1.0) return 0.0;
+    return -66.84507609859604 * ((1.0 - 4.0 * x) * pw2(1.0 - x)) / (pw4(h) * h);
+}
+double wendland1(double h, double r) {  // kernels.jl:206-212
+    double x = r / h;
+    if (x > 1.0) return 0.0;
+    return 1.5 * pw4(1.0 - x) * (1.0 + 4.0 * x) / h;
+}
+double Dwendland1(double h, double r) {  // kernels.jl:214-220
+    double x = r / h;
+    if (x > 1.0) return 0.0;
+    return -30.0 * x * pw3(1.0 - x) / pw2(h);
+}
+double rDwendland1(double h, double r) {  // kernels.jl:222-228
+    double x = r / h;
+    if (x > 1.0) return 0.0;
+    return -30.0 * pw3(1.0 - x) / pw3(h);
+}
+
+double kernel_eval(int kernel, int kfun, double h, double r) {
+    switch (kernel) {
+        case SP_KERNEL_WENDLAND1:
+            return kfun == SP_KFUN_W ? wendland1(h, r) : kfun == SP_KFUN_DW ? Dwendland1(h, r) : rDwendland1(h, r);
+        case SP_KERNEL_WENDLAND2:
+            return kfun == SP_KFUN_W ? wendland2(h, r) : kfun == SP_KFUN_DW ? Dwendland2(h, r) : rDwendland2(h, r);
+        case SP_KERNEL_WENDLAND3:
+            return kfun == SP_KFUN_W    ? wendland3(h, r)
+                   : kfun == SP_KFUN_DW ? Dwendland3(h, r)
+                   : kfun == SP_KFUN_DDW ? DDwendland3(h, r)
+                                         : rDwendland3(h, r);
+        case SP_KERNEL_SPLINE23:
+            return kfun == SP_KFUN_W ? spline23(h, r) : kfun == SP_KFUN_DW ? Dspline23(h, r) : rDspline23(h, r);
+        case SP_KERNEL_SPLINE24:
+            return kfun == SP_KFUN_W ? spline24(h, r) : kfun == SP_KFUN_DW ? Dspline24(h, r) : rDspline24(h, r);
+    }
+    return std::numeric_limits<double>::quiet_NaN();
+}
+
+// ------------------------------------------------------------------ structs.jl
+// ParticleSystem constructor, structs.jl:57-91
+void init_keys(OSys& s) {
+    for (int a = 0; a < 3; a++) {
+        s.key_phase[a] = (int64_t)std::floor(s.lo[a] / s.h);                        // :66
+        s.key_lim[a] = (int64_t)std::floor(s.hi[a] / s.h) - s.key_phase[a] + 1;    // :67
+    }
+    s.key_max = s.key_lim[0] * s.key_lim[1] * s.key_lim[2];  // :68
+    s.key_diff.clear();
+    if (s.key_lim[2] == 1) {  // :70  2-D
+        for (int di = -1; di <= 1; di++)
+            for (int dj = -1; dj <= 1; dj++) s.key_diff.push_back(di + s.key_lim[0] * dj);  // :73-75
+    } else {
+        for (int di = -1; di <= 1; di++)
+            for (int dj = -1; dj <= 1; dj++)
+                for (int dk = -1; dk <= 1; dk++)
+                    s.key_diff.push_back(di + s.key_lim[0] * (dj + s.key_lim[1] * dk));  // :79-81
+    }
+}
+
+// find_key, structs.jl:97-106.  Int64(floor(x/h)) throws on NaN/Inf -> -1.
+inline int64_t find_key(const OSys& s, const double* x) {
+    double q0 = std::floor(x[0] / s.h), q1 = std::floor(x[1] / s.h), q2 = std::floor(x[2] / s.h);
+    if (!std::isfinite(q0) || !std::isfinite(q1) || !std::isfinite(q2)) return -1;
+    if (std::fabs(q0) > 9.0e18 || std::fabs(q1) > 9.0e18 || std::fabs(q2) > 9.0e18) return -1;
+    int64_t i = 1 + (int64_t)q0 - s.key_phase[0];
+    int64_t j = 1 + (int64_t)q1 - s.key_phase[1];
+    int64_t k = 1 + (int64_t)q2 - s.key_phase[2];
+    return i + s.key_lim[0] * (j - 1) + s.key_lim[0] * s.key_lim[1] * (k - 1);
+}
+
+// is_inside(x, Box), geometry.jl:24-30 — closed intervals, NaN compares false => outside.
+inline bool is_inside_box(const OSys& s, const double* x) {
+    return s.lo[0] <= x[0] && x[0] <= s.hi[0] && s.lo[1] <= x[1] && x[1] <= s.hi[1] && s.lo[2] <= x[2] &&
+           x[2] <= s.hi[2];
+}
+
+// ------------------------------------------------------------------ core.jl
+// dist, core.jl:8-10 -> norm/dot algebra.jl:49-60: sqrt((dx*dx + dy*dy) + dz*dz), un-fused.
+inline double dist3(const double* a, const double* b, double* d) {
+    d[0] = a[0] - b[0];
+    d[1] = a[1] - b[1];
+    d[2] = a[2] - b[2];
+    return std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+}
+
+// Removal of out-of-domain particles, core.jl:63-81 (literal, serial).
+// removal_cell.entries ends up sorted DESCENDING (add_index!, core.jl:26-41); the i-th victim slot
+// receives the CURRENT particles[end+1-i]; then the vector is truncated.
+int64_t remove_outside(OSys& s) {
+    const int64_t N = (int64_t)s.particles.size();
+    std::vector<int64_t> victims;  // 1-based
+    for (int64_t i = N; i >= 1; i--)
+        if (!is_inside_box(s, s.particles[i - 1].f)) victims.push_back(i);  // descending
+    int64_t i = 1;
+    while (i <= (int64_t)victims.size()) {
+        s.particles[victims[i - 1] - 1] = s.particles[N + 1 - i - 1];  // :74
+        i++;
+    }
+    if (i > 1) s.particles.resize(N + 1 - i);  // :77-79
+    return i - 1;
+}
+
+// create_cell_list!, core.jl:51-90.  The observable result (each cell's member indices in descending
+// order) is independent of thread interleaving; it is produced here by a stable counting sort.
+void create_cell_list(OSys& s) {
+    s.n_removed += remove_outside(s);
+    const int64_t N = (int64_t)s.particles.size();
+    std::vector<int64_t> keys(N);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < N; i++) keys[i] = find_key(s, s.particles[i].f);  // :86
+    s.cell_start.assign(s.key_max + 1, 0);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < N; i++) {
+#pragma omp atomic
+        s.cell_start[keys[i]]++;  // keys are 1-based: count of cell k at [k]
+    }
+    // exclusive scan: cell_start[k-1] = first slot of cell k
+    int64_t run = 0;
+    for (int64_t k = 1; k <= s.key_max; k++) {
+        int64_t c = s.cell_start[k];
+        s.cell_start[k - 1] = run;
+        run += c;
+    }
+    s.cell_start[s.key_max] = run;
+    s.entries.resize(N);
+    std::vector<int64_t> fill(s.cell_start.begin(), s.cell_start.end() - 1);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 1; i <= N; i++) {
+        int64_t slot;
+#pragma omp atomic capture
+        slot = fill[keys[i - 1] - 1]++;
+        s.entries[slot] = i;
+    }
+    // add_index! keeps every cell sorted DESCENDING whatever the insertion order (core.jl:32-37)
+#pragma omp parallel for schedule(dynamic, 4096)
+    for (int64_t k = 1; k <= s.key_max; k++)
+        if (s.cell_start[k] - s.cell_start[k - 1] > 1)
+            std::sort(s.entries.begin() + s.cell_start[k - 1], s.entries.begin() + s.cell_start[k],
+                      std::greater<int64_t>());
+    s.have_cells = true;
+}
+
+// Literal restatement of the insertion path (find_vacation!/add_index!, core.jl:13-41) used only to
+// cross-check create_cell_list() in the tests: cells are growable zero-padded vectors.
+void create_cell_list_literal(OSys& s, std::vector<std::vector<int64_t>>& cells) {
+    cells.assign(s.key_max, {});
+    const int64_t N = (int64_t)s.particles.size();
+    for (int64_t i = 1; i <= N; i++) {
+        int64_t key = find_key(s, s.particles[i - 1].f);
+        std::vector<int64_t>& e = cells[key - 1];
+        size_t ind = 0;
+        while (ind < e.size() && e[ind] != 0) ind++;  // find_vacation!
+        if (ind == e.size()) e.resize(ind + 1);
+        e[ind] = i;
+        while (ind > 0 && e[ind - 1] < e[ind]) {  // reorder
+            std::swap(e[ind], e[ind - 1]);
+            ind--;
+        }
+    }
+}
+
+// _apply_binary!, core.jl:94-112, for the particle with 1-based index ip.
+template <class Action>
+inline void apply_binary_one(OSys& s, int64_t ip, Action&& action) {
+    Particle& p = s.particles[ip - 1];
+    int64_t key = find_key(s, p.f);  // :95
+    for (int64_t dkey : s.key_diff) {  // :96
+        int64_t nk = key + dkey;
+        if (1 <= nk && nk <= s.key_max) {  // :98
+            for (int64_t e = s.cell_start[nk - 1]; e < s.cell_start[nk]; e++) {
+                int64_t j = s.entries[e];
+                const Particle& q = s.particles[j - 1];
+                double d[3];
+                double r = dist3(p.f, q.f, d);      // :104
+                if (r > s.h || j == ip) continue;  // :105  (p == q is object identity)
+                action(p, q, d, r);
+            }
+        }
+    }
+}
+
+// apply_binary!, core.jl:125-129
+template <class Action>
+void apply_binary(OSys& s, Action&& action) {
+    const int64_t N = (int64_t)s.particles.size();
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 1; i <= N; i++) apply_binary_one(s, i, action);
+}
+// apply_unary!, core.jl:138-142
+template <class Action>
+void apply_unary(OSys& s, Action&& action) {
+    const int64_t N = (int64_t)s.particles.size();
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < N; i++) action(s.particles[i]);
+}
+
+typedef double (*kfn)(double, double);
+kfn pick_rD(int kernel) {
+    switch (kernel) {
+        case SP_KERNEL_WENDLAND1: return rDwendland1;
+        case SP_KERNEL_WENDLAND2: return rDwendland2;
+        case SP_KERNEL_WENDLAND3: return rDwendland3;
+        case SP_KERNEL_SPLINE23: return rDspline23;
+        case SP_KERNEL_SPLINE24: return rDspline24;
+    }
+    return nullptr;
+}
+kfn pick_w(int kernel) {
+    switch (kernel) {
+        case SP_KERNEL_WENDLAND1: return wendland1;
+        case SP_KERNEL_WENDLAND2: return wendland2;
+        case SP_KERNEL_WENDLAND3: return wendland3;
+        case SP_KERNEL_SPLINE23: return spline23;
+        case SP_KERNEL_SPLINE24: return spline24;
+    }
+    return nullptr;
+}
+
+inline double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }  // algebra.jl:49-51
+
+// apply!, core.jl:151-161, specialised to the registered operators (the example closures).
+int apply_op(OSys& s, int op, const int32_t* F, int nf, const double* P, int np, int flags) {
+    auto need = [&](int f, int p) { return nf == f && np == p; };
+    const bool self = (flags & SP_FLAG_SELF) != 0;
+    switch (op) {
+        case SP_OP_BALANCE_OF_MASS: {  // collapse_dry.jl:112-115, collapse3d.jl:87-90, cavity_flow.jl:92-94
+            if (!need(4, 4)) return SP_ERR_INVALID;
+            const int ox = F[0], ov = F[1], orho = F[2], oD = F[3];
+            kfn rDw = pick_rD((int)P[0]);
+            const double m = P[1], h = P[2], two_nu = P[3];
+            if (!rDw) return SP_ERR_INVALID;
+            apply_binary(s, [=](Particle& p, const Particle& q, const double* xpq, double r) {
+                double ker = m * rDw(h, r);
+                double vpq[3] = {p.f[ov] - q.f[ov], p.f[ov + 1] - q.f[ov + 1], p.f[ov + 2] - q.f[ov + 2]};
+                (void)ox;
+                p.f[oD] += ker * (dot3(xpq, vpq) + two_nu * (p.f[orho] - q.f[orho]));
+            });
+            return SP_OK;
+        }
+        case SP_OP_FIND_PRESSURE: {  // collapse_dry.jl:123-127, cavity_flow.jl:96-100
+            if (!need(3, 4)) return SP_ERR_INVALID;
+            const int orho = F[0], oD = F[1], oP = F[2];
+            const double dt = P[0], c2 = P[1], rho0 = P[2], P0 = P[3];
+            apply_unary(s, [=](Particle& p) {
+                p.f[orho] += p.f[oD] * dt;
+                p.f[oD] = 0.0;
+                double pr = c2 * (p.f[orho] - rho0);
+                p.f[oP] = (P0 != 0.0) ? P0 + pr : pr;
+            });
+            return SP_OK;
+        }
+        case SP_OP_INTERNAL_FORCE: {  // collapse_dry.jl:135-141
+            if (!need(6, 5)) return SP_ERR_INVALID;
+            const int ov = F[1], oP = F[2], orho = F[3], oDv = F[4], ot = F[5];
+            kfn rDw = pick_rD((int)P[0]);
+            const double m = P[1], h = P[2], mu = P[3], rho0 = P[4];
+            if (!rDw) return SP_ERR_INVALID;
+            apply_binary(s, [=](Particle& p, const Particle& q, const double* xpq, double r) {
+                if (p.f[ot] == 0.0) {
+                    double ker = m * rDw(h, r);
+                    double a = -ker * (p.f[oP] / (p.f[orho] * p.f[orho]) + q.f[oP] / (q.f[orho] * q.f[orho]));
+                    for (int c = 0; c < 3; c++) p.f[oDv + c] += a * xpq[c];
+                    double b = 2 * ker * mu / (rho0 * rho0);
+                    for (int c = 0; c < 3; c++) p.f[oDv + c] += b * (p.f[ov + c] - q.f[ov + c]);
+                }
+            });
+            return SP_OK;
+        }
+        case SP_OP_INTERNAL_FORCE_CAVITY: {  // cavity_flow.jl:102-114
+            if (!need(6, 6)) return SP_ERR_INVALID;
+            const int ox = F[0], ov = F[1], oP = F[2], orho = F[3], oDv = F[4], ot = F[5];
+            const double m = P[0], h = P[1], Re = P[2], vlid = P[3], ylid = P[4], lid = P[5];
+            const double eps = 0.01 * (h * h), tenth_h = 0.1 * h;
+            apply_binary(s, [=](Particle& p, const Particle& q, const double* xpq, double r) {
+                double rDk = rDwendland2(h, r);
+                double vpq[3] = {p.f[ov] - q.f[ov], p.f[ov + 1] - q.f[ov + 1], p.f[ov + 2] - q.f[ov + 2]};
+                if (q.f[ot] == lid) {
+                    double sc = std::fabs(xpq[1]) / (tenth_h + std::fabs(p.f[ox + 1] - ylid));
+                    vpq[0] = sc * (p.f[ov] - vlid * 1.0);
+                    vpq[1] = sc * (p.f[ov + 1] - vlid * 0.0);
+                    vpq[2] = sc * (p.f[ov + 2] - vlid * 0.0);
+                }
+                double a = -m * rDk * (p.f[oP] / (p.f[orho] * p.f[orho]) + q.f[oP] / (q.f[orho] * q.f[orho]));
+                for (int c = 0; c < 3; c++) p.f[oDv + c] += a * xpq[c];
+                double b = 8 / (Re * p.f[orho] * q.f[orho]) * m * rDk * dot3(vpq, xpq) / (r * r + eps);
+                for (int c = 0; c < 3; c++) p.f[oDv + c] += b * xpq[c];
+            });
+            return SP_OK;
+        }
+        case SP_OP_MOVE: {  // collapse_dry.jl:148-153
+            if (!need(4, 1)) return SP_ERR_INVALID;
+            const int ox = F[0], ov = F[1], oDv = F[2], ot = F[3];
+            const double dtm = P[0];
+            apply_unary(s, [=](Particle& p) {
+                p.f[oDv] = p.f[oDv + 1] = p.f[oDv + 2] = 0.0;
+                if (p.f[ot] == 0.0)
+                    for (int c = 0; c < 3; c++) p.f[ox + c] += dtm * p.f[ov + c];
+            });
+            return SP_OK;
+        }
+        case SP_OP_ACCELERATE: {  // collapse_dry.jl:155-159
+            if (!need(3, 4)) return SP_ERR_INVALID;
+            const int ov = F[0], oDv = F[1], ot = F[2];
+            const double hdt = P[0], g[3] = {P[1], P[2], P[3]};
+            apply_unary(s, [=](Particle& p) {
+                if (p.f[ot] == 0.0)
+                    for (int c = 0; c < 3; c++) p.f[ov + c] += hdt * (p.f[oDv + c] + g[c]);
+            });
+            return SP_OK;
+        }
+        case SP_OP_DENSITY_SUM: {  // test_collision_2d.jl:63-69; self term added last (core.jl:155-157)
+            if (!need(2, 3)) return SP_ERR_INVALID;
+            const int oo = F[1];
+            kfn w = pick_w((int)P[0]);
+            const double m = P[1], h = P[2];
+            if (!w) return SP_ERR_INVALID;
+            apply_binary(s, [=](Particle& p, const Particle&, const double*, double r) { p.f[oo] += m * w(h, r); });
+            if (self) apply_unary(s, [=](Particle& p) { p.f[oo] += m * w(h, 0.0); });
+            return SP_OK;
+        }
+        case SP_OP_PRESSURE_FROM_RHO: {  // test_collision_2d.jl:71-73
+            if (!need(3, 1)) return SP_ERR_INVALID;
+            const int orho = F[0], orho0 = F[1], oP = F[2];
+            const double c2 = P[0];
+            apply_unary(s, [=](Particle& p) { p.f[oP] = c2 * (p.f[orho] - p.f[orho0]); });
+            return SP_OK;
+        }
+        case SP_OP_INTERNAL_FORCE_SYM: {  // test_collision_2d.jl:75-78
+            if (!need(3, 4)) return SP_ERR_INVALID;
+            const int oP = F[1], oa = F[2];
+            kfn rDw = pick_rD((int)P[0]);
+            const double m = P[1], h = P[2], rho0 = P[3];
+            if (!rDw) return SP_ERR_INVALID;
+            apply_binary(s, [=](Particle& p, const Particle& q, const double* xpq, double r) {
+                double ker = m * rDw(h, r);
+                double a = -ker * (p.f[oP] / (rho0 * rho0) + q.f[oP] / (rho0 * rho0));
+                for (int c = 0; c < 3; c++) p.f[oa + c] += a * xpq[c];
+            });
+            return SP_OK;
+        }
+        case SP_OP_FILL: {  // test_collision_2d.jl:80-86; F[1] = ncomp passed as second "field"
+            if (!need(2, 1)) return SP_ERR_INVALID;
+            const int of = F[0], nc = F[1];
+            const double v = P[0];
+            apply_unary(s, [=](Particle& p) {
+                for (int c = 0; c < nc; c++) p.f[of + c] = v;
+            });
+            return SP_OK;
+        }
+        case SP_OP_ADVECT: {  // test_collision_2d.jl:88-90
+            if (!need(2, 1)) return SP_ERR_INVALID;
+            const int ox = F[0], ov = F[1];
+            const double dt = P[0];
+            apply_unary(s, [=](Particle& p) {
+                for (int c = 0; c < 3; c++) p.f[ox + c] += dt * p.f[ov + c];
+            });
+            return SP_OK;
+        }
+        case SP_OP_KICK: {  // test_collision_2d.jl:92-94
+            if (!need(2, 1)) return SP_ERR_INVALID;
+            const int ov = F[0], oa = F[1];
+            const double hdt = P[0];
+            apply_unary(s, [=](Particle& p) {
+                for (int c = 0; c < 3; c++) p.f[ov + c] += hdt * p.f[oa + c];
+            });
+            return SP_OK;
+        }
+        case SP_OP_ISPH_INITIALIZE: {  // collapse_dry_implicit.jl:118-126
+            if (!need(6, 4)) return SP_ERR_INVALID;
+            const int ox = F[0], ov = F[1], odiv = F[2], oL = F[3], olam = F[4], ot = F[5];
+            const double dt = P[0], g[3] = {P[1], P[2], P[3]};
+            apply_unary(s, [=](Particle& p) {
+                if (p.f[ot] == 0.0) {
+                    for (int c = 0; c < 3; c++) p.f[ox + c] += dt * p.f[ov + c];
+                    for (int c = 0; c < 3; c++) p.f[ov + c] += dt * g[c];
+                }
+                p.f[odiv] = 0.0;
+                p.f[oL] = 0.0;
+                p.f[olam] = 1.0;
+            });
+            return SP_OK;
+        }
+        case SP_OP_ISPH_VISCOUS_FORCE: {  // collapse_dry_implicit.jl:128-130
+            if (!need(3, 5)) return SP_ERR_INVALID;
+            const int ov = F[1], oDv = F[2];
+            kfn rDk = pick_rD((int)P[0]);
+            const double m = P[1], h = P[2], mu = P[3], rho = P[4];
+            if (!rDk) return SP_ERR_INVALID;
+            apply_binary(s, [=](Particle& p, const Particle& q, const double*, double r) {
+                double a = 2.0 * m * mu * rDk(h, r) / (rho * rho);
+                for (int c = 0; c < 3; c++) p.f[oDv + c] += a * (p.f[ov + c] - q.f[ov + c]);
+            });
+            return SP_OK;
+        }
+        case SP_OP_ISPH_DIV_L_LAMBDA: {  // collapse_dry_implicit.jl:147-152
+            if (!need(5, 5)) return SP_ERR_INVALID;
+            const int ov = F[1], odiv = F[2], oL = F[3], olam = F[4];
+            kfn rDkf = pick_rD((int)P[0]);
+            const double m = P[1], h = P[2], rho = P[3], dim = P[4];
+            if (!rDkf) return SP_ERR_INVALID;
+            apply_binary(s, [=](Particle& p, const Particle& q, const double* xpq, double r) {
+                double rDk = rDkf(h, r);
+                double vpq[3] = {p.f[ov] - q.f[ov], p.f[ov + 1] - q.f[ov + 1], p.f[ov + 2] - q.f[ov + 2]};
+                p.f[odiv] += -dot3(xpq, vpq) * m * rDk;
+                p.f[oL] += -2.0 * m / rho * rDk;
+                p.f[olam] += m / rho * rDk * (r * r) / dim;
+            });
+            return SP_OK;
+        }
+        case SP_OP_ISPH_PROJECTION_VECTOR: {  // collapse_dry_implicit.jl:165-167 via assemble_vector core.jl:175-182
+            if (!need(2, 2)) return SP_ERR_INVALID;
+            const int odiv = F[0], ob = F[1];
+            const double h = P[0], dt = P[1];
+            apply_unary(s, [=](Particle& p) { p.f[ob] = -(h * h) * p.f[odiv] / dt; });
+            return SP_OK;
+        }
+        case SP_OP_ISPH_INTERNAL_FORCE: {  // collapse_dry_implicit.jl:132-134
+            if (!need(3, 4)) return SP_ERR_INVALID;
+            const int oP = F[1], oDv = F[2];
+            kfn rDk = pick_rD((int)P[0]);
+            const double m = P[1], h = P[2], rho = P[3];
+            if (!rDk) return SP_ERR_INVALID;
+            apply_binary(s, [=](Particle& p, const Particle& q, const double* xpq, double r) {
+                double a = m * rDk(h, r) * (p.f[oP] + q.f[oP]) / (rho * rho);
+                for (int c = 0; c < 3; c++) p.f[oDv + c] -= a * xpq[c];
+            });
+            return SP_OK;
+        }
+        case SP_OP_ISPH_ACCELERATE: {  // collapse_dry_implicit.jl:136-141
+            if (!need(3, 1)) return SP_ERR_INVALID;
+            const int ov = F[0], oDv = F[1], ot = F[2];
+            const double dt = P[0];
+            apply_unary(s, [=](Particle& p) {
+                if (p.f[ot] == 0.0)
+                    for (int c = 0; c < 3; c++) p.f[ov + c] += dt * p.f[oDv + c];
+                p.f[oDv] = p.f[oDv + 1] = p.f[oDv + 2] = 0.0;
+            });
+            return SP_OK;
+        }
+    }
+    return SP_ERR_INVALID;
+}
+
+// projection_matrix, collapse_dry_implicit.jl:154-163
+inline double projection_matrix(const Particle& p, bool same, double r, int oL, int olam, int ot, kfn rDk, double m,
+                                double h, double rho, double C_free) {
+    if (same) {
+        if (p.f[ot] == 0.0) return (h * h) * p.f[oL] + C_free * std::max(p.f[olam], 0.0);
+        else return (h * h) * p.f[oL];
+    }
+    return 2.0 * (h * h) * m / rho * rDk(h, r);
+}
+
+}  // namespace
+
+// ============================================================== C API (ctypes)
+extern "C" {
+
+void* so_create(const double lo[3], const double hi[3], double h) {
+    if (!(h > 0.0)) return nullptr;  // structs.jl:59
+    OSys* s = new OSys();
+    s->h = h;
+    for (int a = 0; a < 3; a++) {
+        s->lo[a] = lo[a];
+        s->hi[a] = hi[a];
+    }
+    init_keys(*s);
+    return s;
+}
+void so_destroy(void* hnd) { delete (OSys*)hnd; }
+int so_num_slots() { return NSLOT; }
+int so_max_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+void so_set_threads(int n) {
+#ifdef _OPENMP
+    omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+void so_key_params(void* hnd, int64_t phase[3], int64_t lim[3], int64_t* key_max, int32_t* ndiff, int64_t diff[27]) {
+    OSys& s = *(OSys*)hnd;
+    for (int a = 0; a < 3; a++) {
+        phase[a] = s.key_phase[a];
+        lim[a] = s.key_lim[a];
+    }
+    *key_max = s.key_max;
+    *ndiff = (int32_t)s.key_diff.size();
+    for (size_t i = 0; i < s.key_diff.size(); i++) diff[i] = s.key_diff[i];
+}
+
+void so_resize(void* hnd, int64_t n) {
+    OSys& s = *(OSys*)hnd;
+    Particle z;
+    std::memset(&z, 0, sizeof z);
+    s.particles.resize(n, z);
+    s.have_cells = false;
+}
+int64_t so_num_particles(void* hnd) { return (int64_t)((OSys*)hnd)->particles.size(); }
+int64_t so_num_removed(void* hnd) { return ((OSys*)hnd)->n_removed; }
+
+// host AoS [n][ncomp] <-> record offset `slot`
+void so_set_field(void* hnd, int slot, int ncomp, const double* host) {
+    OSys& s = *(OSys*)hnd;
+    const int64_t N = (int64_t)s.particles.size();
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < N; i++)
+        for (int c = 0; c < ncomp; c++) s.particles[i].f[slot + c] = host[i * ncomp + c];
+}
+void so_get_field(void* hnd, int slot, int ncomp, double* host) {
+    OSys& s = *(OSys*)hnd;
+    const int64_t N = (int64_t)s.particles.size();
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < N; i++)
+        for (int c = 0; c < ncomp; c++) host[i * ncomp + c] = s.particles[i].f[slot + c];
+}
+
+void so_create_cell_list(void* hnd) { create_cell_list(*(OSys*)hnd); }
+
+int so_apply(void* hnd, int op, const int32_t* fields, int nf, const double* params, int np, int flags) {
+    OSys& s = *(OSys*)hnd;
+    return apply_op(s, op, fields, nf, params, np, flags);
+}
+
+// keys[i] = find_key(particles[i].x)
+void so_get_cell_keys(void* hnd, int64_t* keys) {
+    OSys& s = *(OSys*)hnd;
+    for (size_t i = 0; i < s.particles.size(); i++) keys[i] = find_key(s, s.particles[i].f);
+}
+void so_get_cell_list(void* hnd, int64_t* offsets, int64_t* members) {
+    OSys& s = *(OSys*)hnd;
+    std::copy(s.cell_start.begin(), s.cell_start.end(), offsets);
+    std::copy(s.entries.begin(), s.entries.end(), members);
+}
+// returns 1 if the literal insertion path (core.jl:13-41) yields exactly the CSR cell list
+int so_check_cell_list_literal(void* hnd) {
+    OSys& s = *(OSys*)hnd;
+    std::vector<std::vector<int64_t>> cells;
+    create_cell_list_literal(s, cells);
+    for (int64_t k = 1; k <= s.key_max; k++) {
+        const auto& e = cells[k - 1];
+        int64_t n = s.cell_start[k] - s.cell_start[k - 1];
+        size_t cnt = 0;
+        while (cnt < e.size() && e[cnt] != 0) cnt++;
+        if ((int64_t)cnt != n) return 0;
+        for (int64_t t = 0; t < n; t++)
+            if (e[t] != s.entries[s.cell_start[k - 1] + t]) return 0;
+    }
+    return 1;
+}
+
+// neighbour lists in the visiting order of _apply_binary! (core.jl:94-112)
+int64_t so_get_neighbour_lists(void* hnd, int64_t* offsets, int64_t* ids, int64_t cap) {
+    OSys& s = *(OSys*)hnd;
+    const int64_t N = (int64_t)s.particles.size();
+    int64_t total = 0;
+    for (int64_t i = 1; i <= N; i++) {
+        offsets[i - 1] = total;
+        Particle& p = s.particles[i - 1];
+        int64_t key = find_key(s, p.f);
+        for (int64_t dkey : s.key_diff) {
+            int64_t nk = key + dkey;
+            if (1 <= nk && nk <= s.key_max)
+                for (int64_t e = s.cell_start[nk - 1]; e < s.cell_start[nk]; e++) {
+                    int64_t j = s.entries[e];
+                    double d[3];
+                    double r = dist3(p.f, s.particles[j - 1].f, d);
+                    if (r > s.h || j == i) continue;
+                    if (ids && total < cap) ids[total] = j;
+                    total++;
+                }
+        }
+    }
+    offsets[N] = total;
+    return total;
+}
+
+// sum(sys, func, x), core.jl:240-260 for the registered point sums (cavity_flow.jl:162-180)
+int so_sum_at_points(void* hnd, int sum_op, const int32_t* F, int nf, const double* P, int np, const double* xyz,
+                     int64_t m_pts, double* out) {
+    OSys& s = *(OSys*)hnd;
+    if (!((sum_op == SP_SUM_MASS_W && nf == 2 && np == 4) || (sum_op == SP_SUM_MASS_F_W && nf == 3 && np == 5)))
+        return SP_ERR_INVALID;
+    kfn w = pick_w((int)P[0]);
+    if (!w) return SP_ERR_INVALID;
+    const double m = P[1], h = P[2], tsel = P[3];
+    const int ot = F[1];
+    const int of = sum_op == SP_SUM_MASS_F_W ? F[2] + (int)P[4] : 0;
+    for (int64_t k = 0; k < m_pts; k++) {
+        const double* x = xyz + 3 * k;
+        double acc = 0.0;
+        int64_t key = find_key(s, x);
+        for (int64_t dkey : s.key_diff) {
+            int64_t nk = key + dkey;
+            if (1 <= nk && nk <= s.key_max)
+                for (int64_t e = s.cell_start[nk - 1]; e < s.cell_start[nk]; e++) {
+                    const Particle& q = s.particles[s.entries[e] - 1];
+                    double d[3];
+                    double r = dist3(x, q.f, d);  // norm(x - q.x)
+                    if (r > s.h) continue;
+                    double sel = (q.f[ot] == tsel) ? 1.0 : 0.0;  // Float64(p.type==FLUID)
+                    if (sum_op == SP_SUM_MASS_W) acc += sel * m * w(h, r);
+                    else acc += sel * m * q.f[of] * w(h, r);
+                }
+        }
+        out[k] = acc;
+    }
+    return SP_OK;
+}
+
+// serial diagnostic loops of the examples
+int so_reduce(void* hnd, int red, const int32_t* F, int nf, const double* P, int np, double* out) {
+    OSys& s = *(OSys*)hnd;
+    switch (red) {
+        case SP_RED_ENERGY_WCSPH: {  // collapse_dry.jl:166-171
+            if (nf != 3 || np != 6) return SP_ERR_INVALID;
+            const int ox = F[0], ov = F[1], orho = F[2];
+            const double m = P[0], c = P[1], rho0 = P[2], g[3] = {P[3], P[4], P[5]};
+            double E = 0.0;
+            for (const Particle& p : s.particles) {
+                double kinetic = 0.5 * m * dot3(p.f + ov, p.f + ov);
+                double potential = -m * dot3(g, p.f + ox);
+                double internal = m * (c * c) * (std::log(std::fabs(p.f[orho] / rho0)) + rho0 / p.f[orho] - 1.0);
+                E += kinetic + potential + internal;
+            }
+            out[0] = E;
+            return SP_OK;
+        }
+        case SP_RED_FRONT: {  // collapse_dry.jl:173-187
+            if (nf != 2 || np != 4) return SP_ERR_INVALID;
+            const int ox = F[0], ot = F[1];
+            const double width = P[0], height = P[1], h = P[2], xmax = P[3];
+            double X = 0.0, H = 0.0;
+            for (const Particle& p : s.particles) {
+                if (p.f[ot] == 0.0) X = std::max(X, p.f[ox] / width);
+                if (p.f[ot] == 0.0 && xmax > p.f[ox] && p.f[ox] > h) H = std::max(H, p.f[ox + 1] / height);
+            }
+            out[0] = X;
+            out[1] = H;
+            return SP_OK;
+        }
+        case SP_RED_ENERGY_COLLISION: {  // test_collision_2d.jl:96-100
+            if (nf != 3 || np != 3) return SP_ERR_INVALID;
+            const int ov = F[0], orho = F[1], orho0 = F[2];
+            const double m = P[0], c = P[1], rho0 = P[2];
+            double E = 0.0;
+            for (const Particle& p : s.particles) {
+                double kinetic = 0.5 * m * dot3(p.f + ov, p.f + ov);
+                double dr = p.f[orho] - p.f[orho0];
+                double internal = 0.5 * m * (c * c) * (dr * dr) / (rho0 * rho0);
+                E += kinetic + internal;
+            }
+            out[0] = E;
+            return SP_OK;
+        }
+        case SP_RED_SUM: {
+            if (nf != 2) return SP_ERR_INVALID;
+            for (int c = 0; c < F[1]; c++) {
+                double a = 0.0;
+                for (const Particle& p : s.particles) a += p.f[F[0] + c];
+                out[c] = a;
+            }
+            return SP_OK;
+        }
+        case SP_RED_ENERGY_ISPH: {  // collapse_dry_implicit.jl:173-177
+            if (nf != 2 || np != 4) return SP_ERR_INVALID;
+            const int ox = F[0], ov = F[1];
+            const double m = P[0], g[3] = {P[1], P[2], P[3]};
+            double E = 0.0;
+            for (const Particle& p : s.particles)
+                E += 0.5 * m * dot3(p.f + ov, p.f + ov) + -m * dot3(g, p.f + ox);
+            out[0] = E;
+            return SP_OK;
+        }
+    }
+    return SP_ERR_INVALID;
+}
+
+// assemble_matrix(sys, projection_matrix), core.jl:196-225: COO triplets in visiting order, 1-based,
+// INCLUDING the diagonal (no p == q skip).  Returns nnz; fills arrays when non-null and cap suffices.
+// fields {x, L, lambda, type}; params {kernel, m, h, rho, C_free}
+int64_t so_assemble_matrix(void* hnd, const int32_t* F, int nf, const double* P, int np, int64_t* I, int64_t* J,
+                           double* V, int64_t cap) {
+    OSys& s = *(OSys*)hnd;
+    if (nf < 4 || np != 5) return -1;
+    const int oL = F[1], olam = F[2], ot = F[3];
+    kfn rDk = pick_rD((int)P[0]);
+    if (!rDk) return -1;
+    const double m = P[1], h = P[2], rho = P[3], C_free = P[4];
+    const int64_t N = (int64_t)s.particles.size();
+    int64_t nnz = 0;
+    for (int64_t i = 1; i <= N; i++) {
+        const Particle& p = s.particles[i - 1];
+        int64_t key = find_key(s, p.f);
+        for (int64_t dkey : s.key_diff) {
+            int64_t nk = key + dkey;
+            if (1 <= nk && nk <= s.key_max)
+                for (int64_t e = s.cell_start[nk - 1]; e < s.cell_start[nk]; e++) {
+                    int64_t l = s.entries[e];
+                    double d[3];
+                    double r = dist3(p.f, s.particles[l - 1].f, d);
+                    if (r > s.h) continue;  // :214
+                    if (I && nnz < cap) {
+                        I[nnz] = i;
+                        J[nnz] = l;
+                        V[nnz] = projection_matrix(p, l == i, r, oL, olam, ot, rDk, m, h, rho, C_free);
+                    }
+                    nnz++;
+                }
+        }
+    }
+    return nnz;
+}
+
+// y = A x for COO triplets (duplicates add, like sparse(I,J,V), core.jl:224)
+void so_coo_matvec(int64_t nnz, const int64_t* I, const int64_t* J, const double* V, const double* x, double* y,
+                   int64_t n) {
+    for (int64_t i = 0; i < n; i++) y[i] = 0.0;
+    for (int64_t k = 0; k < nnz; k++) y[I[k] - 1] += V[k] * x[J[k] - 1];
+}
+
+// cg(A, b): IterativeSolvers.jl (third-party, NOT under /root/reference, version unpinned — the package's
+// Project.toml does not declare it; call site examples/collapse_dry_implicit.jl:40,227).  Published
+// algorithm of its un-preconditioned CGIterable: x0 = 0, u = 0, r = b, tol = max(reltol*|r0|, abstol);
+// loop while |r| > tol and it < maxiter: beta = |r|^2/|r_prev|^2 (|r_prev| = 1 initially);
+// u = r + beta u; c = A u; alpha = |r|^2 / (u.c); x += alpha u; r -= alpha c.
+int64_t so_cg_coo(int64_t nnz, const int64_t* I, const int64_t* J, const double* V, const double* b, double* x,
+                  int64_t n, double reltol, double abstol, int64_t maxiter, double* resid_out) {
+    std::vector<double> r(b, b + n), u(n, 0.0), c(n, 0.0);
+    for (int64_t i = 0; i < n; i++) x[i] = 0.0;
+    auto nrm = [&](const std::vector<double>& v) {
+        double a = 0.0;
+        for (double t : v) a += t * t;
+        return std::sqrt(a);
+    };
+    double residual = nrm(r), prev = 1.0;
+    const double tol = std::max(reltol * residual, abstol);
+    if (maxiter <= 0) maxiter = n;
+    int64_t it = 0;
+    while (it < maxiter && residual > tol) {
+        double beta = residual * residual / (prev * prev);
+        for (int64_t i = 0; i < n; i++) u[i] = r[i] + beta * u[i];
+        so_coo_matvec(nnz, I, J, V, u.data(), c.data(), n);
+        double uc = 0.0;
+        for (int64_t i = 0; i < n; i++) uc += u[i] * c[i];
+        double alpha = residual * residual / uc;
+        for (int64_t i = 0; i < n; i++) {
+            x[i] += alpha * u[i];
+            r[i] -= alpha * c[i];
+        }
+        prev = residual;
+        residual = nrm(r);
+        it++;
+    }
+    if (resid_out) *resid_out = residual;
+    return it;
+}
+
+void so_kernel_eval(int kernel, int kfun, double h, const double* r, double* out, int64_t n) {
+    for (int64_t i = 0; i < n; i++) out[i] = kernel_eval(kernel, kfun, h, r[i]);
+}
+
+// Step programs for the CPU baseline: the time loops of the examples without I/O.
+// fields {x, v, Dv, rho, Drho, P, type}; params {kernel, m, h, two_nu, dt, c2, rho0, mu, gx, gy, gz}
+// returns wall seconds of the loop.
+double so_run_program(void* hnd, int program, const int32_t* F, int nf, const double* P, int np, int64_t nsteps) {
+    OSys& s = *(OSys*)hnd;
+    if (nf != 7 || np != 11) return -1.0;
+    const int32_t x = F[0], v = F[1], Dv = F[2], rho = F[3], Drho = F[4], Pr = F[5], ty = F[6];
+    const double kernel = P[0], m = P[1], h = P[2], two_nu = P[3], dt = P[4], c2 = P[5], rho0 = P[6], mu = P[7];
+    const int32_t f_bom[4] = {x, v, rho, Drho}, f_fp[3] = {rho, Drho, Pr}, f_if[6] = {x, v, Pr, rho, Dv, ty},
+                  f_mv[4] = {x, v, Dv, ty}, f_ac[3] = {v, Dv, ty};
+    const double p_bom[4] = {kernel, m, h, two_nu}, p_fp[4] = {dt, c2, rho0, 0.0}, p_if[5] = {kernel, m, h, mu, rho0},
+                 p_ac[4] = {0.5 * dt, P[8], P[9], P[10]};
+    auto t0 = std::chrono::steady_clock::now();
+    for (int64_t k = 0; k < nsteps; k++) {
+        if (program == SP_PROGRAM_WCSPH_3D) {  // collapse3d.jl:136-150
+            const double p_mv[1] = {dt};
+            apply_op(s, SP_OP_MOVE, f_mv, 4, p_mv, 1, 0);
+            create_cell_list(s);
+            apply_op(s, SP_OP_BALANCE_OF_MASS, f_bom, 4, p_bom, 4, 0);
+            apply_op(s, SP_OP_FIND_PRESSURE, f_fp, 3, p_fp, 4, 0);
+            apply_op(s, SP_OP_INTERNAL_FORCE, f_if, 6, p_if, 5, 0);
+            apply_op(s, SP_OP_ACCELERATE, f_ac, 3, p_ac, 4, 0);
+            apply_op(s, SP_OP_ACCELERATE, f_ac, 3, p_ac, 4, 0);
+        } else if (program == SP_PROGRAM_WCSPH_2D) {  // collapse_dry.jl:203-211
+            const double p_mv[1] = {0.5 * dt};
+            apply_op(s, SP_OP_ACCELERATE, f_ac, 3, p_ac, 4, 0);
+            apply_op(s, SP_OP_MOVE, f_mv, 4, p_mv, 1, 0);
+            create_cell_list(s);
+            apply_op(s, SP_OP_BALANCE_OF_MASS, f_bom, 4, p_bom, 4, 0);
+            apply_op(s, SP_OP_FIND_PRESSURE, f_fp, 3, p_fp, 4, 0);
+            apply_op(s, SP_OP_MOVE, f_mv, 4, p_mv, 1, 0);
+            create_cell_list(s);
+            apply_op(s, SP_OP_INTERNAL_FORCE, f_if, 6, p_if, 5, 0);
+            apply_op(s, SP_OP_ACCELERATE, f_ac, 3, p_ac, 4, 0);
+        } else
+            return -1.0;
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+}  // extern "C"

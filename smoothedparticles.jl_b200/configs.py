@@ -1,0 +1,383 @@
+"""The BASELINE configs as host programs over registered operators.
+
+Each ``Case`` restates one reference script: constants, particle struct, initial state
+(``make_system``) and the body of its time loop, calling ``apply`` / ``create_cell_list`` in the same
+order as the script.  A Case is backend-agnostic: ``case.make(ParticleSystem)`` builds it on the GPU,
+``case.make(OracleSystem)`` on the CPU oracle (tests only), and ``case.step(sys)`` advances either.
+
+  collapse_dry           examples/collapse_dry.jl            2-D WCSPH dam break
+  collapse3d             examples/collapse3d.jl              3-D WCSPH dam break (dr scalable to 10 M)
+  cavity_flow            examples/cavity_flow.jl             2-D lid-driven cavity
+  collapse_dry_implicit  examples/collapse_dry_implicit.jl   2-D ISPH, matrix-free pressure Poisson + CG
+  collision_2d           tests/test_collision_2d.jl          two colliding discs (the reference's own test)
+  lattice_box            synthetic S1 block of SURVEY §8(d)  jittered cubic lattice, all fluid
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional
+
+import numpy as np
+
+from . import abi, geometry as geo, operators as ops
+
+K = abi.K
+
+
+@dataclass
+class Case:
+    name: str
+    fields: Dict[str, int]
+    domain: geo.Box
+    h: float
+    init: Dict[str, np.ndarray]          # initial field arrays in reference order ("x" required)
+    step: Callable                        # step(sys): one pass of the script's time loop body
+    prologue: Callable = lambda sys: None  # what the script does once before the loop
+    consts: Dict[str, float] = field(default_factory=dict)
+    program: Optional[int] = None         # SP_PROGRAM_* equivalent of step(), if any
+    program_fields: tuple = ()
+    program_params: tuple = ()
+    dim: int = 3
+
+    @property
+    def n(self) -> int:
+        return len(self.init["x"])
+
+    def make(self, system_cls, **kw):
+        sys = system_cls(self.fields, self.domain, self.h, **kw)
+        sys.add_particles(**self.init)
+        return sys
+
+
+# --------------------------------------------------------------------------- collapse_dry.jl
+def collapse_dry(dr: float = 1.5e-2) -> Case:
+    """examples/collapse_dry.jl:44-102 (constants, make_system) and :194-211 (loop)."""
+    h = 3.0 * dr
+    rho0 = 1000.0
+    m = rho0 * dr ** 2
+    c = 50.0
+    g = (0.0, -7.0, 0.0)  # -7.0*VECY
+    mu = 8.4e-4
+    nu = 1.0e-6
+    wcw, wch, bh, bw = 1.0, 2.0, 3.0, 4.0
+    wall_width = 2.5 * dr
+    dt = 0.1 * h / c
+    grid = geo.Hexagrid(dr)
+    box = geo.Rectangle(0.0, 0.0, bw, bh)
+    fluid = geo.Rectangle(0.0, 0.0, wcw, wch)
+    walls = geo.BoundaryLayer(box, grid, wall_width)
+    walls = geo.Specification(walls, lambda X: X[:, 1] < bh)
+    domain = (box + walls).boundarybox()
+    xf = geo.covering(grid, fluid)
+    xw = geo.covering(grid, walls)
+    x = np.concatenate([xf, xw])
+    typ = np.concatenate([np.zeros(len(xf)), np.ones(len(xw))])
+    P = rho0 * g[1] * (x[:, 1] - wch)       # :98 hydrostatic pressure
+    rho = rho0 + P / c ** 2                 # :99
+    fields = {"v": 3, "Dv": 3, "rho": 1, "Drho": 1, "P": 1, "type": 1}
+    init = {"x": x, "rho": rho, "P": P, "type": typ}
+    o_bom = ops.balance_of_mass("wendland2", m, h, nu)
+    o_fp = ops.find_pressure(dt, c, rho0)
+    o_if = ops.internal_force("wendland2", m, h, mu, rho0)
+    o_mv = ops.move(0.5 * dt)
+    o_ac = ops.accelerate(0.5 * dt, g)
+
+    def prologue(sys):  # :200-201
+        sys.create_cell_list()
+        sys.apply(o_if)
+
+    def step(sys):  # :203-211
+        sys.apply(o_ac)
+        sys.apply(o_mv)
+        sys.create_cell_list()
+        sys.apply(o_bom)
+        sys.apply(o_fp)
+        sys.apply(o_mv)
+        sys.create_cell_list()
+        sys.apply(o_if)
+        sys.apply(o_ac)
+
+    return Case("collapse_dry", fields, domain, h, init, step, prologue,
+                consts=dict(dr=dr, h=h, rho0=rho0, m=m, c=c, mu=mu, nu=nu, dt=dt, g=g, width=wcw, height=wch),
+                program=K["SP_PROGRAM_WCSPH_2D"], program_fields=("x", "v", "Dv", "rho", "Drho", "P", "type"),
+                program_params=(float(K["SP_KERNEL_WENDLAND2"]), m, h, 2 * nu, dt, c * c, rho0, mu, *g), dim=2)
+
+
+# --------------------------------------------------------------------------- collapse3d.jl
+def collapse3d(dr: float = 5.0e-3) -> Case:
+    """examples/collapse3d.jl:28-84 and :134-151.
+
+    The shipped script does not run (``import`` instead of ``using``; ``rho`` undefined in
+    internal_force!, :101).  Adopted correction: the pressure term of
+    collapse_dry.jl:138, ``p.P/p.rho^2 + q.P/q.rho^2``, with rDwendland3.
+    """
+    h = 2.0 * dr
+    rho0 = 1000.0
+    m = rho0 * dr ** 3
+    c = 50.0
+    g = (0.0, 0.0, -9.8)  # -9.8*VECZ
+    mu = 8.4e-4
+    nu = 1.0e-4
+    wcw, wch, bh, bw, bd = 0.142, 0.293, 0.35, 0.584, 0.15
+    wall_width = 2.5 * dr
+    dt = 0.1 * h / c
+    grid = geo.CubicGrid(dr)
+    box = geo.Box(0.0, 0.0, 0.0, bw, bh, bd)
+    fluid = geo.Box(0.0, 0.0, 0.0, wcw, wch, bd)
+    walls = geo.BoundaryLayer(box, grid, wall_width)
+    walls = geo.Specification(walls, lambda X: X[:, 1] < bh)
+    domain = walls.boundarybox()
+    xf = geo.covering(grid, fluid)
+    xw = geo.covering(grid, walls)
+    x = np.concatenate([xf, xw])
+    typ = np.concatenate([np.zeros(len(xf)), np.ones(len(xw))])
+    fields = {"v": 3, "Dv": 3, "P": 1, "rho": 1, "Drho": 1, "type": 1}
+    init = {"x": x, "rho": np.full(len(x), rho0), "type": typ}
+    o_bom = ops.balance_of_mass("wendland3", m, h, nu)
+    o_fp = ops.find_pressure(dt, c, rho0)
+    o_if = ops.internal_force("wendland3", m, h, mu, rho0)
+    o_mv = ops.move(dt)
+    o_ac = ops.accelerate(0.5 * dt, g)
+
+    def step(sys):  # :136-150
+        sys.apply(o_mv)
+        sys.create_cell_list()
+        sys.apply(o_bom)
+        sys.apply(o_fp)
+        sys.apply(o_if)
+        sys.apply(o_ac)
+        sys.apply(o_ac)
+
+    return Case("collapse3d", fields, domain, h, init, step,
+                consts=dict(dr=dr, h=h, rho0=rho0, m=m, c=c, mu=mu, nu=nu, dt=dt, g=g),
+                program=K["SP_PROGRAM_WCSPH_3D"], program_fields=("x", "v", "Dv", "rho", "Drho", "P", "type"),
+                program_params=(float(K["SP_KERNEL_WENDLAND3"]), m, h, 2 * nu, dt, c * c, rho0, mu, *g), dim=3)
+
+
+def collapse3d_dr_for(n_target: float) -> float:
+    """dr that scales examples/collapse3d.jl to about n_target particles (walls scale with area)."""
+    # N(dr) ~ V_fluid/dr^3 + A_wall*2.5/dr^2 ; solve by bisection on the analytic estimate
+    vf = 0.142 * 0.293 * 0.15
+    aw = 2 * (0.584 * 0.35 + 0.35 * 0.15) + 0.584 * 0.15  # 4 side walls + floor, no lid
+    lo, hi = 1e-4, 5e-2
+    for _ in range(80):
+        mid = 0.5 * (lo + hi)
+        n = vf / mid ** 3 + aw * 3.0 / mid ** 2
+        if n > n_target:
+            lo = mid
+        else:
+            hi = mid
+    return 0.5 * (lo + hi)
+
+
+# --------------------------------------------------------------------------- cavity_flow.jl
+def cavity_flow(N: int = 100, Re: int = 100) -> Case:
+    """examples/cavity_flow.jl:28-86 (constants, make_system) and :137-151 (loop)."""
+    llid = 1.0
+    rho0 = 1.0
+    vlid = 1.0
+    dr = llid / N
+    h = 3.0 * dr
+    m = rho0 * dr ** 2
+    c = 20 * vlid
+    P0 = 5.0
+    wwall = h
+    dt = 0.1 * h / c
+    grid = geo.Hexagrid(dr)
+    box = geo.Rectangle(0.0, 0.0, llid, llid)
+    wall = geo.BoundaryLayer(box, grid, wwall)
+    domain = (box + wall).boundarybox()
+    lid = geo.Specification(wall, lambda X: X[:, 1] > llid)
+    wall2 = geo.Specification(wall, lambda X: X[:, 1] <= llid)
+    xf, xl, xw = geo.covering(grid, box), geo.covering(grid, lid), geo.covering(grid, wall2)
+    x = np.concatenate([xf, xl, xw])
+    typ = np.concatenate([np.zeros(len(xf)), np.full(len(xl), 2.0), np.ones(len(xw))])
+    fields = {"v": 3, "Dv": 3, "rho": 1, "Drho": 1, "P": 1, "type": 1}
+    init = {"x": x, "rho": np.full(len(x), rho0), "type": typ}
+    o_bom = ops.balance_of_mass("wendland2", m, h, 0.0)
+    o_fp = ops.find_pressure(dt, c, rho0, P0)
+    o_if = ops.internal_force_cavity(m, h, Re, vlid, ylid=1.0, lid_type=2.0)
+    o_mv = ops.move(0.5 * dt)
+    o_ac = ops.accelerate(0.5 * dt)
+
+    def prologue(sys):  # :82-84
+        sys.create_cell_list()
+        sys.apply(o_fp)
+        sys.apply(o_if)
+
+    def step(sys):  # :138-150
+        sys.apply(o_ac)
+        sys.apply(o_mv)
+        sys.create_cell_list()
+        sys.apply(o_bom)
+        sys.apply(o_fp)
+        sys.apply(o_mv)
+        sys.create_cell_list()
+        sys.apply(o_if)
+        sys.apply(o_ac)
+
+    return Case("cavity_flow", fields, domain, h, init, step, prologue,
+                consts=dict(dr=dr, h=h, rho0=rho0, m=m, c=c, dt=dt, Re=Re, P0=P0), dim=2)
+
+
+# --------------------------------------------------------------------------- collapse_dry_implicit.jl
+def collapse_dry_implicit(dr: float = 1.0e-2) -> Case:
+    """examples/collapse_dry_implicit.jl:47-114 (constants, make_system) and :218-233 (loop).
+    The serial assemble_matrix + cg of :223-227 becomes the matrix-free CG of sp_poisson_cg."""
+    dim = 2
+    h = 2.8 * dr
+    rho = 1000.0
+    g = (0.0, -9.8, 0.0)
+    mu = 8.4e-4
+    m = dr ** dim * rho
+    C_free = 10.0
+    v_char = 5.0
+    wcw, wch, bh, bw = 1.0, 2.0, 3.0, 4.0
+    nlayers = 3.5
+    dt = 0.1 * h / v_char
+    grid = geo.Hexagrid(dr)
+    box = geo.Rectangle(0.0, 0.0, bw, bh)
+    fluid = geo.Rectangle(0.0, 0.0, wcw, wch)
+    walls = geo.Specification(geo.BoundaryLayer(box, grid, 1.2 * dr), lambda X: X[:, 1] < bh)
+    dummy = geo.Specification(geo.BoundaryLayer(box, grid, nlayers * dr) - walls, lambda X: X[:, 1] < bh)
+    domain = (fluid + dummy + walls).boundarybox()
+    xf, xw, xd = geo.covering(grid, fluid), geo.covering(grid, walls), geo.covering(grid, dummy)
+    x = np.concatenate([xf, xw, xd])
+    typ = np.concatenate([np.zeros(len(xf)), np.ones(len(xw)), np.full(len(xd), 2.0)])
+    fields = {"v": 3, "Dv": 3, "P": 1, "div": 1, "L": 1, "lambda": 1, "type": 1, "b": 1}
+    init = {"x": x, "type": typ}
+    o_init = ops.isph_initialize(dt, g)
+    o_visc = ops.isph_viscous_force("spline23", m, h, mu, rho)
+    o_dll = ops.isph_div_L_lambda("spline23", m, h, rho, dim)
+    o_b = ops.isph_projection_vector(h, dt)
+    A = ops.isph_projection_matrix("spline23", m, h, rho, C_free)
+    o_if = ops.isph_internal_force("spline23", m, h, rho)
+    o_ac = ops.isph_accelerate(dt)
+
+    def prologue(sys):  # :113
+        sys.create_cell_list()
+
+    def step(sys):  # :218-233
+        sys.apply(o_init)
+        sys.create_cell_list()
+        sys.apply(o_visc)
+        sys.apply(o_dll)
+        sys.apply(o_b)
+        sys.poisson_cg(A, "b", "P")
+        sys.apply(o_if)
+        sys.apply(o_ac)
+
+    case = Case("collapse_dry_implicit", fields, domain, h, init, step, prologue,
+                consts=dict(dr=dr, h=h, rho=rho, m=m, dt=dt, g=g, C_free=C_free, mu=mu), dim=2)
+    case.ops = dict(init=o_init, visc=o_visc, dll=o_dll, b=o_b, A=A, force=o_if, acc=o_ac)
+    return case
+
+
+# --------------------------------------------------------------------------- test_collision_2d.jl
+def collision_2d() -> Case:
+    """tests/test_collision_2d.jl:14-59 (constants, make_system), :104-126 (verlet_step!, init)."""
+    dr = 2.0e-2
+    h = 2.4 * dr
+    rho0 = 1000.0
+    m = rho0 * dr ** 2
+    c = 20.0
+    circ_rad, dom_len, dom_wid, deltaX, deltaY = 0.4, 20.0, 20.0, 1.0, 0.2
+    dt = 0.1 * h / c
+    grid = geo.Squaregrid(dr)
+    circ1 = geo.Circle(-0.5 * deltaX, -0.5 * deltaY, circ_rad)
+    circ2 = geo.Circle(0.5 * deltaX, 0.5 * deltaY, circ_rad)
+    domain = geo.Rectangle(-0.5 * dom_len, -0.5 * dom_wid, 0.5 * dom_len, 0.5 * dom_wid)
+    x1, x2 = geo.covering(grid, circ1), geo.covering(grid, circ2)
+    x = np.concatenate([x1, x2])
+    v = np.zeros_like(x)
+    v[: len(x1), 0] = 1.0
+    v[len(x1):, 0] = -1.0
+    fields = {"v": 3, "a": 3, "P": 1, "rho": 1, "rho0": 1}
+    init = {"x": x, "v": v}
+    o_rho = ops.density_sum("wendland2", m, h, out="rho")
+    o_rho0 = ops.density_sum("wendland2", m, h, out="rho0")
+    o_p = ops.pressure_from_rho(c)
+    o_f = ops.internal_force_sym("wendland2", m, h, rho0)
+    o_ra = ops.fill("a", 0.0)
+    o_rr = ops.fill("rho", 0.0)
+    o_mv = ops.advect(dt)
+    o_ac = ops.kick(0.5 * dt)
+
+    def prologue(sys):  # :121-126
+        sys.create_cell_list()
+        sys.apply(o_rho0, self_=True)
+        sys.apply(o_rho, self_=True)
+        sys.apply(o_p)
+        sys.apply(o_f)
+
+    def step(sys):  # verlet_step! :104-114
+        sys.apply(o_ac)
+        sys.apply(o_mv)
+        sys.create_cell_list()
+        sys.apply(o_rr)
+        sys.apply(o_rho, self_=True)
+        sys.apply(o_p)
+        sys.apply(o_ra)
+        sys.apply(o_f)
+        sys.apply(o_ac)
+
+    return Case("collision_2d", fields, domain, h, init, step, prologue,
+                consts=dict(dr=dr, h=h, rho0=rho0, m=m, c=c, dt=dt, t_end=1.0), dim=2)
+
+
+# --------------------------------------------------------------------------- synthetic S1 block
+def lattice_box(n_side, jitter: float = 0.1, seed: int = 1234, shuffle: bool = True, dr: float = 1.0) -> Case:
+    """n_side^3 (or (nx,ny,nz)) cubic lattice, h = 2 dr, positions jittered by
+    U(-jitter*dr, jitter*dr) from Philox(seed), v ~ U(-0.01c, 0.01c) from Philox(seed+1), all fluid;
+    domain = lattice bounds +- h; initial particle order shuffled with Philox(99) so the sort does work.
+    The step is the collapse3d loop."""
+    if isinstance(n_side, int):
+        n_side = (n_side, n_side, n_side)
+    nx, ny, nz = n_side
+    h = 2.0 * dr
+    rho0 = 1000.0
+    m = rho0 * dr ** 3
+    c = 50.0
+    g = (0.0, 0.0, -9.8)
+    mu = 8.4e-4
+    nu = 1.0e-4
+    dt = 0.1 * h / c
+    I, J, Kk = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    x = np.empty((nx * ny * nz, 3))
+    x[:, 0] = I.ravel() * dr
+    x[:, 1] = J.ravel() * dr
+    x[:, 2] = Kk.ravel() * dr
+    n = len(x)
+    if jitter:
+        rng = np.random.Generator(np.random.Philox(seed))
+        x += rng.uniform(-jitter * dr, jitter * dr, size=(n, 3))
+    rng = np.random.Generator(np.random.Philox(seed + 1))
+    v = rng.uniform(-0.01 * c, 0.01 * c, size=(n, 3))
+    if shuffle:
+        perm = np.random.Generator(np.random.Philox(99)).permutation(n)
+        x, v = x[perm], v[perm]
+    domain = geo.Box(-h, -h, -h, (nx - 1) * dr + h, (ny - 1) * dr + h, (nz - 1) * dr + h)
+    fields = {"v": 3, "Dv": 3, "P": 1, "rho": 1, "Drho": 1, "type": 1}
+    init = {"x": x, "v": v, "rho": np.full(n, rho0), "type": np.zeros(n)}
+    o_bom = ops.balance_of_mass("wendland3", m, h, nu)
+    o_fp = ops.find_pressure(dt, c, rho0)
+    o_if = ops.internal_force("wendland3", m, h, mu, rho0)
+    o_mv = ops.move(dt)
+    o_ac = ops.accelerate(0.5 * dt, g)
+
+    def step(sys):
+        sys.apply(o_mv)
+        sys.create_cell_list()
+        sys.apply(o_bom)
+        sys.apply(o_fp)
+        sys.apply(o_if)
+        sys.apply(o_ac)
+        sys.apply(o_ac)
+
+    case = Case(f"lattice_box_{nx}x{ny}x{nz}", fields, domain, h, init, step,
+                consts=dict(dr=dr, h=h, rho0=rho0, m=m, c=c, mu=mu, nu=nu, dt=dt, g=g),
+                program=K["SP_PROGRAM_WCSPH_3D"], program_fields=("x", "v", "Dv", "rho", "Drho", "P", "type"),
+                program_params=(float(K["SP_KERNEL_WENDLAND3"]), m, h, 2 * nu, dt, c * c, rho0, mu, *g), dim=3)
+    case.ops = dict(bom=o_bom, fp=o_fp, force=o_if, move=o_mv, acc=o_ac)
+    return case

@@ -1,0 +1,274 @@
+// sp_cells.cu — create_cell_list! on the device (reference src/core.jl:51-90, src/structs.jl:97-106).
+//
+// Reference semantics reproduced bit-exactly:
+//   * particles outside the closed domain box (or with NaN coordinates) are removed with the
+//     swap-with-tail rule of core.jl:72-81 — victims in descending index order, the i-th victim slot
+//     receives the CURRENT particles[end+1-i] — which fixes the post-removal numbering;
+//   * key = find_key(x) with true division and floor;
+//   * every cell lists its members in DESCENDING particle index (add_index!, core.jl:26-41).
+// Device algorithm: one pass computes keys and a per-cell arrival offset with warp-aggregated atomics,
+// an exclusive scan of the per-cell counts gives cell_start, a scatter groups slots by cell, a rank
+// pass orders each cell by descending reference index (deterministic whatever the atomic order was),
+// and one gather pass permutes every SoA plane so that a cell's particles are contiguous in HBM.
+#include <algorithm>
+
+#include "sp_internal.cuh"
+
+// ------------------------------------------------------------------ exclusive scan (int32)
+// 256 threads x 4 items; block sums scanned recursively.
+#define SCAN_B 256
+#define SCAN_ITEMS 4
+#define SCAN_TILE (SCAN_B * SCAN_ITEMS)
+
+__global__ void k_scan_tile(int* data, long long len, int* block_sums) {
+    __shared__ int warp_tot[SCAN_B / 32];
+    const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int sum = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        v[i] = (base + i < len) ? data[base + i] : 0;
+        sum += v[i];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = (lane < SCAN_B / 32) ? warp_tot[lane] : 0;
+        int wi = w;
+#pragma unroll
+        for (int d = 1; d < SCAN_B / 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += t;
+        }
+        if (lane < SCAN_B / 32) warp_tot[lane] = wi - w;  // exclusive warp offsets
+        if (lane == SCAN_B / 32 - 1 && block_sums) block_sums[blockIdx.x] = wi;
+    }
+    __syncthreads();
+    int run = warp_tot[warp] + incl - sum;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        if (base + i < len) data[base + i] = run;
+        run += v[i];
+    }
+}
+__global__ void k_scan_add(int* data, long long len, const int* block_offsets) {
+    const long long i = (long long)blockIdx.x * SCAN_TILE + threadIdx.x;
+    const int off = block_offsets[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        long long j = i + (long long)k * SCAN_B;
+        if (j < len) data[j] += off;
+    }
+}
+
+static int scan_rec(sp_system* s, int* data, long long len, int* tmp, long long tmp_len) {
+    const long long nb = (len + SCAN_TILE - 1) / SCAN_TILE;
+    if (nb <= 1) {
+        SP_LAUNCH(s, k_scan_tile, 1, SCAN_B, 0, data, len, (int*)nullptr);
+        return SP_OK;
+    }
+    if (nb > tmp_len) return sp_fail(s, SP_ERR_STATE, "scan scratch too small");
+    SP_LAUNCH(s, k_scan_tile, (unsigned)nb, SCAN_B, 0, data, len, tmp);
+    int rc = scan_rec(s, tmp, nb, tmp + nb, tmp_len - nb);
+    if (rc) return rc;
+    SP_LAUNCH(s, k_scan_add, (unsigned)nb, SCAN_B, 0, data, len, tmp);
+    return SP_OK;
+}
+
+int sp_exclusive_scan_i32(sp_system* s, int* data, long long len) {
+    if (len <= 0) return SP_OK;
+    long long need = len / SCAN_TILE + 2048;
+    if (need > s->scan_tmp_len) {
+        if (s->scan_tmp) SP_CUDA(s, cudaFree(s->scan_tmp));
+        s->scan_tmp = nullptr;
+        SP_CUDA(s, cudaMalloc(&s->scan_tmp, (size_t)need * sizeof(int)));
+        s->scan_tmp_len = need;
+    }
+    return scan_rec(s, data, len, s->scan_tmp, s->scan_tmp_len);
+}
+
+// ------------------------------------------------------------------ cell list kernels
+// Pass 1: domain test (core.jl:64-69), key (structs.jl:97-106), per-cell count and arrival offset.
+// Particles outside the domain get the trash key key_max+1 and are counted in counters[0].
+__global__ void k_cull_key(SpGrid g, const double* __restrict__ x, long long cap, long long n, int* __restrict__ key,
+                           int* __restrict__ off, int* __restrict__ cell_count, int* __restrict__ counters) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int k = -1 - lane;  // inactive lanes: unique negative keys, no atomic
+    if (s < n) {
+        double px = x[s], py = x[cap + s], pz = x[2 * cap + s];
+        if (sp_inside(g, px, py, pz)) k = (int)sp_find_key(g, px, py, pz);
+        else k = (int)g.key_max + 1;
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, k);
+    const int leader = __ffs(peers) - 1;
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    int base = 0;
+    if (lane == leader && k >= 0) {
+        base = atomicAdd(&cell_count[k], __popc(peers));
+        if (k == (int)g.key_max + 1) atomicAdd(&counters[0], __popc(peers));
+    }
+    base = __shfl_sync(peers, base, leader);
+    if (s < n) {
+        key[s] = k;
+        off[s] = base + rank;
+    }
+}
+
+// ---- removal renumbering (rare path), all arrays indexed by reference index r
+__global__ void k_mark_victims(const int* key, const int* ref, int trash, int* V, int* Vscan, long long n) {
+    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) {
+        int v = key[s] == trash;
+        V[ref[s]] = v;
+        Vscan[ref[s]] = v;
+    }
+}
+// For a hole r (victim with r < n_new): i0 = number of victims with a larger index; the particle that lands
+// in r is the one at tail position t = N-1-i0, following the chain while t is itself a victim
+// (its content was overwritten earlier by the same rule).  Verified against the literal loop in
+// tests/test_removal_rule.py.
+__global__ void k_chain(const int* V, const int* Vexcl, int n_out, long long N, long long n_new, int* newref) {
+    long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_new || !V[r]) return;
+    long long t = N - 1 - (n_out - (Vexcl[r] + 1));
+    while (V[t]) t = N - 1 - (n_out - (Vexcl[t] + 1));
+    newref[t] = (int)r;
+}
+__global__ void k_apply_newref(const int* key, int trash, int* ref, const int* newref, long long n_new, long long n) {
+    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n && key[s] != trash && ref[s] >= n_new) ref[s] = newref[ref[s]];
+}
+
+__global__ void k_scatter(const int* __restrict__ key, const int* __restrict__ off, const int* __restrict__ cell_start,
+                          int* __restrict__ member, long long n) {
+    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) member[cell_start[key[s]] + off[s]] = (int)s;
+}
+
+// Order every cell by descending reference index: perm[cell_start + rank] = slot.
+__global__ void k_rank(const int* __restrict__ key, const int* __restrict__ ref, const int* __restrict__ cell_start,
+                       const int* __restrict__ member, int* __restrict__ perm, long long n_keep) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_keep) return;
+    const int s = member[t];
+    const int k = key[s];
+    const int mine = ref[s];
+    const int b = cell_start[k], e = cell_start[k + 1];
+    int rank = 0;
+    for (int u = b; u < e; u++) rank += (ref[member[u]] > mine);
+    perm[b + rank] = s;
+}
+
+#define PERM_PLANES 40
+struct PlaneTable {
+    const double* in[PERM_PLANES];
+    double* out[PERM_PLANES];
+    int count;
+};
+__global__ void k_permute(PlaneTable tab, const int* __restrict__ perm, const int* __restrict__ ref_in,
+                          int* __restrict__ ref_out, const int* __restrict__ key_in, int* __restrict__ key_out,
+                          long long n) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int p = perm[t];
+    if (ref_out) {
+        ref_out[t] = ref_in[p];
+        key_out[t] = key_in[p];
+    }
+#pragma unroll 4
+    for (int c = 0; c < tab.count; c++) tab.out[c][t] = tab.in[c][p];
+}
+
+int sp_permute_all(sp_system* s, long long n_keep) {
+    const int B = 256;
+    PlaneTable tab;
+    tab.count = 0;
+    bool first = true;
+    auto flush = [&]() -> int {
+        if (tab.count == 0 && !first) return SP_OK;
+        SP_LAUNCH(s, k_permute, sp_blocks(n_keep, B), B, 0, tab, s->perm, s->ref, first ? s->ref_alt : (int*)nullptr,
+                  s->key, s->key_alt, n_keep);
+        first = false;
+        tab.count = 0;
+        return SP_OK;
+    };
+    for (SpField& f : s->fields)
+        for (int c = 0; c < f.ncomp && !f.transient; c++) {
+            tab.in[tab.count] = f.d + (size_t)c * s->cap;
+            tab.out[tab.count] = f.alt + (size_t)c * s->cap;
+            if (++tab.count == PERM_PLANES) {
+                int rc = flush();
+                if (rc) return rc;
+            }
+        }
+    int rc = flush();
+    if (rc) return rc;
+    for (SpField& f : s->fields)
+        if (!f.transient) std::swap(f.d, f.alt);
+    std::swap(s->ref, s->ref_alt);
+    std::swap(s->key, s->key_alt);
+    return SP_OK;
+}
+
+int sp_build_cells(sp_system* s) {
+    const SpGrid& g = s->g;
+    const int B = 256;
+    const long long N = s->n;
+    const long long K = g.key_max;
+    SP_CUDA(s, cudaMemsetAsync(s->cell_start, 0, (size_t)(K + 3) * sizeof(int), s->stream));
+    SP_CUDA(s, cudaMemsetAsync(s->counters, 0, sizeof(int), s->stream));
+    if (N == 0) {
+        s->have_cells = true;
+        return SP_OK;
+    }
+    int* off = s->perm;  // arrival offsets live in perm until the scatter has consumed them
+    SP_LAUNCH(s, k_cull_key, sp_blocks(N, B), B, 0, g, s->fields[0].d, s->cap, N, s->key, off, s->cell_start, s->counters);
+    SP_CUDA(s, cudaMemcpyAsync(s->h_counters, s->counters, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    SP_CUDA(s, cudaStreamSynchronize(s->stream));
+    const int n_out = s->h_counters[0];
+    const long long n_new = N - n_out;
+    if (n_out > 0) {
+        // swap-with-tail renumbering of the reference indices (core.jl:72-81)
+        int* V = s->flags;
+        int* Vscan = s->key_alt;
+        int* newref = s->ref_alt;
+        SP_LAUNCH(s, k_mark_victims, sp_blocks(N, B), B, 0, s->key, s->ref, (int)K + 1, V, Vscan, N);
+        int rc = sp_exclusive_scan_i32(s, Vscan, N);
+        if (rc) return rc;
+        if (n_new > 0) {
+            SP_LAUNCH(s, k_chain, sp_blocks(n_new, B), B, 0, V, Vscan, n_out, N, n_new, newref);
+            SP_LAUNCH(s, k_apply_newref, sp_blocks(N, B), B, 0, s->key, (int)K + 1, s->ref, newref, n_new, N);
+        }
+        s->n_removed += n_out;
+    }
+    int rc = sp_exclusive_scan_i32(s, s->cell_start, K + 3);
+    if (rc) return rc;
+    SP_LAUNCH(s, k_scatter, sp_blocks(N, B), B, 0, s->key, off, s->cell_start, s->tmp_slot, N);
+    if (n_new > 0) {
+        SP_LAUNCH(s, k_rank, sp_blocks(n_new, B), B, 0, s->key, s->ref, s->cell_start, s->tmp_slot, s->perm, n_new);
+        rc = sp_permute_all(s, n_new);
+        if (rc) return rc;
+    }
+    s->n = n_new;
+    s->identity_order = false;
+    s->have_cells = true;
+    return SP_OK;
+}
+
+extern "C" int32_t sp_create_cell_list(sp_system* s) {
+    if (!s) return SP_ERR_INVALID;
+    SP_CUDA(s, cudaSetDevice(s->device));
+    if (s->slab) return sp_fail(s, SP_ERR_STATE, "slab system: use sp_slab_create_cell_list");
+    int rc = sp_time_begin(s);
+    if (rc) return rc;
+    if ((rc = sp_build_cells(s))) return rc;
+    return sp_time_end(s);
+}

@@ -1,0 +1,141 @@
+// sp_internal.cuh — host-side system state and shared device helpers of libsp_b200.so.
+//
+// HBM layout (all Float64 unless stated; capacity `cap` is a multiple of 128 so every plane is
+// 1 KiB aligned):
+//   field f with ncomp components: planes  f.d[c*cap + s], s = device slot (true SoA)
+//   ref[s]   int32  reference index (0-based position in the reference's sys.particles) of slot s
+//   key[s]   int32  1-based linear cell key of slot s at the last create_cell_list
+//   cell_start[k] int32, k = 1..key_max+1: cell k owns slots [cell_start[k], cell_start[k+1]);
+//            k = key_max+1 is the "trash" cell of particles outside the domain (dropped by the build)
+// After sp_create_cell_list the slots are sorted by (key ascending, ref descending): the slot order
+// inside a cell IS the reference's descending-index order of Cell.entries (src/core.jl:26-41).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/sp_b200.h"
+
+#define SP_MAX_FIELDS 64
+
+struct SpField {
+    std::string name;
+    int ncomp = 0;
+    double* d = nullptr;    // current planes
+    double* alt = nullptr;  // permutation target (swapped with d by the cell-list build)
+    bool transient = false;  // solver scratch: contents need not survive a cell-list rebuild
+};
+
+// Parameters every device kernel needs about the cell grid (passed by value).
+struct SpGrid {
+    double h;       // neighbour radius
+    double T2;      // largest double t with sqrt_rn(t) <= h:  (r > h) <=> (d2 > T2)  for r = sqrt_rn(d2)
+    double lo[3], hi[3];
+    long long phase[3];  // key_phase
+    long long lim[3];    // key_lim
+    long long key_max;
+    int dim;  // 2 iff key_lim[2] == 1 (src/structs.jl:70)
+};
+
+struct SlabState;  // sp_slab.cu
+
+struct sp_system {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    SpGrid g{};
+    int n_key_diff = 0;
+    long long key_diff[27]{};
+
+    long long n = 0;    // current particle count (owned + ghosts on a slab system)
+    long long cap = 0;  // plane stride
+    std::vector<SpField> fields;
+    int *ref = nullptr, *ref_alt = nullptr;
+    int *key = nullptr, *key_alt = nullptr;
+    int* cell_start = nullptr;  // key_max + 3 ints
+    int* cell_fill = nullptr;   // key_max + 3 ints (scatter cursors)
+    int* perm = nullptr;        // cap ints
+    int* tmp_slot = nullptr;    // cap ints
+    int* flags = nullptr;       // cap ints (cull flags / scratch)
+    int* scan_tmp = nullptr;    // block sums for the scan
+    long long scan_tmp_len = 0;
+    int* counters = nullptr;    // small device counters
+    int* h_counters = nullptr;  // pinned mirror
+    double* stage = nullptr;    // upload/download staging + reduction scratch
+    long long stage_len = 0;    // in doubles
+    double* dscal = nullptr;    // CG scalars + dot partials (3*1024 + 16 doubles)
+    double* h_scal = nullptr;   // pinned mirror of a few scalars
+
+    bool have_cells = false;
+    bool identity_order = true;  // slot s holds reference particle s
+    long long n_removed = 0;
+    long long launches = 0;
+    float last_ms = 0.f;
+    std::string err;
+    SlabState* slab = nullptr;
+};
+
+extern thread_local std::string g_sp_create_error;
+
+int sp_fail(sp_system* s, int code, const std::string& msg);
+int sp_fail_cuda(sp_system* s, cudaError_t e, const char* what, const char* file, int line);
+
+#define SP_CUDA(sys, call)                                                             \
+    do {                                                                               \
+        cudaError_t _e = (call);                                                       \
+        if (_e != cudaSuccess) return sp_fail_cuda((sys), _e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+// launch + count + check
+#define SP_LAUNCH(sys, kernel, grid, block, smem, ...)                                       \
+    do {                                                                                     \
+        kernel<<<(grid), (block), (smem), (sys)->stream>>>(__VA_ARGS__);                     \
+        (sys)->launches++;                                                                   \
+        cudaError_t _e = cudaGetLastError();                                                 \
+        if (_e != cudaSuccess) return sp_fail_cuda((sys), _e, #kernel, __FILE__, __LINE__);  \
+    } while (0)
+
+static inline unsigned sp_blocks(long long n, int block) { return (unsigned)((n + block - 1) / block); }
+
+// grow-only device scratch
+int sp_ensure_stage(sp_system* s, long long doubles);
+int sp_ensure_capacity(sp_system* s, long long n);
+// exclusive scan of `len` ints in place (device), sp_cells.cu
+int sp_exclusive_scan_i32(sp_system* s, int* data, long long len);
+// validate a field binding
+int sp_check_fields(sp_system* s, const int32_t* fields, int nfields, const int* ncomps, int nexpected);
+
+// RAII-less timing helpers
+int sp_time_begin(sp_system* s);
+int sp_time_end(sp_system* s);
+void sp_slab_free(sp_system* s);  // sp_slab.cu
+
+// ------------------------------------------------------------------ device helpers
+#ifdef __CUDACC__
+
+// find_key, src/structs.jl:97-106: true IEEE division and floor; 1-based linear key.
+// Returns -1 when a coordinate is NaN/Inf (Int64(floor(.)) would throw).
+__device__ __forceinline__ long long sp_find_key(const SpGrid& g, double x, double y, double z) {
+    double q0 = floor(__ddiv_rn(x, g.h)), q1 = floor(__ddiv_rn(y, g.h)), q2 = floor(__ddiv_rn(z, g.h));
+    if (!(fabs(q0) < 9.0e18) || !(fabs(q1) < 9.0e18) || !(fabs(q2) < 9.0e18)) return -1;
+    long long i = 1 + (long long)q0 - g.phase[0];
+    long long j = 1 + (long long)q1 - g.phase[1];
+    long long k = 1 + (long long)q2 - g.phase[2];
+    return i + g.lim[0] * (j - 1) + g.lim[0] * g.lim[1] * (k - 1);
+}
+
+// is_inside(x, Box), src/geometry.jl:24-30 (closed; NaN -> false)
+__device__ __forceinline__ bool sp_inside(const SpGrid& g, double x, double y, double z) {
+    return g.lo[0] <= x && x <= g.hi[0] && g.lo[1] <= y && y <= g.hi[1] && g.lo[2] <= z && z <= g.hi[2];
+}
+
+// squared distance exactly as dist() rounds it before the sqrt: (dx*dx + dy*dy) + dz*dz, no FMA
+// (src/core.jl:8-10, src/algebra.jl:49-60).
+__device__ __forceinline__ double sp_d2(double dx, double dy, double dz) {
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+#endif

@@ -1,0 +1,456 @@
+// sp_ops.cuh — the registered operators: device restatements of the per-pair / per-particle closures
+// the reference's examples pass to apply!.  Each struct cites its source.
+//
+// Pair operator interface used by the sweep kernels (sp_sweep.cu):
+//   Params            POD block: field plane pointers + folded constants
+//   PS                per-p state loaded once (registers)
+//   Acc               accumulators; init() loads the CURRENT value of the p-owned output so the
+//                     accumulation order is the reference's:  ((old + t1) + t2) + ...
+//   active(P,i)       type guard of the closure (skips the whole neighbour loop)
+//   pair(P,p,j,dx,dy,dz,r,acc)   one accepted pair; q fields are read at slot j
+//   self(P,p,acc)     the (p,p,0.0) term of apply!(...; self=true)  (core.jl:155-157)
+//   store(P,i,p,acc)  write back p-owned outputs
+#pragma once
+#include "sp_kernels.cuh"
+
+struct RV3 {
+    const double *x, *y, *z;
+};
+struct WV3 {
+    double *x, *y, *z;
+};
+
+// ---------------------------------------------------------------- WCSPH
+// balance_of_mass!  collapse_dry.jl:112-115, collapse3d.jl:87-90, cavity_flow.jl:92-94 (two_nu = 0)
+template <class K>
+struct OpBalanceOfMass {
+    struct Params {
+        RV3 v;
+        const double* rho;
+        double* Drho;
+        double m, two_nu;
+        SpKC kc;
+    };
+    struct PS {
+        double vx, vy, vz, rho;
+    };
+    struct Acc {
+        double d;
+    };
+    __device__ static __forceinline__ bool active(const Params&, int) { return true; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
+        p.vx = P.v.x[i]; p.vy = P.v.y[i]; p.vz = P.v.z[i];
+        p.rho = P.rho[i];
+        a.d = P.Drho[i];
+    }
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, int j, double dx, double dy, double dz,
+                                                double r, Acc& a) {
+        double ker = P.m * K::rD(P.kc, r);
+        double dvx = p.vx - P.v.x[j], dvy = p.vy - P.v.y[j], dvz = p.vz - P.v.z[j];
+        a.d += ker * ((dx * dvx + dy * dvy + dz * dvz) + P.two_nu * (p.rho - P.rho[j]));
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) { P.Drho[i] = a.d; }
+};
+
+// internal_force!  collapse_dry.jl:135-141 (3-D: collapse3d.jl:98-104 with the same formula)
+template <class K>
+struct OpInternalForce {
+    struct Params {
+        RV3 v;
+        const double *P, *rho, *type;
+        WV3 Dv;
+        double m, visc;  // visc = 2*mu/rho0^2
+        SpKC kc;
+    };
+    struct PS {
+        double vx, vy, vz, pr;  // pr = P_p/rho_p^2
+    };
+    struct Acc {
+        double x, y, z;
+    };
+    __device__ static __forceinline__ bool active(const Params& P, int i) { return P.type[i] == 0.0; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
+        p.vx = P.v.x[i]; p.vy = P.v.y[i]; p.vz = P.v.z[i];
+        double rho = P.rho[i];
+        p.pr = P.P[i] / (rho * rho);
+        a.x = P.Dv.x[i]; a.y = P.Dv.y[i]; a.z = P.Dv.z[i];
+    }
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, int j, double dx, double dy, double dz,
+                                                double r, Acc& a) {
+        double ker = P.m * K::rD(P.kc, r);
+        double rq = P.rho[j];
+        double c = -ker * (p.pr + P.P[j] / (rq * rq));
+        double b = ker * P.visc;
+        a.x += c * dx; a.y += c * dy; a.z += c * dz;
+        a.x += b * (p.vx - P.v.x[j]); a.y += b * (p.vy - P.v.y[j]); a.z += b * (p.vz - P.v.z[j]);
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) {
+        P.Dv.x[i] = a.x; P.Dv.y[i] = a.y; P.Dv.z[i] = a.z;
+    }
+};
+
+// internal_force!  cavity_flow.jl:102-114 (rDwendland2; lid extrapolation; Monaghan viscosity)
+template <class K>
+struct OpInternalForceCavity {
+    struct Params {
+        RV3 v;
+        const double *P, *rho, *type;
+        WV3 Dv;
+        double m, Re, vlid, ylid, lid, tenth_h, eps;  // eps = 0.01*h^2
+        SpKC kc;
+    };
+    struct PS {
+        double vx, vy, vz, pr, rho, ay;  // ay = 0.1*h + |p.x[2] - ylid|
+    };
+    struct Acc {
+        double x, y, z;
+    };
+    __device__ static __forceinline__ bool active(const Params&, int) { return true; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double yi, double, PS& p, Acc& a) {
+        p.vx = P.v.x[i]; p.vy = P.v.y[i]; p.vz = P.v.z[i];
+        p.rho = P.rho[i];
+        p.pr = P.P[i] / (p.rho * p.rho);
+        p.ay = P.tenth_h + fabs(yi - P.ylid);
+        a.x = P.Dv.x[i]; a.y = P.Dv.y[i]; a.z = P.Dv.z[i];
+    }
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, int j, double dx, double dy, double dz,
+                                                double r, Acc& a) {
+        double rDk = K::rD(P.kc, r);
+        double vx = p.vx - P.v.x[j], vy = p.vy - P.v.y[j], vz = p.vz - P.v.z[j];
+        if (P.type[j] == P.lid) {
+            double s = fabs(dy) / p.ay;
+            vx = s * (p.vx - P.vlid); vy = s * p.vy; vz = s * p.vz;
+        }
+        double rq = P.rho[j];
+        double c = -P.m * rDk * (p.pr + P.P[j] / (rq * rq));
+        a.x += c * dx; a.y += c * dy; a.z += c * dz;
+        double b = 8.0 / (P.Re * p.rho * rq) * P.m * rDk * (vx * dx + vy * dy + vz * dz) / (r * r + P.eps);
+        a.x += b * dx; a.y += b * dy; a.z += b * dz;
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) {
+        P.Dv.x[i] = a.x; P.Dv.y[i] = a.y; P.Dv.z[i] = a.z;
+    }
+};
+
+// ---------------------------------------------------------------- tests/test_collision_2d.jl
+// find_rho! / find_rho0!  :63-69, used with self=true
+template <class K>
+struct OpDensitySum {
+    struct Params {
+        double* out;
+        double m;
+        SpKC kc;
+    };
+    struct PS {};
+    struct Acc {
+        double d;
+    };
+    __device__ static __forceinline__ bool active(const Params&, int) { return true; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS&, Acc& a) {
+        a.d = P.out[i];
+    }
+    __device__ static __forceinline__ void pair(const Params& P, const PS&, int, double, double, double, double r,
+                                                Acc& a) {
+        a.d += P.m * K::w(P.kc, r);
+    }
+    __device__ static __forceinline__ void self(const Params& P, const PS&, Acc& a) { a.d += P.m * K::w(P.kc, 0.0); }
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) { P.out[i] = a.d; }
+};
+
+// internal_force!  test_collision_2d.jl:75-78
+template <class K>
+struct OpInternalForceSym {
+    struct Params {
+        const double* P;
+        WV3 a;
+        double m, inv_rho0sq;
+        SpKC kc;
+    };
+    struct PS {
+        double pr;
+    };
+    struct Acc {
+        double x, y, z;
+    };
+    __device__ static __forceinline__ bool active(const Params&, int) { return true; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
+        p.pr = P.P[i] * P.inv_rho0sq;
+        a.x = P.a.x[i]; a.y = P.a.y[i]; a.z = P.a.z[i];
+    }
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, int j, double dx, double dy, double dz,
+                                                double r, Acc& a) {
+        double ker = P.m * K::rD(P.kc, r);
+        double c = -ker * (p.pr + P.P[j] * P.inv_rho0sq);
+        a.x += c * dx; a.y += c * dy; a.z += c * dz;
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) {
+        P.a.x[i] = a.x; P.a.y[i] = a.y; P.a.z[i] = a.z;
+    }
+};
+
+// ---------------------------------------------------------------- ISPH, examples/collapse_dry_implicit.jl
+// viscous_force!  :128-130
+template <class K>
+struct OpIsphViscous {
+    struct Params {
+        RV3 v;
+        WV3 Dv;
+        double coef;  // 2*m*mu/rho^2
+        SpKC kc;
+    };
+    struct PS {
+        double vx, vy, vz;
+    };
+    struct Acc {
+        double x, y, z;
+    };
+    __device__ static __forceinline__ bool active(const Params&, int) { return true; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
+        p.vx = P.v.x[i]; p.vy = P.v.y[i]; p.vz = P.v.z[i];
+        a.x = P.Dv.x[i]; a.y = P.Dv.y[i]; a.z = P.Dv.z[i];
+    }
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, int j, double, double, double, double r,
+                                                Acc& a) {
+        double c = P.coef * K::rD(P.kc, r);
+        a.x += c * (p.vx - P.v.x[j]); a.y += c * (p.vy - P.v.y[j]); a.z += c * (p.vz - P.v.z[j]);
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) {
+        P.Dv.x[i] = a.x; P.Dv.y[i] = a.y; P.Dv.z[i] = a.z;
+    }
+};
+
+// div_L_lambda!  :147-152
+template <class K>
+struct OpIsphDivLLambda {
+    struct Params {
+        RV3 v;
+        double *div, *L, *lambda;
+        double m, m_over_rho, inv_dim;
+        SpKC kc;
+    };
+    struct PS {
+        double vx, vy, vz;
+    };
+    struct Acc {
+        double div, L, lam;
+    };
+    __device__ static __forceinline__ bool active(const Params&, int) { return true; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
+        p.vx = P.v.x[i]; p.vy = P.v.y[i]; p.vz = P.v.z[i];
+        a.div = P.div[i]; a.L = P.L[i]; a.lam = P.lambda[i];
+    }
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, int j, double dx, double dy, double dz,
+                                                double r, Acc& a) {
+        double rDk = K::rD(P.kc, r);
+        double dvx = p.vx - P.v.x[j], dvy = p.vy - P.v.y[j], dvz = p.vz - P.v.z[j];
+        a.div += -(dx * dvx + dy * dvy + dz * dvz) * P.m * rDk;
+        a.L += -2.0 * P.m_over_rho * rDk;
+        a.lam += P.m_over_rho * rDk * (r * r) * P.inv_dim;
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) {
+        P.div[i] = a.div; P.L[i] = a.L; P.lambda[i] = a.lam;
+    }
+};
+
+// internal_force!  :132-134
+template <class K>
+struct OpIsphInternalForce {
+    struct Params {
+        const double* P;
+        WV3 Dv;
+        double coef;  // m/rho^2
+        SpKC kc;
+    };
+    struct PS {
+        double P;
+    };
+    struct Acc {
+        double x, y, z;
+    };
+    __device__ static __forceinline__ bool active(const Params&, int) { return true; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
+        p.P = P.P[i];
+        a.x = P.Dv.x[i]; a.y = P.Dv.y[i]; a.z = P.Dv.z[i];
+    }
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, int j, double dx, double dy, double dz,
+                                                double r, Acc& a) {
+        double c = P.coef * K::rD(P.kc, r) * (p.P + P.P[j]);
+        a.x -= c * dx; a.y -= c * dy; a.z -= c * dz;
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) {
+        P.Dv.x[i] = a.x; P.Dv.y[i] = a.y; P.Dv.z[i] = a.z;
+    }
+};
+
+// Matrix-free (A p)_i of projection_matrix  :154-163 with assemble_matrix core.jl:196-225
+//   y_i = A_ii p_i + sum_{j != i} (2 h^2 m/rho) rDk(r_ij) p_j,   A_ii = h^2 L_i + [type_i==0] C_free max(lambda_i,0)
+template <class K>
+struct OpPoissonApply {
+    struct Params {
+        const double *L, *lambda, *type, *pin;
+        double* y;
+        double off_coef;  // 2*h^2*m/rho
+        double h2, C_free;
+        SpKC kc;
+    };
+    struct PS {
+        double diag;
+    };
+    struct Acc {
+        double s;
+    };
+    __device__ static __forceinline__ bool active(const Params&, int) { return true; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
+        double Aii = P.h2 * P.L[i];
+        if (P.type[i] == 0.0) Aii += P.C_free * fmax(P.lambda[i], 0.0);
+        p.diag = Aii * P.pin[i];
+        a.s = 0.0;
+    }
+    __device__ static __forceinline__ void pair(const Params& P, const PS&, int j, double, double, double, double r,
+                                                Acc& a) {
+        a.s += P.off_coef * K::rD(P.kc, r) * P.pin[j];
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS& p, const Acc& a) {
+        P.y[i] = a.s + p.diag;
+    }
+};
+
+// ---------------------------------------------------------------- unary operators
+// find_pressure!  collapse_dry.jl:123-127, cavity_flow.jl:96-100
+struct UFindPressure {
+    struct Params {
+        double *rho, *Drho, *P;
+        double dt, c2, rho0, P0;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        double rho = P.rho[i] + P.Drho[i] * P.dt;
+        P.rho[i] = rho;
+        P.Drho[i] = 0.0;
+        double pr = P.c2 * (rho - P.rho0);
+        P.P[i] = (P.P0 != 0.0) ? P.P0 + pr : pr;
+    }
+};
+// move!  collapse_dry.jl:148-153
+struct UMove {
+    struct Params {
+        WV3 x;
+        RV3 v;
+        WV3 Dv;
+        const double* type;
+        double dtm;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        P.Dv.x[i] = 0.0; P.Dv.y[i] = 0.0; P.Dv.z[i] = 0.0;
+        if (P.type[i] == 0.0) {
+            P.x.x[i] += P.dtm * P.v.x[i]; P.x.y[i] += P.dtm * P.v.y[i]; P.x.z[i] += P.dtm * P.v.z[i];
+        }
+    }
+};
+// accelerate!  collapse_dry.jl:155-159
+struct UAccelerate {
+    struct Params {
+        WV3 v;
+        RV3 Dv;
+        const double* type;
+        double hdt, gx, gy, gz;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        if (P.type[i] == 0.0) {
+            P.v.x[i] += P.hdt * (P.Dv.x[i] + P.gx);
+            P.v.y[i] += P.hdt * (P.Dv.y[i] + P.gy);
+            P.v.z[i] += P.hdt * (P.Dv.z[i] + P.gz);
+        }
+    }
+};
+// find_pressure!  test_collision_2d.jl:71-73
+struct UPressureFromRho {
+    struct Params {
+        const double *rho, *rho0;
+        double* P;
+        double c2;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) { P.P[i] = P.c2 * (P.rho[i] - P.rho0[i]); }
+};
+// reset_a! / reset_rho!  test_collision_2d.jl:80-86
+struct UFill {
+    struct Params {
+        double* f;
+        long long cap;
+        int ncomp;
+        double value;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        for (int c = 0; c < P.ncomp; c++) P.f[(size_t)c * P.cap + i] = P.value;
+    }
+};
+// move!  test_collision_2d.jl:88-90
+struct UAdvect {
+    struct Params {
+        WV3 x;
+        RV3 v;
+        double dt;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        P.x.x[i] += P.dt * P.v.x[i]; P.x.y[i] += P.dt * P.v.y[i]; P.x.z[i] += P.dt * P.v.z[i];
+    }
+};
+// accelerate!  test_collision_2d.jl:92-94
+struct UKick {
+    struct Params {
+        WV3 v;
+        RV3 a;
+        double hdt;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        P.v.x[i] += P.hdt * P.a.x[i]; P.v.y[i] += P.hdt * P.a.y[i]; P.v.z[i] += P.hdt * P.a.z[i];
+    }
+};
+// initialize!  collapse_dry_implicit.jl:118-126
+struct UIsphInitialize {
+    struct Params {
+        WV3 x, v;
+        double *div, *L, *lambda;
+        const double* type;
+        double dt, gx, gy, gz;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        if (P.type[i] == 0.0) {
+            P.x.x[i] += P.dt * P.v.x[i]; P.x.y[i] += P.dt * P.v.y[i]; P.x.z[i] += P.dt * P.v.z[i];
+            P.v.x[i] += P.dt * P.gx; P.v.y[i] += P.dt * P.gy; P.v.z[i] += P.dt * P.gz;
+        }
+        P.div[i] = 0.0;
+        P.L[i] = 0.0;
+        P.lambda[i] = 1.0;
+    }
+};
+// projection_vector  collapse_dry_implicit.jl:165-167
+struct UIsphProjectionVector {
+    struct Params {
+        const double* div;
+        double* b;
+        double neg_h2, dt;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) { P.b[i] = P.neg_h2 * P.div[i] / P.dt; }
+};
+// accelerate!  collapse_dry_implicit.jl:136-141
+struct UIsphAccelerate {
+    struct Params {
+        WV3 v, Dv;
+        const double* type;
+        double dt;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        if (P.type[i] == 0.0) {
+            P.v.x[i] += P.dt * P.Dv.x[i]; P.v.y[i] += P.dt * P.Dv.y[i]; P.v.z[i] += P.dt * P.Dv.z[i];
+        }
+        P.Dv.x[i] = 0.0; P.Dv.y[i] = 0.0; P.Dv.z[i] = 0.0;
+    }
+};

@@ -1,0 +1,311 @@
+"""Host-side shapes and lattice generators (set-up only, never on the step loop).
+
+Vectorised numpy restatement of the few pieces of the reference's set-up code needed to
+regenerate the initial states of the BASELINE configs with identical Float64 positions and
+identical particle ORDER:
+
+* shapes: ``Box``/``Rectangle``/``Circle``/``Ball``, boolean ``+ - *``, ``Specification``,
+  ``BoundaryLayer``  — reference ``src/geometry.py`` counterpart: ``src/geometry.jl:15-43, 49-68,
+  108-234, 240-258``
+* grids: ``Squaregrid``, ``Hexagrid``, ``CubicGrid`` and ``covering`` — ``src/grids.jl:48-91, 124-144``
+* ``generate_positions`` = the position part of ``generate_particles!`` — ``src/grids.jl:253-258``
+
+Order contract: ``for i in a, j in b, k in c`` in Julia nests with the LAST range innermost, which is
+numpy's C-order ravel of an ``indexing='ij'`` mesh.  Points are produced in that order.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Callable
+
+import numpy as np
+
+__all__ = [
+    "Box", "Rectangle", "Circle", "Ball", "BooleanUnion", "BooleanIntersection", "BooleanDifference",
+    "Specification", "BoundaryLayer", "Grid", "Squaregrid", "Hexagrid", "CubicGrid", "covering",
+    "generate_positions", "boundarybox",
+]
+
+
+class Shape:
+    """Supertype for shapes (src/structs.jl:19).  ``is_inside`` takes an (n,3) array."""
+
+    def is_inside(self, X: np.ndarray) -> np.ndarray:  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    def boundarybox(self) -> "Box":  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    # src/geometry.jl:237-239
+    def __add__(self, other: "Shape") -> "Shape":
+        return BooleanUnion(self, other)
+
+    def __sub__(self, other: "Shape") -> "Shape":
+        return BooleanDifference(self, other)
+
+    def __mul__(self, other: "Shape") -> "Shape":
+        return BooleanIntersection(self, other)
+
+
+@dataclass(frozen=True)
+class Box(Shape):
+    """src/geometry.jl:15-34 — closed on every face."""
+    x1_min: float
+    x2_min: float
+    x3_min: float
+    x1_max: float
+    x2_max: float
+    x3_max: float
+
+    def is_inside(self, X):
+        return ((self.x1_min <= X[:, 0]) & (X[:, 0] <= self.x1_max) & (self.x2_min <= X[:, 1])
+                & (X[:, 1] <= self.x2_max) & (self.x3_min <= X[:, 2]) & (X[:, 2] <= self.x3_max))
+
+    def boundarybox(self):
+        return self
+
+    @property
+    def lo(self):
+        return (self.x1_min, self.x2_min, self.x3_min)
+
+    @property
+    def hi(self):
+        return (self.x1_max, self.x2_max, self.x3_max)
+
+
+def Rectangle(x1_min, x2_min, x1_max, x2_max) -> Box:
+    """src/geometry.jl:41-43"""
+    return Box(float(x1_min), float(x2_min), 0.0, float(x1_max), float(x2_max), 0.0)
+
+
+@dataclass(frozen=True)
+class Circle(Shape):
+    """src/geometry.jl:49-68"""
+    x1: float
+    x2: float
+    r: float
+
+    def is_inside(self, X):
+        a = X[:, 0] - self.x1
+        b = X[:, 1] - self.x2
+        return a * a + b * b <= self.r * self.r
+
+    def boundarybox(self):
+        return Rectangle(self.x1 - self.r, self.x2 - self.r, self.x1 + self.r, self.x2 + self.r)
+
+
+@dataclass(frozen=True)
+class Ball(Shape):
+    """src/geometry.jl:245-258"""
+    x1: float
+    x2: float
+    x3: float
+    r: float
+
+    def is_inside(self, X):
+        a = X[:, 0] - self.x1
+        b = X[:, 1] - self.x2
+        c = X[:, 2] - self.x3
+        return a * a + b * b + c * c <= self.r * self.r
+
+    def boundarybox(self):
+        return Box(self.x1 - self.r, self.x2 - self.r, self.x3 - self.r, self.x1 + self.r, self.x2 + self.r,
+                   self.x3 + self.r)
+
+
+@dataclass(frozen=True)
+class BooleanUnion(Shape):
+    """src/geometry.jl:108-127"""
+    s1: Shape
+    s2: Shape
+
+    def is_inside(self, X):
+        return self.s1.is_inside(X) | self.s2.is_inside(X)
+
+    def boundarybox(self):
+        r1, r2 = self.s1.boundarybox(), self.s2.boundarybox()
+        return Box(min(r1.x1_min, r2.x1_min), min(r1.x2_min, r2.x2_min), min(r1.x3_min, r2.x3_min),
+                   max(r1.x1_max, r2.x1_max), max(r1.x2_max, r2.x2_max), max(r1.x3_max, r2.x3_max))
+
+
+@dataclass(frozen=True)
+class BooleanIntersection(Shape):
+    """src/geometry.jl:134-153"""
+    s1: Shape
+    s2: Shape
+
+    def is_inside(self, X):
+        return self.s1.is_inside(X) & self.s2.is_inside(X)
+
+    def boundarybox(self):
+        r1, r2 = self.s1.boundarybox(), self.s2.boundarybox()
+        return Box(max(r1.x1_min, r2.x1_min), max(r1.x2_min, r2.x2_min), max(r1.x3_min, r2.x3_min),
+                   min(r1.x1_max, r2.x1_max), min(r1.x2_max, r2.x2_max), min(r1.x3_max, r2.x3_max))
+
+
+@dataclass(frozen=True)
+class BooleanDifference(Shape):
+    """src/geometry.jl:160-171"""
+    s1: Shape
+    s2: Shape
+
+    def is_inside(self, X):
+        return self.s1.is_inside(X) & ~self.s2.is_inside(X)
+
+    def boundarybox(self):
+        return self.s1.boundarybox()
+
+
+@dataclass(frozen=True)
+class Specification(Shape):
+    """src/geometry.jl:178-189.  ``f`` maps an (n,3) array to a boolean mask."""
+    s: Shape
+    f: Callable[[np.ndarray], np.ndarray]
+
+    def is_inside(self, X):
+        return np.asarray(self.f(X), dtype=bool) & self.s.is_inside(X)
+
+    def boundarybox(self):
+        return self.s.boundarybox()
+
+
+class Grid:
+    dim = 0
+
+
+@dataclass(frozen=True)
+class Squaregrid(Grid):
+    """src/grids.jl:48-66"""
+    dr: float
+    dim = 2
+
+
+class Hexagrid(Grid):
+    """src/grids.jl:68-91"""
+    dim = 2
+
+    def __init__(self, dr: float):
+        self.dr = dr
+        self.a = (4 / 3) ** (1 / 4) * dr
+        self.b = (3 / 4) ** (1 / 4) * dr
+
+
+@dataclass(frozen=True)
+class CubicGrid(Grid):
+    """src/grids.jl:124-144"""
+    dr: float
+    dim = 3
+
+
+def make_grid(dr: float, symm: str) -> Grid:
+    """Grid(dr, symm), src/grids.jl:27-38 (square / hexagonal / cubic only)."""
+    if symm == "square":
+        return Squaregrid(dr)
+    if symm == "hexagonal":
+        return Hexagrid(dr)
+    if symm == "cubic":
+        return CubicGrid(dr)
+    raise ValueError("Unsupported grid type: " + symm)
+
+
+def boundarybox(s: Shape) -> Box:
+    return s.boundarybox()
+
+
+_CHUNK = 4_000_000  # lattice points evaluated per batch
+
+
+def _ifloor(x: float) -> int:
+    return int(math.floor(x))
+
+
+def _iceil(x: float) -> int:
+    return int(math.ceil(x))
+
+
+def covering(grid: Grid, s: Shape) -> np.ndarray:
+    """All lattice points of ``grid`` inside ``s`` as an (n,3) Float64 array, in the reference's order."""
+    box = s.boundarybox()
+    out = []
+    if isinstance(grid, Squaregrid):
+        i0, j0 = _ifloor(box.x1_min / grid.dr), _ifloor(box.x2_min / grid.dr)
+        i1, j1 = _iceil(box.x1_max / grid.dr), _iceil(box.x2_max / grid.dr)
+        js = np.arange(j0, j1 + 1, dtype=np.int64)
+        rows = max(1, _CHUNK // max(1, len(js)))
+        for ia in range(i0, i1 + 1, rows):
+            is_ = np.arange(ia, min(ia + rows, i1 + 1), dtype=np.int64)
+            I, J = np.meshgrid(is_, js, indexing="ij")
+            X = np.empty((I.size, 3))
+            X[:, 0] = I.ravel() * grid.dr
+            X[:, 1] = J.ravel() * grid.dr
+            X[:, 2] = 0.0
+            out.append(X[s.is_inside(X)])
+    elif isinstance(grid, Hexagrid):
+        i0, j0 = _ifloor(box.x1_min / grid.a) - 1, _ifloor(box.x2_min / grid.b)
+        i1, j1 = _iceil(box.x1_max / grid.a), _iceil(box.x2_max / grid.b)
+        js = np.arange(j0, j1 + 1, dtype=np.int64)
+        rows = max(1, _CHUNK // max(1, len(js)))
+        for ia in range(i0, i1 + 1, rows):
+            is_ = np.arange(ia, min(ia + rows, i1 + 1), dtype=np.int64)
+            I, J = np.meshgrid(is_, js, indexing="ij")
+            I, J = I.ravel(), J.ravel()
+            X = np.empty((I.size, 3))
+            # j % 2 in Julia is the C remainder (sign of the dividend), src/grids.jl:83
+            X[:, 0] = (I + np.fmod(J, 2) / 2) * grid.a
+            X[:, 1] = J * grid.b
+            X[:, 2] = 0.0
+            out.append(X[s.is_inside(X)])
+    elif isinstance(grid, CubicGrid):
+        i0, j0, k0 = (_ifloor(box.x1_min / grid.dr), _ifloor(box.x2_min / grid.dr), _ifloor(box.x3_min / grid.dr))
+        i1, j1, k1 = (_iceil(box.x1_max / grid.dr), _iceil(box.x2_max / grid.dr), _iceil(box.x3_max / grid.dr))
+        js = np.arange(j0, j1 + 1, dtype=np.int64)
+        ks = np.arange(k0, k1 + 1, dtype=np.int64)
+        rows = max(1, _CHUNK // max(1, len(js) * len(ks)))
+        for ia in range(i0, i1 + 1, rows):
+            is_ = np.arange(ia, min(ia + rows, i1 + 1), dtype=np.int64)
+            I, J, K = np.meshgrid(is_, js, ks, indexing="ij")
+            X = np.empty((I.size, 3))
+            X[:, 0] = I.ravel() * grid.dr
+            X[:, 1] = J.ravel() * grid.dr
+            X[:, 2] = K.ravel() * grid.dr
+            out.append(X[s.is_inside(X)])
+    else:
+        raise TypeError("unsupported grid")
+    return np.concatenate(out, axis=0) if out else np.zeros((0, 3))
+
+
+class BoundaryLayer(Shape):
+    """src/geometry.jl:198-234: not in ``s`` but ``x + dx`` in ``s`` for a lattice offset |dx| <= width."""
+
+    def __init__(self, s: Shape, grid: Grid, width: float):
+        self.s = s
+        self.dim = grid.dim
+        self.dxs = covering(grid, Ball(0.0, 0.0, 0.0, width))
+        self.width = width
+
+    def is_inside(self, X):
+        res = np.zeros(len(X), dtype=bool)
+        cand = np.flatnonzero(~self.s.is_inside(X))
+        if cand.size:
+            Xc = X[cand]
+            hit = np.zeros(cand.size, dtype=bool)
+            for dx in self.dxs:
+                todo = np.flatnonzero(~hit)
+                if todo.size == 0:
+                    break
+                hit[todo] = self.s.is_inside(Xc[todo] + dx)
+            res[cand] = hit
+        return res
+
+    def boundarybox(self):
+        r = self.s.boundarybox()
+        w = self.width
+        if self.dim == 2:
+            return Rectangle(r.x1_min - w, r.x2_min - w, r.x1_max + w, r.x2_max + w)
+        return Box(r.x1_min - w, r.x2_min - w, r.x3_min - w, r.x1_max + w, r.x2_max + w, r.x3_max + w)
+
+
+def generate_positions(grid: Grid, geometry: Shape) -> np.ndarray:
+    """Positions ``generate_particles!`` would push, in order (src/grids.jl:253-258)."""
+    return covering(grid, geometry)

@@ -1,0 +1,128 @@
+"""Registered operators: the named, parameterised counterparts of the closures the reference's examples
+pass to ``apply!``.  Each factory returns an :class:`Operator` carrying the
+operator id, the field binding (names of the particle fields playing each role) and the Float64 parameter
+block.  Parameter expressions are folded here exactly as the reference's ``const`` expressions are
+(e.g. ``2*nu``, ``c^2``, ``0.5*dt``), so host and device see the same doubles.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Tuple
+
+from . import abi
+
+K = abi.K
+
+
+@dataclass(frozen=True)
+class Operator:
+    op: int
+    fields: Tuple[str, ...]
+    params: Tuple[float, ...]
+    binary: bool
+    name: str = ""
+
+
+def _kid(kernel) -> float:
+    return float(abi.KERNEL_IDS[kernel] if isinstance(kernel, str) else int(kernel))
+
+
+# ---- WCSPH: examples/collapse_dry.jl, collapse3d.jl, cavity_flow.jl
+def balance_of_mass(kernel, m, h, nu=0.0, x="x", v="v", rho="rho", Drho="Drho"):
+    """collapse_dry.jl:112-115 / collapse3d.jl:87-90; cavity_flow.jl:92-94 with nu = 0."""
+    return Operator(K["SP_OP_BALANCE_OF_MASS"], (x, v, rho, Drho), (_kid(kernel), m, h, 2 * nu), True,
+                    "balance_of_mass!")
+
+
+def find_pressure(dt, c, rho0, P0=0.0, rho="rho", Drho="Drho", P="P"):
+    """collapse_dry.jl:123-127; cavity_flow.jl:96-100 adds P0."""
+    return Operator(K["SP_OP_FIND_PRESSURE"], (rho, Drho, P), (dt, c * c, rho0, P0), False, "find_pressure!")
+
+
+def internal_force(kernel, m, h, mu, rho0, x="x", v="v", P="P", rho="rho", Dv="Dv", type="type"):
+    """collapse_dry.jl:135-141."""
+    return Operator(K["SP_OP_INTERNAL_FORCE"], (x, v, P, rho, Dv, type), (_kid(kernel), m, h, mu, rho0), True,
+                    "internal_force!")
+
+
+def internal_force_cavity(m, h, Re, vlid, ylid=1.0, lid_type=2.0, x="x", v="v", P="P", rho="rho", Dv="Dv",
+                          type="type"):
+    """cavity_flow.jl:102-114."""
+    return Operator(K["SP_OP_INTERNAL_FORCE_CAVITY"], (x, v, P, rho, Dv, type),
+                    (m, h, float(Re), vlid, ylid, lid_type), True, "internal_force! (cavity)")
+
+
+def move(dtm, x="x", v="v", Dv="Dv", type="type"):
+    """collapse_dry.jl:148-153 (dtm = 0.5*dt), collapse3d.jl:106-111 (dtm = dt)."""
+    return Operator(K["SP_OP_MOVE"], (x, v, Dv, type), (dtm,), False, "move!")
+
+
+def accelerate(hdt, g=(0.0, 0.0, 0.0), v="v", Dv="Dv", type="type"):
+    """collapse_dry.jl:155-159: v += hdt*(Dv + g) for fluid particles."""
+    return Operator(K["SP_OP_ACCELERATE"], (v, Dv, type), (hdt, g[0], g[1], g[2]), False, "accelerate!")
+
+
+# ---- tests/test_collision_2d.jl
+def density_sum(kernel, m, h, out="rho", x="x"):
+    """find_rho! / find_rho0!, test_collision_2d.jl:63-69 (use with self=True)."""
+    return Operator(K["SP_OP_DENSITY_SUM"], (x, out), (_kid(kernel), m, h), True, "find_rho!")
+
+
+def pressure_from_rho(c, rho="rho", rho0="rho0", P="P"):
+    return Operator(K["SP_OP_PRESSURE_FROM_RHO"], (rho, rho0, P), (c * c,), False, "find_pressure! (collision)")
+
+
+def internal_force_sym(kernel, m, h, rho0, x="x", P="P", a="a"):
+    return Operator(K["SP_OP_INTERNAL_FORCE_SYM"], (x, P, a), (_kid(kernel), m, h, rho0), True,
+                    "internal_force! (collision)")
+
+
+def fill(field, value=0.0):
+    return Operator(K["SP_OP_FILL"], (field,), (value,), False, "reset!")
+
+
+def advect(dt, x="x", v="v"):
+    return Operator(K["SP_OP_ADVECT"], (x, v), (dt,), False, "move! (collision)")
+
+
+def kick(hdt, v="v", a="a"):
+    return Operator(K["SP_OP_KICK"], (v, a), (hdt,), False, "accelerate! (collision)")
+
+
+# ---- ISPH: examples/collapse_dry_implicit.jl
+def isph_initialize(dt, g, x="x", v="v", div="div", L="L", lam="lambda", type="type"):
+    return Operator(K["SP_OP_ISPH_INITIALIZE"], (x, v, div, L, lam, type), (dt, g[0], g[1], g[2]), False,
+                    "initialize!")
+
+
+def isph_viscous_force(kernel, m, h, mu, rho, x="x", v="v", Dv="Dv"):
+    return Operator(K["SP_OP_ISPH_VISCOUS_FORCE"], (x, v, Dv), (_kid(kernel), m, h, mu, rho), True, "viscous_force!")
+
+
+def isph_div_L_lambda(kernel, m, h, rho, dim, x="x", v="v", div="div", L="L", lam="lambda"):
+    return Operator(K["SP_OP_ISPH_DIV_L_LAMBDA"], (x, v, div, L, lam), (_kid(kernel), m, h, rho, float(dim)), True,
+                    "div_L_lambda!")
+
+
+def isph_projection_vector(h, dt, div="div", b="b"):
+    return Operator(K["SP_OP_ISPH_PROJECTION_VECTOR"], (div, b), (h, dt), False, "projection_vector")
+
+
+def isph_internal_force(kernel, m, h, rho, x="x", P="P", Dv="Dv"):
+    return Operator(K["SP_OP_ISPH_INTERNAL_FORCE"], (x, P, Dv), (_kid(kernel), m, h, rho), True,
+                    "internal_force! (isph)")
+
+
+def isph_accelerate(dt, v="v", Dv="Dv", type="type"):
+    return Operator(K["SP_OP_ISPH_ACCELERATE"], (v, Dv, type), (dt,), False, "accelerate! (isph)")
+
+
+@dataclass(frozen=True)
+class PoissonOperator:
+    """projection_matrix of collapse_dry_implicit.jl:154-163 as a matrix-free operator."""
+    fields: Tuple[str, ...]  # x, L, lambda, type
+    params: Tuple[float, ...]  # kernel, m, h, rho, C_free
+
+
+def isph_projection_matrix(kernel, m, h, rho, C_free, x="x", L="L", lam="lambda", type="type"):
+    return PoissonOperator((x, L, lam, type), (_kid(kernel), m, h, rho, C_free))

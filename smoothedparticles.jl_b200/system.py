@@ -1,0 +1,296 @@
+"""Host-side mirror of the reference's ``ParticleSystem / create_cell_list! / apply!`` surface
+(src/structs.jl:44-125, src/core.jl:51-291) over the C ABI of include/sp_b200.h.
+
+The particle struct of the reference becomes a dict ``{field name: ncomp}``; the particles live in HBM as
+struct-of-arrays planes owned by the library.  Per-particle access ``sys.particles[i].x`` becomes bulk
+``sys.get("x")`` / ``sys.set("x", array)`` in REFERENCE ORDER (the order the reference's
+``sys.particles`` vector would have, including its swap-with-tail renumbering on removal).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, Mapping, Sequence
+
+import numpy as np
+
+from . import abi
+from .operators import Operator, PoissonOperator
+
+K = abi.K
+
+
+def _farr(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class ParticleSystem:
+    """``ParticleSystem(T, domain, h)`` (src/structs.jl:57-91).
+
+    ``particle_fields`` plays the role of the particle type ``T``: field name -> number of components
+    (1 scalar, 3 RealVector).  ``x`` (3) always exists.  ``domain`` is any shape with ``boundarybox()``
+    (or an object with ``lo``/``hi``); only its bounding box is kept, as in the reference (:63,:87).
+    """
+
+    def __init__(self, particle_fields: Mapping[str, int], domain, h: float, device: int = 0):
+        self._lib = abi.load()
+        box = domain.boundarybox() if hasattr(domain, "boundarybox") else domain
+        lo = (C.c_double * 3)(*[float(v) for v in box.lo])
+        hi = (C.c_double * 3)(*[float(v) for v in box.hi])
+        handle = C.c_void_p()
+        abi.check(self._lib.sp_create(C.byref(handle), lo, hi, float(h), int(device)), None)
+        self._h = handle
+        self.h = float(h)
+        self.domain = box
+        self.device = device
+        self.fields: Dict[str, int] = {"x": 3}
+        self._fid: Dict[str, int] = {"x": 0}
+        for name, nc in particle_fields.items():
+            self.add_field(name, nc)
+        phase = (C.c_int64 * 3)()
+        lim = (C.c_int64 * 3)()
+        kmax = C.c_int64()
+        nd = C.c_int32()
+        diff = (C.c_int64 * 27)()
+        abi.check(self._lib.sp_key_params(self._h, phase, lim, C.byref(kmax), C.byref(nd), diff), self._h)
+        self.key_phase = tuple(phase)
+        self.key_lim = tuple(lim)
+        self.key_max = kmax.value
+        self.key_diff = list(diff[: nd.value])
+
+    # -- life cycle
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.sp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- fields
+    def add_field(self, name: str, ncomp: int = 1) -> int:
+        fid = C.c_int32()
+        abi.check(self._lib.sp_add_field(self._h, name.encode(), int(ncomp), C.byref(fid)), self._h)
+        self.fields[name] = int(ncomp)
+        self._fid[name] = fid.value
+        return fid.value
+
+    def fid(self, name: str) -> int:
+        return self._fid[name]
+
+    def __len__(self) -> int:
+        n = C.c_int64()
+        abi.check(self._lib.sp_num_particles(self._h, C.byref(n)), self._h)
+        return n.value
+
+    @property
+    def n(self) -> int:
+        return len(self)
+
+    def resize(self, n: int):
+        abi.check(self._lib.sp_resize(self._h, int(n)), self._h)
+
+    def add_particles(self, **arrays):
+        """``generate_particles!`` / ``push!`` (src/grids.jl:253-258): append particles at the end of the
+        reference order.  ``x`` is required; missing fields are zero."""
+        x = _farr(arrays["x"])
+        if x.ndim != 2 or x.shape[1] != 3:
+            raise ValueError("x must have shape (n, 3)")
+        n_new = x.shape[0]
+        n_old = len(self)
+        if n_new == 0:
+            return
+        self.resize(n_old + n_new)
+        for name, nc in self.fields.items():
+            if name.startswith("_"):
+                continue
+            cur = self.get(name) if n_old else np.zeros((0, nc) if nc > 1 else (0,))
+            if name in arrays:
+                add = _farr(arrays[name])
+                if nc == 1:
+                    add = np.broadcast_to(add, (n_new,))
+                else:
+                    add = np.broadcast_to(add, (n_new, nc))
+            else:
+                add = cur[n_old:]
+            full = np.concatenate([cur[:n_old], add], axis=0)
+            self.set(name, full)
+
+    def set(self, name: str, values):
+        """Upload a field in reference order: shape (n,) or (n, ncomp)."""
+        nc = self.fields[name]
+        a = _farr(values)
+        n = len(self)
+        if a.size != n * nc:
+            raise ValueError(f"field {name}: expected {n}x{nc} values, got shape {a.shape}")
+        abi.check(self._lib.sp_upload(self._h, self._fid[name], abi.ptr_f64(a), n, K["SP_LAYOUT_AOS"]), self._h)
+
+    def get(self, name: str) -> np.ndarray:
+        """Download a field in reference order."""
+        nc = self.fields[name]
+        n = len(self)
+        out = np.empty((n, nc) if nc > 1 else (n,), dtype=np.float64)
+        if n:
+            abi.check(self._lib.sp_download(self._h, self._fid[name], abi.ptr_f64(out), n, K["SP_LAYOUT_AOS"]),
+                      self._h)
+        return out
+
+    def upload_raw(self, name: str, host_ptr, n: int, layout: int):
+        abi.check(self._lib.sp_upload(self._h, self._fid[name], host_ptr, n, layout), self._h)
+
+    def download_raw(self, name: str, host_ptr, n: int, layout: int):
+        abi.check(self._lib.sp_download(self._h, self._fid[name], host_ptr, n, layout), self._h)
+
+    def synchronize(self):
+        abi.check(self._lib.sp_synchronize(self._h), self._h)
+
+    # -- the hot path
+    def create_cell_list(self):
+        """``create_cell_list!(sys)`` (src/core.jl:51-90)."""
+        abi.check(self._lib.sp_create_cell_list(self._h), self._h)
+
+    def _bind(self, names: Sequence[str]):
+        return np.asarray([self._fid[nm] for nm in names], dtype=np.int32)
+
+    def apply(self, op: Operator, self_: bool = False, strict_order: bool = False):
+        """``apply!(sys, action!; self=false)`` (src/core.jl:151-161) for a registered operator."""
+        F = self._bind(op.fields)
+        P = _farr(op.params)
+        flags = (K["SP_FLAG_SELF"] if self_ else 0) | (K["SP_FLAG_STRICT_ORDER"] if strict_order else 0)
+        abi.check(self._lib.sp_apply(self._h, op.op, abi.ptr_i32(F), len(F), abi.ptr_f64(P), len(P), flags), self._h)
+
+    def sum_at_points(self, sum_op: int, fields: Sequence[str], params: Sequence[float], points) -> np.ndarray:
+        """``SmoothedParticles.sum(sys, f, x)`` (src/core.jl:240-260) for many points at once."""
+        pts = _farr(points).reshape(-1, 3)
+        out = np.empty(len(pts))
+        F = self._bind(fields)
+        P = _farr(params)
+        abi.check(self._lib.sp_sum_at_points(self._h, sum_op, abi.ptr_i32(F), len(F), abi.ptr_f64(P), len(P),
+                                             abi.ptr_f64(pts), len(pts), abi.ptr_f64(out)), self._h)
+        return out
+
+    def reduce(self, red: int, fields: Sequence[str], params: Sequence[float] = (), nout: int = 1) -> np.ndarray:
+        F = self._bind(fields)
+        P = _farr(params) if len(params) else np.zeros(1)
+        out = np.zeros(3)
+        abi.check(self._lib.sp_reduce(self._h, red, abi.ptr_i32(F), len(F), abi.ptr_f64(P), len(params),
+                                      abi.ptr_f64(out)), self._h)
+        return out[:nout].copy()
+
+    def assemble_vector(self, op: Operator) -> np.ndarray:
+        """``assemble_vector(sys, func)`` (src/core.jl:175-182): the unary operator writes its LAST bound
+        field, which is then downloaded."""
+        self.apply(op)
+        return self.get(op.fields[-1])
+
+    def poisson_apply(self, A: PoissonOperator, p_in: str, y_out: str):
+        F = self._bind(tuple(A.fields) + (p_in, y_out))
+        P = _farr(A.params)
+        abi.check(self._lib.sp_poisson_apply(self._h, abi.ptr_i32(F), len(F), abi.ptr_f64(P), len(P)), self._h)
+
+    def poisson_cg(self, A: PoissonOperator, b: str, P_out: str, reltol=None, abstol=0.0, maxiter=0):
+        """``P .= cg(A, b)`` (collapse_dry_implicit.jl:227) without assembling A."""
+        if reltol is None:
+            reltol = float(np.sqrt(np.finfo(np.float64).eps))
+        F = self._bind(tuple(A.fields) + (b, P_out))
+        P = _farr(A.params)
+        iters = C.c_int64()
+        resid = C.c_double()
+        abi.check(self._lib.sp_poisson_cg(self._h, abi.ptr_i32(F), len(F), abi.ptr_f64(P), len(P), float(reltol),
+                                          float(abstol), int(maxiter), C.byref(iters), C.byref(resid)), self._h)
+        return iters.value, resid.value
+
+    def run_program(self, program: int, fields: Sequence[str], params: Sequence[float], nsteps: int):
+        F = self._bind(fields)
+        P = _farr(params)
+        abi.check(self._lib.sp_run_program(self._h, program, abi.ptr_i32(F), len(F), abi.ptr_f64(P), len(P),
+                                           int(nsteps)), self._h)
+
+    # -- parity / debug views (1-based, reference order)
+    def cell_keys(self) -> np.ndarray:
+        n = len(self)
+        out = np.empty(n, dtype=np.int64)
+        if n:
+            abi.check(self._lib.sp_get_cell_keys(self._h, abi.ptr_i64(out), n), self._h)
+        return out
+
+    def cell_list(self):
+        n = len(self)
+        offsets = np.empty(self.key_max + 1, dtype=np.int64)
+        members = np.empty(max(n, 1), dtype=np.int64)
+        abi.check(self._lib.sp_get_cell_list(self._h, abi.ptr_i64(offsets), abi.ptr_i64(members)), self._h)
+        return offsets, members[:n]
+
+    def neighbour_lists(self):
+        n = len(self)
+        offsets = np.zeros(n + 1, dtype=np.int64)
+        abi.check(self._lib.sp_get_neighbour_lists(self._h, abi.ptr_i64(offsets), None, 0), self._h)
+        total = int(offsets[n])
+        ids = np.empty(max(total, 1), dtype=np.int64)
+        abi.check(self._lib.sp_get_neighbour_lists(self._h, abi.ptr_i64(offsets), abi.ptr_i64(ids), total), self._h)
+        return offsets, ids[:total]
+
+    @property
+    def n_removed(self) -> int:
+        n = C.c_int64()
+        abi.check(self._lib.sp_num_removed(self._h, C.byref(n)), self._h)
+        return n.value
+
+    def last_call_ms(self) -> float:
+        ms = C.c_float()
+        abi.check(self._lib.sp_last_call_ms(self._h, C.byref(ms)), self._h)
+        return ms.value
+
+    @property
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        abi.check(self._lib.sp_launch_count(self._h, C.byref(n)), self._h)
+        return n.value
+
+
+# free functions with the reference's names (src/SmoothedParticles.jl:10-72)
+def create_cell_list(sys: ParticleSystem):
+    sys.create_cell_list()
+
+
+def apply(sys: ParticleSystem, op: Operator, self: bool = False, strict_order: bool = False):
+    sys.apply(op, self_=self, strict_order=strict_order)
+
+
+def assemble_vector(sys: ParticleSystem, op: Operator) -> np.ndarray:
+    return sys.assemble_vector(op)
+
+
+class ParticleField:
+    """``ParticleField(sys, :var)`` (src/structs.jl:118-125): array-like view of one scalar field.
+    Reads download, ``field[:] = values`` uploads."""
+
+    def __init__(self, sys: ParticleSystem, name: str):
+        self.sys = sys
+        self.name = name
+
+    def __len__(self):
+        return len(self.sys)
+
+    def __array__(self, dtype=None, copy=None):
+        return self.sys.get(self.name)
+
+    def __getitem__(self, idx):
+        return self.sys.get(self.name)[idx]
+
+    def __setitem__(self, idx, val):
+        cur = self.sys.get(self.name)
+        cur[idx] = val
+        self.sys.set(self.name, cur)
+
+
+def kernel_eval(kernel, kfun: int, h: float, r, device: int = 0) -> np.ndarray:
+    """Evaluate a kernel function of src/kernels.jl on the device."""
+    lib = abi.load()
+    r = _farr(r)
+    out = np.empty_like(r)
+    kid = abi.KERNEL_IDS[kernel] if isinstance(kernel, str) else int(kernel)
+    abi.check(lib.sp_kernel_eval(kid, int(kfun), float(h), abi.ptr_f64(r), abi.ptr_f64(out), r.size, device), None)
+    return out

@@ -1,0 +1,171 @@
+"""Pins the CPU oracle to the reference: the reference's own tests, ported 1:1 and run against the oracle.
+
+  tests/test_kernels.jl:20-61        kernel known-answer properties
+  tests/test_collision_2d.jl:118-149 particle count constant, energy growth < 1e-2 over 4 167 steps
+plus independent checks of the neighbour search (brute force), of the literal insertion path
+(core.jl:13-41) and of the removal rule (core.jl:72-81).
+"""
+import math
+
+import numpy as np
+import pytest
+
+import smoothedparticles_jl_b200 as sp
+from smoothedparticles_jl_b200 import configs, geometry as geo, operators as ops
+from oracle import oracle
+from oracle.oracle import OracleSystem
+
+K = sp.K
+TOL = 0.01
+N = 1000
+
+
+def simpson_rule(f, a, b, n=N):
+    # tests/test_kernels.jl:8-18 (sic: starts at i = 1)
+    I = 0.0
+    h = (b - a) / n
+    for i in range(1, n):
+        _a = a + i * h
+        _b = a + (i + 1) * h
+        I += h / 6.0 * (f(_a) + 4.0 * f(0.5 * (_a + _b)) + f(_b))
+    return I
+
+
+def _ker(kid, kfun):
+    return lambda h, r: float(oracle.kernel_eval(kid, kfun, h, np.array([r]))[0])
+
+
+@pytest.mark.parametrize("name,dim", [("wendland1", 1), ("wendland2", 2), ("wendland3", 3), ("spline23", 2),
+                                      ("spline24", 2)])
+def test_local_ker(name, dim):
+    # tests/test_kernels.jl:20-43
+    kid = sp.abi.KERNEL_IDS[name]
+    f, Df, rDf = _ker(kid, K["SP_KFUN_W"]), _ker(kid, K["SP_KFUN_DW"]), _ker(kid, K["SP_KFUN_RDW"])
+    h = 0.42
+    assert f(h, 4.0) == 0.0
+    assert math.isfinite(f(h, 0.0))
+    if dim == 1:
+        integral = simpson_rule(lambda r: 2.0 * f(h, r), 0.0, h)
+    elif dim == 2:
+        integral = simpson_rule(lambda r: 2.0 * math.pi * r * f(h, r), 0.0, h)
+    else:
+        integral = simpson_rule(lambda r: 4.0 * math.pi * r * r * f(h, r), 0.0, h)
+    assert integral == pytest.approx(1.0, rel=TOL)
+    assert Df(h, 4.0) == 0.0
+    assert math.isfinite(Df(h, 0.0))
+    integral = simpson_rule(lambda r: Df(h, r), 0.2, 0.3)
+    diff = f(h, 0.3) - f(h, 0.2)
+    assert integral == pytest.approx(diff, rel=0.01)
+    assert rDf(h, 4.0) == 0.0
+    assert math.isfinite(rDf(h, 0.0))
+    assert rDf(h, 0.1) == pytest.approx(Df(h, 0.1) / 0.1, rel=TOL)
+
+
+def test_collision_2d_reference_assertions():
+    # tests/test_collision_2d.jl:116-149, full length
+    case = configs.collision_2d()
+    sys_ = case.make(OracleSystem)
+    c = case.consts
+    case.prologue(sys_)
+    dt, t_end = c["dt"], c["t_end"]
+    dt_frame = t_end / 10
+    Ns, Es = [], []
+    every = int(round(dt_frame / dt))
+    for k in range(0, int(round(t_end / dt)) + 1):
+        case.step(sys_)
+        if k % every == 0:
+            Ns.append(len(sys_))
+            Es.append(sys_.reduce(K["SP_RED_ENERGY_COLLISION"], ("v", "rho", "rho0"), (c["m"], c["c"], c["rho0"]))[0])
+    assert all(n == Ns[0] for n in Ns)                 # "count particles"
+    err = max(e / Es[0] - 1.0 for e in Es)             # "energy conservation"
+    assert err < 1e-2
+    assert len(Es) == 10                               # k = 0, 417, ..., 3753 of 0:4167
+
+
+def _brute_neighbours(x, h):
+    d = x[:, None, :] - x[None, :, :]
+    r = np.sqrt((d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2])
+    ok = ~(r > h)
+    np.fill_diagonal(ok, False)
+    return ok
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_neighbour_sets_vs_brute_force(dim):
+    rng = np.random.default_rng(7)
+    n = 600
+    h = 0.11
+    x = rng.uniform(0.0, 1.0, size=(n, 3))
+    if dim == 2:
+        x[:, 2] = 0.0
+        dom = geo.Rectangle(0.0, 0.0, 1.0, 1.0)
+    else:
+        dom = geo.Box(0.0, 0.0, 0.0, 1.0, 1.0, 1.0)
+    s = OracleSystem({}, dom, h)
+    s.add_particles(x=x)
+    s.create_cell_list()
+    off, ids = s.neighbour_lists()
+    ok = _brute_neighbours(x, h)
+    for i in range(n):
+        got = sorted(ids[off[i]:off[i + 1]] - 1)
+        assert got == list(np.flatnonzero(ok[i]))
+    assert s.check_cell_list_literal()
+
+
+def test_cell_members_descending_and_keys():
+    case = configs.collapse_dry()
+    s = case.make(OracleSystem)
+    s.create_cell_list()
+    off, mem = s.cell_list()
+    keys = s.cell_keys()
+    assert off[-1] == len(s)
+    for k in np.flatnonzero(np.diff(off) > 0)[:500]:
+        cell = mem[off[k]:off[k + 1]]
+        assert np.all(np.diff(cell) < 0)                # descending (core.jl:32-37)
+        assert np.all(keys[cell - 1] == k + 1)
+    assert s.check_cell_list_literal()
+    # find_key formula, structs.jl:97-106
+    x = case.init["x"]
+    i = 1 + np.floor(x[:, 0] / case.h).astype(np.int64) - s.key_phase[0]
+    j = 1 + np.floor(x[:, 1] / case.h).astype(np.int64) - s.key_phase[1]
+    k3 = 1 + np.floor(x[:, 2] / case.h).astype(np.int64) - s.key_phase[2]
+    assert np.array_equal(keys, i + s.key_lim[0] * (j - 1) + s.key_lim[0] * s.key_lim[1] * (k3 - 1))
+
+
+def _literal_removal(ids, inside):
+    # core.jl:63-81 on a python list
+    A = list(ids)
+    N = len(A)
+    victims = [i for i in range(N, 0, -1) if not inside[i - 1]]   # descending, 1-based
+    for t, r in enumerate(victims, start=1):
+        A[r - 1] = A[N + 1 - t - 1]
+    return A[: N - len(victims)]
+
+
+def test_removal_rule_matches_literal_loop():
+    rng = np.random.default_rng(3)
+    dom = geo.Box(0.0, 0.0, 0.0, 1.0, 1.0, 1.0)
+    for trial in range(40):
+        n = int(rng.integers(1, 60))
+        x = rng.uniform(0.05, 0.95, size=(n, 3))
+        out = rng.random(n) < rng.uniform(0, 0.9)
+        x[out, 0] = rng.choice([-0.5, 1.5, np.nan], size=out.sum())
+        s = OracleSystem({"tag": 1}, dom, 0.2)
+        s.add_particles(x=x, tag=np.arange(1, n + 1, dtype=float))
+        s.create_cell_list()
+        expect = _literal_removal(range(1, n + 1), ~out)
+        assert list(s.get("tag").astype(int)) == expect
+        assert s.n_removed == out.sum()
+
+
+def test_key_params_match_constructor_formula():
+    # structs.jl:63-82 on the collapse3d box
+    case = configs.collapse3d()
+    s = case.make(OracleSystem)
+    assert s.key_lim == (62, 39, 19) and s.key_max == 45942
+    L1, L2 = s.key_lim[0], s.key_lim[1]
+    expect = [di + L1 * (dj + L2 * dk) for di in (-1, 0, 1) for dj in (-1, 0, 1) for dk in (-1, 0, 1)]
+    assert s.key_diff == expect
+    c2 = configs.collapse_dry()
+    s2 = c2.make(OracleSystem)
+    assert s2.key_diff == [di + s2.key_lim[0] * dj for di in (-1, 0, 1) for dj in (-1, 0, 1)]
