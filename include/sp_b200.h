@@ -241,6 +241,10 @@ int32_t sp_get_neighbour_lists(sp_system* sys, int64_t* offsets /* n+1 */, int64
 int32_t sp_num_removed(sp_system* sys, int64_t* n_removed);
 /* Device timing of the last call in ms (CUDA events on the handle's stream). */
 int32_t sp_last_call_ms(sp_system* sys, float* ms);
+/* Time a region of calls on the handle's stream with CUDA events: start records, stop records,
+ * synchronises and returns the elapsed device time in ms. */
+int32_t sp_timer_start(sp_system* sys);
+int32_t sp_timer_stop(sp_system* sys, float* ms);
 /* Count of kernel launches issued by this handle since creation. */
 int32_t sp_launch_count(sp_system* sys, int64_t* launches);
 

@@ -66,6 +66,8 @@ SIGNATURES = {
     "sp_get_neighbour_lists": (_i32, [_p, _pi64, _pi64, _i64]),
     "sp_num_removed": (_i32, [_p, _pi64]),
     "sp_last_call_ms": (_i32, [_p, C.POINTER(C.c_float)]),
+    "sp_timer_start": (_i32, [_p]),
+    "sp_timer_stop": (_i32, [_p, C.POINTER(C.c_float)]),
     "sp_launch_count": (_i32, [_p, _pi64]),
     "sp_slab_unique_id": (_i32, [C.POINTER(C.c_uint8)]),
     "sp_slab_init": (_i32, [_p, C.POINTER(C.c_uint8), _i32, _i32, _i32, _i32]),

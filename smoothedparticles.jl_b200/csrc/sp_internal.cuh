@@ -45,7 +45,8 @@ struct SlabState;  // sp_slab.cu
 struct sp_system {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;    // per-call timing
+    cudaEvent_t tev0 = nullptr, tev1 = nullptr;  // sp_timer_start/stop
     SpGrid g{};
     int n_key_diff = 0;
     long long key_diff[27]{};

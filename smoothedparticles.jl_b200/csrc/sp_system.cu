@@ -232,6 +232,8 @@ int32_t sp_create(sp_system** out, const double lo[3], const double hi[3], doubl
     CREATE_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     CREATE_TRY(cudaEventCreate(&s->ev0));
     CREATE_TRY(cudaEventCreate(&s->ev1));
+    CREATE_TRY(cudaEventCreate(&s->tev0));
+    CREATE_TRY(cudaEventCreate(&s->tev1));
     CREATE_TRY(cudaMalloc(&s->cell_start, (size_t)(g.key_max + 3) * sizeof(int)));
     CREATE_TRY(cudaMalloc(&s->cell_fill, (size_t)(g.key_max + 3) * sizeof(int)));
     CREATE_TRY(cudaMemset(s->cell_start, 0, (size_t)(g.key_max + 3) * sizeof(int)));
@@ -275,6 +277,8 @@ int32_t sp_destroy(sp_system* s) {
     if (s->h_counters) cudaFreeHost(s->h_counters);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->tev0) cudaEventDestroy(s->tev0);
+    if (s->tev1) cudaEventDestroy(s->tev1);
     if (s->stream) cudaStreamDestroy(s->stream);
     cudaGetLastError();
     delete s;
@@ -426,6 +430,21 @@ int32_t sp_last_call_ms(sp_system* s, float* ms) {
     SP_CUDA(s, cudaSetDevice(s->device));
     SP_CUDA(s, cudaEventSynchronize(s->ev1));
     SP_CUDA(s, cudaEventElapsedTime(ms, s->ev0, s->ev1));
+    return SP_OK;
+}
+
+int32_t sp_timer_start(sp_system* s) {
+    if (!s) return SP_ERR_INVALID;
+    SP_CUDA(s, cudaSetDevice(s->device));
+    SP_CUDA(s, cudaEventRecord(s->tev0, s->stream));
+    return SP_OK;
+}
+int32_t sp_timer_stop(sp_system* s, float* ms) {
+    if (!s || !ms) return SP_ERR_INVALID;
+    SP_CUDA(s, cudaSetDevice(s->device));
+    SP_CUDA(s, cudaEventRecord(s->tev1, s->stream));
+    SP_CUDA(s, cudaEventSynchronize(s->tev1));
+    SP_CUDA(s, cudaEventElapsedTime(ms, s->tev0, s->tev1));
     return SP_OK;
 }
 

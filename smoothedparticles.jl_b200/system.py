@@ -103,20 +103,14 @@ class ParticleSystem:
         if n_new == 0:
             return
         self.resize(n_old + n_new)
-        for name, nc in self.fields.items():
-            if name.startswith("_"):
-                continue
-            cur = self.get(name) if n_old else np.zeros((0, nc) if nc > 1 else (0,))
-            if name in arrays:
-                add = _farr(arrays[name])
-                if nc == 1:
-                    add = np.broadcast_to(add, (n_new,))
-                else:
-                    add = np.broadcast_to(add, (n_new, nc))
+        for name, values in arrays.items():
+            nc = self.fields[name]
+            add = np.broadcast_to(_farr(values), (n_new,) if nc == 1 else (n_new, nc))
+            if n_old:
+                full = np.concatenate([self.get(name)[:n_old], add], axis=0)
             else:
-                add = cur[n_old:]
-            full = np.concatenate([cur[:n_old], add], axis=0)
-            self.set(name, full)
+                full = add
+            self.set(name, full)   # fields not given stay zero (sp_resize zero-fills the new tail)
 
     def set(self, name: str, values):
         """Upload a field in reference order: shape (n,) or (n, ncomp)."""
@@ -241,6 +235,14 @@ class ParticleSystem:
     def last_call_ms(self) -> float:
         ms = C.c_float()
         abi.check(self._lib.sp_last_call_ms(self._h, C.byref(ms)), self._h)
+        return ms.value
+
+    def timer_start(self):
+        abi.check(self._lib.sp_timer_start(self._h), self._h)
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        abi.check(self._lib.sp_timer_stop(self._h, C.byref(ms)), self._h)
         return ms.value
 
     @property
