@@ -129,7 +129,9 @@ enum {
 /* sp_apply flags */
 enum {
     SP_FLAG_SELF = 1,        /* apply!(...; self=true): add the (p,p,0.0) term after the sweep (core.jl:155-157) */
-    SP_FLAG_STRICT_ORDER = 2 /* accumulate in the reference's order: key_diff order x descending index */
+    SP_FLAG_STRICT_ORDER = 2, /* accumulate in the reference's order: key_diff order x descending index */
+    SP_FLAG_TILE_KERNEL = 4,  /* experimental: shared-memory tile kernel (TMA bulk staging + FP32 pre-filter) */
+    SP_FLAG_PACKED_KERNEL = 8 /* experimental: packed 32-byte records + two-phase compaction through L1 */
 };
 
 /* reductions (diagnostic loops of the examples) */

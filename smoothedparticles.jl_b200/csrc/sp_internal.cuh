@@ -67,6 +67,10 @@ struct sp_system {
     int* h_counters = nullptr;  // pinned mirror
     double* stage = nullptr;    // upload/download staging + reduction scratch
     long long stage_len = 0;    // in doubles
+    void* pk = nullptr;         // 2 x cap packed 32-byte records (default sweep kernel)
+    long long pk_cap = 0;
+    float* ucoord = nullptr;    // 3 planes of FP32 cell-unit coordinates (tile kernel pre-filter)
+    long long ucoord_cap = 0;
     double* dscal = nullptr;    // CG scalars + dot partials (3*1024 + 16 doubles)
     double* h_scal = nullptr;   // pinned mirror of a few scalars
 

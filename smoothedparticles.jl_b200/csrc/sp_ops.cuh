@@ -7,7 +7,10 @@
 //   Acc               accumulators; init() loads the CURRENT value of the p-owned output so the
 //                     accumulation order is the reference's:  ((old + t1) + t2) + ...
 //   active(P,i)       type guard of the closure (skips the whole neighbour loop)
-//   pair(P,p,j,dx,dy,dz,r,acc)   one accepted pair; q fields are read at slot j
+//   NQ, P.qp[NQ]      the q-side Float64 planes the pair body reads (beyond x); the sweep kernels hand
+//                     pair() an accessor q(k) = value of plane k for the current neighbour, read either
+//                     from HBM/L1 (reference-order kernel) or from the staged shared-memory tile
+//   pair(P,p,q,dx,dy,dz,r,acc)    one accepted pair
 //   self(P,p,acc)     the (p,p,0.0) term of apply!(...; self=true)  (core.jl:155-157)
 //   store(P,i,p,acc)  write back p-owned outputs
 #pragma once
@@ -24,9 +27,9 @@ struct WV3 {
 // balance_of_mass!  collapse_dry.jl:112-115, collapse3d.jl:87-90, cavity_flow.jl:92-94 (two_nu = 0)
 template <class K>
 struct OpBalanceOfMass {
+    static constexpr int NQ = 4;  // vx, vy, vz, rho
     struct Params {
-        RV3 v;
-        const double* rho;
+        const double* qp[NQ];
         double* Drho;
         double m, two_nu;
         SpKC kc;
@@ -39,15 +42,16 @@ struct OpBalanceOfMass {
     };
     __device__ static __forceinline__ bool active(const Params&, int) { return true; }
     __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
-        p.vx = P.v.x[i]; p.vy = P.v.y[i]; p.vz = P.v.z[i];
-        p.rho = P.rho[i];
+        p.vx = P.qp[0][i]; p.vy = P.qp[1][i]; p.vz = P.qp[2][i];
+        p.rho = P.qp[3][i];
         a.d = P.Drho[i];
     }
-    __device__ static __forceinline__ void pair(const Params& P, const PS& p, int j, double dx, double dy, double dz,
-                                                double r, Acc& a) {
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, const Q& q, double dx, double dy,
+                                                double dz, double r, Acc& a) {
         double ker = P.m * K::rD(P.kc, r);
-        double dvx = p.vx - P.v.x[j], dvy = p.vy - P.v.y[j], dvz = p.vz - P.v.z[j];
-        a.d += ker * ((dx * dvx + dy * dvy + dz * dvz) + P.two_nu * (p.rho - P.rho[j]));
+        double dvx = p.vx - q(0), dvy = p.vy - q(1), dvz = p.vz - q(2);
+        a.d += ker * ((dx * dvx + dy * dvy + dz * dvz) + P.two_nu * (p.rho - q(3)));
     }
     __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
     __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) { P.Drho[i] = a.d; }
@@ -56,34 +60,36 @@ struct OpBalanceOfMass {
 // internal_force!  collapse_dry.jl:135-141 (3-D: collapse3d.jl:98-104 with the same formula)
 template <class K>
 struct OpInternalForce {
+    // The per-particle quotient P/rho^2 of both p and q is evaluated ONCE per particle by UPressureOverRho2
+    // (same IEEE division as the closure's p.P/p.rho^2, just hoisted out of the pair loop).
+    static constexpr int NQ = 4;  // vx, vy, vz, pr = P/rho^2
     struct Params {
-        RV3 v;
-        const double *P, *rho, *type;
+        const double* qp[NQ];
+        const double* type;
         WV3 Dv;
         double m, visc;  // visc = 2*mu/rho0^2
         SpKC kc;
     };
     struct PS {
-        double vx, vy, vz, pr;  // pr = P_p/rho_p^2
+        double vx, vy, vz, pr;
     };
     struct Acc {
         double x, y, z;
     };
     __device__ static __forceinline__ bool active(const Params& P, int i) { return P.type[i] == 0.0; }
     __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
-        p.vx = P.v.x[i]; p.vy = P.v.y[i]; p.vz = P.v.z[i];
-        double rho = P.rho[i];
-        p.pr = P.P[i] / (rho * rho);
+        p.vx = P.qp[0][i]; p.vy = P.qp[1][i]; p.vz = P.qp[2][i];
+        p.pr = P.qp[3][i];
         a.x = P.Dv.x[i]; a.y = P.Dv.y[i]; a.z = P.Dv.z[i];
     }
-    __device__ static __forceinline__ void pair(const Params& P, const PS& p, int j, double dx, double dy, double dz,
-                                                double r, Acc& a) {
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, const Q& q, double dx, double dy,
+                                                double dz, double r, Acc& a) {
         double ker = P.m * K::rD(P.kc, r);
-        double rq = P.rho[j];
-        double c = -ker * (p.pr + P.P[j] / (rq * rq));
+        double c = -ker * (p.pr + q(3));
         double b = ker * P.visc;
         a.x += c * dx; a.y += c * dy; a.z += c * dz;
-        a.x += b * (p.vx - P.v.x[j]); a.y += b * (p.vy - P.v.y[j]); a.z += b * (p.vz - P.v.z[j]);
+        a.x += b * (p.vx - q(0)); a.y += b * (p.vy - q(1)); a.z += b * (p.vz - q(2));
     }
     __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
     __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) {
@@ -94,9 +100,9 @@ struct OpInternalForce {
 // internal_force!  cavity_flow.jl:102-114 (rDwendland2; lid extrapolation; Monaghan viscosity)
 template <class K>
 struct OpInternalForceCavity {
+    static constexpr int NQ = 6;  // vx, vy, vz, pr = P/rho^2, rho, type
     struct Params {
-        RV3 v;
-        const double *P, *rho, *type;
+        const double* qp[NQ];
         WV3 Dv;
         double m, Re, vlid, ylid, lid, tenth_h, eps;  // eps = 0.01*h^2
         SpKC kc;
@@ -109,22 +115,23 @@ struct OpInternalForceCavity {
     };
     __device__ static __forceinline__ bool active(const Params&, int) { return true; }
     __device__ static __forceinline__ void load(const Params& P, int i, double, double yi, double, PS& p, Acc& a) {
-        p.vx = P.v.x[i]; p.vy = P.v.y[i]; p.vz = P.v.z[i];
-        p.rho = P.rho[i];
-        p.pr = P.P[i] / (p.rho * p.rho);
+        p.vx = P.qp[0][i]; p.vy = P.qp[1][i]; p.vz = P.qp[2][i];
+        p.pr = P.qp[3][i];
+        p.rho = P.qp[4][i];
         p.ay = P.tenth_h + fabs(yi - P.ylid);
         a.x = P.Dv.x[i]; a.y = P.Dv.y[i]; a.z = P.Dv.z[i];
     }
-    __device__ static __forceinline__ void pair(const Params& P, const PS& p, int j, double dx, double dy, double dz,
-                                                double r, Acc& a) {
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, const Q& q, double dx, double dy,
+                                                double dz, double r, Acc& a) {
         double rDk = K::rD(P.kc, r);
-        double vx = p.vx - P.v.x[j], vy = p.vy - P.v.y[j], vz = p.vz - P.v.z[j];
-        if (P.type[j] == P.lid) {
+        double vx = p.vx - q(0), vy = p.vy - q(1), vz = p.vz - q(2);
+        if (q(5) == P.lid) {
             double s = fabs(dy) / p.ay;
             vx = s * (p.vx - P.vlid); vy = s * p.vy; vz = s * p.vz;
         }
-        double rq = P.rho[j];
-        double c = -P.m * rDk * (p.pr + P.P[j] / (rq * rq));
+        double rq = q(4);
+        double c = -P.m * rDk * (p.pr + q(3));
         a.x += c * dx; a.y += c * dy; a.z += c * dz;
         double b = 8.0 / (P.Re * p.rho * rq) * P.m * rDk * (vx * dx + vy * dy + vz * dz) / (r * r + P.eps);
         a.x += b * dx; a.y += b * dy; a.z += b * dz;
@@ -139,7 +146,9 @@ struct OpInternalForceCavity {
 // find_rho! / find_rho0!  :63-69, used with self=true
 template <class K>
 struct OpDensitySum {
+    static constexpr int NQ = 0;
     struct Params {
+        const double* qp[1];
         double* out;
         double m;
         SpKC kc;
@@ -152,7 +161,8 @@ struct OpDensitySum {
     __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS&, Acc& a) {
         a.d = P.out[i];
     }
-    __device__ static __forceinline__ void pair(const Params& P, const PS&, int, double, double, double, double r,
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS&, const Q&, double, double, double, double r,
                                                 Acc& a) {
         a.d += P.m * K::w(P.kc, r);
     }
@@ -163,8 +173,9 @@ struct OpDensitySum {
 // internal_force!  test_collision_2d.jl:75-78
 template <class K>
 struct OpInternalForceSym {
+    static constexpr int NQ = 1;  // P
     struct Params {
-        const double* P;
+        const double* qp[NQ];
         WV3 a;
         double m, inv_rho0sq;
         SpKC kc;
@@ -177,13 +188,14 @@ struct OpInternalForceSym {
     };
     __device__ static __forceinline__ bool active(const Params&, int) { return true; }
     __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
-        p.pr = P.P[i] * P.inv_rho0sq;
+        p.pr = P.qp[0][i] * P.inv_rho0sq;
         a.x = P.a.x[i]; a.y = P.a.y[i]; a.z = P.a.z[i];
     }
-    __device__ static __forceinline__ void pair(const Params& P, const PS& p, int j, double dx, double dy, double dz,
-                                                double r, Acc& a) {
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, const Q& q, double dx, double dy,
+                                                double dz, double r, Acc& a) {
         double ker = P.m * K::rD(P.kc, r);
-        double c = -ker * (p.pr + P.P[j] * P.inv_rho0sq);
+        double c = -ker * (p.pr + q(0) * P.inv_rho0sq);
         a.x += c * dx; a.y += c * dy; a.z += c * dz;
     }
     __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
@@ -196,8 +208,9 @@ struct OpInternalForceSym {
 // viscous_force!  :128-130
 template <class K>
 struct OpIsphViscous {
+    static constexpr int NQ = 3;  // vx, vy, vz
     struct Params {
-        RV3 v;
+        const double* qp[NQ];
         WV3 Dv;
         double coef;  // 2*m*mu/rho^2
         SpKC kc;
@@ -210,13 +223,14 @@ struct OpIsphViscous {
     };
     __device__ static __forceinline__ bool active(const Params&, int) { return true; }
     __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
-        p.vx = P.v.x[i]; p.vy = P.v.y[i]; p.vz = P.v.z[i];
+        p.vx = P.qp[0][i]; p.vy = P.qp[1][i]; p.vz = P.qp[2][i];
         a.x = P.Dv.x[i]; a.y = P.Dv.y[i]; a.z = P.Dv.z[i];
     }
-    __device__ static __forceinline__ void pair(const Params& P, const PS& p, int j, double, double, double, double r,
-                                                Acc& a) {
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, const Q& q, double, double, double,
+                                                double r, Acc& a) {
         double c = P.coef * K::rD(P.kc, r);
-        a.x += c * (p.vx - P.v.x[j]); a.y += c * (p.vy - P.v.y[j]); a.z += c * (p.vz - P.v.z[j]);
+        a.x += c * (p.vx - q(0)); a.y += c * (p.vy - q(1)); a.z += c * (p.vz - q(2));
     }
     __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
     __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) {
@@ -227,8 +241,9 @@ struct OpIsphViscous {
 // div_L_lambda!  :147-152
 template <class K>
 struct OpIsphDivLLambda {
+    static constexpr int NQ = 3;  // vx, vy, vz
     struct Params {
-        RV3 v;
+        const double* qp[NQ];
         double *div, *L, *lambda;
         double m, m_over_rho, inv_dim;
         SpKC kc;
@@ -241,13 +256,14 @@ struct OpIsphDivLLambda {
     };
     __device__ static __forceinline__ bool active(const Params&, int) { return true; }
     __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
-        p.vx = P.v.x[i]; p.vy = P.v.y[i]; p.vz = P.v.z[i];
+        p.vx = P.qp[0][i]; p.vy = P.qp[1][i]; p.vz = P.qp[2][i];
         a.div = P.div[i]; a.L = P.L[i]; a.lam = P.lambda[i];
     }
-    __device__ static __forceinline__ void pair(const Params& P, const PS& p, int j, double dx, double dy, double dz,
-                                                double r, Acc& a) {
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, const Q& q, double dx, double dy,
+                                                double dz, double r, Acc& a) {
         double rDk = K::rD(P.kc, r);
-        double dvx = p.vx - P.v.x[j], dvy = p.vy - P.v.y[j], dvz = p.vz - P.v.z[j];
+        double dvx = p.vx - q(0), dvy = p.vy - q(1), dvz = p.vz - q(2);
         a.div += -(dx * dvx + dy * dvy + dz * dvz) * P.m * rDk;
         a.L += -2.0 * P.m_over_rho * rDk;
         a.lam += P.m_over_rho * rDk * (r * r) * P.inv_dim;
@@ -261,8 +277,9 @@ struct OpIsphDivLLambda {
 // internal_force!  :132-134
 template <class K>
 struct OpIsphInternalForce {
+    static constexpr int NQ = 1;  // P
     struct Params {
-        const double* P;
+        const double* qp[NQ];
         WV3 Dv;
         double coef;  // m/rho^2
         SpKC kc;
@@ -275,12 +292,13 @@ struct OpIsphInternalForce {
     };
     __device__ static __forceinline__ bool active(const Params&, int) { return true; }
     __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
-        p.P = P.P[i];
+        p.P = P.qp[0][i];
         a.x = P.Dv.x[i]; a.y = P.Dv.y[i]; a.z = P.Dv.z[i];
     }
-    __device__ static __forceinline__ void pair(const Params& P, const PS& p, int j, double dx, double dy, double dz,
-                                                double r, Acc& a) {
-        double c = P.coef * K::rD(P.kc, r) * (p.P + P.P[j]);
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, const Q& q, double dx, double dy,
+                                                double dz, double r, Acc& a) {
+        double c = P.coef * K::rD(P.kc, r) * (p.P + q(0));
         a.x -= c * dx; a.y -= c * dy; a.z -= c * dz;
     }
     __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
@@ -293,8 +311,10 @@ struct OpIsphInternalForce {
 //   y_i = A_ii p_i + sum_{j != i} (2 h^2 m/rho) rDk(r_ij) p_j,   A_ii = h^2 L_i + [type_i==0] C_free max(lambda_i,0)
 template <class K>
 struct OpPoissonApply {
+    static constexpr int NQ = 1;  // p_in
     struct Params {
-        const double *L, *lambda, *type, *pin;
+        const double* qp[NQ];
+        const double *L, *lambda, *type;
         double* y;
         double off_coef;  // 2*h^2*m/rho
         double h2, C_free;
@@ -310,12 +330,13 @@ struct OpPoissonApply {
     __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
         double Aii = P.h2 * P.L[i];
         if (P.type[i] == 0.0) Aii += P.C_free * fmax(P.lambda[i], 0.0);
-        p.diag = Aii * P.pin[i];
+        p.diag = Aii * P.qp[0][i];
         a.s = 0.0;
     }
-    __device__ static __forceinline__ void pair(const Params& P, const PS&, int j, double, double, double, double r,
-                                                Acc& a) {
-        a.s += P.off_coef * K::rD(P.kc, r) * P.pin[j];
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS&, const Q& q, double, double, double,
+                                                double r, Acc& a) {
+        a.s += P.off_coef * K::rD(P.kc, r) * q(0);
     }
     __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
     __device__ static __forceinline__ void store(const Params& P, int i, const PS& p, const Acc& a) {
@@ -324,6 +345,17 @@ struct OpPoissonApply {
 };
 
 // ---------------------------------------------------------------- unary operators
+// pr = P/rho^2, the per-particle quotient of internal_force! (collapse_dry.jl:138, cavity_flow.jl:112)
+struct UPressureOverRho2 {
+    struct Params {
+        const double *P, *rho;
+        double* pr;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        double rho = P.rho[i];
+        P.pr[i] = P.P[i] / (rho * rho);
+    }
+};
 // find_pressure!  collapse_dry.jl:123-127, cavity_flow.jl:96-100
 struct UFindPressure {
     struct Params {

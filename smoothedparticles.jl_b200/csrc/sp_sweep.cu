@@ -10,12 +10,18 @@
 // contiguous slot range; the default order walks those 3 (2-D) / 9 (3-D) ranges, SP_FLAG_STRICT_ORDER
 // walks the 9/27 cells in key_diff order (di outermost), which with the descending in-cell order is
 // exactly the reference's accumulation order.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
 #include "sp_internal.cuh"
 #include "sp_ops.cuh"
 
 struct SweepCtx {
     const double *x, *y, *z;
+    const float *ux, *uy, *uz;  // cell-unit FP32 coordinates (x - lo)/h for the conservative pre-filter
     const int* cell_start;
+    float thr;                  // pre-filter threshold on the FP32 squared distance in cell units
     int n;
 };
 
@@ -55,6 +61,18 @@ __device__ __forceinline__ void sp_for_candidates(const SpGrid& g, const SweepCt
     }
 }
 
+// q-field accessor of the reference-order kernel: plane k of the neighbour at slot j, through L1/L2
+template <int NQ>
+struct QGlobal {
+    const double* const* qp;
+    int j;
+    __device__ __forceinline__ double operator()(int k) const { return qp[k][j]; }
+};
+
+// ---- reference-order kernel (SP_FLAG_STRICT_ORDER, and the parity views): one thread per particle,
+// candidates read straight from the sorted planes.
+__device__ __forceinline__ double sp_sqrt_fast(double a);
+
 template <class Op, bool STRICT>
 __global__ void __launch_bounds__(128) k_sweep(SpGrid g, SweepCtx c, typename Op::Params P, int self_flag) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -67,9 +85,482 @@ __global__ void __launch_bounds__(128) k_sweep(SpGrid g, SweepCtx c, typename Op
     sp_for_candidates<STRICT>(g, c, xi, yi, zi, [&](int j, double dx, double dy, double dz, double d2) {
         // (r > h || p == q) && continue   (core.jl:105), r = sqrt_rn(d2)  <=>  d2 > T2
         if (d2 > g.T2 || j == i) return;
-        Op::pair(P, p, j, dx, dy, dz, sqrt(d2), acc);
+        QGlobal<Op::NQ> q{P.qp, j};
+        Op::pair(P, p, q, dx, dy, dz, STRICT ? sqrt(d2) : sp_sqrt_fast(d2), acc);
     });
-    if (self_flag) Op::self(P, p, acc);
+    if (self_flag & 1) Op::self(P, p, acc);
+    Op::store(P, i, p, acc);
+}
+
+// ---- tile kernel (default path).
+// A CTA owns TP consecutive slots of the cell-sorted planes (its targets, one per thread).  For each of
+// the 3 (2-D) / 9 (3-D) stencil rows the candidates of ALL its targets form one contiguous slot range;
+// the ranges are cut into segments and staged, batch by batch, into shared memory as SoA Float64 planes
+// (x, y, z + the NQ planes the operator reads of q) by TMA 1-D bulk copies (cp.async.bulk -> UBLKCP)
+// completing on an mbarrier: every plane segment is contiguous in HBM, so one elected thread issues
+// nseg*(3+NQ) bulk copies and the LSU pipe stays free.  Per batch:
+//   phase 1  every thread walks its own cells' sub-range of each staged segment, evaluates the exact
+//            un-fused distance predicate (4 candidates in flight), and appends accepted candidates
+//            (16-bit tile index) to a private list in shared memory — a tight, branch-free loop;
+//   phase 2  every thread runs the operator body over its list — the expensive part (sqrt, kernel, FMAs)
+//            executes with nearly all lanes active instead of ~15 % of them.
+// Any density works: a row that does not fit is split over several batches, a list that fills is flushed.
+#define TILE_MAX_SEG 16
+struct TileSeg {
+    int pos;   // first global slot staged (even: 16-byte aligned for the bulk copy)
+    int cnt;   // slots staged (even)
+    int soff;  // offset of the segment in the tile (even)
+    int row;   // stencil row index (0..8)
+};
+
+__device__ __forceinline__ unsigned sp_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sp_mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sp_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void sp_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sp_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sp_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     sp_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(sp_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void sp_mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(sp_smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+template <int NQ, int CAP>
+struct QTile {
+    const double* sq;  // [NQ][CAP] planes of the current buffer, already offset by the tile index
+    __device__ __forceinline__ double operator()(int k) const { return sq[k * CAP]; }
+};
+
+// r = sqrt(d2) for the operator bodies of the tile kernel: MUFU.RSQ64H seed + two Newton steps, ~1 ulp,
+// branch-free (the neighbour DECISION never uses it: that is the exact d2 > T2 test).
+__device__ __forceinline__ double sp_sqrt_fast(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double h = 0.5 * a;
+    y = y * fma(-h, y * y, 1.5);
+    y = y * fma(-h, y * y, 1.5);
+    const double r = a * y;
+    return a > 0.0 ? r : 0.0;  // coincident particles: r = 0 (rsqrt(0) = inf)
+}
+
+template <class Op, int TP, int LCAP, int CAPB, int NROWS, int RPB, int MINB>
+__global__ void __launch_bounds__(TP, MINB) k_sweep_tile(SpGrid g, SweepCtx c, typename Op::Params P, int self_flag) {
+    constexpr int NQ = Op::NQ;
+    constexpr int NPL = 6 + NQ;                                    // planes per buffer: 3+NQ doubles, 3 floats
+    constexpr size_t BUF_BYTES = (size_t)CAPB * ((3 + NQ) * 8 + 12);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned short* list = reinterpret_cast<unsigned short*>(smem_raw + 2 * BUF_BYTES);  // [LCAP][TP]
+    __shared__ TileSeg segs[2][TILE_MAX_SEG];
+    __shared__ int s_nseg[2], s_fill[2];
+    __shared__ int s_rowpos[NROWS], s_rowend[NROWS];
+    __shared__ long long s_kmin, s_kmax;
+    __shared__ int s_any;
+    __shared__ __align__(8) unsigned long long s_bar[2];
+
+    const int tid = threadIdx.x;
+    const int i = blockIdx.x * TP + tid;
+    const bool act = (i < c.n) && Op::active(P, i);
+    double xi = 0.0, yi = 0.0, zi = 0.0;
+    float ui = 0.f, vi = 0.f, wi = 0.f;
+    long long key = 0;
+    typename Op::PS p;
+    typename Op::Acc acc;
+    if (tid == 0) {
+        s_kmin = 0x7fffffffffffffffLL;
+        s_kmax = -0x7fffffffffffffffLL;
+        s_any = 0;
+        sp_mbar_init(&s_bar[0], 1);
+        sp_mbar_init(&s_bar[1], 1);
+    }
+    __syncthreads();
+    if (act) {
+        xi = c.x[i]; yi = c.y[i]; zi = c.z[i];
+        ui = c.ux[i]; vi = c.uy[i]; wi = c.uz[i];
+        key = sp_find_key(g, xi, yi, zi);  // core.jl:95
+    }
+    {
+        // key span of the active targets: warp reduction, then one shared atomic per warp
+        long long kmn = act ? key : 0x7fffffffffffffffLL, kmx = act ? key : -0x7fffffffffffffffLL;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const long long a = __shfl_xor_sync(0xffffffffu, kmn, d), b = __shfl_xor_sync(0xffffffffu, kmx, d);
+            kmn = a < kmn ? a : kmn;
+            kmx = b > kmx ? b : kmx;
+        }
+        if ((tid & 31) == 0 && kmn <= kmx) {
+            atomicMin(&s_kmin, kmn);
+            atomicMax(&s_kmax, kmx);
+            s_any = 1;
+        }
+    }
+    // own candidate slot range of every stencil row (registers; rows are unrolled at compile time)
+    const long long L1 = g.lim[0], L12 = g.lim[0] * g.lim[1];
+    int jb[NROWS], je[NROWS];
+#pragma unroll
+    for (int row = 0; row < NROWS; row++) {
+        const int dj = row % 3 - 1, dk = (NROWS == 3) ? 0 : row / 3 - 1;
+        const long long mid = key + L1 * dj + L12 * dk;
+        long long klo = mid - 1, khi = mid + 1;
+        if (klo < 1) klo = 1;
+        if (khi > g.key_max) khi = g.key_max;
+        jb[row] = je[row] = 0;
+        if (act && klo <= khi) {
+            jb[row] = c.cell_start[klo];
+            je[row] = c.cell_start[khi + 1];
+        }
+    }
+    if (act) Op::load(P, i, xi, yi, zi, p, acc);
+    __syncthreads();
+    if (!s_any) return;  // e.g. a block of wall particles under a fluid-only operator
+    // slot span of the whole block for every row: NROWS threads fetch them concurrently
+    if (tid < NROWS) {
+        const int dj = tid % 3 - 1, dk = (NROWS == 3) ? 0 : tid / 3 - 1;
+        long long klo = s_kmin - 1 + L1 * dj + L12 * dk, khi = s_kmax + 1 + L1 * dj + L12 * dk;
+        if (klo < 1) klo = 1;
+        if (khi > g.key_max) khi = g.key_max;
+        int a = 0, b = 0;
+        if (klo <= khi) {
+            a = c.cell_start[klo];
+            b = c.cell_start[khi + 1];
+        }
+        s_rowpos[tid] = a;
+        s_rowend[tid] = b;
+    }
+    __syncthreads();
+
+    const double T2 = g.T2;
+    const float thr = c.thr;
+    unsigned short* lp = list + tid;  // next free list entry of this thread
+    int self_s = -1;                  // tile index of p itself in the current batch
+    double *sx, *sy, *sz, *sq;        // planes of the buffer being processed
+    float *fx, *fy, *fz;
+    auto set_buf = [&](int b) {
+        sx = reinterpret_cast<double*>(smem_raw + (size_t)b * BUF_BYTES);
+        sy = sx + CAPB;
+        sz = sy + CAPB;
+        sq = sz + CAPB;
+        fx = reinterpret_cast<float*>(sq + (size_t)NQ * CAPB);
+        fy = fx + CAPB;
+        fz = fy + CAPB;
+    };
+
+    // ---- phase 2: exact un-fused predicate (core.jl:104-105) and the operator body, 4 list entries at a time,
+    // branch-free: rejected / padding entries are computed and then discarded by a select.
+    auto flush = [&]() {
+        const int cnt = (int)((lp - (list + tid)) / TP);
+        lp = list + tid;
+        if (self_flag & 256) return;
+        for (int k = 0; k < cnt; k += 4) {
+            int s4[4];
+            bool ok[4];
+            double dx[4], dy[4], dz[4], d2[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                ok[u] = (k + u) < cnt;
+                s4[u] = ok[u] ? (int)list[(k + u) * TP + tid] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                dx[u] = __dsub_rn(xi, sx[s4[u]]);
+                dy[u] = __dsub_rn(yi, sy[s4[u]]);
+                dz[u] = __dsub_rn(zi, sz[s4[u]]);
+                d2[u] = sp_d2(dx[u], dy[u], dz[u]);
+                // (r > h || p == q) && continue  <=>  d2 > T2 with r = sqrt_rn(d2)
+                ok[u] = ok[u] && !(d2[u] > T2) && s4[u] != self_s;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                typename Op::Acc t = acc;
+                QTile<NQ, CAPB> q{sq + s4[u]};
+                Op::pair(P, p, q, dx[u], dy[u], dz[u], sp_sqrt_fast(d2[u]), t);
+                if (ok[u]) acc = t;
+            }
+        }
+    };
+
+    // ---- batch planner (block-uniform): up to RPB stencil rows, or as much of them as fits one buffer
+    int row = 0, pos = 0;
+    auto plan = [&](int b) -> int {
+        int fill = 0, nseg = 0;
+        while (row < NROWS && nseg == 0) {  // skip row groups without candidates
+            const int row_stop = min(NROWS, (row / RPB + 1) * RPB);
+            while (row < row_stop && nseg < TILE_MAX_SEG) {
+                const int rend = s_rowend[row];
+                if (pos < s_rowpos[row]) pos = s_rowpos[row];
+                if (pos >= rend) {
+                    row++;
+                    pos = 0;
+                    continue;
+                }
+                const int room = (CAPB - fill) & ~3;
+                if (room < 8) break;
+                const int pos_al = pos & ~3;                // 16-byte aligned sources for the 8 B and 4 B planes
+                const int want = (rend - pos_al + 3) & ~3;  // multiple of 4 slots
+                const int take = min(want, room);
+                if (tid == 0) segs[b][nseg] = TileSeg{pos_al, take, fill, row};
+                nseg++;
+                fill += take;
+                pos = pos_al + take;
+            }
+        }
+        if (tid == 0) {
+            s_nseg[b] = nseg;
+            s_fill[b] = fill;
+        }
+        return nseg;
+    };
+    // TMA bulk copies of one batch: one per (segment, plane), spread over the lanes of warp 0
+    auto issue = [&](int b, int nseg, int fill) {
+        if (tid < 32) {
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                sp_mbar_expect_tx(&s_bar[b], (unsigned)fill * ((3 + NQ) * 8u + 12u));
+            }
+            __syncwarp();
+            unsigned char* base = smem_raw + (size_t)b * BUF_BYTES;
+            for (int w = tid; w < nseg * NPL; w += 32) {
+                const int sgi = w / NPL, pl = w % NPL;
+                const TileSeg sg = segs[b][sgi];
+                if (pl < 3 + NQ) {
+                    const double* src = pl == 0 ? c.x : pl == 1 ? c.y : c.z;
+#pragma unroll
+                    for (int k = 0; k < NQ; k++)
+                        if (pl == 3 + k) src = P.qp[k];  // static indices: keeps Params in the constant bank
+                    sp_bulk_g2s(reinterpret_cast<double*>(base) + (size_t)pl * CAPB + sg.soff, src + sg.pos,
+                                (unsigned)sg.cnt * 8u, &s_bar[b]);
+                } else {
+                    const int f = pl - (3 + NQ);
+                    const float* src = f == 0 ? c.ux : f == 1 ? c.uy : c.uz;
+                    sp_bulk_g2s(reinterpret_cast<float*>(base + (size_t)(3 + NQ) * CAPB * 8) + (size_t)f * CAPB + sg.soff,
+                                src + sg.pos, (unsigned)sg.cnt * 4u, &s_bar[b]);
+                }
+            }
+        }
+    };
+
+    int cur = 0;
+    unsigned parity[2] = {0u, 0u};
+    int nseg_cur = plan(0);
+    __syncthreads();  // segs[0] visible to warp 0
+    if (nseg_cur) issue(0, nseg_cur, s_fill[0]);
+    while (nseg_cur) {
+        // prefetch the next batch into the other buffer (it was released by the barrier ending the last round)
+        const int nseg_next = plan(cur ^ 1);
+        __syncthreads();  // segs[cur^1] visible; also orders this round after the previous flush
+        if (nseg_next) issue(cur ^ 1, nseg_next, s_fill[cur ^ 1]);
+        sp_mbar_wait(&s_bar[cur], parity[cur]);
+        parity[cur] ^= 1u;
+        set_buf(cur);
+        if (act && !(self_flag & 512)) {
+            self_s = -1;
+            int sgi = 0;
+#pragma unroll
+            for (int r = 0; r < NROWS; r++) {
+                while (sgi < nseg_cur && segs[cur][sgi].row == r) {
+                    const TileSeg sg = segs[cur][sgi];
+                    sgi++;
+                    const int lo = max(jb[r], sg.pos), hi = min(je[r], sg.pos + sg.cnt);
+                    if (lo >= hi) continue;
+                    const int shift = sg.soff - sg.pos;
+                    if (r == NROWS / 2 && i >= lo && i < hi) self_s = i + shift;
+                    // ---- phase 1: conservative FP32 pre-filter, 4 candidates per 128-bit shared load
+                    int s_lo = lo + shift;
+                    const int s_hi = hi + shift;
+                    while (s_lo < s_hi) {
+                        int s_end = s_hi;
+                        const int have = (int)((lp - (list + tid)) / TP);
+                        if (have + (s_end - s_lo) > LCAP) {
+                            if (have > 0) {
+                                flush();
+                                continue;
+                            }
+                            s_end = s_lo + LCAP;
+                        }
+#pragma unroll 2
+                        for (int gs = s_lo & ~3; gs < s_end; gs += 4) {
+                            const float4 qx = *reinterpret_cast<const float4*>(fx + gs);
+                            const float4 qy = *reinterpret_cast<const float4*>(fy + gs);
+                            const float4 qz = *reinterpret_cast<const float4*>(fz + gs);
+                            const float ax[4] = {qx.x, qx.y, qx.z, qx.w}, ay[4] = {qy.x, qy.y, qy.z, qy.w},
+                                        az[4] = {qz.x, qz.y, qz.z, qz.w};
+                            int pass[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const float ddx = ui - ax[u], ddy = vi - ay[u], ddz = wi - az[u];
+                                const float dd = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx));
+                                const int s = gs + u;
+                                // !(d2 > thr) keeps NaN distances, which the reference also lets through
+                                pass[u] = (!(dd > thr) && s >= s_lo && s < s_end) ? 1 : 0;
+                            }
+                            const int o1 = pass[0], o2 = o1 + pass[1], o3 = o2 + pass[2];
+                            if (pass[0]) lp[0] = (unsigned short)gs;
+                            if (pass[1]) lp[o1 * TP] = (unsigned short)(gs + 1);
+                            if (pass[2]) lp[o2 * TP] = (unsigned short)(gs + 2);
+                            if (pass[3]) lp[o3 * TP] = (unsigned short)(gs + 3);
+                            lp += (o3 + pass[3]) * TP;
+                        }
+                        s_lo = s_end;
+                    }
+                }
+            }
+            flush();
+        }
+        __syncthreads();  // everyone is done with buffer `cur` and its segment table before they are re-planned
+        cur ^= 1;
+        nseg_cur = nseg_next;
+    }
+    if (act) {
+        if (self_flag & 1) Op::self(P, p, acc);
+        Op::store(P, i, p, acc);
+    }
+}
+
+// ---- packed-record kernel (default path).
+// One thread per target, candidates read through L1 — but from two 32-byte records per particle that a
+// prep pass packs from the SoA planes:  pk0 = {x, y, z, qa}  pk1 = {q0, q1, q2, qb}, so a candidate test costs
+// ONE 256-bit load (LDG.E.256) instead of three 64-bit loads from three planes (the reference-order kernel is
+// bound by L1 wavefronts: 90 % in the round-1 baseline profile).  The sweep is split in two phases:
+//   phase 1  exact un-fused predicate over the 3/9 row ranges; accepted slots are appended to a private
+//            list in shared memory — a short branch-light loop;
+//   phase 2  the operator body (sqrt, kernel, FMAs) over the list, so the expensive part runs with nearly all
+//            lanes active instead of the ~15 % hit rate of the candidate loop.
+// Lanes of one cell share most neighbours, so phase-2 gathers touch only a few 128-byte lines per request.
+struct __align__(32) SpRec {
+    double a, b, c, d;
+};
+__device__ __forceinline__ SpRec sp_ld256(const SpRec* p) {
+    // two 128-bit read-only loads that allocate in L1.  (A single ld.global.nc.v4.f64 = LDG.E.ENL2.256 was
+    // measured to bypass L1 on sm_100a: 7 % L1 hit rate, every candidate a trip to L2 — profiles/r1_notes.md.)
+    const double2 lo = __ldg(reinterpret_cast<const double2*>(p));
+    const double2 hi = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    return SpRec{lo.x, lo.y, hi.x, hi.y};
+}
+// which record component carries q-plane k (see k_pack)
+template <int NQ>
+struct QPacked {
+    const double* const* qp;
+    SpRec r0, r1;
+    int j;
+    __device__ __forceinline__ double operator()(int k) const {
+        if (NQ == 1) return r0.d;
+        if (k < 3) return k == 0 ? r1.a : k == 1 ? r1.b : r1.c;
+        if (k == 3) return r0.d;
+        if (k == 4) return r1.d;
+        return qp[k][j];
+    }
+};
+template <int NQ>
+struct PackPlanes {
+    const double* qp[NQ > 0 ? NQ : 1];
+};
+template <int NQ>
+__global__ void __launch_bounds__(256) k_pack(const double* __restrict__ x, long long cap, PackPlanes<NQ> pl,
+                                              SpRec* __restrict__ pk0, SpRec* __restrict__ pk1, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    SpRec a{x[i], x[cap + i], x[2 * cap + i], 0.0};
+    if (NQ == 1) a.d = pl.qp[0][i];
+    if (NQ >= 4) a.d = pl.qp[3][i];
+    pk0[i] = a;
+    if (NQ >= 2) {
+        SpRec b{pl.qp[0][i], pl.qp[1][i], NQ >= 3 ? pl.qp[2 < NQ ? 2 : 0][i] : 0.0, NQ >= 5 ? pl.qp[4 < NQ ? 4 : 0][i] : 0.0};
+        pk1[i] = b;
+    }
+}
+
+template <class Op, int TP, int LCAP>
+__global__ void __launch_bounds__(TP) k_sweep_pk(SpGrid g, SweepCtx c, typename Op::Params P, const SpRec* __restrict__ pk0,
+                                                 const SpRec* __restrict__ pk1, int self_flag) {
+    constexpr int NQ = Op::NQ;
+    extern __shared__ int list[];  // [LCAP][TP]
+    const int tid = threadIdx.x;
+    const int i = blockIdx.x * TP + tid;
+    if (i >= c.n) return;
+    if (!Op::active(P, i)) return;
+    const SpRec me = sp_ld256(pk0 + i);
+    const double xi = me.a, yi = me.b, zi = me.c;
+    typename Op::PS p;
+    typename Op::Acc acc;
+    Op::load(P, i, xi, yi, zi, p, acc);
+    const double T2 = g.T2;
+    int cnt = 0;
+    auto flush = [&]() {
+        for (int k = 0; k < cnt; k += 2) {
+            // two list entries in flight (the second may be padding: computed, then discarded)
+            const bool two = (k + 1) < cnt;
+            QPacked<NQ> q[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                q[u].qp = P.qp;
+                q[u].j = list[((u == 1 && !two) ? k : k + u) * TP + tid];
+                q[u].r0 = sp_ld256(pk0 + q[u].j);
+                if (NQ >= 2) q[u].r1 = sp_ld256(pk1 + q[u].j);
+            }
+            double dx[2], dy[2], dz[2], r[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                dx[u] = __dsub_rn(xi, q[u].r0.a);
+                dy[u] = __dsub_rn(yi, q[u].r0.b);
+                dz[u] = __dsub_rn(zi, q[u].r0.c);
+                r[u] = sp_sqrt_fast(sp_d2(dx[u], dy[u], dz[u]));
+            }
+            Op::pair(P, p, q[0], dx[0], dy[0], dz[0], r[0], acc);
+            typename Op::Acc t = acc;
+            Op::pair(P, p, q[1], dx[1], dy[1], dz[1], r[1], t);
+            if (two) acc = t;
+        }
+        cnt = 0;
+    };
+    const long long key = sp_find_key(g, xi, yi, zi);  // core.jl:95 recomputes the key from the current x
+    const long long L1 = g.lim[0], L12 = g.lim[0] * g.lim[1];
+    const int nk = (g.dim == 2) ? 0 : 1;
+    for (int dk = -nk; dk <= nk; dk++)
+        for (int dj = -1; dj <= 1; dj++) {
+            const long long mid = key + L1 * dj + L12 * dk;
+            long long klo = mid - 1, khi = mid + 1;
+            if (klo < 1) klo = 1;
+            if (khi > g.key_max) khi = g.key_max;
+            if (klo > khi) continue;
+            const int jb = c.cell_start[klo], je = c.cell_start[khi + 1];
+            for (int j0 = jb; j0 < je; j0 += LCAP) {
+                const int j1 = min(je, j0 + LCAP);
+                if (cnt + (j1 - j0) > LCAP) flush();
+                for (int j = j0; j < j1; j += 4) {
+                    // 4 independent candidates in flight: all loads first, then the exact tests
+                    SpRec r[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) r[u] = sp_ld256(pk0 + min(j + u, j1 - 1));
+                    bool hit[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const double dx = __dsub_rn(xi, r[u].a), dy = __dsub_rn(yi, r[u].b), dz = __dsub_rn(zi, r[u].c);
+                        // (r > h || p == q) && continue   (core.jl:105)  <=>  d2 > T2 with r = sqrt_rn(d2)
+                        hit[u] = !(sp_d2(dx, dy, dz) > T2) && (j + u) != i && (j + u) < j1;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (hit[u]) {
+                            list[cnt * TP + tid] = j + u;
+                            cnt++;
+                        }
+                }
+            }
+        }
+    flush();
+    if (self_flag & 1) Op::self(P, p, acc);
     Op::store(P, i, p, acc);
 }
 
@@ -77,6 +568,41 @@ template <class U>
 __global__ void __launch_bounds__(256) k_unary(typename U::Params P, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) U::apply(P, i);
+}
+
+#define TILE_TP 128
+#define TILE_LCAP 40
+#define TILE_RPB 3                     /* stencil rows per batch (3-D: 3 batches of 3 rows; 2-D: 1 row each) */
+#define TILE_CAPB3 (3 * (TILE_TP + 24)) /* slots per buffer, 3-D */
+#define TILE_CAPB2 (TILE_TP + 96)       /* slots per buffer, 2-D (rows are ~3x longer per cell) */
+
+// FP32 cell-unit coordinates u = (x - lo)/h of every slot, the input of the tile kernel's pre-filter.
+__global__ void __launch_bounds__(256) k_prefilter_coords(SpGrid g, const double* __restrict__ x, long long cap,
+                                                          float* __restrict__ u, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double ih = 1.0 / g.h;
+    u[i] = (float)((x[i] - g.lo[0]) * ih);
+    u[cap + i] = (float)((x[cap + i] - g.lo[1]) * ih);
+    u[2 * cap + i] = (float)((x[2 * cap + i] - g.lo[2]) * ih);
+}
+
+template <class Op, int CAPB, int NROWS, int RPB>
+static int launch_tile(sp_system* s, const SweepCtx& c, const typename Op::Params& P, int self_flag) {
+    const size_t buf = (size_t)CAPB * ((3 + Op::NQ) * sizeof(double) + 3 * sizeof(float));
+    const size_t smem = 2 * buf + (size_t)TILE_LCAP * TILE_TP * sizeof(unsigned short);
+    constexpr int MINB = 3;
+    auto kern = k_sweep_tile<Op, TILE_TP, TILE_LCAP, CAPB, NROWS, RPB, MINB>;
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        SP_CUDA(s, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    kern<<<sp_blocks(s->n, TILE_TP), TILE_TP, smem, s->stream>>>(s->g, c, P, self_flag);
+    s->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return sp_fail_cuda(s, e, "k_sweep_tile", __FILE__, __LINE__);
+    return SP_OK;
 }
 
 template <class Op>
@@ -89,11 +615,55 @@ static int launch_sweep(sp_system* s, const typename Op::Params& P, int flags) {
     c.z = X + 2 * s->cap;
     c.cell_start = s->cell_start;
     c.n = (int)s->n;
-    const int self_flag = (flags & SP_FLAG_SELF) ? 1 : 0;
-    if (flags & SP_FLAG_STRICT_ORDER)
+    int self_flag = (flags & SP_FLAG_SELF) ? 1 : 0;
+    if (const char* dbg = getenv("SP_DEBUG_SWEEP")) self_flag |= atoi(dbg) << 8;  // profiling switches only
+    if (flags & SP_FLAG_STRICT_ORDER) {
         SP_LAUNCH(s, (k_sweep<Op, true>), sp_blocks(s->n, 128), 128, 0, s->g, c, P, self_flag);
-    else
+        return SP_OK;
+    }
+    if ((flags & SP_FLAG_TILE_KERNEL) || getenv("SP_SWEEP_TILE")) {
+        // experimental shared-memory tile kernel (TMA-staged, FP32 pre-filter): see DESIGN.md, round-2 work.
+        // pre-filter inputs: FP32 coordinates in cell units and a threshold that can never reject a true neighbour.
+        // |u| <= U = max key_lim + 2; rounding x -> u costs <= U*2^-24 per coordinate, the FP32 difference and the
+        // three products/sums a few 2^-24 relative more: d2_f32 <= d2/h^2 + 8*2^-23*U + 1e-6 for d2 <= h^2.
+        if (!s->ucoord || s->ucoord_cap != s->cap) {
+            if (s->ucoord) SP_CUDA(s, cudaFree(s->ucoord));
+            s->ucoord = nullptr;
+            SP_CUDA(s, cudaMalloc(&s->ucoord, (size_t)3 * s->cap * sizeof(float)));
+            s->ucoord_cap = s->cap;
+        }
+        SP_LAUNCH(s, k_prefilter_coords, sp_blocks(s->n, 256), 256, 0, s->g, X, s->cap, s->ucoord, s->n);
+        c.ux = s->ucoord;
+        c.uy = s->ucoord + s->cap;
+        c.uz = s->ucoord + 2 * s->cap;
+        const double U = (double)std::max(std::max(s->g.lim[0], s->g.lim[1]), s->g.lim[2]) + 2.0;
+        c.thr = (float)(1.0 + 8.0 * U / 8388608.0 + 1e-6);
+        c.thr = std::nextafter(c.thr, 2.0f);
+        if (s->g.dim == 2) return launch_tile<Op, TILE_CAPB2, 3, 1>(s, c, P, self_flag);
+        return launch_tile<Op, TILE_CAPB3, 9, TILE_RPB>(s, c, P, self_flag);
+    }
+    static const int variant = getenv("SP_SWEEP_VARIANT") ? atoi(getenv("SP_SWEEP_VARIANT")) : 0;
+    if (variant == 0 && !(flags & SP_FLAG_PACKED_KERNEL)) {
+        // default: one thread per target over the sorted SoA planes (L1-resident candidate rows)
         SP_LAUNCH(s, (k_sweep<Op, false>), sp_blocks(s->n, 128), 128, 0, s->g, c, P, self_flag);
+        return SP_OK;
+    }
+    // SP_FLAG_PACKED_KERNEL: packed-record two-phase kernel (experimental, see profiles/r1_sweep_exploration.md)
+    if (!s->pk || s->pk_cap != s->cap) {
+        if (s->pk) SP_CUDA(s, cudaFree(s->pk));
+        s->pk = nullptr;
+        SP_CUDA(s, cudaMalloc(&s->pk, (size_t)2 * s->cap * sizeof(SpRec)));
+        s->pk_cap = s->cap;
+    }
+    SpRec* pk0 = reinterpret_cast<SpRec*>(s->pk);
+    SpRec* pk1 = pk0 + s->cap;
+    PackPlanes<Op::NQ> pl;
+    for (int k = 0; k < Op::NQ; k++) pl.qp[k] = P.qp[k];
+    SP_LAUNCH(s, (k_pack<Op::NQ>), sp_blocks(s->n, 256), 256, 0, X, s->cap, pl, pk0, pk1, (int)s->n);
+    // the hit lists share the 228 KB L1/shared array with the L1 cache the candidate rows live in: keep them small
+    constexpr int TP = 128, LCAP = 20;
+    SP_LAUNCH(s, (k_sweep_pk<Op, TP, LCAP>), sp_blocks(s->n, TP), TP, (size_t)TP * LCAP * sizeof(int), s->g, c, P, pk0, pk1,
+              self_flag);
     return SP_OK;
 }
 
@@ -142,6 +712,28 @@ static inline WV3 wv3(sp_system* s, int fid) {
     return WV3{d, d + s->cap, d + 2 * s->cap};
 }
 static inline double* sc(sp_system* s, int fid) { return s->fields[fid].d; }
+static inline void set_v3(sp_system* s, int fid, const double** qp) {
+    const double* d = s->fields[fid].d;
+    qp[0] = d;
+    qp[1] = d + s->cap;
+    qp[2] = d + 2 * s->cap;
+}
+
+template <class U>
+static int launch_unary(sp_system* s, const typename U::Params& P);
+
+// pr = P/rho^2 for every particle into the transient scratch field "_pr" (one IEEE division per particle,
+// the same value the closure computes per pair)
+static int pressure_over_rho2(sp_system* s, int fP, int frho, double** out) {
+    int32_t fid;
+    int rc = sp_add_field(s, "_pr", 1, &fid);
+    if (rc) return rc;
+    s->fields[fid].transient = true;
+    UPressureOverRho2::Params P{s->fields[fP].d, s->fields[frho].d, s->fields[fid].d};
+    if ((rc = launch_unary<UPressureOverRho2>(s, P))) return rc;
+    *out = s->fields[fid].d;
+    return SP_OK;
+}
 
 // Internal entry shared with the step programs (sp_program.cu) and the CG (sp_isph.cu).
 int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const double* Pm, int32_t np, int32_t flags) {
@@ -162,8 +754,8 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
             NEED(4, 4, 3, 3, 1, 1);
             NEED_CELLS();
             return dispatch_kernel<OpBalanceOfMass>(s, (int)Pm[0], Pm[2], flags, [&](auto& P) {
-                P.v = rv3(s, F[1]);
-                P.rho = sc(s, F[2]);
+                set_v3(s, F[1], P.qp);
+                P.qp[3] = sc(s, F[2]);
                 P.Drho = sc(s, F[3]);
                 P.m = Pm[1];
                 P.two_nu = Pm[3];
@@ -177,10 +769,14 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
         case SP_OP_INTERNAL_FORCE: {
             NEED(6, 5, 3, 3, 1, 1, 3, 1);
             NEED_CELLS();
+            double* pr = nullptr;
+            {
+                int rc2 = pressure_over_rho2(s, F[2], F[3], &pr);
+                if (rc2) return rc2;
+            }
             return dispatch_kernel<OpInternalForce>(s, (int)Pm[0], Pm[2], flags, [&](auto& P) {
-                P.v = rv3(s, F[1]);
-                P.P = sc(s, F[2]);
-                P.rho = sc(s, F[3]);
+                set_v3(s, F[1], P.qp);
+                P.qp[3] = pr;
                 P.Dv = wv3(s, F[4]);
                 P.type = sc(s, F[5]);
                 P.m = Pm[1];
@@ -190,12 +786,17 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
         case SP_OP_INTERNAL_FORCE_CAVITY: {
             NEED(6, 6, 3, 3, 1, 1, 3, 1);
             NEED_CELLS();
+            double* pr = nullptr;
+            {
+                int rc2 = pressure_over_rho2(s, F[2], F[3], &pr);
+                if (rc2) return rc2;
+            }
             return dispatch_kernel<OpInternalForceCavity>(s, SP_KERNEL_WENDLAND2, Pm[1], flags, [&](auto& P) {
-                P.v = rv3(s, F[1]);
-                P.P = sc(s, F[2]);
-                P.rho = sc(s, F[3]);
+                set_v3(s, F[1], P.qp);
+                P.qp[3] = pr;
+                P.qp[4] = sc(s, F[3]);
+                P.qp[5] = sc(s, F[5]);
                 P.Dv = wv3(s, F[4]);
-                P.type = sc(s, F[5]);
                 P.m = Pm[0];
                 P.Re = Pm[2];
                 P.vlid = Pm[3];
@@ -219,6 +820,7 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
             NEED(2, 3, 3, 1);
             NEED_CELLS();
             return dispatch_kernel<OpDensitySum>(s, (int)Pm[0], Pm[2], flags, [&](auto& P) {
+                P.qp[0] = nullptr;
                 P.out = sc(s, F[1]);
                 P.m = Pm[1];
             });
@@ -232,7 +834,7 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
             NEED(3, 4, 3, 1, 3);
             NEED_CELLS();
             return dispatch_kernel<OpInternalForceSym>(s, (int)Pm[0], Pm[2], flags, [&](auto& P) {
-                P.P = sc(s, F[1]);
+                P.qp[0] = sc(s, F[1]);
                 P.a = wv3(s, F[2]);
                 P.m = Pm[1];
                 P.inv_rho0sq = 1.0 / (Pm[3] * Pm[3]);
@@ -263,7 +865,7 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
             NEED(3, 5, 3, 3, 3);
             NEED_CELLS();
             return dispatch_kernel<OpIsphViscous>(s, (int)Pm[0], Pm[2], flags, [&](auto& P) {
-                P.v = rv3(s, F[1]);
+                set_v3(s, F[1], P.qp);
                 P.Dv = wv3(s, F[2]);
                 P.coef = 2.0 * Pm[1] * Pm[3] / (Pm[4] * Pm[4]);
             });
@@ -272,7 +874,7 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
             NEED(5, 5, 3, 3, 1, 1, 1);
             NEED_CELLS();
             return dispatch_kernel<OpIsphDivLLambda>(s, (int)Pm[0], Pm[2], flags, [&](auto& P) {
-                P.v = rv3(s, F[1]);
+                set_v3(s, F[1], P.qp);
                 P.div = sc(s, F[2]);
                 P.L = sc(s, F[3]);
                 P.lambda = sc(s, F[4]);
@@ -290,7 +892,7 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
             NEED(3, 4, 3, 1, 3);
             NEED_CELLS();
             return dispatch_kernel<OpIsphInternalForce>(s, (int)Pm[0], Pm[2], flags, [&](auto& P) {
-                P.P = sc(s, F[1]);
+                P.qp[0] = sc(s, F[1]);
                 P.Dv = wv3(s, F[2]);
                 P.coef = Pm[1] / (Pm[3] * Pm[3]);
             });
@@ -314,7 +916,7 @@ int sp_poisson_apply_impl(sp_system* s, const int32_t* F, int32_t nf, const doub
         P.L = sc(s, F[1]);
         P.lambda = sc(s, F[2]);
         P.type = sc(s, F[3]);
-        P.pin = sc(s, F[4]);
+        P.qp[0] = sc(s, F[4]);
         P.y = sc(s, F[5]);
         P.off_coef = 2.0 * (Pm[2] * Pm[2]) * Pm[1] / Pm[3];
         P.h2 = Pm[2] * Pm[2];

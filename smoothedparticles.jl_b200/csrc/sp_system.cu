@@ -58,7 +58,8 @@ static int regrow(sp_system* s, T** p, long long old_cap, long long new_cap, int
 
 int sp_ensure_capacity(sp_system* s, long long n) {
     if (n <= s->cap) return SP_OK;
-    long long nc = n + n / 16;  // a little head room: slab systems receive migrants and ghosts
+    long long nc = n + n / 16 + 8;  // head room: migrants/ghosts on slab systems; the tile kernel's aligned
+                                    // bulk copies may read one slot past n
     nc = (nc + 127) / 128 * 128;
     int rc;
     for (SpField& f : s->fields) {
@@ -273,6 +274,8 @@ int32_t sp_destroy(sp_system* s) {
     cudaFree(s->counters);
     cudaFree(s->stage);
     cudaFree(s->dscal);
+    cudaFree(s->ucoord);
+    cudaFree(s->pk);
     if (s->h_scal) cudaFreeHost(s->h_scal);
     if (s->h_counters) cudaFreeHost(s->h_counters);
     if (s->ev0) cudaEventDestroy(s->ev0);

@@ -166,9 +166,12 @@ def _rand_state(case, seed=1):
     return st
 
 
-@pytest.mark.parametrize("strict", [False, True])
+@pytest.mark.parametrize("mode", ["default", "strict", "tile", "packed"])
 @pytest.mark.parametrize("maker", [configs.collapse_dry, configs.collapse3d])
-def test_wcsph_operators_single_call(maker, strict):
+def test_wcsph_operators_single_call(maker, mode):
+    # default = packed-record kernel, strict = reference accumulation order, tile = shared-memory tile kernel
+    strict = mode == "strict"
+    dev_kw = {"strict": {"strict_order": True}, "tile": {"tile_kernel": True}, "packed": {"packed_kernel": True}}.get(mode, {})
     case = maker()
     case.init = _rand_state(case)
     dev, ora = _pair(case)
@@ -177,14 +180,14 @@ def test_wcsph_operators_single_call(maker, strict):
     dev.create_cell_list()
     ora.create_cell_list()
     for s in (dev, ora):
-        kw = dict(strict_order=strict) if s is dev else {}
+        kw = dev_kw if s is dev else {}
         s.apply(ops.balance_of_mass(ker, c["m"], c["h"], c["nu"]), **kw)
     assert_fields_close(dev, ora, ["Drho"], rtol=1e-12 if strict else RTOL_STEP, what="balance_of_mass")
     for s in (dev, ora):
         s.apply(ops.find_pressure(c["dt"], c["c"], c["rho0"]))
     assert_fields_close(dev, ora, ["rho", "P", "Drho"], rtol=1e-14, what="find_pressure")
     for s in (dev, ora):
-        kw = dict(strict_order=strict) if s is dev else {}
+        kw = dev_kw if s is dev else {}
         s.apply(ops.internal_force(ker, c["m"], c["h"], c["mu"], c["rho0"]), **kw)
     assert_fields_close(dev, ora, ["Dv"], rtol=1e-12 if strict else RTOL_STEP, what="internal_force")
     # walls untouched
@@ -220,6 +223,45 @@ def test_collision_operators_and_self_term():
     c = case.consts
     w0 = oracle.kernel_eval(K["SP_KERNEL_WENDLAND2"], K["SP_KFUN_W"], c["h"], np.array([0.0]))[0]
     assert np.min(dev.get("rho")) >= c["m"] * w0 * (1 - 1e-14)
+
+
+def test_dense_cluster_list_overflow_all_kernels():
+    # hundreds of particles inside one kernel radius: per-thread hit lists overflow and are flushed, the tile
+    # kernel has to split rows over several batches; every kernel variant must still match the oracle
+    rng = np.random.default_rng(8)
+    h = 0.1
+    dom = geo.Box(0.0, 0.0, 0.0, 1.0, 1.0, 1.0)
+    x = np.concatenate([rng.uniform(0.45, 0.55, size=(700, 3)), rng.uniform(0.0, 1.0, size=(3000, 3))])
+    ora = OracleSystem({"rho": 1}, dom, h)
+    ora.add_particles(x=x)
+    ora.create_cell_list()
+    ora.apply(ops.density_sum("wendland3", 1.0, h), self_=True)
+    for kw in ({}, {"strict_order": True}, {"tile_kernel": True}, {"packed_kernel": True}):
+        dev = ParticleSystem({"rho": 1}, dom, h)
+        dev.add_particles(x=x)
+        dev.create_cell_list()
+        dev.apply(ops.density_sum("wendland3", 1.0, h), self_=True, **kw)
+        assert neighbour_sets_equal(dev, ora, ordered=True)
+        assert_fields_close(dev, ora, ["rho"], what=f"dense cluster {kw}")
+    off, _ = ora.neighbour_lists()
+    assert np.max(np.diff(off)) > 300
+
+
+@pytest.mark.parametrize("tile", [False, True])
+def test_isph_pair_operators_both_kernels(tile):
+    case = configs.collapse_dry_implicit(dr=2.0e-2)
+    rng = np.random.default_rng(4)
+    case.init["v"] = rng.uniform(-1, 1, size=(case.n, 3)) * np.array([1.0, 1.0, 0.0])
+    case.init["P"] = rng.uniform(0, 1e3, case.n)
+    dev, ora = _pair(case)
+    o = case.ops
+    for s in (dev, ora):
+        kw = {"tile_kernel": tile} if s is dev else {}
+        s.create_cell_list()
+        s.apply(o["visc"], **kw)
+        s.apply(o["dll"], **kw)
+        s.apply(o["force"], **kw)
+    assert_fields_close(dev, ora, ["Dv", "div", "L", "lambda"], what="ISPH pair operators")
 
 
 # ----------------------------------------------------------------------------- N-step programs
