@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(128) k_sweep(SpGrid g, SweepCtx c, typename Op
     Op::store(P, i, p, acc);
 }
 
-// ---- tile kernel (default path).
+// ---- tile kernel (experimental, SP_FLAG_TILE_KERNEL).
 // A CTA owns TP consecutive slots of the cell-sorted planes (its targets, one per thread).  For each of
 // the 3 (2-D) / 9 (3-D) stencil rows the candidates of ALL its targets form one contiguous slot range;
 // the ranges are cut into segments and staged, batch by batch, into shared memory as SoA Float64 planes
@@ -428,7 +428,82 @@ __global__ void __launch_bounds__(TP, MINB) k_sweep_tile(SpGrid g, SweepCtx c, t
     }
 }
 
-// ---- packed-record kernel (default path).
+// ---- hit-mask kernel (default path).
+// Same mapping as the reference-order kernel (one thread per target, candidate rows through L1, 16+ warps
+// per SM) but the divergent pair body is taken out of the candidate loop:
+//   phase 1  for a chunk of up to 32 candidates of a stencil row, evaluate the exact un-fused predicate and set
+//            a bit of a 32-bit REGISTER mask — no branch, no shared memory (the unified L1/shared array stays L1);
+//   phase 2  after three chunks (one dk-plane of the stencil) walk the set bits and run the operator body.
+// The body then executes max-over-lanes(hits per 3 rows) ~ 16 times per plane instead of ~72 times (once per
+// candidate iteration at ~15 % lane use in the baseline profile).
+template <class Op>
+__global__ void __launch_bounds__(128, 4) k_sweep_mask(SpGrid g, SweepCtx c, typename Op::Params P, int self_flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    if (!Op::active(P, i)) return;
+    const double xi = c.x[i], yi = c.y[i], zi = c.z[i];
+    const float ui = c.ux[i], vi = c.uy[i], wi = c.uz[i];
+    typename Op::PS p;
+    typename Op::Acc acc;
+    Op::load(P, i, xi, yi, zi, p, acc);
+    const double T2 = g.T2;
+    const float thr = c.thr;
+    unsigned m0 = 0u, m1 = 0u, m2 = 0u;  // pending chunks (newest in m0)
+    int b0 = 0, b1 = 0, b2 = 0;          // first slot of each pending chunk
+    auto run = [&](unsigned m, int base) {
+        while (m) {
+            const int j = base + __ffs(m) - 1;
+            m &= m - 1;
+            const double dx = __dsub_rn(xi, c.x[j]), dy = __dsub_rn(yi, c.y[j]), dz = __dsub_rn(zi, c.z[j]);
+            const double d2 = sp_d2(dx, dy, dz);
+            // the decision itself: (r > h || p == q) && continue (core.jl:105)  <=>  d2 > T2 with r = sqrt_rn(d2)
+            if (d2 > T2 || j == i) continue;
+            QGlobal<Op::NQ> q{P.qp, j};
+            Op::pair(P, p, q, dx, dy, dz, sp_sqrt_fast(d2), acc);
+        }
+    };
+    auto drain = [&]() {
+        run(m2, b2);
+        run(m1, b1);
+        run(m0, b0);
+        m0 = m1 = m2 = 0u;
+    };
+    const long long key = sp_find_key(g, xi, yi, zi);  // core.jl:95 recomputes the key from the current x
+    const long long L1 = g.lim[0], L12 = g.lim[0] * g.lim[1];
+    const int nk = (g.dim == 2) ? 0 : 1;
+    for (int dk = -nk; dk <= nk; dk++) {
+        for (int dj = -1; dj <= 1; dj++) {
+            const long long mid = key + L1 * dj + L12 * dk;
+            long long klo = mid - 1, khi = mid + 1;
+            if (klo < 1) klo = 1;
+            if (khi > g.key_max) khi = g.key_max;
+            if (klo > khi) continue;
+            const int jb = c.cell_start[klo], je = c.cell_start[khi + 1];
+            for (int j0 = jb; j0 < je; j0 += 32) {
+                const int nj = min(32, je - j0);
+                unsigned m = 0u;
+                // phase 1: conservative FP32 pre-filter in cell units (never rejects a true neighbour, see launch)
+#pragma unroll 8
+                for (int t = 0; t < nj; t++) {
+                    const int j = j0 + t;
+                    const float dx = ui - c.ux[j], dy = vi - c.uy[j], dz = wi - c.uz[j];
+                    const float dd = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    // !(dd > thr) also keeps NaN distances, which the reference lets through as well
+                    m |= (!(dd > thr) ? 1u : 0u) << t;
+                }
+                if (m2) drain();
+                m2 = m1; b2 = b1;
+                m1 = m0; b1 = b0;
+                m0 = m;  b0 = j0;
+            }
+        }
+        drain();
+    }
+    if (self_flag & 1) Op::self(P, p, acc);
+    Op::store(P, i, p, acc);
+}
+
+// ---- packed-record kernel (experimental, SP_FLAG_PACKED_KERNEL).
 // One thread per target, candidates read through L1 — but from two 32-byte records per particle that a
 // prep pass packs from the SoA planes:  pk0 = {x, y, z, qa}  pk1 = {q0, q1, q2, qb}, so a candidate test costs
 // ONE 256-bit load (LDG.E.256) instead of three 64-bit loads from three planes (the reference-order kernel is
@@ -621,11 +696,16 @@ static int launch_sweep(sp_system* s, const typename Op::Params& P, int flags) {
         SP_LAUNCH(s, (k_sweep<Op, true>), sp_blocks(s->n, 128), 128, 0, s->g, c, P, self_flag);
         return SP_OK;
     }
-    if ((flags & SP_FLAG_TILE_KERNEL) || getenv("SP_SWEEP_TILE")) {
-        // experimental shared-memory tile kernel (TMA-staged, FP32 pre-filter): see DESIGN.md, round-2 work.
-        // pre-filter inputs: FP32 coordinates in cell units and a threshold that can never reject a true neighbour.
-        // |u| <= U = max key_lim + 2; rounding x -> u costs <= U*2^-24 per coordinate, the FP32 difference and the
-        // three products/sums a few 2^-24 relative more: d2_f32 <= d2/h^2 + 8*2^-23*U + 1e-6 for d2 <= h^2.
+    const bool tile = (flags & SP_FLAG_TILE_KERNEL) || getenv("SP_SWEEP_TILE");
+    static const int variant = getenv("SP_SWEEP_VARIANT") ? atoi(getenv("SP_SWEEP_VARIANT")) : 0;
+    const bool packed = (flags & SP_FLAG_PACKED_KERNEL) || variant == 1;
+    if (!packed) {
+        // FP32 pre-filter inputs: coordinates in cell units u = (x - lo)/h and a threshold that can never reject
+        // a true neighbour.  |u| <= U = max key_lim + 2; rounding x -> u costs <= U*2^-24 per coordinate, the FP32
+        // difference and the three products/sums a few 2^-24 relative more:
+        //   d2_f32 <= d2/h^2 + 8*2^-23*U + 1e-6   for d2 <= h^2.
+        // Every candidate that passes is re-tested with the exact FP64 predicate, so the neighbour set is the
+        // reference's bit for bit.
         if (!s->ucoord || s->ucoord_cap != s->cap) {
             if (s->ucoord) SP_CUDA(s, cudaFree(s->ucoord));
             s->ucoord = nullptr;
@@ -639,13 +719,18 @@ static int launch_sweep(sp_system* s, const typename Op::Params& P, int flags) {
         const double U = (double)std::max(std::max(s->g.lim[0], s->g.lim[1]), s->g.lim[2]) + 2.0;
         c.thr = (float)(1.0 + 8.0 * U / 8388608.0 + 1e-6);
         c.thr = std::nextafter(c.thr, 2.0f);
+    }
+    if (tile) {
+        // experimental shared-memory tile kernel (TMA-staged): see profiles/r1_sweep_exploration.md
         if (s->g.dim == 2) return launch_tile<Op, TILE_CAPB2, 3, 1>(s, c, P, self_flag);
         return launch_tile<Op, TILE_CAPB3, 9, TILE_RPB>(s, c, P, self_flag);
     }
-    static const int variant = getenv("SP_SWEEP_VARIANT") ? atoi(getenv("SP_SWEEP_VARIANT")) : 0;
-    if (variant == 0 && !(flags & SP_FLAG_PACKED_KERNEL)) {
-        // default: one thread per target over the sorted SoA planes (L1-resident candidate rows)
-        SP_LAUNCH(s, (k_sweep<Op, false>), sp_blocks(s->n, 128), 128, 0, s->g, c, P, self_flag);
+    if (!packed) {
+        // default: one thread per target over the sorted SoA planes (L1-resident candidate rows), register hit masks
+        if (getenv("SP_SWEEP_NOMASK"))
+            SP_LAUNCH(s, (k_sweep<Op, false>), sp_blocks(s->n, 128), 128, 0, s->g, c, P, self_flag);
+        else
+            SP_LAUNCH(s, (k_sweep_mask<Op>), sp_blocks(s->n, 128), 128, 0, s->g, c, P, self_flag);
         return SP_OK;
     }
     // SP_FLAG_PACKED_KERNEL: packed-record two-phase kernel (experimental, see profiles/r1_sweep_exploration.md)
