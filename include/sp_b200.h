@@ -250,23 +250,29 @@ int32_t sp_timer_stop(sp_system* sys, float* ms);
 /* Count of kernel launches issued by this handle since creation. */
 int32_t sp_launch_count(sp_system* sys, int64_t* launches);
 
-/* ---- slab decomposition over the GPUs of one node (no counterpart in the reference) ----
- * One process per GPU.  The host exchanges an NCCL unique id out of band (128 bytes from
- * sp_slab_unique_id on rank 0) and every rank calls sp_slab_init.  The global cell grid of
- * sp_create is cut along `axis` into `nranks` slabs of whole cells; each rank owns the particles
- * whose cell lies in its slab and keeps one ghost cell layer per side.  periodic != 0 wraps the
- * slab axis (and ONLY that axis) with period = key_lim[axis]*h. */
+/* ---- slab decomposition over the GPUs of one node (no counterpart in the reference: SURVEY 8(e)) ----
+ * One process per GPU.  Rank 0 obtains a 128-byte NCCL unique id (sp_slab_unique_id), the host passes it to
+ * the other ranks out of band, and every rank calls sp_slab_init on a system created with the SAME global box
+ * and h, BEFORE adding particles.  The global cell grid is cut along the slowest key axis (z in 3-D, y in 2-D)
+ * into `nranks` slabs of whole cell layers; each rank must be given the particles whose cell layer lies in
+ * its slab (sp_slab_range).  periodic != 0 wraps the slab axis (only that axis) with period key_lim[axis]*h;
+ * the global box must then start and end on cell faces along that axis. */
 int32_t sp_slab_unique_id(uint8_t id[128]);
-int32_t sp_slab_init(sp_system* sys, const uint8_t id[128], int32_t rank, int32_t nranks, int32_t axis,
-                     int32_t periodic);
-/* Migration of owned particles that left the slab + rebuild of the local cell list + ghost exchange
- * of every field.  Replaces sp_create_cell_list on a slab system. */
+int32_t sp_slab_init(sp_system* sys, const uint8_t id[128], int32_t rank, int32_t nranks, int32_t periodic);
+/* Owned cell layers [cell_lo, cell_hi) (0-based from the global key_phase) and their coordinate interval. */
+int32_t sp_slab_range(sp_system* sys, int64_t* cell_lo, int64_t* cell_hi, double* coord_lo, double* coord_hi,
+                      int32_t* axis);
+/* create_cell_list! for a slab system: migration of owned particles that left the slab (ncclSend/ncclRecv of
+ * every field), ghost halo of the two boundary cell layers, then the local cell-list build.  Afterwards the
+ * particle count includes the ghosts; field "_ghost" is 0 for owned particles, 1 / 2 for ghosts received from
+ * the lower / upper neighbour.  Particle order on a slab system is the device order (no reference numbering
+ * exists across ranks): identify particles by a field of your own (e.g. a global id). */
 int32_t sp_slab_create_cell_list(sp_system* sys);
-/* Refresh the ghost copies of the listed fields from their owners (e.g. P, rho after find_pressure). */
+/* Refresh the ghost copies of the listed fields from their owners (e.g. rho, P after find_pressure!). */
 int32_t sp_slab_halo_refresh(sp_system* sys, const int32_t* fields, int32_t nfields);
-/* Owned (non-ghost) particle count on this rank. */
+/* Owned (non-ghost) particle count on this rank after the last sp_slab_create_cell_list. */
 int32_t sp_slab_num_owned(sp_system* sys, int64_t* n_owned);
-/* Sum / max all-reduce of host doubles over the slab communicator (CG dots, diagnostics). */
+/* Sum / max all-reduce of host doubles over the slab communicator (diagnostics, time-step control). */
 int32_t sp_slab_allreduce(sp_system* sys, double* inout, int32_t count, int32_t is_max);
 
 #ifdef __cplusplus

@@ -7,6 +7,8 @@ from .geometry import (Ball, BoundaryLayer, Box, Circle, CubicGrid, Hexagrid, Re
                        Squaregrid, covering, generate_positions, make_grid)
 from .system import (ParticleField, ParticleSystem, apply, assemble_vector, create_cell_list,  # noqa: F401
                      kernel_eval)
+from . import slab  # noqa: F401,E402
+from .slab import SlabSystem  # noqa: F401,E402
 
 K = abi.K
 __version__ = "0.1.0"

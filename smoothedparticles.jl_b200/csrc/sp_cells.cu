@@ -235,7 +235,7 @@ int sp_build_cells(sp_system* s) {
     SP_CUDA(s, cudaStreamSynchronize(s->stream));
     const int n_out = s->h_counters[0];
     const long long n_new = N - n_out;
-    if (n_out > 0) {
+    if (n_out > 0 && g.slab_axis < 0) {
         // swap-with-tail renumbering of the reference indices (core.jl:72-81)
         int* V = s->flags;
         int* Vscan = s->key_alt;
@@ -260,6 +260,7 @@ int sp_build_cells(sp_system* s) {
     s->n = n_new;
     s->identity_order = false;
     s->have_cells = true;
+    s->last_culled = n_out;
     return SP_OK;
 }
 

@@ -38,6 +38,10 @@ struct SpGrid {
     long long lim[3];    // key_lim
     long long key_max;
     int dim;  // 2 iff key_lim[2] == 1 (src/structs.jl:70)
+    // slab decomposition (sp_slab.cu): phase/lim above describe the LOCAL cell window (owned layers + one ghost
+    // layer per side along slab_axis); lo/hi stay the GLOBAL domain box.
+    int slab_axis;      // -1 = not a slab system
+    int slab_periodic;  // the slab axis wraps: no domain test along it
 };
 
 struct SlabState;  // sp_slab.cu
@@ -77,6 +81,7 @@ struct sp_system {
     bool have_cells = false;
     bool identity_order = true;  // slot s holds reference particle s
     long long n_removed = 0;
+    long long last_culled = 0;  // particles dropped by the last cell-list build
     long long launches = 0;
     float last_ms = 0.f;
     std::string err;
@@ -117,6 +122,8 @@ int sp_check_fields(sp_system* s, const int32_t* fields, int nfields, const int*
 int sp_time_begin(sp_system* s);
 int sp_time_end(sp_system* s);
 void sp_slab_free(sp_system* s);  // sp_slab.cu
+int sp_build_cells(sp_system* s);  // sp_cells.cu
+const double* sp_slab_ghost_mask(sp_system* s);  // nullptr unless a slab system: 0 = owned, 1/2 = ghost
 
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__
@@ -134,7 +141,22 @@ __device__ __forceinline__ long long sp_find_key(const SpGrid& g, double x, doub
 
 // is_inside(x, Box), src/geometry.jl:24-30 (closed; NaN -> false)
 __device__ __forceinline__ bool sp_inside(const SpGrid& g, double x, double y, double z) {
-    return g.lo[0] <= x && x <= g.hi[0] && g.lo[1] <= y && y <= g.hi[1] && g.lo[2] <= z && z <= g.hi[2];
+    if (g.slab_axis < 0)
+        return g.lo[0] <= x && x <= g.hi[0] && g.lo[1] <= y && y <= g.hi[1] && g.lo[2] <= z && z <= g.hi[2];
+    // slab system: global box on the other axes (and on the slab axis unless it is periodic), plus the local
+    // cell window along the slab axis (anything else has been migrated away before the build)
+    const double p[3] = {x, y, z};
+    bool in = true;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        if (a == g.slab_axis) {
+            if (!g.slab_periodic) in = in && g.lo[a] <= p[a] && p[a] <= g.hi[a];
+            const double q = floor(__ddiv_rn(p[a], g.h));
+            in = in && (q >= (double)g.phase[a]) && (q < (double)(g.phase[a] + g.lim[a]));
+        } else
+            in = in && g.lo[a] <= p[a] && p[a] <= g.hi[a];
+    }
+    return in;
 }
 
 // squared distance exactly as dist() rounds it before the sqrt: (dx*dx + dy*dy) + dz*dz, no FMA

@@ -75,7 +75,7 @@ extern "C" int32_t sp_poisson_cg(sp_system* s, const int32_t* F, int32_t nf, con
     const int32_t Fa[6] = {F[0], F[1], F[2], F[3], fu, fc};
     SP_LAUNCH(s, k_cg_init, sp_blocks(n, B), B, 0, b, r, u, x, n);
     auto norm2 = [&](double* out_host) -> int {
-        int rc2 = sp_dot_device(s, r, r, s->slab ? /* owned only */ n : n, partial, d_rr);
+        int rc2 = sp_dot_device(s, r, r, n, partial, d_rr);  // ghosts are masked inside
         if (rc2) return rc2;
         if ((rc2 = sp_slab_allreduce_device(s, d_rr, 1, 0))) return rc2;
         SP_CUDA(s, cudaMemcpyAsync(s->h_scal, d_rr, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
@@ -92,6 +92,10 @@ extern "C" int32_t sp_poisson_cg(sp_system* s, const int32_t* F, int32_t nf, con
     while (it < maxiter && residual > tol) {
         const double beta = residual * residual / (prev * prev);
         SP_LAUNCH(s, k_cg_dir, sp_blocks(n, B), B, 0, r, u, beta, n);
+        if (s->slab) {  // ghosts of the search direction come from their owners
+            const int32_t fh[1] = {fu};
+            if ((rc = sp_slab_halo_refresh(s, fh, 1))) return rc;
+        }
         if ((rc = sp_poisson_apply_impl(s, Fa, 6, Pm, 5))) return rc;
         if ((rc = sp_dot_device(s, u, c, n, partial, d_uc))) return rc;
         if ((rc = sp_slab_allreduce_device(s, d_uc, 1, 0))) return rc;

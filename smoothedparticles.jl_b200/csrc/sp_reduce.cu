@@ -7,11 +7,14 @@
 #include "sp_internal.cuh"
 #include "sp_ops.cuh"
 
+int sp_slab_allreduce_device(sp_system* s, double* d_inout, int count, int is_max);  // sp_slab.cu
+
 #define RED_B 256
 #define RED_MAXBLOCKS 1024
 
 struct RedParams {
     const double* f[4];  // field bases
+    const double* ghost; // slab systems: non-zero = ghost copy, skipped (nullptr otherwise)
     long long cap;
     double p[8];
     int ncomp;
@@ -84,6 +87,7 @@ __global__ void __launch_bounds__(RED_B) k_reduce(RedParams R, long long n, doub
     double acc[3] = {0.0, 0.0, 0.0};
     for (long long i = blockIdx.x * (long long)RED_B + threadIdx.x; i < n; i += (long long)gridDim.x * RED_B) {
         double v[3] = {0.0, 0.0, 0.0};
+        if (R.ghost && R.ghost[i] != 0.0) continue;
         red_map<RED>(R, i, v);
 #pragma unroll
         for (int c = 0; c < 3; c++) acc[c] = red_op<IS_MAX>(acc[c], v[c]);
@@ -100,17 +104,18 @@ __global__ void __launch_bounds__(RED_B) k_reduce_final(const double* partial, i
 }
 
 // Shared with sp_isph.cu: sum of a[i]*b[i] into a device scalar (deterministic two-stage).
-__global__ void __launch_bounds__(RED_B) k_dot_partial(const double* a, const double* b, long long n, double* partial) {
+__global__ void __launch_bounds__(RED_B) k_dot_partial(const double* a, const double* b, const double* ghost, long long n,
+                                                       double* partial) {
     double acc[3] = {0.0, 0.0, 0.0};
     for (long long i = blockIdx.x * (long long)RED_B + threadIdx.x; i < n; i += (long long)gridDim.x * RED_B)
-        acc[0] += a[i] * b[i];
+        if (!ghost || ghost[i] == 0.0) acc[0] += a[i] * b[i];
     block_reduce3<false>(acc, partial + 3 * blockIdx.x);
 }
 int sp_dot_device(sp_system* s, const double* a, const double* b, long long n, double* partial, double* out3) {
     int nb = (int)((n + RED_B - 1) / RED_B);
     if (nb > RED_MAXBLOCKS) nb = RED_MAXBLOCKS;
     if (nb < 1) nb = 1;
-    SP_LAUNCH(s, k_dot_partial, nb, RED_B, 0, a, b, n, partial);
+    SP_LAUNCH(s, k_dot_partial, nb, RED_B, 0, a, b, sp_slab_ghost_mask(s), n, partial);
     SP_LAUNCH(s, k_reduce_final<false>, 1, RED_B, 0, partial, nb, out3);
     return SP_OK;
 }
@@ -126,6 +131,7 @@ static int run_reduce(sp_system* s, const RedParams& R, int nout, double* out) {
     double* res = s->stage + 3 * RED_MAXBLOCKS;
     SP_LAUNCH(s, (k_reduce<RED, IS_MAX>), nb, RED_B, 0, R, (long long)s->n, partial);
     SP_LAUNCH(s, (k_reduce_final<IS_MAX>), 1, RED_B, 0, partial, nb, res);
+    if ((rc = sp_slab_allreduce_device(s, res, 3, IS_MAX ? 1 : 0))) return rc;
     double h[3];
     SP_CUDA(s, cudaMemcpyAsync(h, res, 3 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     SP_CUDA(s, cudaStreamSynchronize(s->stream));
@@ -191,6 +197,7 @@ int32_t sp_reduce(sp_system* s, int32_t red, const int32_t* F, int32_t nf, const
     SP_CUDA(s, cudaSetDevice(s->device));
     RedParams R{};
     R.cap = s->cap;
+    R.ghost = sp_slab_ghost_mask(s);
     auto bind = [&](int nexp, const int* nc, int npar) -> int {
         int rc = sp_check_fields(s, F, nf, nc, nexp);
         if (rc) return rc;

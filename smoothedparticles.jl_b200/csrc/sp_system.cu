@@ -205,6 +205,8 @@ int32_t sp_create(sp_system** out, const double lo[3], const double hi[3], doubl
         return sp_fail(nullptr, SP_ERR_INVALID, "key_max exceeds the 31-bit cell index of this build");
     }
     g.dim = (g.lim[2] == 1) ? 2 : 3;  // structs.jl:70
+    g.slab_axis = -1;
+    g.slab_periodic = 0;
     s->n_key_diff = 0;
     if (g.dim == 2) {
         for (int di = -1; di <= 1; di++)
