@@ -9,8 +9,10 @@ N = 1   workload = examples/collapse3d.jl scaled to 10 M particles (BASELINE.jso
         pass of its time loop (move, create_cell_list, balance_of_mass, find_pressure, internal_force,
         accelerate, accelerate).  Particle state (1.04 GB) is far larger than the 126 MB L2, so no flush is
         needed between steps.
-N > 1   workload = the synthetic periodic 3-D lattice box, 25 M particles per GPU, slab-decomposed with NCCL
-        halo exchange (BASELINE.json configs[4]); weak scaling.
+N > 1   weak scaling over slabs (one process per GPU, NCCL halos/migration inside the library):
+        --workload dambreak (default): the same dam break with the box depth x N along z, i.e. one copy of the
+        N = 1 workload per GPU, so the per-N values are directly comparable;
+        --workload box: the synthetic periodic 3-D lattice box, 25 M particles per GPU (BASELINE.json configs[4]).
 
 One JSON line is printed by rank 0; see DESIGN.md §Measurement for every key.
 """
@@ -182,7 +184,7 @@ def run_single(args):
             traffic = json.load(open(tpath)).get(dominant)
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": f"k_sweep<{dominant}>", "achieved": achieved, "peak": hbm_peak,
+    roofline = {"bound": "hbm", "kernel": f"k_sweep_mask<{dominant}>", "achieved": achieved, "peak": hbm_peak,
                 "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_kind": peak_kind,
                 "alg_bytes_per_particle": ALG_BYTES[dominant], "launch_ms": dom_ms,
                 "note": "pair sweeps are FP64-issue bound, not HBM bound: see fp64 and step_hbm_frac"}
@@ -340,9 +342,11 @@ def run_reference(args):
 
 def _slab_case_for_reference(args):
     from smoothedparticles_jl_b200 import configs
-    # bounded sample of the multi-GPU workload: one GPU's share of the periodic box is too large for a few
-    # minutes of CPU time, so the CPU runs a 2.1 M-particle block of the same lattice, density and step
-    return configs.lattice_box(128, jitter=0.1)
+    # bounded sample of the multi-GPU workload: the CPU runs ONE GPU's share (the N = 1 dam break) — the weak-
+    # scaled workload is N copies of it along z; for the periodic box a 2.1 M-particle block of the same lattice
+    if args.workload == "box":
+        return configs.lattice_box(128, jitter=0.1)
+    return configs.collapse3d(args.dr)
 
 
 # ------------------------------------------------------------------------------------------------ N > 1
@@ -360,7 +364,10 @@ def main():
     ap.add_argument("--dr", type=float, default=DR_10M)
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--per-gpu", type=int, default=292, help="lattice side per GPU for N > 1 (292^3 = 24.9 M)")
+    ap.add_argument("--workload", default="dambreak", choices=["dambreak", "box"],
+                    help="N > 1: 'dambreak' = collapse3d with the box depth x N (one N=1 workload per GPU); "
+                         "'box' = periodic lattice box, --per-gpu^3 particles per GPU (BASELINE configs[4])")
+    ap.add_argument("--per-gpu", type=int, default=292, help="lattice side per GPU for --workload box (292^3 = 24.9 M)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours" and not os.environ.get("SP_BENCH_ALLOW_SHORT"):
         args.warmup = 3

@@ -1,0 +1,231 @@
+"""bench.py --gpus N (N > 1): weak scaling of the 3-D WCSPH step on the synthetic periodic lattice box
+(BASELINE.json configs[4]): `per_gpu`^3 particles per GPU (292^3 = 24.9 M), slab-decomposed along z, one
+process per GPU, NCCL ghost halos / migration inside the library, gloo for the control plane."""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import time
+
+import numpy as np
+
+
+def make_rank_particles(per_gpu: int, rank: int, world: int, dr: float = 1.0, jitter: float = 0.1, seed: int = 1234):
+    """This rank's share of the global nx x ny x (nz*world) lattice: planes k in [rank*nz, (rank+1)*nz)."""
+    nx = ny = nz = per_gpu
+    c = 50.0
+    I, J, Kk = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(rank * nz, (rank + 1) * nz), indexing="ij")
+    n = I.size
+    x = np.empty((n, 3))
+    x[:, 0] = I.ravel() * dr
+    x[:, 1] = J.ravel() * dr
+    x[:, 2] = (Kk.ravel() + 0.5) * dr
+    rng = np.random.Generator(np.random.Philox(key=seed + 1000 * rank))
+    x += rng.uniform(-jitter * dr, jitter * dr, size=(n, 3))
+    v = rng.uniform(-0.01 * c, 0.01 * c, size=(n, 3))
+    perm = np.random.Generator(np.random.Philox(key=99 + rank)).permutation(n)  # unsorted input order
+    return x[perm], v[perm]
+
+
+def run_multi(args, METRIC, UNIT, ClockSampler, peaks):
+    import torch
+    import torch.distributed as dist
+
+    import smoothedparticles_jl_b200 as sp
+    from smoothedparticles_jl_b200 import geometry as geo, operators as ops, slab
+
+    K = sp.K
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29541")
+    torch.cuda.set_device(local)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def fresh_id():
+        # one NCCL unique id per communicator: rank 0 draws it, gloo carries the 128 bytes to the others
+        ids = [slab.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        return ids[0]
+
+    per = args.per_gpu
+    rho0, c, mu, nu = 1000.0, 50.0, 8.4e-4, 1.0e-4
+    fields = {"v": 3, "Dv": 3, "P": 1, "rho": 1, "Drho": 1, "type": 1}
+    t0 = time.time()
+    if args.workload == "box":
+        # BASELINE.json configs[4]: periodic lattice box, per^3 particles per GPU
+        dr = 1.0
+        h = 2.0 * dr
+        g = (0.0, 0.0, -9.8)
+        Lz = per * world * dr
+        dom = geo.Box(-h, -h, 0.0, (per - 1) * dr + h, (per - 1) * dr + h, Lz * (1 - 1e-13))
+        periodic = True
+        x, v = make_rank_particles(per, rank, world, dr)
+        typ = np.zeros(len(x))
+        wname = (f"periodic 3-D lattice box, {per}^3 particles per GPU, slab-decomposed along z (h = 2 dr, jitter "
+                 f"0.1 dr, collapse3d step)")
+    else:
+        # examples/collapse3d.jl at dr = args.dr (10 M particles per unit depth), box depth x N along z — the
+        # direction the dam break is invariant in — so every GPU holds one copy of the N = 1 workload
+        from smoothedparticles_jl_b200 import configs
+        dr = args.dr
+        h = 2.0 * dr
+        g = (0.0, 0.0, -9.8)
+        probe = configs.collapse3d(5e-2, depth_scale=world)          # cheap: only for the global box
+        dom_probe = probe.domain
+        wall = 2.5 * dr
+        dom = geo.Box(-wall, -wall, -wall, 0.584 + wall, 0.35 + wall, 0.15 * world + wall)
+        del probe, dom_probe
+        gphase = int(np.floor(dom.lo[2] / h))
+        glim = int(np.floor(dom.hi[2] / h)) - gphase + 1
+        c0, c1 = slab.partition_layers(glim, world)[rank]
+        zlo, zhi = (gphase + c0) * h - dr, (gphase + c1) * h + dr      # generous: ownership is decided below
+        case = configs.collapse3d(dr, depth_scale=world, z_range=(zlo, zhi))
+        x = case.init["x"]
+        cell = np.floor(x[:, 2] / h).astype(np.int64) - gphase
+        mine = (cell >= c0) & (cell < c1)
+        x = x[mine]
+        typ = case.init["type"][mine]
+        v = np.zeros_like(x)
+        periodic = False
+        assert np.allclose(case.domain.lo, dom.lo) and np.allclose(case.domain.hi, dom.hi), (case.domain, dom)
+        dom = case.domain
+        wname = (f"examples/collapse3d.jl dam break, dr={dr:g}, box depth x{world} along z (one 10 M-particle copy of "
+                 f"the N=1 workload per GPU), slab-decomposed along z")
+    m = rho0 * dr ** 3
+    dt = 0.1 * h / c
+    n_local = len(x)
+    gen_s = time.time() - t0
+    o = dict(bom=ops.balance_of_mass("wendland3", m, h, nu), fp=ops.find_pressure(dt, c, rho0),
+             force=ops.internal_force("wendland3", m, h, mu, rho0), move=ops.move(dt), acc=ops.accelerate(0.5 * dt, g))
+
+    def make_system():
+        s = slab.SlabSystem(fields, dom, h, rank, world, fresh_id(), periodic=periodic, device=local)
+        return s
+
+    sysd = make_system()
+    assert np.all(sysd.owns(x)), "generator and slab partition disagree"
+    sysd.add_particles(x=x, v=v, rho=np.full(n_local, rho0), type=typ)
+    for _ in range(args.warmup):
+        slab.wcsph3d_slab_step(sysd, o)
+    sysd.synchronize()
+    launches0 = sysd.launch_count
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sysd.timer_start()
+    for _ in range(args.steps):
+        slab.wcsph3d_slab_step(sysd, o)
+    ms = sysd.timer_stop()
+    torch.cuda.synchronize()
+    dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    gpu_launches = sysd.launch_count - launches0
+    t = torch.tensor([ms], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t[0])
+    n_tot = int(sysd.allreduce([sysd.n_owned])[0])
+    n_ghost = len(sysd) - sysd.n_owned
+    value = n_tot * args.steps / (ms_max * 1e-3)
+
+    # per-kernel breakdown on this rank (same steps, per-call timing)
+    acc = {k: 0.0 for k in ("move", "cell_list+halo", "balance_of_mass", "find_pressure", "halo_refresh", "internal_force",
+                            "accelerate")}
+
+    def timed(name, fn):
+        fn()
+        acc[name] += sysd.last_call_ms()
+
+    for _ in range(args.steps):
+        timed("move", lambda: sysd.apply(o["move"]))
+        timed("cell_list+halo", sysd.create_cell_list)
+        timed("balance_of_mass", lambda: sysd.apply(o["bom"]))
+        timed("find_pressure", lambda: sysd.apply(o["fp"]))
+        timed("halo_refresh", lambda: sysd.halo_refresh("rho", "P"))
+        timed("internal_force", lambda: sysd.apply(o["force"]))
+        timed("accelerate", lambda: sysd.apply(o["acc"]))
+        timed("accelerate", lambda: sysd.apply(o["acc"]))
+    breakdown = {k: vv / args.steps for k, vv in acc.items()}
+    E = sysd.reduce(K["SP_RED_ENERGY_WCSPH"], ("x", "v", "rho"), (m, c, rho0, *g))[0]
+    sysd.close()
+    del sysd
+
+    # end to end: upload from pinned host memory, K steps with a per-step all-reduced energy read-back, download
+    host_x = torch.from_numpy(x).pin_memory()
+    host_v = torch.from_numpy(v).pin_memory()
+    host_rho = torch.full((n_local,), rho0, dtype=torch.float64).pin_memory()
+    host_typ = torch.from_numpy(np.ascontiguousarray(typ)).pin_memory()
+    out_bufs = {}
+
+    def job(s):
+        # the NCCL communicator is created once per system outside the timed region (ncclCommInitRank takes ~1 s
+        # and a production run pays it once); everything a job moves or computes is inside
+        s.resize(n_local)
+        for nm, tt in (("x", host_x), ("v", host_v), ("rho", host_rho), ("type", host_typ)):
+            s.upload_raw(nm, C.cast(tt.data_ptr(), C.POINTER(C.c_double)), n_local, K["SP_LAYOUT_AOS"])
+        e = 0.0
+        for _ in range(args.steps):
+            slab.wcsph3d_slab_step(s, o)
+            e = s.reduce(K["SP_RED_ENERGY_WCSPH"], ("x", "v", "rho"), (m, c, rho0, *g))[0]
+        nl = len(s)
+        for nm in ("x", "v", "rho", "P", "_ghost"):
+            nc = 3 if nm in ("x", "v") else 1
+            key = (nm, nl)
+            if key not in out_bufs:
+                out_bufs[key] = torch.empty((nl, nc) if nc > 1 else (nl,), dtype=torch.float64).pin_memory()
+            s.download_raw(nm, C.cast(out_bufs[key].data_ptr(), C.POINTER(C.c_double)), nl, K["SP_LAYOUT_AOS"])
+        s.synchronize()
+        return e, nl
+
+    s_warm = make_system()
+    job(s_warm)
+    s_warm.close()
+    s_job = make_system()
+    s_job.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    e_job, nl = job(s_job)
+    torch.cuda.synchronize()
+    dt_job = time.perf_counter() - t1
+    s_job.close()
+    tj = torch.tensor([dt_job], dtype=torch.float64)
+    dist.all_reduce(tj, op=dist.ReduceOp.MAX)
+    h2d = (host_x.numel() + host_v.numel() + host_rho.numel() + host_typ.numel()) * 8
+    d2h = nl * 9 * 8
+    tot = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64)
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    e2e = {"value": n_tot * args.steps / float(tj[0]), "unit": UNIT, "h2d_bytes_per_step": float(tot[0]) / args.steps,
+           "d2h_bytes_per_step": float(tot[1]) / args.steps + 24 * world, "seconds": float(tj[0]),
+           "what": "every rank: upload of x,v,rho,type from pinned host memory into a fresh slab system, K slab steps "
+                   "driven call by call with a per-step all-reduced energy read-back, download of x,v,rho,P,_ghost "
+                   "(NCCL communicator creation excluded)"}
+
+    if rank == 0:
+        hbm_peak, peak_kind = peaks()
+        dominant = max(("internal_force", "balance_of_mass"), key=lambda k: breakdown[k])
+        alg = {"internal_force": 120, "balance_of_mass": 72}[dominant]
+        achieved = alg * (n_local + n_ghost) / (breakdown[dominant] * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wname, "particles": n_tot,
+                       "particles_per_gpu": n_local, "ghosts_per_gpu": int(n_ghost),
+                       "l2": "state >= 1 GB per GPU >> 126 MB L2, no flush needed", "setup_s": round(gen_s, 1),
+                       "parallelism": f"slab{world}", "energy": E},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches),
+            "roofline": {"bound": "hbm", "kernel": f"k_sweep_mask<{dominant}>", "achieved": achieved, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+                         "alg_bytes_per_particle": alg, "launch_ms": breakdown[dominant],
+                         "step_hbm_frac": 736 * value / world / (hbm_peak * 1e9),
+                         "note": "pair sweeps are FP64-issue / L1 bound, not HBM bound"},
+            "breakdown_ms": breakdown, "cpu_baseline": None,
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()

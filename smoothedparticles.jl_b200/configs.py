@@ -105,8 +105,12 @@ def collapse_dry(dr: float = 1.5e-2) -> Case:
 
 
 # --------------------------------------------------------------------------- collapse3d.jl
-def collapse3d(dr: float = 5.0e-3) -> Case:
+def collapse3d(dr: float = 5.0e-3, depth_scale: float = 1.0, z_range=None) -> Case:
     """examples/collapse3d.jl:28-84 and :134-151.
+
+    ``depth_scale`` extrudes the box (and the water column) along z — the direction the dam break is invariant
+    in — for weak scaling over slabs; ``z_range=(lo, hi)`` generates only the lattice points with lo <= z < hi
+    (one rank's share), the domain stays the global one.
 
     The shipped script does not run (``import`` instead of ``using``; ``rho`` undefined in
     internal_force!, :101).  Adopted correction: the pressure term of
@@ -119,7 +123,7 @@ def collapse3d(dr: float = 5.0e-3) -> Case:
     g = (0.0, 0.0, -9.8)  # -9.8*VECZ
     mu = 8.4e-4
     nu = 1.0e-4
-    wcw, wch, bh, bw, bd = 0.142, 0.293, 0.35, 0.584, 0.15
+    wcw, wch, bh, bw, bd = 0.142, 0.293, 0.35, 0.584, 0.15 * depth_scale
     wall_width = 2.5 * dr
     dt = 0.1 * h / c
     grid = geo.CubicGrid(dr)
@@ -128,8 +132,16 @@ def collapse3d(dr: float = 5.0e-3) -> Case:
     walls = geo.BoundaryLayer(box, grid, wall_width)
     walls = geo.Specification(walls, lambda X: X[:, 1] < bh)
     domain = walls.boundarybox()
-    xf = geo.covering(grid, fluid)
-    xw = geo.covering(grid, walls)
+    if z_range is not None:
+        zlo, zhi = z_range
+        big = 1e30
+        zslab = geo.Box(-big, -big, zlo, big, big, zhi)
+        fluid_g = geo.Specification(fluid * zslab, lambda X: X[:, 2] < zhi)
+        walls_g = geo.Specification(walls * zslab, lambda X: X[:, 2] < zhi)
+    else:
+        fluid_g, walls_g = fluid, walls
+    xf = geo.covering(grid, fluid_g)
+    xw = geo.covering(grid, walls_g)
     x = np.concatenate([xf, xw])
     typ = np.concatenate([np.zeros(len(xf)), np.ones(len(xw))])
     fields = {"v": 3, "Dv": 3, "P": 1, "rho": 1, "Drho": 1, "type": 1}
