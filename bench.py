@@ -254,11 +254,22 @@ def run_e2e(case, args, dev_index):
     pe = (c["m"], c["c"], c["rho0"], *c["g"])
     import ctypes as C
 
+    phases = {}
+
     def job():
+        tp = [time.perf_counter()]
+
+        def mark(name):
+            tp.append(time.perf_counter())
+            phases[name] = tp[-1] - tp[-2]
+
         s = ParticleSystem(case.fields, case.domain, case.h, device=dev_index)
         s.resize(n)
+        s.synchronize()
+        mark("create_s")
         for nm, t in host_in.items():
             s.upload_raw(nm, C.cast(t.data_ptr(), C.POINTER(C.c_double)), n, K["SP_LAYOUT_AOS"])
+        mark("upload_s")
         energy = 0.0
         for _ in range(args.steps):
             s.apply(o_mv)
@@ -269,10 +280,13 @@ def run_e2e(case, args, dev_index):
             s.apply(o_ac)
             s.apply(o_ac)
             energy = s.reduce(K["SP_RED_ENERGY_WCSPH"], ("x", "v", "rho"), pe)[0]   # D2H every step
+        mark("steps_s")
         for nm, t in host_out.items():
             s.download_raw(nm, C.cast(t.data_ptr(), C.POINTER(C.c_double)), len(s), K["SP_LAYOUT_AOS"])
         s.synchronize()
+        mark("download_s")
         s.close()
+        mark("destroy_s")
         return energy
 
     job()  # warm-up (allocations, page-ins)
@@ -284,7 +298,7 @@ def run_e2e(case, args, dev_index):
     h2d = sum(t.numel() * 8 for t in host_in.values())
     d2h = sum(t.numel() * 8 for t in host_out.values())
     return {"value": n * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
-            "d2h_bytes_per_step": d2h / args.steps + 24, "seconds": dt,
+            "d2h_bytes_per_step": d2h / args.steps + 24, "seconds": dt, "phases": {k: round(v, 4) for k, v in phases.items()},
             "what": "one job = sp_create + upload of x,v,rho,type from pinned host memory, K steps driven call by "
                     "call through the C ABI with a per-step energy read-back, download of x,v,rho,P, sp_destroy",
             "energy": energy}

@@ -1,0 +1,180 @@
+# SmoothedParticlesB200.jl — thin Julia shim over libsp_b200.so (include/sp_b200.h).
+#
+# Keeps the reference's surface — ParticleSystem / create_cell_list! / apply! / ParticleField /
+# assemble_vector / sum (src/SmoothedParticles.jl:10-72) — and forwards every call with `ccall`.
+# All logic lives in the shared library; this file only marshals arguments.  It could not be executed in the
+# build environment (no Julia runtime there); the same entry points are exercised through Python ctypes.
+#
+# Differences a user sees (unavoidable once particles live in HBM):
+#   * the particle struct is declared as a list of fields  (:v => 3, :rho => 1, ...)  instead of a mutable struct;
+#   * `sys.particles[i].x` becomes bulk `download(sys, :x)` / `upload!(sys, :x, array)` in reference order;
+#   * the closures passed to apply! are registered operators (Operators.balance_of_mass(...), ...).
+module SmoothedParticlesB200
+
+export ParticleSystem, create_cell_list!, apply!, upload!, download, add_particles!, ParticleField,
+       assemble_vector, Operators, poisson_cg!, reduce_energy_wcsph, sum_at_points
+
+const LIB = get(ENV, "SP_B200_LIB", joinpath(@__DIR__, "..", "smoothedparticles.jl_b200", "libsp_b200.so"))
+
+const SP_LAYOUT_AOS = Int32(0)
+const SP_FLAG_SELF = Int32(1)
+const KERNELS = Dict(:wendland1 => 1.0, :wendland2 => 2.0, :wendland3 => 3.0, :spline23 => 4.0, :spline24 => 5.0)
+
+struct SpError <: Exception
+    code::Int32
+    msg::String
+end
+
+function check(code::Int32, handle::Ptr{Cvoid} = C_NULL)
+    code == 0 && return
+    msg = unsafe_string(ccall((:sp_last_error, LIB), Cstring, (Ptr{Cvoid},), handle))
+    throw(SpError(code, msg))     # the reference throws / @asserts; the ABI never throws across ccall
+end
+
+mutable struct ParticleSystem
+    handle::Ptr{Cvoid}
+    h::Float64
+    fields::Dict{Symbol,Tuple{Int32,Int32}}   # name => (field id, ncomp)
+    # ParticleSystem(T, domain, h), src/structs.jl:57-91: `fields` replaces T, `lo`/`hi` = boundarybox(domain)
+    function ParticleSystem(fields::Vector{Pair{Symbol,Int}}, lo::NTuple{3,Float64}, hi::NTuple{3,Float64},
+                            h::Float64; device::Integer = 0)
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:sp_create, LIB), Int32, (Ref{Ptr{Cvoid}}, Ref{NTuple{3,Float64}}, Ref{NTuple{3,Float64}}, Float64, Int32),
+                    out, Ref(lo), Ref(hi), h, Int32(device)))
+        sys = new(out[], h, Dict{Symbol,Tuple{Int32,Int32}}(:x => (Int32(0), Int32(3))))
+        for (name, nc) in fields
+            fid = Ref{Int32}(0)
+            check(ccall((:sp_add_field, LIB), Int32, (Ptr{Cvoid}, Cstring, Int32, Ref{Int32}), sys.handle, String(name),
+                        Int32(nc), fid), sys.handle)
+            sys.fields[name] = (fid[], Int32(nc))
+        end
+        finalizer(s -> ccall((:sp_destroy, LIB), Int32, (Ptr{Cvoid},), s.handle), sys)
+        return sys
+    end
+end
+
+Base.length(sys::ParticleSystem) = begin
+    n = Ref{Int64}(0)
+    check(ccall((:sp_num_particles, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}), sys.handle, n), sys.handle)
+    Int(n[])
+end
+
+# host arrays are ncomp x n column-major (a reinterpreted Vector{SVector{3,Float64}}) == SP_LAYOUT_AOS
+function upload!(sys::ParticleSystem, name::Symbol, a::AbstractArray{Float64})
+    fid, _ = sys.fields[name]
+    check(ccall((:sp_upload, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64, Int32), sys.handle, fid, a,
+                length(sys), SP_LAYOUT_AOS), sys.handle)
+end
+function download(sys::ParticleSystem, name::Symbol)
+    fid, nc = sys.fields[name]
+    a = nc == 1 ? Vector{Float64}(undef, length(sys)) : Matrix{Float64}(undef, nc, length(sys))
+    check(ccall((:sp_download, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64, Int32), sys.handle, fid, a,
+                length(sys), SP_LAYOUT_AOS), sys.handle)
+    return a
+end
+# generate_particles! / push!, src/grids.jl:253-258: append at the end of the reference order
+function add_particles!(sys::ParticleSystem; kwargs...)
+    x = kwargs[:x]
+    n_old, n_new = length(sys), size(x, 2)
+    old = Dict(k => download(sys, k) for k in keys(kwargs) if n_old > 0)
+    check(ccall((:sp_resize, LIB), Int32, (Ptr{Cvoid}, Int64), sys.handle, n_old + n_new), sys.handle)
+    for (k, v) in kwargs
+        upload!(sys, k, n_old > 0 ? hcat(old[k], v) : v)
+    end
+end
+
+# create_cell_list!(sys), src/core.jl:51-90
+create_cell_list!(sys::ParticleSystem) =
+    check(ccall((:sp_create_cell_list, LIB), Int32, (Ptr{Cvoid},), sys.handle), sys.handle)
+
+struct Operator
+    id::Int32
+    fields::Vector{Symbol}
+    params::Vector{Float64}
+end
+
+# apply!(sys, action!; self = false), src/core.jl:151-161
+function apply!(sys::ParticleSystem, op::Operator; self::Bool = false)
+    F = Int32[sys.fields[f][1] for f in op.fields]
+    check(ccall((:sp_apply, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{Float64}, Int32, Int32), sys.handle,
+                op.id, F, length(F), op.params, length(op.params), self ? SP_FLAG_SELF : Int32(0)), sys.handle)
+end
+
+# the closures of the shipped examples as registered operators (ids and parameter order: include/sp_b200.h)
+module Operators
+import ..Operator, ..KERNELS
+balance_of_mass(kernel, m, h, nu; x = :x, v = :v, rho = :rho, Drho = :Drho) =
+    Operator(1, [x, v, rho, Drho], [KERNELS[kernel], m, h, 2 * nu])                  # collapse_dry.jl:112-115
+find_pressure(dt, c, rho0; P0 = 0.0, rho = :rho, Drho = :Drho, P = :P) =
+    Operator(2, [rho, Drho, P], [dt, c^2, rho0, P0])                                 # collapse_dry.jl:123-127
+internal_force(kernel, m, h, mu, rho0; x = :x, v = :v, P = :P, rho = :rho, Dv = :Dv, type = :type) =
+    Operator(3, [x, v, P, rho, Dv, type], [KERNELS[kernel], m, h, mu, rho0])         # collapse_dry.jl:135-141
+internal_force_cavity(m, h, Re, vlid; ylid = 1.0, lid = 2.0, x = :x, v = :v, P = :P, rho = :rho, Dv = :Dv, type = :type) =
+    Operator(4, [x, v, P, rho, Dv, type], [m, h, Float64(Re), vlid, ylid, lid])      # cavity_flow.jl:102-114
+move(dtm; x = :x, v = :v, Dv = :Dv, type = :type) = Operator(5, [x, v, Dv, type], [dtm])                 # :148-153
+accelerate(hdt, g = (0.0, 0.0, 0.0); v = :v, Dv = :Dv, type = :type) = Operator(6, [v, Dv, type], [hdt, g...])  # :155-159
+density_sum(kernel, m, h; x = :x, out = :rho) = Operator(7, [x, out], [KERNELS[kernel], m, h])           # test_collision_2d.jl:63-69
+pressure_from_rho(c; rho = :rho, rho0 = :rho0, P = :P) = Operator(8, [rho, rho0, P], [c^2])
+internal_force_sym(kernel, m, h, rho0; x = :x, P = :P, a = :a) = Operator(9, [x, P, a], [KERNELS[kernel], m, h, rho0])
+fill(field, value = 0.0) = Operator(10, [field], [value])
+advect(dt; x = :x, v = :v) = Operator(11, [x, v], [dt])
+kick(hdt; v = :v, a = :a) = Operator(12, [v, a], [hdt])
+isph_initialize(dt, g; x = :x, v = :v, div = :div, L = :L, lambda = :lambda, type = :type) =
+    Operator(20, [x, v, div, L, lambda, type], [dt, g...])                           # collapse_dry_implicit.jl:118-126
+isph_viscous_force(kernel, m, h, mu, rho; x = :x, v = :v, Dv = :Dv) = Operator(21, [x, v, Dv], [KERNELS[kernel], m, h, mu, rho])
+isph_div_L_lambda(kernel, m, h, rho, dim; x = :x, v = :v, div = :div, L = :L, lambda = :lambda) =
+    Operator(22, [x, v, div, L, lambda], [KERNELS[kernel], m, h, rho, Float64(dim)])
+isph_projection_vector(h, dt; div = :div, b = :b) = Operator(23, [div, b], [h, dt])
+isph_internal_force(kernel, m, h, rho; x = :x, P = :P, Dv = :Dv) = Operator(25, [x, P, Dv], [KERNELS[kernel], m, h, rho])
+isph_accelerate(dt; v = :v, Dv = :Dv, type = :type) = Operator(26, [v, Dv, type], [dt])
+end # module Operators
+
+# assemble_vector(sys, func), src/core.jl:175-182: the unary operator writes its last bound field
+function assemble_vector(sys::ParticleSystem, op::Operator)
+    apply!(sys, op)
+    return download(sys, op.fields[end])
+end
+
+# P .= cg(assemble_matrix(sys, projection_matrix), b), collapse_dry_implicit.jl:223-227, matrix-free
+function poisson_cg!(sys::ParticleSystem, kernel, m, h, rho, C_free; x = :x, L = :L, lambda = :lambda, type = :type,
+                     b = :b, P = :P, reltol = sqrt(eps()), abstol = 0.0, maxiter = 0)
+    F = Int32[sys.fields[f][1] for f in (x, L, lambda, type, b, P)]
+    prm = Float64[KERNELS[kernel], m, h, rho, C_free]
+    iters = Ref{Int64}(0); resid = Ref{Float64}(0.0)
+    check(ccall((:sp_poisson_cg, LIB), Int32,
+                (Ptr{Cvoid}, Ptr{Int32}, Int32, Ptr{Float64}, Int32, Float64, Float64, Int64, Ref{Int64}, Ref{Float64}),
+                sys.handle, F, 6, prm, 5, reltol, abstol, maxiter, iters, resid), sys.handle)
+    return iters[], resid[]
+end
+
+# sum(energy, sys.particles), collapse_dry.jl:166-171
+function reduce_energy_wcsph(sys::ParticleSystem, m, c, rho0, g; x = :x, v = :v, rho = :rho)
+    F = Int32[sys.fields[f][1] for f in (x, v, rho)]
+    out = zeros(3)
+    check(ccall((:sp_reduce, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{Float64}, Int32, Ptr{Float64}),
+                sys.handle, 1, F, 3, Float64[m, c, rho0, g...], 6, out), sys.handle)
+    return out[1]
+end
+
+# SmoothedParticles.sum(sys, f, x), src/core.jl:240-260, for many points at once (3 x m matrix)
+function sum_at_points(sys::ParticleSystem, sum_op::Integer, fields::Vector{Symbol}, params::Vector{Float64},
+                       pts::Matrix{Float64})
+    F = Int32[sys.fields[f][1] for f in fields]
+    out = Vector{Float64}(undef, size(pts, 2))
+    check(ccall((:sp_sum_at_points, LIB), Int32,
+                (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{Float64}, Int32, Ptr{Float64}, Int64, Ptr{Float64}),
+                sys.handle, Int32(sum_op), F, length(F), params, length(params), pts, size(pts, 2), out), sys.handle)
+    return out
+end
+
+# ParticleField(sys, :var), src/structs.jl:118-125
+struct ParticleField <: AbstractVector{Float64}
+    sys::ParticleSystem
+    name::Symbol
+end
+Base.size(f::ParticleField) = (length(f.sys),)
+Base.getindex(f::ParticleField, i::Int) = download(f.sys, f.name)[i]     # bulk use: collect(f)
+Base.collect(f::ParticleField) = download(f.sys, f.name)
+Base.copyto!(f::ParticleField, v::AbstractVector{Float64}) = (upload!(f.sys, f.name, collect(v)); f)
+
+end # module

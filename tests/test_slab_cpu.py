@@ -1,0 +1,42 @@
+"""N > 1 host logic on CPU: world_size-2 (and 3) gloo runs of the numpy/oracle emulation of the slab protocol,
+plus unit checks of the partition helpers the GPU path shares."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from smoothedparticles_jl_b200 import slab
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("mode,world", [("nonperiodic", 2), ("periodic", 2), ("periodic", 3)])
+def test_slab_protocol_emulation_gloo(mode, world):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "slab_emulation.py"), mode]
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0 and "EMU-OK" in r.stdout, (r.stdout + r.stderr)[-2000:]
+
+
+def test_partition_layers_and_owner():
+    assert slab.partition_layers(13, 4) == [(0, 4), (4, 7), (7, 10), (10, 13)]
+    assert slab.partition_layers(8, 8) == [(i, i + 1) for i in range(8)]
+    lay = slab.partition_layers(10, 3)
+    assert lay[0][0] == 0 and lay[-1][1] == 10 and all(a[1] == b[0] for a, b in zip(lay, lay[1:]))
+    h = 0.01
+    z = np.array([-0.0051, 0.0, 0.0099999, 0.01, 0.0949, 0.0999, 0.1])
+    own = slab.owner_of(z, h, -1, slab.partition_layers(11, 2))   # cells -1..9 -> layers 0..10
+    cells = np.floor(z / h).astype(int) + 1
+    assert np.array_equal(own, np.where(cells < 6, 0, np.where(cells < 11, 1, -1)))
