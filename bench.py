@@ -289,18 +289,25 @@ def run_e2e(case, args, dev_index):
         mark("destroy_s")
         return energy
 
-    job()  # warm-up (allocations, page-ins)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    energy = job()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    job()  # warm-up (allocations, page-ins, lazy module load)
+    best, best_phases, energy = None, None, 0.0
+    for _ in range(3):  # best of 3 jobs: the job is ~0.1 s and host-side noise (page faults, other tenants) is visible
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        energy = job()
+        torch.cuda.synchronize()
+        dt_job = time.perf_counter() - t0
+        if best is None or dt_job < best:
+            best, best_phases = dt_job, dict(phases)
+    dt = best
+    phases.update(best_phases)
     h2d = sum(t.numel() * 8 for t in host_in.values())
     d2h = sum(t.numel() * 8 for t in host_out.values())
     return {"value": n * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
             "d2h_bytes_per_step": d2h / args.steps + 24, "seconds": dt, "phases": {k: round(v, 4) for k, v in phases.items()},
             "what": "one job = sp_create + upload of x,v,rho,type from pinned host memory, K steps driven call by "
-                    "call through the C ABI with a per-step energy read-back, download of x,v,rho,P, sp_destroy",
+                    "call through the C ABI with a per-step energy read-back, download of x,v,rho,P, sp_destroy; "
+                    "best of 3 jobs",
             "energy": energy}
 
 

@@ -448,6 +448,10 @@ __global__ void __launch_bounds__(128, 4) k_sweep_mask(SpGrid g, SweepCtx c, typ
     Op::load(P, i, xi, yi, zi, p, acc);
     const double T2 = g.T2;
     const float thr = c.thr;
+    unsigned long long ui2, vi2, wi2;  // own coordinates duplicated into FP32x2 registers
+    asm("mov.b64 %0, {%1,%1};" : "=l"(ui2) : "f"(ui));
+    asm("mov.b64 %0, {%1,%1};" : "=l"(vi2) : "f"(vi));
+    asm("mov.b64 %0, {%1,%1};" : "=l"(wi2) : "f"(wi));
     unsigned m0 = 0u, m1 = 0u, m2 = 0u;  // pending chunks (newest in m0)
     int b0 = 0, b1 = 0, b2 = 0;          // first slot of each pending chunk
     auto run = [&](unsigned m, int base) {
@@ -479,18 +483,36 @@ __global__ void __launch_bounds__(128, 4) k_sweep_mask(SpGrid g, SweepCtx c, typ
             if (khi > g.key_max) khi = g.key_max;
             if (klo > khi) continue;
             const int jb = c.cell_start[klo], je = c.cell_start[khi + 1];
-            for (int j0 = jb; j0 < je; j0 += 32) {
+            // chunks of 32 slots starting at an even slot, so two candidates share one 64-bit load per plane and
+            // one packed FP32x2 instruction per operation (FADD2 / FMUL2 / FFMA2 on sm_100)
+            for (int j0 = jb & ~1; j0 < je; j0 += 32) {
                 const int nj = min(32, je - j0);
                 unsigned m = 0u;
                 // phase 1: conservative FP32 pre-filter in cell units (never rejects a true neighbour, see launch)
-#pragma unroll 8
-                for (int t = 0; t < nj; t++) {
-                    const int j = j0 + t;
-                    const float dx = ui - c.ux[j], dy = vi - c.uy[j], dz = wi - c.uz[j];
-                    const float dd = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+#pragma unroll
+                for (int u = 0; u < 16; u++) {
+                    if (2 * u >= nj) break;
+                    const unsigned long long qx = __ldg(reinterpret_cast<const unsigned long long*>(c.ux + j0) + u);
+                    const unsigned long long qy = __ldg(reinterpret_cast<const unsigned long long*>(c.uy + j0) + u);
+                    const unsigned long long qz = __ldg(reinterpret_cast<const unsigned long long*>(c.uz + j0) + u);
+                    unsigned long long dx, dy, dz, dd;
+                    asm("sub.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(ui2), "l"(qx));
+                    asm("sub.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(vi2), "l"(qy));
+                    asm("sub.f32x2 %0, %1, %2;" : "=l"(dz) : "l"(wi2), "l"(qz));
+                    asm("mul.f32x2 %0, %1, %1;" : "=l"(dd) : "l"(dx));
+                    asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(dd) : "l"(dy), "l"(dd));
+                    asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(dd) : "l"(dz), "l"(dd));
+                    float d0, d1;
+                    asm("mov.b64 {%0,%1}, %2;" : "=f"(d0), "=f"(d1) : "l"(dd));
                     // !(dd > thr) also keeps NaN distances, which the reference lets through as well
-                    m |= (!(dd > thr) ? 1u : 0u) << t;
+                    if (!(d0 > thr)) m |= 1u << (2 * u);
+                    if (!(d1 > thr)) m |= 2u << (2 * u);
                 }
+                // only slots of this row range count (the aligned chunk may start one slot early / end one late)
+                const int lo_bit = max(jb - j0, 0);
+                unsigned valid = nj >= 32 ? 0xffffffffu : ((1u << nj) - 1u);
+                valid &= ~((1u << lo_bit) - 1u);
+                m &= valid;
                 if (m2) drain();
                 m2 = m1; b2 = b1;
                 m1 = m0; b1 = b0;
