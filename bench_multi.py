@@ -182,9 +182,14 @@ def run_multi(args, METRIC, UNIT, ClockSampler, peaks):
         return e, nl
 
     s_warm = make_system()
+    s_warm.create_cell_list()
     job(s_warm)
     s_warm.close()
     s_job = make_system()
+    # NCCL sets up its peer-to-peer and ring connections lazily at the first send/recv and all-reduce of a new
+    # communicator (hundreds of ms): trigger both on the still empty system, outside the timed region
+    s_job.create_cell_list()
+    s_job.allreduce([0.0])
     s_job.synchronize()
     dist.barrier()
     torch.cuda.synchronize()

@@ -123,6 +123,7 @@ int sp_time_begin(sp_system* s);
 int sp_time_end(sp_system* s);
 void sp_slab_free(sp_system* s);  // sp_slab.cu
 int sp_build_cells(sp_system* s);  // sp_cells.cu
+void sp_slab_host_touched(sp_system* s);  // positions / particle set changed by the host: full selection next time
 const double* sp_slab_ghost_mask(sp_system* s);  // nullptr unless a slab system: 0 = owned, 1/2 = ghost
 
 // ------------------------------------------------------------------ device helpers

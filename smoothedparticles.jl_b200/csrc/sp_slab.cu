@@ -84,6 +84,11 @@ struct SlabState {
     long long n_send[2] = {0, 0};   // ghost message sizes sent down / up at the last rebuild
     long long n_ghost[2] = {0, 0};  // ghosts received from below / above
     long long n_owned = 0;
+    // slot window of the selection passes: after a rebuild the slots are sorted by cell layer, and a particle moves
+    // less than one cell per step, so only slots [0, sel_a) and [sel_b, n) (three cell layers per side) can hold
+    // old ghosts, migrants or new boundary particles.  sel_valid is dropped whenever the host touched positions.
+    long long sel_a = 0, sel_b = 0;
+    bool sel_valid = false;
 };
 
 #define SP_NCCL(s, call)                                                                                  \
@@ -107,6 +112,10 @@ void sp_slab_free(sp_system* s) {
     s->slab = nullptr;
 }
 
+void sp_slab_host_touched(sp_system* s) {
+    if (s->slab) s->slab->sel_valid = false;
+}
+
 const double* sp_slab_ghost_mask(sp_system* s) {
     if (!s->slab) return nullptr;
     return s->fields[s->slab->f_ghost].d;
@@ -127,11 +136,18 @@ struct SlabPlanes {
     int axis_plane;  // index of the plane holding the slab-axis coordinate, or -1
 };
 
-// flags: dn[s] = 1 if the particle migrates to the lower neighbour, up[s] likewise; old ghosts are killed (x = NaN)
+// selection passes run over t in [0, n_sel): slot = t below sel_a, sel_b + (t - sel_a) above
+struct SlabSel {
+    long long a, b, n_sel;
+    __host__ __device__ long long slot(long long t) const { return t < a ? t : b + (t - a); }
+};
+
+// flags: dn[t] = 1 if the particle migrates to the lower neighbour, up[t] likewise; old ghosts are killed (x = NaN)
 __global__ void k_slab_classify(SpGrid g, int rank, int nranks, long long gphase, long long c0, long long c1,
-                                double* x, long long cap, const double* ghost, long long n, int* dn, int* up) {
-    const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (s >= n) return;
+                                double* x, long long cap, const double* ghost, SlabSel sel, int* dn, int* up) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= sel.n_sel) return;
+    const long long s = sel.slot(t);
     int fd = 0, fu = 0;
     if (ghost[s] != 0.0) {
         x[s] = nan("");  // dropped by the build
@@ -144,14 +160,15 @@ __global__ void k_slab_classify(SpGrid g, int rank, int nranks, long long gphase
             else if (ca >= c1) fu = (g.slab_periodic || rank < nranks - 1) ? 1 : 0;
         }
     }
-    dn[s] = fd;
-    up[s] = fu;
+    dn[t] = fd;
+    up[t] = fu;
 }
 // owned, alive particles in the first / last owned layer are sent as ghosts down / up
 __global__ void k_slab_boundary(SpGrid g, int rank, int nranks, long long gphase, long long c0, long long c1,
-                                const double* x, long long cap, const double* ghost, long long n, int* dn, int* up) {
-    const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (s >= n) return;
+                                const double* x, long long cap, const double* ghost, SlabSel sel, int* dn, int* up) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= sel.n_sel) return;
+    const long long s = sel.slot(t);
     int fd = 0, fu = 0;
     const double x0 = x[s];
     if (ghost[s] == 0.0 && x0 == x0) {
@@ -162,28 +179,37 @@ __global__ void k_slab_boundary(SpGrid g, int rank, int nranks, long long gphase
             if (ca == c1 - 1) fu = (g.slab_periodic || rank < nranks - 1) ? 1 : 0;
         }
     }
-    dn[s] = fd;
-    up[s] = fu;
+    dn[t] = fd;
+    up[t] = fu;
 }
 // message index of every selected slot (exclusive scans in posd/posu), -1 otherwise, as Float64 fields
+__global__ void k_slab_fill2(double* a, double* b, double v, long long n) {
+    const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (s < n) {
+        a[s] = v;
+        b[s] = v;
+    }
+}
 __global__ void k_slab_record(const int* fd, const int* fu, const int* posd, const int* posu, double* sdn, double* sup,
-                              long long n) {
-    const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    sdn[s] = fd[s] ? (double)posd[s] : -1.0;
-    sup[s] = fu[s] ? (double)posu[s] : -1.0;
+                              SlabSel sel) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= sel.n_sel) return;
+    const long long s = sel.slot(t);
+    sdn[s] = fd[t] ? (double)posd[t] : -1.0;
+    sup[s] = fu[t] ? (double)posu[t] : -1.0;
 }
-__global__ void k_slab_pack(SlabPlanes tab, const int* flag, const int* pos, long long n, double* buf, long long count) {
-    const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (s >= n || !flag[s]) return;
-    const long long t = pos[s];
-    for (int c = 0; c < tab.count; c++) buf[(size_t)c * count + t] = tab.p[c][s];
+__global__ void k_slab_pack(SlabPlanes tab, const int* flag, const int* pos, SlabSel sel, double* buf, long long count) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= sel.n_sel || !flag[t]) return;
+    const long long s = sel.slot(t);
+    const long long m = pos[t];
+    for (int c = 0; c < tab.count; c++) buf[(size_t)c * count + m] = tab.p[c][s];
 }
-__global__ void k_slab_kill(const int* fd, const int* fu, double* x, long long n) {
-    const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (s < n && (fd[s] | fu[s])) x[s] = nan("");
+__global__ void k_slab_kill(const int* fd, const int* fu, double* x, SlabSel sel) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t < sel.n_sel && (fd[t] | fu[t])) x[sel.slot(t)] = nan("");
 }
-__global__ void k_slab_unpack(SlabPlanes tab, const double* buf, long long count, long long base, double shift) {
+__global__ void k_slab_unpack(SlabPlanes tab, const double* buf, long long count, long long base, double shift, int* ref) {
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t >= count) return;
     for (int c = 0; c < tab.count; c++) {
@@ -191,6 +217,7 @@ __global__ void k_slab_unpack(SlabPlanes tab, const double* buf, long long count
         if (c == tab.axis_plane) v += shift;
         tab.p[c][base + t] = v;
     }
+    if (ref) ref[base + t] = (int)(base + t);
 }
 __global__ void k_slab_mark(double* ghost, double* hidx, double* sdn, double* sup, long long base, long long count,
                             double side) {
@@ -352,23 +379,33 @@ static int slab_round(sp_system* s, bool ghosts, long long* n_recv_lo, long long
     int* posu = s->tmp_slot;
     double* X = s->fields[0].d;
     const double* ghost = s->fields[sl->f_ghost].d;
-    if (n > 0) {
+    SlabSel sel;
+    if (sl->sel_valid && sl->sel_a < sl->sel_b && sl->sel_b <= n) {
+        sel.a = sl->sel_a;
+        sel.b = sl->sel_b;
+    } else {
+        sel.a = n;  // everything
+        sel.b = n;
+    }
+    sel.n_sel = sel.a + (n - sel.b);
+    const long long ns = sel.n_sel;
+    if (ns > 0) {
         if (!ghosts)
-            SP_LAUNCH(s, k_slab_classify, sp_blocks(n, B), B, 0, s->g, sl->rank, sl->nranks, sl->gphase, sl->c0, sl->c1, X,
-                      s->cap, ghost, n, fd, fu);
+            SP_LAUNCH(s, k_slab_classify, sp_blocks(ns, B), B, 0, s->g, sl->rank, sl->nranks, sl->gphase, sl->c0, sl->c1, X,
+                      s->cap, ghost, sel, fd, fu);
         else
-            SP_LAUNCH(s, k_slab_boundary, sp_blocks(n, B), B, 0, s->g, sl->rank, sl->nranks, sl->gphase, sl->c0, sl->c1, X,
-                      s->cap, ghost, n, fd, fu);
-        SP_CUDA(s, cudaMemcpyAsync(posd, fd, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, s->stream));
-        SP_CUDA(s, cudaMemcpyAsync(posu, fu, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, s->stream));
-        int rc = sp_exclusive_scan_i32(s, posd, n);
+            SP_LAUNCH(s, k_slab_boundary, sp_blocks(ns, B), B, 0, s->g, sl->rank, sl->nranks, sl->gphase, sl->c0, sl->c1, X,
+                      s->cap, ghost, sel, fd, fu);
+        SP_CUDA(s, cudaMemcpyAsync(posd, fd, (size_t)ns * sizeof(int), cudaMemcpyDeviceToDevice, s->stream));
+        SP_CUDA(s, cudaMemcpyAsync(posu, fu, (size_t)ns * sizeof(int), cudaMemcpyDeviceToDevice, s->stream));
+        int rc = sp_exclusive_scan_i32(s, posd, ns);
         if (rc) return rc;
-        if ((rc = sp_exclusive_scan_i32(s, posu, n))) return rc;
+        if ((rc = sp_exclusive_scan_i32(s, posu, ns))) return rc;
         // totals = last exclusive value + last flag
-        SP_CUDA(s, cudaMemcpyAsync(sl->h_cnt + 4, posd + n - 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-        SP_CUDA(s, cudaMemcpyAsync(sl->h_cnt + 5, fd + n - 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-        SP_CUDA(s, cudaMemcpyAsync(sl->h_cnt + 6, posu + n - 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-        SP_CUDA(s, cudaMemcpyAsync(sl->h_cnt + 7, fu + n - 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        SP_CUDA(s, cudaMemcpyAsync(sl->h_cnt + 4, posd + ns - 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        SP_CUDA(s, cudaMemcpyAsync(sl->h_cnt + 5, fd + ns - 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        SP_CUDA(s, cudaMemcpyAsync(sl->h_cnt + 6, posu + ns - 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        SP_CUDA(s, cudaMemcpyAsync(sl->h_cnt + 7, fu + ns - 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
         SP_CUDA(s, cudaStreamSynchronize(s->stream));
     } else
         sl->h_cnt[4] = sl->h_cnt[5] = sl->h_cnt[6] = sl->h_cnt[7] = 0;
@@ -376,8 +413,12 @@ static int slab_round(sp_system* s, bool ghosts, long long* n_recv_lo, long long
     long long recv_lo = 0, recv_hi = 0;
     int rc = slab_exchange_counts(s, send_dn, send_up, &recv_lo, &recv_hi);
     if (rc) return rc;
-    if (ghosts && n > 0)
-        SP_LAUNCH(s, k_slab_record, sp_blocks(n, B), B, 0, fd, fu, posd, posu, s->fields[sl->f_sdn].d, s->fields[sl->f_sup].d, n);
+    if (ghosts && n > 0) {
+        SP_LAUNCH(s, k_slab_fill2, sp_blocks(n, B), B, 0, s->fields[sl->f_sdn].d, s->fields[sl->f_sup].d, -1.0, n);
+        if (ns > 0)
+            SP_LAUNCH(s, k_slab_record, sp_blocks(ns, B), B, 0, fd, fu, posd, posu, s->fields[sl->f_sdn].d,
+                      s->fields[sl->f_sup].d, sel);
+    }
     std::vector<SlabPlanes> tabs;
     int nplanes = 0;
     slab_planes(s, tabs, &nplanes);
@@ -386,11 +427,11 @@ static int slab_round(sp_system* s, bool ghosts, long long* n_recv_lo, long long
     // pack
     int plane0 = 0;
     for (SlabPlanes& t : tabs) {
-        if (send_dn) SP_LAUNCH(s, k_slab_pack, sp_blocks(n, B), B, 0, t, fd, posd, n, sl->sendbuf[0] + (size_t)plane0 * send_dn, send_dn);
-        if (send_up) SP_LAUNCH(s, k_slab_pack, sp_blocks(n, B), B, 0, t, fu, posu, n, sl->sendbuf[1] + (size_t)plane0 * send_up, send_up);
+        if (send_dn) SP_LAUNCH(s, k_slab_pack, sp_blocks(ns, B), B, 0, t, fd, posd, sel, sl->sendbuf[0] + (size_t)plane0 * send_dn, send_dn);
+        if (send_up) SP_LAUNCH(s, k_slab_pack, sp_blocks(ns, B), B, 0, t, fu, posu, sel, sl->sendbuf[1] + (size_t)plane0 * send_up, send_up);
         plane0 += t.count;
     }
-    if (!ghosts && (send_dn || send_up)) SP_LAUNCH(s, k_slab_kill, sp_blocks(n, B), B, 0, fd, fu, X, n);
+    if (!ghosts && (send_dn || send_up)) SP_LAUNCH(s, k_slab_kill, sp_blocks(ns, B), B, 0, fd, fu, X, sel);
     if ((rc = slab_exchange_payload(s, send_dn, send_up, recv_lo, recv_hi, nplanes))) return rc;
     // append arrivals after the current particles
     const long long n_new = n + recv_lo + recv_hi;
@@ -405,8 +446,9 @@ static int slab_round(sp_system* s, bool ghosts, long long* n_recv_lo, long long
     const double shift_hi = (sl->periodic && sl->rank == sl->nranks - 1) ? sl->period : 0.0;  // came from rank 0
     plane0 = 0;
     for (SlabPlanes& t : tabs) {
-        if (recv_lo) SP_LAUNCH(s, k_slab_unpack, sp_blocks(recv_lo, B), B, 0, t, sl->recvbuf[0] + (size_t)plane0 * recv_lo, recv_lo, n, shift_lo);
-        if (recv_hi) SP_LAUNCH(s, k_slab_unpack, sp_blocks(recv_hi, B), B, 0, t, sl->recvbuf[1] + (size_t)plane0 * recv_hi, recv_hi, n + recv_lo, shift_hi);
+        int* ref = plane0 == 0 ? s->ref : nullptr;  // arrivals are numbered by their slot
+        if (recv_lo) SP_LAUNCH(s, k_slab_unpack, sp_blocks(recv_lo, B), B, 0, t, sl->recvbuf[0] + (size_t)plane0 * recv_lo, recv_lo, n, shift_lo, ref);
+        if (recv_hi) SP_LAUNCH(s, k_slab_unpack, sp_blocks(recv_hi, B), B, 0, t, sl->recvbuf[1] + (size_t)plane0 * recv_hi, recv_hi, n + recv_lo, shift_hi, ref);
         plane0 += t.count;
     }
     if (ghosts) {
@@ -532,16 +574,27 @@ int32_t sp_slab_create_cell_list(sp_system* s) {
     sl->n_send[0] = sd;
     sl->n_send[1] = su;
     // 4: local build; the reference numbering has no meaning across ranks: slots are renumbered in place
-    if (s->n) SP_LAUNCH(s, k_slab_iota, sp_blocks(s->n, 256), 256, 0, s->ref, s->n);
+    // (ref is already the slot order unless the host added or re-ordered particles since the last rebuild)
+    if (s->n && !sl->sel_valid) SP_LAUNCH(s, k_slab_iota, sp_blocks(s->n, 256), 256, 0, s->ref, s->n);
     if ((rc = sp_build_cells(s))) return rc;
     if (s->n) SP_LAUNCH(s, k_slab_iota, sp_blocks(s->n, 256), 256, 0, s->ref, s->n);
     s->identity_order = true;
-    // owned count
+    // owned count, and the slot window of the next rebuild's selection passes (three cell layers per side)
     SP_CUDA(s, cudaMemsetAsync(sl->d_cnt + 8, 0, sizeof(int), s->stream));
     if (s->n)
         SP_LAUNCH(s, k_slab_count_owned, sp_blocks(s->n, 256), 256, 0, s->fields[sl->f_ghost].d, s->n, sl->d_cnt + 8);
     SP_CUDA(s, cudaMemcpyAsync(sl->h_cnt + 8, sl->d_cnt + 8, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    const long long layer = s->g.lim[0] * (sl->axis == 2 ? s->g.lim[1] : 1);  // cells per layer
+    const long long nl = s->g.lim[sl->axis];
+    const bool window = nl >= 8;
+    if (window) {
+        SP_CUDA(s, cudaMemcpyAsync(sl->h_cnt + 9, s->cell_start + 3 * layer + 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        SP_CUDA(s, cudaMemcpyAsync(sl->h_cnt + 10, s->cell_start + (nl - 3) * layer + 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    }
     SP_CUDA(s, cudaStreamSynchronize(s->stream));
+    sl->sel_valid = window;
+    sl->sel_a = sl->h_cnt[9];
+    sl->sel_b = sl->h_cnt[10];
     sl->n_owned = sl->h_cnt[8];
     return sp_time_end(s);
 }

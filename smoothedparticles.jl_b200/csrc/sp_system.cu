@@ -344,6 +344,7 @@ int32_t sp_resize(sp_system* s, int64_t n) {
     if (n >= (1LL << 31) - 256) return sp_fail(s, SP_ERR_INVALID, "particle count exceeds 31 bits");
     SP_CUDA(s, cudaSetDevice(s->device));
     if (n == s->n) return SP_OK;
+    sp_slab_host_touched(s);
     if (n < s->n) {
         int rc = restore_reference_order(s);
         if (rc) return rc;
@@ -382,6 +383,7 @@ int32_t sp_upload(sp_system* s, int32_t fid, const double* host, int64_t n, int3
     if (n == 0) return SP_OK;
     SP_CUDA(s, cudaSetDevice(s->device));
     SpField& f = s->fields[fid];
+    if (fid == 0) sp_slab_host_touched(s);
     int rc = sp_time_begin(s);
     if (rc) return rc;
     if (s->identity_order && layout == SP_LAYOUT_SOA) {
