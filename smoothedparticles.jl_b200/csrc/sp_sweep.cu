@@ -525,6 +525,173 @@ __global__ void __launch_bounds__(128, 4) k_sweep_mask(SpGrid g, SweepCtx c, typ
     Op::store(P, i, p, acc);
 }
 
+// ---- hit-mask kernel, two targets per thread.
+// Adjacent slots are almost always in the same cell, so they share their candidate rows: one thread owns the
+// targets 2t and 2t+1, loads every candidate pair once and tests it against both (half the L1 traffic and a
+// quarter fewer instructions per test in phase 1, two independent dependency chains).  Each target keeps its own
+// masks, restricted to its own row range, so the visited set per target is exactly the reference's.  When the two
+// targets are not in the same or adjacent cells (end of a cell row) they are swept one after the other.
+template <class Op>
+__global__ void __launch_bounds__(128, 4) k_sweep_mask2(SpGrid g, SweepCtx c, typename Op::Params P, int self_flag) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int iA = 2 * t, iB = 2 * t + 1;
+    if (iA >= c.n) return;
+    const bool actA = Op::active(P, iA);
+    const bool actB = (iB < c.n) && Op::active(P, iB);
+    if (!actA && !actB) return;
+    const double T2 = g.T2;
+    const float thr = c.thr;
+    const long long L1 = g.lim[0], L12 = g.lim[0] * g.lim[1];
+    const int nk = (g.dim == 2) ? 0 : 1;
+
+    double xA = 0, yA = 0, zA = 0, xB = 0, yB = 0, zB = 0;
+    long long keyA = 0, keyB = 0;
+    typename Op::PS pA, pB;
+    typename Op::Acc accA, accB;
+    unsigned long long uA = 0, vA = 0, wA = 0, uB = 0, vB = 0, wB = 0;
+    if (actA) {
+        xA = c.x[iA]; yA = c.y[iA]; zA = c.z[iA];
+        keyA = sp_find_key(g, xA, yA, zA);
+        Op::load(P, iA, xA, yA, zA, pA, accA);
+        const float a = c.ux[iA], b = c.uy[iA], d = c.uz[iA];
+        asm("mov.b64 %0, {%1,%1};" : "=l"(uA) : "f"(a));
+        asm("mov.b64 %0, {%1,%1};" : "=l"(vA) : "f"(b));
+        asm("mov.b64 %0, {%1,%1};" : "=l"(wA) : "f"(d));
+    }
+    if (actB) {
+        xB = c.x[iB]; yB = c.y[iB]; zB = c.z[iB];
+        keyB = sp_find_key(g, xB, yB, zB);
+        Op::load(P, iB, xB, yB, zB, pB, accB);
+        const float a = c.ux[iB], b = c.uy[iB], d = c.uz[iB];
+        asm("mov.b64 %0, {%1,%1};" : "=l"(uB) : "f"(a));
+        asm("mov.b64 %0, {%1,%1};" : "=l"(vB) : "f"(b));
+        asm("mov.b64 %0, {%1,%1};" : "=l"(wB) : "f"(d));
+    }
+    const bool both = actA && actB;
+    const bool near = both && (keyA - keyB <= 1) && (keyB - keyA <= 1);
+    const int npass = (both && !near) ? 2 : 1;
+
+    for (int pass = 0; pass < npass; pass++) {
+        // which targets this pass sweeps
+        const bool onA = actA && (pass == 0);
+        const bool onB = actB && (npass == 1 || pass == 1);
+        unsigned mA0 = 0u, mA1 = 0u, mA2 = 0u, mB0 = 0u, mB1 = 0u, mB2 = 0u;  // pending chunks (newest in *0)
+        int b0 = 0, b1 = 0, b2 = 0;
+        auto runA = [&](unsigned m, int base) {
+            while (m) {
+                const int j = base + __ffs(m) - 1;
+                m &= m - 1;
+                const double dx = __dsub_rn(xA, c.x[j]), dy = __dsub_rn(yA, c.y[j]), dz = __dsub_rn(zA, c.z[j]);
+                const double d2 = sp_d2(dx, dy, dz);
+                // the decision itself: (r > h || p == q) && continue (core.jl:105)  <=>  d2 > T2, r = sqrt_rn(d2)
+                if (d2 > T2 || j == iA) continue;
+                QGlobal<Op::NQ> q{P.qp, j};
+                Op::pair(P, pA, q, dx, dy, dz, sp_sqrt_fast(d2), accA);
+            }
+        };
+        auto runB = [&](unsigned m, int base) {
+            while (m) {
+                const int j = base + __ffs(m) - 1;
+                m &= m - 1;
+                const double dx = __dsub_rn(xB, c.x[j]), dy = __dsub_rn(yB, c.y[j]), dz = __dsub_rn(zB, c.z[j]);
+                const double d2 = sp_d2(dx, dy, dz);
+                if (d2 > T2 || j == iB) continue;
+                QGlobal<Op::NQ> q{P.qp, j};
+                Op::pair(P, pB, q, dx, dy, dz, sp_sqrt_fast(d2), accB);
+            }
+        };
+        auto drain = [&]() {
+            runA(mA2, b2); runA(mA1, b1); runA(mA0, b0);
+            runB(mB2, b2); runB(mB1, b1); runB(mB0, b0);
+            mA0 = mA1 = mA2 = mB0 = mB1 = mB2 = 0u;
+        };
+        for (int dk = -nk; dk <= nk; dk++) {
+            for (int dj = -1; dj <= 1; dj++) {
+                // own row range of each swept target, then their union
+                int jbA = 0, jeA = 0, jbB = 0, jeB = 0;
+                if (onA) {
+                    const long long mid = keyA + L1 * dj + L12 * dk;
+                    long long klo = mid - 1, khi = mid + 1;
+                    if (klo < 1) klo = 1;
+                    if (khi > g.key_max) khi = g.key_max;
+                    if (klo <= khi) {
+                        jbA = c.cell_start[klo];
+                        jeA = c.cell_start[khi + 1];
+                    }
+                }
+                if (onB) {
+                    const long long mid = keyB + L1 * dj + L12 * dk;
+                    long long klo = mid - 1, khi = mid + 1;
+                    if (klo < 1) klo = 1;
+                    if (khi > g.key_max) khi = g.key_max;
+                    if (klo <= khi) {
+                        jbB = c.cell_start[klo];
+                        jeB = c.cell_start[khi + 1];
+                    }
+                }
+                const bool hasA = jeA > jbA, hasB = jeB > jbB;
+                if (!hasA && !hasB) continue;
+                const int jb = hasA && hasB ? min(jbA, jbB) : hasA ? jbA : jbB;
+                const int je = hasA && hasB ? max(jeA, jeB) : hasA ? jeA : jeB;
+                for (int j0 = jb & ~1; j0 < je; j0 += 32) {
+                    const int nj = min(32, je - j0);
+                    unsigned mA = 0u, mB = 0u;
+                    // phase 1: conservative FP32 pre-filter, two candidates per load, both targets per candidate
+#pragma unroll
+                    for (int u = 0; u < 16; u++) {
+                        if (2 * u >= nj) break;
+                        const unsigned long long qx = __ldg(reinterpret_cast<const unsigned long long*>(c.ux + j0) + u);
+                        const unsigned long long qy = __ldg(reinterpret_cast<const unsigned long long*>(c.uy + j0) + u);
+                        const unsigned long long qz = __ldg(reinterpret_cast<const unsigned long long*>(c.uz + j0) + u);
+                        unsigned long long dx, dy, dz, dd;
+                        float d0, d1;
+                        asm("sub.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(uA), "l"(qx));
+                        asm("sub.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(vA), "l"(qy));
+                        asm("sub.f32x2 %0, %1, %2;" : "=l"(dz) : "l"(wA), "l"(qz));
+                        asm("mul.f32x2 %0, %1, %1;" : "=l"(dd) : "l"(dx));
+                        asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(dd) : "l"(dy), "l"(dd));
+                        asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(dd) : "l"(dz), "l"(dd));
+                        asm("mov.b64 {%0,%1}, %2;" : "=f"(d0), "=f"(d1) : "l"(dd));
+                        if (!(d0 > thr)) mA |= 1u << (2 * u);
+                        if (!(d1 > thr)) mA |= 2u << (2 * u);
+                        asm("sub.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(uB), "l"(qx));
+                        asm("sub.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(vB), "l"(qy));
+                        asm("sub.f32x2 %0, %1, %2;" : "=l"(dz) : "l"(wB), "l"(qz));
+                        asm("mul.f32x2 %0, %1, %1;" : "=l"(dd) : "l"(dx));
+                        asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(dd) : "l"(dy), "l"(dd));
+                        asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(dd) : "l"(dz), "l"(dd));
+                        asm("mov.b64 {%0,%1}, %2;" : "=f"(d0), "=f"(d1) : "l"(dd));
+                        if (!(d0 > thr)) mB |= 1u << (2 * u);
+                        if (!(d1 > thr)) mB |= 2u << (2 * u);
+                    }
+                    // each target only sees the slots of its OWN row range
+                    auto window = [&](int lo, int hi) -> unsigned {
+                        const int a = max(lo - j0, 0), b = min(hi - j0, 32);
+                        if (b <= a) return 0u;
+                        const unsigned up = b >= 32 ? 0xffffffffu : ((1u << b) - 1u);
+                        return up & ~((1u << a) - 1u);
+                    };
+                    mA &= hasA ? window(jbA, jeA) : 0u;
+                    mB &= hasB ? window(jbB, jeB) : 0u;
+                    if (mA2 | mB2) drain();
+                    mA2 = mA1; mB2 = mB1; b2 = b1;
+                    mA1 = mA0; mB1 = mB0; b1 = b0;
+                    mA0 = mA;  mB0 = mB;  b0 = j0;
+                }
+            }
+            drain();
+        }
+    }
+    if (actA) {
+        if (self_flag & 1) Op::self(P, pA, accA);
+        Op::store(P, iA, pA, accA);
+    }
+    if (actB) {
+        if (self_flag & 1) Op::self(P, pB, accB);
+        Op::store(P, iB, pB, accB);
+    }
+}
+
 // ---- packed-record kernel (experimental, SP_FLAG_PACKED_KERNEL).
 // One thread per target, candidates read through L1 — but from two 32-byte records per particle that a
 // prep pass packs from the SoA planes:  pk0 = {x, y, z, qa}  pk1 = {q0, q1, q2, qb}, so a candidate test costs
@@ -749,10 +916,13 @@ static int launch_sweep(sp_system* s, const typename Op::Params& P, int flags) {
     }
     if (!packed) {
         // default: one thread per target over the sorted SoA planes (L1-resident candidate rows), register hit masks
-        if (getenv("SP_SWEEP_NOMASK"))
+        static const int mask_mode = getenv("SP_SWEEP_MASK") ? atoi(getenv("SP_SWEEP_MASK")) : 1;  // 2 = two targets per thread (slower, see profiles/r1_sweep_exploration.md)
+        if (mask_mode == 0)
             SP_LAUNCH(s, (k_sweep<Op, false>), sp_blocks(s->n, 128), 128, 0, s->g, c, P, self_flag);
-        else
+        else if (mask_mode == 1)
             SP_LAUNCH(s, (k_sweep_mask<Op>), sp_blocks(s->n, 128), 128, 0, s->g, c, P, self_flag);
+        else
+            SP_LAUNCH(s, (k_sweep_mask2<Op>), sp_blocks((s->n + 1) / 2, 128), 128, 0, s->g, c, P, self_flag);
         return SP_OK;
     }
     // SP_FLAG_PACKED_KERNEL: packed-record two-phase kernel (experimental, see profiles/r1_sweep_exploration.md)
