@@ -239,6 +239,10 @@ int32_t sp_get_cell_list(sp_system* sys, int64_t* offsets /* key_max+1 */, int64
  * ids[offsets[i] .. offsets[i+1]) = 1-based indices q in the reference's visiting order.
  * Call with ids == NULL to get only offsets (offsets[n] = total). */
 int32_t sp_get_neighbour_lists(sp_system* sys, int64_t* offsets /* n+1 */, int64_t* ids, int64_t ids_cap);
+/* The neighbour lists the default pair sweeps actually replay (the per-position-version cache built by the first
+ * sweep after positions change; built here if needed).  Same id SET per particle as sp_get_neighbour_lists; the
+ * order is the default sweep's visiting order (stencil rows dk,dj outer, slots ascending), not the reference's. */
+int32_t sp_get_sweep_neighbour_lists(sp_system* sys, int64_t* offsets /* n+1 */, int64_t* ids, int64_t ids_cap);
 /* Number of particles removed by all sp_create_cell_list calls so far. */
 int32_t sp_num_removed(sp_system* sys, int64_t* n_removed);
 /* Device timing of the last call in ms (CUDA events on the handle's stream). */

@@ -220,6 +220,7 @@ int sp_permute_all(sp_system* s, long long n_keep) {
 
 int sp_build_cells(sp_system* s) {
     const SpGrid& g = s->g;
+    s->x_version++;  // the slot order changes
     const int B = 256;
     const long long N = s->n;
     const long long K = g.key_max;

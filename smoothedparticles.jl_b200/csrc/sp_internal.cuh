@@ -73,8 +73,16 @@ struct sp_system {
     long long stage_len = 0;    // in doubles
     void* pk = nullptr;         // 2 x cap packed 32-byte records (default sweep kernel)
     long long pk_cap = 0;
-    float* ucoord = nullptr;    // 3 planes of FP32 cell-unit coordinates (tile kernel pre-filter)
+    float* ucoord = nullptr;    // 3 planes of FP32 cell-unit coordinates (sweep pre-filter)
     long long ucoord_cap = 0;
+    long long x_version = 1;       // bumped whenever positions or the slot order may have changed
+    long long ucoord_version = 0;  // x_version the ucoord planes were computed for
+    int* nbr_ids = nullptr;        // cached neighbour lists (sp_sweep.cu): cap/32 warp tiles x CAPK x 32 slots
+    int* nbr_cnt = nullptr;        // neighbours per target slot
+    long long nbr_cap = 0;
+    long long nbr_version = 0;     // x_version the lists were built for
+    long long nbr_n = 0;
+    int nbr_group = 0;             // lanes per target the list layout was written for
     double* dscal = nullptr;    // CG scalars + dot partials (3*1024 + 16 doubles)
     double* h_scal = nullptr;   // pinned mirror of a few scalars
 

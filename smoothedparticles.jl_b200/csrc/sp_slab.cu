@@ -460,6 +460,7 @@ static int slab_round(sp_system* s, bool ghosts, long long* n_recv_lo, long long
         if (recv_hi) SP_LAUNCH(s, k_slab_mark, sp_blocks(recv_hi, B), B, 0, gh, hx, sd, su, n + recv_lo, recv_hi, 2.0);
     }
     s->n = n_new;
+    s->x_version++;
     *n_recv_lo = recv_lo;
     *n_recv_hi = recv_hi;
     *n_sent_dn = send_dn;
@@ -633,6 +634,7 @@ int32_t sp_slab_halo_refresh(sp_system* s, const int32_t* fields, int32_t nfield
     for (int k = 0; k < nfields && n > 0; k++) {
         SpField& f = s->fields[fields[k]];
         const int axis_comp = fields[k] == 0 ? sl->axis : -1;
+        if (fields[k] == 0) s->x_version++;
         if (rl || rh)
             SP_LAUNCH(s, k_slab_refresh_unpack, sp_blocks(n, B), B, 0, f.d, s->cap, f.ncomp, s->fields[sl->f_ghost].d,
                       s->fields[sl->f_hidx].d, n, sl->recvbuf[0] + (size_t)c0 * rl, rl, sl->recvbuf[1] + (size_t)c0 * rh, rh,

@@ -21,7 +21,8 @@ struct SweepCtx {
     const double *x, *y, *z;
     const float *ux, *uy, *uz;  // cell-unit FP32 coordinates (x - lo)/h for the conservative pre-filter
     const int* cell_start;
-    float thr;                  // pre-filter threshold on the FP32 squared distance in cell units
+    float thr;                  // pre-filter threshold on the FP32 squared distance in cell units: above = not a neighbour
+    float thr_lo;               // at or below = certainly a neighbour (k_nbr_build)
     int n;
 };
 
@@ -525,6 +526,170 @@ __global__ void __launch_bounds__(128, 4) k_sweep_mask(SpGrid g, SweepCtx c, typ
     Op::store(P, i, p, acc);
 }
 
+// ---- neighbour-list cache (default path): build once per position version, replay per operator.
+// Positions do not change between the pair sweeps of one time step (WCSPH: balance_of_mass! and internal_force!;
+// ISPH: viscous_force!, div_L_lambda!, every CG mat-vec, internal_force!), so the op-independent part of
+// apply_binary! (core.jl:94-110: key, candidate cells, dist, r > h, identity) is evaluated ONCE by k_nbr_build and
+// its result — the exact accepted neighbour slots of every target, in visiting order — is stored in HBM:
+//   ids[((i >> 5) * CAPK + k) * 32 + (i & 31)]   k-th neighbour of target slot i (warp-tiled: a warp's k-th
+//                                                 entries are one 128-byte line)
+//   cnt[i]                                        number of neighbours (may exceed CAPK: such a target is swept
+//                                                 by the exact candidate scan instead, nothing is dropped)
+// k_sweep_list<Op> then runs only the pair bodies: no candidate loop, no predicate, ~88 % active lanes.
+// The cache is keyed on sp_system::x_version, which every position write / re-sort / resize bumps.
+#define SP_NBR_CAPK 64
+
+// The FP32 distance (cell units) classifies a candidate three ways — the rounding bound delta of the pre-filter is
+// symmetric (see launch_sweep): dd <= 1 - delta is certainly a neighbour, dd > 1 + delta certainly is not, and only
+// the thin shell in between (~0.1 % of the candidates) needs the exact FP64 predicate.  So the build kernel reads
+// FP64 positions only for those few.
+template <int G>
+__global__ void __launch_bounds__(128, 5) k_nbr_build(SpGrid g, SweepCtx c, int* __restrict__ cnt, int* __restrict__ ids) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    const float ui = c.ux[i], vi = c.uy[i], wi = c.uz[i];
+    const double T2 = g.T2;
+    const float thr = c.thr, thr_lo = c.thr_lo;
+    unsigned long long ui2, vi2, wi2;
+    asm("mov.b64 %0, {%1,%1};" : "=l"(ui2) : "f"(ui));
+    asm("mov.b64 %0, {%1,%1};" : "=l"(vi2) : "f"(vi));
+    asm("mov.b64 %0, {%1,%1};" : "=l"(wi2) : "f"(wi));
+    // entry k of target i lives at ((i / TPW) * (CAPK / G) + k / G) * 32 + (i % TPW) * G + k % G, TPW = 32 / G
+    const int TPW = 32 / G;
+    int* col = ids + ((size_t)(i / TPW) * (SP_NBR_CAPK / G) << 5) + (i % TPW) * G;
+    int n_out = 0;
+    unsigned m0 = 0u, m1 = 0u, m2 = 0u;  // pending chunks: candidates that may be neighbours (newest in m0)
+    unsigned s0 = 0u, s1 = 0u, s2 = 0u;  // ... of which certainly neighbours
+    int b0 = 0, b1 = 0, b2 = 0;
+    auto run = [&](unsigned m, unsigned sure, int base) {
+        while (m) {
+            const unsigned bit = m & (0u - m);
+            const int j = base + __ffs(m) - 1;
+            m ^= bit;
+            if (!(sure & bit)) {
+                // (r > h) && continue (core.jl:105)  <=>  d2 > T2 with r = sqrt_rn(d2), decided in FP64 as the reference does
+                const double dx = __dsub_rn(c.x[i], c.x[j]), dy = __dsub_rn(c.y[i], c.y[j]), dz = __dsub_rn(c.z[i], c.z[j]);
+                if (sp_d2(dx, dy, dz) > T2) continue;
+            }
+            if (j == i) continue;  // p == q (core.jl:105)
+            if (n_out < SP_NBR_CAPK) col[((n_out / G) << 5) + (n_out % G)] = j;
+            n_out++;
+        }
+    };
+    auto drain = [&]() {
+        run(m2, s2, b2);
+        run(m1, s1, b1);
+        run(m0, s0, b0);
+        m0 = m1 = m2 = 0u;
+    };
+    const long long key = sp_find_key(g, c.x[i], c.y[i], c.z[i]);  // core.jl:95
+    const long long L1 = g.lim[0], L12 = g.lim[0] * g.lim[1];
+    const int nk = (g.dim == 2) ? 0 : 1;
+    for (int dk = -nk; dk <= nk; dk++) {
+        for (int dj = -1; dj <= 1; dj++) {
+            const long long mid = key + L1 * dj + L12 * dk;
+            long long klo = mid - 1, khi = mid + 1;
+            if (klo < 1) klo = 1;
+            if (khi > g.key_max) khi = g.key_max;
+            if (klo > khi) continue;
+            const int jb = c.cell_start[klo], je = c.cell_start[khi + 1];
+            for (int j0 = jb & ~1; j0 < je; j0 += 32) {
+                const int nj = min(32, je - j0);
+                unsigned m = 0u, sure = 0u;
+#pragma unroll
+                for (int u = 0; u < 16; u++) {
+                    if (2 * u >= nj) break;
+                    const unsigned long long qx = __ldg(reinterpret_cast<const unsigned long long*>(c.ux + j0) + u);
+                    const unsigned long long qy = __ldg(reinterpret_cast<const unsigned long long*>(c.uy + j0) + u);
+                    const unsigned long long qz = __ldg(reinterpret_cast<const unsigned long long*>(c.uz + j0) + u);
+                    unsigned long long dx, dy, dz, dd;
+                    asm("sub.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(ui2), "l"(qx));
+                    asm("sub.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(vi2), "l"(qy));
+                    asm("sub.f32x2 %0, %1, %2;" : "=l"(dz) : "l"(wi2), "l"(qz));
+                    asm("mul.f32x2 %0, %1, %1;" : "=l"(dd) : "l"(dx));
+                    asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(dd) : "l"(dy), "l"(dd));
+                    asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(dd) : "l"(dz), "l"(dd));
+                    float d0, d1;
+                    asm("mov.b64 {%0,%1}, %2;" : "=f"(d0), "=f"(d1) : "l"(dd));
+                    // !(dd > thr) keeps NaN distances for the exact test, which lets them through like the reference
+                    if (!(d0 > thr)) m |= 1u << (2 * u);
+                    if (!(d1 > thr)) m |= 2u << (2 * u);
+                    if (d0 <= thr_lo) sure |= 1u << (2 * u);
+                    if (d1 <= thr_lo) sure |= 2u << (2 * u);
+                }
+                const int lo_bit = max(jb - j0, 0);
+                unsigned valid = nj >= 32 ? 0xffffffffu : ((1u << nj) - 1u);
+                valid &= ~((1u << lo_bit) - 1u);
+                m &= valid;
+                if (m2) drain();
+                m2 = m1; s2 = s1; b2 = b1;
+                m1 = m0; s1 = s0; b1 = b0;
+                m0 = m;  s0 = sure; b0 = j0;
+            }
+        }
+        drain();
+    }
+    cnt[i] = n_out;
+}
+
+// Replay: G adjacent lanes share one target and take every G-th entry of its list, so a warp covers 32/G
+// consecutive slots (about one cell for G = 4): the G lanes of a target read neighbouring slots and the targets of
+// one cell walk the same candidate rows, which cuts the distinct cache lines per gather (the L1 data pipe is what
+// bounds this kernel).  Partial sums are combined by a fixed xor-butterfly, so results are deterministic.
+template <class Op, int G>
+__global__ void __launch_bounds__(128, 6) k_sweep_list(SpGrid g, SweepCtx c, const int* __restrict__ cnt,
+                                                       const int* __restrict__ ids, typename Op::Params P, int self_flag) {
+    constexpr int NACC = (int)(sizeof(typename Op::Acc) / sizeof(double));
+    static_assert(sizeof(typename Op::Acc) == NACC * sizeof(double), "Acc must be plain doubles");
+    const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int i = (int)(gt / G);
+    const int sub = (int)(gt % G);
+    // whole groups leave together (i is uniform within a group), so the group shuffles below are safe
+    if (i >= c.n) return;
+    if (!Op::active(P, i)) return;
+    const double xi = c.x[i], yi = c.y[i], zi = c.z[i];
+    typename Op::PS p;
+    typename Op::Acc acc;
+    Op::load(P, i, xi, yi, zi, p, acc);
+    double* av = reinterpret_cast<double*>(&acc);
+    if (G > 1 && sub != 0) {
+#pragma unroll
+        for (int a = 0; a < NACC; a++) av[a] = 0.0;
+    }
+    const int n_nb = cnt[i];
+    if (n_nb <= SP_NBR_CAPK) {
+        constexpr int TPW = 32 / G;  // targets per warp tile
+        const int* col = ids + ((size_t)(i / TPW) * (SP_NBR_CAPK / G) << 5) + (i % TPW) * G + sub;
+        const int n_it = (n_nb - sub + G - 1) / G;  // entries sub, sub+G, ...
+#pragma unroll 2
+        for (int k = 0; k < n_it; k++) {
+            const int j = __ldcs(col + (k << 5));
+            const double dx = __dsub_rn(xi, c.x[j]), dy = __dsub_rn(yi, c.y[j]), dz = __dsub_rn(zi, c.z[j]);
+            const double d2 = sp_d2(dx, dy, dz);
+            QGlobal<Op::NQ> q{P.qp, j};
+            Op::pair(P, p, q, dx, dy, dz, sp_sqrt_fast(d2), acc);
+        }
+    } else if (sub == 0) {
+        // more neighbours than the cache holds per target: the exact candidate scan, same visiting order
+        sp_for_candidates<false>(g, c, xi, yi, zi, [&](int j, double dx, double dy, double dz, double d2) {
+            if (d2 > g.T2 || j == i) return;
+            QGlobal<Op::NQ> q{P.qp, j};
+            Op::pair(P, p, q, dx, dy, dz, sp_sqrt_fast(d2), acc);
+        });
+    }
+    if (G > 1) {
+        const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << ((threadIdx.x & 31) / G * G);
+#pragma unroll
+        for (int a = 0; a < NACC; a++) {
+#pragma unroll
+            for (int d = 1; d < G; d <<= 1) av[a] += __shfl_xor_sync(gmask, av[a], d);
+        }
+        if (sub != 0) return;
+    }
+    if (self_flag & 1) Op::self(P, p, acc);
+    Op::store(P, i, p, acc);
+}
+
 // ---- hit-mask kernel, two targets per thread.
 // Adjacent slots are almost always in the same cell, so they share their candidate rows: one thread owns the
 // targets 2t and 2t+1, loads every candidate pair once and tests it against both (half the L1 traffic and a
@@ -745,6 +910,37 @@ __global__ void __launch_bounds__(256) k_pack(const double* __restrict__ x, long
     }
 }
 
+// list replay over packed 32-byte records (experimental, SP_SWEEP_MASK=4): 4 x LDG.128 per pair instead of 7 x LDG.64
+template <class Op>
+__global__ void __launch_bounds__(128, 6) k_sweep_list_pk(SpGrid g, SweepCtx c, const int* __restrict__ cnt,
+                                                          const int* __restrict__ ids, typename Op::Params P,
+                                                          const SpRec* __restrict__ pk0, const SpRec* __restrict__ pk1,
+                                                          int self_flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    if (!Op::active(P, i)) return;
+    const double xi = c.x[i], yi = c.y[i], zi = c.z[i];
+    typename Op::PS p;
+    typename Op::Acc acc;
+    Op::load(P, i, xi, yi, zi, p, acc);
+    const int n_nb = min(cnt[i], SP_NBR_CAPK);
+    const int* col = ids + ((size_t)(i >> 5) * SP_NBR_CAPK << 5) + (i & 31);
+#pragma unroll 2
+    for (int k = 0; k < n_nb; k++) {
+        const int j = __ldcs(col + (k << 5));
+        QPacked<Op::NQ> q;
+        q.qp = P.qp;
+        q.j = j;
+        q.r0 = sp_ld256(pk0 + j);
+        if (Op::NQ >= 2) q.r1 = sp_ld256(pk1 + j);
+        const double dx = __dsub_rn(xi, q.r0.a), dy = __dsub_rn(yi, q.r0.b), dz = __dsub_rn(zi, q.r0.c);
+        const double d2 = sp_d2(dx, dy, dz);
+        Op::pair(P, p, q, dx, dy, dz, sp_sqrt_fast(d2), acc);
+    }
+    if (self_flag & 1) Op::self(P, p, acc);
+    Op::store(P, i, p, acc);
+}
+
 template <class Op, int TP, int LCAP>
 __global__ void __launch_bounds__(TP) k_sweep_pk(SpGrid g, SweepCtx c, typename Op::Params P, const SpRec* __restrict__ pk0,
                                                  const SpRec* __restrict__ pk1, int self_flag) {
@@ -869,16 +1065,77 @@ static int launch_tile(sp_system* s, const SweepCtx& c, const typename Op::Param
     return SP_OK;
 }
 
-template <class Op>
-static int launch_sweep(sp_system* s, const typename Op::Params& P, int flags) {
-    if (s->n == 0) return SP_OK;
-    SweepCtx c;
+static void sp_sweep_ctx(sp_system* s, SweepCtx& c) {
     const double* X = s->fields[0].d;
     c.x = X;
     c.y = X + s->cap;
     c.z = X + 2 * s->cap;
+    c.ux = c.uy = c.uz = nullptr;
     c.cell_start = s->cell_start;
+    c.thr = c.thr_lo = 0.f;
     c.n = (int)s->n;
+}
+
+// FP32 pre-filter inputs: coordinates in cell units u = (x - lo)/h and thresholds that can never misclassify.
+// |u| <= U; rounding x -> u costs <= U*2^-24 per coordinate, the FP32 difference and the three products/sums a
+// few 2^-24 relative more:   |d2_f32 - d2/h^2| <= delta = 8*2^-23*U + 1e-6   for d2 <~ h^2.
+//   d2_f32 > 1 + delta   certainly not a neighbour        (thr)
+//   d2_f32 <= 1 - delta  certainly a neighbour            (thr_lo, used by k_nbr_build only)
+// Everything in between is decided by the exact FP64 predicate, so the neighbour set is the reference's bit for bit.
+static int sp_ensure_prefilter(sp_system* s, SweepCtx& c) {
+    if (!s->ucoord || s->ucoord_cap != s->cap) {
+        if (s->ucoord) SP_CUDA(s, cudaFree(s->ucoord));
+        s->ucoord = nullptr;
+        SP_CUDA(s, cudaMalloc(&s->ucoord, (size_t)3 * s->cap * sizeof(float)));
+        s->ucoord_cap = s->cap;
+        s->ucoord_version = 0;
+    }
+    if (s->ucoord_version != s->x_version) {  // positions unchanged since the last sweep: keep the planes
+        SP_LAUNCH(s, k_prefilter_coords, sp_blocks(s->n, 256), 256, 0, s->g, s->fields[0].d, s->cap, s->ucoord, s->n);
+        s->ucoord_version = s->x_version;
+    }
+    c.ux = s->ucoord;
+    c.uy = s->ucoord + s->cap;
+    c.uz = s->ucoord + 2 * s->cap;
+    // U bounds |u| from the GLOBAL box (on a slab system key_lim is only the local window along the slab axis)
+    double U = (double)std::max(std::max(s->g.lim[0], s->g.lim[1]), s->g.lim[2]);
+    for (int a = 0; a < 3; a++) U = std::max(U, std::ceil((s->g.hi[a] - s->g.lo[a]) / s->g.h) + 1.0);
+    U += 2.0;
+    c.thr = (float)(1.0 + 8.0 * U / 8388608.0 + 1e-6);
+    c.thr = std::nextafter(c.thr, 2.0f);
+    // 1e-6 more for the FP64 rounding of d2 and of T2 itself
+    c.thr_lo = (float)(1.0 - 8.0 * U / 8388608.0 - 2e-6);
+    c.thr_lo = std::nextafter(c.thr_lo, -1.0f);
+    return SP_OK;
+}
+
+// (re)build the cached neighbour lists if positions / slot order changed since they were built
+static int sp_ensure_nbr_cache(sp_system* s, SweepCtx& c) {
+    int rc = sp_ensure_prefilter(s, c);
+    if (rc) return rc;
+    if (!s->nbr_ids || s->nbr_cap != s->cap) {
+        if (s->nbr_ids) SP_CUDA(s, cudaFree(s->nbr_ids));
+        if (s->nbr_cnt) SP_CUDA(s, cudaFree(s->nbr_cnt));
+        s->nbr_ids = s->nbr_cnt = nullptr;
+        SP_CUDA(s, cudaMalloc(&s->nbr_ids, (size_t)s->cap * SP_NBR_CAPK * sizeof(int)));
+        SP_CUDA(s, cudaMalloc(&s->nbr_cnt, (size_t)s->cap * sizeof(int)));
+        s->nbr_cap = s->cap;
+        s->nbr_version = 0;
+    }
+    if (s->nbr_version != s->x_version || s->nbr_n != s->n) {
+        SP_LAUNCH(s, k_nbr_build<1>, sp_blocks(s->n, 128), 128, 0, s->g, c, s->nbr_cnt, s->nbr_ids);
+        s->nbr_version = s->x_version;
+        s->nbr_n = s->n;
+    }
+    return SP_OK;
+}
+
+template <class Op>
+static int launch_sweep(sp_system* s, const typename Op::Params& P, int flags) {
+    if (s->n == 0) return SP_OK;
+    SweepCtx c;
+    sp_sweep_ctx(s, c);
+    const double* X = s->fields[0].d;
     int self_flag = (flags & SP_FLAG_SELF) ? 1 : 0;
     if (const char* dbg = getenv("SP_DEBUG_SWEEP")) self_flag |= atoi(dbg) << 8;  // profiling switches only
     if (flags & SP_FLAG_STRICT_ORDER) {
@@ -889,25 +1146,8 @@ static int launch_sweep(sp_system* s, const typename Op::Params& P, int flags) {
     static const int variant = getenv("SP_SWEEP_VARIANT") ? atoi(getenv("SP_SWEEP_VARIANT")) : 0;
     const bool packed = (flags & SP_FLAG_PACKED_KERNEL) || variant == 1;
     if (!packed) {
-        // FP32 pre-filter inputs: coordinates in cell units u = (x - lo)/h and a threshold that can never reject
-        // a true neighbour.  |u| <= U = max key_lim + 2; rounding x -> u costs <= U*2^-24 per coordinate, the FP32
-        // difference and the three products/sums a few 2^-24 relative more:
-        //   d2_f32 <= d2/h^2 + 8*2^-23*U + 1e-6   for d2 <= h^2.
-        // Every candidate that passes is re-tested with the exact FP64 predicate, so the neighbour set is the
-        // reference's bit for bit.
-        if (!s->ucoord || s->ucoord_cap != s->cap) {
-            if (s->ucoord) SP_CUDA(s, cudaFree(s->ucoord));
-            s->ucoord = nullptr;
-            SP_CUDA(s, cudaMalloc(&s->ucoord, (size_t)3 * s->cap * sizeof(float)));
-            s->ucoord_cap = s->cap;
-        }
-        SP_LAUNCH(s, k_prefilter_coords, sp_blocks(s->n, 256), 256, 0, s->g, X, s->cap, s->ucoord, s->n);
-        c.ux = s->ucoord;
-        c.uy = s->ucoord + s->cap;
-        c.uz = s->ucoord + 2 * s->cap;
-        const double U = (double)std::max(std::max(s->g.lim[0], s->g.lim[1]), s->g.lim[2]) + 2.0;
-        c.thr = (float)(1.0 + 8.0 * U / 8388608.0 + 1e-6);
-        c.thr = std::nextafter(c.thr, 2.0f);
+        int rc = sp_ensure_prefilter(s, c);
+        if (rc) return rc;
     }
     if (tile) {
         // experimental shared-memory tile kernel (TMA-staged): see profiles/r1_sweep_exploration.md
@@ -916,8 +1156,30 @@ static int launch_sweep(sp_system* s, const typename Op::Params& P, int flags) {
     }
     if (!packed) {
         // default: one thread per target over the sorted SoA planes (L1-resident candidate rows), register hit masks
-        static const int mask_mode = getenv("SP_SWEEP_MASK") ? atoi(getenv("SP_SWEEP_MASK")) : 1;  // 2 = two targets per thread (slower, see profiles/r1_sweep_exploration.md)
-        if (mask_mode == 0)
+        // 3 (default) = cached neighbour lists; 1 = register hit masks per sweep; 2 = two targets per thread
+        // (slower, see profiles/r1_sweep_exploration.md); 0 = plain candidate scan
+        static const int mask_mode = getenv("SP_SWEEP_MASK") ? atoi(getenv("SP_SWEEP_MASK")) : 3;
+        if (mask_mode == 3 || mask_mode == 4) {
+            int rc = sp_ensure_nbr_cache(s, c);
+            if (rc) return rc;
+            const unsigned nb = sp_blocks(s->n, 128);
+            if (mask_mode == 3) {
+                SP_LAUNCH(s, (k_sweep_list<Op, 1>), nb, 128, 0, s->g, c, s->nbr_cnt, s->nbr_ids, P, self_flag);
+            } else {
+                if (!s->pk || s->pk_cap != s->cap) {
+                    if (s->pk) SP_CUDA(s, cudaFree(s->pk));
+                    s->pk = nullptr;
+                    SP_CUDA(s, cudaMalloc(&s->pk, (size_t)2 * s->cap * sizeof(SpRec)));
+                    s->pk_cap = s->cap;
+                }
+                SpRec* pk0 = reinterpret_cast<SpRec*>(s->pk);
+                SpRec* pk1 = pk0 + s->cap;
+                PackPlanes<Op::NQ> pl;
+                for (int k = 0; k < Op::NQ; k++) pl.qp[k] = P.qp[k];
+                SP_LAUNCH(s, (k_pack<Op::NQ>), sp_blocks(s->n, 256), 256, 0, X, s->cap, pl, pk0, pk1, (int)s->n);
+                SP_LAUNCH(s, (k_sweep_list_pk<Op>), nb, 128, 0, s->g, c, s->nbr_cnt, s->nbr_ids, P, pk0, pk1, self_flag);
+            }
+        } else if (mask_mode == 0)
             SP_LAUNCH(s, (k_sweep<Op, false>), sp_blocks(s->n, 128), 128, 0, s->g, c, P, self_flag);
         else if (mask_mode == 1)
             SP_LAUNCH(s, (k_sweep_mask<Op>), sp_blocks(s->n, 128), 128, 0, s->g, c, P, self_flag);
@@ -1086,6 +1348,7 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
         case SP_OP_MOVE: {
             NEED(4, 1, 3, 3, 3, 1);
             UMove::Params P{wv3(s, F[0]), rv3(s, F[1]), wv3(s, F[2]), sc(s, F[3]), Pm[0]};
+            if (F[0] == 0) s->x_version++;
             return launch_unary<UMove>(s, P);
         }
         case SP_OP_ACCELERATE: {
@@ -1120,22 +1383,26 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
         case SP_OP_FILL: {
             NEED(1, 1, 0);
             UFill::Params P{sc(s, F[0]), s->cap, s->fields[F[0]].ncomp, Pm[0]};
+            if (F[0] == 0) s->x_version++;
             return launch_unary<UFill>(s, P);
         }
         case SP_OP_ADVECT: {
             NEED(2, 1, 3, 3);
             UAdvect::Params P{wv3(s, F[0]), rv3(s, F[1]), Pm[0]};
+            if (F[0] == 0) s->x_version++;
             return launch_unary<UAdvect>(s, P);
         }
         case SP_OP_KICK: {
             NEED(2, 1, 3, 3);
             UKick::Params P{wv3(s, F[0]), rv3(s, F[1]), Pm[0]};
+            if (F[0] == 0) s->x_version++;
             return launch_unary<UKick>(s, P);
         }
         case SP_OP_ISPH_INITIALIZE: {
             NEED(6, 4, 3, 3, 1, 1, 1, 1);
             UIsphInitialize::Params P{wv3(s, F[0]), wv3(s, F[1]), sc(s, F[2]), sc(s, F[3]), sc(s, F[4]),
                                       sc(s, F[5]),  Pm[0],        Pm[1],       Pm[2],       Pm[3]};
+            if (F[0] == 0) s->x_version++;
             return launch_unary<UIsphInitialize>(s, P);
         }
         case SP_OP_ISPH_VISCOUS_FORCE: {
@@ -1224,7 +1491,86 @@ __global__ void k_nbr_fill(SpGrid g, SweepCtx c, const int* ref, const long long
     });
 }
 
+// the lists the default sweeps replay (cached), in their visiting order
+__global__ void k_cache_count(SpGrid g, SweepCtx c, const int* cnt, const int* ref, long long* counts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    counts[ref[i]] = cnt[i];
+}
+__global__ void k_cache_fill(SpGrid g, SweepCtx c, const int* cnt, const int* lists, const int* ref,
+                             const long long* offsets, long long* ids) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    long long o = offsets[ref[i]];
+    const int n_nb = cnt[i];
+    if (n_nb <= SP_NBR_CAPK) {
+        const int* col = lists + ((size_t)(i >> 5) * SP_NBR_CAPK << 5) + (i & 31);
+        for (int k = 0; k < n_nb; k++) ids[o++] = (long long)ref[col[k << 5]] + 1;
+    } else {
+        sp_for_candidates<false>(g, c, c.x[i], c.y[i], c.z[i], [&](int j, double, double, double, double d2) {
+            if (d2 > g.T2 || j == i) return;
+            ids[o++] = (long long)ref[j] + 1;
+        });
+    }
+}
+
+// shared tail of the two list exports: counts (by reference index) -> offsets on the host, then fill
+template <class Fill>
+static int sp_export_lists(sp_system* s, long long* counts, int64_t* offsets, int64_t* ids, int64_t ids_cap, Fill&& fill) {
+    const long long n = s->n;
+    std::vector<long long> h(n + 1);
+    SP_CUDA(s, cudaMemcpyAsync(h.data(), counts, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
+    SP_CUDA(s, cudaStreamSynchronize(s->stream));
+    long long run = 0;
+    for (long long i = 0; i < n; i++) {
+        long long cnt = h[i];
+        h[i] = run;
+        offsets[i] = run;
+        run += cnt;
+    }
+    h[n] = run;
+    offsets[n] = run;
+    if (!ids) return SP_OK;
+    if (ids_cap < run) return sp_fail(s, SP_ERR_INVALID, "ids buffer too small");
+    if (run == 0) return SP_OK;
+    long long *d_off = nullptr, *d_ids = nullptr;
+    SP_CUDA(s, cudaMalloc(&d_off, (size_t)(n + 1) * sizeof(long long)));
+    cudaError_t e = cudaMalloc(&d_ids, (size_t)run * sizeof(long long));
+    if (e != cudaSuccess) {
+        cudaFree(d_off);
+        return sp_fail_cuda(s, e, "cudaMalloc ids", __FILE__, __LINE__);
+    }
+    cudaMemcpyAsync(d_off, h.data(), (size_t)(n + 1) * sizeof(long long), cudaMemcpyHostToDevice, s->stream);
+    fill(d_off, d_ids);
+    s->launches++;
+    cudaMemcpyAsync(ids, d_ids, (size_t)run * sizeof(long long), cudaMemcpyDeviceToHost, s->stream);
+    e = cudaStreamSynchronize(s->stream);
+    cudaFree(d_off);
+    cudaFree(d_ids);
+    if (e != cudaSuccess) return sp_fail_cuda(s, e, "neighbour list export", __FILE__, __LINE__);
+    return SP_OK;
+}
+
 extern "C" {
+
+int32_t sp_get_sweep_neighbour_lists(sp_system* s, int64_t* offsets, int64_t* ids, int64_t ids_cap) {
+    if (!s || !offsets) return SP_ERR_INVALID;
+    if (!s->have_cells) return sp_fail(s, SP_ERR_STATE, "no cell list: call sp_create_cell_list first");
+    SP_CUDA(s, cudaSetDevice(s->device));
+    const long long n = s->n;
+    offsets[0] = 0;
+    if (n == 0) return SP_OK;
+    SweepCtx c;
+    sp_sweep_ctx(s, c);
+    int rc = sp_ensure_nbr_cache(s, c);
+    if (rc) return rc;
+    if ((rc = sp_ensure_stage(s, n + 1))) return rc;
+    long long* counts = (long long*)s->stage;
+    SP_LAUNCH(s, k_cache_count, sp_blocks(n, 128), 128, 0, s->g, c, s->nbr_cnt, s->ref, counts);
+    return sp_export_lists(s, counts, offsets, ids, ids_cap, [&](long long* d_off, long long* d_ids) {
+        k_cache_fill<<<sp_blocks(n, 128), 128, 0, s->stream>>>(s->g, c, s->nbr_cnt, s->nbr_ids, s->ref, d_off, d_ids);
+    });
+}
 
 int32_t sp_apply(sp_system* s, int32_t op, const int32_t* fields, int32_t nfields, const double* params, int32_t nparams,
                  int32_t flags) {
@@ -1253,47 +1599,14 @@ int32_t sp_get_neighbour_lists(sp_system* s, int64_t* offsets, int64_t* ids, int
     offsets[0] = 0;
     if (n == 0) return SP_OK;
     SweepCtx c;
-    const double* X = s->fields[0].d;
-    c.x = X;
-    c.y = X + s->cap;
-    c.z = X + 2 * s->cap;
-    c.cell_start = s->cell_start;
-    c.n = (int)n;
+    sp_sweep_ctx(s, c);
     int rc = sp_ensure_stage(s, n + 1);
     if (rc) return rc;
     long long* counts = (long long*)s->stage;
     SP_LAUNCH(s, k_nbr_count, sp_blocks(n, 128), 128, 0, s->g, c, s->ref, counts);
-    std::vector<long long> h(n + 1);
-    SP_CUDA(s, cudaMemcpyAsync(h.data(), counts, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
-    SP_CUDA(s, cudaStreamSynchronize(s->stream));
-    long long run = 0;
-    for (long long i = 0; i < n; i++) {
-        long long cnt = h[i];
-        h[i] = run;
-        offsets[i] = run;
-        run += cnt;
-    }
-    h[n] = run;
-    offsets[n] = run;
-    if (!ids) return SP_OK;
-    if (ids_cap < run) return sp_fail(s, SP_ERR_INVALID, "ids buffer too small");
-    if (run == 0) return SP_OK;
-    long long *d_off = nullptr, *d_ids = nullptr;
-    SP_CUDA(s, cudaMalloc(&d_off, (size_t)(n + 1) * sizeof(long long)));
-    cudaError_t e = cudaMalloc(&d_ids, (size_t)run * sizeof(long long));
-    if (e != cudaSuccess) {
-        cudaFree(d_off);
-        return sp_fail_cuda(s, e, "cudaMalloc ids", __FILE__, __LINE__);
-    }
-    cudaMemcpyAsync(d_off, h.data(), (size_t)(n + 1) * sizeof(long long), cudaMemcpyHostToDevice, s->stream);
-    k_nbr_fill<<<sp_blocks(n, 128), 128, 0, s->stream>>>(s->g, c, s->ref, d_off, d_ids);
-    s->launches++;
-    cudaMemcpyAsync(ids, d_ids, (size_t)run * sizeof(long long), cudaMemcpyDeviceToHost, s->stream);
-    e = cudaStreamSynchronize(s->stream);
-    cudaFree(d_off);
-    cudaFree(d_ids);
-    if (e != cudaSuccess) return sp_fail_cuda(s, e, "neighbour list export", __FILE__, __LINE__);
-    return SP_OK;
+    return sp_export_lists(s, counts, offsets, ids, ids_cap, [&](long long* d_off, long long* d_ids) {
+        k_nbr_fill<<<sp_blocks(n, 128), 128, 0, s->stream>>>(s->g, c, s->ref, d_off, d_ids);
+    });
 }
 
 }  // extern "C"

@@ -144,6 +144,7 @@ static int restore_reference_order(sp_system* s) {
     SP_LAUNCH(s, k_iota_ref, sp_blocks(s->n, B), B, 0, s->ref, 0LL, s->n);
     s->identity_order = true;
     s->have_cells = false;
+    s->x_version++;
     return SP_OK;
 }
 
@@ -277,6 +278,8 @@ int32_t sp_destroy(sp_system* s) {
     cudaFree(s->stage);
     cudaFree(s->dscal);
     cudaFree(s->ucoord);
+    cudaFree(s->nbr_ids);
+    cudaFree(s->nbr_cnt);
     cudaFree(s->pk);
     if (s->h_scal) cudaFreeHost(s->h_scal);
     if (s->h_counters) cudaFreeHost(s->h_counters);
@@ -345,6 +348,7 @@ int32_t sp_resize(sp_system* s, int64_t n) {
     SP_CUDA(s, cudaSetDevice(s->device));
     if (n == s->n) return SP_OK;
     sp_slab_host_touched(s);
+    s->x_version++;
     if (n < s->n) {
         int rc = restore_reference_order(s);
         if (rc) return rc;
@@ -383,7 +387,10 @@ int32_t sp_upload(sp_system* s, int32_t fid, const double* host, int64_t n, int3
     if (n == 0) return SP_OK;
     SP_CUDA(s, cudaSetDevice(s->device));
     SpField& f = s->fields[fid];
-    if (fid == 0) sp_slab_host_touched(s);
+    if (fid == 0) {
+        sp_slab_host_touched(s);
+        s->x_version++;
+    }
     int rc = sp_time_begin(s);
     if (rc) return rc;
     if (s->identity_order && layout == SP_LAYOUT_SOA) {

@@ -229,6 +229,16 @@ class ParticleSystem:
         abi.check(self._lib.sp_get_neighbour_lists(self._h, abi.ptr_i64(offsets), abi.ptr_i64(ids), total), self._h)
         return offsets, ids[:total]
 
+    def sweep_neighbour_lists(self):
+        """The cached lists the default pair sweeps replay (same sets as neighbour_lists(), sweep visiting order)."""
+        n = len(self)
+        offsets = np.zeros(n + 1, dtype=np.int64)
+        abi.check(self._lib.sp_get_sweep_neighbour_lists(self._h, abi.ptr_i64(offsets), None, 0), self._h)
+        total = int(offsets[n])
+        ids = np.empty(max(total, 1), dtype=np.int64)
+        abi.check(self._lib.sp_get_sweep_neighbour_lists(self._h, abi.ptr_i64(offsets), abi.ptr_i64(ids), total), self._h)
+        return offsets, ids[:total]
+
     @property
     def n_removed(self) -> int:
         n = C.c_int64()

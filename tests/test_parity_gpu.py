@@ -76,6 +76,58 @@ def test_cell_list_unjittered_lattice_r_equals_h():
     assert np.max(np.diff(off)) == 32                         # 6+12+8+6 lattice neighbours within 2 dr
 
 
+def _sorted_segments(off, ids):
+    seg = np.repeat(np.arange(len(off) - 1), np.diff(off))
+    return ids[np.lexsort((ids, seg))]
+
+
+@pytest.mark.parametrize("maker", [configs.collapse_dry, configs.cavity_flow, configs.collapse_dry_implicit,
+                                   lambda: configs.collapse3d(5e-3),
+                                   lambda: configs.lattice_box(12, jitter=0.0, shuffle=True, dr=5e-3),
+                                   lambda: configs.lattice_box(20, jitter=0.1, shuffle=True, dr=1.0)])
+def test_cached_sweep_lists_are_the_reference_sets(maker):
+    # the lists the default sweeps replay (FP32 three-way classification + exact FP64 test of the thin shell)
+    # must hold exactly the reference's neighbours, including the r == h pairs of the un-jittered lattice
+    case = maker()
+    dev, ora = _pair(case)
+    dev.create_cell_list()
+    ora.create_cell_list()
+    od, idd = dev.sweep_neighbour_lists()
+    oo, ido = ora.neighbour_lists()
+    assert np.array_equal(od, oo)
+    assert np.array_equal(_sorted_segments(od, idd), _sorted_segments(oo, ido))
+    # and they follow the positions: move the particles without rebuilding the cells (core.jl:95 re-keys from
+    # the current x), the cache must be rebuilt
+    x = dev.get("x")
+    rng = np.random.default_rng(3)
+    x2 = x + rng.uniform(-0.05, 0.05, size=x.shape) * case.h * np.array([1.0, 1.0, 0.0])   # in-plane for the 2-D cases
+    dev.set("x", x2)
+    ora.set("x", x2)
+    od, idd = dev.sweep_neighbour_lists()
+    oo, ido = ora.neighbour_lists()
+    assert np.array_equal(od, oo)
+    assert np.array_equal(_sorted_segments(od, idd), _sorted_segments(oo, ido))
+
+
+def test_cached_sweep_lists_overflow_cluster():
+    # more neighbours than the cache holds per target (64): those targets are swept by the exact scan
+    rng = np.random.default_rng(8)
+    h = 0.1
+    dom = geo.Box(0.0, 0.0, 0.0, 1.0, 1.0, 1.0)
+    x = np.concatenate([rng.uniform(0.45, 0.55, size=(700, 3)), rng.uniform(0.0, 1.0, size=(3000, 3))])
+    ora = OracleSystem({"rho": 1}, dom, h)
+    ora.add_particles(x=x)
+    ora.create_cell_list()
+    dev = ParticleSystem({"rho": 1}, dom, h)
+    dev.add_particles(x=x)
+    dev.create_cell_list()
+    od, idd = dev.sweep_neighbour_lists()
+    oo, ido = ora.neighbour_lists()
+    assert np.max(np.diff(oo)) > 300
+    assert np.array_equal(od, oo)
+    assert np.array_equal(_sorted_segments(od, idd), _sorted_segments(oo, ido))
+
+
 def test_removal_order_and_nan_positions():
     rng = np.random.default_rng(11)
     dom = geo.Box(0.0, 0.0, 0.0, 1.0, 1.0, 1.0)
