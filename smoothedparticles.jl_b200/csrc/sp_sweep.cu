@@ -549,11 +549,12 @@ __global__ void __launch_bounds__(128, 5) k_nbr_build(SpGrid g, SweepCtx c, int*
     if (i >= c.n) return;
     const float ui = c.ux[i], vi = c.uy[i], wi = c.uz[i];
     const double T2 = g.T2;
-    const float thr = c.thr, thr_lo = c.thr_lo;
-    unsigned long long ui2, vi2, wi2;
+    unsigned long long ui2, vi2, wi2, thr2, thr_lo2;
     asm("mov.b64 %0, {%1,%1};" : "=l"(ui2) : "f"(ui));
     asm("mov.b64 %0, {%1,%1};" : "=l"(vi2) : "f"(vi));
     asm("mov.b64 %0, {%1,%1};" : "=l"(wi2) : "f"(wi));
+    asm("mov.b64 %0, {%1,%1};" : "=l"(thr2) : "f"(c.thr));
+    asm("mov.b64 %0, {%1,%1};" : "=l"(thr_lo2) : "f"(c.thr_lo));
     // entry k of target i lives at ((i / TPW) * (CAPK / G) + k / G) * 32 + (i % TPW) * G + k % G, TPW = 32 / G
     const int TPW = 32 / G;
     int* col = ids + ((size_t)(i / TPW) * (SP_NBR_CAPK / G) << 5) + (i % TPW) * G;
@@ -561,28 +562,40 @@ __global__ void __launch_bounds__(128, 5) k_nbr_build(SpGrid g, SweepCtx c, int*
     unsigned m0 = 0u, m1 = 0u, m2 = 0u;  // pending chunks: candidates that may be neighbours (newest in m0)
     unsigned s0 = 0u, s1 = 0u, s2 = 0u;  // ... of which certainly neighbours
     int b0 = 0, b1 = 0, b2 = 0;
-    auto run = [&](unsigned m, unsigned sure, int base) {
+    const double xi = c.x[i], yi = c.y[i], zi = c.z[i];
+    // exact FP64 predicate for the ambiguous candidates of a chunk: returns the bits that are NOT neighbours.
+    // (r > h) && continue (core.jl:105)  <=>  d2 > T2 with r = sqrt_rn(d2), decided in FP64 as the reference does
+    auto reject = [&](unsigned amb, int base) -> unsigned {
+        unsigned out = 0u;
+        while (amb) {
+            const unsigned bit = amb & (0u - amb);
+            const int j = base + __ffs(amb) - 1;
+            amb ^= bit;
+            const double dx = __dsub_rn(xi, c.x[j]), dy = __dsub_rn(yi, c.y[j]), dz = __dsub_rn(zi, c.z[j]);
+            if (sp_d2(dx, dy, dz) > T2) out |= bit;
+        }
+        return out;
+    };
+    auto append = [&](unsigned m, int base) {
         while (m) {
-            const unsigned bit = m & (0u - m);
             const int j = base + __ffs(m) - 1;
-            m ^= bit;
-            if (!(sure & bit)) {
-                // (r > h) && continue (core.jl:105)  <=>  d2 > T2 with r = sqrt_rn(d2), decided in FP64 as the reference does
-                const double dx = __dsub_rn(c.x[i], c.x[j]), dy = __dsub_rn(c.y[i], c.y[j]), dz = __dsub_rn(c.z[i], c.z[j]);
-                if (sp_d2(dx, dy, dz) > T2) continue;
-            }
-            if (j == i) continue;  // p == q (core.jl:105)
+            m &= m - 1;
             if (n_out < SP_NBR_CAPK) col[((n_out / G) << 5) + (n_out % G)] = j;
             n_out++;
         }
     };
     auto drain = [&]() {
-        run(m2, s2, b2);
-        run(m1, s1, b1);
-        run(m0, s0, b0);
+        // first the few exact tests of all three chunks (kept out of the append loop: on a lattice at rest ~6 of 32
+        // neighbours sit at r == h and are ambiguous in FP32), then the appends, which touch no particle data
+        m2 &= ~reject(m2 & ~s2, b2);
+        m1 &= ~reject(m1 & ~s1, b1);
+        m0 &= ~reject(m0 & ~s0, b0);
+        append(m2, b2);
+        append(m1, b1);
+        append(m0, b0);
         m0 = m1 = m2 = 0u;
     };
-    const long long key = sp_find_key(g, c.x[i], c.y[i], c.z[i]);  // core.jl:95
+    const long long key = sp_find_key(g, xi, yi, zi);  // core.jl:95
     const long long L1 = g.lim[0], L12 = g.lim[0] * g.lim[1];
     const int nk = (g.dim == 2) ? 0 : 1;
     for (int dk = -nk; dk <= nk; dk++) {
@@ -593,34 +606,53 @@ __global__ void __launch_bounds__(128, 5) k_nbr_build(SpGrid g, SweepCtx c, int*
             if (khi > g.key_max) khi = g.key_max;
             if (klo > khi) continue;
             const int jb = c.cell_start[klo], je = c.cell_start[khi + 1];
-            for (int j0 = jb & ~1; j0 < je; j0 += 32) {
+            // chunks of 32 slots starting at a multiple of 4: one LDG.128 per plane brings 4 candidates, the distance
+            // runs in packed FP32x2 (FADD2/FMUL2/FFMA2), and the two classifications are read off the SIGN of
+            // thr - dd and thr_lo - dd, shifted into the masks by one funnel shift per candidate (no compare/select)
+            for (int j0 = jb & ~3; j0 < je; j0 += 32) {
                 const int nj = min(32, je - j0);
-                unsigned m = 0u, sure = 0u;
+                const int nq = (nj + 3) >> 2;
+                unsigned not_maybe = 0u, not_sure = 0u;  // candidate k of the chunk lands in bit 4*nq-1-k
+                const ulonglong2* px = reinterpret_cast<const ulonglong2*>(c.ux + j0);
+                const ulonglong2* py = reinterpret_cast<const ulonglong2*>(c.uy + j0);
+                const ulonglong2* pz = reinterpret_cast<const ulonglong2*>(c.uz + j0);
 #pragma unroll
-                for (int u = 0; u < 16; u++) {
-                    if (2 * u >= nj) break;
-                    const unsigned long long qx = __ldg(reinterpret_cast<const unsigned long long*>(c.ux + j0) + u);
-                    const unsigned long long qy = __ldg(reinterpret_cast<const unsigned long long*>(c.uy + j0) + u);
-                    const unsigned long long qz = __ldg(reinterpret_cast<const unsigned long long*>(c.uz + j0) + u);
-                    unsigned long long dx, dy, dz, dd;
-                    asm("sub.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(ui2), "l"(qx));
-                    asm("sub.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(vi2), "l"(qy));
-                    asm("sub.f32x2 %0, %1, %2;" : "=l"(dz) : "l"(wi2), "l"(qz));
-                    asm("mul.f32x2 %0, %1, %1;" : "=l"(dd) : "l"(dx));
-                    asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(dd) : "l"(dy), "l"(dd));
-                    asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(dd) : "l"(dz), "l"(dd));
-                    float d0, d1;
-                    asm("mov.b64 {%0,%1}, %2;" : "=f"(d0), "=f"(d1) : "l"(dd));
-                    // !(dd > thr) keeps NaN distances for the exact test, which lets them through like the reference
-                    if (!(d0 > thr)) m |= 1u << (2 * u);
-                    if (!(d1 > thr)) m |= 2u << (2 * u);
-                    if (d0 <= thr_lo) sure |= 1u << (2 * u);
-                    if (d1 <= thr_lo) sure |= 2u << (2 * u);
+                for (int q = 0; q < 8; q++) {
+                    if (q >= nq) break;
+                    const ulonglong2 qx = __ldg(px + q), qy = __ldg(py + q), qz = __ldg(pz + q);
+                    const unsigned long long cx[2] = {qx.x, qx.y}, cy[2] = {qy.x, qy.y}, cz[2] = {qz.x, qz.y};
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        unsigned long long dx, dy, dz, dd, ta, tb;
+                        asm("sub.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(ui2), "l"(cx[e]));
+                        asm("sub.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(vi2), "l"(cy[e]));
+                        asm("sub.f32x2 %0, %1, %2;" : "=l"(dz) : "l"(wi2), "l"(cz[e]));
+                        asm("mul.f32x2 %0, %1, %1;" : "=l"(dd) : "l"(dx));
+                        asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(dd) : "l"(dy), "l"(dd));
+                        asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(dd) : "l"(dz), "l"(dd));
+                        // sign(thr - dd) = 1  <=>  dd > thr  (certainly not a neighbour); a NaN distance gives the
+                        // canonical positive NaN: it stays a candidate and the reference accepts it as well
+                        asm("sub.f32x2 %0, %1, %2;" : "=l"(ta) : "l"(thr2), "l"(dd));
+                        asm("sub.f32x2 %0, %1, %2;" : "=l"(tb) : "l"(thr_lo2), "l"(dd));
+                        unsigned a0, a1, c0, c1;
+                        asm("mov.b64 {%0,%1}, %2;" : "=r"(a0), "=r"(a1) : "l"(ta));
+                        asm("mov.b64 {%0,%1}, %2;" : "=r"(c0), "=r"(c1) : "l"(tb));
+                        not_maybe = __funnelshift_l(a0, not_maybe, 1);
+                        not_maybe = __funnelshift_l(a1, not_maybe, 1);
+                        not_sure = __funnelshift_l(c0, not_sure, 1);
+                        not_sure = __funnelshift_l(c1, not_sure, 1);
+                    }
                 }
+                const int sh = 32 - 4 * nq;
+                unsigned m = __brev(~not_maybe) >> sh;
+                unsigned sure = __brev(~not_sure) >> sh;
+                // only slots of this row range count (the aligned chunk may start up to 3 slots early / end late)
                 const int lo_bit = max(jb - j0, 0);
                 unsigned valid = nj >= 32 ? 0xffffffffu : ((1u << nj) - 1u);
                 valid &= ~((1u << lo_bit) - 1u);
                 m &= valid;
+                const unsigned self_off = (unsigned)(i - j0);  // p == q (core.jl:105): drop the own slot's bit
+                if (self_off < 32u) m &= ~(1u << self_off);
                 if (m2) drain();
                 m2 = m1; s2 = s1; b2 = b1;
                 m1 = m0; s1 = s0; b1 = b0;
