@@ -200,8 +200,9 @@ int sp_permute_all(sp_system* s, long long n_keep) {
         tab.count = 0;
         return SP_OK;
     };
+    // transient fields need not survive; a field that is +0.0 everywhere is its own permutation (no traffic, no swap)
     for (SpField& f : s->fields)
-        for (int c = 0; c < f.ncomp && !f.transient; c++) {
+        for (int c = 0; c < f.ncomp && !f.transient && !f.known_zero; c++) {
             tab.in[tab.count] = f.d + (size_t)c * s->cap;
             tab.out[tab.count] = f.alt + (size_t)c * s->cap;
             if (++tab.count == PERM_PLANES) {
@@ -212,7 +213,7 @@ int sp_permute_all(sp_system* s, long long n_keep) {
     int rc = flush();
     if (rc) return rc;
     for (SpField& f : s->fields)
-        if (!f.transient) std::swap(f.d, f.alt);
+        if (!f.transient && !f.known_zero) std::swap(f.d, f.alt);
     std::swap(s->ref, s->ref_alt);
     std::swap(s->key, s->key_alt);
     return SP_OK;

@@ -27,6 +27,9 @@ struct SpField {
     double* d = nullptr;    // current planes
     double* alt = nullptr;  // permutation target (swapped with d by the cell-list build)
     bool transient = false;  // solver scratch: contents need not survive a cell-list rebuild
+    long long version = 1;   // bumped by every call that may write the field (host upload, operators, halos)
+    bool known_zero = false; // every slot holds +0.0 (set by the operators that reset a field): the cell-list
+                             // build has nothing to permute for such a field
 };
 
 // Parameters every device kernel needs about the cell grid (passed by value).
@@ -83,6 +86,13 @@ struct sp_system {
     long long nbr_version = 0;     // x_version the lists were built for
     long long nbr_n = 0;
     int nbr_group = 0;             // lanes per target the list layout was written for
+    // what the last balance_of_mass sweep left in the scratch fields _kx/_kv (sp_ops.cuh: OpBalanceOfMassAux)
+    struct {
+        bool valid = false;
+        long long x_version = 0, v_version = 0, n = 0;
+        int v_fid = -1, kernel = -1, f_kx = -1, f_kv = -1;
+        double m = 0, h = 0;
+    } pair_aux;
     double* dscal = nullptr;    // CG scalars + dot partials (3*1024 + 16 doubles)
     double* h_scal = nullptr;   // pinned mirror of a few scalars
 
@@ -129,6 +139,17 @@ int sp_check_fields(sp_system* s, const int32_t* fields, int nfields, const int*
 // RAII-less timing helpers
 int sp_time_begin(sp_system* s);
 int sp_time_end(sp_system* s);
+// bookkeeping for the per-field caches: call BEFORE launching anything that writes field `fid`
+static inline void sp_wrote(sp_system* s, int fid) {
+    SpField& f = s->fields[fid];
+    f.version++;
+    f.known_zero = false;
+    if (fid == 0) s->x_version++;
+}
+static inline void sp_zeroed(sp_system* s, int fid) {
+    sp_wrote(s, fid);
+    s->fields[fid].known_zero = true;
+}
 void sp_slab_free(sp_system* s);  // sp_slab.cu
 int sp_build_cells(sp_system* s);  // sp_cells.cu
 void sp_slab_host_touched(sp_system* s);  // positions / particle set changed by the host: full selection next time

@@ -73,6 +73,10 @@ extern "C" int32_t sp_poisson_cg(sp_system* s, const int32_t* F, int32_t nf, con
     double *r = s->fields[fr].d, *u = s->fields[fu].d, *c = s->fields[fc].d;
     const int B = 256;
     const int32_t Fa[6] = {F[0], F[1], F[2], F[3], fu, fc};
+    sp_wrote(s, F[5]);
+    sp_wrote(s, fr);
+    sp_wrote(s, fu);
+    sp_wrote(s, fc);
     SP_LAUNCH(s, k_cg_init, sp_blocks(n, B), B, 0, b, r, u, x, n);
     auto norm2 = [&](double* out_host) -> int {
         int rc2 = sp_dot_device(s, r, r, n, partial, d_rr);  // ghosts are masked inside

@@ -97,6 +97,91 @@ struct OpInternalForce {
     }
 };
 
+// ---- cross-operator cache for the WCSPH pair (balance_of_mass!, internal_force!) of one time step.
+// internal_force! sums  -ker*(pr_p + pr_q)*x_pq + visc*ker*v_pq  over the same neighbours, with the same
+// ker = m*rDw(h,r), x_pq and v_pq that balance_of_mass! has just evaluated (positions and velocities do not
+// change in between, collapse3d.jl:136-150).  Splitting the sum,
+//     Dv_p += -pr_p * A_p - B_p + visc * C_p,    A_p = sum ker*x_pq,  C_p = sum ker*v_pq,  B_p = sum ker*pr_q*x_pq,
+// lets the mass sweep accumulate A and C on the side (6 FMAs per pair, no extra loads) and leaves the force sweep
+// with B only: it gathers x and pr of q (4 planes instead of 7) — the gathers are what bounds the replay kernels.
+// Same terms, different association: within the 1e-10 parity bar (measured ~1e-13); SP_FLAG_STRICT_ORDER and any
+// change of x, v, kernel, m or h in between fall back to the plain operator.
+template <class K>
+struct OpBalanceOfMassAux {
+    static constexpr int NQ = 4;  // vx, vy, vz, rho
+    struct Params {
+        const double* qp[NQ];
+        double* Drho;
+        WV3 kx, kv;  // A and C
+        double m, two_nu;
+        SpKC kc;
+    };
+    struct PS {
+        double vx, vy, vz, rho;
+    };
+    struct Acc {
+        double d, ax, ay, az, cx, cy, cz;
+    };
+    __device__ static __forceinline__ bool active(const Params&, int) { return true; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
+        p.vx = P.qp[0][i]; p.vy = P.qp[1][i]; p.vz = P.qp[2][i];
+        p.rho = P.qp[3][i];
+        a.d = P.Drho[i];
+        a.ax = a.ay = a.az = a.cx = a.cy = a.cz = 0.0;
+    }
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, const Q& q, double dx, double dy,
+                                                double dz, double r, Acc& a) {
+        double ker = P.m * K::rD(P.kc, r);
+        double dvx = p.vx - q(0), dvy = p.vy - q(1), dvz = p.vz - q(2);
+        a.d += ker * ((dx * dvx + dy * dvy + dz * dvz) + P.two_nu * (p.rho - q(3)));
+        a.ax += ker * dx; a.ay += ker * dy; a.az += ker * dz;
+        a.cx += ker * dvx; a.cy += ker * dvy; a.cz += ker * dvz;
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) {
+        P.Drho[i] = a.d;
+        P.kx.x[i] = a.ax; P.kx.y[i] = a.ay; P.kx.z[i] = a.az;
+        P.kv.x[i] = a.cx; P.kv.y[i] = a.cy; P.kv.z[i] = a.cz;
+    }
+};
+
+template <class K>
+struct OpInternalForceCached {
+    static constexpr int NQ = 1;  // pr = P/rho^2
+    struct Params {
+        const double* qp[NQ];
+        const double* type;
+        WV3 Dv;
+        RV3 kx, kv;
+        double m, visc;  // visc = 2*mu/rho0^2
+        SpKC kc;
+    };
+    struct PS {
+        double pr;
+    };
+    struct Acc {
+        double x, y, z;  // B
+    };
+    __device__ static __forceinline__ bool active(const Params& P, int i) { return P.type[i] == 0.0; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
+        p.pr = P.qp[0][i];
+        a.x = a.y = a.z = 0.0;
+    }
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS&, const Q& q, double dx, double dy,
+                                                double dz, double r, Acc& a) {
+        double c = (P.m * K::rD(P.kc, r)) * q(0);
+        a.x += c * dx; a.y += c * dy; a.z += c * dz;
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS& p, const Acc& a) {
+        P.Dv.x[i] += P.visc * P.kv.x[i] - (p.pr * P.kx.x[i] + a.x);
+        P.Dv.y[i] += P.visc * P.kv.y[i] - (p.pr * P.kx.y[i] + a.y);
+        P.Dv.z[i] += P.visc * P.kv.z[i] - (p.pr * P.kx.z[i] + a.z);
+    }
+};
+
 // internal_force!  cavity_flow.jl:102-114 (rDwendland2; lid extrapolation; Monaghan viscosity)
 template <class K>
 struct OpInternalForceCavity {

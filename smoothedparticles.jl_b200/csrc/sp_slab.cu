@@ -634,6 +634,7 @@ int32_t sp_slab_halo_refresh(sp_system* s, const int32_t* fields, int32_t nfield
     for (int k = 0; k < nfields && n > 0; k++) {
         SpField& f = s->fields[fields[k]];
         const int axis_comp = fields[k] == 0 ? sl->axis : -1;
+        f.version++;  // ghost values change (a field that is zero everywhere stays zero: known_zero is kept)
         if (fields[k] == 0) s->x_version++;
         if (rl || rh)
             SP_LAUNCH(s, k_slab_refresh_unpack, sp_blocks(n, B), B, 0, f.d, s->cap, f.ncomp, s->fields[sl->f_ghost].d,

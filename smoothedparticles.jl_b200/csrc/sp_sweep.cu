@@ -1097,6 +1097,19 @@ static int launch_tile(sp_system* s, const SweepCtx& c, const typename Op::Param
     return SP_OK;
 }
 
+// 3 (default) = cached neighbour lists; 1 = register hit masks per sweep; 2 = two targets per thread (slower, see
+// profiles/r1_sweep_exploration.md); 4 = lists + packed records; 0 = plain candidate scan
+static int sp_sweep_mode() {
+    static const int mode = getenv("SP_SWEEP_MASK") ? atoi(getenv("SP_SWEEP_MASK")) : 3;
+    return mode;
+}
+// the balance_of_mass -> internal_force cache (OpBalanceOfMassAux) is used on the default path only
+static bool sp_pair_aux_enabled(int flags) {
+    static const bool on = !(getenv("SP_PAIR_AUX") && atoi(getenv("SP_PAIR_AUX")) == 0);
+    return on && sp_sweep_mode() == 3 && !(flags & (SP_FLAG_STRICT_ORDER | SP_FLAG_TILE_KERNEL | SP_FLAG_PACKED_KERNEL)) &&
+           !getenv("SP_SWEEP_TILE") && !getenv("SP_SWEEP_VARIANT");
+}
+
 static void sp_sweep_ctx(sp_system* s, SweepCtx& c) {
     const double* X = s->fields[0].d;
     c.x = X;
@@ -1190,7 +1203,7 @@ static int launch_sweep(sp_system* s, const typename Op::Params& P, int flags) {
         // default: one thread per target over the sorted SoA planes (L1-resident candidate rows), register hit masks
         // 3 (default) = cached neighbour lists; 1 = register hit masks per sweep; 2 = two targets per thread
         // (slower, see profiles/r1_sweep_exploration.md); 0 = plain candidate scan
-        static const int mask_mode = getenv("SP_SWEEP_MASK") ? atoi(getenv("SP_SWEEP_MASK")) : 3;
+        const int mask_mode = sp_sweep_mode();
         if (mask_mode == 3 || mask_mode == 4) {
             int rc = sp_ensure_nbr_cache(s, c);
             if (rc) return rc;
@@ -1324,6 +1337,37 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
         case SP_OP_BALANCE_OF_MASS: {
             NEED(4, 4, 3, 3, 1, 1);
             NEED_CELLS();
+            sp_wrote(s, F[3]);
+            s->pair_aux.valid = false;
+            if (sp_pair_aux_enabled(flags)) {
+                int32_t fkx, fkv;
+                int rc2 = sp_add_field(s, "_kx", 3, &fkx);
+                if (!rc2) rc2 = sp_add_field(s, "_kv", 3, &fkv);
+                if (rc2) return rc2;
+                s->fields[fkx].transient = s->fields[fkv].transient = true;
+                rc2 = dispatch_kernel<OpBalanceOfMassAux>(s, (int)Pm[0], Pm[2], flags, [&](auto& P) {
+                    set_v3(s, F[1], P.qp);
+                    P.qp[3] = sc(s, F[2]);
+                    P.Drho = sc(s, F[3]);
+                    P.kx = wv3(s, fkx);
+                    P.kv = wv3(s, fkv);
+                    P.m = Pm[1];
+                    P.two_nu = Pm[3];
+                });
+                if (rc2) return rc2;
+                auto& t = s->pair_aux;
+                t.valid = true;
+                t.x_version = s->x_version;
+                t.v_fid = F[1];
+                t.v_version = s->fields[F[1]].version;
+                t.n = s->n;
+                t.kernel = (int)Pm[0];
+                t.m = Pm[1];
+                t.h = Pm[2];
+                t.f_kx = fkx;
+                t.f_kv = fkv;
+                return SP_OK;
+            }
             return dispatch_kernel<OpBalanceOfMass>(s, (int)Pm[0], Pm[2], flags, [&](auto& P) {
                 set_v3(s, F[1], P.qp);
                 P.qp[3] = sc(s, F[2]);
@@ -1334,16 +1378,36 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
         }
         case SP_OP_FIND_PRESSURE: {
             NEED(3, 4, 1, 1, 1);
+            sp_wrote(s, F[0]);
+            sp_zeroed(s, F[1]);
+            sp_wrote(s, F[2]);
             UFindPressure::Params P{sc(s, F[0]), sc(s, F[1]), sc(s, F[2]), Pm[0], Pm[1], Pm[2], Pm[3]};
             return launch_unary<UFindPressure>(s, P);
         }
         case SP_OP_INTERNAL_FORCE: {
             NEED(6, 5, 3, 3, 1, 1, 3, 1);
             NEED_CELLS();
+            sp_wrote(s, F[4]);
             double* pr = nullptr;
             {
                 int rc2 = pressure_over_rho2(s, F[2], F[3], &pr);
                 if (rc2) return rc2;
+            }
+            {
+                const auto& t = s->pair_aux;
+                if (t.valid && sp_pair_aux_enabled(flags) && t.x_version == s->x_version && t.v_fid == F[1] &&
+                    t.v_version == s->fields[F[1]].version && t.n == s->n && t.kernel == (int)Pm[0] && t.m == Pm[1] &&
+                    t.h == Pm[2]) {
+                    return dispatch_kernel<OpInternalForceCached>(s, (int)Pm[0], Pm[2], flags, [&](auto& P) {
+                        P.qp[0] = pr;
+                        P.Dv = wv3(s, F[4]);
+                        P.type = sc(s, F[5]);
+                        P.kx = rv3(s, t.f_kx);
+                        P.kv = rv3(s, t.f_kv);
+                        P.m = Pm[1];
+                        P.visc = 2 * Pm[3] / (Pm[4] * Pm[4]);
+                    });
+                }
             }
             return dispatch_kernel<OpInternalForce>(s, (int)Pm[0], Pm[2], flags, [&](auto& P) {
                 set_v3(s, F[1], P.qp);
@@ -1357,6 +1421,7 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
         case SP_OP_INTERNAL_FORCE_CAVITY: {
             NEED(6, 6, 3, 3, 1, 1, 3, 1);
             NEED_CELLS();
+            sp_wrote(s, F[4]);
             double* pr = nullptr;
             {
                 int rc2 = pressure_over_rho2(s, F[2], F[3], &pr);
@@ -1379,18 +1444,21 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
         }
         case SP_OP_MOVE: {
             NEED(4, 1, 3, 3, 3, 1);
+            sp_wrote(s, F[0]);
+            sp_zeroed(s, F[2]);
             UMove::Params P{wv3(s, F[0]), rv3(s, F[1]), wv3(s, F[2]), sc(s, F[3]), Pm[0]};
-            if (F[0] == 0) s->x_version++;
             return launch_unary<UMove>(s, P);
         }
         case SP_OP_ACCELERATE: {
             NEED(3, 4, 3, 3, 1);
+            sp_wrote(s, F[0]);
             UAccelerate::Params P{wv3(s, F[0]), rv3(s, F[1]), sc(s, F[2]), Pm[0], Pm[1], Pm[2], Pm[3]};
             return launch_unary<UAccelerate>(s, P);
         }
         case SP_OP_DENSITY_SUM: {
             NEED(2, 3, 3, 1);
             NEED_CELLS();
+            sp_wrote(s, F[1]);
             return dispatch_kernel<OpDensitySum>(s, (int)Pm[0], Pm[2], flags, [&](auto& P) {
                 P.qp[0] = nullptr;
                 P.out = sc(s, F[1]);
@@ -1399,12 +1467,16 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
         }
         case SP_OP_PRESSURE_FROM_RHO: {
             NEED(3, 1, 1, 1, 1);
+            sp_wrote(s, F[0]);
+            sp_wrote(s, F[1]);
+            sp_wrote(s, F[2]);
             UPressureFromRho::Params P{sc(s, F[0]), sc(s, F[1]), sc(s, F[2]), Pm[0]};
             return launch_unary<UPressureFromRho>(s, P);
         }
         case SP_OP_INTERNAL_FORCE_SYM: {
             NEED(3, 4, 3, 1, 3);
             NEED_CELLS();
+            sp_wrote(s, F[2]);
             return dispatch_kernel<OpInternalForceSym>(s, (int)Pm[0], Pm[2], flags, [&](auto& P) {
                 P.qp[0] = sc(s, F[1]);
                 P.a = wv3(s, F[2]);
@@ -1414,32 +1486,33 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
         }
         case SP_OP_FILL: {
             NEED(1, 1, 0);
+            if (Pm[0] == 0.0 && !std::signbit(Pm[0])) sp_zeroed(s, F[0]); else sp_wrote(s, F[0]);
             UFill::Params P{sc(s, F[0]), s->cap, s->fields[F[0]].ncomp, Pm[0]};
-            if (F[0] == 0) s->x_version++;
             return launch_unary<UFill>(s, P);
         }
         case SP_OP_ADVECT: {
             NEED(2, 1, 3, 3);
+            sp_wrote(s, F[0]);
             UAdvect::Params P{wv3(s, F[0]), rv3(s, F[1]), Pm[0]};
-            if (F[0] == 0) s->x_version++;
             return launch_unary<UAdvect>(s, P);
         }
         case SP_OP_KICK: {
             NEED(2, 1, 3, 3);
+            sp_wrote(s, F[0]);
             UKick::Params P{wv3(s, F[0]), rv3(s, F[1]), Pm[0]};
-            if (F[0] == 0) s->x_version++;
             return launch_unary<UKick>(s, P);
         }
         case SP_OP_ISPH_INITIALIZE: {
             NEED(6, 4, 3, 3, 1, 1, 1, 1);
+            for (int k = 0; k < 6; k++) sp_wrote(s, F[k]);
             UIsphInitialize::Params P{wv3(s, F[0]), wv3(s, F[1]), sc(s, F[2]), sc(s, F[3]), sc(s, F[4]),
                                       sc(s, F[5]),  Pm[0],        Pm[1],       Pm[2],       Pm[3]};
-            if (F[0] == 0) s->x_version++;
             return launch_unary<UIsphInitialize>(s, P);
         }
         case SP_OP_ISPH_VISCOUS_FORCE: {
             NEED(3, 5, 3, 3, 3);
             NEED_CELLS();
+            sp_wrote(s, F[2]);
             return dispatch_kernel<OpIsphViscous>(s, (int)Pm[0], Pm[2], flags, [&](auto& P) {
                 set_v3(s, F[1], P.qp);
                 P.Dv = wv3(s, F[2]);
@@ -1449,6 +1522,9 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
         case SP_OP_ISPH_DIV_L_LAMBDA: {
             NEED(5, 5, 3, 3, 1, 1, 1);
             NEED_CELLS();
+            sp_wrote(s, F[2]);
+            sp_wrote(s, F[3]);
+            sp_wrote(s, F[4]);
             return dispatch_kernel<OpIsphDivLLambda>(s, (int)Pm[0], Pm[2], flags, [&](auto& P) {
                 set_v3(s, F[1], P.qp);
                 P.div = sc(s, F[2]);
@@ -1461,12 +1537,15 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
         }
         case SP_OP_ISPH_PROJECTION_VECTOR: {
             NEED(2, 2, 1, 1);
+            sp_wrote(s, F[0]);
+            sp_wrote(s, F[1]);
             UIsphProjectionVector::Params P{sc(s, F[0]), sc(s, F[1]), -(Pm[0] * Pm[0]), Pm[1]};
             return launch_unary<UIsphProjectionVector>(s, P);
         }
         case SP_OP_ISPH_INTERNAL_FORCE: {
             NEED(3, 4, 3, 1, 3);
             NEED_CELLS();
+            sp_wrote(s, F[2]);
             return dispatch_kernel<OpIsphInternalForce>(s, (int)Pm[0], Pm[2], flags, [&](auto& P) {
                 P.qp[0] = sc(s, F[1]);
                 P.Dv = wv3(s, F[2]);
@@ -1475,6 +1554,8 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
         }
         case SP_OP_ISPH_ACCELERATE: {
             NEED(3, 1, 3, 3, 1);
+            sp_wrote(s, F[0]);
+            sp_zeroed(s, F[1]);
             UIsphAccelerate::Params P{wv3(s, F[0]), wv3(s, F[1]), sc(s, F[2]), Pm[0]};
             return launch_unary<UIsphAccelerate>(s, P);
         }
@@ -1488,6 +1569,7 @@ int sp_poisson_apply_impl(sp_system* s, const int32_t* F, int32_t nf, const doub
     (void)op;
     NEED(6, 5, 3, 1, 1, 1, 1, 1);
     NEED_CELLS();
+    sp_wrote(s, F[5]);
     return dispatch_kernel<OpPoissonApply>(s, (int)Pm[0], Pm[2], 0, [&](auto& P) {
         P.L = sc(s, F[1]);
         P.lambda = sc(s, F[2]);

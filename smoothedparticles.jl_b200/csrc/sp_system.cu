@@ -387,10 +387,8 @@ int32_t sp_upload(sp_system* s, int32_t fid, const double* host, int64_t n, int3
     if (n == 0) return SP_OK;
     SP_CUDA(s, cudaSetDevice(s->device));
     SpField& f = s->fields[fid];
-    if (fid == 0) {
-        sp_slab_host_touched(s);
-        s->x_version++;
-    }
+    if (fid == 0) sp_slab_host_touched(s);
+    sp_wrote(s, fid);
     int rc = sp_time_begin(s);
     if (rc) return rc;
     if (s->identity_order && layout == SP_LAYOUT_SOA) {
