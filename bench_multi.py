@@ -224,11 +224,11 @@ def run_multi(args, METRIC, UNIT, ClockSampler, peaks):
                        "l2": "state >= 1 GB per GPU >> 126 MB L2, no flush needed", "setup_s": round(gen_s, 1),
                        "parallelism": f"slab{world}", "energy": E},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches),
-            "roofline": {"bound": "hbm", "kernel": f"k_sweep_mask<{dominant}>", "achieved": achieved, "peak": hbm_peak,
+            "roofline": {"bound": "hbm", "kernel": f"k_sweep_list<{dominant}> (+ k_nbr_build inside the first sweep of a step)", "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_kind": peak_kind,
                          "alg_bytes_per_particle": alg, "launch_ms": breakdown[dominant],
                          "step_hbm_frac": 736 * value / world / (hbm_peak * 1e9),
-                         "note": "pair sweeps are FP64-issue / L1 bound, not HBM bound"},
+                         "note": "pair sweeps are bound by the L1 data pipe (FP64 gathers), not by HBM"},
             "breakdown_ms": breakdown, "cpu_baseline": None,
         }
         print(json.dumps(line), flush=True)

@@ -239,6 +239,11 @@ int32_t sp_get_cell_list(sp_system* sys, int64_t* offsets /* key_max+1 */, int64
  * ids[offsets[i] .. offsets[i+1]) = 1-based indices q in the reference's visiting order.
  * Call with ids == NULL to get only offsets (offsets[n] = total). */
 int32_t sp_get_neighbour_lists(sp_system* sys, int64_t* offsets /* n+1 */, int64_t* ids, int64_t ids_cap);
+/* Optional: build the cached neighbour lists of the current positions now (the first binary operator after the
+ * positions change does it implicitly).  The op-independent part of apply_binary! (core.jl:94-110: key, candidate
+ * cells, dist, r > h, identity) runs once here; every following sp_apply of a binary operator replays the lists
+ * until a position write, re-sort or resize invalidates them. */
+int32_t sp_build_neighbour_lists(sp_system* sys);
 /* The neighbour lists the default pair sweeps actually replay (the per-position-version cache built by the first
  * sweep after positions change; built here if needed).  Same id SET per particle as sp_get_neighbour_lists; the
  * order is the default sweep's visiting order (stencil rows dk,dj outer, slots ascending), not the reference's. */

@@ -65,6 +65,7 @@ SIGNATURES = {
     "sp_get_cell_list": (_i32, [_p, _pi64, _pi64]),
     "sp_get_neighbour_lists": (_i32, [_p, _pi64, _pi64, _i64]),
     "sp_get_sweep_neighbour_lists": (_i32, [_p, _pi64, _pi64, _i64]),
+    "sp_build_neighbour_lists": (_i32, [_p]),
     "sp_num_removed": (_i32, [_p, _pi64]),
     "sp_last_call_ms": (_i32, [_p, C.POINTER(C.c_float)]),
     "sp_timer_start": (_i32, [_p]),

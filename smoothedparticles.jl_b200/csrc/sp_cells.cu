@@ -86,9 +86,9 @@ int sp_exclusive_scan_i32(sp_system* s, int* data, long long len) {
     if (len <= 0) return SP_OK;
     long long need = len / SCAN_TILE + 2048;
     if (need > s->scan_tmp_len) {
-        if (s->scan_tmp) SP_CUDA(s, cudaFree(s->scan_tmp));
+        if (s->scan_tmp) SP_CUDA(s, sp_dfree(s, s->scan_tmp));
         s->scan_tmp = nullptr;
-        SP_CUDA(s, cudaMalloc(&s->scan_tmp, (size_t)need * sizeof(int)));
+        SP_CUDA(s, sp_dmalloc(&s->scan_tmp, (size_t)need * sizeof(int)));
         s->scan_tmp_len = need;
     }
     return scan_rec(s, data, len, s->scan_tmp, s->scan_tmp_len);

@@ -61,7 +61,7 @@ extern "C" int32_t sp_poisson_cg(sp_system* s, const int32_t* F, int32_t nf, con
         (rc = scratch_field(s, "_cg_c", &fc)))
         return rc;
     if (!s->dscal) {
-        SP_CUDA(s, cudaMalloc(&s->dscal, (3 * 1024 + 16) * sizeof(double)));
+        SP_CUDA(s, sp_dmalloc(&s->dscal, (3 * 1024 + 16) * sizeof(double)));
         SP_CUDA(s, cudaHostAlloc(&s->h_scal, 16 * sizeof(double), cudaHostAllocDefault));
     }
     if ((rc = sp_time_begin(s))) return rc;

@@ -103,10 +103,10 @@ void sp_slab_free(sp_system* s) {
     if (!sl) return;
     if (sl->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(sl->comm);
     for (int d = 0; d < 2; d++) {
-        cudaFree(sl->sendbuf[d]);
-        cudaFree(sl->recvbuf[d]);
+        sp_dfree(s, sl->sendbuf[d]);
+        sp_dfree(s, sl->recvbuf[d]);
     }
-    cudaFree(sl->d_cnt);
+    sp_dfree(s, sl->d_cnt);
     if (sl->h_cnt) cudaFreeHost(sl->h_cnt);
     delete sl;
     s->slab = nullptr;
@@ -297,14 +297,14 @@ static int slab_ensure_buffers(sp_system* s, long long doubles) {
     if (doubles <= sl->buf_len) return SP_OK;
     const long long want = doubles + doubles / 4 + 4096;
     for (int d = 0; d < 2; d++) {
-        if (sl->sendbuf[d]) SP_CUDA(s, cudaFree(sl->sendbuf[d]));
-        if (sl->recvbuf[d]) SP_CUDA(s, cudaFree(sl->recvbuf[d]));
+        if (sl->sendbuf[d]) SP_CUDA(s, sp_dfree(s, sl->sendbuf[d]));
+        if (sl->recvbuf[d]) SP_CUDA(s, sp_dfree(s, sl->recvbuf[d]));
         sl->sendbuf[d] = sl->recvbuf[d] = nullptr;
     }
     sl->buf_len = 0;
     for (int d = 0; d < 2; d++) {
-        SP_CUDA(s, cudaMalloc(&sl->sendbuf[d], (size_t)want * sizeof(double)));
-        SP_CUDA(s, cudaMalloc(&sl->recvbuf[d], (size_t)want * sizeof(double)));
+        SP_CUDA(s, sp_dmalloc(&sl->sendbuf[d], (size_t)want * sizeof(double)));
+        SP_CUDA(s, sp_dmalloc(&sl->recvbuf[d], (size_t)want * sizeof(double)));
     }
     sl->buf_len = want;
     return SP_OK;
@@ -512,18 +512,18 @@ int32_t sp_slab_init(sp_system* s, const uint8_t id[128], int32_t rank, int32_t 
         delete sl;
         return sp_fail(s, SP_ERR_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
     }
-    SP_CUDA(s, cudaMalloc(&sl->d_cnt, 16 * sizeof(int)));
+    SP_CUDA(s, sp_dmalloc(&sl->d_cnt, 16 * sizeof(int)));
     SP_CUDA(s, cudaHostAlloc(&sl->h_cnt, 16 * sizeof(int), cudaHostAllocDefault));
     // local cell window: owned layers [c0, c1) plus one ghost layer per side
     g.phase[axis] = sl->gphase + sl->c0 - 1;
     g.lim[axis] = (sl->c1 - sl->c0) + 2;
     g.key_max = g.lim[0] * g.lim[1] * g.lim[2];
     // the local window (with its two ghost layers) can be larger than the global grid when nranks is small
-    SP_CUDA(s, cudaFree(s->cell_start));
-    SP_CUDA(s, cudaFree(s->cell_fill));
+    SP_CUDA(s, sp_dfree(s, s->cell_start));
+    SP_CUDA(s, sp_dfree(s, s->cell_fill));
     s->cell_start = s->cell_fill = nullptr;
-    SP_CUDA(s, cudaMalloc(&s->cell_start, (size_t)(g.key_max + 3) * sizeof(int)));
-    SP_CUDA(s, cudaMalloc(&s->cell_fill, (size_t)(g.key_max + 3) * sizeof(int)));
+    SP_CUDA(s, sp_dmalloc(&s->cell_start, (size_t)(g.key_max + 3) * sizeof(int)));
+    SP_CUDA(s, sp_dmalloc(&s->cell_fill, (size_t)(g.key_max + 3) * sizeof(int)));
     SP_CUDA(s, cudaMemset(s->cell_start, 0, (size_t)(g.key_max + 3) * sizeof(int)));
     g.slab_axis = axis;
     g.slab_periodic = sl->periodic;

@@ -1129,9 +1129,9 @@ static void sp_sweep_ctx(sp_system* s, SweepCtx& c) {
 // Everything in between is decided by the exact FP64 predicate, so the neighbour set is the reference's bit for bit.
 static int sp_ensure_prefilter(sp_system* s, SweepCtx& c) {
     if (!s->ucoord || s->ucoord_cap != s->cap) {
-        if (s->ucoord) SP_CUDA(s, cudaFree(s->ucoord));
+        if (s->ucoord) SP_CUDA(s, sp_dfree(s, s->ucoord));
         s->ucoord = nullptr;
-        SP_CUDA(s, cudaMalloc(&s->ucoord, (size_t)3 * s->cap * sizeof(float)));
+        SP_CUDA(s, sp_dmalloc(&s->ucoord, (size_t)3 * s->cap * sizeof(float)));
         s->ucoord_cap = s->cap;
         s->ucoord_version = 0;
     }
@@ -1159,11 +1159,11 @@ static int sp_ensure_nbr_cache(sp_system* s, SweepCtx& c) {
     int rc = sp_ensure_prefilter(s, c);
     if (rc) return rc;
     if (!s->nbr_ids || s->nbr_cap != s->cap) {
-        if (s->nbr_ids) SP_CUDA(s, cudaFree(s->nbr_ids));
-        if (s->nbr_cnt) SP_CUDA(s, cudaFree(s->nbr_cnt));
+        if (s->nbr_ids) SP_CUDA(s, sp_dfree(s, s->nbr_ids));
+        if (s->nbr_cnt) SP_CUDA(s, sp_dfree(s, s->nbr_cnt));
         s->nbr_ids = s->nbr_cnt = nullptr;
-        SP_CUDA(s, cudaMalloc(&s->nbr_ids, (size_t)s->cap * SP_NBR_CAPK * sizeof(int)));
-        SP_CUDA(s, cudaMalloc(&s->nbr_cnt, (size_t)s->cap * sizeof(int)));
+        SP_CUDA(s, sp_dmalloc(&s->nbr_ids, (size_t)s->cap * SP_NBR_CAPK * sizeof(int)));
+        SP_CUDA(s, sp_dmalloc(&s->nbr_cnt, (size_t)s->cap * sizeof(int)));
         s->nbr_cap = s->cap;
         s->nbr_version = 0;
     }
@@ -1212,9 +1212,9 @@ static int launch_sweep(sp_system* s, const typename Op::Params& P, int flags) {
                 SP_LAUNCH(s, (k_sweep_list<Op, 1>), nb, 128, 0, s->g, c, s->nbr_cnt, s->nbr_ids, P, self_flag);
             } else {
                 if (!s->pk || s->pk_cap != s->cap) {
-                    if (s->pk) SP_CUDA(s, cudaFree(s->pk));
+                    if (s->pk) SP_CUDA(s, sp_dfree(s, s->pk));
                     s->pk = nullptr;
-                    SP_CUDA(s, cudaMalloc(&s->pk, (size_t)2 * s->cap * sizeof(SpRec)));
+                    SP_CUDA(s, sp_dmalloc(&s->pk, (size_t)2 * s->cap * sizeof(SpRec)));
                     s->pk_cap = s->cap;
                 }
                 SpRec* pk0 = reinterpret_cast<SpRec*>(s->pk);
@@ -1234,9 +1234,9 @@ static int launch_sweep(sp_system* s, const typename Op::Params& P, int flags) {
     }
     // SP_FLAG_PACKED_KERNEL: packed-record two-phase kernel (experimental, see profiles/r1_sweep_exploration.md)
     if (!s->pk || s->pk_cap != s->cap) {
-        if (s->pk) SP_CUDA(s, cudaFree(s->pk));
+        if (s->pk) SP_CUDA(s, sp_dfree(s, s->pk));
         s->pk = nullptr;
-        SP_CUDA(s, cudaMalloc(&s->pk, (size_t)2 * s->cap * sizeof(SpRec)));
+        SP_CUDA(s, sp_dmalloc(&s->pk, (size_t)2 * s->cap * sizeof(SpRec)));
         s->pk_cap = s->cap;
     }
     SpRec* pk0 = reinterpret_cast<SpRec*>(s->pk);
@@ -1648,10 +1648,10 @@ static int sp_export_lists(sp_system* s, long long* counts, int64_t* offsets, in
     if (ids_cap < run) return sp_fail(s, SP_ERR_INVALID, "ids buffer too small");
     if (run == 0) return SP_OK;
     long long *d_off = nullptr, *d_ids = nullptr;
-    SP_CUDA(s, cudaMalloc(&d_off, (size_t)(n + 1) * sizeof(long long)));
-    cudaError_t e = cudaMalloc(&d_ids, (size_t)run * sizeof(long long));
+    SP_CUDA(s, sp_dmalloc(&d_off, (size_t)(n + 1) * sizeof(long long)));
+    cudaError_t e = sp_dmalloc(&d_ids, (size_t)run * sizeof(long long));
     if (e != cudaSuccess) {
-        cudaFree(d_off);
+        sp_dfree(s, d_off);
         return sp_fail_cuda(s, e, "cudaMalloc ids", __FILE__, __LINE__);
     }
     cudaMemcpyAsync(d_off, h.data(), (size_t)(n + 1) * sizeof(long long), cudaMemcpyHostToDevice, s->stream);
@@ -1659,13 +1659,27 @@ static int sp_export_lists(sp_system* s, long long* counts, int64_t* offsets, in
     s->launches++;
     cudaMemcpyAsync(ids, d_ids, (size_t)run * sizeof(long long), cudaMemcpyDeviceToHost, s->stream);
     e = cudaStreamSynchronize(s->stream);
-    cudaFree(d_off);
-    cudaFree(d_ids);
+    sp_dfree(s, d_off);
+    sp_dfree(s, d_ids);
     if (e != cudaSuccess) return sp_fail_cuda(s, e, "neighbour list export", __FILE__, __LINE__);
     return SP_OK;
 }
 
 extern "C" {
+
+int32_t sp_build_neighbour_lists(sp_system* s) {
+    if (!s) return SP_ERR_INVALID;
+    if (!s->have_cells) return sp_fail(s, SP_ERR_STATE, "no cell list: call sp_create_cell_list first");
+    SP_CUDA(s, cudaSetDevice(s->device));
+    int rc = sp_time_begin(s);
+    if (rc) return rc;
+    if (s->n > 0) {
+        SweepCtx c;
+        sp_sweep_ctx(s, c);
+        if ((rc = sp_ensure_nbr_cache(s, c))) return rc;
+    }
+    return sp_time_end(s);
+}
 
 int32_t sp_get_sweep_neighbour_lists(sp_system* s, int64_t* offsets, int64_t* ids, int64_t ids_cap) {
     if (!s || !offsets) return SP_ERR_INVALID;

@@ -29,13 +29,59 @@ int sp_time_end(sp_system* s) {
     return SP_OK;
 }
 
+// ------------------------------------------------------------------ caching device allocator
+namespace {
+struct PoolState {
+    bool tried = false, use_pool = false;
+    cudaStream_t stream = nullptr;
+};
+PoolState g_pool[64];
+PoolState& pool_for_current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    PoolState& ps = g_pool[dev & 63];
+    if (!ps.tried) {
+        ps.tried = true;
+        int supported = 0;
+        cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, dev);
+        const char* off = getenv("SP_NO_MEMPOOL");
+        if (supported && !(off && atoi(off))) {
+            cudaMemPool_t mp;
+            unsigned long long keep = ~0ULL;
+            if (cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess &&
+                cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess &&
+                cudaStreamCreateWithFlags(&ps.stream, cudaStreamNonBlocking) == cudaSuccess)
+                ps.use_pool = true;
+        }
+        cudaGetLastError();
+    }
+    return ps;
+}
+}  // namespace
+
+cudaError_t sp_dmalloc_impl(void** p, size_t bytes) {
+    PoolState& ps = pool_for_current_device();
+    if (bytes == 0) bytes = 1;
+    if (!ps.use_pool) return cudaMalloc(p, bytes);
+    cudaError_t e = cudaMallocAsync(p, bytes, ps.stream);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(ps.stream);  // complete before any other stream touches the block
+}
+
+cudaError_t sp_dfree_impl(void* p) {
+    if (!p) return cudaSuccess;
+    PoolState& ps = pool_for_current_device();
+    if (!ps.use_pool) return cudaFree(p);
+    return cudaFreeAsync(p, ps.stream);
+}
+
 int sp_ensure_stage(sp_system* s, long long doubles) {
     if (doubles <= s->stage_len) return SP_OK;
     long long want = doubles + doubles / 4 + 1024;
-    if (s->stage) SP_CUDA(s, cudaFree(s->stage));
+    if (s->stage) SP_CUDA(s, sp_dfree(s, s->stage));
     s->stage = nullptr;
     s->stage_len = 0;
-    SP_CUDA(s, cudaMalloc(&s->stage, (size_t)want * sizeof(double)));
+    SP_CUDA(s, sp_dmalloc(&s->stage, (size_t)want * sizeof(double)));
     s->stage_len = want;
     return SP_OK;
 }
@@ -43,14 +89,14 @@ int sp_ensure_stage(sp_system* s, long long doubles) {
 template <class T>
 static int regrow(sp_system* s, T** p, long long old_cap, long long new_cap, int planes, long long n_keep) {
     T* q = nullptr;
-    SP_CUDA(s, cudaMalloc(&q, (size_t)new_cap * planes * sizeof(T)));
+    SP_CUDA(s, sp_dmalloc(&q, (size_t)new_cap * planes * sizeof(T)));
     SP_CUDA(s, cudaMemsetAsync(q, 0, (size_t)new_cap * planes * sizeof(T), s->stream));
     if (*p) {
         for (int c = 0; c < planes && n_keep > 0; c++)
             SP_CUDA(s, cudaMemcpyAsync(q + (size_t)c * new_cap, *p + (size_t)c * old_cap, (size_t)n_keep * sizeof(T),
                                        cudaMemcpyDeviceToDevice, s->stream));
         SP_CUDA(s, cudaStreamSynchronize(s->stream));
-        SP_CUDA(s, cudaFree(*p));
+        SP_CUDA(s, sp_dfree(s, *p));
     }
     *p = q;
     return SP_OK;
@@ -238,14 +284,14 @@ int32_t sp_create(sp_system** out, const double lo[3], const double hi[3], doubl
     CREATE_TRY(cudaEventCreate(&s->ev1));
     CREATE_TRY(cudaEventCreate(&s->tev0));
     CREATE_TRY(cudaEventCreate(&s->tev1));
-    CREATE_TRY(cudaMalloc(&s->cell_start, (size_t)(g.key_max + 3) * sizeof(int)));
-    CREATE_TRY(cudaMalloc(&s->cell_fill, (size_t)(g.key_max + 3) * sizeof(int)));
+    CREATE_TRY(sp_dmalloc(&s->cell_start, (size_t)(g.key_max + 3) * sizeof(int)));
+    CREATE_TRY(sp_dmalloc(&s->cell_fill, (size_t)(g.key_max + 3) * sizeof(int)));
     CREATE_TRY(cudaMemset(s->cell_start, 0, (size_t)(g.key_max + 3) * sizeof(int)));
-    CREATE_TRY(cudaMalloc(&s->counters, 64 * sizeof(int)));
+    CREATE_TRY(sp_dmalloc(&s->counters, 64 * sizeof(int)));
     CREATE_TRY(cudaMemset(s->counters, 0, 64 * sizeof(int)));
     CREATE_TRY(cudaHostAlloc(&s->h_counters, 64 * sizeof(int), cudaHostAllocDefault));
     s->scan_tmp_len = (g.key_max + 3) / 1024 + 1024;
-    CREATE_TRY(cudaMalloc(&s->scan_tmp, (size_t)s->scan_tmp_len * sizeof(int)));
+    CREATE_TRY(sp_dmalloc(&s->scan_tmp, (size_t)s->scan_tmp_len * sizeof(int)));
 #undef CREATE_TRY
     SpField fx;
     fx.name = "x";
@@ -261,26 +307,26 @@ int32_t sp_destroy(sp_system* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     sp_slab_free(s);
     for (SpField& f : s->fields) {
-        cudaFree(f.d);
-        cudaFree(f.alt);
+        sp_dfree(s, f.d);
+        sp_dfree(s, f.alt);
     }
-    cudaFree(s->ref);
-    cudaFree(s->ref_alt);
-    cudaFree(s->key);
-    cudaFree(s->key_alt);
-    cudaFree(s->cell_start);
-    cudaFree(s->cell_fill);
-    cudaFree(s->perm);
-    cudaFree(s->tmp_slot);
-    cudaFree(s->flags);
-    cudaFree(s->scan_tmp);
-    cudaFree(s->counters);
-    cudaFree(s->stage);
-    cudaFree(s->dscal);
-    cudaFree(s->ucoord);
-    cudaFree(s->nbr_ids);
-    cudaFree(s->nbr_cnt);
-    cudaFree(s->pk);
+    sp_dfree(s, s->ref);
+    sp_dfree(s, s->ref_alt);
+    sp_dfree(s, s->key);
+    sp_dfree(s, s->key_alt);
+    sp_dfree(s, s->cell_start);
+    sp_dfree(s, s->cell_fill);
+    sp_dfree(s, s->perm);
+    sp_dfree(s, s->tmp_slot);
+    sp_dfree(s, s->flags);
+    sp_dfree(s, s->scan_tmp);
+    sp_dfree(s, s->counters);
+    sp_dfree(s, s->stage);
+    sp_dfree(s, s->dscal);
+    sp_dfree(s, s->ucoord);
+    sp_dfree(s, s->nbr_ids);
+    sp_dfree(s, s->nbr_cnt);
+    sp_dfree(s, s->pk);
     if (s->h_scal) cudaFreeHost(s->h_scal);
     if (s->h_counters) cudaFreeHost(s->h_counters);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -323,8 +369,8 @@ int32_t sp_add_field(sp_system* s, const char* name, int32_t ncomp, int32_t* fid
     f.ncomp = ncomp;
     if (s->cap > 0) {
         size_t bytes = (size_t)s->cap * ncomp * sizeof(double);
-        SP_CUDA(s, cudaMalloc(&f.d, bytes));
-        SP_CUDA(s, cudaMalloc(&f.alt, bytes));
+        SP_CUDA(s, sp_dmalloc(&f.d, bytes));
+        SP_CUDA(s, sp_dmalloc(&f.alt, bytes));
         SP_CUDA(s, cudaMemsetAsync(f.d, 0, bytes, s->stream));
     }
     s->fields.push_back(f);

@@ -229,6 +229,10 @@ class ParticleSystem:
         abi.check(self._lib.sp_get_neighbour_lists(self._h, abi.ptr_i64(offsets), abi.ptr_i64(ids), total), self._h)
         return offsets, ids[:total]
 
+    def build_neighbour_lists(self):
+        """Build the cached neighbour lists now (optional: the first binary apply() after a move does it lazily)."""
+        abi.check(self._lib.sp_build_neighbour_lists(self._h), self._h)
+
     def sweep_neighbour_lists(self):
         """The cached lists the default pair sweeps replay (same sets as neighbour_lists(), sweep visiting order)."""
         n = len(self)
