@@ -24,6 +24,9 @@
 #include <cstdio>
 #include <cstring>
 
+#include <time.h>
+#include <cstdio>
+
 #include "sp_internal.cuh"
 
 namespace {
@@ -89,7 +92,20 @@ struct SlabState {
     // old ghosts, migrants or new boundary particles.  sel_valid is dropped whenever the host touched positions.
     long long sel_a = 0, sel_b = 0;
     bool sel_valid = false;
+    // SP_SLAB_TRACE=1: host wall-clock of the phases of sp_slab_create_cell_list (each ends in a stream sync)
+    double trace_s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long trace_calls = 0;
 };
+
+static bool slab_trace_on() {
+    static const bool on = getenv("SP_SLAB_TRACE") && atoi(getenv("SP_SLAB_TRACE"));
+    return on;
+}
+static double slab_now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
 
 #define SP_NCCL(s, call)                                                                                  \
     do {                                                                                                  \
@@ -262,8 +278,8 @@ __global__ void k_slab_iota(int* ref, long long n) {
 __global__ void k_slab_count_owned(const double* ghost, long long n, int* out) {
     const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const int owned = (s < n && ghost[s] == 0.0) ? 1 : 0;
-    const unsigned b = __ballot_sync(0xffffffffu, owned);
-    if ((threadIdx.x & 31) == 0 && b) atomicAdd(out, __popc(b));
+    const int total = __syncthreads_count(owned);  // one atomic per CTA: 300 k same-address atomics cost 0.15 ms
+    if (threadIdx.x == 0 && total) atomicAdd(out, total);
 }
 
 // ------------------------------------------------------------------ host helpers
@@ -566,10 +582,24 @@ int32_t sp_slab_create_cell_list(sp_system* s) {
     int rc = sp_time_begin(s);
     if (rc) return rc;
     long long rl, rh, sd, su;
+    const bool trace = slab_trace_on();
+    double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    if (trace) {
+        cudaStreamSynchronize(s->stream);
+        t0 = slab_now();
+    }
     // 1+2: drop old ghosts, migrate
     if ((rc = slab_round(s, false, &rl, &rh, &sd, &su))) return rc;
+    if (trace) {
+        cudaStreamSynchronize(s->stream);
+        t1 = slab_now();
+    }
     // 3: ghost halo
     if ((rc = slab_round(s, true, &rl, &rh, &sd, &su))) return rc;
+    if (trace) {
+        cudaStreamSynchronize(s->stream);
+        t2 = slab_now();
+    }
     sl->n_ghost[0] = rl;
     sl->n_ghost[1] = rh;
     sl->n_send[0] = sd;
@@ -580,6 +610,10 @@ int32_t sp_slab_create_cell_list(sp_system* s) {
     if ((rc = sp_build_cells(s))) return rc;
     if (s->n) SP_LAUNCH(s, k_slab_iota, sp_blocks(s->n, 256), 256, 0, s->ref, s->n);
     s->identity_order = true;
+    if (trace) {
+        cudaStreamSynchronize(s->stream);
+        t3 = slab_now();
+    }
     // owned count, and the slot window of the next rebuild's selection passes (three cell layers per side)
     SP_CUDA(s, cudaMemsetAsync(sl->d_cnt + 8, 0, sizeof(int), s->stream));
     if (s->n)
@@ -597,6 +631,17 @@ int32_t sp_slab_create_cell_list(sp_system* s) {
     sl->sel_a = sl->h_cnt[9];
     sl->sel_b = sl->h_cnt[10];
     sl->n_owned = sl->h_cnt[8];
+    if (trace) {
+        const double t4 = slab_now();
+        sl->trace_s[0] += t1 - t0;
+        sl->trace_s[1] += t2 - t1;
+        sl->trace_s[2] += t3 - t2;
+        sl->trace_s[3] += t4 - t3;
+        if (++sl->trace_calls % 20 == 0)
+            fprintf(stderr, "[slab trace rank %d] calls=%lld migrate=%.3f ms ghosts=%.3f ms build=%.3f ms tail=%.3f ms (n=%lld ghosts=%lld+%lld)\n",
+                    sl->rank, sl->trace_calls, 1e3 * sl->trace_s[0] / sl->trace_calls, 1e3 * sl->trace_s[1] / sl->trace_calls,
+                    1e3 * sl->trace_s[2] / sl->trace_calls, 1e3 * sl->trace_s[3] / sl->trace_calls, (long long)s->n, rl, rh);
+    }
     return sp_time_end(s);
 }
 

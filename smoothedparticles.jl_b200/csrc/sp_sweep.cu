@@ -70,6 +70,13 @@ struct QGlobal {
     __device__ __forceinline__ double operator()(int k) const { return qp[k][j]; }
 };
 
+// q-field values of one neighbour already in registers (list replay kernel)
+template <int NQ>
+struct QRegs {
+    double v[NQ > 0 ? NQ : 1];
+    __device__ __forceinline__ double operator()(int k) const { return v[k]; }
+};
+
 // ---- reference-order kernel (SP_FLAG_STRICT_ORDER, and the parity views): one thread per particle,
 // candidates read straight from the sorted planes.
 __device__ __forceinline__ double sp_sqrt_fast(double a);
@@ -693,13 +700,35 @@ __global__ void __launch_bounds__(128, 6) k_sweep_list(SpGrid g, SweepCtx c, con
         constexpr int TPW = 32 / G;  // targets per warp tile
         const int* col = ids + ((size_t)(i / TPW) * (SP_NBR_CAPK / G) << 5) + (i % TPW) * G + sub;
         const int n_it = (n_nb - sub + G - 1) / G;  // entries sub, sub+G, ...
-#pragma unroll 2
-        for (int k = 0; k < n_it; k++) {
+        // U pairs per trip: all their loads (ids first, then the gathers) are issued before the first pair body, so
+        // each warp keeps U*(3+NQ) gathers in flight — the kernel is bound by the latency / L1 cost of these loads
+        constexpr int U = Op::NQ <= 1 ? 4 : 2;
+        int k = 0;
+        for (; k + U <= n_it; k += U) {
+            int jj[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) jj[u] = __ldcs(col + ((k + u) << 5));
+            double qx[U], qy[U], qz[U];
+            QRegs<Op::NQ> q[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                qx[u] = c.x[jj[u]];
+                qy[u] = c.y[jj[u]];
+                qz[u] = c.z[jj[u]];
+#pragma unroll
+                for (int e = 0; e < Op::NQ; e++) q[u].v[e] = P.qp[e][jj[u]];
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const double dx = __dsub_rn(xi, qx[u]), dy = __dsub_rn(yi, qy[u]), dz = __dsub_rn(zi, qz[u]);
+                Op::pair(P, p, q[u], dx, dy, dz, sp_sqrt_fast(sp_d2(dx, dy, dz)), acc);
+            }
+        }
+        for (; k < n_it; k++) {
             const int j = __ldcs(col + (k << 5));
             const double dx = __dsub_rn(xi, c.x[j]), dy = __dsub_rn(yi, c.y[j]), dz = __dsub_rn(zi, c.z[j]);
-            const double d2 = sp_d2(dx, dy, dz);
             QGlobal<Op::NQ> q{P.qp, j};
-            Op::pair(P, p, q, dx, dy, dz, sp_sqrt_fast(d2), acc);
+            Op::pair(P, p, q, dx, dy, dz, sp_sqrt_fast(sp_d2(dx, dy, dz)), acc);
         }
     } else if (sub == 0) {
         // more neighbours than the cache holds per target: the exact candidate scan, same visiting order
