@@ -108,8 +108,12 @@ def run_multi(args, METRIC, UNIT, ClockSampler, peaks):
     sysd = make_system()
     assert np.all(sysd.owns(x)), "generator and slab partition disagree"
     sysd.add_particles(x=x, v=v, rho=np.full(n_local, rho0), type=typ)
-    for _ in range(args.warmup):
-        slab.wcsph3d_slab_step(sysd, o)
+    # the step loop is issued from inside the library (sp_run_program on a slab system: slab rebuild with migration
+    # and ghost halos, sweeps, halo refresh of rho and P) — the same driver as the N = 1 `value`
+    prog = K["SP_PROGRAM_WCSPH_3D"]
+    prog_fields = ("x", "v", "Dv", "rho", "Drho", "P", "type")
+    prog_params = (float(K["SP_KERNEL_WENDLAND3"]), m, h, 2 * nu, dt, c * c, rho0, mu, *g)
+    sysd.run_program(prog, prog_fields, prog_params, args.warmup)
     sysd.synchronize()
     launches0 = sysd.launch_count
     sampler = ClockSampler(local)
@@ -118,8 +122,7 @@ def run_multi(args, METRIC, UNIT, ClockSampler, peaks):
     dist.barrier()
     torch.cuda.synchronize()
     sysd.timer_start()
-    for _ in range(args.steps):
-        slab.wcsph3d_slab_step(sysd, o)
+    sysd.run_program(prog, prog_fields, prog_params, args.steps)
     ms = sysd.timer_stop()
     torch.cuda.synchronize()
     dist.barrier()

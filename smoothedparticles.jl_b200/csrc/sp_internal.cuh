@@ -20,6 +20,7 @@
 #include "../../include/sp_b200.h"
 
 #define SP_MAX_FIELDS 64
+#define SP_FLAG_INTERNAL_PR_READY (1 << 30) /* library-internal: _pr = P/rho^2 is already up to date */
 
 struct SpField {
     std::string name;
@@ -97,6 +98,7 @@ struct sp_system {
     double* h_scal = nullptr;   // pinned mirror of a few scalars
 
     bool have_cells = false;
+    bool in_program = false;  // inside sp_run_program: nested entry points do not touch the per-call timing events
     bool identity_order = true;  // slot s holds reference particle s
     long long n_removed = 0;
     long long last_culled = 0;  // particles dropped by the last cell-list build

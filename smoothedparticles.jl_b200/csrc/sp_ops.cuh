@@ -487,6 +487,43 @@ struct UAccelerate {
         }
     }
 };
+// ---- fused unary passes used by the step programs (sp_program.cu): the same statements in the same order as the
+// separate operators (bit-identical results), one trip through HBM instead of two or three.
+// accelerate!; accelerate!; move!  — the end of one collapse3d.jl step and the start of the next (:136-150)
+struct UKickKickMove {
+    struct Params {
+        WV3 v, Dv, x;
+        const double* type;
+        double hdt, gx, gy, gz, dtm;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        if (P.type[i] == 0.0) {
+            const double ax = P.Dv.x[i] + P.gx, ay = P.Dv.y[i] + P.gy, az = P.Dv.z[i] + P.gz;
+            double vx = P.v.x[i], vy = P.v.y[i], vz = P.v.z[i];
+            vx += P.hdt * ax; vy += P.hdt * ay; vz += P.hdt * az;  // accelerate!
+            vx += P.hdt * ax; vy += P.hdt * ay; vz += P.hdt * az;  // accelerate!
+            P.v.x[i] = vx; P.v.y[i] = vy; P.v.z[i] = vz;
+            P.x.x[i] += P.dtm * vx; P.x.y[i] += P.dtm * vy; P.x.z[i] += P.dtm * vz;  // move!
+        }
+        P.Dv.x[i] = 0.0; P.Dv.y[i] = 0.0; P.Dv.z[i] = 0.0;
+    }
+};
+// find_pressure! followed by the hoisted P/rho^2 of internal_force! (UPressureOverRho2)
+struct UFindPressurePr {
+    struct Params {
+        double *rho, *Drho, *P, *pr;
+        double dt, c2, rho0, P0;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        double rho = P.rho[i] + P.Drho[i] * P.dt;
+        P.rho[i] = rho;
+        P.Drho[i] = 0.0;
+        double pr = P.c2 * (rho - P.rho0);
+        double pp = (P.P0 != 0.0) ? P.P0 + pr : pr;
+        P.P[i] = pp;
+        P.pr[i] = pp / (rho * rho);
+    }
+};
 // find_pressure!  test_collision_2d.jl:71-73
 struct UPressureFromRho {
     struct Params {

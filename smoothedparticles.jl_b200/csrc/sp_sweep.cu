@@ -1418,7 +1418,12 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
             NEED_CELLS();
             sp_wrote(s, F[4]);
             double* pr = nullptr;
-            {
+            if (flags & SP_FLAG_INTERNAL_PR_READY) {  // the step program's fused find_pressure pass has written _pr
+                int32_t fid;
+                if (sp_find_field(s, "_pr", &fid)) return sp_fail(s, SP_ERR_STATE, "_pr missing");
+                pr = s->fields[fid].d;
+                flags &= ~SP_FLAG_INTERNAL_PR_READY;
+            } else {
                 int rc2 = pressure_over_rho2(s, F[2], F[3], &pr);
                 if (rc2) return rc2;
             }
@@ -1590,6 +1595,28 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
         }
     }
     return sp_fail(s, SP_ERR_INVALID, "unknown operator id");
+}
+
+// fused unary passes of the step programs (sp_program.cu)
+// fields {v, Dv, x, type}; params {hdt, gx, gy, gz, dt_move}
+int sp_kick_kick_move_impl(sp_system* s, const int32_t* F, const double* Pm) {
+    sp_wrote(s, F[0]);
+    sp_zeroed(s, F[1]);
+    sp_wrote(s, F[2]);
+    UKickKickMove::Params P{wv3(s, F[0]), wv3(s, F[1]), wv3(s, F[2]), sc(s, F[3]), Pm[0], Pm[1], Pm[2], Pm[3], Pm[4]};
+    return launch_unary<UKickKickMove>(s, P);
+}
+// fields {rho, Drho, P}; params {dt, c2, rho0, P0}; also fills the scratch field _pr = P/rho^2
+int sp_find_pressure_pr_impl(sp_system* s, const int32_t* F, const double* Pm) {
+    int32_t fid;
+    int rc = sp_add_field(s, "_pr", 1, &fid);
+    if (rc) return rc;
+    s->fields[fid].transient = true;
+    sp_wrote(s, F[0]);
+    sp_zeroed(s, F[1]);
+    sp_wrote(s, F[2]);
+    UFindPressurePr::Params P{sc(s, F[0]), sc(s, F[1]), sc(s, F[2]), s->fields[fid].d, Pm[0], Pm[1], Pm[2], Pm[3]};
+    return launch_unary<UFindPressurePr>(s, P);
 }
 
 // fields {x, L, lambda, type, p_in, y_out}; params {kernel, m, h, rho, C_free}

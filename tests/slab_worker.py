@@ -41,7 +41,7 @@ def main():
     K = sp.K
     ok = True
     msg = ""
-    if case_name in ("box_nonperiodic", "box_steps"):
+    if case_name in ("box_nonperiodic", "box_steps", "box_program"):
         case = configs.lattice_box((20, 18, 26), jitter=0.15, dr=5e-3, seed=7)
         c = case.consts
         n = case.n
@@ -55,8 +55,12 @@ def main():
         o = case.ops
         names = ["x", "v", "rho", "P", "Dv"]
         nsteps = 1 if case_name == "box_nonperiodic" else 12
-        for _ in range(nsteps):
-            slab.wcsph3d_slab_step(sysd, o)
+        if case_name == "box_program":
+            # the same 12 steps issued from inside the library (sp_run_program on a slab system)
+            sysd.run_program(case.program, case.program_fields, case.program_params, nsteps)
+        else:
+            for _ in range(nsteps):
+                slab.wcsph3d_slab_step(sysd, o)
         tot = sysd.allreduce([sysd.n_owned])[0]
         res = gather_by_gid(sysd, names, rank, world)
         E = sysd.reduce(K["SP_RED_ENERGY_WCSPH"], ("x", "v", "rho"), (c["m"], c["c"], c["rho0"], *c["g"]))[0]

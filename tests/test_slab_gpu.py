@@ -35,12 +35,12 @@ def _run(case, world):
     assert r.returncode == 0 and "SLAB-OK" in out, out[-3000:]
 
 
-@pytest.mark.parametrize("case", ["box_nonperiodic", "box_steps", "box_periodic"])
+@pytest.mark.parametrize("case", ["box_nonperiodic", "box_steps", "box_program", "box_periodic"])
 def test_slab_single_rank(case):
     _run(case, 1)
 
 
-@pytest.mark.parametrize("case", ["box_nonperiodic", "box_steps", "box_periodic"])
+@pytest.mark.parametrize("case", ["box_nonperiodic", "box_steps", "box_program", "box_periodic"])
 def test_slab_two_ranks(case):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
