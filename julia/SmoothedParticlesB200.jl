@@ -11,7 +11,7 @@
 #   * the closures passed to apply! are registered operators (Operators.balance_of_mass(...), ...).
 module SmoothedParticlesB200
 
-export ParticleSystem, create_cell_list!, apply!, upload!, download, add_particles!, ParticleField,
+export ParticleSystem, create_cell_list!, build_neighbour_lists!, apply!, upload!, download, add_particles!, ParticleField,
        assemble_vector, Operators, poisson_cg!, reduce_energy_wcsph, sum_at_points
 
 const LIB = get(ENV, "SP_B200_LIB", joinpath(@__DIR__, "..", "smoothedparticles.jl_b200", "libsp_b200.so"))
@@ -86,6 +86,11 @@ end
 # create_cell_list!(sys), src/core.jl:51-90
 create_cell_list!(sys::ParticleSystem) =
     check(ccall((:sp_create_cell_list, LIB), Int32, (Ptr{Cvoid},), sys.handle), sys.handle)
+
+# Optional: evaluate the op-independent half of apply_binary! (src/core.jl:94-110) now; every binary apply! replays
+# the cached neighbour lists until positions change (the first apply! after a move does this lazily).
+build_neighbour_lists!(sys::ParticleSystem) =
+    check(ccall((:sp_build_neighbour_lists, LIB), Int32, (Ptr{Cvoid},), sys.handle), sys.handle)
 
 struct Operator
     id::Int32
