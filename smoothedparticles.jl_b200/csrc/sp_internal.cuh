@@ -94,6 +94,8 @@ struct sp_system {
         int v_fid = -1, kernel = -1, f_kx = -1, f_kv = -1;
         double m = 0, h = 0;
     } pair_aux;
+    double* ell_val = nullptr;  // ISPH: Poisson-operator coefficients in the neighbour-list layout (sp_isph.cu)
+    long long ell_cap = 0;
     double* dscal = nullptr;    // CG scalars + dot partials (3*1024 + 16 doubles)
     double* h_scal = nullptr;   // pinned mirror of a few scalars
 

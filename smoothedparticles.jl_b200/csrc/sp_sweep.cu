@@ -1597,6 +1597,69 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
     return sp_fail(s, SP_ERR_INVALID, "unknown operator id");
 }
 
+// ---- ISPH: coefficients of the pressure-Poisson operator in the layout of the cached neighbour lists (ELL).
+// A is constant during a CG solve (positions are fixed), so A_ij = 2h^2 (m/rho) rDk(r_ij) is evaluated once per
+// solve — what assemble_matrix(sys, projection_matrix) does in the reference (core.jl:196-225,
+// collapse_dry_implicit.jl:154-163) — and every mat-vec of the CG is then one gather per entry (sp_isph.cu).
+template <class K>
+__global__ void __launch_bounds__(128) k_poisson_coeffs(SweepCtx c, const int* __restrict__ cnt, const int* __restrict__ ids,
+                                                        const double* __restrict__ L, const double* __restrict__ lambda,
+                                                        const double* __restrict__ type, double off_coef, double h2,
+                                                        double C_free, SpKC kc, double* __restrict__ aval,
+                                                        double* __restrict__ diag, int* __restrict__ overflow) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    double Aii = h2 * L[i];
+    if (type[i] == 0.0) Aii += C_free * fmax(lambda[i], 0.0);
+    diag[i] = Aii;
+    const int n_nb = cnt[i];
+    if (n_nb > SP_NBR_CAPK) {
+        *overflow = 1;  // the caller falls back to the matrix-free operator
+        return;
+    }
+    const double xi = c.x[i], yi = c.y[i], zi = c.z[i];
+    const size_t base = ((size_t)(i >> 5) * SP_NBR_CAPK << 5) + (i & 31);
+    for (int k = 0; k < n_nb; k++) {
+        const int j = ids[base + ((size_t)k << 5)];
+        const double dx = __dsub_rn(xi, c.x[j]), dy = __dsub_rn(yi, c.y[j]), dz = __dsub_rn(zi, c.z[j]);
+        aval[base + ((size_t)k << 5)] = off_coef * K::rD(kc, sp_sqrt_fast(sp_d2(dx, dy, dz)));
+    }
+}
+
+// fields {x, L, lambda, type}; params {kernel, m, h, rho, C_free}; aval: cap*SP_NBR_CAPK doubles, diag: n doubles
+int sp_poisson_ell_build(sp_system* s, const int32_t* F, const double* Pm, double* aval, double* diag, int* d_overflow,
+                         const int** ids_out, const int** cnt_out) {
+    SweepCtx c;
+    sp_sweep_ctx(s, c);
+    int rc = sp_ensure_nbr_cache(s, c);
+    if (rc) return rc;
+    SpKC kc;
+    const int kernel = (int)Pm[0];
+    if (!sp_make_kc(kernel, Pm[2], &kc)) return sp_fail(s, SP_ERR_INVALID, "unknown SPH kernel id");
+    const double off_coef = 2.0 * (Pm[2] * Pm[2]) * Pm[1] / Pm[3], h2 = Pm[2] * Pm[2], C_free = Pm[4];
+    const double *L = sc(s, F[1]), *lam = sc(s, F[2]), *ty = sc(s, F[3]);
+    const unsigned nb = sp_blocks(s->n, 128);
+    switch (kernel) {
+        case SP_KERNEL_WENDLAND1:
+        case SP_KERNEL_WENDLAND2:
+        case SP_KERNEL_WENDLAND3:
+            SP_LAUNCH(s, k_poisson_coeffs<KWendland>, nb, 128, 0, c, s->nbr_cnt, s->nbr_ids, L, lam, ty, off_coef, h2, C_free,
+                      kc, aval, diag, d_overflow);
+            break;
+        case SP_KERNEL_SPLINE23:
+            SP_LAUNCH(s, k_poisson_coeffs<KSpline23>, nb, 128, 0, c, s->nbr_cnt, s->nbr_ids, L, lam, ty, off_coef, h2, C_free,
+                      kc, aval, diag, d_overflow);
+            break;
+        default:
+            SP_LAUNCH(s, k_poisson_coeffs<KSpline24>, nb, 128, 0, c, s->nbr_cnt, s->nbr_ids, L, lam, ty, off_coef, h2, C_free,
+                      kc, aval, diag, d_overflow);
+    }
+    *ids_out = s->nbr_ids;
+    *cnt_out = s->nbr_cnt;
+    return SP_OK;
+}
+int sp_nbr_capk() { return SP_NBR_CAPK; }
+
 // fused unary passes of the step programs (sp_program.cu)
 // fields {v, Dv, x, type}; params {hdt, gx, gy, gz, dt_move}
 int sp_kick_kick_move_impl(sp_system* s, const int32_t* F, const double* Pm) {

@@ -327,6 +327,7 @@ int32_t sp_destroy(sp_system* s) {
     sp_dfree(s, s->dscal);
     sp_dfree(s, s->ucoord);
     sp_dfree(s, s->nbr_ids);
+    sp_dfree(s, s->ell_val);
     sp_dfree(s, s->nbr_cnt);
     sp_dfree(s, s->pk);
     if (s->h_scal) cudaFreeHost(s->h_scal);
