@@ -62,6 +62,8 @@ class ClockSampler:
         self.path = None
 
     def start(self):
+        if os.environ.get("SP_BENCH_NO_SAMPLER"):   # diagnostic: does the nvidia-smi poll perturb the timed region?
+            return
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)

@@ -338,16 +338,23 @@ static void slab_peers(const SlabState* sl, int* below, int* above) {
     }
 }
 
-// exchange send counts with both neighbours: h_cnt[0],[1] = my counts down/up -> h_cnt[2],[3] = counts arriving
-// from below / above
-static int slab_exchange_counts(sp_system* s, long long n_dn, long long n_up, long long* from_below, long long* from_above) {
+// totals of the two selections on the device: d_cnt[0] = to send down, d_cnt[1] = to send up (last exclusive-scan
+// value + last flag), d_cnt[2], d_cnt[3] cleared for the receive counts
+__global__ void k_slab_totals(const int* fd, const int* fu, const int* posd, const int* posu, long long ns, int* d_cnt) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        d_cnt[0] = ns > 0 ? posd[ns - 1] + fd[ns - 1] : 0;
+        d_cnt[1] = ns > 0 ? posu[ns - 1] + fu[ns - 1] : 0;
+        d_cnt[2] = 0;
+        d_cnt[3] = 0;
+    }
+}
+
+// exchange the send counts (already in d_cnt[0], d_cnt[1]) with both neighbours and bring all four numbers to the
+// host with ONE synchronisation: h_cnt[0],[1] = my counts down/up, h_cnt[2],[3] = counts arriving from below / above
+static int slab_exchange_counts(sp_system* s, long long* n_dn, long long* n_up, long long* from_below, long long* from_above) {
     SlabState* sl = s->slab;
     int below, above;
     slab_peers(sl, &below, &above);
-    sl->h_cnt[0] = (int)n_dn;
-    sl->h_cnt[1] = (int)n_up;
-    sl->h_cnt[2] = sl->h_cnt[3] = 0;
-    SP_CUDA(s, cudaMemcpyAsync(sl->d_cnt, sl->h_cnt, 4 * sizeof(int), cudaMemcpyHostToDevice, s->stream));
     // Call order matters when below == above (1 or 2 ranks, periodic): messages between one pair of ranks are
     // matched in issue order, and what I send DOWN arrives at my lower neighbour FROM ABOVE.  So: send down,
     // send up, then receive from above, receive from below.
@@ -359,6 +366,8 @@ static int slab_exchange_counts(sp_system* s, long long n_dn, long long n_up, lo
     SP_NCCL(s, g_nccl.GroupEnd());
     SP_CUDA(s, cudaMemcpyAsync(sl->h_cnt, sl->d_cnt, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     SP_CUDA(s, cudaStreamSynchronize(s->stream));
+    *n_dn = sl->h_cnt[0];
+    *n_up = sl->h_cnt[1];
     *from_below = below >= 0 ? sl->h_cnt[2] : 0;
     *from_above = above >= 0 ? sl->h_cnt[3] : 0;
     return SP_OK;
@@ -417,17 +426,12 @@ static int slab_round(sp_system* s, bool ghosts, long long* n_recv_lo, long long
         int rc = sp_exclusive_scan_i32(s, posd, ns);
         if (rc) return rc;
         if ((rc = sp_exclusive_scan_i32(s, posu, ns))) return rc;
-        // totals = last exclusive value + last flag
-        SP_CUDA(s, cudaMemcpyAsync(sl->h_cnt + 4, posd + ns - 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-        SP_CUDA(s, cudaMemcpyAsync(sl->h_cnt + 5, fd + ns - 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-        SP_CUDA(s, cudaMemcpyAsync(sl->h_cnt + 6, posu + ns - 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-        SP_CUDA(s, cudaMemcpyAsync(sl->h_cnt + 7, fu + ns - 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-        SP_CUDA(s, cudaStreamSynchronize(s->stream));
-    } else
-        sl->h_cnt[4] = sl->h_cnt[5] = sl->h_cnt[6] = sl->h_cnt[7] = 0;
-    const long long send_dn = sl->h_cnt[4] + sl->h_cnt[5], send_up = sl->h_cnt[6] + sl->h_cnt[7];
-    long long recv_lo = 0, recv_hi = 0;
-    int rc = slab_exchange_counts(s, send_dn, send_up, &recv_lo, &recv_hi);
+    }
+    // totals stay on the device: they go to the neighbours from there, and one synchronisation brings the send and
+    // receive counts to the host together
+    SP_LAUNCH(s, k_slab_totals, 1, 32, 0, fd, fu, posd, posu, ns, sl->d_cnt);
+    long long send_dn = 0, send_up = 0, recv_lo = 0, recv_hi = 0;
+    int rc = slab_exchange_counts(s, &send_dn, &send_up, &recv_lo, &recv_hi);
     if (rc) return rc;
     if (ghosts && n > 0) {
         SP_LAUNCH(s, k_slab_fill2, sp_blocks(n, B), B, 0, s->fields[sl->f_sdn].d, s->fields[sl->f_sup].d, -1.0, n);
