@@ -1,7 +1,7 @@
 """B200-native neighbour search and pair sweeps behind the ParticleSystem / create_cell_list! / apply!
 surface of SmoothedParticles.jl.  Importing this package does not load the CUDA library; constructing a
 ParticleSystem does, and fails loudly when it is not built (no CPU fallback)."""
-from . import abi, geometry, operators  # noqa: F401
+from . import abi, geometry, io, operators  # noqa: F401
 from .abi import SpError  # noqa: F401
 from .geometry import (Ball, BoundaryLayer, Box, Circle, CubicGrid, Hexagrid, Rectangle, Specification,  # noqa: F401
                        Squaregrid, covering, generate_positions, make_grid)

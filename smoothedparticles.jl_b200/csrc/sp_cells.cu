@@ -234,7 +234,13 @@ int sp_build_cells(sp_system* s) {
     int* off = s->perm;  // arrival offsets live in perm until the scatter has consumed them
     SP_LAUNCH(s, k_cull_key, sp_blocks(N, B), B, 0, g, s->fields[0].d, s->cap, N, s->key, off, s->cell_start, s->counters);
     SP_CUDA(s, cudaMemcpyAsync(s->h_counters, s->counters, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-    SP_CUDA(s, cudaStreamSynchronize(s->stream));
+    SP_CUDA(s, cudaEventRecord(s->ev_count, s->stream));
+    // the scan of the per-cell counts and the scatter do not depend on the removed count (nor on ref): they are
+    // queued BEHIND the 4-byte read-back, so the GPU has work while the host waits for the count
+    int rc = sp_exclusive_scan_i32(s, s->cell_start, K + 3);
+    if (rc) return rc;
+    SP_LAUNCH(s, k_scatter, sp_blocks(N, B), B, 0, s->key, off, s->cell_start, s->tmp_slot, N);
+    SP_CUDA(s, cudaEventSynchronize(s->ev_count));
     const int n_out = s->h_counters[0];
     const long long n_new = N - n_out;
     if (n_out > 0 && g.slab_axis < 0) {
@@ -243,17 +249,13 @@ int sp_build_cells(sp_system* s) {
         int* Vscan = s->key_alt;
         int* newref = s->ref_alt;
         SP_LAUNCH(s, k_mark_victims, sp_blocks(N, B), B, 0, s->key, s->ref, (int)K + 1, V, Vscan, N);
-        int rc = sp_exclusive_scan_i32(s, Vscan, N);
-        if (rc) return rc;
+        if ((rc = sp_exclusive_scan_i32(s, Vscan, N))) return rc;
         if (n_new > 0) {
             SP_LAUNCH(s, k_chain, sp_blocks(n_new, B), B, 0, V, Vscan, n_out, N, n_new, newref);
             SP_LAUNCH(s, k_apply_newref, sp_blocks(N, B), B, 0, s->key, (int)K + 1, s->ref, newref, n_new, N);
         }
         s->n_removed += n_out;
     }
-    int rc = sp_exclusive_scan_i32(s, s->cell_start, K + 3);
-    if (rc) return rc;
-    SP_LAUNCH(s, k_scatter, sp_blocks(N, B), B, 0, s->key, off, s->cell_start, s->tmp_slot, N);
     if (n_new > 0) {
         SP_LAUNCH(s, k_rank, sp_blocks(n_new, B), B, 0, s->key, s->ref, s->cell_start, s->tmp_slot, s->perm, n_new);
         rc = sp_permute_all(s, n_new);

@@ -55,6 +55,7 @@ struct sp_system {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;    // per-call timing
     cudaEvent_t tev0 = nullptr, tev1 = nullptr;  // sp_timer_start/stop
+    cudaEvent_t ev_count = nullptr;              // the removed-count read-back of the cell-list build
     SpGrid g{};
     int n_key_diff = 0;
     long long key_diff[27]{};
