@@ -1160,7 +1160,8 @@ static int sp_ensure_prefilter(sp_system* s, SweepCtx& c) {
     if (!s->ucoord || s->ucoord_cap != s->cap) {
         if (s->ucoord) SP_CUDA(s, sp_dfree(s, s->ucoord));
         s->ucoord = nullptr;
-        SP_CUDA(s, sp_dmalloc(&s->ucoord, (size_t)3 * s->cap * sizeof(float)));
+        // + 64: the pre-filter reads whole aligned groups of 4 (pairs) of candidates, up to 3 slots past slot n-1
+        SP_CUDA(s, sp_dmalloc(&s->ucoord, ((size_t)3 * s->cap + 64) * sizeof(float)));
         s->ucoord_cap = s->cap;
         s->ucoord_version = 0;
     }
