@@ -122,8 +122,20 @@ enum {
     /* unary (assemble_vector). fields {div, b}; params {h, dt}   b = -h^2*div/dt   :165-167 */
     SP_OP_ISPH_INTERNAL_FORCE = 25,
     /* binary. fields {x, P, Dv}; params {kernel, m, h, rho}   Dv_p -= (m*rDk*(P_p+P_q)/rho^2)*x_pq   :132-134 */
-    SP_OP_ISPH_ACCELERATE = 26
+    SP_OP_ISPH_ACCELERATE = 26,
     /* unary. fields {v, Dv, type}; params {dt}   if type == 0: v += dt*Dv;  Dv = 0   :136-141 */
+
+    /* WCSPH with the density integrated in the pair loop — examples/static_container.jl */
+    SP_OP_SC_BALANCE_OF_MASS = 30,
+    /* binary. fields {x, v, rho}; params {kernel, m, h, dt}
+       rho_p += dt*dot(x_pq, v_pq)*m*rDw(h,r)        static_container.jl:102-104 */
+    SP_OP_SC_INTERNAL_FORCE = 31,
+    /* binary. fields {x, v, rho, a, type}; params {kernel, m, h, mu, c2, rho0}   with P(rho) = c2*(rho - rho0):
+       if type_p == 0: ker = m*rDw(h,r);
+         a_p += (-ker*(P(rho_p)/rho_p^2 + P(rho_q)/rho_q^2))*x_pq;  a_p += (ker*2*mu/(rho_p*rho_q))*v_pq
+       static_container.jl:106-114 (pressure: :68-70) */
+    SP_OP_MOVE_ALL = 32
+    /* unary. fields {x, v, a}; params {dtm}   x += dtm*v (every particle); a = 0   static_container.jl:116-119 */
 };
 
 /* sp_apply flags */

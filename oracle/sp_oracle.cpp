@@ -440,6 +440,46 @@ int apply_op(OSys& s, int op, const int32_t* F, int nf, const double* P, int np,
             });
             return SP_OK;
         }
+        case SP_OP_SC_BALANCE_OF_MASS: {  // static_container.jl:102-104
+            if (!need(3, 4)) return SP_ERR_INVALID;
+            const int ov = F[1], orho = F[2];
+            kfn rDw = pick_rD((int)P[0]);
+            const double m = P[1], h = P[2], dt = P[3];
+            if (!rDw) return SP_ERR_INVALID;
+            apply_binary(s, [=](Particle& p, const Particle& q, const double* xpq, double r) {
+                double vpq[3] = {p.f[ov] - q.f[ov], p.f[ov + 1] - q.f[ov + 1], p.f[ov + 2] - q.f[ov + 2]};
+                p.f[orho] += dt * dot3(xpq, vpq) * m * rDw(h, r);
+            });
+            return SP_OK;
+        }
+        case SP_OP_SC_INTERNAL_FORCE: {  // static_container.jl:106-114, pressure(p) :68-70
+            if (!need(5, 6)) return SP_ERR_INVALID;
+            const int ov = F[1], orho = F[2], oa = F[3], ot = F[4];
+            kfn rDw = pick_rD((int)P[0]);
+            const double m = P[1], h = P[2], mu = P[3], c2 = P[4], rho0 = P[5];
+            if (!rDw) return SP_ERR_INVALID;
+            apply_binary(s, [=](Particle& p, const Particle& q, const double* xpq, double r) {
+                if (p.f[ot] == 0.0) {
+                    double ker = m * rDw(h, r);
+                    double Pp = c2 * (p.f[orho] - rho0), Pq = c2 * (q.f[orho] - rho0);
+                    double a = -ker * (Pp / (p.f[orho] * p.f[orho]) + Pq / (q.f[orho] * q.f[orho]));
+                    for (int c = 0; c < 3; c++) p.f[oa + c] += a * xpq[c];
+                    double b = ker * 2 * mu / (p.f[orho] * q.f[orho]);
+                    for (int c = 0; c < 3; c++) p.f[oa + c] += b * (p.f[ov + c] - q.f[ov + c]);
+                }
+            });
+            return SP_OK;
+        }
+        case SP_OP_MOVE_ALL: {  // static_container.jl:116-119
+            if (!need(3, 1)) return SP_ERR_INVALID;
+            const int ox = F[0], ov = F[1], oa = F[2];
+            const double dtm = P[0];
+            apply_unary(s, [=](Particle& p) {
+                for (int c = 0; c < 3; c++) p.f[ox + c] += dtm * p.f[ov + c];
+                p.f[oa] = p.f[oa + 1] = p.f[oa + 2] = 0.0;
+            });
+            return SP_OK;
+        }
         case SP_OP_DENSITY_SUM: {  // test_collision_2d.jl:63-69; self term added last (core.jl:155-157)
             if (!need(2, 3)) return SP_ERR_INVALID;
             const int oo = F[1];

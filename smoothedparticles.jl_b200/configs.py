@@ -233,6 +233,55 @@ def cavity_flow(N: int = 100, Re: int = 100) -> Case:
                 consts=dict(dr=dr, h=h, rho0=rho0, m=m, c=c, dt=dt, Re=Re, P0=P0), dim=2)
 
 
+# --------------------------------------------------------------------------- static_container.jl
+def static_container(dr: float = 1.5e-3) -> Case:
+    """examples/static_container.jl:25-45 (constants), :82-98 (make_system), :133-141 (loop): a tank at rest with
+    the hydrostatic density profile; the density is integrated inside the pair loop and the pressure comes from the
+    equation of state inside internal_force!."""
+    h = 1.8 * dr
+    rho0 = 1000.0
+    m = rho0 * dr ** 2
+    c = 40.0
+    g = (0.0, -1.0, 0.0)  # -VECY
+    mu = 8.4e-4
+    water_depth, box_height, box_width = 0.14, 0.18, 0.14
+    wall_width = 2.5 * dr
+    dt = 0.2 * h / c
+    grid = geo.Squaregrid(dr)
+    box = geo.Rectangle(0.0, 0.0, box_width, box_height)
+    fluid = geo.Rectangle(0.0, 0.0, box_width, water_depth)
+    walls = geo.BoundaryLayer(box, grid, wall_width)
+    domain = (box + walls).boundarybox()
+    xf, xw = geo.covering(grid, fluid), geo.covering(grid, walls)
+    x = np.concatenate([xf, xw])
+    typ = np.concatenate([np.zeros(len(xf)), np.ones(len(xw))])
+    P = rho0 * g[1] * (x[:, 1] - water_depth)          # hydrostatic pressure, :91
+    rho = rho0 + P / c ** 2                            # :92
+    fields = {"v": 3, "a": 3, "rho": 1, "type": 1}
+    init = {"x": x, "rho": rho, "type": typ}
+    o_bom = ops.sc_balance_of_mass("wendland2", m, h, dt)
+    o_if = ops.sc_internal_force("wendland2", m, h, mu, c, rho0)
+    o_mv = ops.move_all(0.5 * dt)
+    o_ac = ops.accelerate(0.5 * dt, g, Dv="a")
+
+    def prologue(sys):  # :94-95
+        sys.create_cell_list()
+        sys.apply(o_if)
+
+    def step(sys):  # :133-141
+        sys.apply(o_ac)
+        sys.apply(o_mv)
+        sys.create_cell_list()
+        sys.apply(o_bom)
+        sys.apply(o_mv)
+        sys.create_cell_list()
+        sys.apply(o_if)
+        sys.apply(o_ac)
+
+    return Case("static_container", fields, domain, h, init, step, prologue,
+                consts=dict(dr=dr, h=h, rho0=rho0, m=m, c=c, mu=mu, dt=dt, g=g, water_depth=water_depth), dim=2)
+
+
 # --------------------------------------------------------------------------- collapse_dry_implicit.jl
 def collapse_dry_implicit(dr: float = 1.0e-2) -> Case:
     """examples/collapse_dry_implicit.jl:47-114 (constants, make_system) and :218-233 (loop).

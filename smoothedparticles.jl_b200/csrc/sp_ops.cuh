@@ -227,6 +227,77 @@ struct OpInternalForceCavity {
     }
 };
 
+// ---------------------------------------------------------------- examples/static_container.jl
+// balance_of_mass!  :102-104 — the density itself is integrated in the pair loop
+template <class K>
+struct OpScBalanceOfMass {
+    static constexpr int NQ = 3;  // vx, vy, vz
+    struct Params {
+        const double* qp[NQ];
+        double* rho;
+        double m, dt;
+        SpKC kc;
+    };
+    struct PS {
+        double vx, vy, vz;
+    };
+    struct Acc {
+        double d;
+    };
+    __device__ static __forceinline__ bool active(const Params&, int) { return true; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
+        p.vx = P.qp[0][i]; p.vy = P.qp[1][i]; p.vz = P.qp[2][i];
+        a.d = P.rho[i];
+    }
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, const Q& q, double dx, double dy,
+                                                double dz, double r, Acc& a) {
+        double dvx = p.vx - q(0), dvy = p.vy - q(1), dvz = p.vz - q(2);
+        a.d += P.dt * (dx * dvx + dy * dvy + dz * dvz) * P.m * K::rD(P.kc, r);
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) { P.rho[i] = a.d; }
+};
+
+// internal_force!  :106-114 with pressure(p) = c^2*(rho - rho0) (:68-70) hoisted to one evaluation per particle
+template <class K>
+struct OpScInternalForce {
+    static constexpr int NQ = 5;  // vx, vy, vz, pr = P(rho)/rho^2, rho
+    struct Params {
+        const double* qp[NQ];
+        const double* type;
+        WV3 a;
+        double m, two_mu;
+        SpKC kc;
+    };
+    struct PS {
+        double vx, vy, vz, pr, rho;
+    };
+    struct Acc {
+        double x, y, z;
+    };
+    __device__ static __forceinline__ bool active(const Params& P, int i) { return P.type[i] == 0.0; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
+        p.vx = P.qp[0][i]; p.vy = P.qp[1][i]; p.vz = P.qp[2][i];
+        p.pr = P.qp[3][i];
+        p.rho = P.qp[4][i];
+        a.x = P.a.x[i]; a.y = P.a.y[i]; a.z = P.a.z[i];
+    }
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, const Q& q, double dx, double dy,
+                                                double dz, double r, Acc& a) {
+        double ker = P.m * K::rD(P.kc, r);
+        double c = -ker * (p.pr + q(3));
+        a.x += c * dx; a.y += c * dy; a.z += c * dz;
+        double b = ker * P.two_mu / (p.rho * q(4));
+        a.x += b * (p.vx - q(0)); a.y += b * (p.vy - q(1)); a.z += b * (p.vz - q(2));
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) {
+        P.a.x[i] = a.x; P.a.y[i] = a.y; P.a.z[i] = a.z;
+    }
+};
+
 // ---------------------------------------------------------------- tests/test_collision_2d.jl
 // find_rho! / find_rho0!  :63-69, used with self=true
 template <class K>
@@ -522,6 +593,31 @@ struct UFindPressurePr {
         double pp = (P.P0 != 0.0) ? P.P0 + pr : pr;
         P.P[i] = pp;
         P.pr[i] = pp / (rho * rho);
+    }
+};
+// pr = c2*(rho - rho0)/rho^2: the per-particle part of static_container.jl's internal_force! (:68-70, :110)
+struct UEosPressureOverRho2 {
+    struct Params {
+        const double* rho;
+        double* pr;
+        double c2, rho0;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        double rho = P.rho[i];
+        P.pr[i] = (P.c2 * (rho - P.rho0)) / (rho * rho);
+    }
+};
+// move!  static_container.jl:116-119: every particle moves (walls have v = 0)
+struct UMoveAll {
+    struct Params {
+        WV3 x;
+        RV3 v;
+        WV3 a;
+        double dtm;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        P.x.x[i] += P.dtm * P.v.x[i]; P.x.y[i] += P.dtm * P.v.y[i]; P.x.z[i] += P.dtm * P.v.z[i];
+        P.a.x[i] = 0.0; P.a.y[i] = 0.0; P.a.z[i] = 0.0;
     }
 };
 // find_pressure!  test_collision_2d.jl:71-73

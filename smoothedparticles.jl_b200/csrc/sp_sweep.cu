@@ -1594,6 +1594,46 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
             UIsphAccelerate::Params P{wv3(s, F[0]), wv3(s, F[1]), sc(s, F[2]), Pm[0]};
             return launch_unary<UIsphAccelerate>(s, P);
         }
+        case SP_OP_SC_BALANCE_OF_MASS: {
+            NEED(3, 4, 3, 3, 1);
+            NEED_CELLS();
+            sp_wrote(s, F[2]);
+            return dispatch_kernel<OpScBalanceOfMass>(s, (int)Pm[0], Pm[2], flags, [&](auto& P) {
+                set_v3(s, F[1], P.qp);
+                P.rho = sc(s, F[2]);
+                P.m = Pm[1];
+                P.dt = Pm[3];
+            });
+        }
+        case SP_OP_SC_INTERNAL_FORCE: {
+            NEED(5, 6, 3, 3, 1, 3, 1);
+            NEED_CELLS();
+            sp_wrote(s, F[3]);
+            int32_t fpr;
+            {
+                int rc2 = sp_add_field(s, "_pr", 1, &fpr);
+                if (rc2) return rc2;
+                s->fields[fpr].transient = true;
+                UEosPressureOverRho2::Params Pp{sc(s, F[2]), s->fields[fpr].d, Pm[4], Pm[5]};
+                if ((rc2 = launch_unary<UEosPressureOverRho2>(s, Pp))) return rc2;
+            }
+            return dispatch_kernel<OpScInternalForce>(s, (int)Pm[0], Pm[2], flags, [&](auto& P) {
+                set_v3(s, F[1], P.qp);
+                P.qp[3] = s->fields[fpr].d;
+                P.qp[4] = sc(s, F[2]);
+                P.a = wv3(s, F[3]);
+                P.type = sc(s, F[4]);
+                P.m = Pm[1];
+                P.two_mu = 2 * Pm[3];
+            });
+        }
+        case SP_OP_MOVE_ALL: {
+            NEED(3, 1, 3, 3, 3);
+            sp_wrote(s, F[0]);
+            sp_zeroed(s, F[2]);
+            UMoveAll::Params P{wv3(s, F[0]), rv3(s, F[1]), wv3(s, F[2]), Pm[0]};
+            return launch_unary<UMoveAll>(s, P);
+        }
     }
     return sp_fail(s, SP_ERR_INVALID, "unknown operator id");
 }

@@ -89,6 +89,23 @@ def kick(hdt, v="v", a="a"):
     return Operator(K["SP_OP_KICK"], (v, a), (hdt,), False, "accelerate! (collision)")
 
 
+# ---- examples/static_container.jl
+def sc_balance_of_mass(kernel, m, h, dt, x="x", v="v", rho="rho"):
+    """static_container.jl:102-104: the density is integrated inside the pair loop."""
+    return Operator(K["SP_OP_SC_BALANCE_OF_MASS"], (x, v, rho), (_kid(kernel), m, h, dt), True, "balance_of_mass! (sc)")
+
+
+def sc_internal_force(kernel, m, h, mu, c, rho0, x="x", v="v", rho="rho", a="a", type="type"):
+    """static_container.jl:106-114 with pressure(p) = c^2*(rho - rho0) (:68-70)."""
+    return Operator(K["SP_OP_SC_INTERNAL_FORCE"], (x, v, rho, a, type), (_kid(kernel), m, h, mu, c * c, rho0), True,
+                    "internal_force! (sc)")
+
+
+def move_all(dtm, x="x", v="v", a="a"):
+    """static_container.jl:116-119."""
+    return Operator(K["SP_OP_MOVE_ALL"], (x, v, a), (dtm,), False, "move! (all)")
+
+
 # ---- ISPH: examples/collapse_dry_implicit.jl
 def isph_initialize(dt, g, x="x", v="v", div="div", L="L", lam="lambda", type="type"):
     return Operator(K["SP_OP_ISPH_INITIALIZE"], (x, v, div, L, lam, type), (dt, g[0], g[1], g[2]), False,

@@ -9,7 +9,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import smoothedparticles_jl_b200 as sp  # noqa: E402
 from smoothedparticles_jl_b200 import ParticleSystem, configs  # noqa: E402
 
-for maker in (configs.collapse_dry, configs.cavity_flow, configs.collision_2d, configs.collapse_dry_implicit):
+for maker in (configs.collapse_dry, configs.cavity_flow, configs.collision_2d, configs.static_container,
+              configs.collapse_dry_implicit):
     case = maker()
     s = case.make(ParticleSystem)
     case.prologue(s)
