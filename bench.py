@@ -203,6 +203,21 @@ def run_single(args):
     sysd.close()
     del sysd
 
+    # ---- the same initial state built by the device generator (sp_generate_particles) instead of numpy + upload
+    device_setup_s = None
+    try:
+        tmp = case.make_on_device(ParticleSystem, device=dev_index)   # warm-up (pool growth, module load)
+        tmp.close()
+        t0 = time.perf_counter()
+        tmp = case.make_on_device(ParticleSystem, device=dev_index)
+        tmp.synchronize()
+        device_setup_s = time.perf_counter() - t0
+        assert len(tmp) == n
+        tmp.close()
+        del tmp
+    except Exception as e:  # noqa: BLE001 - the generator is not on the measured path
+        device_setup_s = f"failed: {e}"
+
     # ---- end to end through the C ABI with HOST buffers: upload from pinned memory, K steps driven call by
     # call with a per-step device->host diagnostic (total energy), download of the result fields.
     e2e = run_e2e(case, args, dev_index)
@@ -217,7 +232,8 @@ def run_single(args):
         "config": {"workload": "examples/collapse3d.jl dam break scaled to 10 M particles (dr=%g)" % args.dr,
                    "particles": n, "particles_after": n_after, "h": case.h, "cells": int(np.prod(_key_lim(case))),
                    "l2": "state 1.04 GB >> 126 MB L2, no flush needed", "driver": "sp_run_program (fused step loop)",
-                   "setup_s": round(gen_s, 1)},
+                   "setup_s": round(gen_s, 1),
+                   "device_setup_s": (round(device_setup_s, 4) if isinstance(device_setup_s, float) else device_setup_s)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
         "breakdown_ms": breakdown, "cpu_baseline": cpu,
     }
@@ -278,6 +294,7 @@ def run_e2e(case, args, dev_index):
             s.upload_raw(nm, C.cast(t.data_ptr(), C.POINTER(C.c_double)), n, K["SP_LAYOUT_AOS"])
         mark("upload_s")
         energy = 0.0
+        energies = []
         for _ in range(args.steps):
             s.apply(o_mv)
             s.create_cell_list()
@@ -287,6 +304,7 @@ def run_e2e(case, args, dev_index):
             s.apply(o_ac)
             s.apply(o_ac)
             energy = s.reduce(K["SP_RED_ENERGY_WCSPH"], ("x", "v", "rho"), pe)[0]   # D2H every step
+            energies.append(energy)
         mark("steps_s")
         for nm, t in host_out.items():
             s.download_raw(nm, C.cast(t.data_ptr(), C.POINTER(C.c_double)), len(s), K["SP_LAYOUT_AOS"])
@@ -294,6 +312,7 @@ def run_e2e(case, args, dev_index):
         mark("download_s")
         s.close()
         mark("destroy_s")
+        phases["energy_first"] = energies[0] if energies else 0.0
         return energy
 
     job()  # warm-up (allocations, page-ins, lazy module load)
@@ -311,11 +330,13 @@ def run_e2e(case, args, dev_index):
     h2d = sum(t.numel() * 8 for t in host_in.values())
     d2h = sum(t.numel() * 8 for t in host_out.values())
     return {"value": n * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
-            "d2h_bytes_per_step": d2h / args.steps + 24, "seconds": dt, "phases": {k: round(v, 4) for k, v in phases.items()},
+            "d2h_bytes_per_step": d2h / args.steps + 24, "seconds": dt, "phases": {k: round(v, 4) for k, v in phases.items() if k.endswith("_s")},
             "what": "one job = sp_create + upload of x,v,rho,type from pinned host memory, K steps driven call by "
                     "call through the C ABI with a per-step energy read-back, download of x,v,rho,P, sp_destroy; "
                     "best of 3 jobs",
-            "energy": energy}
+            "energy": energy,
+            "energy_drift": ((energy - phases["energy_first"]) / abs(phases["energy_first"])
+                             if phases.get("energy_first") else None)}
 
 
 def cpu_baseline(case, sample_budget_s=20.0, steps=None, warmup=1):

@@ -203,6 +203,32 @@ int32_t sp_upload(sp_system* sys, int32_t fid, const double* host, int64_t n, in
 int32_t sp_download(sp_system* sys, int32_t fid, double* host, int64_t n, int32_t layout);
 int32_t sp_synchronize(sp_system* sys);
 
+/* ---- generate_particles! on the device (src/grids.jl:52-144, 253-258; shapes src/geometry.jl:15-258) ----------
+ * Every lattice point of the index box irange = {i0,i1,j0,j1,k0,k1} (inclusive; what floor/ceil of the shape's
+ * boundarybox over the lattice constant give, grids.jl:53-56) is tested against the shape; the points inside are
+ * appended to the system in the reference's generation order with the same Float64 coordinates.  The shape is a
+ * postfix program (children before parents, root last).  fill_fields/fill_values set constant scalar or vector
+ * fields of the new particles (what the example's particle constructor does, e.g. type, rho0); the rest is zero. */
+typedef struct {
+    int32_t kind;  /* SP_SHAPE_* */
+    int32_t a, b;  /* child node indices; HALFSPACE: a = axis (0,1,2), b = 0 '<', 1 '<=', 2 '>', 3 '>=' */
+    double p[8];   /* BOX lo[3],hi[3] | CIRCLE cx,cy,r*r | BALL cx,cy,cz,r*r | HALFSPACE bound */
+} sp_shape_node;
+enum {
+    SP_SHAPE_BOX = 1,            /* Box / Rectangle, closed            geometry.jl:15-43 */
+    SP_SHAPE_CIRCLE = 2,         /* geometry.jl:49-68 */
+    SP_SHAPE_BALL = 3,           /* geometry.jl:245-258 */
+    SP_SHAPE_UNION = 4,          /* geometry.jl:108-127 */
+    SP_SHAPE_INTERSECTION = 5,   /* geometry.jl:134-153 */
+    SP_SHAPE_DIFFERENCE = 6,     /* geometry.jl:160-171 */
+    SP_SHAPE_HALFSPACE = 7,      /* the Specification predicates of the examples (x[2] < h, ...)  geometry.jl:178-189 */
+    SP_SHAPE_BOUNDARY_LAYER = 8  /* geometry.jl:198-234: not in a, but x + dx in a for a lattice offset |dx| <= width */
+};
+enum { SP_GRID_SQUARE = 1, SP_GRID_HEXAGONAL = 2, SP_GRID_CUBIC = 3 }; /* grids.jl:48-91, 124-144 */
+int32_t sp_generate_particles(sp_system* sys, int32_t grid, double dr, const sp_shape_node* nodes, int32_t n_nodes,
+                              const double* offsets /* n_off x 3 */, int32_t n_off, const int64_t irange[6],
+                              const int32_t* fill_fields, const double* fill_values, int32_t n_fill, int64_t* n_added);
+
 /* ---- the hot path --------------------------------------------------------- */
 int32_t sp_create_cell_list(sp_system* sys);
 int32_t sp_apply(sp_system* sys, int32_t op, const int32_t* fields, int32_t nfields, const double* params,

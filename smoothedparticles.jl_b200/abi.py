@@ -39,6 +39,13 @@ KERNEL_IDS = {
 _p = C.c_void_p
 _i32, _i64, _f64 = C.c_int32, C.c_int64, C.c_double
 _pi32, _pi64, _pf64 = C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_double)
+
+
+class ShapeNode(C.Structure):
+    """sp_shape_node of include/sp_b200.h"""
+    _fields_ = [("kind", C.c_int32), ("a", C.c_int32), ("b", C.c_int32), ("p", C.c_double * 8)]
+
+
 SIGNATURES = {
     "sp_version": (_i32, []),
     "sp_last_error": (C.c_char_p, [_p]),
@@ -66,6 +73,8 @@ SIGNATURES = {
     "sp_get_neighbour_lists": (_i32, [_p, _pi64, _pi64, _i64]),
     "sp_get_sweep_neighbour_lists": (_i32, [_p, _pi64, _pi64, _i64]),
     "sp_build_neighbour_lists": (_i32, [_p]),
+    "sp_generate_particles": (_i32, [_p, _i32, _f64, C.POINTER(ShapeNode), _i32, _pf64, _i32, _pi64, _pi32, _pf64, _i32,
+                                     _pi64]),
     "sp_num_removed": (_i32, [_p, _pi64]),
     "sp_last_call_ms": (_i32, [_p, C.POINTER(C.c_float)]),
     "sp_timer_start": (_i32, [_p]),

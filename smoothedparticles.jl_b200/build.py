@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsp_b200.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["sp_system.cu", "sp_cells.cu", "sp_sweep.cu", "sp_reduce.cu", "sp_isph.cu", "sp_program.cu", "sp_slab.cu"]
+SOURCES = ["sp_system.cu", "sp_cells.cu", "sp_sweep.cu", "sp_reduce.cu", "sp_isph.cu", "sp_program.cu", "sp_slab.cu", "sp_generate.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 

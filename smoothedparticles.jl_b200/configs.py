@@ -39,6 +39,7 @@ class Case:
     program_fields: tuple = ()
     program_params: tuple = ()
     dim: int = 3
+    recipe: tuple = ()                    # ((grid, shape, {field: constant}), ...): the generate_particles! calls
 
     @property
     def n(self) -> int:
@@ -47,6 +48,16 @@ class Case:
     def make(self, system_cls, **kw):
         sys = system_cls(self.fields, self.domain, self.h, **kw)
         sys.add_particles(**self.init)
+        return sys
+
+    def make_on_device(self, system_cls, **kw):
+        """The same initial state built by the device generator (sp_generate_particles) instead of a host upload:
+        one generate_particles call per entry of ``recipe``, in the script's order."""
+        if not self.recipe:
+            raise ValueError(f"{self.name}: no device recipe")
+        sys = system_cls(self.fields, self.domain, self.h, **kw)
+        for grid, shape, constants in self.recipe:
+            sys.generate_particles(grid, shape, **constants)
         return sys
 
 
@@ -130,14 +141,14 @@ def collapse3d(dr: float = 5.0e-3, depth_scale: float = 1.0, z_range=None) -> Ca
     box = geo.Box(0.0, 0.0, 0.0, bw, bh, bd)
     fluid = geo.Box(0.0, 0.0, 0.0, wcw, wch, bd)
     walls = geo.BoundaryLayer(box, grid, wall_width)
-    walls = geo.Specification(walls, lambda X: X[:, 1] < bh)
+    walls = geo.Specification(walls, geo.HalfSpace(1, "<", bh))   # x -> (x[2] < box_height), :74-75
     domain = walls.boundarybox()
     if z_range is not None:
         zlo, zhi = z_range
         big = 1e30
         zslab = geo.Box(-big, -big, zlo, big, big, zhi)
-        fluid_g = geo.Specification(fluid * zslab, lambda X: X[:, 2] < zhi)
-        walls_g = geo.Specification(walls * zslab, lambda X: X[:, 2] < zhi)
+        fluid_g = geo.Specification(fluid * zslab, geo.HalfSpace(2, "<", zhi))
+        walls_g = geo.Specification(walls * zslab, geo.HalfSpace(2, "<", zhi))
     else:
         fluid_g, walls_g = fluid, walls
     xf = geo.covering(grid, fluid_g)
@@ -164,7 +175,8 @@ def collapse3d(dr: float = 5.0e-3, depth_scale: float = 1.0, z_range=None) -> Ca
     return Case("collapse3d", fields, domain, h, init, step,
                 consts=dict(dr=dr, h=h, rho0=rho0, m=m, c=c, mu=mu, nu=nu, dt=dt, g=g),
                 program=K["SP_PROGRAM_WCSPH_3D"], program_fields=("x", "v", "Dv", "rho", "Drho", "P", "type"),
-                program_params=(float(K["SP_KERNEL_WENDLAND3"]), m, h, 2 * nu, dt, c * c, rho0, mu, *g), dim=3)
+                program_params=(float(K["SP_KERNEL_WENDLAND3"]), m, h, 2 * nu, dt, c * c, rho0, mu, *g), dim=3,
+                recipe=((grid, fluid_g, {"rho": rho0, "type": 0.0}), (grid, walls_g, {"rho": rho0, "type": 1.0})))
 
 
 def collapse3d_dr_for(n_target: float) -> float:

@@ -23,7 +23,7 @@ import numpy as np
 
 __all__ = [
     "Box", "Rectangle", "Circle", "Ball", "BooleanUnion", "BooleanIntersection", "BooleanDifference",
-    "Specification", "BoundaryLayer", "Grid", "Squaregrid", "Hexagrid", "CubicGrid", "covering",
+    "Specification", "HalfSpace", "BoundaryLayer", "Grid", "Squaregrid", "Hexagrid", "CubicGrid", "covering",
     "generate_positions", "boundarybox",
 ]
 
@@ -170,6 +170,20 @@ class Specification(Shape):
         return self.s.boundarybox()
 
 
+@dataclass(frozen=True)
+class HalfSpace:
+    """A predicate for ``Specification`` that can also run on the device: ``x[axis] op bound`` with op one of
+    ``< <= > >=`` — the form of every Specification lambda in the reference's examples (e.g.
+    ``x -> (x[2] < box_height)``, collapse3d.jl:74-75, cavity_flow.jl:62-63)."""
+    axis: int
+    op: str
+    bound: float
+
+    def __call__(self, X):
+        v = X[:, self.axis]
+        return {"<": v < self.bound, "<=": v <= self.bound, ">": v > self.bound, ">=": v >= self.bound}[self.op]
+
+
 class Grid:
     dim = 0
 
@@ -309,3 +323,61 @@ class BoundaryLayer(Shape):
 def generate_positions(grid: Grid, geometry: Shape) -> np.ndarray:
     """Positions ``generate_particles!`` would push, in order (src/grids.jl:253-258)."""
     return covering(grid, geometry)
+
+
+# --------------------------------------------------------------------------- device generation (sp_generate.cu)
+def lattice_index_box(grid: Grid, s: Shape):
+    """(i0, i1, j0, j1, k0, k1), inclusive: the index ranges ``covering`` loops over (src/grids.jl:53-56, 76-79,
+    129-134)."""
+    box = s.boundarybox()
+    if isinstance(grid, Squaregrid):
+        return (_ifloor(box.x1_min / grid.dr), _iceil(box.x1_max / grid.dr), _ifloor(box.x2_min / grid.dr),
+                _iceil(box.x2_max / grid.dr), 0, 0)
+    if isinstance(grid, Hexagrid):
+        return (_ifloor(box.x1_min / grid.a) - 1, _iceil(box.x1_max / grid.a), _ifloor(box.x2_min / grid.b),
+                _iceil(box.x2_max / grid.b), 0, 0)
+    if isinstance(grid, CubicGrid):
+        return (_ifloor(box.x1_min / grid.dr), _iceil(box.x1_max / grid.dr), _ifloor(box.x2_min / grid.dr),
+                _iceil(box.x2_max / grid.dr), _ifloor(box.x3_min / grid.dr), _iceil(box.x3_max / grid.dr))
+    raise TypeError("unsupported grid")
+
+
+def compile_shape(s: Shape):
+    """Postfix program of the shape for ``sp_generate_particles``: a list of (kind, a, b, params) with children
+    before parents and the root last, plus the lattice offsets of the (single) BoundaryLayer if there is one."""
+    from . import abi
+    K = abi.K
+    nodes, offsets = [], [None]
+
+    def emit(kind, a=0, b=0, p=()):
+        nodes.append((K[kind], a, b, tuple(float(v) for v in p)))
+        return len(nodes) - 1
+
+    def walk(sh):
+        if isinstance(sh, Box):
+            return emit("SP_SHAPE_BOX", p=sh.lo + sh.hi)
+        if isinstance(sh, Circle):
+            return emit("SP_SHAPE_CIRCLE", p=(sh.x1, sh.x2, sh.r * sh.r))
+        if isinstance(sh, Ball):
+            return emit("SP_SHAPE_BALL", p=(sh.x1, sh.x2, sh.x3, sh.r * sh.r))
+        if isinstance(sh, (BooleanUnion, BooleanIntersection, BooleanDifference)):
+            a, b = walk(sh.s1), walk(sh.s2)
+            kind = {BooleanUnion: "SP_SHAPE_UNION", BooleanIntersection: "SP_SHAPE_INTERSECTION",
+                    BooleanDifference: "SP_SHAPE_DIFFERENCE"}[type(sh)]
+            return emit(kind, a, b)
+        if isinstance(sh, Specification):
+            if not isinstance(sh.f, HalfSpace):
+                raise TypeError("only HalfSpace predicates can run on the device (a Python lambda cannot)")
+            a = walk(sh.s)
+            b = emit("SP_SHAPE_HALFSPACE", sh.f.axis, {"<": 0, "<=": 1, ">": 2, ">=": 3}[sh.f.op], (sh.f.bound,))
+            return emit("SP_SHAPE_INTERSECTION", b, a)   # f(x) && is_inside(x, s), geometry.jl:183-185
+        if isinstance(sh, BoundaryLayer):
+            if offsets[0] is not None:
+                raise TypeError("one BoundaryLayer per shape on the device")
+            a = walk(sh.s)
+            offsets[0] = np.ascontiguousarray(sh.dxs, dtype=np.float64)
+            return emit("SP_SHAPE_BOUNDARY_LAYER", a)
+        raise TypeError(f"shape {type(sh).__name__} is not supported by the device generator")
+
+    walk(s)
+    return nodes, offsets[0]

@@ -112,6 +112,32 @@ class ParticleSystem:
                 full = add
             self.set(name, full)   # fields not given stay zero (sp_resize zero-fills the new tail)
 
+    def generate_particles(self, grid, shape, **constants) -> int:
+        """``generate_particles!(sys, grid, shape, constructor)`` on the device (src/grids.jl:253-258): the lattice
+        points of ``grid`` inside ``shape`` are appended in the reference's order with identical coordinates;
+        ``constants`` are the fields the constructor sets to a constant (e.g. ``type=1.0, rho=1000.0``), everything
+        else is zero.  Returns the number of particles added."""
+        from . import geometry as geo
+        nodes, offsets = geo.compile_shape(shape)
+        arr = (abi.ShapeNode * len(nodes))()
+        for k, (kind, a, b, p) in enumerate(nodes):
+            arr[k].kind, arr[k].a, arr[k].b = kind, a, b
+            for i, v in enumerate(p):
+                arr[k].p[i] = v
+        gk = {geo.Squaregrid: K["SP_GRID_SQUARE"], geo.Hexagrid: K["SP_GRID_HEXAGONAL"],
+              geo.CubicGrid: K["SP_GRID_CUBIC"]}[type(grid)]
+        irange = np.asarray(geo.lattice_index_box(grid, shape), dtype=np.int64)
+        names = [n for n in constants if n != "x"]
+        ff = np.asarray([self._fid[n] for n in names], dtype=np.int32) if names else np.zeros(1, dtype=np.int32)
+        fv = _farr([constants[n] for n in names]) if names else np.zeros(1)
+        n_off = 0 if offsets is None else len(offsets)
+        off = _farr(offsets).ravel() if n_off else np.zeros(3)
+        added = C.c_int64()
+        abi.check(self._lib.sp_generate_particles(self._h, gk, float(grid.dr), arr, len(nodes), abi.ptr_f64(off), n_off,
+                                                  abi.ptr_i64(irange), abi.ptr_i32(ff), abi.ptr_f64(fv), len(names),
+                                                  C.byref(added)), self._h)
+        return added.value
+
     def set(self, name: str, values):
         """Upload a field in reference order: shape (n,) or (n, ncomp)."""
         nc = self.fields[name]
