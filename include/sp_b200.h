@@ -134,8 +134,19 @@ enum {
        if type_p == 0: ker = m*rDw(h,r);
          a_p += (-ker*(P(rho_p)/rho_p^2 + P(rho_q)/rho_q^2))*x_pq;  a_p += (ker*2*mu/(rho_p*rho_q))*v_pq
        static_container.jl:106-114 (pressure: :68-70) */
-    SP_OP_MOVE_ALL = 32
+    SP_OP_MOVE_ALL = 32,
     /* unary. fields {x, v, a}; params {dtm}   x += dtm*v (every particle); a = 0   static_container.jl:116-119 */
+
+    /* surface tension by colour-field normals — examples/drop.jl (Wendland quintic 3-D only: uses DDwendland3) */
+    SP_OP_FIND_NORMAL = 33,
+    /* binary. fields {x, n}; params {kernel, coef, h}   n_p += (coef*rDw(h,r))*x_pq, coef = 2*vol*vol   drop.jl:76-78 */
+    SP_OP_NORMALIZE = 34,
+    /* unary. fields {n}; params {s0}   s = norm(n); n /= (s + s0)   drop.jl:84-87 */
+    SP_OP_INTERNAL_FORCE_TENSION = 35
+    /* binary. fields {x, v, P, n, a}; params {m, h, mu, rho0, beta, s0}   ker = m*rDwendland3(h,r);
+         a_p += (-ker*(P_p/rho0^2 + P_q/rho0^2))*x_pq;   a_p += (2*ker*mu/rho0^2)*v_pq;
+         a_p -= (2*beta/rho0^2)*(((m*DDwendland3(h,r) - ker)*dot(x_pq, n_pq))*x_pq/(r^2 + s0) + ker*n_pq)
+       drop.jl:101-113 */
 };
 
 /* sp_apply flags */
@@ -282,6 +293,11 @@ int32_t sp_get_neighbour_lists(sp_system* sys, int64_t* offsets /* n+1 */, int64
  * cells, dist, r > h, identity) runs once here; every following sp_apply of a binary operator replays the lists
  * until a position write, re-sort or resize invalidates them. */
 int32_t sp_build_neighbour_lists(sp_system* sys);
+/* Entries per target the cached lists currently hold (64 at first).  A build that meets a target with more neighbours
+ * sweeps that target with the exact candidate scan, reports its longest list, and the next build allocates
+ * 1.25 x that (multiple of 32, at most 512): dense kernels such as h = 3 dr in 3-D (~113 neighbours) reach the list
+ * path after the first step. */
+int32_t sp_neighbour_list_capacity(sp_system* sys, int32_t* capk);
 /* The neighbour lists the default pair sweeps actually replay (the per-position-version cache built by the first
  * sweep after positions change; built here if needed).  Same id SET per particle as sp_get_neighbour_lists; the
  * order is the default sweep's visiting order (stencil rows dk,dj outer, slots ascending), not the reference's. */

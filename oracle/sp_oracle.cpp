@@ -470,6 +470,46 @@ int apply_op(OSys& s, int op, const int32_t* F, int nf, const double* P, int np,
             });
             return SP_OK;
         }
+        case SP_OP_FIND_NORMAL: {  // drop.jl:76-78
+            if (!need(2, 3)) return SP_ERR_INVALID;
+            const int on = F[1];
+            kfn rDw = pick_rD((int)P[0]);
+            const double coef = P[1], h = P[2];
+            if (!rDw) return SP_ERR_INVALID;
+            apply_binary(s, [=](Particle& p, const Particle&, const double* xpq, double r) {
+                double k = coef * rDw(h, r);
+                for (int c = 0; c < 3; c++) p.f[on + c] += k * xpq[c];
+            });
+            if (self) apply_unary(s, [=](Particle& p) { for (int c = 0; c < 3; c++) p.f[on + c] += (coef * rDw(h, 0.0)) * 0.0; });
+            return SP_OK;
+        }
+        case SP_OP_NORMALIZE: {  // drop.jl:84-87
+            if (!need(1, 1)) return SP_ERR_INVALID;
+            const int on = F[0];
+            const double s0 = P[0];
+            apply_unary(s, [=](Particle& p) {
+                double sn = std::sqrt(dot3(&p.f[on], &p.f[on]));
+                for (int c = 0; c < 3; c++) p.f[on + c] /= (sn + s0);
+            });
+            return SP_OK;
+        }
+        case SP_OP_INTERNAL_FORCE_TENSION: {  // drop.jl:101-113
+            if (!need(5, 6)) return SP_ERR_INVALID;
+            const int ov = F[1], oP = F[2], on = F[3], oa = F[4];
+            const double m = P[0], h = P[1], mu = P[2], rho0 = P[3], beta = P[4], s0 = P[5];
+            apply_binary(s, [=](Particle& p, const Particle& q, const double* xpq, double r) {
+                double ker = m * rDwendland3(h, r);
+                double a = -ker * (p.f[oP] / (rho0 * rho0) + q.f[oP] / (rho0 * rho0));
+                for (int c = 0; c < 3; c++) p.f[oa + c] += a * xpq[c];
+                double b = 2 * ker * mu / (rho0 * rho0);
+                for (int c = 0; c < 3; c++) p.f[oa + c] += b * (p.f[ov + c] - q.f[ov + c]);
+                double npq[3] = {p.f[on] - q.f[on], p.f[on + 1] - q.f[on + 1], p.f[on + 2] - q.f[on + 2]};
+                double w = (m * DDwendland3(h, r) - ker) * dot3(xpq, npq);
+                double t = 2 * beta / (rho0 * rho0);
+                for (int c = 0; c < 3; c++) p.f[oa + c] -= t * (w * xpq[c] / (r * r + s0) + ker * npq[c]);
+            });
+            return SP_OK;
+        }
         case SP_OP_MOVE_ALL: {  // static_container.jl:116-119
             if (!need(3, 1)) return SP_ERR_INVALID;
             const int ox = F[0], ov = F[1], oa = F[2];

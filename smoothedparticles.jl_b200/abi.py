@@ -73,6 +73,7 @@ SIGNATURES = {
     "sp_get_neighbour_lists": (_i32, [_p, _pi64, _pi64, _i64]),
     "sp_get_sweep_neighbour_lists": (_i32, [_p, _pi64, _pi64, _i64]),
     "sp_build_neighbour_lists": (_i32, [_p]),
+    "sp_neighbour_list_capacity": (_i32, [_p, _pi32]),
     "sp_generate_particles": (_i32, [_p, _i32, _f64, C.POINTER(ShapeNode), _i32, _pf64, _i32, _pi64, _pi32, _pf64, _i32,
                                      _pi64]),
     "sp_num_removed": (_i32, [_p, _pi64]),

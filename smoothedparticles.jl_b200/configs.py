@@ -294,6 +294,69 @@ def static_container(dr: float = 1.5e-3) -> Case:
                 consts=dict(dr=dr, h=h, rho0=rho0, m=m, c=c, mu=mu, dt=dt, g=g, water_depth=water_depth), dim=2)
 
 
+# --------------------------------------------------------------------------- drop.jl
+def drop(dr: float = 3.7e-5) -> Case:
+    """examples/drop.jl:18-71 (constants, make_system), :139-152 (verlet_step!), :168-175 (initialisation): a water
+    drop on a desk with colour-field surface tension.  h = 3 dr in 3-D: ~113 neighbours per particle."""
+    h = 3.0 * dr
+    rad = 1e-3
+    deskw = 0.9 * h
+    rho0 = 1000.0
+    m = rho0 * dr ** 3
+    mu = 0.1
+    beta = 72e-3
+    vol = dr ** 3
+    g = (0.0, 0.0, -9.8)
+    c = 10.0 * max(np.sqrt(beta / rho0 / dr), np.sqrt(4 * 9.8 * rad))
+    dt = 0.3 * dr / c
+    s0 = dr * dr / 100
+    grid = geo.CubicGrid(dr)
+    ball = geo.Ball(0.0, 0.0, rad + h, rad)
+    desk = geo.Box(-2 * rad, -2 * rad, -deskw, 2 * rad, 2 * rad, 0.0)
+    domain = geo.Box(-2 * rad, -2 * rad, -2 * deskw, 2 * rad, 2 * rad, 2.2 * rad)
+    xf, xs = geo.covering(grid, ball), geo.covering(grid, desk)
+    x = np.concatenate([xf, xs])
+    typ = np.concatenate([np.zeros(len(xf)), np.ones(len(xs))])
+    fields = {"v": 3, "a": 3, "P": 1, "rho": 1, "rho0": 1, "n": 3, "type": 1}
+    init = {"x": x, "type": typ}
+    o_rho = ops.density_sum("wendland3", m, h, out="rho")
+    o_rho0 = ops.density_sum("wendland3", m, h, out="rho0")
+    o_p = ops.pressure_from_rho(c)
+    o_n = ops.find_normal("wendland3", vol, h)
+    o_nn = ops.normalize(s0)
+    o_f = ops.internal_force_tension(m, h, mu, rho0, beta, s0)
+    o_ra, o_rr, o_rn = ops.fill("a", 0.0), ops.fill("rho", 0.0), ops.fill("n", 0.0)
+    o_mv = ops.advect(dt)                     # x += (type==FLUID)*dt*v: the desk never gains a velocity
+    o_ac = ops.accelerate(0.5 * dt, g, Dv="a")
+
+    def prologue(sys):  # :168-175
+        sys.create_cell_list()
+        sys.apply(o_rho0, self_=True)
+        sys.apply(o_rho, self_=True)
+        sys.apply(o_p)
+        sys.apply(o_n)
+        sys.apply(o_nn)
+        sys.apply(o_f)
+
+    def step(sys):  # :139-152
+        sys.apply(o_ac)
+        sys.apply(o_mv)
+        sys.create_cell_list()
+        sys.apply(o_rr)
+        sys.apply(o_rho, self_=True)
+        sys.apply(o_rn)
+        sys.apply(o_n, self_=True)
+        sys.apply(o_nn)
+        sys.apply(o_p)
+        sys.apply(o_ra)
+        sys.apply(o_f)
+        sys.apply(o_ac)
+
+    return Case("drop", fields, domain, h, init, step, prologue,
+                consts=dict(dr=dr, h=h, rho0=rho0, m=m, c=c, mu=mu, beta=beta, dt=dt, g=g, s0=s0, vol=vol), dim=3,
+                recipe=((grid, ball, {"type": 0.0}), (grid, desk, {"type": 1.0})))
+
+
 # --------------------------------------------------------------------------- collapse_dry_implicit.jl
 def collapse_dry_implicit(dr: float = 1.0e-2) -> Case:
     """examples/collapse_dry_implicit.jl:47-114 (constants, make_system) and :218-233 (loop).

@@ -88,6 +88,9 @@ struct sp_system {
     long long nbr_version = 0;     // x_version the lists were built for
     long long nbr_n = 0;
     int nbr_group = 0;             // lanes per target the list layout was written for
+    int nbr_capk = 64;             // list entries per target (multiple of 32; grows when a build reports more)
+    bool nbr_max_pending = false;  // a build's longest-list report is on its way to h_counters[40]
+    cudaEvent_t ev_nbr = nullptr;
     // what the last balance_of_mass sweep left in the scratch fields _kx/_kv (sp_ops.cuh: OpBalanceOfMassAux)
     struct {
         bool valid = false;
@@ -97,6 +100,7 @@ struct sp_system {
     } pair_aux;
     double* ell_val = nullptr;  // ISPH: Poisson-operator coefficients in the neighbour-list layout (sp_isph.cu)
     long long ell_cap = 0;
+    int ell_capk = 0;
     double* dscal = nullptr;    // CG scalars + dot partials (3*1024 + 16 doubles)
     double* h_scal = nullptr;   // pinned mirror of a few scalars
 

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256) k_cg_persistent(CgArgs a) {
 
 int sp_poisson_ell_build(sp_system* s, const int32_t* F, const double* Pm, double* aval, double* diag, int* d_overflow,
                          const int** ids_out, const int** cnt_out);
-int sp_nbr_capk();
+int sp_nbr_prepare(sp_system* s, int* capk);
 
 static int scratch_field(sp_system* s, const char* name, int32_t* fid) {
     int rc = sp_add_field(s, name, 1, fid);
@@ -154,9 +154,11 @@ static int cg_persistent(sp_system* s, const int32_t* F, const double* Pm, int32
                          double abstol, int64_t maxiter, int64_t* iters, double* resid, int* done) {
     *done = 0;
     const long long n = s->n;
-    const int capk = sp_nbr_capk();
+    int capk = 0;
+    int rc = sp_nbr_prepare(s, &capk);  // the lists (and their capacity) of the current positions
+    if (rc) return rc;
     const size_t need = (size_t)s->cap * capk * sizeof(double);
-    if (!s->ell_val || s->ell_cap != s->cap) {
+    if (!s->ell_val || s->ell_cap != s->cap || s->ell_capk != capk) {
         size_t free_b = 0, total_b = 0;
         SP_CUDA(s, cudaMemGetInfo(&free_b, &total_b));
         if (s->ell_val) SP_CUDA(s, sp_dfree(s, s->ell_val));
@@ -165,9 +167,10 @@ static int cg_persistent(sp_system* s, const int32_t* F, const double* Pm, int32
         if (need > free_b / 2) return SP_OK;  // too large: matrix-free path
         SP_CUDA(s, sp_dmalloc(&s->ell_val, need));
         s->ell_cap = s->cap;
+        s->ell_capk = capk;
     }
     int32_t fdiag;
-    int rc = sp_add_field(s, "_cg_diag", 1, &fdiag);
+    rc = sp_add_field(s, "_cg_diag", 1, &fdiag);
     if (rc) return rc;
     s->fields[fdiag].transient = true;
     int* d_flag = s->counters + 32;

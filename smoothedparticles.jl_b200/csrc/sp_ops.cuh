@@ -298,6 +298,81 @@ struct OpScInternalForce {
     }
 };
 
+// ---------------------------------------------------------------- examples/drop.jl
+// find_n!  :76-78
+template <class K>
+struct OpFindNormal {
+    static constexpr int NQ = 0;
+    struct Params {
+        const double* qp[1];
+        WV3 n;
+        double coef;  // 2*vol*vol
+        SpKC kc;
+    };
+    struct PS {};
+    struct Acc {
+        double x, y, z;
+    };
+    __device__ static __forceinline__ bool active(const Params&, int) { return true; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS&, Acc& a) {
+        a.x = P.n.x[i]; a.y = P.n.y[i]; a.z = P.n.z[i];
+    }
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS&, const Q&, double dx, double dy, double dz,
+                                                double r, Acc& a) {
+        double k = P.coef * K::rD(P.kc, r);
+        a.x += k * dx; a.y += k * dy; a.z += k * dz;
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}  // (p,p,0): x_pp = 0 adds nothing
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) {
+        P.n.x[i] = a.x; P.n.y[i] = a.y; P.n.z[i] = a.z;
+    }
+};
+
+// internal_force!  :101-113 (pressure with the constant rho0, viscosity, surface tension)
+template <class K>
+struct OpInternalForceTension {
+    static constexpr int NQ = 7;  // vx, vy, vz, P, nx, ny, nz
+    struct Params {
+        const double* qp[NQ];
+        WV3 a;
+        double m, mu, rho0sq, tens, s0;  // tens = 2*beta/rho0^2
+        SpKC kc;
+    };
+    struct PS {
+        double vx, vy, vz, P, nx, ny, nz;
+    };
+    struct Acc {
+        double x, y, z;
+    };
+    __device__ static __forceinline__ bool active(const Params&, int) { return true; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
+        p.vx = P.qp[0][i]; p.vy = P.qp[1][i]; p.vz = P.qp[2][i];
+        p.P = P.qp[3][i];
+        p.nx = P.qp[4][i]; p.ny = P.qp[5][i]; p.nz = P.qp[6][i];
+        a.x = P.a.x[i]; a.y = P.a.y[i]; a.z = P.a.z[i];
+    }
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, const Q& q, double dx, double dy,
+                                                double dz, double r, Acc& a) {
+        double ker = P.m * K::rD(P.kc, r);
+        double c = -ker * (p.P / P.rho0sq + q(3) / P.rho0sq);
+        a.x += c * dx; a.y += c * dy; a.z += c * dz;
+        double b = 2 * ker * P.mu / P.rho0sq;
+        a.x += b * (p.vx - q(0)); a.y += b * (p.vy - q(1)); a.z += b * (p.vz - q(2));
+        double nx = p.nx - q(4), ny = p.ny - q(5), nz = p.nz - q(6);
+        double w = (P.m * K::DD(P.kc, r) - ker) * (dx * nx + dy * ny + dz * nz);
+        double den = r * r + P.s0;
+        a.x -= P.tens * (w * dx / den + ker * nx);
+        a.y -= P.tens * (w * dy / den + ker * ny);
+        a.z -= P.tens * (w * dz / den + ker * nz);
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) {
+        P.a.x[i] = a.x; P.a.y[i] = a.y; P.a.z[i] = a.z;
+    }
+};
+
 // ---------------------------------------------------------------- tests/test_collision_2d.jl
 // find_rho! / find_rho0!  :63-69, used with self=true
 template <class K>
@@ -618,6 +693,18 @@ struct UMoveAll {
     __device__ static __forceinline__ void apply(const Params& P, int i) {
         P.x.x[i] += P.dtm * P.v.x[i]; P.x.y[i] += P.dtm * P.v.y[i]; P.x.z[i] += P.dtm * P.v.z[i];
         P.a.x[i] = 0.0; P.a.y[i] = 0.0; P.a.z[i] = 0.0;
+    }
+};
+// normalize_n!  drop.jl:84-87
+struct UNormalize {
+    struct Params {
+        WV3 n;
+        double s0;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        const double a = P.n.x[i], b = P.n.y[i], c = P.n.z[i];
+        const double s = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(c, c))) + P.s0;
+        P.n.x[i] = a / s; P.n.y[i] = b / s; P.n.z[i] = c / s;
     }
 };
 // find_pressure!  test_collision_2d.jl:71-73

@@ -23,6 +23,7 @@ struct SweepCtx {
     const int* cell_start;
     float thr;                  // pre-filter threshold on the FP32 squared distance in cell units: above = not a neighbour
     float thr_lo;               // at or below = certainly a neighbour (k_nbr_build)
+    int capk;                   // entries per target in the cached neighbour lists (multiple of 32)
     int n;
 };
 
@@ -544,14 +545,16 @@ __global__ void __launch_bounds__(128, 4) k_sweep_mask(SpGrid g, SweepCtx c, typ
 //                                                 by the exact candidate scan instead, nothing is dropped)
 // k_sweep_list<Op> then runs only the pair bodies: no candidate loop, no predicate, ~88 % active lanes.
 // The cache is keyed on sp_system::x_version, which every position write / re-sort / resize bumps.
-#define SP_NBR_CAPK 64
+#define SP_NBR_CAPK_DEFAULT 64 /* grows by itself when a build reports longer lists (3-D runs with h = 3 dr: ~113) */
+#define SP_NBR_CAPK_MAX 512
 
 // The FP32 distance (cell units) classifies a candidate three ways — the rounding bound delta of the pre-filter is
 // symmetric (see launch_sweep): dd <= 1 - delta is certainly a neighbour, dd > 1 + delta certainly is not, and only
 // the thin shell in between (~0.1 % of the candidates) needs the exact FP64 predicate.  So the build kernel reads
 // FP64 positions only for those few.
 template <int G>
-__global__ void __launch_bounds__(128, 5) k_nbr_build(SpGrid g, SweepCtx c, int* __restrict__ cnt, int* __restrict__ ids) {
+__global__ void __launch_bounds__(128, 5) k_nbr_build(SpGrid g, SweepCtx c, int* __restrict__ cnt, int* __restrict__ ids,
+                                                      int* __restrict__ max_cnt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.n) return;
     const float ui = c.ux[i], vi = c.uy[i], wi = c.uz[i];
@@ -564,7 +567,8 @@ __global__ void __launch_bounds__(128, 5) k_nbr_build(SpGrid g, SweepCtx c, int*
     asm("mov.b64 %0, {%1,%1};" : "=l"(thr_lo2) : "f"(c.thr_lo));
     // entry k of target i lives at ((i / TPW) * (CAPK / G) + k / G) * 32 + (i % TPW) * G + k % G, TPW = 32 / G
     const int TPW = 32 / G;
-    int* col = ids + ((size_t)(i / TPW) * (SP_NBR_CAPK / G) << 5) + (i % TPW) * G;
+    const int capk = c.capk;
+    int* col = ids + ((size_t)(i / TPW) * (capk / G) << 5) + (i % TPW) * G;
     int n_out = 0;
     unsigned m0 = 0u, m1 = 0u, m2 = 0u;  // pending chunks: candidates that may be neighbours (newest in m0)
     unsigned s0 = 0u, s1 = 0u, s2 = 0u;  // ... of which certainly neighbours
@@ -587,7 +591,7 @@ __global__ void __launch_bounds__(128, 5) k_nbr_build(SpGrid g, SweepCtx c, int*
         while (m) {
             const int j = base + __ffs(m) - 1;
             m &= m - 1;
-            if (n_out < SP_NBR_CAPK) col[((n_out / G) << 5) + (n_out % G)] = j;
+            if (n_out < capk) col[((n_out / G) << 5) + (n_out % G)] = j;
             n_out++;
         }
     };
@@ -669,6 +673,7 @@ __global__ void __launch_bounds__(128, 5) k_nbr_build(SpGrid g, SweepCtx c, int*
         drain();
     }
     cnt[i] = n_out;
+    if (n_out > capk) atomicMax(max_cnt, n_out);  // rare: lets the host grow the lists for the next build
 }
 
 // Replay: G adjacent lanes share one target and take every G-th entry of its list, so a warp covers 32/G
@@ -696,9 +701,9 @@ __global__ void __launch_bounds__(128, 6) k_sweep_list(SpGrid g, SweepCtx c, con
         for (int a = 0; a < NACC; a++) av[a] = 0.0;
     }
     const int n_nb = cnt[i];
-    if (n_nb <= SP_NBR_CAPK) {
+    if (n_nb <= c.capk) {
         constexpr int TPW = 32 / G;  // targets per warp tile
-        const int* col = ids + ((size_t)(i / TPW) * (SP_NBR_CAPK / G) << 5) + (i % TPW) * G + sub;
+        const int* col = ids + ((size_t)(i / TPW) * (c.capk / G) << 5) + (i % TPW) * G + sub;
         const int n_it = (n_nb - sub + G - 1) / G;  // entries sub, sub+G, ...
         // U pairs per trip: all their loads (ids first, then the gathers) are issued before the first pair body, so
         // each warp keeps U*(3+NQ) gathers in flight — the kernel is bound by the latency / L1 cost of these loads
@@ -984,8 +989,8 @@ __global__ void __launch_bounds__(128, 6) k_sweep_list_pk(SpGrid g, SweepCtx c, 
     typename Op::PS p;
     typename Op::Acc acc;
     Op::load(P, i, xi, yi, zi, p, acc);
-    const int n_nb = min(cnt[i], SP_NBR_CAPK);
-    const int* col = ids + ((size_t)(i >> 5) * SP_NBR_CAPK << 5) + (i & 31);
+    const int n_nb = min(cnt[i], c.capk);
+    const int* col = ids + ((size_t)(i >> 5) * c.capk << 5) + (i & 31);
 #pragma unroll 2
     for (int k = 0; k < n_nb; k++) {
         const int j = __ldcs(col + (k << 5));
@@ -1147,6 +1152,7 @@ static void sp_sweep_ctx(sp_system* s, SweepCtx& c) {
     c.ux = c.uy = c.uz = nullptr;
     c.cell_start = s->cell_start;
     c.thr = c.thr_lo = 0.f;
+    c.capk = s->nbr_capk;
     c.n = (int)s->n;
 }
 
@@ -1188,17 +1194,39 @@ static int sp_ensure_prefilter(sp_system* s, SweepCtx& c) {
 static int sp_ensure_nbr_cache(sp_system* s, SweepCtx& c) {
     int rc = sp_ensure_prefilter(s, c);
     if (rc) return rc;
+    const bool rebuild = s->nbr_version != s->x_version || s->nbr_n != s->n || !s->nbr_ids || s->nbr_cap != s->cap;
+    if (rebuild && s->nbr_max_pending && cudaEventQuery(s->ev_nbr) == cudaSuccess) {
+        // the previous build met targets with more neighbours than the lists hold (they were swept by the exact scan):
+        // give the lists room before building them again
+        s->nbr_max_pending = false;
+        const int mx = s->h_counters[40];
+        if (mx > s->nbr_capk && s->nbr_capk < SP_NBR_CAPK_MAX) {
+            int want = std::min(SP_NBR_CAPK_MAX, ((mx + mx / 4) + 31) & ~31);
+            size_t free_b = 0, total_b = 0;
+            SP_CUDA(s, cudaMemGetInfo(&free_b, &total_b));
+            if ((size_t)s->cap * want * sizeof(int) < free_b / 4) {
+                s->nbr_capk = want;
+                if (s->nbr_ids) SP_CUDA(s, sp_dfree(s, s->nbr_ids));
+                s->nbr_ids = nullptr;
+            }
+        }
+    }
     if (!s->nbr_ids || s->nbr_cap != s->cap) {
         if (s->nbr_ids) SP_CUDA(s, sp_dfree(s, s->nbr_ids));
         if (s->nbr_cnt) SP_CUDA(s, sp_dfree(s, s->nbr_cnt));
         s->nbr_ids = s->nbr_cnt = nullptr;
-        SP_CUDA(s, sp_dmalloc(&s->nbr_ids, (size_t)s->cap * SP_NBR_CAPK * sizeof(int)));
+        SP_CUDA(s, sp_dmalloc(&s->nbr_ids, (size_t)s->cap * s->nbr_capk * sizeof(int)));
         SP_CUDA(s, sp_dmalloc(&s->nbr_cnt, (size_t)s->cap * sizeof(int)));
         s->nbr_cap = s->cap;
         s->nbr_version = 0;
     }
+    c.capk = s->nbr_capk;
     if (s->nbr_version != s->x_version || s->nbr_n != s->n) {
-        SP_LAUNCH(s, k_nbr_build<1>, sp_blocks(s->n, 128), 128, 0, s->g, c, s->nbr_cnt, s->nbr_ids);
+        SP_CUDA(s, cudaMemsetAsync(s->counters + 40, 0, sizeof(int), s->stream));
+        SP_LAUNCH(s, k_nbr_build<1>, sp_blocks(s->n, 128), 128, 0, s->g, c, s->nbr_cnt, s->nbr_ids, s->counters + 40);
+        SP_CUDA(s, cudaMemcpyAsync(s->h_counters + 40, s->counters + 40, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        SP_CUDA(s, cudaEventRecord(s->ev_nbr, s->stream));
+        s->nbr_max_pending = true;
         s->nbr_version = s->x_version;
         s->nbr_n = s->n;
     }
@@ -1627,6 +1655,38 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
                 P.two_mu = 2 * Pm[3];
             });
         }
+        case SP_OP_FIND_NORMAL: {
+            NEED(2, 3, 3, 3);
+            NEED_CELLS();
+            sp_wrote(s, F[1]);
+            return dispatch_kernel<OpFindNormal>(s, (int)Pm[0], Pm[2], flags, [&](auto& P) {
+                P.qp[0] = nullptr;
+                P.n = wv3(s, F[1]);
+                P.coef = Pm[1];
+            });
+        }
+        case SP_OP_NORMALIZE: {
+            NEED(1, 1, 3);
+            sp_wrote(s, F[0]);
+            UNormalize::Params P{wv3(s, F[0]), Pm[0]};
+            return launch_unary<UNormalize>(s, P);
+        }
+        case SP_OP_INTERNAL_FORCE_TENSION: {
+            NEED(5, 6, 3, 3, 1, 3, 3);
+            NEED_CELLS();
+            sp_wrote(s, F[4]);
+            return dispatch_kernel<OpInternalForceTension>(s, SP_KERNEL_WENDLAND3, Pm[1], flags, [&](auto& P) {
+                set_v3(s, F[1], P.qp);
+                P.qp[3] = sc(s, F[2]);
+                set_v3(s, F[3], P.qp + 4);
+                P.a = wv3(s, F[4]);
+                P.m = Pm[0];
+                P.mu = Pm[2];
+                P.rho0sq = Pm[3] * Pm[3];
+                P.tens = 2 * Pm[4] / (Pm[3] * Pm[3]);
+                P.s0 = Pm[5];
+            });
+        }
         case SP_OP_MOVE_ALL: {
             NEED(3, 1, 3, 3, 3);
             sp_wrote(s, F[0]);
@@ -1654,12 +1714,12 @@ __global__ void __launch_bounds__(128) k_poisson_coeffs(SweepCtx c, const int* _
     if (type[i] == 0.0) Aii += C_free * fmax(lambda[i], 0.0);
     diag[i] = Aii;
     const int n_nb = cnt[i];
-    if (n_nb > SP_NBR_CAPK) {
+    if (n_nb > c.capk) {
         *overflow = 1;  // the caller falls back to the matrix-free operator
         return;
     }
     const double xi = c.x[i], yi = c.y[i], zi = c.z[i];
-    const size_t base = ((size_t)(i >> 5) * SP_NBR_CAPK << 5) + (i & 31);
+    const size_t base = ((size_t)(i >> 5) * c.capk << 5) + (i & 31);
     for (int k = 0; k < n_nb; k++) {
         const int j = ids[base + ((size_t)k << 5)];
         const double dx = __dsub_rn(xi, c.x[j]), dy = __dsub_rn(yi, c.y[j]), dz = __dsub_rn(zi, c.z[j]);
@@ -1667,7 +1727,7 @@ __global__ void __launch_bounds__(128) k_poisson_coeffs(SweepCtx c, const int* _
     }
 }
 
-// fields {x, L, lambda, type}; params {kernel, m, h, rho, C_free}; aval: cap*SP_NBR_CAPK doubles, diag: n doubles
+// fields {x, L, lambda, type}; params {kernel, m, h, rho, C_free}; aval: cap*capk doubles, diag: n doubles
 int sp_poisson_ell_build(sp_system* s, const int32_t* F, const double* Pm, double* aval, double* diag, int* d_overflow,
                          const int** ids_out, const int** cnt_out) {
     SweepCtx c;
@@ -1699,7 +1759,15 @@ int sp_poisson_ell_build(sp_system* s, const int32_t* F, const double* Pm, doubl
     *cnt_out = s->nbr_cnt;
     return SP_OK;
 }
-int sp_nbr_capk() { return SP_NBR_CAPK; }
+// settle the cached lists (and their capacity) for the current positions; returns the capacity per target
+int sp_nbr_prepare(sp_system* s, int* capk) {
+    SweepCtx c;
+    sp_sweep_ctx(s, c);
+    int rc = sp_ensure_nbr_cache(s, c);
+    if (rc) return rc;
+    *capk = s->nbr_capk;
+    return SP_OK;
+}
 
 // fused unary passes of the step programs (sp_program.cu)
 // fields {v, Dv, x, type}; params {hdt, gx, gy, gz, dt_move}
@@ -1777,8 +1845,8 @@ __global__ void k_cache_fill(SpGrid g, SweepCtx c, const int* cnt, const int* li
     if (i >= c.n) return;
     long long o = offsets[ref[i]];
     const int n_nb = cnt[i];
-    if (n_nb <= SP_NBR_CAPK) {
-        const int* col = lists + ((size_t)(i >> 5) * SP_NBR_CAPK << 5) + (i & 31);
+    if (n_nb <= c.capk) {
+        const int* col = lists + ((size_t)(i >> 5) * c.capk << 5) + (i & 31);
         for (int k = 0; k < n_nb; k++) ids[o++] = (long long)ref[col[k << 5]] + 1;
     } else {
         sp_for_candidates<false>(g, c, c.x[i], c.y[i], c.z[i], [&](int j, double, double, double, double d2) {
@@ -1839,6 +1907,12 @@ int32_t sp_build_neighbour_lists(sp_system* s) {
         if ((rc = sp_ensure_nbr_cache(s, c))) return rc;
     }
     return sp_time_end(s);
+}
+
+int32_t sp_neighbour_list_capacity(sp_system* s, int32_t* capk) {
+    if (!s || !capk) return SP_ERR_INVALID;
+    *capk = s->nbr_capk;
+    return SP_OK;
 }
 
 int32_t sp_get_sweep_neighbour_lists(sp_system* s, int64_t* offsets, int64_t* ids, int64_t ids_cap) {

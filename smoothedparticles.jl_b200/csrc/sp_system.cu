@@ -287,6 +287,7 @@ int32_t sp_create(sp_system** out, const double lo[3], const double hi[3], doubl
     CREATE_TRY(cudaEventCreate(&s->tev0));
     CREATE_TRY(cudaEventCreate(&s->tev1));
     CREATE_TRY(cudaEventCreateWithFlags(&s->ev_count, cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&s->ev_nbr, cudaEventDisableTiming));
     CREATE_TRY(sp_dmalloc(&s->cell_start, (size_t)(g.key_max + 3) * sizeof(int)));
     CREATE_TRY(sp_dmalloc(&s->cell_fill, (size_t)(g.key_max + 3) * sizeof(int)));
     CREATE_TRY(cudaMemset(s->cell_start, 0, (size_t)(g.key_max + 3) * sizeof(int)));
@@ -338,6 +339,7 @@ int32_t sp_destroy(sp_system* s) {
     if (s->tev0) cudaEventDestroy(s->tev0);
     if (s->tev1) cudaEventDestroy(s->tev1);
     if (s->ev_count) cudaEventDestroy(s->ev_count);
+    if (s->ev_nbr) cudaEventDestroy(s->ev_nbr);
     if (s->stream) cudaStreamDestroy(s->stream);
     cudaGetLastError();
     delete s;

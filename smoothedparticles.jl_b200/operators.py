@@ -89,6 +89,23 @@ def kick(hdt, v="v", a="a"):
     return Operator(K["SP_OP_KICK"], (v, a), (hdt,), False, "accelerate! (collision)")
 
 
+# ---- examples/drop.jl
+def find_normal(kernel, vol, h, x="x", n="n"):
+    """drop.jl:76-78: n_p += 2*vol*vol*rDw(h,r)*x_pq."""
+    return Operator(K["SP_OP_FIND_NORMAL"], (x, n), (_kid(kernel), 2 * vol * vol, h), True, "find_n!")
+
+
+def normalize(s0, n="n"):
+    """drop.jl:84-87."""
+    return Operator(K["SP_OP_NORMALIZE"], (n,), (s0,), False, "normalize_n!")
+
+
+def internal_force_tension(m, h, mu, rho0, beta, s0, x="x", v="v", P="P", n="n", a="a"):
+    """drop.jl:101-113 (rDwendland3 / DDwendland3)."""
+    return Operator(K["SP_OP_INTERNAL_FORCE_TENSION"], (x, v, P, n, a), (m, h, mu, rho0, beta, s0), True,
+                    "internal_force! (surface tension)")
+
+
 # ---- examples/static_container.jl
 def sc_balance_of_mass(kernel, m, h, dt, x="x", v="v", rho="rho"):
     """static_container.jl:102-104: the density is integrated inside the pair loop."""

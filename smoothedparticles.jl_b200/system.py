@@ -259,6 +259,12 @@ class ParticleSystem:
         """Build the cached neighbour lists now (optional: the first binary apply() after a move does it lazily)."""
         abi.check(self._lib.sp_build_neighbour_lists(self._h), self._h)
 
+    @property
+    def neighbour_list_capacity(self) -> int:
+        k = C.c_int32()
+        abi.check(self._lib.sp_neighbour_list_capacity(self._h, C.byref(k)), self._h)
+        return k.value
+
     def sweep_neighbour_lists(self):
         """The cached lists the default pair sweeps replay (same sets as neighbour_lists(), sweep visiting order)."""
         n = len(self)

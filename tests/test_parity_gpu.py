@@ -128,6 +128,39 @@ def test_cached_sweep_lists_overflow_cluster():
     assert np.array_equal(_sorted_segments(od, idd), _sorted_segments(oo, ido))
 
 
+def test_list_capacity_grows_for_dense_kernels():
+    # 3-D with h = 3 dr (~113 neighbours, examples/drop.jl): the first build overflows the default 64 entries per
+    # target (those targets are swept by the exact scan), reports its longest list, and the next build has room.
+    rng = np.random.default_rng(21)
+    n1 = 14
+    I, J, Kk = np.meshgrid(np.arange(n1), np.arange(n1), np.arange(n1), indexing="ij")
+    x = np.stack([I.ravel(), J.ravel(), Kk.ravel()], 1) * 1.0 + rng.uniform(-0.1, 0.1, size=(n1 ** 3, 3))
+    h = 3.0
+    dom = geo.Box(-h, -h, -h, n1 + h, n1 + h, n1 + h)
+    m = 1.0
+    ora = OracleSystem({"rho": 1}, dom, h)
+    ora.add_particles(x=x)
+    ora.create_cell_list()
+    ora.apply(ops.density_sum("wendland3", m, h), self_=True)
+    oo, ido = ora.neighbour_lists()
+    assert np.max(np.diff(oo)) > 100
+    dev = ParticleSystem({"rho": 1}, dom, h)
+    dev.add_particles(x=x)
+    for attempt in range(3):            # 0: overflow path, 1+: grown lists
+        dev.set("x", x)                 # bumps the position version: the lists are rebuilt
+        dev.set("rho", np.zeros(len(x)))
+        dev.create_cell_list()
+        dev.apply(ops.density_sum("wendland3", m, h), self_=True)
+        assert_fields_close(dev, ora, ["rho"], what=f"dense kernel, build {attempt}")
+        od, idd = dev.sweep_neighbour_lists()
+        assert np.array_equal(od, oo)
+        assert np.array_equal(_sorted_segments(od, idd), _sorted_segments(oo, ido))
+        if attempt == 0:
+            assert dev.neighbour_list_capacity == 64
+            dev.synchronize()           # the longest-list report of build 0 has arrived
+    assert dev.neighbour_list_capacity >= int(np.max(np.diff(oo)))
+
+
 def test_removal_order_and_nan_positions():
     rng = np.random.default_rng(11)
     dom = geo.Box(0.0, 0.0, 0.0, 1.0, 1.0, 1.0)
@@ -363,6 +396,23 @@ def test_static_container_operators_and_time_loop():
                         floors={"v": 1e-3, "a": 1.0})
     # hydrostatic equilibrium: velocities stay far below the sound speed / the free-fall speed over the run
     assert np.max(np.abs(dev.get("v"))) < 1e-2 * c["c"]
+
+
+def test_drop_surface_tension_operators_and_time_loop():
+    # examples/drop.jl at a coarser spacing: colour-field normals, normalisation, pressure + viscosity + surface
+    # tension force with DDwendland3; h = 3 dr in 3-D, so the lists start in overflow and grow after the first build
+    case = configs.drop(dr=1.2e-4)
+    dev, ora = _pair(case)
+    case.prologue(dev)
+    case.prologue(ora)
+    _check_cells(dev, ora)
+    assert_fields_close(dev, ora, ["rho0", "rho", "P", "n", "a"], what="drop prologue", floors={"P": 1e-6})
+    for _ in range(6):
+        case.step(dev)
+        case.step(ora)
+    assert len(dev) == len(ora)
+    assert_fields_close(dev, ora, ["x", "v", "rho", "n", "a"], rtol=1e-9, what="drop 6 steps")
+    assert dev.neighbour_list_capacity > 64
 
 
 def test_collision_2d_reference_assertions_on_device():
