@@ -41,7 +41,7 @@ def steps(maker, name, nsteps, sub, **kw):
     s.create_cell_list()
     idx = np.arange(0, len(s), sub)
     off, ids = s.neighbour_lists()
-    out = {"n": len(s), "nsteps": nsteps, "idx": idx, "keys": s.cell_keys()[idx], "nbr_count": np.diff(off)[idx],
+    out = {"n": len(s), "count": len(s), "nsteps": nsteps,   # "count" = "n" (a field of drop.jl is called n) "idx": idx, "keys": s.cell_keys()[idx], "nbr_count": np.diff(off)[idx],
            "nbr_checksum": np.array([int(ids[off[i]:off[i + 1]].sum()) for i in idx], dtype=np.int64)}
     for f in case.fields:
         out[f] = s.get(f)[idx]
@@ -55,5 +55,7 @@ if __name__ == "__main__":
     steps(configs.collapse3d, "collapse3d_3steps", 3, 61, dr=1.0e-2)
     steps(configs.cavity_flow, "cavity_flow_5steps", 5, 7)
     steps(configs.collision_2d, "collision_2d_20steps", 20, 3)
+    steps(configs.static_container, "static_container_5steps", 5, 9)
+    steps(configs.drop, "drop_3steps", 3, 11, dr=1.2e-4)
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -13,8 +13,10 @@ from oracle.oracle import OracleSystem
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 K = sp.K
 CASES = [("collapse_dry_5steps", configs.collapse_dry, {}), ("collapse3d_3steps", configs.collapse3d, {"dr": 1.0e-2}),
-         ("cavity_flow_5steps", configs.cavity_flow, {}), ("collision_2d_20steps", configs.collision_2d, {})]
-FLOORS = {"collision_2d_20steps": {"P": 4e5, "a": 1e3}}
+         ("cavity_flow_5steps", configs.cavity_flow, {}), ("collision_2d_20steps", configs.collision_2d, {}),
+         ("static_container_5steps", configs.static_container, {}), ("drop_3steps", configs.drop, {"dr": 1.2e-4})]
+FLOORS = {"collision_2d_20steps": {"P": 4e5, "a": 1e3}, "static_container_5steps": {"v": 1e-3, "a": 1.0},
+          "drop_3steps": {"P": 1e-3}}
 
 
 def _run(system_cls, maker, kw, nsteps):
@@ -28,7 +30,7 @@ def _run(system_cls, maker, kw, nsteps):
 
 def _compare(s, case, g, rtol, name, exact_cells):
     idx = g["idx"]
-    assert len(s) == int(g["n"])
+    assert len(s) == int(g["count"] if "count" in g.files else g["n"])
     for f in list(case.fields) + ["x"]:
         a, b = s.get(f)[idx], g[f]
         scale = max(np.max(np.abs(b)), FLOORS.get(name, {}).get(f, 0.0), 1e-300)
