@@ -41,7 +41,8 @@ def steps(maker, name, nsteps, sub, **kw):
     s.create_cell_list()
     idx = np.arange(0, len(s), sub)
     off, ids = s.neighbour_lists()
-    out = {"n": len(s), "count": len(s), "nsteps": nsteps,   # "count" = "n" (a field of drop.jl is called n) "idx": idx, "keys": s.cell_keys()[idx], "nbr_count": np.diff(off)[idx],
+    # "count" repeats "n": a field of drop.jl is itself called n and overwrites that key
+    out = {"n": len(s), "count": len(s), "nsteps": nsteps, "idx": idx, "keys": s.cell_keys()[idx], "nbr_count": np.diff(off)[idx],
            "nbr_checksum": np.array([int(ids[off[i]:off[i + 1]].sum()) for i in idx], dtype=np.int64)}
     for f in case.fields:
         out[f] = s.get(f)[idx]
