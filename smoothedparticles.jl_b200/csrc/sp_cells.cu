@@ -183,8 +183,16 @@ __global__ void k_permute(PlaneTable tab, const int* __restrict__ perm, const in
         ref_out[t] = ref_in[p];
         key_out[t] = key_in[p];
     }
-#pragma unroll 4
-    for (int c = 0; c < tab.count; c++) tab.out[c][t] = tab.in[c][p];
+    // 12 planes per trip: all gathers are issued before the first store (memory-level parallelism per thread)
+    for (int c0 = 0; c0 < tab.count; c0 += 12) {
+        double v[12];
+#pragma unroll
+        for (int u = 0; u < 12; u++)
+            if (c0 + u < tab.count) v[u] = tab.in[c0 + u][p];
+#pragma unroll
+        for (int u = 0; u < 12; u++)
+            if (c0 + u < tab.count) tab.out[c0 + u][t] = v[u];
+    }
 }
 
 int sp_permute_all(sp_system* s, long long n_keep) {
