@@ -142,11 +142,42 @@ enum {
     /* binary. fields {x, n}; params {kernel, coef, h}   n_p += (coef*rDw(h,r))*x_pq, coef = 2*vol*vol   drop.jl:76-78 */
     SP_OP_NORMALIZE = 34,
     /* unary. fields {n}; params {s0}   s = norm(n); n /= (s + s0)   drop.jl:84-87 */
-    SP_OP_INTERNAL_FORCE_TENSION = 35
+    SP_OP_INTERNAL_FORCE_TENSION = 35,
     /* binary. fields {x, v, P, n, a}; params {m, h, mu, rho0, beta, s0}   ker = m*rDwendland3(h,r);
          a_p += (-ker*(P_p/rho0^2 + P_q/rho0^2))*x_pq;   a_p += (2*ker*mu/rho0^2)*v_pq;
          a_p -= (2*beta/rho0^2)*(((m*DDwendland3(h,r) - ker)*dot(x_pq, n_pq))*x_pq/(r^2 + s0) + ker*n_pq)
        drop.jl:101-113 */
+
+    /* reversible (symplectic, fixed-point) WCSPH with Lennard-Jones walls — examples/collapse_symplectic.jl,
+       examples/Kepler_vortex.jl, examples/utils/FixPA.jl.
+       rev_add(a, b) = 2^-30 * (Int64(round(a*2^30)) + Int64(round(b*2^30)))   FixPA.jl:11-42 (round half to even) */
+    SP_OP_DENSITY_SUM_FLUID = 40,
+    /* binary, honours self. fields {x, out, type}; params {kernel, m, h}
+       if type_p == 0 && type_q == 0: out_p += m*w(h,r)
+       collapse_symplectic.jl:98-108, Kepler_vortex.jl:139-149 (find_rho!, find_rho0!) */
+    SP_OP_INTERNAL_FORCE_LJ = 41,
+    /* binary. fields {x, P, rho, a, type}; params {kernel, m, h, rho0, wall_type, dr_wall, E_wall, eps}
+       if type_p == 0 && type_q == 0:  a_p += (-(m*rDw(h,r))*(pr_p + pr_q))*x_pq
+            with pr = P/rho^2 when rho0 == 0 (collapse_symplectic.jl:114-117), pr = P/rho0^2 otherwise
+            (Kepler_vortex.jl:155-158)
+       else if type_p == 0 && type_q == wall_type && r < dr_wall:
+            s = dr_wall/(r + eps);  a_p += (-E_wall/(r + eps)^2*(s^2 - s^4))*x_pq
+       collapse_symplectic.jl:114-123, Kepler_vortex.jl:155-164 */
+    SP_OP_MOVE_REV = 42,
+    /* unary. fields {x, v, type}; params {dt}   if type == 0: x = rev_add(x, dt*v)
+       collapse_symplectic.jl:134-138, Kepler_vortex.jl:174-178 */
+    SP_OP_ACCELERATE_REV = 43,
+    /* unary. fields {v, a, type}; params {hdt, gx, gy, gz}   if type == 0: v = rev_add(v, hdt*(a + g))
+       collapse_symplectic.jl:140-144 */
+    SP_OP_ACCELERATE_REV_CENTRAL = 44,
+    /* unary. fields {x, v, a, type}; params {hdt, GM}
+       if type == 0: v = rev_add(v, hdt*rev_add(a, (-GM/norm(x)^3)*x))   Kepler_vortex.jl:180-184 */
+    SP_OP_LJ_POTENTIAL = 45
+    /* binary (the per-particle sum(sys, LJ_potential, p), core.jl:271-291). fields {x, out, type};
+       params {h, coef, wall_type, dr_wall, eps}
+       if type_q == wall_type && type_p == 0 && r < dr_wall: s = dr_wall/(r + eps);
+            out_p += coef*(0.5*s^2 - 0.25*s^4 - 0.25),  coef = m*E_wall
+       collapse_symplectic.jl:146-153, Kepler_vortex.jl:186-193 */
 };
 
 /* sp_apply flags */

@@ -350,6 +350,20 @@ kfn pick_w(int kernel) {
 
 inline double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }  // algebra.jl:49-51
 
+// ---- examples/utils/FixPA.jl:11-42: reversible fixed-point addition.  FixPA_eps = 1/2^30, so x/FixPA_eps is the
+// exact product x*2^30; Julia's round() is round-half-to-even (nearbyint in the default rounding mode).
+inline int64_t fixpa_nom(double x) { return (int64_t)std::nearbyint(x / (1.0 / 1073741824.0)); }  // :19-21
+inline double rev_add(double x, double y) { return (1.0 / 1073741824.0) * (double)(fixpa_nom(x) + fixpa_nom(y)); }  // :28-30
+// s^4 with an integer literal exponent is Base.pow_body(x, 4) (Julia >= 1.8: power by squaring with the low parts
+// of the two squarings carried along); written out for n = 4.  Older Julia: (s*s)*(s*s), at most 1 ulp away.
+inline double julia_pow4(double x) {
+    double x2 = x * x, lo2 = std::fma(x, x, -x2);
+    double err = x2 * 2 * lo2;
+    double x4 = x2 * x2, lo4 = std::fma(x2, x2, -x4);
+    lo4 += err;
+    return (std::isfinite(x4) && std::isfinite(lo4)) ? x4 + lo4 : x4;
+}
+
 // apply!, core.jl:151-161, specialised to the registered operators (the example closures).
 int apply_op(OSys& s, int op, const int32_t* F, int nf, const double* P, int np, int flags) {
     auto need = [&](int f, int p) { return nf == f && np == p; };
@@ -517,6 +531,89 @@ int apply_op(OSys& s, int op, const int32_t* F, int nf, const double* P, int np,
             apply_unary(s, [=](Particle& p) {
                 for (int c = 0; c < 3; c++) p.f[ox + c] += dtm * p.f[ov + c];
                 p.f[oa] = p.f[oa + 1] = p.f[oa + 2] = 0.0;
+            });
+            return SP_OK;
+        }
+        case SP_OP_DENSITY_SUM_FLUID: {  // collapse_symplectic.jl:98-108, Kepler_vortex.jl:139-149
+            if (!need(3, 3)) return SP_ERR_INVALID;
+            const int oo = F[1], ot = F[2];
+            kfn w = pick_w((int)P[0]);
+            const double m = P[1], h = P[2];
+            if (!w) return SP_ERR_INVALID;
+            apply_binary(s, [=](Particle& p, const Particle& q, const double*, double r) {
+                if (p.f[ot] == 0.0 && q.f[ot] == 0.0) p.f[oo] += m * w(h, r);
+            });
+            if (self)  // action!(p, p, 0.0), core.jl:155-157
+                apply_unary(s, [=](Particle& p) {
+                    if (p.f[ot] == 0.0) p.f[oo] += m * w(h, 0.0);
+                });
+            return SP_OK;
+        }
+        case SP_OP_INTERNAL_FORCE_LJ: {  // collapse_symplectic.jl:114-123, Kepler_vortex.jl:155-164
+            if (!need(5, 8)) return SP_ERR_INVALID;
+            const int oP = F[1], orho = F[2], oa = F[3], ot = F[4];
+            kfn rDw = pick_rD((int)P[0]);
+            const double m = P[1], h = P[2], rho0 = P[3], wall = P[4], dr_wall = P[5], E_wall = P[6], eps = P[7];
+            if (!rDw) return SP_ERR_INVALID;
+            apply_binary(s, [=](Particle& p, const Particle& q, const double* xpq, double r) {
+                if (p.f[ot] == 0.0 && q.f[ot] == 0.0) {
+                    double ker = m * rDw(h, r);
+                    double a = (rho0 == 0.0)
+                                   ? -ker * (p.f[oP] / (p.f[orho] * p.f[orho]) + q.f[oP] / (q.f[orho] * q.f[orho]))
+                                   : -ker * (p.f[oP] / (rho0 * rho0) + q.f[oP] / (rho0 * rho0));
+                    for (int c = 0; c < 3; c++) p.f[oa + c] += a * xpq[c];
+                } else if (p.f[ot] == 0.0 && q.f[ot] == wall && r < dr_wall) {
+                    double s_ = dr_wall / (r + eps);
+                    double a = -E_wall / ((r + eps) * (r + eps)) * (s_ * s_ - julia_pow4(s_));
+                    for (int c = 0; c < 3; c++) p.f[oa + c] += a * xpq[c];
+                }
+            });
+            return SP_OK;
+        }
+        case SP_OP_MOVE_REV: {  // collapse_symplectic.jl:134-138, Kepler_vortex.jl:174-178
+            if (!need(3, 1)) return SP_ERR_INVALID;
+            const int ox = F[0], ov = F[1], ot = F[2];
+            const double dt = P[0];
+            apply_unary(s, [=](Particle& p) {
+                if (p.f[ot] == 0.0)
+                    for (int c = 0; c < 3; c++) p.f[ox + c] = rev_add(p.f[ox + c], dt * p.f[ov + c]);
+            });
+            return SP_OK;
+        }
+        case SP_OP_ACCELERATE_REV: {  // collapse_symplectic.jl:140-144
+            if (!need(3, 4)) return SP_ERR_INVALID;
+            const int ov = F[0], oa = F[1], ot = F[2];
+            const double hdt = P[0], g[3] = {P[1], P[2], P[3]};
+            apply_unary(s, [=](Particle& p) {
+                if (p.f[ot] == 0.0)
+                    for (int c = 0; c < 3; c++) p.f[ov + c] = rev_add(p.f[ov + c], hdt * (p.f[oa + c] + g[c]));
+            });
+            return SP_OK;
+        }
+        case SP_OP_ACCELERATE_REV_CENTRAL: {  // Kepler_vortex.jl:180-184
+            if (!need(4, 2)) return SP_ERR_INVALID;
+            const int ox = F[0], ov = F[1], oa = F[2], ot = F[3];
+            const double hdt = P[0], GM = P[1];
+            apply_unary(s, [=](Particle& p) {
+                if (p.f[ot] == 0.0) {
+                    double n = std::sqrt(dot3(p.f + ox, p.f + ox));  // norm, algebra.jl:58-60
+                    double k = -GM / (n * n * n);
+                    for (int c = 0; c < 3; c++)
+                        p.f[ov + c] = rev_add(p.f[ov + c], hdt * rev_add(p.f[oa + c], k * p.f[ox + c]));
+                }
+            });
+            return SP_OK;
+        }
+        case SP_OP_LJ_POTENTIAL: {  // sum(sys, LJ_potential, p): core.jl:271-291 with collapse_symplectic.jl:146-153
+            if (!need(3, 5)) return SP_ERR_INVALID;
+            const int oo = F[1], ot = F[2];
+            const double coef = P[1], wall = P[2], dr_wall = P[3], eps = P[4];
+            // sum() does not skip q === p; LJ_potential(p, p, 0) = 0 because p cannot be both fluid and wall
+            apply_binary(s, [=](Particle& p, const Particle& q, const double*, double r) {
+                if (q.f[ot] == wall && p.f[ot] == 0.0 && r < dr_wall) {
+                    double s_ = dr_wall / (r + eps);
+                    p.f[oo] += coef * (0.5 * (s_ * s_) - 0.25 * julia_pow4(s_) - 0.25);
+                }
             });
             return SP_OK;
         }

@@ -10,6 +10,10 @@ order as the script.  A Case is backend-agnostic: ``case.make(ParticleSystem)`` 
   cavity_flow            examples/cavity_flow.jl             2-D lid-driven cavity
   collapse_dry_implicit  examples/collapse_dry_implicit.jl   2-D ISPH, matrix-free pressure Poisson + CG
   collision_2d           tests/test_collision_2d.jl          two colliding discs (the reference's own test)
+  static_container       examples/static_container.jl        tank at rest, density integrated in the pair loop
+  drop                   examples/drop.jl                    3-D drop with colour-field surface tension
+  collapse_symplectic    examples/collapse_symplectic.jl     reversible fixed-point Verlet, Lennard-Jones walls
+  kepler_vortex          examples/Kepler_vortex.jl           fluid ring in central gravity, same integrator
   lattice_box            synthetic S1 block of SURVEY §8(d)  jittered cubic lattice, all fluid
 """
 from __future__ import annotations
@@ -355,6 +359,154 @@ def drop(dr: float = 3.7e-5) -> Case:
     return Case("drop", fields, domain, h, init, step, prologue,
                 consts=dict(dr=dr, h=h, rho0=rho0, m=m, c=c, mu=mu, beta=beta, dt=dt, g=g, s0=s0, vol=vol), dim=3,
                 recipe=((grid, ball, {"type": 0.0}), (grid, desk, {"type": 1.0})))
+
+
+# --------------------------------------------------------------------------- collapse_symplectic.jl
+def collapse_symplectic(dr: float = 1.0e-2) -> Case:
+    """examples/collapse_symplectic.jl:39-95 (constants, make_system), :171-181 (verlet_step!), :198-203 (init):
+    the dam break integrated with the reversible fixed-point Verlet scheme of utils/FixPA.jl; walls repel through
+    a Lennard-Jones force instead of carrying pressure."""
+    h = 3.0 * dr
+    rho0 = 1000.0
+    m = rho0 * dr ** 2
+    g = (0.0, -9.8, 0.0)  # -9.8*VECY
+    wcw, wch, bh, bw = 1.0, 2.0, 3.0, 4.0
+    wall_width = 2.5 * dr
+    c = 50.0
+    dr_wall = 0.95 * dr
+    E_wall = 10 * math.sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]) * wch  # 10*norm(g)*water_column_height
+    eps = 1e-16
+    dt = 0.1 * h / c
+    grid = geo.Squaregrid(dr)
+    box = geo.Rectangle(0.0, 0.0, bw, bh)
+    fluid = geo.Rectangle(0.0, 0.0, wcw, wch)
+    walls = geo.BoundaryLayer(box, grid, wall_width)
+    domain = geo.Rectangle(-bw, -bw, 2 * bw, 3 * bh)
+    xf, xw = geo.covering(grid, fluid), geo.covering(grid, walls)
+    x = np.concatenate([xf, xw])
+    typ = np.concatenate([np.zeros(len(xf)), np.ones(len(xw))])
+    fields = {"v": 3, "a": 3, "P": 1, "rho": 1, "rho0": 1, "type": 1, "U": 1}
+    init = {"x": x, "type": typ}
+    o_rho = ops.density_sum_fluid("wendland2", m, h, out="rho")
+    o_rho0 = ops.density_sum_fluid("wendland2", m, h, out="rho0")
+    o_p = ops.pressure_from_rho(c)
+    o_f = ops.internal_force_lj("wendland2", m, h, dr_wall, E_wall, eps)
+    o_ra = ops.fill("a", 0.0)
+    o_rr = ops.fill("rho", 0.0)
+    o_mv = ops.move_rev(dt)
+    o_ac = ops.accelerate_rev(0.5 * dt, g)
+
+    def prologue(sys):  # :198-203
+        sys.create_cell_list()
+        sys.apply(o_rho0, self_=True)
+        sys.apply(o_rho, self_=True)
+        sys.apply(o_p)
+        sys.apply(o_f)
+
+    def step(sys):  # verlet_step! :171-181
+        sys.apply(o_ac)
+        sys.apply(o_mv)
+        sys.create_cell_list()
+        sys.apply(o_rr)
+        sys.apply(o_rho, self_=True)
+        sys.apply(o_p)
+        sys.apply(o_ra)
+        sys.apply(o_f)
+        sys.apply(o_ac)
+
+    return Case("collapse_symplectic", fields, domain, h, init, step, prologue,
+                consts=dict(dr=dr, h=h, rho0=rho0, m=m, c=c, dt=dt, g=g, dr_wall=dr_wall, E_wall=E_wall, eps=eps),
+                dim=2, recipe=((grid, fluid, {"type": 0.0}), (grid, walls, {"type": 1.0})))
+
+
+# --------------------------------------------------------------------------- Kepler_vortex.jl
+def kepler_ring_radii(N_rings: int = 25, r0: float = 10.0):
+    """Kepler_vortex.jl:43-60,68: radii of the Gaussian rings, r_f(u) = inverse of the normalised cumulative
+    surface density f(r) = int_0^r 2 pi s exp(-30 (1 - s/r0)^2) ds / int_0^40 (...).  The script tabulates f at
+    0:0.5:25 with QuadGK (rtol 1e-3), interpolates the table with a cubic B-spline and inverts it with Roots.jl;
+    here: scipy quad, a natural cubic spline through the same table and brentq.  Set-up only (no Julia output to
+    compare with); the operators do not depend on it."""
+    from scipy.integrate import quad
+    from scipy.interpolate import CubicSpline
+    from scipy.optimize import brentq
+
+    def sigma(r):
+        return 2 * math.pi * r * math.exp(-30 * (1 - r / r0) ** 2)
+
+    den = quad(sigma, 0, 40, epsrel=1e-6)[0]
+    rs = np.arange(0.0, 25.0 + 1e-9, 0.5)
+    table = np.array([quad(sigma, 0, r, epsrel=1e-3)[0] / den for r in rs])
+    spline = CubicSpline(rs, table, bc_type="natural")
+
+    def r_f(F):
+        return brentq(lambda r: float(spline(r)) - F, 2.0, 20.0, xtol=1e-14)
+
+    us = 0.01 + (0.99 - 0.01) / N_rings * np.arange(N_rings + 1)  # 0.01:(0.99-0.01)/N_rings:0.99
+    return np.array([r_f(u) for u in us]), r_f(0.25 + 1 / N_rings) - r_f(0.25)
+
+
+def kepler_vortex(N_rings: int = 25) -> Case:
+    """examples/Kepler_vortex.jl:28-99 (constants), :109-134 (rings of particles on Keplerian orbits),
+    :220-230 (verlet_step!), :253-258 (init): a self-gravitating-free fluid ring around a central mass, integrated
+    with the reversible fixed-point scheme; no wall particles are generated (the LJ branch stays idle)."""
+    r0, GM = 10.0, 1000.0
+    radii, dr = kepler_ring_radii(N_rings, r0)
+    h = 3.0 * dr
+    rho0 = 1.0
+    m = rho0 * dr ** 2
+    bw = 4 * r0
+    c = 0.01
+    dr_wall = 0.95 * dr
+    E_wall = GM / r0
+    eps = 1e-16
+    dt = 0.0001 * h / c
+    xs, vs = [], []
+    dphi = radii[1] / radii[0] - 1.0  # :126
+    for i in range(len(radii) - 1):  # :127-131
+        r = radii[i]
+        vphi = math.sqrt(GM) / math.sqrt(r)  # vphi_r :35-37
+        phi = 0.0
+        while phi < 2 * math.pi + 0.0:  # generate_circle! :109-119
+            cx, sy = math.cos(phi), math.sin(phi)
+            xs.append((0.0 + r * cx, 0.0 + r * sy, 0.0))
+            vs.append((-vphi * sy, vphi * cx, 0.0))
+            phi += dphi
+        dphi = (radii[i + 1] - r) / r
+    x = np.array(xs)
+    v = np.array(vs)
+    domain = geo.Rectangle(-bw, -bw, bw, bw)
+    fields = {"v": 3, "a": 3, "P": 1, "rho": 1, "rho0": 1, "type": 1, "U": 1}
+    init = {"x": x, "v": v, "type": np.zeros(len(x))}
+    o_rho = ops.density_sum_fluid("wendland2", m, h, out="rho")
+    o_rho0 = ops.density_sum_fluid("wendland2", m, h, out="rho0")
+    o_p = ops.pressure_from_rho(c)
+    o_f = ops.internal_force_lj("wendland2", m, h, dr_wall, E_wall, eps, rho0=rho0)
+    o_ra = ops.fill("a", 0.0)
+    o_rr = ops.fill("rho", 0.0)
+    o_mv = ops.move_rev(dt)
+    o_ac = ops.accelerate_rev_central(0.5 * dt, GM)
+
+    def prologue(sys):  # :253-258
+        sys.create_cell_list()
+        sys.apply(o_rho0, self_=True)
+        sys.apply(o_rho, self_=True)
+        sys.apply(o_p)
+        sys.apply(o_f)
+
+    def step(sys):  # verlet_step! :220-230
+        sys.apply(o_ac)
+        sys.apply(o_mv)
+        sys.create_cell_list()
+        sys.apply(o_rr)
+        sys.apply(o_rho, self_=True)
+        sys.apply(o_p)
+        sys.apply(o_ra)
+        sys.apply(o_f)
+        sys.apply(o_ac)
+
+    return Case("kepler_vortex", fields, domain, h, init, step, prologue,
+                consts=dict(dr=dr, h=h, rho0=rho0, m=m, c=c, dt=dt, GM=GM, r0=r0, dr_wall=dr_wall, E_wall=E_wall,
+                            eps=eps), dim=2)
 
 
 # --------------------------------------------------------------------------- collapse_dry_implicit.jl

@@ -373,6 +373,123 @@ struct OpInternalForceTension {
     }
 };
 
+// ---------------------------------------------------------------- examples/collapse_symplectic.jl, Kepler_vortex.jl
+// s^4 as Julia evaluates an integer-literal power of a Float64 (Base.pow_body for n = 4: two squarings with their
+// low parts carried along); at most 1 ulp from (s*s)*(s*s)
+__device__ __forceinline__ double sp_julia_pow4(double x) {
+    const double x2 = __dmul_rn(x, x), lo2 = __fma_rn(x, x, -x2);
+    const double err = __dmul_rn(__dmul_rn(x2, 2.0), lo2);
+    const double x4 = __dmul_rn(x2, x2);
+    const double lo4 = __dadd_rn(__fma_rn(x2, x2, -x4), err);
+    return (isfinite(x4) && isfinite(lo4)) ? __dadd_rn(x4, lo4) : x4;
+}
+// rev_add  examples/utils/FixPA.jl:28-30: 2^-30 * (Int64(round(x*2^30)) + Int64(round(y*2^30))), round half to even
+__device__ __forceinline__ double sp_rev_add(double x, double y) {
+    const long long a = __double2ll_rn(__dmul_rn(x, 1073741824.0)), b = __double2ll_rn(__dmul_rn(y, 1073741824.0));
+    return __dmul_rn(__ll2double_rn(a + b), 1.0 / 1073741824.0);
+}
+
+// find_rho! / find_rho0!  collapse_symplectic.jl:98-108, Kepler_vortex.jl:139-149 (fluid-fluid pairs only; self=true)
+template <class K>
+struct OpDensitySumFluid {
+    static constexpr int NQ = 1;  // type
+    struct Params {
+        const double* qp[NQ];
+        double* out;
+        double m;
+        SpKC kc;
+    };
+    struct PS {};
+    struct Acc {
+        double d;
+    };
+    __device__ static __forceinline__ bool active(const Params& P, int i) { return P.qp[0][i] == 0.0; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS&, Acc& a) {
+        a.d = P.out[i];
+    }
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS&, const Q& q, double, double, double, double r,
+                                                Acc& a) {
+        if (q(0) == 0.0) a.d += P.m * K::w(P.kc, r);
+    }
+    // (p, p, 0.0): only active (fluid) particles get here
+    __device__ static __forceinline__ void self(const Params& P, const PS&, Acc& a) { a.d += P.m * K::w(P.kc, 0.0); }
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) { P.out[i] = a.d; }
+};
+
+// internal_force!  collapse_symplectic.jl:114-123, Kepler_vortex.jl:155-164: pressure between fluid particles,
+// Lennard-Jones repulsion from wall particles closer than dr_wall.  pr is the hoisted per-particle quotient
+// (P/rho^2 or P/rho0^2); it is 0/0 on wall particles of collapse_symplectic, where it is never used.
+template <class K>
+struct OpInternalForceLJ {
+    static constexpr int NQ = 2;  // pr, type
+    struct Params {
+        const double* qp[NQ];
+        WV3 a;
+        double m, wall, dr_wall, E_wall, eps;
+        SpKC kc;
+    };
+    struct PS {
+        double pr;
+    };
+    struct Acc {
+        double x, y, z;
+    };
+    __device__ static __forceinline__ bool active(const Params& P, int i) { return P.qp[1][i] == 0.0; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
+        p.pr = P.qp[0][i];
+        a.x = P.a.x[i]; a.y = P.a.y[i]; a.z = P.a.z[i];
+    }
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, const Q& q, double dx, double dy,
+                                                double dz, double r, Acc& a) {
+        const double tq = q(1);
+        if (tq == 0.0) {
+            const double c = -(P.m * K::rD(P.kc, r)) * (p.pr + q(0));
+            a.x += c * dx; a.y += c * dy; a.z += c * dz;
+        } else if (tq == P.wall && r < P.dr_wall) {
+            const double re = r + P.eps;
+            const double s = P.dr_wall / re;
+            const double c = -P.E_wall / (re * re) * (s * s - sp_julia_pow4(s));
+            a.x += c * dx; a.y += c * dy; a.z += c * dz;
+        }
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) {
+        P.a.x[i] = a.x; P.a.y[i] = a.y; P.a.z[i] = a.z;
+    }
+};
+
+// sum(sys, LJ_potential, p) for every p  (core.jl:271-291 with collapse_symplectic.jl:146-153, Kepler_vortex.jl:186-193)
+template <class K>
+struct OpLJPotential {
+    static constexpr int NQ = 1;  // type
+    struct Params {
+        const double* qp[NQ];
+        double* out;
+        double coef, wall, dr_wall, eps;
+        SpKC kc;
+    };
+    struct PS {};
+    struct Acc {
+        double d;
+    };
+    __device__ static __forceinline__ bool active(const Params& P, int i) { return P.qp[0][i] == 0.0; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS&, Acc& a) {
+        a.d = P.out[i];
+    }
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS&, const Q& q, double, double, double, double r,
+                                                Acc& a) {
+        if (q(0) == P.wall && r < P.dr_wall) {
+            const double s = P.dr_wall / (r + P.eps);
+            a.d += P.coef * (0.5 * (s * s) - 0.25 * sp_julia_pow4(s) - 0.25);
+        }
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) { P.out[i] = a.d; }
+};
+
 // ---------------------------------------------------------------- tests/test_collision_2d.jl
 // find_rho! / find_rho0!  :63-69, used with self=true
 template <class K>
@@ -705,6 +822,67 @@ struct UNormalize {
         const double a = P.n.x[i], b = P.n.y[i], c = P.n.z[i];
         const double s = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(c, c))) + P.s0;
         P.n.x[i] = a / s; P.n.y[i] = b / s; P.n.z[i] = c / s;
+    }
+};
+// pr = P/rho0^2 with the constant rho0: the per-particle quotient of Kepler_vortex.jl:158
+struct UPressureOverConst {
+    struct Params {
+        const double* P;
+        double* pr;
+        double rho0sq;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) { P.pr[i] = P.P[i] / P.rho0sq; }
+};
+// move!  collapse_symplectic.jl:134-138, Kepler_vortex.jl:174-178
+struct UMoveRev {
+    struct Params {
+        WV3 x;
+        RV3 v;
+        const double* type;
+        double dt;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        if (P.type[i] == 0.0) {
+            P.x.x[i] = sp_rev_add(P.x.x[i], __dmul_rn(P.dt, P.v.x[i]));
+            P.x.y[i] = sp_rev_add(P.x.y[i], __dmul_rn(P.dt, P.v.y[i]));
+            P.x.z[i] = sp_rev_add(P.x.z[i], __dmul_rn(P.dt, P.v.z[i]));
+        }
+    }
+};
+// accelerate!  collapse_symplectic.jl:140-144
+struct UAccelerateRev {
+    struct Params {
+        WV3 v;
+        RV3 a;
+        const double* type;
+        double hdt, gx, gy, gz;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        if (P.type[i] == 0.0) {
+            P.v.x[i] = sp_rev_add(P.v.x[i], __dmul_rn(P.hdt, __dadd_rn(P.a.x[i], P.gx)));
+            P.v.y[i] = sp_rev_add(P.v.y[i], __dmul_rn(P.hdt, __dadd_rn(P.a.y[i], P.gy)));
+            P.v.z[i] = sp_rev_add(P.v.z[i], __dmul_rn(P.hdt, __dadd_rn(P.a.z[i], P.gz)));
+        }
+    }
+};
+// accelerate!  Kepler_vortex.jl:180-184 (central gravity -GM x/|x|^3 added reversibly to the SPH acceleration)
+struct UAccelerateRevCentral {
+    struct Params {
+        RV3 x;
+        WV3 v;
+        RV3 a;
+        const double* type;
+        double hdt, GM;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        if (P.type[i] == 0.0) {
+            const double x = P.x.x[i], y = P.x.y[i], z = P.x.z[i];
+            const double n = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
+            const double k = -P.GM / __dmul_rn(__dmul_rn(n, n), n);
+            P.v.x[i] = sp_rev_add(P.v.x[i], __dmul_rn(P.hdt, sp_rev_add(P.a.x[i], __dmul_rn(k, x))));
+            P.v.y[i] = sp_rev_add(P.v.y[i], __dmul_rn(P.hdt, sp_rev_add(P.a.y[i], __dmul_rn(k, y))));
+            P.v.z[i] = sp_rev_add(P.v.z[i], __dmul_rn(P.hdt, sp_rev_add(P.a.z[i], __dmul_rn(k, z))));
+        }
     }
 };
 // find_pressure!  test_collision_2d.jl:71-73

@@ -1694,6 +1694,76 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
             UMoveAll::Params P{wv3(s, F[0]), rv3(s, F[1]), wv3(s, F[2]), Pm[0]};
             return launch_unary<UMoveAll>(s, P);
         }
+        case SP_OP_DENSITY_SUM_FLUID: {
+            NEED(3, 3, 3, 1, 1);
+            NEED_CELLS();
+            sp_wrote(s, F[1]);
+            return dispatch_kernel<OpDensitySumFluid>(s, (int)Pm[0], Pm[2], flags, [&](auto& P) {
+                P.qp[0] = sc(s, F[2]);
+                P.out = sc(s, F[1]);
+                P.m = Pm[1];
+            });
+        }
+        case SP_OP_INTERNAL_FORCE_LJ: {
+            NEED(5, 8, 3, 1, 1, 3, 1);
+            NEED_CELLS();
+            sp_wrote(s, F[3]);
+            double* pr = nullptr;
+            if (Pm[3] == 0.0) {  // collapse_symplectic.jl:116: P/rho^2 of each particle
+                int rc2 = pressure_over_rho2(s, F[1], F[2], &pr);
+                if (rc2) return rc2;
+            } else {  // Kepler_vortex.jl:158: P/rho0^2 with the constant rho0
+                int32_t fpr;
+                int rc2 = sp_add_field(s, "_pr", 1, &fpr);
+                if (rc2) return rc2;
+                s->fields[fpr].transient = true;
+                pr = s->fields[fpr].d;
+                UPressureOverConst::Params Pp{sc(s, F[1]), pr, Pm[3] * Pm[3]};
+                if ((rc2 = launch_unary<UPressureOverConst>(s, Pp))) return rc2;
+            }
+            return dispatch_kernel<OpInternalForceLJ>(s, (int)Pm[0], Pm[2], flags, [&](auto& P) {
+                P.qp[0] = pr;
+                P.qp[1] = sc(s, F[4]);
+                P.a = wv3(s, F[3]);
+                P.m = Pm[1];
+                P.wall = Pm[4];
+                P.dr_wall = Pm[5];
+                P.E_wall = Pm[6];
+                P.eps = Pm[7];
+            });
+        }
+        case SP_OP_MOVE_REV: {
+            NEED(3, 1, 3, 3, 1);
+            sp_wrote(s, F[0]);
+            UMoveRev::Params P{wv3(s, F[0]), rv3(s, F[1]), sc(s, F[2]), Pm[0]};
+            return launch_unary<UMoveRev>(s, P);
+        }
+        case SP_OP_ACCELERATE_REV: {
+            NEED(3, 4, 3, 3, 1);
+            sp_wrote(s, F[0]);
+            UAccelerateRev::Params P{wv3(s, F[0]), rv3(s, F[1]), sc(s, F[2]), Pm[0], Pm[1], Pm[2], Pm[3]};
+            return launch_unary<UAccelerateRev>(s, P);
+        }
+        case SP_OP_ACCELERATE_REV_CENTRAL: {
+            NEED(4, 2, 3, 3, 3, 1);
+            sp_wrote(s, F[1]);
+            UAccelerateRevCentral::Params P{rv3(s, F[0]), wv3(s, F[1]), rv3(s, F[2]), sc(s, F[3]), Pm[0], Pm[1]};
+            return launch_unary<UAccelerateRevCentral>(s, P);
+        }
+        case SP_OP_LJ_POTENTIAL: {
+            NEED(3, 5, 3, 1, 1);
+            NEED_CELLS();
+            sp_wrote(s, F[1]);
+            // no SPH kernel in this sum: any family serves the dispatch, only the cut-off h matters
+            return dispatch_kernel<OpLJPotential>(s, SP_KERNEL_WENDLAND2, Pm[0], flags & ~SP_FLAG_SELF, [&](auto& P) {
+                P.qp[0] = sc(s, F[2]);
+                P.out = sc(s, F[1]);
+                P.coef = Pm[1];
+                P.wall = Pm[2];
+                P.dr_wall = Pm[3];
+                P.eps = Pm[4];
+            });
+        }
     }
     return sp_fail(s, SP_ERR_INVALID, "unknown operator id");
 }

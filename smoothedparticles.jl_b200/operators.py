@@ -106,6 +106,43 @@ def internal_force_tension(m, h, mu, rho0, beta, s0, x="x", v="v", P="P", n="n",
                     "internal_force! (surface tension)")
 
 
+# ---- examples/collapse_symplectic.jl, examples/Kepler_vortex.jl (reversible fixed-point integrator, LJ walls)
+def density_sum_fluid(kernel, m, h, out="rho", x="x", type="type"):
+    """find_rho! / find_rho0!, collapse_symplectic.jl:98-108: fluid-fluid pairs only (use with self=True)."""
+    return Operator(K["SP_OP_DENSITY_SUM_FLUID"], (x, out, type), (_kid(kernel), m, h), True, "find_rho! (fluid)")
+
+
+def internal_force_lj(kernel, m, h, dr_wall, E_wall, eps, rho0=0.0, wall_type=1.0, x="x", P="P", rho="rho", a="a",
+                      type="type"):
+    """collapse_symplectic.jl:114-123 (rho0 = 0: P/rho^2 of each particle) and Kepler_vortex.jl:155-164 (P/rho0^2):
+    pressure force between fluid particles, Lennard-Jones repulsion from wall particles closer than dr_wall."""
+    return Operator(K["SP_OP_INTERNAL_FORCE_LJ"], (x, P, rho, a, type),
+                    (_kid(kernel), m, h, rho0, wall_type, dr_wall, E_wall, eps), True, "internal_force! (LJ walls)")
+
+
+def move_rev(dt, x="x", v="v", type="type"):
+    """collapse_symplectic.jl:134-138: x = rev_add(x, dt*v) for fluid particles (utils/FixPA.jl)."""
+    return Operator(K["SP_OP_MOVE_REV"], (x, v, type), (dt,), False, "move! (rev_add)")
+
+
+def accelerate_rev(hdt, g=(0.0, 0.0, 0.0), v="v", a="a", type="type"):
+    """collapse_symplectic.jl:140-144: v = rev_add(v, hdt*(a + g)) for fluid particles."""
+    return Operator(K["SP_OP_ACCELERATE_REV"], (v, a, type), (hdt, g[0], g[1], g[2]), False, "accelerate! (rev_add)")
+
+
+def accelerate_rev_central(hdt, GM, x="x", v="v", a="a", type="type"):
+    """Kepler_vortex.jl:180-184: v = rev_add(v, hdt*rev_add(a, -GM/norm(x)^3*x)) for fluid particles."""
+    return Operator(K["SP_OP_ACCELERATE_REV_CENTRAL"], (x, v, a, type), (hdt, GM), False,
+                    "accelerate! (rev_add, central gravity)")
+
+
+def lj_potential(h, m, E_wall, dr_wall, eps, wall_type=1.0, out="U", x="x", type="type"):
+    """sum(sys, LJ_potential, p) for every particle p (core.jl:271-291, collapse_symplectic.jl:146-153):
+    out_p += m*E_wall*(0.5 s^2 - 0.25 s^4 - 0.25), s = dr_wall/(r + eps), over wall neighbours with r < dr_wall."""
+    return Operator(K["SP_OP_LJ_POTENTIAL"], (x, out, type), (h, m * E_wall, wall_type, dr_wall, eps), True,
+                    "LJ_potential")
+
+
 # ---- examples/static_container.jl
 def sc_balance_of_mass(kernel, m, h, dt, x="x", v="v", rho="rho"):
     """static_container.jl:102-104: the density is integrated inside the pair loop."""
