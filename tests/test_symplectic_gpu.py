@@ -118,7 +118,7 @@ def test_symplectic_time_loop_parity(maker, kw, nsteps):
 
 
 @pytest.mark.parametrize("maker,kw,nsteps", [(configs.collapse_symplectic, dict(dr=2e-2), 60),
-                                             (configs.collapse_symplectic, dict(dr=5e-3), 12),
+                                             (configs.collapse_symplectic, dict(dr=5e-3), 40),
                                              (configs.kepler_vortex, dict(), 30)])
 def test_reverting_velocities_retraces_the_run_exactly_on_device(maker, kw, nsteps):
     # collapse_symplectic.jl:232-255 (revert = true), see tests/test_symplectic_cpu.py: exact, at any size
@@ -132,7 +132,7 @@ def test_reverting_velocities_retraces_the_run_exactly_on_device(maker, kw, nste
     for _ in range(nsteps):
         case.step(s)
     assert len(s) == case.n
-    assert np.max(np.abs(s.get("x") - x1)) > 1e3 / TWO30, "nothing moved: the test would be vacuous"
+    assert np.max(np.abs(s.get("x") - x1)) > 100 / TWO30, "nothing moved: the test would be vacuous"
     s.set("v", -s.get("v"))
     for _ in range(nsteps):
         case.step(s)
