@@ -172,12 +172,35 @@ enum {
     SP_OP_ACCELERATE_REV_CENTRAL = 44,
     /* unary. fields {x, v, a, type}; params {hdt, GM}
        if type == 0: v = rev_add(v, hdt*rev_add(a, (-GM/norm(x)^3)*x))   Kepler_vortex.jl:180-184 */
-    SP_OP_LJ_POTENTIAL = 45
+    SP_OP_LJ_POTENTIAL = 45,
     /* binary (the per-particle sum(sys, LJ_potential, p), core.jl:271-291). fields {x, out, type};
        params {h, coef, wall_type, dr_wall, eps}
        if type_q == wall_type && type_p == 0 && r < dr_wall: s = dr_wall/(r + eps);
             out_p += coef*(0.5*s^2 - 0.25*s^4 - 0.25),  coef = m*E_wall
        collapse_symplectic.jl:146-153, Kepler_vortex.jl:186-193 */
+
+    /* channel flow past a cylinder with an inflow buffer and per-particle mass — examples/cylinder.jl */
+    SP_OP_CYL_BALANCE_OF_MASS = 50,
+    /* binary. fields {x, v, rho, Drho, m, type}; params {kernel, h, two_nu}
+       Drho_p += (m_q*rDw(h,r))*dot(x_pq, v_pq);  if type_p == 0 && type_q == 0: Drho_p += two_nu/rho_p*(rho_p - rho_q)
+       cylinder.jl:102-108 */
+    SP_OP_CYL_FIND_PRESSURE = 51,
+    /* unary. fields {x, rho, Drho, P}; params {dt, c2, rho0, x1_min}
+       if x[1] >= x1_min: rho += Drho*dt;   Drho = 0;  P = c2*(rho - rho0)       cylinder.jl:110-116 */
+    SP_OP_CYL_INTERNAL_FORCE = 52,
+    /* binary. fields {x, v, P, rho, a, m}; params {kernel, h, mu, eps2}   ker = m_q*rDw(h,r);
+       a_p += (-ker*(P_p/rho_p^2 + P_q/rho_q^2))*x_pq;
+       a_p += (8*ker*mu/(rho_p*rho_q)*dot(v_pq, x_pq)/(r*r + eps2))*x_pq,  eps2 = 0.01*h*h      cylinder.jl:118-123 */
+    SP_OP_MOVE_TYPES = 53,
+    /* unary. fields {x, v, a, type}; params {dt, type_a, type_b}
+       a = 0;  if type == type_a || type == type_b: x += dt*v                     cylinder.jl:125-130 */
+    SP_OP_CYL_ACCELERATE = 54,
+    /* unary. fields {x, v, a, type}; params {hdt, cyl1, coef}   if type == 0:
+       f = (cyl1 - x[1], -x[2], 0);  v += hdt*(a + coef*f/((cyl1 - x[1])^2 + x[2]^2))   cylinder.jl:132-143 */
+    SP_OP_SET_INFLOW_SPEED = 55
+    /* unary. fields {x, v, type}; params {inflow_type, s, U_max, chan_w}
+       if type == inflow_type: v = (s*U_max*(1 - (2*x[2]/chan_w)^2))*VECX,  s = min(1, t/t_acc) from the host
+       cylinder.jl:91-97 */
 };
 
 /* sp_apply flags */
@@ -199,8 +222,11 @@ enum {
     /* fields {v, rho, rho0}; params {m, c, rho0}; out[1]   test_collision_2d.jl:96-100 */
     SP_RED_SUM = 4,
     /* fields {f}; out[ncomp] plain sum of every component */
-    SP_RED_ENERGY_ISPH = 5
+    SP_RED_ENERGY_ISPH = 5,
     /* fields {x, v}; params {m, gx, gy, gz}; out[1]   collapse_dry_implicit.jl:173-177 */
+    SP_RED_FORCE_ON_TYPE = 6
+    /* fields {a, m, type}; params {type_sel}; out[3] = sum of m*a over the particles with type == type_sel
+       cylinder.jl:158-159 (calculate_force over the obstacle particles) */
 };
 
 /* point sums:  out[k] = sum_q func(q, |x_k - q.x|)  over !(r > h), no self exclusion (core.jl:240-260) */
@@ -270,6 +296,13 @@ enum { SP_GRID_SQUARE = 1, SP_GRID_HEXAGONAL = 2, SP_GRID_CUBIC = 3 }; /* grids.
 int32_t sp_generate_particles(sp_system* sys, int32_t grid, double dr, const sp_shape_node* nodes, int32_t n_nodes,
                               const double* offsets /* n_off x 3 */, int32_t n_off, const int64_t irange[6],
                               const int32_t* fill_fields, const double* fill_values, int32_t n_fill, int64_t* n_added);
+
+/* Inflow buffer, add_new_particles! of examples/cylinder.jl:145-156: every particle (in reference order) with
+ * type == from_type and x[1] >= x1_min becomes to_type, and a new particle of type from_type is appended at
+ * x - shift*VECX; the appended particles keep the order of their sources.  New particles are what the script's
+ * constructor makes: every field zero except the `n_fill` constant fields (e.g. rho = rho0, m = m0) and `type`. */
+int32_t sp_respawn(sp_system* sys, int32_t type_field, double from_type, double to_type, double x1_min, double shift,
+                   const int32_t* fill_fields, const double* fill_values, int32_t n_fill, int64_t* n_added);
 
 /* ---- the hot path --------------------------------------------------------- */
 int32_t sp_create_cell_list(sp_system* sys);

@@ -63,6 +63,7 @@ def load():
         "so_coo_matvec": (None, [_i64, _pi64, _pi64, _pf64, _pf64, _pf64, _i64]),
         "so_cg_coo": (_i64, [_i64, _pi64, _pi64, _pf64, _pf64, _pf64, _i64, _f64, _f64, _i64, _pf64]),
         "so_kernel_eval": (None, [C.c_int, C.c_int, _f64, _pf64, _pf64, _i64]),
+        "so_respawn": (_i64, [_p, C.c_int, _f64, _f64, _f64, _f64, _pi32, _pf64, C.c_int]),
         "so_run_program": (_f64, [_p, C.c_int, _pi32, C.c_int, _pf64, C.c_int, _i64]),
     }
     for name, (res, args) in sig.items():
@@ -167,6 +168,14 @@ class OracleSystem:
             else:
                 add = np.zeros((n_new,) if nc == 1 else (n_new, nc))
             self.set(name, np.concatenate([old, add], axis=0))
+
+    def respawn(self, type_field, from_type, to_type, x1_min, shift, **constants):
+        """add_new_particles!, examples/cylinder.jl:145-156 (literal serial loop in the oracle)."""
+        names = list(constants)
+        slots = np.asarray([self._slot[n] for n in names] or [0], dtype=np.int32)
+        vals = _f([constants[n] for n in names] or [0.0])
+        return int(self._lib.so_respawn(self._h, self._slot[type_field], float(from_type), float(to_type),
+                                        float(x1_min), float(shift), _p32(slots), _pf(vals), len(names)))
 
     def set(self, name, values):
         a = _f(values)

@@ -617,6 +617,86 @@ int apply_op(OSys& s, int op, const int32_t* F, int nf, const double* P, int np,
             });
             return SP_OK;
         }
+        case SP_OP_CYL_BALANCE_OF_MASS: {  // cylinder.jl:102-108
+            if (!need(6, 3)) return SP_ERR_INVALID;
+            const int ov = F[1], orho = F[2], oD = F[3], om = F[4], ot = F[5];
+            kfn rDw = pick_rD((int)P[0]);
+            const double h = P[1], two_nu = P[2];
+            if (!rDw) return SP_ERR_INVALID;
+            apply_binary(s, [=](Particle& p, const Particle& q, const double* xpq, double r) {
+                double ker = q.f[om] * rDw(h, r);
+                double vpq[3] = {p.f[ov] - q.f[ov], p.f[ov + 1] - q.f[ov + 1], p.f[ov + 2] - q.f[ov + 2]};
+                p.f[oD] += ker * dot3(xpq, vpq);
+                if (p.f[ot] == 0.0 && q.f[ot] == 0.0) p.f[oD] += two_nu / p.f[orho] * (p.f[orho] - q.f[orho]);
+            });
+            return SP_OK;
+        }
+        case SP_OP_CYL_FIND_PRESSURE: {  // cylinder.jl:110-116
+            if (!need(4, 4)) return SP_ERR_INVALID;
+            const int ox = F[0], orho = F[1], oD = F[2], oP = F[3];
+            const double dt = P[0], c2 = P[1], rho0 = P[2], x1_min = P[3];
+            apply_unary(s, [=](Particle& p) {
+                if (p.f[ox] >= x1_min) p.f[orho] += p.f[oD] * dt;
+                p.f[oD] = 0.0;
+                p.f[oP] = c2 * (p.f[orho] - rho0);
+            });
+            return SP_OK;
+        }
+        case SP_OP_CYL_INTERNAL_FORCE: {  // cylinder.jl:118-123
+            if (!need(6, 4)) return SP_ERR_INVALID;
+            const int ov = F[1], oP = F[2], orho = F[3], oa = F[4], om = F[5];
+            kfn rDw = pick_rD((int)P[0]);
+            const double h = P[1], mu = P[2], eps2 = P[3];
+            if (!rDw) return SP_ERR_INVALID;
+            apply_binary(s, [=](Particle& p, const Particle& q, const double* xpq, double r) {
+                double ker = q.f[om] * rDw(h, r);
+                double a = -ker * (p.f[oP] / (p.f[orho] * p.f[orho]) + q.f[oP] / (q.f[orho] * q.f[orho]));
+                for (int c = 0; c < 3; c++) p.f[oa + c] += a * xpq[c];
+                double vpq[3] = {p.f[ov] - q.f[ov], p.f[ov + 1] - q.f[ov + 1], p.f[ov + 2] - q.f[ov + 2]};
+                double b = 8.0 * ker * mu / (p.f[orho] * q.f[orho]) * dot3(vpq, xpq) / (r * r + eps2);
+                for (int c = 0; c < 3; c++) p.f[oa + c] += b * xpq[c];
+            });
+            return SP_OK;
+        }
+        case SP_OP_MOVE_TYPES: {  // cylinder.jl:125-130
+            if (!need(4, 3)) return SP_ERR_INVALID;
+            const int ox = F[0], ov = F[1], oa = F[2], ot = F[3];
+            const double dt = P[0], ta = P[1], tb = P[2];
+            apply_unary(s, [=](Particle& p) {
+                p.f[oa] = p.f[oa + 1] = p.f[oa + 2] = 0.0;
+                if (p.f[ot] == ta || p.f[ot] == tb)
+                    for (int c = 0; c < 3; c++) p.f[ox + c] += dt * p.f[ov + c];
+            });
+            return SP_OK;
+        }
+        case SP_OP_CYL_ACCELERATE: {  // cylinder.jl:132-143 (gravity: :132-137)
+            if (!need(4, 3)) return SP_ERR_INVALID;
+            const int ox = F[0], ov = F[1], oa = F[2], ot = F[3];
+            const double hdt = P[0], cyl1 = P[1], coef = P[2];
+            apply_unary(s, [=](Particle& p) {
+                if (p.f[ot] == 0.0) {
+                    double f[3] = {cyl1 - p.f[ox], -p.f[ox + 1], 0.0};
+                    double absf2 = (cyl1 - p.f[ox]) * (cyl1 - p.f[ox]) + p.f[ox + 1] * p.f[ox + 1];
+                    for (int c = 0; c < 3; c++) p.f[ov + c] += hdt * (p.f[oa + c] + coef * f[c] / absf2);
+                }
+            });
+            return SP_OK;
+        }
+        case SP_OP_SET_INFLOW_SPEED: {  // cylinder.jl:91-97
+            if (!need(3, 4)) return SP_ERR_INVALID;
+            const int ox = F[0], ov = F[1], ot = F[2];
+            const double inflow = P[0], sfac = P[1], U_max = P[2], chan_w = P[3];
+            apply_unary(s, [=](Particle& p) {
+                if (p.f[ot] == inflow) {
+                    double q = 2.0 * p.f[ox + 1] / chan_w;
+                    double v1 = sfac * U_max * (1.0 - q * q);
+                    p.f[ov] = v1 * 1.0;
+                    p.f[ov + 1] = v1 * 0.0;
+                    p.f[ov + 2] = v1 * 0.0;
+                }
+            });
+            return SP_OK;
+        }
         case SP_OP_DENSITY_SUM: {  // test_collision_2d.jl:63-69; self term added last (core.jl:155-157)
             if (!need(2, 3)) return SP_ERR_INVALID;
             const int oo = F[1];
@@ -987,6 +1067,18 @@ int so_reduce(void* hnd, int red, const int32_t* F, int nf, const double* P, int
             out[0] = E;
             return SP_OK;
         }
+        case SP_RED_FORCE_ON_TYPE: {  // cylinder.jl:158-159: F = sum(p -> p.m*p.a, obstacle)
+            if (nf != 3 || np != 1) return SP_ERR_INVALID;
+            const int oa = F[0], om = F[1], ot = F[2];
+            double acc[3] = {0.0, 0.0, 0.0};
+            for (const Particle& p : s.particles)
+                if (p.f[ot] == P[0])
+                    for (int c = 0; c < 3; c++) acc[c] += p.f[om] * p.f[oa + c];
+            out[0] = acc[0];
+            out[1] = acc[1];
+            out[2] = acc[2];
+            return SP_OK;
+        }
     }
     return SP_ERR_INVALID;
 }
@@ -1069,6 +1161,30 @@ int64_t so_cg_coo(int64_t nnz, const int64_t* I, const int64_t* J, const double*
     }
     if (resid_out) *resid_out = residual;
     return it;
+}
+
+// add_new_particles!, cylinder.jl:145-156 (literal, serial): slot/value pairs describe what the script's constructor
+// Particle(x, INFLOW) sets besides x and type (every other field is zero).
+int64_t so_respawn(void* hnd, int type_slot, double from_type, double to_type, double x1_min, double shift,
+                   const int32_t* fill_slots, const double* fill_values, int n_fill) {
+    OSys& s = *(OSys*)hnd;
+    std::vector<Particle> fresh;
+    for (Particle& p : s.particles) {
+        if (p.f[type_slot] == from_type && p.f[0] >= x1_min) {
+            p.f[type_slot] = to_type;
+            Particle q;
+            for (int k = 0; k < NSLOT; k++) q.f[k] = 0.0;
+            q.f[0] = p.f[0] - shift * 1.0;  // p.x - bc_width*VECX
+            q.f[1] = p.f[1] - shift * 0.0;
+            q.f[2] = p.f[2] - shift * 0.0;
+            for (int k = 0; k < n_fill; k++) q.f[fill_slots[k]] = fill_values[k];
+            q.f[type_slot] = from_type;
+            fresh.push_back(q);
+        }
+    }
+    s.particles.insert(s.particles.end(), fresh.begin(), fresh.end());
+    s.have_cells = false;
+    return (int64_t)fresh.size();
 }
 
 void so_kernel_eval(int kernel, int kfun, double h, const double* r, double* out, int64_t n) {

@@ -76,6 +76,7 @@ SIGNATURES = {
     "sp_neighbour_list_capacity": (_i32, [_p, _pi32]),
     "sp_generate_particles": (_i32, [_p, _i32, _f64, C.POINTER(ShapeNode), _i32, _pf64, _i32, _pi64, _pi32, _pf64, _i32,
                                      _pi64]),
+    "sp_respawn": (_i32, [_p, _i32, _f64, _f64, _f64, _f64, _pi32, _pf64, _i32, _pi64]),
     "sp_num_removed": (_i32, [_p, _pi64]),
     "sp_last_call_ms": (_i32, [_p, C.POINTER(C.c_float)]),
     "sp_timer_start": (_i32, [_p]),

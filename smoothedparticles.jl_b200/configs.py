@@ -14,6 +14,7 @@ order as the script.  A Case is backend-agnostic: ``case.make(ParticleSystem)`` 
   drop                   examples/drop.jl                    3-D drop with colour-field surface tension
   collapse_symplectic    examples/collapse_symplectic.jl     reversible fixed-point Verlet, Lennard-Jones walls
   kepler_vortex          examples/Kepler_vortex.jl           fluid ring in central gravity, same integrator
+  cylinder               examples/cylinder.jl                channel flow past a cylinder, inflow buffer, per-particle mass
   lattice_box            synthetic S1 block of SURVEY §8(d)  jittered cubic lattice, all fluid
 """
 from __future__ import annotations
@@ -507,6 +508,70 @@ def kepler_vortex(N_rings: int = 25) -> Case:
     return Case("kepler_vortex", fields, domain, h, init, step, prologue,
                 consts=dict(dr=dr, h=h, rho0=rho0, m=m, c=c, dt=dt, GM=GM, r0=r0, dr_wall=dr_wall, E_wall=E_wall,
                             eps=eps), dim=2)
+
+
+# --------------------------------------------------------------------------- cylinder.jl
+def cylinder(init) -> Case:
+    """examples/cylinder.jl:29-61 (constants), :86-89 (make_system: the particles are imported from
+    init/cylinder.vtp), :167-186 (the modified Verlet loop with the inflow buffer).  ``init`` is the path of that
+    .vtp file or a mapping with ``x`` (n, 3) and ``type`` (n,) arrays (tests/golden/cylinder_init.npz holds the
+    file's particles).  The step index k (t = k*dt, :178) is kept on the system object as ``step_index``."""
+    chan_l, chan_w, cyl1, cyl_r = 2.2, 0.41, 0.2, 0.05
+    dr = math.pi * cyl_r / 20
+    h = 2.4 * dr
+    bc_width = 6 * dr
+    x2_min = -chan_w / 2 - 6 * dr
+    x2_max = chan_w / 2 + 6 * dr
+    U_max = 0.3
+    rho0 = 1.0
+    m0 = rho0 * dr ** 2
+    c = 20.0 * U_max
+    mu = 1.0e-3
+    nu = 0.1 * h * c
+    dt = 0.1 * h / c
+    t_acc = 1.0
+    FLUID, INFLOW, WALL, OBSTACLE = 0.0, 1.0, 2.0, 3.0
+    if isinstance(init, str):
+        from . import io as sp_io
+        pts, pf = sp_io.read_vtp(init)
+        x, typ = pts, pf["type"]
+    else:
+        x, typ = np.asarray(init["x"], dtype=np.float64), np.asarray(init["type"], dtype=np.float64)
+    n = len(x)
+    domain = geo.Rectangle(-bc_width, x2_min, chan_l, x2_max)
+    fields = {"v": 3, "a": 3, "rho": 1, "Drho": 1, "P": 1, "m": 1, "type": 1}
+    # Particle(x) :74-76: rho = rho0, m = m0; import_particles! then copies `type` from the file
+    start = {"x": x, "rho": np.full(n, rho0), "m": np.full(n, m0), "type": typ}
+    o_bom = ops.cyl_balance_of_mass("wendland2", h, nu)
+    o_fp = ops.cyl_find_pressure(dt, c, rho0, -bc_width + h)
+    o_if = ops.cyl_internal_force("wendland2", h, mu)
+    o_mv = ops.move_types(dt, FLUID, INFLOW)
+    o_ac = ops.cyl_accelerate(0.5 * dt, cyl1, U_max)
+
+    def step(sys):  # :177-186
+        k = getattr(sys, "step_index", 0) + 1
+        sys.step_index = k
+        t = k * dt
+        sys.apply(o_ac)
+        sys.apply(o_mv)
+        sys.respawn("type", INFLOW, FLUID, 0.0, bc_width, rho=rho0, m=m0)  # add_new_particles! :145-156
+        sys.apply(ops.set_inflow_speed(t, t_acc, U_max, chan_w, INFLOW))
+        sys.create_cell_list()
+        sys.apply(o_bom)
+        sys.apply(o_fp)
+        sys.apply(o_if)
+        sys.apply(o_ac)
+
+    return Case("cylinder", fields, domain, h, start, step,
+                consts=dict(dr=dr, h=h, rho0=rho0, m0=m0, c=c, mu=mu, nu=nu, dt=dt, U_max=U_max, bc_width=bc_width,
+                            chan_w=chan_w, t_acc=t_acc, OBSTACLE=OBSTACLE, L_char=0.1), dim=2)
+
+
+def cylinder_force_coefficients(sys, consts) -> np.ndarray:
+    """calculate_force, cylinder.jl:158-164: C = 2 F/(L_char U_mean^2), F = sum of m*a over the obstacle particles."""
+    F = sys.reduce(K["SP_RED_FORCE_ON_TYPE"], ("a", "m", "type"), (consts["OBSTACLE"],), nout=3)
+    U_mean = 2 / 3 * consts["U_max"]
+    return 2.0 * np.asarray(F) / (consts["L_char"] * U_mean ** 2)
 
 
 # --------------------------------------------------------------------------- collapse_dry_implicit.jl

@@ -202,3 +202,81 @@ extern "C" int32_t sp_generate_particles(sp_system* s, int32_t grid, double dr, 
     if (n_added) *n_added = total;
     return sp_time_end(s);
 }
+
+// ------------------------------------------------------------------ inflow buffer (examples/cylinder.jl:145-156)
+// flag[r] = 1 when the particle with reference index r leaves the buffer; indexed by REFERENCE index so that the
+// exclusive scan numbers the new particles in the order the script's serial loop pushes them
+__global__ void __launch_bounds__(256) k_respawn_flags(const double* __restrict__ x1, const double* __restrict__ type,
+                                                       const int* __restrict__ ref, long long n, double from_type,
+                                                       double x1_min, int* __restrict__ flag, int* __restrict__ pos) {
+    const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int f = (type[s] == from_type && x1[s] >= x1_min) ? 1 : 0;
+    flag[ref[s]] = f;
+    pos[ref[s]] = f;
+}
+__global__ void __launch_bounds__(256) k_respawn_scatter(double* __restrict__ X, long long cap, double* __restrict__ type,
+                                                         const int* __restrict__ ref, long long n_old, double to_type,
+                                                         double shift, const int* __restrict__ flag,
+                                                         const int* __restrict__ pos) {
+    const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (s >= n_old) return;
+    const int r = ref[s];
+    if (!flag[r]) return;
+    type[s] = to_type;
+    const long long d = n_old + pos[r];
+    X[d] = __dsub_rn(X[s], __dmul_rn(shift, 1.0));  // p.x - bc_width*VECX
+    X[cap + d] = __dsub_rn(X[cap + s], __dmul_rn(shift, 0.0));
+    X[2 * cap + d] = __dsub_rn(X[2 * cap + s], __dmul_rn(shift, 0.0));
+}
+
+extern "C" int32_t sp_respawn(sp_system* s, int32_t type_field, double from_type, double to_type, double x1_min,
+                              double shift, const int32_t* fill_fields, const double* fill_values, int32_t n_fill,
+                              int64_t* n_added) {
+    if (!s || n_fill < 0 || (n_fill > 0 && (!fill_fields || !fill_values))) return SP_ERR_INVALID;
+    if (type_field <= 0 || type_field >= (int)s->fields.size() || s->fields[type_field].ncomp != 1)
+        return sp_fail(s, SP_ERR_INVALID, "respawn: bad type field");
+    for (int f = 0; f < n_fill; f++)
+        if (fill_fields[f] <= 0 || fill_fields[f] >= (int)s->fields.size())
+            return sp_fail(s, SP_ERR_INVALID, "respawn: bad fill field");
+    if (s->slab) return sp_fail(s, SP_ERR_STATE, "respawn is not available on a slab system");
+    if (n_added) *n_added = 0;
+    if (s->n == 0) return SP_OK;
+    SP_CUDA(s, cudaSetDevice(s->device));
+    int rc = sp_time_begin(s);
+    if (rc) return rc;
+    const long long n_old = s->n;
+    const int B = 256;
+    int *flag = nullptr, *pos = nullptr;
+    SP_CUDA(s, sp_dmalloc(&flag, (size_t)n_old * sizeof(int)));
+    SP_CUDA(s, sp_dmalloc(&pos, (size_t)n_old * sizeof(int)));
+    SP_LAUNCH(s, k_respawn_flags, sp_blocks(n_old, B), B, 0, s->fields[0].d, s->fields[type_field].d, s->ref, n_old,
+              from_type, x1_min, flag, pos);
+    long long add = 0;
+    if (!(rc = sp_exclusive_scan_i32(s, pos, n_old))) {
+        int last[2];
+        SP_CUDA(s, cudaMemcpyAsync(&last[0], pos + n_old - 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        SP_CUDA(s, cudaMemcpyAsync(&last[1], flag + n_old - 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        SP_CUDA(s, cudaStreamSynchronize(s->stream));
+        add = (long long)last[0] + last[1];
+    }
+    if (!rc && add > 0 && !(rc = sp_resize(s, n_old + add))) {  // zero-fills the new tail, numbers it n_old, n_old+1, ...
+        sp_wrote(s, 0);
+        sp_wrote(s, type_field);
+        SP_LAUNCH(s, k_respawn_scatter, sp_blocks(n_old, B), B, 0, s->fields[0].d, s->cap, s->fields[type_field].d, s->ref,
+                  n_old, to_type, shift, flag, pos);
+        for (int f = 0; f < n_fill; f++) {
+            const int fid = fill_fields[f];
+            sp_wrote(s, fid);
+            SP_LAUNCH(s, k_gen_fill, sp_blocks(add, B), B, 0, s->fields[fid].d, s->cap, s->fields[fid].ncomp, fill_values[f],
+                      n_old, n_old + add);
+        }
+        SP_LAUNCH(s, k_gen_fill, sp_blocks(add, B), B, 0, s->fields[type_field].d, s->cap, 1, from_type, n_old, n_old + add);
+    }
+    cudaStreamSynchronize(s->stream);
+    sp_dfree(s, flag);
+    sp_dfree(s, pos);
+    if (rc) return rc;
+    if (n_added) *n_added = add;
+    return sp_time_end(s);
+}

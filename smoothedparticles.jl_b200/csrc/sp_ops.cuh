@@ -490,6 +490,82 @@ struct OpLJPotential {
     __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) { P.out[i] = a.d; }
 };
 
+// ---------------------------------------------------------------- examples/cylinder.jl (per-particle mass q.m)
+// balance_of_mass!  :102-108
+template <class K>
+struct OpCylBalanceOfMass {
+    static constexpr int NQ = 6;  // vx, vy, vz, rho, m, type
+    struct Params {
+        const double* qp[NQ];
+        double* Drho;
+        double two_nu;
+        SpKC kc;
+    };
+    struct PS {
+        double vx, vy, vz, rho, knu, tp;  // knu = two_nu/rho_p, the quotient the closure forms for every pair
+    };
+    struct Acc {
+        double d;
+    };
+    __device__ static __forceinline__ bool active(const Params&, int) { return true; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
+        p.vx = P.qp[0][i]; p.vy = P.qp[1][i]; p.vz = P.qp[2][i];
+        p.rho = P.qp[3][i];
+        p.knu = P.two_nu / p.rho;
+        p.tp = P.qp[5][i];
+        a.d = P.Drho[i];
+    }
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, const Q& q, double dx, double dy,
+                                                double dz, double r, Acc& a) {
+        const double ker = q(4) * K::rD(P.kc, r);
+        const double dvx = p.vx - q(0), dvy = p.vy - q(1), dvz = p.vz - q(2);
+        a.d += ker * (dx * dvx + dy * dvy + dz * dvz);
+        if (p.tp == 0.0 && q(5) == 0.0) a.d += p.knu * (p.rho - q(3));
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) { P.Drho[i] = a.d; }
+};
+
+// internal_force!  :118-123 (pressure + Monaghan viscosity, every particle type)
+template <class K>
+struct OpCylInternalForce {
+    static constexpr int NQ = 6;  // vx, vy, vz, pr = P/rho^2, rho, m
+    struct Params {
+        const double* qp[NQ];
+        WV3 a;
+        double mu, eps2;  // eps2 = 0.01*h*h
+        SpKC kc;
+    };
+    struct PS {
+        double vx, vy, vz, pr, rho;
+    };
+    struct Acc {
+        double x, y, z;
+    };
+    __device__ static __forceinline__ bool active(const Params&, int) { return true; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
+        p.vx = P.qp[0][i]; p.vy = P.qp[1][i]; p.vz = P.qp[2][i];
+        p.pr = P.qp[3][i];
+        p.rho = P.qp[4][i];
+        a.x = P.a.x[i]; a.y = P.a.y[i]; a.z = P.a.z[i];
+    }
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, const Q& q, double dx, double dy,
+                                                double dz, double r, Acc& a) {
+        const double ker = q(5) * K::rD(P.kc, r);
+        const double c = -ker * (p.pr + q(3));
+        a.x += c * dx; a.y += c * dy; a.z += c * dz;
+        const double dvx = p.vx - q(0), dvy = p.vy - q(1), dvz = p.vz - q(2);
+        const double b = 8.0 * ker * P.mu / (p.rho * q(4)) * (dvx * dx + dvy * dy + dvz * dz) / (r * r + P.eps2);
+        a.x += b * dx; a.y += b * dy; a.z += b * dz;
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) {
+        P.a.x[i] = a.x; P.a.y[i] = a.y; P.a.z[i] = a.z;
+    }
+};
+
 // ---------------------------------------------------------------- tests/test_collision_2d.jl
 // find_rho! / find_rho0!  :63-69, used with self=true
 template <class K>
@@ -882,6 +958,75 @@ struct UAccelerateRevCentral {
             P.v.x[i] = sp_rev_add(P.v.x[i], __dmul_rn(P.hdt, sp_rev_add(P.a.x[i], __dmul_rn(k, x))));
             P.v.y[i] = sp_rev_add(P.v.y[i], __dmul_rn(P.hdt, sp_rev_add(P.a.y[i], __dmul_rn(k, y))));
             P.v.z[i] = sp_rev_add(P.v.z[i], __dmul_rn(P.hdt, sp_rev_add(P.a.z[i], __dmul_rn(k, z))));
+        }
+    }
+};
+// find_pressure!  cylinder.jl:110-116 (the density of the inflow buffer upstream of x1_min is frozen)
+struct UCylFindPressure {
+    struct Params {
+        const double* x;
+        double *rho, *Drho, *P;
+        double dt, c2, rho0, x1_min;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        double rho = P.rho[i];
+        if (P.x[i] >= P.x1_min) {
+            rho += P.Drho[i] * P.dt;
+            P.rho[i] = rho;
+        }
+        P.Drho[i] = 0.0;
+        P.P[i] = P.c2 * (rho - P.rho0);
+    }
+};
+// move!  cylinder.jl:125-130
+struct UMoveTypes {
+    struct Params {
+        WV3 x;
+        RV3 v;
+        WV3 a;
+        const double* type;
+        double dt, ta, tb;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        P.a.x[i] = 0.0; P.a.y[i] = 0.0; P.a.z[i] = 0.0;
+        const double t = P.type[i];
+        if (t == P.ta || t == P.tb) {
+            P.x.x[i] += P.dt * P.v.x[i]; P.x.y[i] += P.dt * P.v.y[i]; P.x.z[i] += P.dt * P.v.z[i];
+        }
+    }
+};
+// accelerate! with the artificial attraction towards the cylinder  cylinder.jl:132-143
+struct UCylAccelerate {
+    struct Params {
+        RV3 x;
+        WV3 v;
+        RV3 a;
+        const double* type;
+        double hdt, cyl1, coef;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        if (P.type[i] == 0.0) {
+            const double fx = P.cyl1 - P.x.x[i], fy = -P.x.y[i], x2 = P.x.y[i];
+            const double absf2 = __dadd_rn(__dmul_rn(fx, fx), __dmul_rn(x2, x2));
+            P.v.x[i] += P.hdt * (P.a.x[i] + P.coef * fx / absf2);
+            P.v.y[i] += P.hdt * (P.a.y[i] + P.coef * fy / absf2);
+            P.v.z[i] += P.hdt * (P.a.z[i] + P.coef * 0.0 / absf2);
+        }
+    }
+};
+// set_inflow_speed!  cylinder.jl:91-97
+struct USetInflowSpeed {
+    struct Params {
+        RV3 x;
+        WV3 v;
+        const double* type;
+        double inflow, s, U_max, chan_w;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        if (P.type[i] == P.inflow) {
+            const double q = 2.0 * P.x.y[i] / P.chan_w;
+            const double v1 = __dmul_rn(__dmul_rn(P.s, P.U_max), __dsub_rn(1.0, __dmul_rn(q, q)));
+            P.v.x[i] = v1; P.v.y[i] = v1 * 0.0; P.v.z[i] = v1 * 0.0;
         }
     }
 };

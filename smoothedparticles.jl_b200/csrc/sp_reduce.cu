@@ -51,6 +51,14 @@ __device__ __forceinline__ void red_map(const RedParams& R, long long i, double 
         double m = R.p[0];
         double vx = V[i], vy = V[cap + i], vz = V[2 * cap + i];
         v[0] = 0.5 * m * (vx * vx + vy * vy + vz * vz) - m * (R.p[1] * X[i] + R.p[2] * X[cap + i] + R.p[3] * X[2 * cap + i]);
+    } else if (RED == SP_RED_FORCE_ON_TYPE) {  // fields {a, m, type}; params {type_sel}
+        if (R.f[2][i] == R.p[0]) {
+            const double* A = R.f[0];
+            const double m = R.f[1][i];
+            v[0] = m * A[i];
+            v[1] = m * A[cap + i];
+            v[2] = m * A[2 * cap + i];
+        }
     }
 }
 
@@ -234,6 +242,11 @@ int32_t sp_reduce(sp_system* s, int32_t red, const int32_t* F, int32_t nf, const
             const int nc[] = {3, 3};
             if ((rc = bind(2, nc, 4))) return rc;
             return run_reduce<SP_RED_ENERGY_ISPH, false>(s, R, 1, out);
+        }
+        case SP_RED_FORCE_ON_TYPE: {
+            const int nc[] = {3, 1, 1};
+            if ((rc = bind(3, nc, 1))) return rc;
+            return run_reduce<SP_RED_FORCE_ON_TYPE, false>(s, R, 3, out);
         }
     }
     return sp_fail(s, SP_ERR_INVALID, "unknown reduction id");

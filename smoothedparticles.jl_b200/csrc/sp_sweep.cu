@@ -1764,6 +1764,65 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
                 P.eps = Pm[4];
             });
         }
+        case SP_OP_CYL_BALANCE_OF_MASS: {
+            NEED(6, 3, 3, 3, 1, 1, 1, 1);
+            NEED_CELLS();
+            sp_wrote(s, F[3]);
+            return dispatch_kernel<OpCylBalanceOfMass>(s, (int)Pm[0], Pm[1], flags, [&](auto& P) {
+                set_v3(s, F[1], P.qp);
+                P.qp[3] = sc(s, F[2]);
+                P.qp[4] = sc(s, F[4]);
+                P.qp[5] = sc(s, F[5]);
+                P.Drho = sc(s, F[3]);
+                P.two_nu = Pm[2];
+            });
+        }
+        case SP_OP_CYL_FIND_PRESSURE: {
+            NEED(4, 4, 3, 1, 1, 1);
+            sp_wrote(s, F[1]);
+            sp_zeroed(s, F[2]);
+            sp_wrote(s, F[3]);
+            UCylFindPressure::Params P{sc(s, F[0]), sc(s, F[1]), sc(s, F[2]), sc(s, F[3]), Pm[0], Pm[1], Pm[2], Pm[3]};
+            return launch_unary<UCylFindPressure>(s, P);
+        }
+        case SP_OP_CYL_INTERNAL_FORCE: {
+            NEED(6, 4, 3, 3, 1, 1, 3, 1);
+            NEED_CELLS();
+            sp_wrote(s, F[4]);
+            double* pr = nullptr;
+            {
+                int rc2 = pressure_over_rho2(s, F[2], F[3], &pr);
+                if (rc2) return rc2;
+            }
+            return dispatch_kernel<OpCylInternalForce>(s, (int)Pm[0], Pm[1], flags, [&](auto& P) {
+                set_v3(s, F[1], P.qp);
+                P.qp[3] = pr;
+                P.qp[4] = sc(s, F[3]);
+                P.qp[5] = sc(s, F[5]);
+                P.a = wv3(s, F[4]);
+                P.mu = Pm[2];
+                P.eps2 = Pm[3];
+            });
+        }
+        case SP_OP_MOVE_TYPES: {
+            NEED(4, 3, 3, 3, 3, 1);
+            sp_wrote(s, F[0]);
+            sp_zeroed(s, F[2]);
+            UMoveTypes::Params P{wv3(s, F[0]), rv3(s, F[1]), wv3(s, F[2]), sc(s, F[3]), Pm[0], Pm[1], Pm[2]};
+            return launch_unary<UMoveTypes>(s, P);
+        }
+        case SP_OP_CYL_ACCELERATE: {
+            NEED(4, 3, 3, 3, 3, 1);
+            sp_wrote(s, F[1]);
+            UCylAccelerate::Params P{rv3(s, F[0]), wv3(s, F[1]), rv3(s, F[2]), sc(s, F[3]), Pm[0], Pm[1], Pm[2]};
+            return launch_unary<UCylAccelerate>(s, P);
+        }
+        case SP_OP_SET_INFLOW_SPEED: {
+            NEED(3, 4, 3, 3, 1);
+            sp_wrote(s, F[1]);
+            USetInflowSpeed::Params P{rv3(s, F[0]), wv3(s, F[1]), sc(s, F[2]), Pm[0], Pm[1], Pm[2], Pm[3]};
+            return launch_unary<USetInflowSpeed>(s, P);
+        }
     }
     return sp_fail(s, SP_ERR_INVALID, "unknown operator id");
 }

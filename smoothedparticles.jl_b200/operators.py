@@ -143,6 +143,42 @@ def lj_potential(h, m, E_wall, dr_wall, eps, wall_type=1.0, out="U", x="x", type
                     "LJ_potential")
 
 
+# ---- examples/cylinder.jl (per-particle mass, inflow buffer)
+def cyl_balance_of_mass(kernel, h, nu, x="x", v="v", rho="rho", Drho="Drho", m="m", type="type"):
+    """cylinder.jl:102-108: ker = q.m*rDw; Drho += ker*dot(x_pq, v_pq); fluid-fluid pairs add 2*nu/rho_p*(rho_p - rho_q)."""
+    return Operator(K["SP_OP_CYL_BALANCE_OF_MASS"], (x, v, rho, Drho, m, type), (_kid(kernel), h, 2 * nu), True,
+                    "balance_of_mass! (cylinder)")
+
+
+def cyl_find_pressure(dt, c, rho0, x1_min, x="x", rho="rho", Drho="Drho", P="P"):
+    """cylinder.jl:110-116: the density is integrated only downstream of x1_min = -bc_width + h."""
+    return Operator(K["SP_OP_CYL_FIND_PRESSURE"], (x, rho, Drho, P), (dt, c * c, rho0, x1_min), False,
+                    "find_pressure! (cylinder)")
+
+
+def cyl_internal_force(kernel, h, mu, x="x", v="v", P="P", rho="rho", a="a", m="m"):
+    """cylinder.jl:118-123: pressure and Monaghan viscosity with the neighbour's mass."""
+    return Operator(K["SP_OP_CYL_INTERNAL_FORCE"], (x, v, P, rho, a, m), (_kid(kernel), h, mu, 0.01 * h * h), True,
+                    "internal_force! (cylinder)")
+
+
+def move_types(dt, type_a, type_b, x="x", v="v", a="a", type="type"):
+    """cylinder.jl:125-130: a = 0; particles of the two given types move."""
+    return Operator(K["SP_OP_MOVE_TYPES"], (x, v, a, type), (dt, type_a, type_b), False, "move! (cylinder)")
+
+
+def cyl_accelerate(hdt, cyl1, U_max, x="x", v="v", a="a", type="type"):
+    """cylinder.jl:132-143: v += hdt*(a + gravity(p)), gravity = 0.3*U_max^2*f/|f|^2 towards (cyl1, 0)."""
+    return Operator(K["SP_OP_CYL_ACCELERATE"], (x, v, a, type), (hdt, cyl1, 0.3 * U_max ** 2), False,
+                    "accelerate! (cylinder)")
+
+
+def set_inflow_speed(t, t_acc, U_max, chan_w, inflow_type=1.0, x="x", v="v", type="type"):
+    """cylinder.jl:91-97 at time t: parabolic inflow profile ramped over t_acc."""
+    return Operator(K["SP_OP_SET_INFLOW_SPEED"], (x, v, type), (inflow_type, min(1.0, t / t_acc), U_max, chan_w), False,
+                    "set_inflow_speed!")
+
+
 # ---- examples/static_container.jl
 def sc_balance_of_mass(kernel, m, h, dt, x="x", v="v", rho="rho"):
     """static_container.jl:102-104: the density is integrated inside the pair loop."""

@@ -138,6 +138,21 @@ class ParticleSystem:
                                                   C.byref(added)), self._h)
         return added.value
 
+    def respawn(self, type_field: str, from_type: float, to_type: float, x1_min: float, shift: float,
+                **constants) -> int:
+        """``add_new_particles!`` of examples/cylinder.jl:145-156 on the device: particles of ``from_type`` with
+        ``x[1] >= x1_min`` become ``to_type`` and a fresh ``from_type`` particle is appended ``shift`` upstream of
+        each, in the order of their sources; ``constants`` are the fields the script's constructor sets
+        (``rho=rho0, m=m0``), everything else is zero.  Returns the number of particles added."""
+        names = list(constants)
+        ff = np.asarray([self._fid[n] for n in names], dtype=np.int32) if names else np.zeros(1, dtype=np.int32)
+        fv = _farr([constants[n] for n in names]) if names else np.zeros(1)
+        added = C.c_int64()
+        abi.check(self._lib.sp_respawn(self._h, self._fid[type_field], float(from_type), float(to_type), float(x1_min),
+                                       float(shift), abi.ptr_i32(ff), abi.ptr_f64(fv), len(names), C.byref(added)),
+                  self._h)
+        return added.value
+
     def set(self, name: str, values):
         """Upload a field in reference order: shape (n,) or (n, ncomp)."""
         nc = self.fields[name]

@@ -27,3 +27,10 @@ summary = {"source": "examples/init/cylinder.vtp", "n": int(pts.shape[0]),
 out = os.path.join(ROOT, "tests", "golden", "cylinder_vtp_summary.json")
 json.dump(summary, open(out, "w"), indent=1)
 print(json.dumps(summary, indent=1))
+
+# the same particles as an initial-state fixture for configs.cylinder() (examples/cylinder.jl:86-89 imports this
+# file): exact coordinates (z is identically 0) and the particle types; checked against the summary above in
+# tests/test_cylinder_cpu.py
+assert np.all(pts[:, 2] == 0.0)
+np.savez_compressed(os.path.join(ROOT, "tests", "golden", "cylinder_init.npz"), xy=pts[:, :2].copy(),
+                    type=fields["type"].astype(np.uint8))
