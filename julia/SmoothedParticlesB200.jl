@@ -11,7 +11,7 @@
 #   * the closures passed to apply! are registered operators (Operators.balance_of_mass(...), ...).
 module SmoothedParticlesB200
 
-export ParticleSystem, create_cell_list!, build_neighbour_lists!, apply!, upload!, download, add_particles!, ParticleField,
+export ParticleSystem, create_cell_list!, build_neighbour_lists!, apply!, respawn!, upload!, download, add_particles!, ParticleField,
        assemble_vector, Operators, poisson_cg!, reduce_energy_wcsph, sum_at_points
 
 const LIB = get(ENV, "SP_B200_LIB", joinpath(@__DIR__, "..", "smoothedparticles.jl_b200", "libsp_b200.so"))
@@ -132,7 +132,51 @@ isph_div_L_lambda(kernel, m, h, rho, dim; x = :x, v = :v, div = :div, L = :L, la
 isph_projection_vector(h, dt; div = :div, b = :b) = Operator(23, [div, b], [h, dt])
 isph_internal_force(kernel, m, h, rho; x = :x, P = :P, Dv = :Dv) = Operator(25, [x, P, Dv], [KERNELS[kernel], m, h, rho])
 isph_accelerate(dt; v = :v, Dv = :Dv, type = :type) = Operator(26, [v, Dv, type], [dt])
+# examples/static_container.jl:102-119
+sc_balance_of_mass(kernel, m, h, dt; x = :x, v = :v, rho = :rho) = Operator(30, [x, v, rho], [KERNELS[kernel], m, h, dt])
+sc_internal_force(kernel, m, h, mu, c, rho0; x = :x, v = :v, rho = :rho, a = :a, type = :type) =
+    Operator(31, [x, v, rho, a, type], [KERNELS[kernel], m, h, mu, c^2, rho0])
+move_all(dtm; x = :x, v = :v, a = :a) = Operator(32, [x, v, a], [dtm])
+# examples/drop.jl:76-113
+find_normal(kernel, vol, h; x = :x, n = :n) = Operator(33, [x, n], [KERNELS[kernel], 2 * vol * vol, h])
+normalize(s0; n = :n) = Operator(34, [n], [s0])
+internal_force_tension(m, h, mu, rho0, beta, s0; x = :x, v = :v, P = :P, n = :n, a = :a) =
+    Operator(35, [x, v, P, n, a], [m, h, mu, rho0, beta, s0])
+# examples/collapse_symplectic.jl:98-153, examples/Kepler_vortex.jl:139-193 (rev_add: examples/utils/FixPA.jl)
+density_sum_fluid(kernel, m, h; x = :x, out = :rho, type = :type) = Operator(40, [x, out, type], [KERNELS[kernel], m, h])
+internal_force_lj(kernel, m, h, dr_wall, E_wall, eps; rho0 = 0.0, wall_type = 1.0, x = :x, P = :P, rho = :rho, a = :a,
+                  type = :type) =
+    Operator(41, [x, P, rho, a, type], [KERNELS[kernel], m, h, rho0, wall_type, dr_wall, E_wall, eps])
+move_rev(dt; x = :x, v = :v, type = :type) = Operator(42, [x, v, type], [dt])
+accelerate_rev(hdt, g = (0.0, 0.0, 0.0); v = :v, a = :a, type = :type) = Operator(43, [v, a, type], [hdt, g...])
+accelerate_rev_central(hdt, GM; x = :x, v = :v, a = :a, type = :type) = Operator(44, [x, v, a, type], [hdt, GM])
+lj_potential(h, m, E_wall, dr_wall, eps; wall_type = 1.0, x = :x, out = :U, type = :type) =
+    Operator(45, [x, out, type], [h, m * E_wall, wall_type, dr_wall, eps])
+# examples/cylinder.jl:91-143
+cyl_balance_of_mass(kernel, h, nu; x = :x, v = :v, rho = :rho, Drho = :Drho, m = :m, type = :type) =
+    Operator(50, [x, v, rho, Drho, m, type], [KERNELS[kernel], h, 2 * nu])
+cyl_find_pressure(dt, c, rho0, x1_min; x = :x, rho = :rho, Drho = :Drho, P = :P) =
+    Operator(51, [x, rho, Drho, P], [dt, c^2, rho0, x1_min])
+cyl_internal_force(kernel, h, mu; x = :x, v = :v, P = :P, rho = :rho, a = :a, m = :m) =
+    Operator(52, [x, v, P, rho, a, m], [KERNELS[kernel], h, mu, 0.01 * h * h])
+move_types(dt, type_a, type_b; x = :x, v = :v, a = :a, type = :type) = Operator(53, [x, v, a, type], [dt, type_a, type_b])
+cyl_accelerate(hdt, cyl1, U_max; x = :x, v = :v, a = :a, type = :type) = Operator(54, [x, v, a, type], [hdt, cyl1, 0.3 * U_max^2])
+set_inflow_speed(t, t_acc, U_max, chan_w; inflow_type = 1.0, x = :x, v = :v, type = :type) =
+    Operator(55, [x, v, type], [inflow_type, min(1.0, t / t_acc), U_max, chan_w])
 end # module Operators
+
+# add_new_particles!, examples/cylinder.jl:145-156: particles of `from_type` with x[1] >= x1_min become `to_type`, a new
+# `from_type` particle appears `shift` upstream of each (reference order kept); `constants` = what the constructor sets
+function respawn!(sys::ParticleSystem, type_field::Symbol, from_type, to_type, x1_min, shift; constants...)
+    ff = Int32[sys.fields[k][1] for (k, _) in constants]
+    fv = Float64[v for (_, v) in constants]
+    added = Ref{Int64}(0)
+    check(ccall((:sp_respawn, LIB), Int32,
+                (Ptr{Cvoid}, Int32, Float64, Float64, Float64, Float64, Ptr{Int32}, Ptr{Float64}, Int32, Ref{Int64}),
+                sys.handle, sys.fields[type_field][1], Float64(from_type), Float64(to_type), Float64(x1_min), Float64(shift),
+                ff, fv, length(ff), added), sys.handle)
+    return added[]
+end
 
 # assemble_vector(sys, func), src/core.jl:175-182: the unary operator writes its last bound field
 function assemble_vector(sys::ParticleSystem, op::Operator)
