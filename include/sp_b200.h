@@ -197,10 +197,31 @@ enum {
     SP_OP_CYL_ACCELERATE = 54,
     /* unary. fields {x, v, a, type}; params {hdt, cyl1, coef}   if type == 0:
        f = (cyl1 - x[1], -x[2], 0);  v += hdt*(a + coef*f/((cyl1 - x[1])^2 + x[2]^2))   cylinder.jl:132-143 */
-    SP_OP_SET_INFLOW_SPEED = 55
+    SP_OP_SET_INFLOW_SPEED = 55,
     /* unary. fields {x, v, type}; params {inflow_type, s, U_max, chan_w}
        if type == inflow_type: v = (s*U_max*(1 - (2*x[2]/chan_w)^2))*VECX,  s = min(1, t/t_acc) from the host
        cylinder.jl:91-97 */
+
+    /* elastic solid with tensor-valued particle fields — examples/rod.jl.  A, H, B are 9-component fields holding a
+       RealMatrix in Julia's column-major order (component c = (i-1) + 3*(j-1) for M[i,j]); the script's own 2-D
+       outer/det/inv/trans/dev (rod.jl:44-85) only populate the in-plane block M[1:2,1:2], which is what is computed. */
+    SP_OP_ROD_FIND_A = 60,
+    /* binary. fields {x, X, A, H}; params {kernel, h}   ker = w(h,r):
+       A_p += -ker*outer(X_pq, x_pq);  H_p += -ker*outer(x_pq, x_pq)              rod.jl:128-134 */
+    SP_OP_ROD_FIND_B = 61,
+    /* unary. fields {A, H, B}; params {m, c_l, c_s}   Hi = inv(H); A = A*Hi; At = trans(A); G = At*A;
+       P = c_l^2*(det(A) - 1);  B = m*(P*inv(At) + c_s^2*A*dev(G))*Hi              rod.jl:136-143 */
+    SP_OP_ROD_FIND_F = 62,
+    /* binary. fields {x, v, X, A, B, f}; params {kernel, h, two_m_vol, nu}        rod.jl:145-160
+       f_p += -ker*(A_p'*(B_p*x_pq)) - ker*(A_q'*(B_q*x_pq)) + eta-correction terms + (two_m_vol*rDker*nu)*v_pq */
+    SP_OP_ROD_PULL = 63,
+    /* unary. fields {X, f}; params {X1_min, fy}   if X[1] > X1_min: f += (0, fy, 0)      rod.jl:162-166 */
+    SP_OP_ROD_UPDATE_V = 64,
+    /* unary. fields {v, f, X}; params {hdt, m, X1_clamp}   v += hdt*f/m;  if X[1] < X1_clamp: v = 0   rod.jl:168-174 */
+    SP_OP_ROD_UPDATE_X = 65,
+    /* unary. fields {x, v, A, H, f, e}; params {dt}   x += dt*v;  H = A = 0; f = 0; e = 0      rod.jl:176-183 */
+    SP_OP_ROD_FIND_E = 66
+    /* binary. fields {x, X, A, e}; params {h}   eta = inv(A_p)*X_pq - x_pq;  e_p += dot(eta, eta)   rod.jl:185-188 */
 };
 
 /* sp_apply flags */
@@ -224,9 +245,12 @@ enum {
     /* fields {f}; out[ncomp] plain sum of every component */
     SP_RED_ENERGY_ISPH = 5,
     /* fields {x, v}; params {m, gx, gy, gz}; out[1]   collapse_dry_implicit.jl:173-177 */
-    SP_RED_FORCE_ON_TYPE = 6
+    SP_RED_FORCE_ON_TYPE = 6,
     /* fields {a, m, type}; params {type_sel}; out[3] = sum of m*a over the particles with type == type_sel
        cylinder.jl:158-159 (calculate_force over the obstacle particles) */
+    SP_RED_ENERGY_ROD = 7
+    /* fields {v, A}; params {m, c_s, c_l}; out[1]   sum of 0.5 m v.v + 0.25 m c_s^2 |dev(A'A)|_F^2
+       + m c_l^2 (d - 1 - log d), d = |det A|                                       rod.jl:190-199 */
 };
 
 /* point sums:  out[k] = sum_q func(q, |x_k - q.x|)  over !(r > h), no self exclusion (core.jl:240-260) */

@@ -163,6 +163,15 @@ move_types(dt, type_a, type_b; x = :x, v = :v, a = :a, type = :type) = Operator(
 cyl_accelerate(hdt, cyl1, U_max; x = :x, v = :v, a = :a, type = :type) = Operator(54, [x, v, a, type], [hdt, cyl1, 0.3 * U_max^2])
 set_inflow_speed(t, t_acc, U_max, chan_w; inflow_type = 1.0, x = :x, v = :v, type = :type) =
     Operator(55, [x, v, type], [inflow_type, min(1.0, t / t_acc), U_max, chan_w])
+# examples/rod.jl:128-188 (A, H, B are 9-component RealMatrix fields)
+rod_find_A(kernel, h; x = :x, X = :X, A = :A, H = :H) = Operator(60, [x, X, A, H], [KERNELS[kernel], h])
+rod_find_B(m, c_l, c_s; A = :A, H = :H, B = :B) = Operator(61, [A, H, B], [m, c_l, c_s])
+rod_find_f(kernel, h, m, vol, nu; x = :x, v = :v, X = :X, A = :A, B = :B, f = :f) =
+    Operator(62, [x, v, X, A, B, f], [KERNELS[kernel], h, 2 * m * vol, nu])
+rod_pull(X1_min, fy; X = :X, f = :f) = Operator(63, [X, f], [X1_min, fy])
+rod_update_v(hdt, m, X1_clamp; v = :v, f = :f, X = :X) = Operator(64, [v, f, X], [hdt, m, X1_clamp])
+rod_update_x(dt; x = :x, v = :v, A = :A, H = :H, f = :f, e = :e) = Operator(65, [x, v, A, H, f, e], [dt])
+rod_find_e(h; x = :x, X = :X, A = :A, e = :e) = Operator(66, [x, X, A, e], [h])
 end # module Operators
 
 # add_new_particles!, examples/cylinder.jl:145-156: particles of `from_type` with x[1] >= x1_min become `to_type`, a new

@@ -15,7 +15,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_build", "libsp_oracle.so")
+LIB_PATH_WIDE = os.path.join(_HERE, "_build", "libsp_oracle_wide.so")  # 48-slot particle record (rod.jl)
 _lib = None
+_lib_wide = None
 
 _p, _i32, _i64, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
 _pi32, _pi64, _pf64 = C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_double)
@@ -24,8 +26,8 @@ _pi32, _pi64, _pf64 = C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "sp_oracle.cpp")
     hdr = os.path.join(os.path.dirname(_HERE), "include", "sp_b200.h")
-    if (not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= os.path.getmtime(src)
-            and os.path.getmtime(LIB_PATH) >= os.path.getmtime(hdr)):
+    if not force and all(os.path.exists(q) and os.path.getmtime(q) >= os.path.getmtime(src)
+                         and os.path.getmtime(q) >= os.path.getmtime(hdr) for q in (LIB_PATH, LIB_PATH_WIDE)):
         return LIB_PATH
     r = subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), capture_output=True, text=True)
     if r.returncode != 0:
@@ -33,12 +35,14 @@ def build(force: bool = False) -> str:
     return LIB_PATH
 
 
-def load():
-    global _lib
-    if _lib is not None:
+def load(wide: bool = False):
+    global _lib, _lib_wide
+    if wide and _lib_wide is not None:
+        return _lib_wide
+    if not wide and _lib is not None:
         return _lib
     build()
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(LIB_PATH_WIDE if wide else LIB_PATH)
     sig = {
         "so_create": (_p, [_pf64, _pf64, _f64]),
         "so_destroy": (None, [_p]),
@@ -70,7 +74,10 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    _lib = lib
+    if wide:
+        _lib_wide = lib
+    else:
+        _lib = lib
     return lib
 
 
@@ -95,7 +102,7 @@ FILL_OP = 10  # SP_OP_FILL takes {slot, ncomp} on the oracle side
 
 class OracleSystem:
     def __init__(self, particle_fields: Mapping[str, int], domain, h: float, threads: int | None = None):
-        self._lib = load()
+        self._lib = load(wide=3 + sum(int(nc) for nm, nc in particle_fields.items() if nm != "x") > 20)
         box = domain.boundarybox() if hasattr(domain, "boundarybox") else domain
         lo = (C.c_double * 3)(*[float(v) for v in box.lo])
         hi = (C.c_double * 3)(*[float(v) for v in box.hi])

@@ -38,7 +38,11 @@
 
 #include "../include/sp_b200.h"  // operator / kernel ids only
 
+// Float64 slots per particle record.  The default (20 = 160 B) is what bench.py's cpu_baseline runs on and fits every
+// scalar/vector example; oracle/Makefile also builds a wide variant (-DNSLOT=48) for the tensor-field example rod.jl.
+#ifndef NSLOT
 #define NSLOT 20
+#endif
 
 namespace {
 
@@ -362,6 +366,40 @@ inline double julia_pow4(double x) {
     double x4 = x2 * x2, lo4 = std::fma(x2, x2, -x4);
     lo4 += err;
     return (std::isfinite(x4) && std::isfinite(lo4)) ? x4 + lo4 : x4;
+}
+
+// ---- examples/rod.jl:44-85: the script's own 2-D matrix helpers.  A RealMatrix field occupies 9 slots in Julia's
+// column-major order (slot c = (i-1) + 3*(j-1)); rod.jl's outer/inv/trans/dev only ever populate M[1:2,1:2]
+// (dev also sets M[3,3], which every product here multiplies by a zero), so the in-plane block is what is computed.
+struct M2 {
+    double a11, a21, a12, a22;
+};
+inline M2 m2_load(const double* f) { return M2{f[0], f[1], f[3], f[4]}; }
+inline void m2_store(double* f, const M2& a) {
+    f[0] = a.a11; f[1] = a.a21; f[3] = a.a12; f[4] = a.a22;
+    f[2] = f[5] = f[6] = f[7] = f[8] = 0.0;
+}
+inline double m2_det(const M2& a) { return a.a11 * a.a22 - a.a12 * a.a21; }  // :52-54
+inline M2 m2_inv(const M2& a) {                                               // :56-63
+    double idet = 1.0 / m2_det(a);
+    return M2{+idet * a.a22, -idet * a.a21, -idet * a.a12, +idet * a.a11};
+}
+inline M2 m2_trans(const M2& a) { return M2{a.a11, a.a12, a.a21, a.a22}; }  // :65-71
+inline M2 m2_mul(const M2& a, const M2& b) {  // SMatrix product restricted to the block (third terms are 0*0)
+    return M2{a.a11 * b.a11 + a.a12 * b.a21, a.a21 * b.a11 + a.a22 * b.a21, a.a11 * b.a12 + a.a12 * b.a22,
+              a.a21 * b.a12 + a.a22 * b.a22};
+}
+inline void m2_vec(const M2& a, const double* x, double* y) {
+    y[0] = a.a11 * x[0] + a.a12 * x[1];
+    y[1] = a.a21 * x[0] + a.a22 * x[1];
+}
+inline M2 m2_scale(double c, const M2& a) { return M2{c * a.a11, c * a.a21, c * a.a12, c * a.a22}; }
+inline M2 m2_add(const M2& a, const M2& b) { return M2{a.a11 + b.a11, a.a21 + b.a21, a.a12 + b.a12, a.a22 + b.a22}; }
+// dev :73-80; lam_out receives lambda so that the caller can form the [3,3] entry 1 - lambda
+inline M2 m2_dev(const M2& g, double* lam_out) {
+    double lam = 1.0 / 3.0 * (g.a11 + g.a22 + 1.0);
+    if (lam_out) *lam_out = lam;
+    return M2{g.a11 - lam, g.a21, g.a12, g.a22 - lam};
 }
 
 // apply!, core.jl:151-161, specialised to the registered operators (the example closures).
@@ -694,6 +732,122 @@ int apply_op(OSys& s, int op, const int32_t* F, int nf, const double* P, int np,
                     p.f[ov + 1] = v1 * 0.0;
                     p.f[ov + 2] = v1 * 0.0;
                 }
+            });
+            return SP_OK;
+        }
+        case SP_OP_ROD_FIND_A: {  // rod.jl:128-134
+            if (!need(4, 2)) return SP_ERR_INVALID;
+            const int oX = F[1], oA = F[2], oH = F[3];
+            kfn w = pick_w((int)P[0]);
+            const double h = P[1];
+            if (!w) return SP_ERR_INVALID;
+            apply_binary(s, [=](Particle& p, const Particle& q, const double* xpq, double r) {
+                double ker = w(h, r);
+                double Xpq[2] = {p.f[oX] - q.f[oX], p.f[oX + 1] - q.f[oX + 1]};
+                // outer(x, y)[i,j] = x[i]*y[j]  (:44-50)
+                p.f[oA + 0] += -ker * (Xpq[0] * xpq[0]);
+                p.f[oA + 1] += -ker * (Xpq[1] * xpq[0]);
+                p.f[oA + 3] += -ker * (Xpq[0] * xpq[1]);
+                p.f[oA + 4] += -ker * (Xpq[1] * xpq[1]);
+                p.f[oH + 0] += -ker * (xpq[0] * xpq[0]);
+                p.f[oH + 1] += -ker * (xpq[1] * xpq[0]);
+                p.f[oH + 3] += -ker * (xpq[0] * xpq[1]);
+                p.f[oH + 4] += -ker * (xpq[1] * xpq[1]);
+            });
+            return SP_OK;
+        }
+        case SP_OP_ROD_FIND_B: {  // rod.jl:136-143
+            if (!need(3, 3)) return SP_ERR_INVALID;
+            const int oA = F[0], oH = F[1], oB = F[2];
+            const double m = P[0], c_l = P[1], c_s = P[2];
+            apply_unary(s, [=](Particle& p) {
+                M2 Hi = m2_inv(m2_load(p.f + oH));
+                M2 A = m2_mul(m2_load(p.f + oA), Hi);
+                m2_store(p.f + oA, A);
+                M2 At = m2_trans(A);
+                M2 G = m2_mul(At, A);
+                double Pr = (c_l * c_l) * (m2_det(A) - 1.0);
+                M2 B = m2_mul(m2_scale(m, m2_add(m2_scale(Pr, m2_inv(At)), m2_mul(m2_scale(c_s * c_s, A), m2_dev(G, nullptr)))), Hi);
+                m2_store(p.f + oB, B);
+            });
+            return SP_OK;
+        }
+        case SP_OP_ROD_FIND_F: {  // rod.jl:145-160
+            if (!need(6, 4)) return SP_ERR_INVALID;
+            const int ov = F[1], oX = F[2], oA = F[3], oB = F[4], of = F[5];
+            kfn w = pick_w((int)P[0]), rDw = pick_rD((int)P[0]);
+            const double h = P[1], two_m_vol = P[2], nu = P[3];
+            if (!w || !rDw) return SP_ERR_INVALID;
+            apply_binary(s, [=](Particle& p, const Particle& q, const double* xpq, double r) {
+                double ker = w(h, r), rDker = rDw(h, r);
+                double Xpq[2] = {p.f[oX] - q.f[oX], p.f[oX + 1] - q.f[oX + 1]};
+                M2 Ap = m2_load(p.f + oA), Bp = m2_load(p.f + oB), Aq = m2_load(q.f + oA), Bq = m2_load(q.f + oB);
+                double y[2], z[2];
+                m2_vec(Bp, xpq, y);
+                m2_vec(m2_trans(Ap), y, z);
+                p.f[of] += -ker * z[0];
+                p.f[of + 1] += -ker * z[1];
+                m2_vec(Bq, xpq, y);
+                m2_vec(m2_trans(Aq), y, z);
+                p.f[of] += -ker * z[0];
+                p.f[of + 1] += -ker * z[1];
+                // "eta" correction
+                double ax[2], wv[2], kpq[2], kqp[2];
+                m2_vec(Ap, xpq, ax);
+                wv[0] = Xpq[0] - ax[0]; wv[1] = Xpq[1] - ax[1];
+                m2_vec(m2_trans(Bp), wv, kpq);
+                m2_vec(Aq, xpq, ax);
+                wv[0] = Xpq[0] - ax[0]; wv[1] = Xpq[1] - ax[1];
+                m2_vec(m2_trans(Bq), wv, kqp);
+                kqp[0] = -kqp[0]; kqp[1] = -kqp[1];
+                double dp = xpq[0] * kpq[0] + xpq[1] * kpq[1], dq = xpq[0] * kqp[0] + xpq[1] * kqp[1];
+                for (int c = 0; c < 2; c++) p.f[of + c] += rDker * dp * xpq[c] + ker * kpq[c];
+                for (int c = 0; c < 2; c++) p.f[of + c] -= rDker * dq * xpq[c] + ker * kqp[c];
+                // artificial viscosity
+                double visc = two_m_vol * rDker * nu;
+                for (int c = 0; c < 3; c++) p.f[of + c] += visc * (p.f[ov + c] - q.f[ov + c]);
+            });
+            return SP_OK;
+        }
+        case SP_OP_ROD_PULL: {  // rod.jl:162-166
+            if (!need(2, 2)) return SP_ERR_INVALID;
+            const int oX = F[0], of = F[1];
+            const double X1_min = P[0], fy = P[1];
+            apply_unary(s, [=](Particle& p) {
+                if (p.f[oX] > X1_min) p.f[of + 1] += fy;
+            });
+            return SP_OK;
+        }
+        case SP_OP_ROD_UPDATE_V: {  // rod.jl:168-174
+            if (!need(3, 3)) return SP_ERR_INVALID;
+            const int ov = F[0], of = F[1], oX = F[2];
+            const double hdt = P[0], m = P[1], X1_clamp = P[2];
+            apply_unary(s, [=](Particle& p) {
+                for (int c = 0; c < 3; c++) p.f[ov + c] += hdt * p.f[of + c] / m;
+                if (p.f[oX] < X1_clamp) p.f[ov] = p.f[ov + 1] = p.f[ov + 2] = 0.0;
+            });
+            return SP_OK;
+        }
+        case SP_OP_ROD_UPDATE_X: {  // rod.jl:176-183
+            if (!need(6, 1)) return SP_ERR_INVALID;
+            const int ox = F[0], ov = F[1], oA = F[2], oH = F[3], of = F[4], oe = F[5];
+            const double dt = P[0];
+            apply_unary(s, [=](Particle& p) {
+                for (int c = 0; c < 3; c++) p.f[ox + c] += dt * p.f[ov + c];
+                for (int c = 0; c < 9; c++) p.f[oH + c] = p.f[oA + c] = 0.0;
+                p.f[of] = p.f[of + 1] = p.f[of + 2] = 0.0;
+                p.f[oe] = 0.0;
+            });
+            return SP_OK;
+        }
+        case SP_OP_ROD_FIND_E: {  // rod.jl:185-188
+            if (!need(4, 1)) return SP_ERR_INVALID;
+            const int oX = F[1], oA = F[2], oe = F[3];
+            apply_binary(s, [=](Particle& p, const Particle& q, const double* xpq, double) {
+                double Xpq[2] = {p.f[oX] - q.f[oX], p.f[oX + 1] - q.f[oX + 1]}, y[2];
+                m2_vec(m2_inv(m2_load(p.f + oA)), Xpq, y);
+                double eta[3] = {y[0] - xpq[0], y[1] - xpq[1], 0.0 - xpq[2]};
+                p.f[oe] += dot3(eta, eta);
             });
             return SP_OK;
         }
@@ -1077,6 +1231,27 @@ int so_reduce(void* hnd, int red, const int32_t* F, int nf, const double* P, int
             out[0] = acc[0];
             out[1] = acc[1];
             out[2] = acc[2];
+            return SP_OK;
+        }
+        case SP_RED_ENERGY_ROD: {  // rod.jl:190-199 (particle_energy summed as in :213)
+            if (nf != 2 || np != 3) return SP_ERR_INVALID;
+            const int ov = F[0], oA = F[1];
+            const double m = P[0], c_s = P[1], c_l = P[2];
+            double E = 0.0;
+            for (const Particle& p : s.particles) {
+                M2 A = m2_load(p.f + oA);
+                double d = std::fabs(m2_det(A));
+                double lam;
+                M2 G0 = m2_dev(m2_mul(m2_trans(A), A), &lam);
+                double g33 = 1.0 - lam;
+                // LinearAlgebra.norm(G0, 2) of an SMatrix: sqrt of the sum of squares in linear index order
+                double n2 = std::sqrt(G0.a11 * G0.a11 + G0.a21 * G0.a21 + G0.a12 * G0.a12 + G0.a22 * G0.a22 + g33 * g33);
+                double E_kinet = 0.5 * m * dot3(p.f + ov, p.f + ov);
+                double E_shear = 0.25 * m * (c_s * c_s) * (n2 * n2);
+                double E_press = m * (c_l * c_l) * (d - 1.0 - std::log(d));
+                E += E_kinet + E_shear + E_press;
+            }
+            out[0] = E;
             return SP_OK;
         }
     }

@@ -15,6 +15,7 @@ order as the script.  A Case is backend-agnostic: ``case.make(ParticleSystem)`` 
   collapse_symplectic    examples/collapse_symplectic.jl     reversible fixed-point Verlet, Lennard-Jones walls
   kepler_vortex          examples/Kepler_vortex.jl           fluid ring in central gravity, same integrator
   cylinder               examples/cylinder.jl                channel flow past a cylinder, inflow buffer, per-particle mass
+  rod                    examples/rod.jl                     elastic rod, tensor-valued particle fields
   lattice_box            synthetic S1 block of SURVEY §8(d)  jittered cubic lattice, all fluid
 """
 from __future__ import annotations
@@ -572,6 +573,67 @@ def cylinder_force_coefficients(sys, consts) -> np.ndarray:
     F = sys.reduce(K["SP_RED_FORCE_ON_TYPE"], ("a", "m", "type"), (consts["OBSTACLE"],), nout=3)
     U_mean = 2 / 3 * consts["U_max"]
     return 2.0 * np.asarray(F) / (consts["L_char"] * U_mean ** 2)
+
+
+# --------------------------------------------------------------------------- rod.jl
+def rod(dr: float = None) -> Case:
+    """examples/rod.jl:17-41 (constants), :101-120 (make_geometry, force_computation!), :207-229 (Verlet loop): a
+    clamped elastic rod pulled at its free end for pull_time, then left to vibrate.  A, H, B are RealMatrix fields
+    (9 components).  The step index k (t = k*dt, :208) is kept on the system object as ``step_index``."""
+    L, W, r_free = 5.0, 0.5, 1.0
+    pull_force, pull_time = 1.0, 0.5
+    c_l, c_s = 20.0, 200.0
+    c_0 = math.sqrt(c_l ** 2 + 4 / 3 * c_s ** 2)
+    rho0 = 1.0
+    nu = 1.0e-4
+    if dr is None:
+        dr = W / 16
+    h = 2.5 * dr
+    vol = dr ** 2
+    m = rho0 * vol
+    dt = 0.1 * h / c_0
+    grid = geo.Hexagrid(dr)
+    body = geo.Rectangle(0.0, 0.0, L, W)
+    domain = geo.Rectangle(-r_free, -r_free, L + r_free, W + r_free)
+    x = geo.covering(grid, body)
+    fields = {"v": 3, "f": 3, "X": 3, "A": 9, "H": 9, "B": 9, "e": 1}
+    init = {"x": x, "X": x.copy()}
+    o_A = ops.rod_find_A("wendland2", h)
+    o_B = ops.rod_find_B(m, c_l, c_s)
+    o_f = ops.rod_find_f("wendland2", h, m, vol, nu)
+    o_pull = ops.rod_pull(L - h, (vol * pull_force) / (h * W))
+    o_v = ops.rod_update_v(0.5 * dt, m, h)
+    o_x = ops.rod_update_x(dt)
+
+    def force_computation(sys, t):  # :112-120
+        sys.apply(o_A)
+        sys.apply(o_B)
+        sys.apply(o_f)
+        if t < pull_time:
+            sys.apply(o_pull)
+
+    def prologue(sys):  # :107-108
+        sys.create_cell_list()
+        force_computation(sys, 0.0)
+
+    def step(sys):  # :207-208, :222-227
+        k = getattr(sys, "step_index", 0)
+        sys.step_index = k + 1
+        t = k * dt
+        sys.apply(o_v)
+        sys.apply(o_x)
+        sys.create_cell_list()
+        force_computation(sys, t)
+        sys.apply(o_v)
+
+    return Case("rod", fields, domain, h, init, step, prologue,
+                consts=dict(dr=dr, h=h, m=m, vol=vol, dt=dt, c_l=c_l, c_s=c_s, nu=nu, L=L, W=W, pull_time=pull_time),
+                dim=2)
+
+
+def rod_energy(sys, consts) -> float:
+    """sum(p -> particle_energy(p), sys.particles), rod.jl:190-199, :213."""
+    return float(sys.reduce(K["SP_RED_ENERGY_ROD"], ("v", "A"), (consts["m"], consts["c_s"], consts["c_l"]))[0])
 
 
 # --------------------------------------------------------------------------- collapse_dry_implicit.jl

@@ -566,6 +566,170 @@ struct OpCylInternalForce {
     }
 };
 
+// ---------------------------------------------------------------- examples/rod.jl (tensor-valued fields)
+// In-plane block of a RealMatrix field (9 planes, Julia's column-major order: plane c = (i-1) + 3*(j-1)); rod.jl's own
+// 2-D outer/det/inv/trans/dev (:44-85) populate nothing else.
+struct SpM2 {
+    double a11, a21, a12, a22;
+};
+__device__ __forceinline__ SpM2 sp_m2_load(const double* f, long long cap, int i) {
+    return SpM2{f[i], f[cap + i], f[3 * cap + i], f[4 * cap + i]};
+}
+__device__ __forceinline__ void sp_m2_store(double* f, long long cap, int i, const SpM2& a) {
+    f[i] = a.a11; f[cap + i] = a.a21; f[3 * cap + i] = a.a12; f[4 * cap + i] = a.a22;
+    f[2 * cap + i] = 0.0; f[5 * cap + i] = 0.0; f[6 * cap + i] = 0.0; f[7 * cap + i] = 0.0; f[8 * cap + i] = 0.0;
+}
+__device__ __forceinline__ double sp_m2_det(const SpM2& a) { return a.a11 * a.a22 - a.a12 * a.a21; }
+__device__ __forceinline__ SpM2 sp_m2_inv(const SpM2& a) {
+    const double idet = 1.0 / sp_m2_det(a);
+    return SpM2{idet * a.a22, -idet * a.a21, -idet * a.a12, idet * a.a11};
+}
+__device__ __forceinline__ SpM2 sp_m2_trans(const SpM2& a) { return SpM2{a.a11, a.a12, a.a21, a.a22}; }
+__device__ __forceinline__ SpM2 sp_m2_mul(const SpM2& a, const SpM2& b) {
+    return SpM2{a.a11 * b.a11 + a.a12 * b.a21, a.a21 * b.a11 + a.a22 * b.a21, a.a11 * b.a12 + a.a12 * b.a22,
+                a.a21 * b.a12 + a.a22 * b.a22};
+}
+__device__ __forceinline__ SpM2 sp_m2_scale(double c, const SpM2& a) { return SpM2{c * a.a11, c * a.a21, c * a.a12, c * a.a22}; }
+__device__ __forceinline__ SpM2 sp_m2_add(const SpM2& a, const SpM2& b) {
+    return SpM2{a.a11 + b.a11, a.a21 + b.a21, a.a12 + b.a12, a.a22 + b.a22};
+}
+__device__ __forceinline__ SpM2 sp_m2_dev(const SpM2& g, double* lam_out) {
+    const double lam = 1.0 / 3.0 * (g.a11 + g.a22 + 1.0);
+    if (lam_out) *lam_out = lam;
+    return SpM2{g.a11 - lam, g.a21, g.a12, g.a22 - lam};
+}
+
+// find_A!  rod.jl:128-134
+template <class K>
+struct OpRodFindA {
+    static constexpr int NQ = 2;  // X1, X2
+    struct Params {
+        const double* qp[NQ];
+        double *A, *H;
+        long long cap;
+        SpKC kc;
+    };
+    struct PS {
+        double X1, X2;
+    };
+    struct Acc {
+        double a11, a21, a12, a22, h11, h21, h12, h22;
+    };
+    __device__ static __forceinline__ bool active(const Params&, int) { return true; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
+        p.X1 = P.qp[0][i]; p.X2 = P.qp[1][i];
+        const SpM2 A = sp_m2_load(P.A, P.cap, i), H = sp_m2_load(P.H, P.cap, i);
+        a.a11 = A.a11; a.a21 = A.a21; a.a12 = A.a12; a.a22 = A.a22;
+        a.h11 = H.a11; a.h21 = H.a21; a.h12 = H.a12; a.h22 = H.a22;
+    }
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, const Q& q, double dx, double dy, double,
+                                                double r, Acc& a) {
+        const double nk = -K::w(P.kc, r);
+        const double X1 = p.X1 - q(0), X2 = p.X2 - q(1);
+        a.a11 += nk * (X1 * dx); a.a21 += nk * (X2 * dx); a.a12 += nk * (X1 * dy); a.a22 += nk * (X2 * dy);
+        a.h11 += nk * (dx * dx); a.h21 += nk * (dy * dx); a.h12 += nk * (dx * dy); a.h22 += nk * (dy * dy);
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) {
+        sp_m2_store(P.A, P.cap, i, SpM2{a.a11, a.a21, a.a12, a.a22});
+        sp_m2_store(P.H, P.cap, i, SpM2{a.h11, a.h21, a.h12, a.h22});
+    }
+};
+
+// find_f!  rod.jl:145-160
+template <class K>
+struct OpRodFindF {
+    static constexpr int NQ = 13;  // A11 A21 A12 A22 | B11 B21 B12 B22 | X1 X2 | vx vy vz
+    struct Params {
+        const double* qp[NQ];
+        WV3 f;
+        double two_m_vol, nu;
+        SpKC kc;
+    };
+    struct PS {
+        SpM2 A, B;
+        double X1, X2, vx, vy, vz;
+    };
+    struct Acc {
+        double x, y, z;
+    };
+    __device__ static __forceinline__ bool active(const Params&, int) { return true; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
+        p.A = SpM2{P.qp[0][i], P.qp[1][i], P.qp[2][i], P.qp[3][i]};
+        p.B = SpM2{P.qp[4][i], P.qp[5][i], P.qp[6][i], P.qp[7][i]};
+        p.X1 = P.qp[8][i]; p.X2 = P.qp[9][i];
+        p.vx = P.qp[10][i]; p.vy = P.qp[11][i]; p.vz = P.qp[12][i];
+        a.x = P.f.x[i]; a.y = P.f.y[i]; a.z = P.f.z[i];
+    }
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, const Q& q, double dx, double dy, double,
+                                                double r, Acc& a) {
+        const double ker = K::w(P.kc, r), rDker = K::rD(P.kc, r);
+        const SpM2 Aq{q(0), q(1), q(2), q(3)}, Bq{q(4), q(5), q(6), q(7)};
+        const double X1 = p.X1 - q(8), X2 = p.X2 - q(9);
+        // -ker*(A'*(B*x_pq)) for p and for q
+        double y1 = p.B.a11 * dx + p.B.a12 * dy, y2 = p.B.a21 * dx + p.B.a22 * dy;
+        a.x += -ker * (p.A.a11 * y1 + p.A.a21 * y2);
+        a.y += -ker * (p.A.a12 * y1 + p.A.a22 * y2);
+        y1 = Bq.a11 * dx + Bq.a12 * dy; y2 = Bq.a21 * dx + Bq.a22 * dy;
+        a.x += -ker * (Aq.a11 * y1 + Aq.a21 * y2);
+        a.y += -ker * (Aq.a12 * y1 + Aq.a22 * y2);
+        // "eta" correction: k_pq = +B_p'*(X_pq - A_p*x_pq), k_qp = -B_q'*(X_pq - A_q*x_pq)
+        double w1 = X1 - (p.A.a11 * dx + p.A.a12 * dy), w2 = X2 - (p.A.a21 * dx + p.A.a22 * dy);
+        const double kp1 = p.B.a11 * w1 + p.B.a21 * w2, kp2 = p.B.a12 * w1 + p.B.a22 * w2;
+        w1 = X1 - (Aq.a11 * dx + Aq.a12 * dy); w2 = X2 - (Aq.a21 * dx + Aq.a22 * dy);
+        const double kq1 = -(Bq.a11 * w1 + Bq.a21 * w2), kq2 = -(Bq.a12 * w1 + Bq.a22 * w2);
+        const double dp = dx * kp1 + dy * kp2, dq = dx * kq1 + dy * kq2;
+        a.x += rDker * dp * dx + ker * kp1;
+        a.y += rDker * dp * dy + ker * kp2;
+        a.x -= rDker * dq * dx + ker * kq1;
+        a.y -= rDker * dq * dy + ker * kq2;
+        // artificial viscosity
+        const double visc = P.two_m_vol * rDker * P.nu;
+        a.x += visc * (p.vx - q(10)); a.y += visc * (p.vy - q(11)); a.z += visc * (p.vz - q(12));
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) {
+        P.f.x[i] = a.x; P.f.y[i] = a.y; P.f.z[i] = a.z;
+    }
+};
+
+// find_e!  rod.jl:185-188
+template <class K>
+struct OpRodFindE {
+    static constexpr int NQ = 2;  // X1, X2
+    struct Params {
+        const double* qp[NQ];
+        const double* A;
+        double* e;
+        long long cap;
+        SpKC kc;
+    };
+    struct PS {
+        double X1, X2;
+        SpM2 Ai;  // inv(A_p): the closure recomputes it for every pair, same value
+    };
+    struct Acc {
+        double e;
+    };
+    __device__ static __forceinline__ bool active(const Params&, int) { return true; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
+        p.X1 = P.qp[0][i]; p.X2 = P.qp[1][i];
+        p.Ai = sp_m2_inv(sp_m2_load(P.A, P.cap, i));
+        a.e = P.e[i];
+    }
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params&, const PS& p, const Q& q, double dx, double dy, double dz,
+                                                double, Acc& a) {
+        const double X1 = p.X1 - q(0), X2 = p.X2 - q(1);
+        const double e1 = (p.Ai.a11 * X1 + p.Ai.a12 * X2) - dx, e2 = (p.Ai.a21 * X1 + p.Ai.a22 * X2) - dy, e3 = 0.0 - dz;
+        a.e += e1 * e1 + e2 * e2 + e3 * e3;
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) { P.e[i] = a.e; }
+};
+
 // ---------------------------------------------------------------- tests/test_collision_2d.jl
 // find_rho! / find_rho0!  :63-69, used with self=true
 template <class K>
@@ -1028,6 +1192,71 @@ struct USetInflowSpeed {
             const double v1 = __dmul_rn(__dmul_rn(P.s, P.U_max), __dsub_rn(1.0, __dmul_rn(q, q)));
             P.v.x[i] = v1; P.v.y[i] = v1 * 0.0; P.v.z[i] = v1 * 0.0;
         }
+    }
+};
+// find_B!  rod.jl:136-143
+struct URodFindB {
+    struct Params {
+        double *A, *H, *B;
+        long long cap;
+        double m, cl2, cs2;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        const SpM2 Hi = sp_m2_inv(sp_m2_load(P.H, P.cap, i));
+        const SpM2 A = sp_m2_mul(sp_m2_load(P.A, P.cap, i), Hi);
+        sp_m2_store(P.A, P.cap, i, A);
+        const SpM2 At = sp_m2_trans(A);
+        const SpM2 G = sp_m2_mul(At, A);
+        const double Pr = P.cl2 * (sp_m2_det(A) - 1.0);
+        const SpM2 M = sp_m2_add(sp_m2_scale(Pr, sp_m2_inv(At)), sp_m2_mul(sp_m2_scale(P.cs2, A), sp_m2_dev(G, nullptr)));
+        sp_m2_store(P.B, P.cap, i, sp_m2_mul(sp_m2_scale(P.m, M), Hi));
+    }
+};
+// pull!  rod.jl:162-166
+struct URodPull {
+    struct Params {
+        const double* X1;
+        double* fy;
+        double X1_min, add;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        if (P.X1[i] > P.X1_min) P.fy[i] += P.add;
+    }
+};
+// update_v!  rod.jl:168-174
+struct URodUpdateV {
+    struct Params {
+        WV3 v;
+        RV3 f;
+        const double* X1;
+        double hdt, m, X1_clamp;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        double vx = P.v.x[i] + P.hdt * P.f.x[i] / P.m, vy = P.v.y[i] + P.hdt * P.f.y[i] / P.m,
+               vz = P.v.z[i] + P.hdt * P.f.z[i] / P.m;
+        if (P.X1[i] < P.X1_clamp) vx = vy = vz = 0.0;  // Dirichlet boundary condition
+        P.v.x[i] = vx; P.v.y[i] = vy; P.v.z[i] = vz;
+    }
+};
+// update_x!  rod.jl:176-183
+struct URodUpdateX {
+    struct Params {
+        WV3 x;
+        RV3 v;
+        double *A, *H;
+        WV3 f;
+        double* e;
+        long long cap;
+        double dt;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        P.x.x[i] += P.dt * P.v.x[i]; P.x.y[i] += P.dt * P.v.y[i]; P.x.z[i] += P.dt * P.v.z[i];
+        for (int c = 0; c < 9; c++) {
+            P.A[(size_t)c * P.cap + i] = 0.0;
+            P.H[(size_t)c * P.cap + i] = 0.0;
+        }
+        P.f.x[i] = 0.0; P.f.y[i] = 0.0; P.f.z[i] = 0.0;
+        P.e[i] = 0.0;
     }
 };
 // find_pressure!  test_collision_2d.jl:71-73

@@ -51,6 +51,18 @@ __device__ __forceinline__ void red_map(const RedParams& R, long long i, double 
         double m = R.p[0];
         double vx = V[i], vy = V[cap + i], vz = V[2 * cap + i];
         v[0] = 0.5 * m * (vx * vx + vy * vy + vz * vz) - m * (R.p[1] * X[i] + R.p[2] * X[cap + i] + R.p[3] * X[2 * cap + i]);
+    } else if (RED == SP_RED_ENERGY_ROD) {  // fields {v, A}; params {m, c_s, c_l}
+        const double* V = R.f[0];
+        const double m = R.p[0], c_s = R.p[1], c_l = R.p[2];
+        const SpM2 A = sp_m2_load(R.f[1], cap, (int)i);
+        const double d = fabs(sp_m2_det(A));
+        double lam;
+        const SpM2 G0 = sp_m2_dev(sp_m2_mul(sp_m2_trans(A), A), &lam);
+        const double g33 = 1.0 - lam;
+        const double n2 = sqrt(G0.a11 * G0.a11 + G0.a21 * G0.a21 + G0.a12 * G0.a12 + G0.a22 * G0.a22 + g33 * g33);
+        const double vx = V[i], vy = V[cap + i], vz = V[2 * cap + i];
+        v[0] = 0.5 * m * (vx * vx + vy * vy + vz * vz) + 0.25 * m * (c_s * c_s) * (n2 * n2) +
+               m * (c_l * c_l) * (d - 1.0 - log(d));
     } else if (RED == SP_RED_FORCE_ON_TYPE) {  // fields {a, m, type}; params {type_sel}
         if (R.f[2][i] == R.p[0]) {
             const double* A = R.f[0];
@@ -242,6 +254,11 @@ int32_t sp_reduce(sp_system* s, int32_t red, const int32_t* F, int32_t nf, const
             const int nc[] = {3, 3};
             if ((rc = bind(2, nc, 4))) return rc;
             return run_reduce<SP_RED_ENERGY_ISPH, false>(s, R, 1, out);
+        }
+        case SP_RED_ENERGY_ROD: {
+            const int nc[] = {3, 9};
+            if ((rc = bind(2, nc, 3))) return rc;
+            return run_reduce<SP_RED_ENERGY_ROD, false>(s, R, 1, out);
         }
         case SP_RED_FORCE_ON_TYPE: {
             const int nc[] = {3, 1, 1};

@@ -1823,6 +1823,76 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
             USetInflowSpeed::Params P{rv3(s, F[0]), wv3(s, F[1]), sc(s, F[2]), Pm[0], Pm[1], Pm[2], Pm[3]};
             return launch_unary<USetInflowSpeed>(s, P);
         }
+        case SP_OP_ROD_FIND_A: {
+            NEED(4, 2, 3, 3, 9, 9);
+            NEED_CELLS();
+            sp_wrote(s, F[2]);
+            sp_wrote(s, F[3]);
+            return dispatch_kernel<OpRodFindA>(s, (int)Pm[0], Pm[1], flags, [&](auto& P) {
+                P.qp[0] = sc(s, F[1]);
+                P.qp[1] = sc(s, F[1]) + s->cap;
+                P.A = sc(s, F[2]);
+                P.H = sc(s, F[3]);
+                P.cap = s->cap;
+            });
+        }
+        case SP_OP_ROD_FIND_B: {
+            NEED(3, 3, 9, 9, 9);
+            sp_wrote(s, F[0]);
+            sp_wrote(s, F[2]);
+            URodFindB::Params P{sc(s, F[0]), sc(s, F[1]), sc(s, F[2]), s->cap, Pm[0], Pm[1] * Pm[1], Pm[2] * Pm[2]};
+            return launch_unary<URodFindB>(s, P);
+        }
+        case SP_OP_ROD_FIND_F: {
+            NEED(6, 4, 3, 3, 3, 9, 9, 3);
+            NEED_CELLS();
+            sp_wrote(s, F[5]);
+            return dispatch_kernel<OpRodFindF>(s, (int)Pm[0], Pm[1], flags, [&](auto& P) {
+                const double *A = sc(s, F[3]), *B = sc(s, F[4]), *X = sc(s, F[2]);
+                const long long cap = s->cap;
+                P.qp[0] = A; P.qp[1] = A + cap; P.qp[2] = A + 3 * cap; P.qp[3] = A + 4 * cap;
+                P.qp[4] = B; P.qp[5] = B + cap; P.qp[6] = B + 3 * cap; P.qp[7] = B + 4 * cap;
+                P.qp[8] = X; P.qp[9] = X + cap;
+                set_v3(s, F[1], P.qp + 10);
+                P.f = wv3(s, F[5]);
+                P.two_m_vol = Pm[2];
+                P.nu = Pm[3];
+            });
+        }
+        case SP_OP_ROD_PULL: {
+            NEED(2, 2, 3, 3);
+            sp_wrote(s, F[1]);
+            URodPull::Params P{sc(s, F[0]), sc(s, F[1]) + s->cap, Pm[0], Pm[1]};
+            return launch_unary<URodPull>(s, P);
+        }
+        case SP_OP_ROD_UPDATE_V: {
+            NEED(3, 3, 3, 3, 3);
+            sp_wrote(s, F[0]);
+            URodUpdateV::Params P{wv3(s, F[0]), rv3(s, F[1]), sc(s, F[2]), Pm[0], Pm[1], Pm[2]};
+            return launch_unary<URodUpdateV>(s, P);
+        }
+        case SP_OP_ROD_UPDATE_X: {
+            NEED(6, 1, 3, 3, 9, 9, 3, 1);
+            sp_wrote(s, F[0]);
+            sp_zeroed(s, F[2]);
+            sp_zeroed(s, F[3]);
+            sp_zeroed(s, F[4]);
+            sp_zeroed(s, F[5]);
+            URodUpdateX::Params P{wv3(s, F[0]), rv3(s, F[1]), sc(s, F[2]), sc(s, F[3]), wv3(s, F[4]), sc(s, F[5]), s->cap, Pm[0]};
+            return launch_unary<URodUpdateX>(s, P);
+        }
+        case SP_OP_ROD_FIND_E: {
+            NEED(4, 1, 3, 3, 9, 1);
+            NEED_CELLS();
+            sp_wrote(s, F[3]);
+            return dispatch_kernel<OpRodFindE>(s, SP_KERNEL_WENDLAND2, Pm[0], flags, [&](auto& P) {
+                P.qp[0] = sc(s, F[1]);
+                P.qp[1] = sc(s, F[1]) + s->cap;
+                P.A = sc(s, F[2]);
+                P.e = sc(s, F[3]);
+                P.cap = s->cap;
+            });
+        }
     }
     return sp_fail(s, SP_ERR_INVALID, "unknown operator id");
 }

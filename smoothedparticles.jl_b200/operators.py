@@ -179,6 +179,42 @@ def set_inflow_speed(t, t_acc, U_max, chan_w, inflow_type=1.0, x="x", v="v", typ
                     "set_inflow_speed!")
 
 
+# ---- examples/rod.jl (elastic solid, tensor-valued fields A, H, B with 9 components each)
+def rod_find_A(kernel, h, x="x", X="X", A="A", H="H"):
+    """rod.jl:128-134: A += -w*outer(X_pq, x_pq); H += -w*outer(x_pq, x_pq)."""
+    return Operator(K["SP_OP_ROD_FIND_A"], (x, X, A, H), (_kid(kernel), h), True, "find_A!")
+
+
+def rod_find_B(m, c_l, c_s, A="A", H="H", B="B"):
+    """rod.jl:136-143: A = A*inv(H); B = m*(P*inv(A') + c_s^2*A*dev(A'A))*inv(H), P = c_l^2*(det A - 1)."""
+    return Operator(K["SP_OP_ROD_FIND_B"], (A, H, B), (m, c_l, c_s), False, "find_B!")
+
+
+def rod_find_f(kernel, h, m, vol, nu, x="x", v="v", X="X", A="A", B="B", f="f"):
+    """rod.jl:145-160: elastic force with the energy-conserving "eta" correction and artificial viscosity."""
+    return Operator(K["SP_OP_ROD_FIND_F"], (x, v, X, A, B, f), (_kid(kernel), h, 2 * m * vol, nu), True, "find_f!")
+
+
+def rod_pull(X1_min, fy, X="X", f="f"):
+    """rod.jl:162-166: the free end is pulled upwards."""
+    return Operator(K["SP_OP_ROD_PULL"], (X, f), (X1_min, fy), False, "pull!")
+
+
+def rod_update_v(hdt, m, X1_clamp, v="v", f="f", X="X"):
+    """rod.jl:168-174: v += hdt*f/m; the clamped end (X[1] < X1_clamp) stays at rest."""
+    return Operator(K["SP_OP_ROD_UPDATE_V"], (v, f, X), (hdt, m, X1_clamp), False, "update_v!")
+
+
+def rod_update_x(dt, x="x", v="v", A="A", H="H", f="f", e="e"):
+    """rod.jl:176-183: x += dt*v and the per-step accumulators are reset."""
+    return Operator(K["SP_OP_ROD_UPDATE_X"], (x, v, A, H, f, e), (dt,), False, "update_x!")
+
+
+def rod_find_e(h, x="x", X="X", A="A", e="e"):
+    """rod.jl:185-188: e += |inv(A_p)*X_pq - x_pq|^2."""
+    return Operator(K["SP_OP_ROD_FIND_E"], (x, X, A, e), (h,), True, "find_e!")
+
+
 # ---- examples/static_container.jl
 def sc_balance_of_mass(kernel, m, h, dt, x="x", v="v", rho="rho"):
     """static_container.jl:102-104: the density is integrated inside the pair loop."""
