@@ -266,6 +266,15 @@ class OracleSystem:
                                  C.byref(resid))
         return x, it, resid.value
 
+    def poisson_cg(self, A, b, P_out, reltol=None, abstol=0.0, maxiter=0):
+        """The reference's own path for ``A = assemble_matrix(sys, projection_matrix); P .= cg(A, b)``
+        (collapse_dry_implicit.jl:223-227): serial assembly of the COO triplets, then CG on them; same signature and
+        return value (iterations, residual norm) as ParticleSystem.poisson_cg so that Case.step runs on both."""
+        I, J, V = self.assemble_matrix(A)
+        x, it, resid = self.cg(I, J, V, self.get(b), reltol=reltol, abstol=abstol, maxiter=maxiter)
+        self.set(P_out, x)
+        return it, resid
+
     def coo_matvec(self, I, J, V, x):
         x = _f(x)
         y = np.empty_like(x)
