@@ -248,9 +248,13 @@ enum {
     SP_RED_FORCE_ON_TYPE = 6,
     /* fields {a, m, type}; params {type_sel}; out[3] = sum of m*a over the particles with type == type_sel
        cylinder.jl:158-159 (calculate_force over the obstacle particles) */
-    SP_RED_ENERGY_ROD = 7
+    SP_RED_ENERGY_ROD = 7,
     /* fields {v, A}; params {m, c_s, c_l}; out[1]   sum of 0.5 m v.v + 0.25 m c_s^2 |dev(A'A)|_F^2
        + m c_l^2 (d - 1 - log d), d = |det A|                                       rod.jl:190-199 */
+    SP_RED_MAX_SPEED = 8
+    /* fields {v}; out[1] = max over the particles of norm(v) (0 for an empty system).  The ingredient of an adaptive
+       CFL time step dt = cfl*h/(c + max|v|); on a slab system the maximum is all-reduced over the ranks (NCCL max),
+       so every rank gets the same dt.  No counterpart in the reference: its examples use fixed time steps. */
 };
 
 /* point sums:  out[k] = sum_q func(q, |x_k - q.x|)  over !(r > h), no self exclusion (core.jl:240-260) */

@@ -1233,6 +1233,13 @@ int so_reduce(void* hnd, int red, const int32_t* F, int nf, const double* P, int
             out[2] = acc[2];
             return SP_OK;
         }
+        case SP_RED_MAX_SPEED: {  // max norm(v) (algebra.jl:58-60); no counterpart in the reference
+            if (nf != 1 || np != 0) return SP_ERR_INVALID;
+            double vmax = 0.0;
+            for (const Particle& p : s.particles) vmax = std::max(vmax, std::sqrt(dot3(p.f + F[0], p.f + F[0])));
+            out[0] = vmax;
+            return SP_OK;
+        }
         case SP_RED_ENERGY_ROD: {  // rod.jl:190-199 (particle_energy summed as in :213)
             if (nf != 2 || np != 3) return SP_ERR_INVALID;
             const int ov = F[0], oA = F[1];

@@ -5,8 +5,8 @@ from . import abi, geometry, io, operators  # noqa: F401
 from .abi import SpError  # noqa: F401
 from .geometry import (Ball, BoundaryLayer, Box, Circle, CubicGrid, Hexagrid, Rectangle, Specification,  # noqa: F401
                        Squaregrid, covering, generate_positions, make_grid)
-from .system import (ParticleField, ParticleSystem, apply, assemble_vector, create_cell_list,  # noqa: F401
-                     kernel_eval)
+from .system import (ParticleField, ParticleSystem, apply, assemble_vector, cfl_time_step,  # noqa: F401
+                     create_cell_list, kernel_eval)
 from . import slab  # noqa: F401,E402
 from .slab import SlabSystem  # noqa: F401,E402
 

@@ -63,6 +63,10 @@ __device__ __forceinline__ void red_map(const RedParams& R, long long i, double 
         const double vx = V[i], vy = V[cap + i], vz = V[2 * cap + i];
         v[0] = 0.5 * m * (vx * vx + vy * vy + vz * vz) + 0.25 * m * (c_s * c_s) * (n2 * n2) +
                m * (c_l * c_l) * (d - 1.0 - log(d));
+    } else if (RED == SP_RED_MAX_SPEED) {  // fields {v}
+        const double* V = R.f[0];
+        const double vx = V[i], vy = V[cap + i], vz = V[2 * cap + i];
+        v[0] = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz)));  // norm, algebra.jl:58-60
     } else if (RED == SP_RED_FORCE_ON_TYPE) {  // fields {a, m, type}; params {type_sel}
         if (R.f[2][i] == R.p[0]) {
             const double* A = R.f[0];
@@ -259,6 +263,11 @@ int32_t sp_reduce(sp_system* s, int32_t red, const int32_t* F, int32_t nf, const
             const int nc[] = {3, 9};
             if ((rc = bind(2, nc, 3))) return rc;
             return run_reduce<SP_RED_ENERGY_ROD, false>(s, R, 1, out);
+        }
+        case SP_RED_MAX_SPEED: {
+            const int nc[] = {3};
+            if ((rc = bind(1, nc, 0))) return rc;
+            return run_reduce<SP_RED_MAX_SPEED, true>(s, R, 1, out);
         }
         case SP_RED_FORCE_ON_TYPE: {
             const int nc[] = {3, 1, 1};

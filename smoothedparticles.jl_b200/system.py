@@ -321,6 +321,15 @@ def create_cell_list(sys: ParticleSystem):
     sys.create_cell_list()
 
 
+def cfl_time_step(sys, cfl: float, h: float, c: float, v: str = "v") -> float:
+    """Adaptive time step dt = cfl*h/(c + max|v|) (BASELINE north_star: "allreduce for the CFL time-step minimum").
+    One device reduction (SP_RED_MAX_SPEED) and an 8-byte read-back; on a slab system the maximum is all-reduced over
+    the ranks, so every rank computes the same dt.  The reference's examples use fixed steps (dt = 0.1*h/c): this is
+    an extension with no upstream counterpart."""
+    vmax = float(sys.reduce(K["SP_RED_MAX_SPEED"], (v,), (), nout=1)[0])
+    return cfl * h / (c + vmax)
+
+
 def apply(sys: ParticleSystem, op: Operator, self: bool = False, strict_order: bool = False):
     sys.apply(op, self_=self, strict_order=strict_order)
 

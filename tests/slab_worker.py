@@ -64,6 +64,11 @@ def main():
         tot = sysd.allreduce([sysd.n_owned])[0]
         res = gather_by_gid(sysd, names, rank, world)
         E = sysd.reduce(K["SP_RED_ENERGY_WCSPH"], ("x", "v", "rho"), (c["m"], c["c"], c["rho0"], *c["g"]))[0]
+        # adaptive CFL step: the max-speed reduction is all-reduced (NCCL max), every rank gets the same dt
+        dt_cfl = sp.cfl_time_step(sysd, 0.1, case.h, c["c"])
+        dts = [None] * world
+        dist.all_gather_object(dts, dt_cfl)
+        ok = ok and all(d == dts[0] for d in dts)
         if rank == 0:
             from oracle.oracle import OracleSystem
             ora = case.make(OracleSystem)
@@ -80,6 +85,9 @@ def main():
                 ok = ok and err <= tol
             ok = ok and abs(E - Eo) <= 1e-9 * abs(Eo)
             msg += f"E {E:.12e} vs {Eo:.12e}"
+            dt_o = sp.cfl_time_step(ora, 0.1, case.h, c["c"])
+            ok = ok and abs(dt_cfl - dt_o) <= 1e-9 * dt_o and dt_o < 0.1 * case.h / c["c"]
+            msg += f" dt_cfl {dt_cfl:.12e} vs {dt_o:.12e}"
     elif case_name == "box_periodic":
         # periodic along z: compare with an oracle run on the same particles plus explicit periodic images
         nx, ny, nz = 14, 12, 24

@@ -152,3 +152,14 @@ def test_cylinder_time_loop_with_inflow():
     fixed0 = case.init["x"][case.init["type"] >= 2.0]
     fixed1 = x[typ >= 2.0]
     assert np.array_equal(fixed0[np.lexsort(fixed0.T)], fixed1[np.lexsort(fixed1.T)])
+
+
+def test_max_speed_reduction_on_the_oracle():
+    case = configs.cylinder(cylinder_init())
+    s = case.make(OracleSystem)
+    rng = np.random.default_rng(1)
+    v = rng.uniform(-2, 2, (case.n, 3))
+    s.set("v", v)
+    want = np.max(np.sqrt((v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1]) + v[:, 2] * v[:, 2]))
+    assert s.reduce(K["SP_RED_MAX_SPEED"], ("v",), (), nout=1)[0] == want
+    assert sp.cfl_time_step(s, 0.1, case.h, 6.0) == 0.1 * case.h / (6.0 + want)
