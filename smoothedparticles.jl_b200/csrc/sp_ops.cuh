@@ -231,6 +231,7 @@ struct OpInternalForceCavity {
 // balance_of_mass!  :102-104 — the density itself is integrated in the pair loop
 template <class K>
 struct OpScBalanceOfMass {
+    static constexpr bool LISTS_ONLY = true;  // see SpListsOnly, sp_sweep.cu
     static constexpr int NQ = 3;  // vx, vy, vz
     struct Params {
         const double* qp[NQ];
@@ -262,6 +263,7 @@ struct OpScBalanceOfMass {
 // internal_force!  :106-114 with pressure(p) = c^2*(rho - rho0) (:68-70) hoisted to one evaluation per particle
 template <class K>
 struct OpScInternalForce {
+    static constexpr bool LISTS_ONLY = true;  // see SpListsOnly, sp_sweep.cu
     static constexpr int NQ = 5;  // vx, vy, vz, pr = P(rho)/rho^2, rho
     struct Params {
         const double* qp[NQ];
@@ -302,6 +304,7 @@ struct OpScInternalForce {
 // find_n!  :76-78
 template <class K>
 struct OpFindNormal {
+    static constexpr bool LISTS_ONLY = true;  // see SpListsOnly, sp_sweep.cu
     static constexpr int NQ = 0;
     struct Params {
         const double* qp[1];
@@ -332,6 +335,7 @@ struct OpFindNormal {
 // internal_force!  :101-113 (pressure with the constant rho0, viscosity, surface tension)
 template <class K>
 struct OpInternalForceTension {
+    static constexpr bool LISTS_ONLY = true;  // see SpListsOnly, sp_sweep.cu
     static constexpr int NQ = 7;  // vx, vy, vz, P, nx, ny, nz
     struct Params {
         const double* qp[NQ];
@@ -392,6 +396,7 @@ __device__ __forceinline__ double sp_rev_add(double x, double y) {
 // find_rho! / find_rho0!  collapse_symplectic.jl:98-108, Kepler_vortex.jl:139-149 (fluid-fluid pairs only; self=true)
 template <class K>
 struct OpDensitySumFluid {
+    static constexpr bool LISTS_ONLY = true;  // see SpListsOnly, sp_sweep.cu
     static constexpr int NQ = 1;  // type
     struct Params {
         const double* qp[NQ];
@@ -422,6 +427,7 @@ struct OpDensitySumFluid {
 // (P/rho^2 or P/rho0^2); it is 0/0 on wall particles of collapse_symplectic, where it is never used.
 template <class K>
 struct OpInternalForceLJ {
+    static constexpr bool LISTS_ONLY = true;  // see SpListsOnly, sp_sweep.cu
     static constexpr int NQ = 2;  // pr, type
     struct Params {
         const double* qp[NQ];
@@ -463,6 +469,7 @@ struct OpInternalForceLJ {
 // sum(sys, LJ_potential, p) for every p  (core.jl:271-291 with collapse_symplectic.jl:146-153, Kepler_vortex.jl:186-193)
 template <class K>
 struct OpLJPotential {
+    static constexpr bool LISTS_ONLY = true;  // see SpListsOnly, sp_sweep.cu
     static constexpr int NQ = 1;  // type
     struct Params {
         const double* qp[NQ];
@@ -494,6 +501,7 @@ struct OpLJPotential {
 // balance_of_mass!  :102-108
 template <class K>
 struct OpCylBalanceOfMass {
+    static constexpr bool LISTS_ONLY = true;  // see SpListsOnly, sp_sweep.cu
     static constexpr int NQ = 6;  // vx, vy, vz, rho, m, type
     struct Params {
         const double* qp[NQ];
@@ -530,6 +538,7 @@ struct OpCylBalanceOfMass {
 // internal_force!  :118-123 (pressure + Monaghan viscosity, every particle type)
 template <class K>
 struct OpCylInternalForce {
+    static constexpr bool LISTS_ONLY = true;  // see SpListsOnly, sp_sweep.cu
     static constexpr int NQ = 6;  // vx, vy, vz, pr = P/rho^2, rho, m
     struct Params {
         const double* qp[NQ];
@@ -602,6 +611,7 @@ __device__ __forceinline__ SpM2 sp_m2_dev(const SpM2& g, double* lam_out) {
 // find_A!  rod.jl:128-134
 template <class K>
 struct OpRodFindA {
+    static constexpr bool LISTS_ONLY = true;  // see SpListsOnly, sp_sweep.cu
     static constexpr int NQ = 2;  // X1, X2
     struct Params {
         const double* qp[NQ];
@@ -640,6 +650,7 @@ struct OpRodFindA {
 // find_f!  rod.jl:145-160
 template <class K>
 struct OpRodFindF {
+    static constexpr bool LISTS_ONLY = true;  // see SpListsOnly, sp_sweep.cu
     static constexpr int NQ = 13;  // A11 A21 A12 A22 | B11 B21 B12 B22 | X1 X2 | vx vy vz
     struct Params {
         const double* qp[NQ];
@@ -698,6 +709,7 @@ struct OpRodFindF {
 // find_e!  rod.jl:185-188
 template <class K>
 struct OpRodFindE {
+    static constexpr bool LISTS_ONLY = true;  // see SpListsOnly, sp_sweep.cu
     static constexpr int NQ = 2;  // X1, X2
     struct Params {
         const double* qp[NQ];

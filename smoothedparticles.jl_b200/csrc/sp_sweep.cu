@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdlib>
 
+#include <type_traits>
 #include "sp_internal.cuh"
 #include "sp_ops.cuh"
 
@@ -1233,6 +1234,16 @@ static int sp_ensure_nbr_cache(sp_system* s, SweepCtx& c) {
     return SP_OK;
 }
 
+// Operators that declare `static constexpr bool LISTS_ONLY = true` (the example zoo beyond the BASELINE configs) are
+// built for the two production kernels only — the cached-list replay and the strict-order scan.  The experimental
+// kernels kept from the exploration (tile, packed records, hit masks; profiles/r1_sweep_exploration.md) are
+// instantiated for the WCSPH / ISPH / collision operators they were measured and parity-tested with: ~10 kernels
+// x 3 kernel families per operator is what the build time of this file is made of.
+template <class Op, class = void>
+struct SpListsOnly : std::false_type {};
+template <class Op>
+struct SpListsOnly<Op, std::void_t<decltype(Op::LISTS_ONLY)>> : std::true_type {};
+
 template <class Op>
 static int launch_sweep(sp_system* s, const typename Op::Params& P, int flags) {
     if (s->n == 0) return SP_OK;
@@ -1248,6 +1259,18 @@ static int launch_sweep(sp_system* s, const typename Op::Params& P, int flags) {
     const bool tile = (flags & SP_FLAG_TILE_KERNEL) || getenv("SP_SWEEP_TILE");
     static const int variant = getenv("SP_SWEEP_VARIANT") ? atoi(getenv("SP_SWEEP_VARIANT")) : 0;
     const bool packed = (flags & SP_FLAG_PACKED_KERNEL) || variant == 1;
+    if constexpr (SpListsOnly<Op>::value) {
+        (void)X;
+        if (tile || packed || sp_sweep_mode() != 3)
+            return sp_fail(s, SP_ERR_INVALID,
+                           "this operator is built for the cached-list and strict-order kernels only "
+                           "(no SP_FLAG_TILE_KERNEL / SP_FLAG_PACKED_KERNEL / SP_SWEEP_* variants)");
+        int rc = sp_ensure_prefilter(s, c);
+        if (!rc) rc = sp_ensure_nbr_cache(s, c);
+        if (rc) return rc;
+        SP_LAUNCH(s, (k_sweep_list<Op, 1>), sp_blocks(s->n, 128), 128, 0, s->g, c, s->nbr_cnt, s->nbr_ids, P, self_flag);
+        return SP_OK;
+    } else {
     if (!packed) {
         int rc = sp_ensure_prefilter(s, c);
         if (rc) return rc;
@@ -1307,6 +1330,7 @@ static int launch_sweep(sp_system* s, const typename Op::Params& P, int flags) {
     SP_LAUNCH(s, (k_sweep_pk<Op, TP, LCAP>), sp_blocks(s->n, TP), TP, (size_t)TP * LCAP * sizeof(int), s->g, c, P, pk0, pk1,
               self_flag);
     return SP_OK;
+    }  // !SpListsOnly
 }
 
 template <template <class> class OpT, class MakeParams>

@@ -163,3 +163,17 @@ def test_collapse_symplectic_energy_on_device():
     drift = abs(energy(dev) - E0)
     # oracle at the same resolution: drift = 7 % of the kinetic energy gained = 1.7e-4 of |E0| after 200 steps
     assert kin > 0 and drift < 0.2 * kin and drift < 1e-3 * abs(E0)
+
+
+def test_zoo_operators_reject_the_experimental_kernels_loudly():
+    # operators beyond the BASELINE configs are built for the cached-list and strict-order kernels only
+    case = configs.collapse_symplectic(dr=4e-2)
+    c = case.consts
+    s = case.make(ParticleSystem)
+    s.create_cell_list()
+    op = ops.density_sum_fluid("wendland2", c["m"], c["h"], out="rho")
+    s.apply(op, self_=True)
+    s.apply(op, self_=True, strict_order=True)
+    for kw in ({"tile_kernel": True}, {"packed_kernel": True}):
+        with pytest.raises(sp.SpError):
+            s.apply(op, self_=True, **kw)
