@@ -12,7 +12,7 @@
 module SmoothedParticlesB200
 
 export ParticleSystem, create_cell_list!, build_neighbour_lists!, apply!, respawn!, upload!, download, add_particles!, ParticleField,
-       assemble_vector, Operators, poisson_cg!, reduce_energy_wcsph, sum_at_points
+       assemble_vector, Operators, poisson_cg!, reduce_energy_wcsph, sum_at_points, run_program!, front, cfl_time_step, positions
 
 const LIB = get(ENV, "SP_B200_LIB", joinpath(@__DIR__, "..", "smoothedparticles.jl_b200", "libsp_b200.so"))
 
@@ -52,6 +52,14 @@ mutable struct ParticleSystem
         return sys
     end
 end
+
+# ParticleSystem(fields, domain, h) with `domain` = boundarybox(shape) of the reference's geometry module (any object
+# with the six Box fields, src/geometry.jl:15-22)
+ParticleSystem(fields::Vector{Pair{Symbol,Int}}, box, h::Float64; device::Integer = 0) =
+    ParticleSystem(fields, (box.x1_min, box.x2_min, box.x3_min), (box.x1_max, box.x2_max, box.x3_max), h; device = device)
+
+# 3 x n Float64 matrix (the AoS layout of upload!) from a Vector of RealVector / SVector{3,Float64}
+positions(xs::AbstractVector) = Float64[x[i] for i in 1:3, x in xs]
 
 Base.length(sys::ParticleSystem) = begin
     n = Ref{Int64}(0)
@@ -203,6 +211,31 @@ function poisson_cg!(sys::ParticleSystem, kernel, m, h, rho, C_free; x = :x, L =
                 (Ptr{Cvoid}, Ptr{Int32}, Int32, Ptr{Float64}, Int32, Float64, Float64, Int64, Ref{Int64}, Ref{Float64}),
                 sys.handle, F, 6, prm, 5, reltol, abstol, maxiter, iters, resid), sys.handle)
     return iters[], resid[]
+end
+
+# generic diagnostics reduction (SP_RED_* of include/sp_b200.h): returns the first `nout` results
+function reduce(sys::ParticleSystem, red::Integer, fields::Vector{Symbol}, params::Vector{Float64} = Float64[]; nout::Integer = 1)
+    F = Int32[sys.fields[f][1] for f in fields]
+    out = zeros(3)
+    prm = isempty(params) ? zeros(1) : params
+    check(ccall((:sp_reduce, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{Float64}, Int32, Ptr{Float64}),
+                sys.handle, Int32(red), F, length(F), prm, length(params), out), sys.handle)
+    return out[1:nout]
+end
+# get_globals, collapse_dry.jl:173-187: (X, H) of the dam-break front
+front(sys::ParticleSystem, width, height, h, xmax; x = :x, type = :type) =
+    reduce(sys, 2, [x, type], Float64[width, height, h, xmax]; nout = 2)
+# adaptive time step dt = cfl*h/(c + max|v|) (no counterpart in the reference; all-reduced on slab systems)
+cfl_time_step(sys::ParticleSystem, cfl, h, c; v = :v) = cfl * h / (c + reduce(sys, 8, [v])[1])
+
+# the whole time loop of examples/collapse3d.jl:136-150 (program = 1) or collapse_dry.jl:203-211 (program = 2) issued
+# from inside the library: one ccall for `nsteps` steps, same arithmetic as the call-by-call loop
+function run_program!(sys::ParticleSystem, program::Integer, kernel, m, h, nu, dt, c, rho0, mu, g, nsteps::Integer;
+                      x = :x, v = :v, Dv = :Dv, rho = :rho, Drho = :Drho, P = :P, type = :type)
+    F = Int32[sys.fields[f][1] for f in (x, v, Dv, rho, Drho, P, type)]
+    prm = Float64[KERNELS[kernel], m, h, 2 * nu, dt, c^2, rho0, mu, g...]
+    check(ccall((:sp_run_program, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{Float64}, Int32, Int64),
+                sys.handle, Int32(program), F, length(F), prm, length(prm), Int64(nsteps)), sys.handle)
 end
 
 # sum(energy, sys.particles), collapse_dry.jl:166-171
