@@ -12,7 +12,7 @@
 module SmoothedParticlesB200
 
 export ParticleSystem, create_cell_list!, build_neighbour_lists!, apply!, respawn!, upload!, download, add_particles!, ParticleField,
-       assemble_vector, Operators, poisson_cg!, reduce_energy_wcsph, sum_at_points, run_program!, front, cfl_time_step, positions
+       assemble_vector, Operators, poisson_cg!, reduce_energy_wcsph, sum_at_points, run_program!, front, cfl_time_step, positions, sp_reduce
 
 const LIB = get(ENV, "SP_B200_LIB", joinpath(@__DIR__, "..", "smoothedparticles.jl_b200", "libsp_b200.so"))
 
@@ -87,7 +87,7 @@ function add_particles!(sys::ParticleSystem; kwargs...)
     old = Dict(k => download(sys, k) for k in keys(kwargs) if n_old > 0)
     check(ccall((:sp_resize, LIB), Int32, (Ptr{Cvoid}, Int64), sys.handle, n_old + n_new), sys.handle)
     for (k, v) in kwargs
-        upload!(sys, k, n_old > 0 ? hcat(old[k], v) : v)
+        upload!(sys, k, n_old > 0 ? (ndims(v) == 1 ? vcat(old[k], v) : hcat(old[k], v)) : v)
     end
 end
 
@@ -214,7 +214,7 @@ function poisson_cg!(sys::ParticleSystem, kernel, m, h, rho, C_free; x = :x, L =
 end
 
 # generic diagnostics reduction (SP_RED_* of include/sp_b200.h): returns the first `nout` results
-function reduce(sys::ParticleSystem, red::Integer, fields::Vector{Symbol}, params::Vector{Float64} = Float64[]; nout::Integer = 1)
+function sp_reduce(sys::ParticleSystem, red::Integer, fields::Vector{Symbol}, params::Vector{Float64} = Float64[]; nout::Integer = 1)
     F = Int32[sys.fields[f][1] for f in fields]
     out = zeros(3)
     prm = isempty(params) ? zeros(1) : params
@@ -224,9 +224,9 @@ function reduce(sys::ParticleSystem, red::Integer, fields::Vector{Symbol}, param
 end
 # get_globals, collapse_dry.jl:173-187: (X, H) of the dam-break front
 front(sys::ParticleSystem, width, height, h, xmax; x = :x, type = :type) =
-    reduce(sys, 2, [x, type], Float64[width, height, h, xmax]; nout = 2)
+    sp_reduce(sys, 2, [x, type], Float64[width, height, h, xmax]; nout = 2)
 # adaptive time step dt = cfl*h/(c + max|v|) (no counterpart in the reference; all-reduced on slab systems)
-cfl_time_step(sys::ParticleSystem, cfl, h, c; v = :v) = cfl * h / (c + reduce(sys, 8, [v])[1])
+cfl_time_step(sys::ParticleSystem, cfl, h, c; v = :v) = cfl * h / (c + sp_reduce(sys, 8, [v])[1])
 
 # the whole time loop of examples/collapse3d.jl:136-150 (program = 1) or collapse_dry.jl:203-211 (program = 2) issued
 # from inside the library: one ccall for `nsteps` steps, same arithmetic as the call-by-call loop
