@@ -50,6 +50,14 @@ def steps(maker, name, nsteps, sub, **kw):
     np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
 
 
+def cylinder_case():
+    """examples/cylinder.jl on the particles of the reference's own init/cylinder.vtp (cylinder_init.npz, made by
+    tools/make_vtp_golden.py)."""
+    d = np.load(os.path.join(HERE, "cylinder_init.npz"))
+    xy = d["xy"]
+    return configs.cylinder({"x": np.column_stack([xy, np.zeros(len(xy))]), "type": d["type"].astype(np.float64)})
+
+
 if __name__ == "__main__":
     kernels()
     steps(configs.collapse_dry, "collapse_dry_5steps", 5, 7)
@@ -58,5 +66,8 @@ if __name__ == "__main__":
     steps(configs.collision_2d, "collision_2d_20steps", 20, 3)
     steps(configs.static_container, "static_container_5steps", 5, 9)
     steps(configs.drop, "drop_3steps", 3, 11, dr=1.2e-4)
+    steps(configs.collapse_symplectic, "collapse_symplectic_10steps", 10, 5, dr=4.0e-2)
+    steps(cylinder_case, "cylinder_5steps", 5, 23)
+    steps(configs.rod, "rod_5steps", 5, 5)
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))
