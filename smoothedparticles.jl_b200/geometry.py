@@ -9,6 +9,11 @@ identical particle ORDER:
   108-234, 240-258``
 * grids: ``Squaregrid``, ``Hexagrid``, ``CubicGrid`` and ``covering`` — ``src/grids.jl:48-91, 124-144``
 * ``generate_positions`` = the position part of ``generate_particles!`` — ``src/grids.jl:253-258``
+* the rest of the reference's geometry module, host side only (the device generator takes the subset above and fails
+  loudly otherwise): ``Ellipse``, ``Ellipsoid``, ``Transform``, ``Polygon``, ``ClosedSpline``, ``Cone``,
+  ``RevolutionBody`` — ``src/geometry.jl:70-100, 262-440``; ``VogelGrid``, ``BodycenteredGrid``, ``FacecenteredGrid``,
+  ``DiamondGrid`` — ``src/grids.jl:93-251``.  Pinned by the reference's own ``tests/test_geometry.jl``
+  (``tests/test_geometry_pins.py``).
 
 Order contract: ``for i in a, j in b, k in c`` in Julia nests with the LAST range innermost, which is
 numpy's C-order ravel of an ``indexing='ij'`` mesh.  Points are produced in that order.
@@ -25,6 +30,8 @@ __all__ = [
     "Box", "Rectangle", "Circle", "Ball", "BooleanUnion", "BooleanIntersection", "BooleanDifference",
     "Specification", "HalfSpace", "BoundaryLayer", "Grid", "Squaregrid", "Hexagrid", "CubicGrid", "covering",
     "generate_positions", "boundarybox",
+    "Ellipse", "Ellipsoid", "Transform", "Polygon", "ClosedSpline", "Cone", "RevolutionBody",
+    "VogelGrid", "BodycenteredGrid", "FacecenteredGrid", "DiamondGrid", "make_grid",
 ]
 
 
@@ -184,6 +191,143 @@ class HalfSpace:
         return {"<": v < self.bound, "<=": v <= self.bound, ">": v > self.bound, ">=": v >= self.bound}[self.op]
 
 
+@dataclass(frozen=True)
+class Ellipse(Shape):
+    """src/geometry.jl:70-98"""
+    x1: float
+    x2: float
+    r1: float
+    r2: float
+
+    def __post_init__(self):
+        if self.r1 <= 0.0 or self.r2 <= 0.0:
+            raise ValueError("Degenerate ellipse definition (r <= 0)!")  # the reference logs @error and carries on
+
+    def is_inside(self, X):
+        a = (X[:, 0] - self.x1) / self.r1
+        b = (X[:, 1] - self.x2) / self.r2
+        return a * a + b * b <= 1
+
+    def boundarybox(self):
+        return Rectangle(self.x1 - self.r1, self.x2 - self.r2, self.x1 + self.r1, self.x2 + self.r2)
+
+
+@dataclass(frozen=True)
+class Ellipsoid(Shape):
+    """src/geometry.jl:262-282"""
+    x1: float
+    x2: float
+    x3: float
+    r1: float
+    r2: float
+    r3: float
+
+    def is_inside(self, X):
+        a = (X[:, 0] - self.x1) / self.r1
+        b = (X[:, 1] - self.x2) / self.r2
+        c = (X[:, 2] - self.x3) / self.r3
+        return a * a + b * b + c * c <= 1.0
+
+    def boundarybox(self):
+        return Box(self.x1 - self.r1, self.x2 - self.r2, self.x3 - self.r3, self.x1 + self.r1, self.x2 + self.r2,
+                   self.x3 + self.r3)
+
+
+class Transform(Shape):
+    """src/geometry.jl:284-316: the shape ``s`` under x -> A x + b (A a 3x3 matrix, b a 3-vector)."""
+
+    def __init__(self, s: Shape, A=None, b=None):
+        self.s = s
+        self.A = np.eye(3) if A is None else np.asarray(A, dtype=np.float64).reshape(3, 3)
+        self.A_inv = np.linalg.inv(self.A)
+        self.b = np.zeros(3) if b is None else np.asarray(b, dtype=np.float64).reshape(3)
+
+    def is_inside(self, X):
+        return self.s.is_inside((X - self.b) @ self.A_inv.T)
+
+    def boundarybox(self):
+        box = self.s.boundarybox()
+        corners = np.array([[x, y, z] for x in (box.x1_min, box.x1_max) for y in (box.x2_min, box.x2_max)
+                            for z in (box.x3_min, box.x3_max)])
+        Y = corners @ self.A.T + self.b
+        lo, hi = Y.min(axis=0), Y.max(axis=0)
+        return Box(float(lo[0]), float(lo[1]), float(lo[2]), float(hi[0]), float(hi[1]), float(hi[2]))
+
+
+class Polygon(Shape):
+    """src/geometry.jl:318-360: winding-number test, half-open in y as in the reference."""
+
+    def __init__(self, *points):
+        self.xs = np.array([float(p[0]) for p in points])
+        self.ys = np.array([float(p[1]) for p in points])
+        self.deg = len(points)
+
+    def is_inside(self, X):
+        x_, y_ = X[:, 0], X[:, 1]
+        wn = np.zeros(len(X), dtype=np.int64)
+        for i in range(self.deg):
+            nxt = (i + 1) % self.deg
+            isleft = (self.xs[nxt] - self.xs[i]) * (y_ - self.ys[i]) - (x_ - self.xs[i]) * (self.ys[nxt] - self.ys[i])
+            wn += ((self.ys[i] <= y_) & (y_ < self.ys[nxt]) & (isleft > 0.0)).astype(np.int64)
+            wn -= ((self.ys[i] > y_) & (y_ >= self.ys[nxt]) & (isleft < 0.0)).astype(np.int64)
+        return wn != 0
+
+    def boundarybox(self):
+        return Rectangle(float(self.xs.min()), float(self.ys.min()), float(self.xs.max()), float(self.ys.max()))
+
+
+def ClosedSpline(*points, n: int = 32) -> Polygon:
+    """src/geometry.jl:362-373: the polygon through ``n`` samples of the natural cubic spline through the points
+    (closed by repeating the first one).  Interpolations.jl's ``BSpline(Cubic(Natural(OnGrid())))`` is the natural
+    interpolating cubic spline, which is what scipy's ``CubicSpline(bc_type="natural")`` evaluates."""
+    from scipy.interpolate import CubicSpline
+    xs = [float(p[0]) for p in points] + [float(points[0][0])]
+    ys = [float(p[1]) for p in points] + [float(points[0][1])]
+    ts = np.arange(len(points) + 1) / len(points)
+    sx, sy = CubicSpline(ts, xs, bc_type="natural"), CubicSpline(ts, ys, bc_type="natural")
+    fine = [i / (n - 1) for i in range(n)]
+    return Polygon(*[(float(sx(t)), float(sy(t))) for t in fine])
+
+
+class Cone(Shape):
+    """src/geometry.jl:375-413, literally (the axial coordinate ``s`` is NOT normalised by the length there, so the
+    shape is a cone only for |b - a| = 1, as in the reference's own test)."""
+
+    def __init__(self, a1, a2, a3, b1, b2, b3, ar, br):
+        self.a = np.array([a1, a2, a3], dtype=np.float64)
+        self.b = np.array([b1, b2, b3], dtype=np.float64)
+        self.ar, self.br = float(ar), float(br)
+        d = self.a - self.b
+        self.len = math.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2])
+
+    def is_inside(self, X):
+        s = (X - self.a) @ (self.b - self.a)
+        ok = (0.0 <= s) & (s <= self.len)
+        Y = X - s[:, None] * self.b - (1 - s)[:, None] * self.a
+        t = np.sqrt(Y[:, 0] * Y[:, 0] + Y[:, 1] * Y[:, 1] + Y[:, 2] * Y[:, 2])
+        return ok & (s / self.len * self.br + (1.0 - s / self.len) * self.ar >= t)
+
+    def boundarybox(self):
+        R = max(self.ar, self.br)
+        lo, hi = np.minimum(self.a, self.b) - R, np.maximum(self.a, self.b) + R
+        return Box(float(lo[0]), float(lo[1]), float(lo[2]), float(hi[0]), float(hi[1]), float(hi[2]))
+
+
+@dataclass(frozen=True)
+class RevolutionBody(Shape):
+    """src/geometry.jl:415-437: the 2-D shape ``s`` (r, z) rotated around the z axis."""
+    s: Shape
+
+    def is_inside(self, X):
+        r = np.sqrt(X[:, 0] * X[:, 0] + X[:, 1] * X[:, 1])
+        return self.s.is_inside(np.column_stack([r, X[:, 2], np.zeros(len(X))]))
+
+    def boundarybox(self):
+        rect = self.s.boundarybox()
+        R = rect.x1_max
+        return Box(-R, -R, rect.x2_min, R, R, rect.x2_max)
+
+
 class Grid:
     dim = 0
 
@@ -212,15 +356,47 @@ class CubicGrid(Grid):
     dim = 3
 
 
+GOLDEN_ANGLE = 2.39996322972865332  # src/grids.jl:7
+
+
+class VogelGrid(Grid):
+    """src/grids.jl:93-122: Vogel's spiral around the origin, one point per area dr^2."""
+    dim = 2
+
+    def __init__(self, dr: float):
+        self.dr = dr
+        self.k = dr / math.sqrt(math.pi)
+        self.center = np.zeros(3)
+
+
+@dataclass(frozen=True)
+class BodycenteredGrid(Grid):
+    """src/grids.jl:146-175"""
+    dr: float
+    dim = 3
+
+
+@dataclass(frozen=True)
+class FacecenteredGrid(Grid):
+    """src/grids.jl:177-212"""
+    dr: float
+    dim = 3
+
+
+@dataclass(frozen=True)
+class DiamondGrid(Grid):
+    """src/grids.jl:214-239"""
+    dr: float
+    dim = 3
+
+
 def make_grid(dr: float, symm: str) -> Grid:
-    """Grid(dr, symm), src/grids.jl:27-38 (square / hexagonal / cubic only)."""
-    if symm == "square":
-        return Squaregrid(dr)
-    if symm == "hexagonal":
-        return Hexagrid(dr)
-    if symm == "cubic":
-        return CubicGrid(dr)
-    raise ValueError("Unsupported grid type: " + symm)
+    """Grid(dr, symm), src/grids.jl:27-38."""
+    kinds = {"square": Squaregrid, "hexagonal": Hexagrid, "vogel": VogelGrid, "cubic": CubicGrid,
+             "facecentered": FacecenteredGrid, "bodycentered": BodycenteredGrid, "diamond": DiamondGrid}
+    if symm not in kinds:
+        raise ValueError("Unsupported grid type: " + symm)
+    return kinds[symm](dr)
 
 
 def boundarybox(s: Shape) -> Box:
@@ -283,6 +459,58 @@ def covering(grid: Grid, s: Shape) -> np.ndarray:
             X[:, 0] = I.ravel() * grid.dr
             X[:, 1] = J.ravel() * grid.dr
             X[:, 2] = K.ravel() * grid.dr
+            out.append(X[s.is_inside(X)])
+    elif isinstance(grid, VogelGrid):  # src/grids.jl:104-122
+        corners = np.array([[box.x1_min, box.x2_min, 0.0], [box.x1_max, box.x2_min, 0.0], [box.x1_max, box.x2_max, 0.0],
+                            [box.x1_min, box.x2_max, 0.0]]) - grid.center
+        R = float(np.max(np.sqrt(corners[:, 0] ** 2 + corners[:, 1] ** 2 + corners[:, 2] ** 2)))
+        N = (R / grid.k) ** 2
+        for n0 in range(1, int(math.floor(N)) + 1, _CHUNK):
+            n = np.arange(n0, min(n0 + _CHUNK, int(math.floor(N)) + 1), dtype=np.float64)  # for n in 1:N (N a Float64)
+            rad = grid.k * np.sqrt(n)
+            X = np.empty((n.size, 3))
+            X[:, 0] = grid.center[0] + rad * np.cos(n * GOLDEN_ANGLE)
+            X[:, 1] = grid.center[1] + rad * np.sin(n * GOLDEN_ANGLE)
+            X[:, 2] = grid.center[2] + rad * 0.0
+            out.append(X[s.is_inside(X)])
+    elif isinstance(grid, (BodycenteredGrid, FacecenteredGrid)):  # src/grids.jl:150-175, 181-212
+        a = (2 ** (1 / 3) if isinstance(grid, BodycenteredGrid) else 4 ** (1 / 3)) * grid.dr
+        i0, j0, k0 = _ifloor(box.x1_min / a), _ifloor(box.x2_min / a), _ifloor(box.x3_min / a)
+        i1, j1, k1 = _iceil(box.x1_max / a), _iceil(box.x2_max / a), _iceil(box.x3_max / a)
+        js = np.arange(j0, j1 + 1, dtype=np.int64)
+        ks = np.arange(k0, k1 + 1, dtype=np.int64)
+        rows = max(1, _CHUNK // max(1, len(js) * len(ks)))
+        # first loop: cell corners; second loop: the centred points, interleaved per (i, j, k) as the reference pushes them
+        if isinstance(grid, BodycenteredGrid):
+            passes = [[(0.0, 0.0, 0.0)], [(0.5, 0.5, 0.5)]]
+        else:
+            passes = [[(0.0, 0.0, 0.0)], [(0.5, 0.5, 0.0), (0.5, 0.0, 0.5), (0.0, 0.5, 0.5)]]
+        for shifts in passes:
+            for ia in range(i0, i1 + 1, rows):
+                is_ = np.arange(ia, min(ia + rows, i1 + 1), dtype=np.int64)
+                I, J, K = (m.ravel() for m in np.meshgrid(is_, js, ks, indexing="ij"))
+                X = np.empty((I.size, len(shifts), 3))
+                for t, (si, sj, sk) in enumerate(shifts):
+                    X[:, t, 0] = (I + si) * a
+                    X[:, t, 1] = (J + sj) * a
+                    X[:, t, 2] = (K + sk) * a
+                X = X.reshape(-1, 3)
+                out.append(X[s.is_inside(X)])
+    elif isinstance(grid, DiamondGrid):  # src/grids.jl:218-239
+        a = 0.5 * grid.dr
+        i0, j0, k0 = _ifloor(box.x1_min / a), _ifloor(box.x2_min / a), _ifloor(box.x3_min / a)
+        i1, j1, k1 = _iceil(box.x1_max / a), _iceil(box.x2_max / a), _iceil(box.x3_max / a)
+        js_all = np.arange(j0, j1 + 1, dtype=np.int64)
+        ks_all = np.arange(k0, k1 + 1, dtype=np.int64)
+        for i in range(i0, i1 + 1):
+            par = i & 1  # isodd(i) == isodd(j) == isodd(k)
+            J, K = (m.ravel() for m in np.meshgrid(js_all[(js_all & 1) == par], ks_all[(ks_all & 1) == par], indexing="ij"))
+            keep = np.mod(i + J + K, 4) <= 1  # ((i+j+k) % 4 + 4) % 4 in {0, 1}
+            J, K = J[keep], K[keep]
+            X = np.empty((J.size, 3))
+            X[:, 0] = i * a
+            X[:, 1] = J * a
+            X[:, 2] = K * a
             out.append(X[s.is_inside(X)])
     else:
         raise TypeError("unsupported grid")
