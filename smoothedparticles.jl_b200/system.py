@@ -334,8 +334,40 @@ def apply(sys: ParticleSystem, op: Operator, self: bool = False, strict_order: b
     sys.apply(op, self_=self, strict_order=strict_order)
 
 
+def apply_unary(sys: ParticleSystem, op: Operator):
+    """``apply_unary!(sys, action!)`` (src/core.jl:138-142): ``op`` must be a per-particle operator."""
+    if op.binary:
+        raise TypeError(f"{op.name or op.op}: a binary operator was passed to apply_unary")
+    sys.apply(op)
+
+
+def apply_binary(sys: ParticleSystem, op: Operator, strict_order: bool = False):
+    """``apply_binary!(sys, action!)`` (src/core.jl:125-129): the pair sweep without the ``self`` term."""
+    if not op.binary:
+        raise TypeError(f"{op.name or op.op}: a unary operator was passed to apply_binary")
+    sys.apply(op, self_=False, strict_order=strict_order)
+
+
 def assemble_vector(sys: ParticleSystem, op: Operator) -> np.ndarray:
     return sys.assemble_vector(op)
+
+
+def _named_kernel(kernel: str, kfun: str):
+    def f(h: float, r, device: int = 0):
+        """Kernel function of src/kernels.jl evaluated on the device (scalar or array ``r``)."""
+        out = kernel_eval(kernel, K[kfun], h, np.atleast_1d(_farr(r)), device)
+        return float(out[0]) if np.ndim(r) == 0 else out
+    return f
+
+
+# the kernel functions under the reference's names (src/SmoothedParticles.jl:23-27): wendland2(h, r), rDspline23(h, r), ...
+KERNEL_FUNCTIONS = {}
+for _k in ("wendland1", "wendland2", "wendland3", "spline23", "spline24"):
+    KERNEL_FUNCTIONS[_k] = _named_kernel(_k, "SP_KFUN_W")
+    KERNEL_FUNCTIONS["D" + _k] = _named_kernel(_k, "SP_KFUN_DW")
+    KERNEL_FUNCTIONS["rD" + _k] = _named_kernel(_k, "SP_KFUN_RDW")
+KERNEL_FUNCTIONS["DDwendland3"] = _named_kernel("wendland3", "SP_KFUN_DDW")
+globals().update(KERNEL_FUNCTIONS)
 
 
 class ParticleField:

@@ -99,3 +99,25 @@ def test_operator_parameter_folding():
     assert o.op == K["SP_OP_BALANCE_OF_MASS"] and o.params == (3.0, 2.0, 0.1, 2 * 1e-4) and o.binary
     assert ops.find_pressure(1e-3, 50.0, 1000.0).params == (1e-3, 2500.0, 1000.0, 0.0)
     assert ops.fill("a").fields == ("a",)
+
+
+def test_reference_surface_names_exist():
+    # the exports of src/SmoothedParticles.jl:10-72 that belong to the hot path, under the same names
+    import smoothedparticles_jl_b200 as sp
+    from smoothedparticles_jl_b200 import geometry as geo, io as sp_io, operators as ops
+    for name in ("ParticleSystem", "ParticleField", "apply", "apply_unary", "apply_binary", "create_cell_list",
+                 "assemble_vector", "wendland1", "Dwendland1", "rDwendland1", "wendland2", "Dwendland2", "rDwendland2",
+                 "wendland3", "Dwendland3", "rDwendland3", "DDwendland3", "spline24", "Dspline24", "rDspline24",
+                 "spline23", "Dspline23", "rDspline23"):
+        assert callable(getattr(sp, name)), name
+    for name in ("Squaregrid", "Hexagrid", "CubicGrid", "FacecenteredGrid", "BodycenteredGrid", "DiamondGrid", "Rectangle",
+                 "Circle", "Ellipse", "Ball", "Box", "BooleanUnion", "BooleanIntersection", "BooleanDifference",
+                 "Specification", "BoundaryLayer", "Transform", "Polygon", "ClosedSpline", "Ellipsoid", "Cone",
+                 "RevolutionBody"):
+        assert hasattr(geo, name), name
+    for name in ("save_frame", "new_pvd_file", "save_pvd_file", "import_particles"):
+        assert callable(getattr(sp_io, name)), name
+    with pytest.raises(TypeError):
+        sp.apply_unary(None, ops.balance_of_mass("wendland2", 1.0, 1.0))
+    with pytest.raises(TypeError):
+        sp.apply_binary(None, ops.move(0.1))
