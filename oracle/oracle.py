@@ -16,6 +16,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_build", "libsp_oracle.so")
 LIB_PATH_WIDE = os.path.join(_HERE, "_build", "libsp_oracle_wide.so")  # 48-slot particle record (rod.jl)
+LIB_PATH_FAST = os.path.join(_HERE, "_build", "libsp_oracle_fast.so")  # -ffast-math build: a yardstick, not an oracle
 _lib = None
 _lib_wide = None
 
@@ -27,7 +28,7 @@ def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "sp_oracle.cpp")
     hdr = os.path.join(os.path.dirname(_HERE), "include", "sp_b200.h")
     if not force and all(os.path.exists(q) and os.path.getmtime(q) >= os.path.getmtime(src)
-                         and os.path.getmtime(q) >= os.path.getmtime(hdr) for q in (LIB_PATH, LIB_PATH_WIDE)):
+                         and os.path.getmtime(q) >= os.path.getmtime(hdr) for q in (LIB_PATH, LIB_PATH_WIDE, LIB_PATH_FAST)):
         return LIB_PATH
     r = subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), capture_output=True, text=True)
     if r.returncode != 0:
@@ -311,6 +312,20 @@ class OracleSystem:
         ids = np.empty(max(total, 1), dtype=np.int64)
         self._lib.so_get_neighbour_lists(self._h, _pi(offsets), _pi(ids), total)
         return offsets, ids[:total]
+
+
+def kernel_eval_fastmath(kernel_id: int, kfun: int, h: float, r):
+    """The kernel functions as a compiler that may reassociate / contract / use reciprocals evaluates them (gcc
+    -ffast-math -mfma): how far the reference's own @fastmath kernels (src/kernels.jl) may sit from the strictly
+    rounded restatement.  Used only to size the tolerance, never as a reference value."""
+    build()
+    lib = C.CDLL(LIB_PATH_FAST)
+    lib.so_kernel_eval.restype = None
+    lib.so_kernel_eval.argtypes = [C.c_int, C.c_int, _f64, _pf64, _pf64, _i64]
+    r = _f(r)
+    out = np.empty_like(r)
+    lib.so_kernel_eval(int(kernel_id), int(kfun), float(h), _pf(r), _pf(out), r.size)
+    return out
 
 
 def kernel_eval(kernel_id: int, kfun: int, h: float, r):
