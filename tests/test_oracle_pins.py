@@ -189,3 +189,70 @@ def test_fastmath_ambiguity_band_of_the_kernel_functions():
             differs = differs or not np.array_equal(a, b)
     assert differs, "the fast-math build produced the same bits: the yardstick measures nothing"
     assert worst < 1e-13
+
+
+def _isph_presolve(dr=4.0e-2, seed=3):
+    case = configs.collapse_dry_implicit(dr=dr)
+    rng = np.random.default_rng(seed)
+    case.init["v"] = rng.uniform(-1, 1, size=(case.n, 3)) * np.array([1.0, 1.0, 0.0])
+    s = case.make(OracleSystem)
+    o = case.ops
+    case.prologue(s)
+    s.apply(o["init"])
+    s.create_cell_list()
+    s.apply(o["visc"])
+    s.apply(o["dll"])
+    s.apply(o["b"])
+    return case, s
+
+
+def test_assemble_matrix_against_the_formulas_of_the_script():
+    # assemble_matrix(sys, projection_matrix): src/core.jl:196-225 with collapse_dry_implicit.jl:154-163, against an
+    # O(N^2) numpy evaluation: A_ij = 2 h^2 m/rho rDspline23(h, r_ij) for r_ij <= h (i != j),
+    # A_ii = h^2 L_i (+ C_free max(lambda_i, 0) on fluid particles); sparse() sums duplicate triplets
+    import scipy.sparse as sps
+    case, s = _isph_presolve()
+    c = case.consts
+    I, J, V = s.assemble_matrix(case.ops["A"])
+    n = len(s)
+    A = sps.coo_matrix((V, (I - 1, J - 1)), shape=(n, n)).toarray()
+    x, L, lam, typ = s.get("x"), s.get("L"), s.get("lambda"), s.get("type")
+    d = x[:, None, :] - x[None, :, :]
+    r = np.sqrt(np.sum(d * d, axis=2))
+    h, m, rho = c["h"], c["m"], c["rho"]
+    q = r / h
+    with np.errstate(divide="ignore", invalid="ignore"):   # rDspline23, kernels.jl:51-60
+        rD = np.where(q < 0.5, -10.91348181201568 * (2.0 - 3.0 * q) / h ** 4,
+                      np.where(q < 1.0, -10.91348181201568 * (1.0 - q) ** 2 / (q * h ** 4), 0.0))
+    want = np.where((r <= h) & ~np.eye(n, dtype=bool), 2.0 * h * h * m / rho * rD, 0.0)
+    diag = h * h * L + np.where(typ == 0.0, c["C_free"] * np.maximum(lam, 0.0), 0.0)
+    want[np.arange(n), np.arange(n)] = diag
+    assert np.max(np.abs(A - want)) <= 1e-12 * np.max(np.abs(want))
+    assert np.max(np.abs(A - A.T)) <= 1e-12 * np.max(np.abs(want))      # symmetric
+    # rows of the h^2-part sum to zero (graph Laplacian): L_i = sum_j -2 m/rho rDk
+    lap = A - np.diag(np.where(typ == 0.0, c["C_free"] * np.maximum(lam, 0.0), 0.0))
+    assert np.max(np.abs(lap.sum(axis=1))) <= 1e-10 * np.max(np.abs(want))
+
+
+def test_cg_against_an_independent_implementation():
+    # `cg(A, b)` of collapse_dry_implicit.jl:227 is IterativeSolvers.jl's un-preconditioned CG (a dependency that is
+    # neither vendored nor version-pinned by the reference; no reference test runs it): x0 = 0, stop at
+    # |r| <= sqrt(eps) |b|.  The restatement is checked against scipy's CG — an independent implementation of the same
+    # published algorithm — on the oracle-assembled matrix: same solution to solver accuracy, same iteration count
+    # up to rounding.
+    import scipy.sparse as sps
+    from scipy.sparse.linalg import cg as scipy_cg
+    case, s = _isph_presolve()
+    I, J, V = s.assemble_matrix(case.ops["A"])
+    n = len(s)
+    A = sps.coo_matrix((V, (I - 1, J - 1)), shape=(n, n)).tocsr()
+    b = s.get("b")
+    reltol = float(np.sqrt(np.finfo(np.float64).eps))
+    x, it, resid = s.cg(I, J, V, b)
+    assert resid <= reltol * np.linalg.norm(b) and 0 < it < n
+    assert np.linalg.norm(A @ x - b) <= 2 * reltol * np.linalg.norm(b)
+    count = [0]
+    xs, info = scipy_cg(A, b, x0=np.zeros(n), rtol=reltol, atol=0.0, maxiter=n, callback=lambda _: count.__setitem__(0, count[0] + 1))
+    assert info == 0
+    assert abs(count[0] - it) <= max(3, it // 20)
+    assert np.linalg.norm(x - xs) <= 1e-5 * np.linalg.norm(xs)
