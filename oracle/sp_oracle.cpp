@@ -11,8 +11,12 @@
 // against this file in tests/test_oracle_pins.py: tests/test_kernels.jl:20-61 (kernel
 // known-answer properties) and tests/test_collision_2d.jl:118-149 (particle count constant,
 // energy growth < 1e-2 over 4 167 Verlet steps); (2) an independent brute-force O(N^2) /
-// scipy cKDTree neighbour check.  No output of the Julia reference itself could be
-// generated, and that limitation is stated in DESIGN.md.
+// scipy cKDTree neighbour check; (3) O(N^2) numpy evaluations of the example closures' formulas
+// for the operators no reference test exercises (symplectic / cylinder / rod scripts,
+// assemble_matrix), exact integer arithmetic for rev_add, scipy's CG for the CG restatement
+// (tests/test_symplectic_cpu.py, test_cylinder_cpu.py, test_rod_cpu.py, test_oracle_pins.py).
+// No output of the Julia reference itself could be generated, and that limitation is stated
+// in DESIGN.md.
 //
 // Every function cites the reference file:line it follows (paths relative to the
 // reference root).  Compile with -ffp-contract=off and without fast-math so each
