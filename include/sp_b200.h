@@ -356,6 +356,15 @@ int32_t sp_poisson_cg(sp_system* sys, const int32_t* fields, int32_t nfields, co
                       int32_t nparams, double reltol, double abstol, int64_t maxiter, int64_t* iters,
                       double* resid);
 
+/* assemble_matrix(sys, projection_matrix) (src/core.jl:196-225 with collapse_dry_implicit.jl:154-163) for a host that
+ * wants the matrix itself (a direct solver, a preconditioner): COO triplets, 1-based reference indices, one triplet
+ * per particle for the diagonal and one per (particle, neighbour within h) — the triplets the reference hands to
+ * sparse(I, J, V, N, N), which sums duplicates (the narrow-domain double visit).  Two-call protocol: with
+ * I == J == V == NULL only *nnz is written; otherwise `cap` entries are available and *nnz are filled.
+ * fields {x, L, lambda, type}; params {kernel, m, h, rho, C_free}.  Single-GPU systems only. */
+int32_t sp_assemble_matrix(sp_system* sys, const int32_t* fields, int32_t nfields, const double* params, int32_t nparams,
+                           int64_t* I, int64_t* J, double* V, int64_t cap, int64_t* nnz);
+
 /* ---- fused step programs (amortise launch latency; same arithmetic) ------ */
 enum {
     SP_PROGRAM_WCSPH_3D = 1, /* examples/collapse3d.jl:136-150 — move, cell list, balance_of_mass,

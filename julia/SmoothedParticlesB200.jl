@@ -12,7 +12,7 @@
 module SmoothedParticlesB200
 
 export ParticleSystem, create_cell_list!, build_neighbour_lists!, apply!, respawn!, upload!, download, add_particles!, ParticleField,
-       assemble_vector, Operators, poisson_cg!, reduce_energy_wcsph, sum_at_points, run_program!, front, cfl_time_step, positions, sp_reduce
+       assemble_vector, assemble_matrix, Operators, poisson_cg!, reduce_energy_wcsph, sum_at_points, run_program!, front, cfl_time_step, positions, sp_reduce
 
 const LIB = get(ENV, "SP_B200_LIB", joinpath(@__DIR__, "..", "smoothedparticles.jl_b200", "libsp_b200.so"))
 
@@ -236,6 +236,22 @@ function run_program!(sys::ParticleSystem, program::Integer, kernel, m, h, nu, d
     prm = Float64[KERNELS[kernel], m, h, 2 * nu, dt, c^2, rho0, mu, g...]
     check(ccall((:sp_run_program, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{Float64}, Int32, Int64),
                 sys.handle, Int32(program), F, length(F), prm, length(prm), Int64(nsteps)), sys.handle)
+end
+
+# A = assemble_matrix(sys, projection_matrix), src/core.jl:196-225, for hosts that want the matrix itself:
+# returns (I, J, V) — feed them to SparseArrays.sparse(I, J, V, N, N) exactly as the reference does
+function assemble_matrix(sys::ParticleSystem, kernel, m, h, rho, C_free; x = :x, L = :L, lambda = :lambda, type = :type)
+    F = Int32[sys.fields[f][1] for f in (x, L, lambda, type)]
+    prm = Float64[KERNELS[kernel], m, h, rho, C_free]
+    nnz = Ref{Int64}(0)
+    check(ccall((:sp_assemble_matrix, LIB), Int32,
+                (Ptr{Cvoid}, Ptr{Int32}, Int32, Ptr{Float64}, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64, Ref{Int64}),
+                sys.handle, F, 4, prm, 5, C_NULL, C_NULL, C_NULL, 0, nnz), sys.handle)
+    I = Vector{Int64}(undef, nnz[]); J = Vector{Int64}(undef, nnz[]); V = Vector{Float64}(undef, nnz[])
+    nnz[] > 0 && check(ccall((:sp_assemble_matrix, LIB), Int32,
+                (Ptr{Cvoid}, Ptr{Int32}, Int32, Ptr{Float64}, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64, Ref{Int64}),
+                sys.handle, F, 4, prm, 5, I, J, V, nnz[], nnz), sys.handle)
+    return I, J, V
 end
 
 # sum(energy, sys.particles), collapse_dry.jl:166-171

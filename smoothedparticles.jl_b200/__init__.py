@@ -6,7 +6,7 @@ from .abi import SpError  # noqa: F401
 from .geometry import (Ball, BoundaryLayer, Box, Circle, CubicGrid, Hexagrid, Rectangle, Specification,  # noqa: F401
                        Squaregrid, covering, generate_positions, make_grid)
 from .system import (KERNEL_FUNCTIONS, ParticleField, ParticleSystem, apply, apply_binary, apply_unary,  # noqa: F401
-                     assemble_vector, cfl_time_step, create_cell_list, kernel_eval)
+                     assemble_matrix, assemble_vector, cfl_time_step, create_cell_list, kernel_eval)
 globals().update(KERNEL_FUNCTIONS)  # wendland2(h, r), rDwendland3(h, r), ... (src/SmoothedParticles.jl:23-27)
 from . import slab  # noqa: F401,E402
 from .slab import SlabSystem  # noqa: F401,E402

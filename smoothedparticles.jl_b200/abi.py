@@ -66,6 +66,7 @@ SIGNATURES = {
     "sp_reduce": (_i32, [_p, _i32, _pi32, _i32, _pf64, _i32, _pf64]),
     "sp_poisson_apply": (_i32, [_p, _pi32, _i32, _pf64, _i32]),
     "sp_poisson_cg": (_i32, [_p, _pi32, _i32, _pf64, _i32, _f64, _f64, _i64, _pi64, _pf64]),
+    "sp_assemble_matrix": (_i32, [_p, _pi32, _i32, _pf64, _i32, _pi64, _pi64, _pf64, _i64, _pi64]),
     "sp_run_program": (_i32, [_p, _i32, _pi32, _i32, _pf64, _i32, _i64]),
     "sp_kernel_eval": (_i32, [_i32, _i32, _f64, _pf64, _pf64, _i64, _i32]),
     "sp_get_cell_keys": (_i32, [_p, _pi64, _i64]),

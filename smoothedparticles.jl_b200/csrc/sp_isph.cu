@@ -304,3 +304,131 @@ extern "C" int32_t sp_poisson_cg(sp_system* s, const int32_t* F, int32_t nf, con
     if (!(residual <= tol)) return sp_fail(s, SP_ERR_NOT_CONVERGED, "CG reached maxiter before the tolerance");
     return SP_OK;
 }
+
+// ------------------------------------------------------------------ assemble_matrix as COO triplets
+__global__ void __launch_bounds__(256) k_coo_counts(const int* __restrict__ cnt, int* __restrict__ off, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) off[i] = cnt[i] + 1;  // the neighbours and the diagonal
+}
+__global__ void __launch_bounds__(128) k_coo_export(long long n, int capk, const int* __restrict__ cnt,
+                                                    const int* __restrict__ ids, const double* __restrict__ aval,
+                                                    const double* __restrict__ diag, const int* __restrict__ ref,
+                                                    const int* __restrict__ off, long long* __restrict__ I,
+                                                    long long* __restrict__ J, double* __restrict__ V) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long o = off[i];
+    const long long row = (long long)ref[i] + 1;  // 1-based index in the reference's sys.particles
+    I[o] = row;
+    J[o] = row;
+    V[o] = diag[i];
+    o++;
+    const size_t base = ((size_t)(i >> 5) * capk << 5) + (i & 31);
+    const int n_nb = cnt[i];
+    for (int k = 0; k < n_nb; k++, o++) {
+        const size_t e = base + ((size_t)k << 5);
+        I[o] = row;
+        J[o] = (long long)ref[ids[e]] + 1;
+        V[o] = aval[e];
+    }
+}
+
+extern "C" int32_t sp_assemble_matrix(sp_system* s, const int32_t* F, int32_t nf, const double* Pm, int32_t np, int64_t* I,
+                                      int64_t* J, double* V, int64_t cap, int64_t* nnz) {
+    if (!s || !nnz) return SP_ERR_INVALID;
+    SP_CUDA(s, cudaSetDevice(s->device));
+    const int nc[] = {3, 1, 1, 1};
+    int rc = sp_check_fields(s, F, nf, nc, 4);
+    if (rc) return rc;
+    if (np != 5 || !Pm) return sp_fail(s, SP_ERR_INVALID, "wrong number of parameters");
+    if (F[0] != 0) return sp_fail(s, SP_ERR_INVALID, "the first field must be x (field 0)");
+    if (!s->have_cells) return sp_fail(s, SP_ERR_STATE, "sp_assemble_matrix before sp_create_cell_list");
+    if (s->slab) return sp_fail(s, SP_ERR_STATE, "sp_assemble_matrix is not available on a slab system");
+    const bool fill = I || J || V;
+    if (fill && !(I && J && V)) return SP_ERR_INVALID;
+    *nnz = 0;
+    const long long n = s->n;
+    if (n == 0) return SP_OK;
+    int capk = 0;
+    if ((rc = sp_nbr_prepare(s, &capk))) return rc;
+    int *d_off = nullptr, *d_flag = s->counters + 32;
+    double *aval = nullptr, *diag = nullptr;
+    long long *dI = nullptr, *dJ = nullptr;
+    double* dV = nullptr;
+    auto release = [&]() {
+        sp_dfree(s, d_off);
+        sp_dfree(s, aval);
+        sp_dfree(s, diag);
+        sp_dfree(s, dI);
+        sp_dfree(s, dJ);
+        sp_dfree(s, dV);
+    };
+#define SP_TRY(call)                                                                   \
+    do {                                                                               \
+        cudaError_t _e = (call);                                                       \
+        if (_e != cudaSuccess) {                                                       \
+            release();                                                                 \
+            return sp_fail_cuda(s, _e, #call, __FILE__, __LINE__);                     \
+        }                                                                              \
+    } while (0)
+    SP_TRY(sp_dmalloc(&d_off, (size_t)(n + 1) * sizeof(int)));
+    {
+        k_coo_counts<<<sp_blocks(n, 256), 256, 0, s->stream>>>(s->nbr_cnt, d_off, n);
+        s->launches++;
+        SP_TRY(cudaGetLastError());
+    }
+    // total = last offset + last count, read before the arrays are filled (two-call protocol)
+    int last_cnt = 0, last_off = 0;
+    SP_TRY(cudaMemcpyAsync(&last_cnt, d_off + n - 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    SP_TRY(cudaStreamSynchronize(s->stream));
+    if ((rc = sp_exclusive_scan_i32(s, d_off, n))) {
+        release();
+        return rc;
+    }
+    SP_TRY(cudaMemcpyAsync(&last_off, d_off + n - 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    SP_TRY(cudaStreamSynchronize(s->stream));
+    const long long total = (long long)last_off + last_cnt;
+    if (total < 0 || total > 2000000000LL) {
+        release();
+        return sp_fail(s, SP_ERR_INVALID, "assemble_matrix: more than 2e9 triplets");
+    }
+    *nnz = total;
+    if (!fill) {
+        release();
+        return SP_OK;
+    }
+    if (cap < total) {
+        release();
+        return sp_fail(s, SP_ERR_INVALID, "assemble_matrix: triplet arrays too small");
+    }
+    SP_TRY(sp_dmalloc(&aval, (size_t)s->cap * capk * sizeof(double)));
+    SP_TRY(sp_dmalloc(&diag, (size_t)n * sizeof(double)));
+    SP_TRY(cudaMemsetAsync(d_flag, 0, sizeof(int), s->stream));
+    const int *ids = nullptr, *cnt = nullptr;
+    if ((rc = sp_poisson_ell_build(s, F, Pm, aval, diag, d_flag, &ids, &cnt))) {
+        release();
+        return rc;
+    }
+    int overflow = 0;
+    SP_TRY(cudaMemcpyAsync(&overflow, d_flag, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    SP_TRY(cudaStreamSynchronize(s->stream));
+    if (overflow) {  // cannot happen after sp_nbr_prepare has grown the lists; kept as a loud guard
+        release();
+        return sp_fail(s, SP_ERR_STATE, "assemble_matrix: a neighbour list overflowed its capacity");
+    }
+    SP_TRY(sp_dmalloc(&dI, (size_t)total * sizeof(long long)));
+    SP_TRY(sp_dmalloc(&dJ, (size_t)total * sizeof(long long)));
+    SP_TRY(sp_dmalloc(&dV, (size_t)total * sizeof(double)));
+    {
+        k_coo_export<<<sp_blocks(n, 128), 128, 0, s->stream>>>(n, capk, cnt, ids, aval, diag, s->ref, d_off, dI, dJ, dV);
+        s->launches++;
+        SP_TRY(cudaGetLastError());
+    }
+    SP_TRY(cudaMemcpyAsync(I, dI, (size_t)total * sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
+    SP_TRY(cudaMemcpyAsync(J, dJ, (size_t)total * sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
+    SP_TRY(cudaMemcpyAsync(V, dV, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    SP_TRY(cudaStreamSynchronize(s->stream));
+#undef SP_TRY
+    release();
+    return SP_OK;
+}

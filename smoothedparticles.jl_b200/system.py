@@ -228,6 +228,24 @@ class ParticleSystem:
         P = _farr(A.params)
         abi.check(self._lib.sp_poisson_apply(self._h, abi.ptr_i32(F), len(F), abi.ptr_f64(P), len(P)), self._h)
 
+    def assemble_matrix(self, A: PoissonOperator):
+        """``assemble_matrix(sys, projection_matrix)`` (src/core.jl:196-225) as COO triplets (I, J, V): 1-based
+        reference indices, the diagonal included, duplicates (narrow-domain double visits) left for the caller's
+        sparse constructor to sum — what the reference passes to ``sparse(I, J, V, N, N)``.  Evaluated on the
+        device (ELL coefficients on the cached neighbour lists) and copied out."""
+        F = self._bind(tuple(A.fields))
+        P = _farr(A.params)
+        nnz = C.c_int64()
+        abi.check(self._lib.sp_assemble_matrix(self._h, abi.ptr_i32(F), len(F), abi.ptr_f64(P), len(P), None, None, None,
+                                               0, C.byref(nnz)), self._h)
+        I = np.empty(max(nnz.value, 1), dtype=np.int64)
+        J = np.empty(max(nnz.value, 1), dtype=np.int64)
+        V = np.empty(max(nnz.value, 1))
+        if nnz.value:
+            abi.check(self._lib.sp_assemble_matrix(self._h, abi.ptr_i32(F), len(F), abi.ptr_f64(P), len(P), abi.ptr_i64(I),
+                                                   abi.ptr_i64(J), abi.ptr_f64(V), nnz.value, C.byref(nnz)), self._h)
+        return I[:nnz.value], J[:nnz.value], V[:nnz.value]
+
     def poisson_cg(self, A: PoissonOperator, b: str, P_out: str, reltol=None, abstol=0.0, maxiter=0):
         """``P .= cg(A, b)`` (collapse_dry_implicit.jl:227) without assembling A."""
         if reltol is None:
@@ -350,6 +368,15 @@ def apply_binary(sys: ParticleSystem, op: Operator, strict_order: bool = False):
 
 def assemble_vector(sys: ParticleSystem, op: Operator) -> np.ndarray:
     return sys.assemble_vector(op)
+
+
+def assemble_matrix(sys: ParticleSystem, A: PoissonOperator):
+    """``assemble_matrix(sys, func)`` (src/core.jl:196-225): the N x N matrix as ``scipy.sparse.csc_matrix`` (the
+    reference returns a SparseMatrixCSC); duplicate triplets are summed, as ``sparse()`` does."""
+    import scipy.sparse as sps
+    I, J, V = sys.assemble_matrix(A)
+    n = len(sys)
+    return sps.coo_matrix((V, (I - 1, J - 1)), shape=(n, n)).tocsc()
 
 
 def _named_kernel(kernel: str, kfun: str):
