@@ -220,8 +220,28 @@ enum {
     /* unary. fields {v, f, X}; params {hdt, m, X1_clamp}   v += hdt*f/m;  if X[1] < X1_clamp: v = 0   rod.jl:168-174 */
     SP_OP_ROD_UPDATE_X = 65,
     /* unary. fields {x, v, A, H, f, e}; params {dt}   x += dt*v;  H = A = 0; f = 0; e = 0      rod.jl:176-183 */
-    SP_OP_ROD_FIND_E = 66
+    SP_OP_ROD_FIND_E = 66,
     /* binary. fields {x, X, A, e}; params {h}   eta = inv(A_p)*X_pq - x_pq;  e_p += dot(eta, eta)   rod.jl:185-188 */
+
+    /* SHTC fluid (full 3x3 distortion field A, stress tensor) — examples/SHTC/ldc.jl.  GPU parity check pending
+       (tests/pending_gpu_round2.py); the oracle side is pinned in tests/test_shtc_cpu.py. */
+    SP_OP_SHTC_FIND_STRESS = 70,
+    /* unary. fields {A, rho, stress}; params {c_l, c_s, rho_ref}   G = A'*A;
+       stress = c_l^2*(rho - rho_ref)*I + c_s^2*rho*G*dev(G),  rho_ref = rho0/(1 + acf)        ldc.jl:118-121 */
+    SP_OP_SHTC_UPDATE_V = 71,
+    /* binary. fields {x, v, rho, stress, type}; params {kernel, h, dtm}   if type_p == 0:
+       v_p += ((-dtm*rDw(h,r))*(stress_p/rho_p^2 + stress_q/rho_q^2))*x_pq,  dtm = dt*m             ldc.jl:123-127 */
+    SP_OP_SHTC_UPDATE_RHO = 72,
+    /* binary. fields {x, v, rho, type}; params {kernel, h, dtm}   if type_p == 0:
+       rho_p += (dtm*rDw(h,r))*dot(x_pq, v_pq)                                                     ldc.jl:90-94 */
+    SP_OP_SHTC_CONVECT_A = 73,
+    /* binary, ORDER-DEPENDENT (each pair uses the A_p the previous pairs left): always swept in the reference's
+       visiting order.  fields {x, v, rho, A, type}; params {kernel, h, dtm, skip_type}   if type_p != skip_type:
+       A_p += ((dtm/rho_p*rDw(h,r))*A_p)*(v_pq*x_pq')                                              ldc.jl:96-100 */
+    SP_OP_SHTC_RELAX_A = 74,
+    /* unary. fields {A}; params {dt, tau}   one RK4 step of dA/dt = -3/tau*A*dev(A'*A)             ldc.jl:102-116 */
+    SP_OP_SHTC_MOVE = 75
+    /* unary. fields {x, v, type}; params {dt}   if type == 0: x += v*dt                            ldc.jl:129-133 */
 };
 
 /* sp_apply flags */

@@ -180,6 +180,15 @@ rod_pull(X1_min, fy; X = :X, f = :f) = Operator(63, [X, f], [X1_min, fy])
 rod_update_v(hdt, m, X1_clamp; v = :v, f = :f, X = :X) = Operator(64, [v, f, X], [hdt, m, X1_clamp])
 rod_update_x(dt; x = :x, v = :v, A = :A, H = :H, f = :f, e = :e) = Operator(65, [x, v, A, H, f, e], [dt])
 rod_find_e(h; x = :x, X = :X, A = :A, e = :e) = Operator(66, [x, X, A, e], [h])
+# examples/SHTC/ldc.jl:90-133 (A and stress are 9-component RealMatrix fields; GPU parity check pending)
+shtc_find_stress(c_l, c_s, rho0, acf; A = :A, rho = :rho, stress = :stress) = Operator(70, [A, rho, stress], [c_l, c_s, rho0 / (1.0 + acf)])
+shtc_update_v(kernel, h, dt, m; x = :x, v = :v, rho = :rho, stress = :stress, type = :type) =
+    Operator(71, [x, v, rho, stress, type], [KERNELS[kernel], h, dt * m])
+shtc_update_rho(kernel, h, dt, m; x = :x, v = :v, rho = :rho, type = :type) = Operator(72, [x, v, rho, type], [KERNELS[kernel], h, dt * m])
+shtc_convect_A(kernel, h, dt, m, skip_type; x = :x, v = :v, rho = :rho, A = :A, type = :type) =
+    Operator(73, [x, v, rho, A, type], [KERNELS[kernel], h, dt * m, skip_type])
+shtc_relax_A(dt, tau; A = :A) = Operator(74, [A], [dt, tau])
+shtc_move(dt; x = :x, v = :v, type = :type) = Operator(75, [x, v, type], [dt])
 end # module Operators
 
 # add_new_particles!, examples/cylinder.jl:145-156: particles of `from_type` with x[1] >= x1_min become `to_type`, a new

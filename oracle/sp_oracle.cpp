@@ -406,6 +406,55 @@ inline M2 m2_dev(const M2& g, double* lam_out) {
     return M2{g.a11 - lam, g.a21, g.a12, g.a22 - lam};
 }
 
+// ---- full 3x3 RealMatrix algebra for examples/SHTC/*.jl: 9 slots in Julia's column-major order, a[i + 3*j] = M[i+1,j+1].
+// StaticArrays' SMatrix product is restated as the plain sum over the inner index (the package is neither vendored nor
+// pinned; whether it contracts to FMA is not observable from the reference — tolerance-level either way).
+struct M3 {
+    double a[9];
+};
+inline M3 m3_load(const double* f) {
+    M3 m;
+    for (int c = 0; c < 9; c++) m.a[c] = f[c];
+    return m;
+}
+inline void m3_store(double* f, const M3& m) {
+    for (int c = 0; c < 9; c++) f[c] = m.a[c];
+}
+inline M3 m3_mul(const M3& A, const M3& B) {
+    M3 C;
+    for (int j = 0; j < 3; j++)
+        for (int i = 0; i < 3; i++) C.a[i + 3 * j] = A.a[i] * B.a[3 * j] + A.a[i + 3] * B.a[1 + 3 * j] + A.a[i + 6] * B.a[2 + 3 * j];
+    return C;
+}
+inline M3 m3_tmul(const M3& A, const M3& B) {  // A'*B
+    M3 C;
+    for (int j = 0; j < 3; j++)
+        for (int i = 0; i < 3; i++)
+            C.a[i + 3 * j] = A.a[3 * i] * B.a[3 * j] + A.a[1 + 3 * i] * B.a[1 + 3 * j] + A.a[2 + 3 * i] * B.a[2 + 3 * j];
+    return C;
+}
+inline M3 m3_scale(double c, const M3& A) {
+    M3 C;
+    for (int k = 0; k < 9; k++) C.a[k] = c * A.a[k];
+    return C;
+}
+inline M3 m3_add(const M3& A, const M3& B) {
+    M3 C;
+    for (int k = 0; k < 9; k++) C.a[k] = A.a[k] + B.a[k];
+    return C;
+}
+inline M3 m3_dev(const M3& G) {  // deviatoric, ldc.jl:84-86: G - 1/3*(G11 + G22 + G33)*MAT1
+    const double lam = 1.0 / 3.0 * (G.a[0] + G.a[4] + G.a[8]);
+    M3 C = G;
+    C.a[0] = G.a[0] - lam;
+    C.a[4] = G.a[4] - lam;
+    C.a[8] = G.a[8] - lam;
+    return C;
+}
+inline M3 shtc_relax_f(const M3& A, double tau) {  // ldc.jl:102-104
+    return m3_mul(m3_scale(-3.0 / tau, A), m3_dev(m3_tmul(A, A)));
+}
+
 // apply!, core.jl:151-161, specialised to the registered operators (the example closures).
 int apply_op(OSys& s, int op, const int32_t* F, int nf, const double* P, int np, int flags) {
     auto need = [&](int f, int p) { return nf == f && np == p; };
@@ -852,6 +901,105 @@ int apply_op(OSys& s, int op, const int32_t* F, int nf, const double* P, int np,
                 m2_vec(m2_inv(m2_load(p.f + oA)), Xpq, y);
                 double eta[3] = {y[0] - xpq[0], y[1] - xpq[1], 0.0 - xpq[2]};
                 p.f[oe] += dot3(eta, eta);
+            });
+            return SP_OK;
+        }
+        case SP_OP_SHTC_FIND_STRESS: {  // SHTC/ldc.jl:118-121
+            if (!need(3, 3)) return SP_ERR_INVALID;
+            const int oA = F[0], orho = F[1], oS = F[2];
+            const double c_l = P[0], c_s = P[1], rho_ref = P[2];
+            apply_unary(s, [=](Particle& p) {
+                M3 finger = m3_tmul(m3_load(p.f + oA), m3_load(p.f + oA));
+                M3 S = m3_mul(m3_scale((c_s * c_s) * p.f[orho], finger), m3_dev(finger));
+                const double iso = (c_l * c_l) * (p.f[orho] - rho_ref);
+                S.a[0] = iso + S.a[0];
+                S.a[4] = iso + S.a[4];
+                S.a[8] = iso + S.a[8];
+                m3_store(p.f + oS, S);
+            });
+            return SP_OK;
+        }
+        case SP_OP_SHTC_UPDATE_V: {  // SHTC/ldc.jl:123-127
+            if (!need(5, 3)) return SP_ERR_INVALID;
+            const int ov = F[1], orho = F[2], oS = F[3], ot = F[4];
+            kfn rDw = pick_rD((int)P[0]);
+            const double h = P[1], dtm = P[2];
+            if (!rDw) return SP_ERR_INVALID;
+            apply_binary(s, [=](Particle& p, const Particle& q, const double* xpq, double r) {
+                if (p.f[ot] == 0.0) {
+                    const double c = -dtm * rDw(h, r);
+                    const double rp2 = p.f[orho] * p.f[orho], rq2 = q.f[orho] * q.f[orho];
+                    M3 S;
+                    for (int k = 0; k < 9; k++) S.a[k] = c * (p.f[oS + k] / rp2 + q.f[oS + k] / rq2);
+                    for (int i = 0; i < 3; i++) p.f[ov + i] += S.a[i] * xpq[0] + S.a[i + 3] * xpq[1] + S.a[i + 6] * xpq[2];
+                }
+            });
+            return SP_OK;
+        }
+        case SP_OP_SHTC_UPDATE_RHO: {  // SHTC/ldc.jl:90-94
+            if (!need(4, 3)) return SP_ERR_INVALID;
+            const int ov = F[1], orho = F[2], ot = F[3];
+            kfn rDw = pick_rD((int)P[0]);
+            const double h = P[1], dtm = P[2];
+            if (!rDw) return SP_ERR_INVALID;
+            apply_binary(s, [=](Particle& p, const Particle& q, const double* xpq, double r) {
+                if (p.f[ot] == 0.0) {
+                    double vpq[3] = {p.f[ov] - q.f[ov], p.f[ov + 1] - q.f[ov + 1], p.f[ov + 2] - q.f[ov + 2]};
+                    p.f[orho] += dtm * rDw(h, r) * dot3(xpq, vpq);
+                }
+            });
+            return SP_OK;
+        }
+        case SP_OP_SHTC_CONVECT_A: {  // SHTC/ldc.jl:96-100 (uses the A_p left by the previous pairs: order-dependent)
+            if (!need(5, 4)) return SP_ERR_INVALID;
+            const int ov = F[1], orho = F[2], oA = F[3], ot = F[4];
+            kfn rDw = pick_rD((int)P[0]);
+            const double h = P[1], dtm = P[2], skip = P[3];
+            if (!rDw) return SP_ERR_INVALID;
+            apply_binary(s, [=](Particle& p, const Particle& q, const double* xpq, double r) {
+                if (p.f[ot] != skip) {
+                    M3 A = m3_load(p.f + oA), M;
+                    for (int j = 0; j < 3; j++)
+                        for (int i = 0; i < 3; i++) M.a[i + 3 * j] = (p.f[ov + i] - q.f[ov + i]) * xpq[j];  // v_pq*x_pq'
+                    m3_store(p.f + oA, m3_add(A, m3_mul(m3_scale(dtm / p.f[orho] * rDw(h, r), A), M)));
+                }
+            });
+            return SP_OK;
+        }
+        case SP_OP_SHTC_RELAX_A: {  // SHTC/ldc.jl:106-116 (RK4)
+            if (!need(1, 2)) return SP_ERR_INVALID;
+            const int oA = F[0];
+            const double dt = P[0], tau = P[1];
+            apply_unary(s, [=](Particle& p) {
+                const M3 A = m3_load(p.f + oA);
+                M3 K;
+                // A_new += dt*K/6 ; K = f(A + dt*K/2) ; A_new += dt*K/3 ; K = f(A + dt*K/2) ; A_new += dt*K/3 ;
+                // K = f(A + dt*K) ; A_new += dt*K/6          (dt*K/n is (dt*K)/n, element by element)
+                auto over = [](const M3& X, double n) {
+                    M3 C;
+                    for (int k = 0; k < 9; k++) C.a[k] = X.a[k] / n;
+                    return C;
+                };
+                M3 R = A;
+                K = shtc_relax_f(A, tau);
+                R = m3_add(R, over(m3_scale(dt, K), 6.0));
+                K = shtc_relax_f(m3_add(A, over(m3_scale(dt, K), 2.0)), tau);
+                R = m3_add(R, over(m3_scale(dt, K), 3.0));
+                K = shtc_relax_f(m3_add(A, over(m3_scale(dt, K), 2.0)), tau);
+                R = m3_add(R, over(m3_scale(dt, K), 3.0));
+                K = shtc_relax_f(m3_add(A, m3_scale(dt, K)), tau);
+                R = m3_add(R, over(m3_scale(dt, K), 6.0));
+                m3_store(p.f + oA, R);
+            });
+            return SP_OK;
+        }
+        case SP_OP_SHTC_MOVE: {  // SHTC/ldc.jl:129-133
+            if (!need(3, 1)) return SP_ERR_INVALID;
+            const int ox = F[0], ov = F[1], ot = F[2];
+            const double dt = P[0];
+            apply_unary(s, [=](Particle& p) {
+                if (p.f[ot] == 0.0)
+                    for (int c = 0; c < 3; c++) p.f[ox + c] += p.f[ov + c] * dt;
             });
             return SP_OK;
         }

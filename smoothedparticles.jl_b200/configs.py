@@ -16,6 +16,7 @@ order as the script.  A Case is backend-agnostic: ``case.make(ParticleSystem)`` 
   kepler_vortex          examples/Kepler_vortex.jl           fluid ring in central gravity, same integrator
   cylinder               examples/cylinder.jl                channel flow past a cylinder, inflow buffer, per-particle mass
   rod                    examples/rod.jl                     elastic rod, tensor-valued particle fields
+  shtc_ldc               examples/SHTC/ldc.jl                lid-driven cavity with the SHTC model (3x3 distortion field)
   lattice_box            synthetic S1 block of SURVEY §8(d)  jittered cubic lattice, all fluid
 """
 from __future__ import annotations
@@ -634,6 +635,55 @@ def rod(dr: float = None) -> Case:
 def rod_energy(sys, consts) -> float:
     """sum(p -> particle_energy(p), sys.particles), rod.jl:190-199, :213."""
     return float(sys.reduce(K["SP_RED_ENERGY_ROD"], ("v", "A"), (consts["m"], consts["c_s"], consts["c_l"]))[0])
+
+
+# --------------------------------------------------------------------------- SHTC/ldc.jl
+def shtc_ldc(N: int = 100, Re: float = 100.0) -> Case:
+    """examples/SHTC/ldc.jl:16-39 (constants), :76-88 (geometry), :152-169 (loop): lid-driven cavity with the SHTC
+    model — every particle carries a 3x3 distortion field A (relaxed by an RK4 step) and a stress tensor."""
+    llid, vlid, rho0 = 1.0, 1.0, 1.0
+    c_l, c_s = 20.0, 20.0
+    tau = 6 * vlid * llid / (Re * c_s ** 2)
+    dr = llid / N
+    h = 2.4 * dr
+    m = rho0 * dr ** 2
+    acf = 1e-3
+    wwall = 1.5 * h
+    dt = 0.05 * h / c_l
+    FLUID, WALL, LID = 0.0, 1.0, 2.0
+    grid = geo.Hexagrid(dr)
+    box = geo.Rectangle(0.0, 0.0, llid, llid)
+    layer = geo.BoundaryLayer(box, grid, wwall)
+    lid = geo.Specification(layer, geo.HalfSpace(1, ">", llid))
+    walls = geo.Specification(layer, geo.HalfSpace(1, "<=", llid))
+    domain = (walls + lid + box).boundarybox()
+    xf, xl, xw = geo.covering(grid, box), geo.covering(grid, lid), geo.covering(grid, walls)
+    x = np.concatenate([xf, xl, xw])
+    n = len(x)
+    typ = np.concatenate([np.full(len(xf), FLUID), np.full(len(xl), LID), np.full(len(xw), WALL)])
+    v = np.zeros((n, 3))
+    v[len(xf):len(xf) + len(xl), 0] = vlid
+    A = np.tile(np.eye(3).ravel(), (n, 1))  # MAT1 (symmetric: row- and column-major agree)
+    fields = {"v": 3, "rho": 1, "type": 1, "A": 9, "stress": 9}
+    init = {"x": x, "v": v, "rho": np.full(n, rho0), "type": typ, "A": A}
+    o_s = ops.shtc_find_stress(c_l, c_s, rho0, acf)
+    o_v = ops.shtc_update_v("wendland2", h, dt, m)
+    o_r = ops.shtc_update_rho("wendland2", h, dt, m)
+    o_c = ops.shtc_convect_A("wendland2", h, dt, m, LID)
+    o_x = ops.shtc_relax_A(dt, tau)
+    o_m = ops.shtc_move(dt)
+
+    def step(sys):  # :159-165
+        sys.create_cell_list()
+        sys.apply(o_s)
+        sys.apply(o_v)
+        sys.apply(o_r)
+        sys.apply(o_c)
+        sys.apply(o_x)
+        sys.apply(o_m)
+
+    return Case("shtc_ldc", fields, domain, h, init, step,
+                consts=dict(dr=dr, h=h, m=m, dt=dt, tau=tau, c_l=c_l, c_s=c_s, rho0=rho0, acf=acf, vlid=vlid, LID=LID), dim=2)
 
 
 # --------------------------------------------------------------------------- collapse_dry_implicit.jl

@@ -742,6 +742,188 @@ struct OpRodFindE {
     __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) { P.e[i] = a.e; }
 };
 
+// ---------------------------------------------------------------- examples/SHTC/ldc.jl (full 3x3 RealMatrix fields)
+// a[i + 3*j] = M[i+1, j+1] (Julia's column-major order; plane c of a 9-component field)
+struct SpM3 {
+    double a[9];
+};
+__device__ __forceinline__ SpM3 sp_m3_load(const double* f, long long cap, int i) {
+    SpM3 m;
+#pragma unroll
+    for (int c = 0; c < 9; c++) m.a[c] = f[(size_t)c * cap + i];
+    return m;
+}
+__device__ __forceinline__ void sp_m3_store(double* f, long long cap, int i, const SpM3& m) {
+#pragma unroll
+    for (int c = 0; c < 9; c++) f[(size_t)c * cap + i] = m.a[c];
+}
+__device__ __forceinline__ SpM3 sp_m3_mul(const SpM3& A, const SpM3& B) {
+    SpM3 C;
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) C.a[i + 3 * j] = A.a[i] * B.a[3 * j] + A.a[i + 3] * B.a[1 + 3 * j] + A.a[i + 6] * B.a[2 + 3 * j];
+    return C;
+}
+__device__ __forceinline__ SpM3 sp_m3_tmul(const SpM3& A, const SpM3& B) {  // A'*B
+    SpM3 C;
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            C.a[i + 3 * j] = A.a[3 * i] * B.a[3 * j] + A.a[1 + 3 * i] * B.a[1 + 3 * j] + A.a[2 + 3 * i] * B.a[2 + 3 * j];
+    return C;
+}
+__device__ __forceinline__ SpM3 sp_m3_scale(double c, const SpM3& A) {
+    SpM3 C;
+#pragma unroll
+    for (int k = 0; k < 9; k++) C.a[k] = c * A.a[k];
+    return C;
+}
+__device__ __forceinline__ SpM3 sp_m3_add(const SpM3& A, const SpM3& B) {
+    SpM3 C;
+#pragma unroll
+    for (int k = 0; k < 9; k++) C.a[k] = A.a[k] + B.a[k];
+    return C;
+}
+__device__ __forceinline__ SpM3 sp_m3_over(const SpM3& A, double n) {
+    SpM3 C;
+#pragma unroll
+    for (int k = 0; k < 9; k++) C.a[k] = A.a[k] / n;
+    return C;
+}
+__device__ __forceinline__ SpM3 sp_m3_dev(const SpM3& G) {  // ldc.jl:84-86
+    const double lam = 1.0 / 3.0 * (G.a[0] + G.a[4] + G.a[8]);
+    SpM3 C = G;
+    C.a[0] = G.a[0] - lam; C.a[4] = G.a[4] - lam; C.a[8] = G.a[8] - lam;
+    return C;
+}
+
+// update_v!  ldc.jl:123-127
+template <class K>
+struct OpShtcUpdateV {
+    static constexpr bool LISTS_ONLY = true;  // see SpListsOnly, sp_sweep.cu
+    static constexpr int NQ = 10;             // stress (9 planes), rho
+    struct Params {
+        const double* qp[NQ];
+        const double* type;
+        WV3 v;
+        double dtm;
+        SpKC kc;
+    };
+    struct PS {
+        SpM3 Sp;  // stress_p/rho_p^2: the quotient the closure forms for every pair
+    };
+    struct Acc {
+        double x, y, z;
+    };
+    __device__ static __forceinline__ bool active(const Params& P, int i) { return P.type[i] == 0.0; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
+        const double r = P.qp[9][i], r2 = r * r;
+#pragma unroll
+        for (int c = 0; c < 9; c++) p.Sp.a[c] = P.qp[c][i] / r2;
+        a.x = P.v.x[i]; a.y = P.v.y[i]; a.z = P.v.z[i];
+    }
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, const Q& q, double dx, double dy,
+                                                double dz, double r, Acc& a) {
+        const double c = -P.dtm * K::rD(P.kc, r);
+        const double rq = q(9), rq2 = rq * rq;
+        double S[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) S[k] = c * (p.Sp.a[k] + q(k) / rq2);
+        a.x += S[0] * dx + S[3] * dy + S[6] * dz;
+        a.y += S[1] * dx + S[4] * dy + S[7] * dz;
+        a.z += S[2] * dx + S[5] * dy + S[8] * dz;
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) {
+        P.v.x[i] = a.x; P.v.y[i] = a.y; P.v.z[i] = a.z;
+    }
+};
+
+// update_rho!  ldc.jl:90-94
+template <class K>
+struct OpShtcUpdateRho {
+    static constexpr bool LISTS_ONLY = true;
+    static constexpr int NQ = 3;  // vx, vy, vz
+    struct Params {
+        const double* qp[NQ];
+        const double* type;
+        double* rho;
+        double dtm;
+        SpKC kc;
+    };
+    struct PS {
+        double vx, vy, vz;
+    };
+    struct Acc {
+        double d;
+    };
+    __device__ static __forceinline__ bool active(const Params& P, int i) { return P.type[i] == 0.0; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
+        p.vx = P.qp[0][i]; p.vy = P.qp[1][i]; p.vz = P.qp[2][i];
+        a.d = P.rho[i];
+    }
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, const Q& q, double dx, double dy,
+                                                double dz, double r, Acc& a) {
+        a.d += P.dtm * K::rD(P.kc, r) * (dx * (p.vx - q(0)) + dy * (p.vy - q(1)) + dz * (p.vz - q(2)));
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) { P.rho[i] = a.d; }
+};
+
+// convect_A!  ldc.jl:96-100 — ORDER-DEPENDENT: every pair multiplies the A_p the previous pairs left, so the
+// accumulator IS the running A_p and the sweep always runs in the reference's visiting order (strict kernel)
+template <class K>
+struct OpShtcConvectA {
+    static constexpr bool LISTS_ONLY = true;
+    static constexpr int NQ = 3;  // vx, vy, vz
+    struct Params {
+        const double* qp[NQ];
+        const double *type, *rho;
+        double* A;
+        long long cap;
+        double dtm, skip;
+        SpKC kc;
+    };
+    struct PS {
+        double vx, vy, vz, s0;  // s0 = dtm/rho_p
+    };
+    struct Acc {
+        double a[9];
+    };
+    __device__ static __forceinline__ bool active(const Params& P, int i) { return P.type[i] != P.skip; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
+        p.vx = P.qp[0][i]; p.vy = P.qp[1][i]; p.vz = P.qp[2][i];
+        p.s0 = P.dtm / P.rho[i];
+#pragma unroll
+        for (int c = 0; c < 9; c++) a.a[c] = P.A[(size_t)c * P.cap + i];
+    }
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, const Q& q, double dx, double dy,
+                                                double dz, double r, Acc& a) {
+        const double s = p.s0 * K::rD(P.kc, r);
+        const double v[3] = {p.vx - q(0), p.vy - q(1), p.vz - q(2)}, x[3] = {dx, dy, dz};
+        SpM3 sA, M;
+#pragma unroll
+        for (int k = 0; k < 9; k++) sA.a[k] = s * a.a[k];
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int i = 0; i < 3; i++) M.a[i + 3 * j] = v[i] * x[j];  // v_pq*x_pq'
+        const SpM3 D = sp_m3_mul(sA, M);
+#pragma unroll
+        for (int k = 0; k < 9; k++) a.a[k] += D.a[k];
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) {
+#pragma unroll
+        for (int c = 0; c < 9; c++) P.A[(size_t)c * P.cap + i] = a.a[c];
+    }
+};
+
 // ---------------------------------------------------------------- tests/test_collision_2d.jl
 // find_rho! / find_rho0!  :63-69, used with self=true
 template <class K>
@@ -1269,6 +1451,62 @@ struct URodUpdateX {
         }
         P.f.x[i] = 0.0; P.f.y[i] = 0.0; P.f.z[i] = 0.0;
         P.e[i] = 0.0;
+    }
+};
+// find_stress!  SHTC/ldc.jl:118-121
+struct UShtcFindStress {
+    struct Params {
+        const double *A, *rho;
+        double* stress;
+        long long cap;
+        double cl2, cs2, rho_ref;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        const SpM3 A = sp_m3_load(P.A, P.cap, i);
+        const SpM3 G = sp_m3_tmul(A, A);
+        const double rho = P.rho[i];
+        SpM3 S = sp_m3_mul(sp_m3_scale(P.cs2 * rho, G), sp_m3_dev(G));
+        const double iso = P.cl2 * (rho - P.rho_ref);
+        S.a[0] += iso; S.a[4] += iso; S.a[8] += iso;
+        sp_m3_store(P.stress, P.cap, i, S);
+    }
+};
+// relax_A!  SHTC/ldc.jl:102-116: one RK4 step of dA/dt = -3/tau*A*dev(A'*A)
+struct UShtcRelaxA {
+    struct Params {
+        double* A;
+        long long cap;
+        double dt, m3_over_tau;  // -3/tau
+    };
+    __device__ static __forceinline__ SpM3 f(const SpM3& B, double c) {
+        return sp_m3_mul(sp_m3_scale(c, B), sp_m3_dev(sp_m3_tmul(B, B)));
+    }
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        const SpM3 A = sp_m3_load(P.A, P.cap, i);
+        const double dt = P.dt, c = P.m3_over_tau;
+        SpM3 K = f(A, c);
+        SpM3 R = sp_m3_add(A, sp_m3_over(sp_m3_scale(dt, K), 6.0));
+        K = f(sp_m3_add(A, sp_m3_over(sp_m3_scale(dt, K), 2.0)), c);
+        R = sp_m3_add(R, sp_m3_over(sp_m3_scale(dt, K), 3.0));
+        K = f(sp_m3_add(A, sp_m3_over(sp_m3_scale(dt, K), 2.0)), c);
+        R = sp_m3_add(R, sp_m3_over(sp_m3_scale(dt, K), 3.0));
+        K = f(sp_m3_add(A, sp_m3_scale(dt, K)), c);
+        R = sp_m3_add(R, sp_m3_over(sp_m3_scale(dt, K), 6.0));
+        sp_m3_store(P.A, P.cap, i, R);
+    }
+};
+// move!  SHTC/ldc.jl:129-133
+struct UShtcMove {
+    struct Params {
+        WV3 x;
+        RV3 v;
+        const double* type;
+        double dt;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        if (P.type[i] == 0.0) {
+            P.x.x[i] += P.v.x[i] * P.dt; P.x.y[i] += P.v.y[i] * P.dt; P.x.z[i] += P.v.z[i] * P.dt;
+        }
     }
 };
 // find_pressure!  test_collision_2d.jl:71-73

@@ -1917,6 +1917,62 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
                 P.cap = s->cap;
             });
         }
+        case SP_OP_SHTC_FIND_STRESS: {
+            NEED(3, 3, 9, 1, 9);
+            sp_wrote(s, F[2]);
+            UShtcFindStress::Params P{sc(s, F[0]), sc(s, F[1]), sc(s, F[2]), s->cap, Pm[0] * Pm[0], Pm[1] * Pm[1], Pm[2]};
+            return launch_unary<UShtcFindStress>(s, P);
+        }
+        case SP_OP_SHTC_UPDATE_V: {
+            NEED(5, 3, 3, 3, 1, 9, 1);
+            NEED_CELLS();
+            sp_wrote(s, F[1]);
+            return dispatch_kernel<OpShtcUpdateV>(s, (int)Pm[0], Pm[1], flags, [&](auto& P) {
+                for (int c = 0; c < 9; c++) P.qp[c] = sc(s, F[3]) + (size_t)c * s->cap;
+                P.qp[9] = sc(s, F[2]);
+                P.type = sc(s, F[4]);
+                P.v = wv3(s, F[1]);
+                P.dtm = Pm[2];
+            });
+        }
+        case SP_OP_SHTC_UPDATE_RHO: {
+            NEED(4, 3, 3, 3, 1, 1);
+            NEED_CELLS();
+            sp_wrote(s, F[2]);
+            return dispatch_kernel<OpShtcUpdateRho>(s, (int)Pm[0], Pm[1], flags, [&](auto& P) {
+                set_v3(s, F[1], P.qp);
+                P.type = sc(s, F[3]);
+                P.rho = sc(s, F[2]);
+                P.dtm = Pm[2];
+            });
+        }
+        case SP_OP_SHTC_CONVECT_A: {
+            NEED(5, 4, 3, 3, 1, 9, 1);
+            NEED_CELLS();
+            sp_wrote(s, F[3]);
+            // order-dependent (ldc.jl:98 multiplies the running A_p): always the reference's visiting order
+            return dispatch_kernel<OpShtcConvectA>(s, (int)Pm[0], Pm[1], flags | SP_FLAG_STRICT_ORDER, [&](auto& P) {
+                set_v3(s, F[1], P.qp);
+                P.type = sc(s, F[4]);
+                P.rho = sc(s, F[2]);
+                P.A = sc(s, F[3]);
+                P.cap = s->cap;
+                P.dtm = Pm[2];
+                P.skip = Pm[3];
+            });
+        }
+        case SP_OP_SHTC_RELAX_A: {
+            NEED(1, 2, 9);
+            sp_wrote(s, F[0]);
+            UShtcRelaxA::Params P{sc(s, F[0]), s->cap, Pm[0], -3.0 / Pm[1]};
+            return launch_unary<UShtcRelaxA>(s, P);
+        }
+        case SP_OP_SHTC_MOVE: {
+            NEED(3, 1, 3, 3, 1);
+            sp_wrote(s, F[0]);
+            UShtcMove::Params P{wv3(s, F[0]), rv3(s, F[1]), sc(s, F[2]), Pm[0]};
+            return launch_unary<UShtcMove>(s, P);
+        }
     }
     return sp_fail(s, SP_ERR_INVALID, "unknown operator id");
 }

@@ -215,6 +215,38 @@ def rod_find_e(h, x="x", X="X", A="A", e="e"):
     return Operator(K["SP_OP_ROD_FIND_E"], (x, X, A, e), (h,), True, "find_e!")
 
 
+# ---- examples/SHTC/ldc.jl (SHTC fluid: full 3x3 distortion field A and stress tensor, 9-component fields)
+def shtc_find_stress(c_l, c_s, rho0, acf, A="A", rho="rho", stress="stress"):
+    """ldc.jl:118-121: stress = c_l^2*(rho - rho0/(1 + acf))*I + c_s^2*rho*G*dev(G), G = A'*A."""
+    return Operator(K["SP_OP_SHTC_FIND_STRESS"], (A, rho, stress), (c_l, c_s, rho0 / (1.0 + acf)), False, "find_stress!")
+
+
+def shtc_update_v(kernel, h, dt, m, x="x", v="v", rho="rho", stress="stress", type="type"):
+    """ldc.jl:123-127."""
+    return Operator(K["SP_OP_SHTC_UPDATE_V"], (x, v, rho, stress, type), (_kid(kernel), h, dt * m), True, "update_v!")
+
+
+def shtc_update_rho(kernel, h, dt, m, x="x", v="v", rho="rho", type="type"):
+    """ldc.jl:90-94."""
+    return Operator(K["SP_OP_SHTC_UPDATE_RHO"], (x, v, rho, type), (_kid(kernel), h, dt * m), True, "update_rho!")
+
+
+def shtc_convect_A(kernel, h, dt, m, skip_type, x="x", v="v", rho="rho", A="A", type="type"):
+    """ldc.jl:96-100: A_p += dt*m/rho_p*rDw*A_p*(v_pq*x_pq'), pair after pair in the reference's visiting order."""
+    return Operator(K["SP_OP_SHTC_CONVECT_A"], (x, v, rho, A, type), (_kid(kernel), h, dt * m, skip_type), True,
+                    "convect_A!")
+
+
+def shtc_relax_A(dt, tau, A="A"):
+    """ldc.jl:102-116: one RK4 step of the strain relaxation dA/dt = -3/tau*A*dev(A'*A)."""
+    return Operator(K["SP_OP_SHTC_RELAX_A"], (A,), (dt, tau), False, "relax_A!")
+
+
+def shtc_move(dt, x="x", v="v", type="type"):
+    """ldc.jl:129-133."""
+    return Operator(K["SP_OP_SHTC_MOVE"], (x, v, type), (dt,), False, "move! (SHTC)")
+
+
 # ---- examples/static_container.jl
 def sc_balance_of_mass(kernel, m, h, dt, x="x", v="v", rho="rho"):
     """static_container.jl:102-104: the density is integrated inside the pair loop."""
