@@ -256,3 +256,68 @@ def test_cg_against_an_independent_implementation():
     assert info == 0
     assert abs(count[0] - it) <= max(3, it // 20)
     assert np.linalg.norm(x - xs) <= 1e-5 * np.linalg.norm(xs)
+
+
+def _random_cloud(rng, dim):
+    """A domain of 1-5 cells per axis (narrow ones included) anywhere on the axis, and a cloud with points on cell
+    and domain faces, duplicates, outsiders and non-finite coordinates."""
+    h = float(rng.choice([0.25, 0.3, 1.0 / 3.0, 0.5]))
+    lo = rng.uniform(-2.0, 1.0, 3)
+    ncell = rng.integers(1, 6, 3)
+    hi = lo + ncell * h * rng.uniform(0.6, 1.0, 3)
+    if dim == 2:
+        lo[2] = hi[2] = 0.0
+    n = int(rng.integers(0, 70))
+    x = lo + (hi - lo) * rng.uniform(-0.08, 1.08, (n, 3))
+    if n:
+        on_grid = rng.random((n, 3)) < 0.15                       # exactly on a cell face
+        x = np.where(on_grid, np.floor(x / h) * h, x)
+        on_box = rng.random((n, 3)) < 0.05                        # exactly on a domain face
+        x = np.where(on_box, np.where(rng.random((n, 3)) < 0.5, lo, hi), x)
+        dup = rng.random(n) < 0.1                                 # coincident distinct particles (r = 0)
+        x[dup] = x[rng.integers(0, n, dup.sum())]
+        bad = rng.random(n) < 0.05
+        x[bad, rng.integers(0, 3, bad.sum())] = rng.choice([np.nan, np.inf, -np.inf], bad.sum())
+    if dim == 2:
+        off = rng.random(n) < 0.05                                # a 2-D particle off the plane is outside (z in [0, 0])
+        x[:, 2] = np.where(off, 1e-9, 0.0)
+    return h, lo, hi, x
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_oracle_against_a_literal_python_port_on_random_inputs(dim):
+    from literal_reference import LiteralSystem
+    rng = np.random.default_rng(100 + dim)
+    checked_pairs = removed = 0
+    for trial in range(60):
+        h, lo, hi, x = _random_cloud(rng, dim)
+        n = len(x)
+        ora = OracleSystem({"tag": 1}, geo.Box(*lo, *hi), h)
+        lit = LiteralSystem(lo, hi, h)
+        assert tuple(lit.key_phase) == tuple(ora.key_phase) and tuple(lit.key_lim) == tuple(ora.key_lim)
+        assert lit.key_max == ora.key_max and lit.key_diff == ora.key_diff
+        if n:
+            ora.add_particles(x=x, tag=np.arange(1, n + 1, dtype=float))
+        lit.particles = [{"x": tuple(map(float, x[i])), "tag": i + 1} for i in range(n)]
+        for rebuild in range(2):          # the second build runs on the renumbered survivors and on re-used cells
+            ora.create_cell_list()
+            lit.create_cell_list()
+            m = len(lit.particles)
+            assert len(ora) == m
+            assert list(ora.get("tag").astype(int)) == [p["tag"] for p in lit.particles] if m else True
+            off, mem = ora.cell_list()
+            for k in range(lit.key_max):
+                assert list(mem[off[k]:off[k + 1]]) == [j for j in lit.cell_list[k] if j != 0]
+            noff, nids = ora.neighbour_lists()
+            for i in range(1, m + 1):
+                want = lit.neighbours(i)
+                assert list(nids[noff[i - 1]:noff[i]]) == want      # same neighbours in the same visiting order
+                checked_pairs += len(want)
+            removed += n - m
+            if m:                                                    # move the survivors a little and rebuild
+                xs = ora.get("x") + rng.uniform(-0.3, 0.3, (m, 3)) * h * (1.0 if dim == 3 else np.array([1.0, 1.0, 0.0]))
+                ora.set("x", xs)
+                for p, row in zip(lit.particles, xs):
+                    p["x"] = tuple(map(float, row))
+                n = m
+    assert checked_pairs > 5000 and removed > 100
