@@ -103,3 +103,39 @@ def test_shtc_ldc_operators_and_time_loop():
         case.step(ora)
     assert len(dev) == len(ora) == case.n
     assert_fields_close(dev, ora, ["x", "v", "rho", "A", "stress"], rtol=1e-8, what="SHTC ldc 40 steps")
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_device_cell_list_on_random_clouds(dim):
+    # the randomized corner cases of test_oracle_against_a_literal_python_port_on_random_inputs, device vs oracle:
+    # survivors and numbering, per-cell member lists, neighbour lists in visiting order — all bit-exact
+    from smoothedparticles_jl_b200 import geometry as geo
+    from test_oracle_pins import _random_cloud
+    rng = np.random.default_rng(200 + dim)
+    for trial in range(40):
+        h, lo, hi, x = _random_cloud(rng, dim)
+        n = len(x)
+        box = geo.Box(*lo, *hi)
+        dev, ora = ParticleSystem({"tag": 1}, box, h), OracleSystem({"tag": 1}, box, h)
+        assert tuple(dev.key_lim) == tuple(ora.key_lim) and dev.key_max == ora.key_max
+        if n:
+            for s in (dev, ora):
+                s.add_particles(x=x, tag=np.arange(1, n + 1, dtype=float))
+        for rebuild in range(2):
+            dev.create_cell_list()
+            ora.create_cell_list()
+            assert len(dev) == len(ora)
+            m = len(ora)
+            if m == 0:
+                break
+            assert np.array_equal(dev.get("tag"), ora.get("tag"))
+            assert np.array_equal(dev.cell_keys(), ora.cell_keys())
+            (od, md), (oo, mo) = dev.cell_list(), ora.cell_list()
+            assert np.array_equal(od, oo) and np.array_equal(md, mo)
+            (nd, idd), (no, ido) = dev.neighbour_lists(), ora.neighbour_lists()
+            assert np.array_equal(nd, no) and np.array_equal(idd, ido)
+            (sd, sid), _ = dev.sweep_neighbour_lists(), None
+            assert np.array_equal(np.diff(sd), np.diff(no))          # the cached lists hold the same sets
+            xs = ora.get("x") + rng.uniform(-0.3, 0.3, (m, 3)) * h * (1.0 if dim == 3 else np.array([1.0, 1.0, 0.0]))
+            dev.set("x", xs)
+            ora.set("x", xs)
