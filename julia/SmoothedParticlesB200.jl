@@ -12,7 +12,11 @@
 module SmoothedParticlesB200
 
 export ParticleSystem, create_cell_list!, build_neighbour_lists!, apply!, respawn!, upload!, download, add_particles!, ParticleField,
-       assemble_vector, assemble_matrix, Operators, poisson_cg!, reduce_energy_wcsph, sum_at_points, run_program!, front, cfl_time_step, positions, sp_reduce
+       assemble_vector, assemble_matrix, Operators, poisson_cg!, reduce_energy_wcsph, sum_at_points, run_program!, front, cfl_time_step, positions, sp_reduce,
+       kernel_eval, wendland1, Dwendland1, rDwendland1, wendland2, Dwendland2, rDwendland2, wendland3, Dwendland3, rDwendland3,
+       DDwendland3, spline23, Dspline23, rDspline23, spline24, Dspline24, rDspline24, synchronize, num_removed, key_params,
+       poisson_apply!, cell_keys, cell_list, neighbour_lists, slab_unique_id, slab_init!, slab_range, slab_create_cell_list!,
+       slab_halo_refresh!, slab_num_owned, slab_allreduce!, generate_particles!, HalfSpace
 
 const LIB = get(ENV, "SP_B200_LIB", joinpath(@__DIR__, "..", "smoothedparticles.jl_b200", "libsp_b200.so"))
 
@@ -281,6 +285,174 @@ function sum_at_points(sys::ParticleSystem, sum_op::Integer, fields::Vector{Symb
                 (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{Float64}, Int32, Ptr{Float64}, Int64, Ptr{Float64}),
                 sys.handle, Int32(sum_op), F, length(F), params, length(params), pts, size(pts, 2), out), sys.handle)
     return out
+end
+
+# ---- generate_particles!(sys, grid, shape, constructor) on the device (src/grids.jl:253-258, sp_generate_particles)
+# `grid` and `shape` are the reference package's own objects (SmoothedParticles.Grid(...), Rectangle, Circle, Ball,
+# Boolean +,-,*, BoundaryLayer, Specification): the shape tree is walked by type NAME (no dependency on the package) into
+# the postfix programme of include/sp_b200.h.  A Specification's predicate must be a HalfSpace (below) — a Julia
+# closure cannot run inside a CUDA kernel; use the host path (SP.covering + add_particles!) for anything else.
+struct HalfSpace          # x[axis] op bound, op in (:<, :<=, :>, :>=): the form of every Specification lambda in the examples
+    axis::Int
+    op::Symbol
+    bound::Float64
+end
+(hs::HalfSpace)(x) = getfield(Base, hs.op)(x[hs.axis], hs.bound)   # so that the reference's own is_inside accepts it too
+
+struct ShapeNode          # sp_shape_node
+    kind::Int32
+    a::Int32
+    b::Int32
+    p::NTuple{8,Float64}
+end
+pad8(v...) = ntuple(i -> i <= length(v) ? Float64(v[i]) : 0.0, 8)
+
+function compile_shape!(nodes::Vector{ShapeNode}, offsets::Vector{Float64}, s)
+    T = nameof(typeof(s))
+    emit(kind, a, b, p) = (push!(nodes, ShapeNode(Int32(kind), Int32(a), Int32(b), p)); length(nodes) - 1)
+    if T == :Box
+        return emit(1, 0, 0, pad8(s.x1_min, s.x2_min, s.x3_min, s.x1_max, s.x2_max, s.x3_max))
+    elseif T == :Circle
+        return emit(2, 0, 0, pad8(s.x1, s.x2, s.r * s.r))
+    elseif T == :Ball
+        return emit(3, 0, 0, pad8(s.x1, s.x2, s.x3, s.r * s.r))
+    elseif T in (:BooleanUnion, :BooleanIntersection, :BooleanDifference)
+        a = compile_shape!(nodes, offsets, s.s1)
+        b = compile_shape!(nodes, offsets, s.s2)
+        return emit(T == :BooleanUnion ? 4 : T == :BooleanIntersection ? 5 : 6, a, b, pad8())
+    elseif T == :Specification
+        s.f isa HalfSpace || error("only HalfSpace predicates can run on the device (a Julia closure cannot)")
+        a = compile_shape!(nodes, offsets, s.s)
+        b = emit(7, s.f.axis - 1, findfirst(==(s.f.op), (:<, :<=, :>, :>=)) - 1, pad8(s.f.bound))
+        return emit(5, b, a, pad8())               # f(x) && is_inside(x, s), geometry.jl:183-185
+    elseif T == :BoundaryLayer
+        isempty(offsets) || error("one BoundaryLayer per shape on the device")
+        a = compile_shape!(nodes, offsets, s.s)
+        for dx in s.dxs, c in 1:3
+            push!(offsets, dx[c])
+        end
+        return emit(8, a, 0, pad8())
+    end
+    error("shape $T is not supported by the device generator")
+end
+
+# `bbox` = SmoothedParticles.boundarybox(shape); `constants` = the fields the constructor sets to a constant
+function generate_particles!(sys::ParticleSystem, grid, shape, bbox; constants...)
+    G = nameof(typeof(grid))
+    kind, a, b = G == :Squaregrid ? (1, grid.dr, grid.dr) : G == :Hexagrid ? (2, grid.a, grid.b) :
+                 G == :CubicGrid ? (3, grid.dr, grid.dr) : error("grid $G is not supported by the device generator")
+    fl(v, d) = Int64(floor(v / d)); cl(v, d) = Int64(ceil(v / d))
+    irange = Int64[fl(bbox.x1_min, a) - (kind == 2 ? 1 : 0), cl(bbox.x1_max, a), fl(bbox.x2_min, b), cl(bbox.x2_max, b),
+                   kind == 3 ? fl(bbox.x3_min, grid.dr) : 0, kind == 3 ? cl(bbox.x3_max, grid.dr) : 0]   # grids.jl:53-56,76-79,129-134
+    nodes = ShapeNode[]; offsets = Float64[]
+    compile_shape!(nodes, offsets, shape)
+    ff = Int32[sys.fields[k][1] for (k, _) in constants]
+    fv = Float64[v for (_, v) in constants]
+    added = Ref{Int64}(0)
+    check(ccall((:sp_generate_particles, LIB), Int32,
+                (Ptr{Cvoid}, Int32, Float64, Ptr{ShapeNode}, Int32, Ptr{Float64}, Int32, Ptr{Int64}, Ptr{Int32}, Ptr{Float64}, Int32,
+                 Ref{Int64}),
+                sys.handle, Int32(kind), grid.dr, nodes, length(nodes), isempty(offsets) ? zeros(3) : offsets,
+                length(offsets) ÷ 3, irange, isempty(ff) ? Int32[0] : ff, isempty(fv) ? [0.0] : fv, length(ff), added), sys.handle)
+    return added[]
+end
+
+# ---- kernel functions under the reference's names (src/kernels.jl), evaluated by the library: wendland2(h, r), ...
+function kernel_eval(kernel::Symbol, kfun::Integer, h::Float64, r::Vector{Float64}; device::Integer = 0)
+    out = similar(r)
+    check(ccall((:sp_kernel_eval, LIB), Int32, (Int32, Int32, Float64, Ptr{Float64}, Ptr{Float64}, Int64, Int32),
+                Int32(KERNELS[kernel]), Int32(kfun), h, r, out, length(r), Int32(device)))
+    return out
+end
+for (k, name) in ((:wendland1, "wendland1"), (:wendland2, "wendland2"), (:wendland3, "wendland3"), (:spline23, "spline23"),
+                  (:spline24, "spline24"))
+    @eval $(Symbol(name))(h::Float64, r::Float64) = kernel_eval($(QuoteNode(k)), 0, h, [r])[1]
+    @eval $(Symbol("D" * name))(h::Float64, r::Float64) = kernel_eval($(QuoteNode(k)), 1, h, [r])[1]
+    @eval $(Symbol("rD" * name))(h::Float64, r::Float64) = kernel_eval($(QuoteNode(k)), 2, h, [r])[1]
+end
+DDwendland3(h::Float64, r::Float64) = kernel_eval(:wendland3, 3, h, [r])[1]
+
+# ---- small entry points
+version() = ccall((:sp_version, LIB), Int32, ())
+function device_count()
+    n = Ref{Int32}(0)
+    check(ccall((:sp_device_count, LIB), Int32, (Ref{Int32},), n))
+    return Int(n[])
+end
+synchronize(sys::ParticleSystem) = check(ccall((:sp_synchronize, LIB), Int32, (Ptr{Cvoid},), sys.handle), sys.handle)
+function num_removed(sys::ParticleSystem)       # particles dropped by create_cell_list! so far (src/core.jl:63-81)
+    n = Ref{Int64}(0)
+    check(ccall((:sp_num_removed, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}), sys.handle, n), sys.handle)
+    return Int(n[])
+end
+function key_params(sys::ParticleSystem)        # key_phase, key_lim, key_max, key_diff of src/structs.jl:63-82
+    phase = zeros(Int64, 3); lim = zeros(Int64, 3); kmax = Ref{Int64}(0); nd = Ref{Int32}(0); diff = zeros(Int64, 27)
+    check(ccall((:sp_key_params, LIB), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ref{Int64}, Ref{Int32}, Ptr{Int64}),
+                sys.handle, phase, lim, kmax, nd, diff), sys.handle)
+    return phase, lim, kmax[], diff[1:nd[]]
+end
+# (A p) of the pressure matrix without assembling it, collapse_dry_implicit.jl:154-163
+function poisson_apply!(sys::ParticleSystem, kernel, m, h, rho, C_free, p_in::Symbol, y_out::Symbol;
+                        x = :x, L = :L, lambda = :lambda, type = :type)
+    F = Int32[sys.fields[f][1] for f in (x, L, lambda, type, p_in, y_out)]
+    prm = Float64[KERNELS[kernel], m, h, rho, C_free]
+    check(ccall((:sp_poisson_apply, LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}, Int32, Ptr{Float64}, Int32), sys.handle, F, 6, prm, 5),
+          sys.handle)
+end
+
+# ---- parity / debug views, all in the reference's numbering (1-based)
+function cell_keys(sys::ParticleSystem)         # find_key(sys, particles[i].x) as stored by the last create_cell_list!
+    keys = Vector{Int64}(undef, length(sys))
+    check(ccall((:sp_get_cell_keys, LIB), Int32, (Ptr{Cvoid}, Ptr{Int64}, Int64), sys.handle, keys, length(keys)), sys.handle)
+    return keys
+end
+function cell_list(sys::ParticleSystem)         # CSR view of sys.cell_list: members of cell k in descending index
+    _, _, kmax, _ = key_params(sys)
+    offsets = Vector{Int64}(undef, kmax + 1); members = Vector{Int64}(undef, max(length(sys), 1))
+    check(ccall((:sp_get_cell_list, LIB), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), sys.handle, offsets, members), sys.handle)
+    return offsets, members[1:length(sys)]
+end
+function neighbour_lists(sys::ParticleSystem)   # the q of every action!(p, q, r) call of apply_binary!, in visiting order
+    n = length(sys)
+    offsets = Vector{Int64}(undef, n + 1)
+    check(ccall((:sp_get_neighbour_lists, LIB), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Int64), sys.handle, offsets,
+                C_NULL, 0), sys.handle)
+    ids = Vector{Int64}(undef, max(offsets[end], 1))
+    check(ccall((:sp_get_neighbour_lists, LIB), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Int64), sys.handle, offsets,
+                ids, length(ids)), sys.handle)
+    return offsets, ids[1:offsets[end]]
+end
+
+# ---- slab decomposition, one Julia process per GPU (INTEGRATION.md section 4)
+function slab_unique_id()
+    id = zeros(UInt8, 128)
+    check(ccall((:sp_slab_unique_id, LIB), Int32, (Ptr{UInt8},), id))
+    return id                                     # rank 0 sends these 128 bytes to the other ranks (MPI.jl / sockets)
+end
+slab_init!(sys::ParticleSystem, id::Vector{UInt8}, rank::Integer, nranks::Integer; periodic::Bool = false) =
+    check(ccall((:sp_slab_init, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32, Int32), sys.handle, id, Int32(rank),
+                Int32(nranks), Int32(periodic)), sys.handle)
+function slab_range(sys::ParticleSystem)          # the cell layers [cell_lo, cell_hi) and coordinates this rank owns
+    clo = Ref{Int64}(0); chi = Ref{Int64}(0); xlo = Ref{Float64}(0.0); xhi = Ref{Float64}(0.0); axis = Ref{Int32}(0)
+    check(ccall((:sp_slab_range, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Float64}, Ref{Float64}, Ref{Int32}),
+                sys.handle, clo, chi, xlo, xhi, axis), sys.handle)
+    return clo[], chi[], xlo[], xhi[], Int(axis[]) + 1
+end
+slab_create_cell_list!(sys::ParticleSystem) =     # migration + ghost layers + the local create_cell_list!
+    check(ccall((:sp_slab_create_cell_list, LIB), Int32, (Ptr{Cvoid},), sys.handle), sys.handle)
+function slab_halo_refresh!(sys::ParticleSystem, names::Symbol...)   # e.g. (:rho, :P) after find_pressure!
+    F = Int32[sys.fields[f][1] for f in names]
+    check(ccall((:sp_slab_halo_refresh, LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}, Int32), sys.handle, F, length(F)), sys.handle)
+end
+function slab_num_owned(sys::ParticleSystem)
+    n = Ref{Int64}(0)
+    check(ccall((:sp_slab_num_owned, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}), sys.handle, n), sys.handle)
+    return Int(n[])
+end
+function slab_allreduce!(sys::ParticleSystem, values::Vector{Float64}; max::Bool = false)
+    check(ccall((:sp_slab_allreduce, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int32, Int32), sys.handle, values, length(values),
+                Int32(max)), sys.handle)
+    return values
 end
 
 # ParticleField(sys, :var), src/structs.jl:118-125
