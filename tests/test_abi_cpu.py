@@ -121,3 +121,18 @@ def test_reference_surface_names_exist():
         sp.apply_unary(None, ops.balance_of_mass("wendland2", 1.0, 1.0))
     with pytest.raises(TypeError):
         sp.apply_binary(None, ops.move(0.1))
+
+
+def test_every_entry_point_is_documented_and_bound_for_julia():
+    # the drop-in boundary must not drift: INTEGRATION.md names every exported function, and the Julia ccall shim binds
+    # every one except the instrumentation used only by bench.py / the tests
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    syms = sp.abi.declared_symbols()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    assert [s for s in syms if s not in doc] == []
+    shim = open(os.path.join(root, "julia", "SmoothedParticlesB200.jl")).read()
+    instrumentation = {"sp_find_field", "sp_get_sweep_neighbour_lists", "sp_last_call_ms", "sp_launch_count",
+                       "sp_neighbour_list_capacity", "sp_timer_start", "sp_timer_stop"}
+    assert {s for s in syms if ":" + s not in shim} <= instrumentation
+    # and the Python binding table covers the header exactly
+    assert sorted(sp.abi.SIGNATURES) == syms
