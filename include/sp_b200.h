@@ -240,8 +240,31 @@ enum {
        A_p += ((dtm/rho_p*rDw(h,r))*A_p)*(v_pq*x_pq')                                              ldc.jl:96-100 */
     SP_OP_SHTC_RELAX_A = 74,
     /* unary. fields {A}; params {dt, tau}   one RK4 step of dA/dt = -3/tau*A*dev(A'*A)             ldc.jl:102-116 */
-    SP_OP_SHTC_MOVE = 75
+    SP_OP_SHTC_MOVE = 75,
     /* unary. fields {x, v, type}; params {dt}   if type == 0: x += v*dt                            ldc.jl:129-133 */
+
+    /* SHTC solid in 2-D (vibrating beryllium plate) — examples/SHTC/beryllium.jl.  T, L, A are RealMatrix fields; the
+       script's own outer/det/inv/dev (:79-103) are the 2-D ones (inv sets [3,3] = 1).  w_h / rDw_h are the script's
+       "structural" kernels wendland2h / rDwendland2h (:44-52, strict x < 1).  GPU parity check pending
+       (tests/pending_gpu_round2.py); the oracle side is pinned in tests/test_shtc_cpu.py.  update_x! is SP_OP_ADVECT. */
+    SP_OP_BE_FIND_L = 80,
+    /* binary. fields {x, v, m, T, L}; params {kernel, h, rho0}   ker = m_q/rho0*rDw(h,r):
+       T_p += ker*outer(x_pq, x_pq);  L_p += ker*outer(v_pq, x_pq)                              beryllium.jl:140-146 */
+    SP_OP_BE_UPDATE_A = 81,
+    /* unary. fields {A, T, L}; params {hdt}   L = L*inv(T);  A = A*(I - hdt*L)*inv(I + hdt*L)   beryllium.jl:148-151 */
+    SP_OP_BE_FIND_J = 82,
+    /* binary. fields {x, m, T, J, K}; params {kernel, h, rho0}   T_p += (m_q/rho0*rDw)*outer(x_pq, x_pq);
+       J_p += m_q/rho0*w(h,r);  K_p += m_q/rho0*w_h(h,r)                                         beryllium.jl:153-158 */
+    SP_OP_BE_FIND_T = 83,
+    /* unary. fields {A, T, P, J}; params {rho0, c_0, c_s}   G = A'*A;
+       P = 0.5*rho0*c_0^2*((1 - 1/J)/J^2 + log(J)/J);  T = P/rho0*I - c_s^2*G*dev(G)*inv(T)       beryllium.jl:160-164 */
+    SP_OP_BE_FIND_F = 84,
+    /* binary. fields {x, m, T, K, f}; params {kernel, h, rho0, c_p}   ker = m_q/rho0*rDw, kerh = m_q/rho0*rDw_h:
+       f_p += -m_p*ker*(T_p*x_pq) - m_p*ker*(T_q*x_pq) - (m_p*kerh*c_p^2*(K_p + K_q))*x_pq      beryllium.jl:166-175 */
+    SP_OP_BE_RESET = 85,
+    /* unary. fields {f, L, T, J, K, J0, K0}   f = 0; L = 0; T = 0; J = J0; K = K0                 beryllium.jl:177-184 */
+    SP_OP_BE_UPDATE_V = 86
+    /* unary. fields {v, f, m}; params {hdt}   v += hdt*f/m                                        beryllium.jl:132-134 */
 };
 
 /* sp_apply flags */

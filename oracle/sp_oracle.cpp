@@ -455,6 +455,17 @@ inline M3 shtc_relax_f(const M3& A, double tau) {  // ldc.jl:102-104
     return m3_mul(m3_scale(-3.0 / tau, A), m3_dev(m3_tmul(A, A)));
 }
 
+// ---- examples/SHTC/beryllium.jl:44-52: the "structural" kernels (strict x < 1, plain arithmetic restatement of the
+// script's @fastmath expressions) and :91-98 the script's 2-D inverse, which sets [3,3] = 1
+inline double wendland2h(double h, double r) {
+    const double x = r / h;
+    return x < 1.0 ? 14.0 * pw3(1.0 - x) * (14.0 * pw2(x) - 3.0 * x - 1.0) / (M_PI * pw2(h)) : 0.0;
+}
+inline double rDwendland2h(double h, double r) {
+    const double x = r / h;
+    return x < 1.0 ? 140.0 * pw2(1.0 - x) * (4.0 - 7.0 * x) / (M_PI * pw4(h)) : 0.0;
+}
+
 // apply!, core.jl:151-161, specialised to the registered operators (the example closures).
 int apply_op(OSys& s, int op, const int32_t* F, int nf, const double* P, int np, int flags) {
     auto need = [&](int f, int p) { return nf == f && np == p; };
@@ -1000,6 +1011,126 @@ int apply_op(OSys& s, int op, const int32_t* F, int nf, const double* P, int np,
             apply_unary(s, [=](Particle& p) {
                 if (p.f[ot] == 0.0)
                     for (int c = 0; c < 3; c++) p.f[ox + c] += p.f[ov + c] * dt;
+            });
+            return SP_OK;
+        }
+        case SP_OP_BE_FIND_L: {  // SHTC/beryllium.jl:140-146
+            if (!need(5, 3)) return SP_ERR_INVALID;
+            const int ov = F[1], om = F[2], oT = F[3], oL = F[4];
+            kfn rDw = pick_rD((int)P[0]);
+            const double h = P[1], rho0 = P[2];
+            if (!rDw) return SP_ERR_INVALID;
+            apply_binary(s, [=](Particle& p, const Particle& q, const double* xpq, double r) {
+                const double ker = q.f[om] / rho0 * rDw(h, r);
+                const double vpq[2] = {p.f[ov] - q.f[ov], p.f[ov + 1] - q.f[ov + 1]};
+                // outer(x, y)[i,j] = x[i]*y[j], in-plane block only (:79-85)
+                p.f[oT + 0] += ker * (xpq[0] * xpq[0]);
+                p.f[oT + 1] += ker * (xpq[1] * xpq[0]);
+                p.f[oT + 3] += ker * (xpq[0] * xpq[1]);
+                p.f[oT + 4] += ker * (xpq[1] * xpq[1]);
+                p.f[oL + 0] += ker * (vpq[0] * xpq[0]);
+                p.f[oL + 1] += ker * (vpq[1] * xpq[0]);
+                p.f[oL + 3] += ker * (vpq[0] * xpq[1]);
+                p.f[oL + 4] += ker * (vpq[1] * xpq[1]);
+            });
+            return SP_OK;
+        }
+        case SP_OP_BE_UPDATE_A: {  // SHTC/beryllium.jl:148-151
+            if (!need(3, 1)) return SP_ERR_INVALID;
+            const int oA = F[0], oT = F[1], oL = F[2];
+            const double hdt = P[0];
+            apply_unary(s, [=](Particle& p) {
+                // L = L*inv(T): both in-plane (inv's [3,3] = 1 meets a zero column of L)
+                const M2 L = m2_mul(m2_load(p.f + oL), m2_inv(m2_load(p.f + oT)));
+                m2_store(p.f + oL, L);
+                // A = A*(MAT1 - hdt*L)*inv(MAT1 + hdt*L): block diagonal, the [3,3] entry is A33*1*1
+                const M2 I2{1.0, 0.0, 0.0, 1.0};
+                const M2 hL = m2_scale(hdt, L);
+                const M2 minus{I2.a11 - hL.a11, I2.a21 - hL.a21, I2.a12 - hL.a12, I2.a22 - hL.a22};
+                const M2 A = m2_mul(m2_mul(m2_load(p.f + oA), minus), m2_inv(m2_add(I2, hL)));
+                const double a33 = p.f[oA + 8];
+                m2_store(p.f + oA, A);
+                p.f[oA + 8] = a33;
+            });
+            return SP_OK;
+        }
+        case SP_OP_BE_FIND_J: {  // SHTC/beryllium.jl:153-158
+            if (!need(5, 3)) return SP_ERR_INVALID;
+            const int om = F[1], oT = F[2], oJ = F[3], oK = F[4];
+            kfn rDw = pick_rD((int)P[0]), w = pick_w((int)P[0]);
+            const double h = P[1], rho0 = P[2];
+            if (!rDw || !w) return SP_ERR_INVALID;
+            apply_binary(s, [=](Particle& p, const Particle& q, const double* xpq, double r) {
+                const double ker = q.f[om] / rho0 * rDw(h, r);
+                p.f[oT + 0] += ker * (xpq[0] * xpq[0]);
+                p.f[oT + 1] += ker * (xpq[1] * xpq[0]);
+                p.f[oT + 3] += ker * (xpq[0] * xpq[1]);
+                p.f[oT + 4] += ker * (xpq[1] * xpq[1]);
+                p.f[oJ] += q.f[om] / rho0 * w(h, r);
+                p.f[oK] += q.f[om] / rho0 * wendland2h(h, r);
+            });
+            return SP_OK;
+        }
+        case SP_OP_BE_FIND_T: {  // SHTC/beryllium.jl:160-164
+            if (!need(4, 3)) return SP_ERR_INVALID;
+            const int oA = F[0], oT = F[1], oP = F[2], oJ = F[3];
+            const double rho0 = P[0], c_0 = P[1], c_s = P[2];
+            apply_unary(s, [=](Particle& p) {
+                const M2 A = m2_load(p.f + oA);
+                const double a33 = p.f[oA + 8];
+                const M2 G = m2_mul(m2_trans(A), A);
+                const double g33 = a33 * a33;
+                const double J = p.f[oJ];
+                const double Pr = 0.5 * rho0 * (c_0 * c_0) * ((1.0 - 1.0 / J) / (J * J) + std::log(J) / J);
+                p.f[oP] = Pr;
+                const double tr = 1.0 / 3.0 * (G.a11 + G.a22 + g33);  // dev :100-103
+                const M2 D{G.a11 - tr, G.a21, G.a12, G.a22 - tr};
+                const M2 S = m2_mul(m2_mul(m2_scale(c_s * c_s, G), D), m2_inv(m2_load(p.f + oT)));
+                const double s33 = (c_s * c_s) * g33 * (g33 - tr) * 1.0;  // inv(T)[3,3] = 1 (:91-98)
+                const double iso = Pr / rho0;
+                m2_store(p.f + oT, M2{iso - S.a11, -S.a21, -S.a12, iso - S.a22});
+                p.f[oT + 8] = iso - s33;
+            });
+            return SP_OK;
+        }
+        case SP_OP_BE_FIND_F: {  // SHTC/beryllium.jl:166-175
+            if (!need(5, 4)) return SP_ERR_INVALID;
+            const int om = F[1], oT = F[2], oK = F[3], of = F[4];
+            kfn rDw = pick_rD((int)P[0]);
+            const double h = P[1], rho0 = P[2], c_p = P[3];
+            if (!rDw) return SP_ERR_INVALID;
+            apply_binary(s, [=](Particle& p, const Particle& q, const double* xpq, double r) {
+                const double ker = q.f[om] / rho0 * rDw(h, r);
+                const double kerh = q.f[om] / rho0 * rDwendland2h(h, r);
+                double y[2];
+                m2_vec(m2_load(p.f + oT), xpq, y);
+                p.f[of] += -p.f[om] * ker * y[0];
+                p.f[of + 1] += -p.f[om] * ker * y[1];
+                m2_vec(m2_load(q.f + oT), xpq, y);
+                p.f[of] += -p.f[om] * ker * y[0];
+                p.f[of + 1] += -p.f[om] * ker * y[1];
+                const double a = -p.f[om] * kerh * (c_p * c_p) * (p.f[oK] + q.f[oK]);
+                for (int c = 0; c < 3; c++) p.f[of + c] += a * xpq[c];
+            });
+            return SP_OK;
+        }
+        case SP_OP_BE_RESET: {  // SHTC/beryllium.jl:177-184
+            if (!need(7, 0)) return SP_ERR_INVALID;
+            const int of = F[0], oL = F[1], oT = F[2], oJ = F[3], oK = F[4], oJ0 = F[5], oK0 = F[6];
+            apply_unary(s, [=](Particle& p) {
+                p.f[of] = p.f[of + 1] = p.f[of + 2] = 0.0;
+                for (int c = 0; c < 9; c++) p.f[oL + c] = p.f[oT + c] = 0.0;
+                p.f[oJ] = p.f[oJ0];
+                p.f[oK] = p.f[oK0];
+            });
+            return SP_OK;
+        }
+        case SP_OP_BE_UPDATE_V: {  // SHTC/beryllium.jl:132-134
+            if (!need(3, 1)) return SP_ERR_INVALID;
+            const int ov = F[0], of = F[1], om = F[2];
+            const double hdt = P[0];
+            apply_unary(s, [=](Particle& p) {
+                for (int c = 0; c < 3; c++) p.f[ov + c] += hdt * p.f[of + c] / p.f[om];
             });
             return SP_OK;
         }

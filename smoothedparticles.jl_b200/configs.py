@@ -17,6 +17,7 @@ order as the script.  A Case is backend-agnostic: ``case.make(ParticleSystem)`` 
   cylinder               examples/cylinder.jl                channel flow past a cylinder, inflow buffer, per-particle mass
   rod                    examples/rod.jl                     elastic rod, tensor-valued particle fields
   shtc_ldc               examples/SHTC/ldc.jl                lid-driven cavity with the SHTC model (3x3 distortion field)
+  shtc_beryllium         examples/SHTC/beryllium.jl          vibrating beryllium plate, SHTC solid (2-D)
   lattice_box            synthetic S1 block of SURVEY §8(d)  jittered cubic lattice, all fluid
 """
 from __future__ import annotations
@@ -684,6 +685,83 @@ def shtc_ldc(N: int = 100, Re: float = 100.0) -> Case:
 
     return Case("shtc_ldc", fields, domain, h, init, step,
                 consts=dict(dr=dr, h=h, m=m, dt=dt, tau=tau, c_l=c_l, c_s=c_s, rho0=rho0, acf=acf, vlid=vlid, LID=LID), dim=2)
+
+
+# --------------------------------------------------------------------------- SHTC/beryllium.jl
+def shtc_beryllium(dr: float = None) -> Case:
+    """examples/SHTC/beryllium.jl:13-41 (constants, init_velocity), :109-127 (make_geometry with the J0/K0
+    calibration), :230-245 (loop): a free beryllium plate vibrating in its first bending mode, SHTC solid model."""
+    L, W = 0.06, 0.01
+    c_s = 9046.59
+    c_0 = c_s
+    c_p = 4 * c_0
+    c = math.sqrt(c_0 ** 2 + 4 / 3 * c_s ** 2)
+    rho0 = 1845.0
+    if dr is None:
+        dr = W / 20
+    h = 3.0 * dr
+    m0 = rho0 * dr * dr
+    dt = 0.05 * dr / c
+    grid = geo.Hexagrid(dr)
+    plate = geo.Rectangle(-L / 2, -W / 2, L / 2, W / 2)
+    domain = geo.BoundaryLayer(plate, grid, W).boundarybox()
+    x = geo.covering(grid, plate)
+    n = len(x)
+    # init_velocity :30-39
+    Aamp, omega, alpha, a1, a2 = 4.3369e-5, 2.3597e5, 78.834, 56.6368, 57.6455
+    sarg = alpha * (x[:, 0] + L / 2)
+    v = np.zeros((n, 3))
+    v[:, 1] = Aamp * omega * (a1 * (np.sinh(sarg) + np.sin(sarg)) - a2 * (np.cosh(sarg) + np.cos(sarg)))
+    fields = {"m": 1, "v": 3, "P": 1, "f": 3, "A": 9, "T": 9, "L": 9, "J": 1, "K": 1, "J0": 1, "K0": 1}
+    init = {"x": x, "m": np.full(n, m0), "v": v, "A": np.tile(np.eye(3).ravel(), (n, 1))}
+    o_L = ops.be_find_L("wendland2", h, rho0)
+    o_A = ops.be_update_A(0.5 * dt)
+    o_J = ops.be_find_J("wendland2", h, rho0)
+    o_T = ops.be_find_T(rho0, c_0, c_s)
+    o_f = ops.be_find_f("wendland2", h, rho0, c_p)
+    o_reset = ops.be_reset()
+    o_v = ops.be_update_v(0.5 * dt)
+    o_x = ops.advect(0.5 * dt)
+
+    def prologue(sys):  # make_geometry :114-125
+        sys.create_cell_list()
+        sys.apply(o_J)
+        sys.set("J0", 1.0 - sys.get("J"))   # the host loop `for p in sys.particles` of :117-120
+        sys.set("K0", -sys.get("K"))
+        sys.apply(o_reset)
+        sys.apply(o_J)
+        sys.apply(o_T)
+        sys.apply(o_f)
+
+    def step(sys):  # :232-244
+        sys.apply(o_v)
+        sys.apply(o_x)
+        sys.create_cell_list()
+        sys.apply(o_reset)
+        sys.apply(o_L)
+        sys.apply(o_A)
+        sys.apply(o_x)
+        sys.create_cell_list()
+        sys.apply(o_reset)
+        sys.apply(o_J)
+        sys.apply(o_T)
+        sys.apply(o_f)
+        sys.apply(o_v)
+
+    return Case("shtc_beryllium", fields, domain, h, init, step, prologue,
+                consts=dict(dr=dr, h=h, m0=m0, dt=dt, rho0=rho0, c_0=c_0, c_s=c_s, c_p=c_p, L=L, W=W), dim=2)
+
+
+def beryllium_energy(sys, consts) -> float:
+    """E_kinetic + E_bulk + E_shear + E_penalty of beryllium.jl:189-204, evaluated on the host from downloaded fields
+    (a per-frame diagnostic of the script)."""
+    m, v, J, Kf = sys.get("m"), sys.get("v"), sys.get("J"), sys.get("K")
+    A = sys.get("A").reshape(-1, 3, 3).transpose(0, 2, 1)
+    G = A.transpose(0, 2, 1) @ A
+    dev = G - (np.trace(G, axis1=1, axis2=2) / 3.0)[:, None, None] * np.eye(3)
+    E = (0.5 * m * np.sum(v * v, axis=1) + 0.25 * m * consts["c_0"] ** 2 * ((1.0 - 1.0 / J) ** 2 + np.log(J) ** 2)
+         + 0.25 * m * consts["c_s"] ** 2 * np.sum(dev * dev, axis=(1, 2)) + 0.5 * m * consts["c_p"] ** 2 * Kf ** 2)
+    return float(np.sum(E))
 
 
 # --------------------------------------------------------------------------- collapse_dry_implicit.jl

@@ -247,6 +247,42 @@ def shtc_move(dt, x="x", v="v", type="type"):
     return Operator(K["SP_OP_SHTC_MOVE"], (x, v, type), (dt,), False, "move! (SHTC)")
 
 
+# ---- examples/SHTC/beryllium.jl (SHTC solid in 2-D; T, L, A are 9-component RealMatrix fields)
+def be_find_L(kernel, h, rho0, x="x", v="v", m="m", T="T", L="L"):
+    """beryllium.jl:140-146: T += ker*outer(x_pq, x_pq); L += ker*outer(v_pq, x_pq), ker = m_q/rho0*rDw."""
+    return Operator(K["SP_OP_BE_FIND_L"], (x, v, m, T, L), (_kid(kernel), h, rho0), True, "find_L!")
+
+
+def be_update_A(hdt, A="A", T="T", L="L"):
+    """beryllium.jl:148-151: L = L*inv(T); A = A*(I - hdt*L)*inv(I + hdt*L)."""
+    return Operator(K["SP_OP_BE_UPDATE_A"], (A, T, L), (hdt,), False, "update_A!")
+
+
+def be_find_J(kernel, h, rho0, x="x", m="m", T="T", J="J", Kf="K"):
+    """beryllium.jl:153-158."""
+    return Operator(K["SP_OP_BE_FIND_J"], (x, m, T, J, Kf), (_kid(kernel), h, rho0), True, "find_J!")
+
+
+def be_find_T(rho0, c_0, c_s, A="A", T="T", P="P", J="J"):
+    """beryllium.jl:160-164."""
+    return Operator(K["SP_OP_BE_FIND_T"], (A, T, P, J), (rho0, c_0, c_s), False, "find_T!")
+
+
+def be_find_f(kernel, h, rho0, c_p, x="x", m="m", T="T", Kf="K", f="f"):
+    """beryllium.jl:166-175: stress force of both particles and the anti-clumping force."""
+    return Operator(K["SP_OP_BE_FIND_F"], (x, m, T, Kf, f), (_kid(kernel), h, rho0, c_p), True, "find_f!")
+
+
+def be_reset(f="f", L="L", T="T", J="J", Kf="K", J0="J0", K0="K0"):
+    """beryllium.jl:177-184."""
+    return Operator(K["SP_OP_BE_RESET"], (f, L, T, J, Kf, J0, K0), (), False, "reset!")
+
+
+def be_update_v(hdt, v="v", f="f", m="m"):
+    """beryllium.jl:132-134: v += hdt*f/m."""
+    return Operator(K["SP_OP_BE_UPDATE_V"], (v, f, m), (hdt,), False, "update_v!")
+
+
 # ---- examples/static_container.jl
 def sc_balance_of_mass(kernel, m, h, dt, x="x", v="v", rho="rho"):
     """static_container.jl:102-104: the density is integrated inside the pair loop."""

@@ -127,3 +127,122 @@ def test_shtc_ldc_time_loop():
     assert 0.98 < rho.min() and rho.max() < 1.03
     # a plane flow never couples the in-plane block of A to z (A33 itself relaxes through the trace in dev)
     assert np.all(A[:, 2, :2] == 0.0) and np.all(A[:, :2, 2] == 0.0)
+
+
+# ----------------------------------------------------------------------------- SHTC/beryllium.jl
+def wendland2(h, r):
+    x = r / h
+    return np.where(x <= 1.0, 2.228169203286535 * (1 - x) ** 4 * (1 + 4 * x) / h ** 2, 0.0)
+
+
+def wendland2h(h, r):  # beryllium.jl:44-47
+    x = r / h
+    return np.where(x < 1.0, 14.0 * (1.0 - x) ** 3 * (14.0 * x ** 2 - 3.0 * x - 1.0) / (np.pi * h ** 2), 0.0)
+
+
+def rDwendland2h(h, r):  # beryllium.jl:49-52
+    x = r / h
+    return np.where(x < 1.0, 140.0 * (1.0 - x) ** 2 * (4.0 - 7.0 * x) / (np.pi * h ** 4), 0.0)
+
+
+def beryllium_patch(seed=9):
+    """One end of the plate, deformed and with perturbed masses, after the script's J0/K0 calibration."""
+    case = configs.shtc_beryllium()
+    keep = np.flatnonzero(case.init["x"][:, 0] < -0.02)
+    rng = np.random.default_rng(seed)
+    n = len(keep)
+    X = case.init["x"][keep]
+    x = X.copy()
+    x[:, 1] += 0.8 * (X[:, 0] + 0.03) ** 2 + 0.03 * X[:, 0]
+    x[:, 0] += 0.02 * X[:, 1]
+    x[:, :2] += rng.uniform(-0.02, 0.02, (n, 2)) * case.consts["dr"]
+    A = np.tile(np.eye(3), (n, 1, 1))
+    A[:, :2, :2] += rng.uniform(-0.03, 0.03, (n, 2, 2))
+    s = OracleSystem(case.fields, case.domain, case.h)
+    s.add_particles(x=x, v=rng.uniform(-30, 30, (n, 3)) * np.array([1, 1, 0]), m=case.consts["m0"] * rng.uniform(0.9, 1.1, n),
+                    A=A.transpose(0, 2, 1).reshape(n, 9), J0=rng.uniform(-0.02, 0.02, n), K0=rng.uniform(-1e-3, 1e-3, n))
+    s.create_cell_list()
+    assert len(s) == n
+    return case, s
+
+
+def test_beryllium_operators_against_numpy():
+    case, s = beryllium_patch()
+    c = case.consts
+    h, rho0 = c["h"], c["rho0"]
+    x, v, m, A = s.get("x"), s.get("v"), s.get("m"), mat(s.get("A"))
+    n = len(x)
+    d = x[:, None, :] - x[None, :, :]
+    r = np.sqrt(np.sum(d * d, axis=2))
+    nb = (r <= h) & ~np.eye(n, dtype=bool)
+    ker = np.where(nb, m[None, :] / rho0 * rDwendland2(h, r), 0.0)
+    d2 = d[:, :, :2]
+    # reset! then find_L!  beryllium.jl:177-184, 140-146
+    s.apply(ops.be_reset())
+    assert np.array_equal(s.get("J"), s.get("J0")) and np.array_equal(s.get("K"), s.get("K0"))
+    s.apply(ops.be_find_L("wendland2", h, rho0))
+    T0 = np.einsum("pq,pqi,pqj->pij", ker, d2, d2)
+    L0 = np.einsum("pq,pqi,pqj->pij", ker, (v[:, None, :] - v[None, :, :])[:, :, :2], d2)
+    assert np.max(np.abs(mat(s.get("T"))[:, :2, :2] - T0)) <= 1e-12 * np.max(np.abs(T0))
+    assert np.max(np.abs(mat(s.get("L"))[:, :2, :2] - L0)) <= 1e-12 * np.max(np.abs(L0))
+    # update_A!  :148-151
+    hdt = 0.5 * c["dt"]
+    s.apply(ops.be_update_A(hdt))
+    L = L0 @ np.linalg.inv(T0)
+    I2 = np.eye(2)
+    A2 = A[:, :2, :2] @ (I2 - hdt * L) @ np.linalg.inv(I2 + hdt * L)
+    got = mat(s.get("A"))
+    assert np.max(np.abs(mat(s.get("L"))[:, :2, :2] - L)) <= 1e-10 * np.max(np.abs(L))
+    assert np.max(np.abs(got[:, :2, :2] - A2)) <= 1e-13 and np.all(got[:, 2, 2] == 1.0)
+    assert np.all(got[:, 2, :2] == 0.0) and np.all(got[:, :2, 2] == 0.0)
+    # reset!, find_J!  :153-158
+    s.apply(ops.be_reset())
+    s.apply(ops.be_find_J("wendland2", h, rho0))
+    mr = np.where(nb, m[None, :] / rho0, 0.0)
+    J = s.get("J0") + np.sum(mr * wendland2(h, r), axis=1)
+    Kf = s.get("K0") + np.sum(mr * wendland2h(h, r), axis=1)
+    np.testing.assert_allclose(s.get("J"), J, rtol=1e-13)
+    np.testing.assert_allclose(s.get("K"), Kf, rtol=1e-11, atol=1e-15)
+    assert np.max(np.abs(mat(s.get("T"))[:, :2, :2] - T0)) <= 1e-12 * np.max(np.abs(T0))
+    # find_T!  :160-164
+    s.apply(ops.be_find_T(rho0, c["c_0"], c["c_s"]))
+    Afull = got
+    G = Afull.transpose(0, 2, 1) @ Afull
+    P = 0.5 * rho0 * c["c_0"] ** 2 * ((1.0 - 1.0 / J) / J ** 2 + np.log(J) / J)
+    invT = np.zeros((n, 3, 3))
+    invT[:, :2, :2] = np.linalg.inv(T0)
+    invT[:, 2, 2] = 1.0                                              # the script's 2-D inv, :91-98
+    T = (P / rho0)[:, None, None] * np.eye(3) - c["c_s"] ** 2 * G @ dev(G) @ invT
+    np.testing.assert_allclose(s.get("P"), P, rtol=1e-10, atol=1e-6 * np.max(np.abs(P)))
+    assert np.max(np.abs(mat(s.get("T")) - T)) <= 1e-9 * np.max(np.abs(T))
+    # find_f!  :166-175
+    s.apply(ops.be_find_f("wendland2", h, rho0, c["c_p"]))
+    Tg = mat(s.get("T"))[:, :2, :2]
+    Kg = s.get("K")
+    kerh = np.where(nb, m[None, :] / rho0 * rDwendland2h(h, r), 0.0)
+    f = (-(m[:, None] * ker)[:, :, None] * (np.einsum("pij,pqj->pqi", Tg, d2) + np.einsum("qij,pqj->pqi", Tg, d2))
+         - (m[:, None] * kerh * c["c_p"] ** 2 * (Kg[:, None] + Kg[None, :]))[:, :, None] * d2)
+    want = np.sum(f, axis=1)
+    gotf = s.get("f")
+    assert np.max(np.abs(gotf[:, :2] - want)) <= 1e-10 * np.max(np.abs(want)) and np.all(gotf[:, 2] == 0.0)
+    # update_v!  :132-134
+    s.apply(ops.be_update_v(hdt))
+    assert np.array_equal(s.get("v"), v + hdt * gotf / m[:, None])
+
+
+def test_beryllium_calibration_and_energy_conservation():
+    case = configs.shtc_beryllium()
+    c = case.consts
+    s = case.make(OracleSystem)
+    case.prologue(s)
+    # the J0/K0 calibration (:117-120) makes the undeformed plate stress-free: J = 1, K = 0, no force
+    assert np.max(np.abs(s.get("J") - 1.0)) < 1e-14 and np.max(np.abs(s.get("K"))) < 1e-14
+    assert np.max(np.abs(s.get("f"))) < 1e-9 * c["m0"] * c["c_s"] ** 2 / c["h"]
+    E0 = configs.beryllium_energy(s, c)
+    x0 = s.get("x").copy()
+    for _ in range(300):
+        case.step(s)
+    assert len(s) == case.n
+    E1 = configs.beryllium_energy(s, c)
+    assert abs(E1 - E0) < 1e-5 * E0                        # measured 7e-7: the symplectic splitting conserves energy
+    assert np.max(np.abs(s.get("x") - x0)) > 1e-4          # and the plate does move
