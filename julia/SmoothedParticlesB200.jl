@@ -193,6 +193,14 @@ shtc_convect_A(kernel, h, dt, m, skip_type; x = :x, v = :v, rho = :rho, A = :A, 
     Operator(73, [x, v, rho, A, type], [KERNELS[kernel], h, dt * m, skip_type])
 shtc_relax_A(dt, tau; A = :A) = Operator(74, [A], [dt, tau])
 shtc_move(dt; x = :x, v = :v, type = :type) = Operator(75, [x, v, type], [dt])
+# examples/SHTC/beryllium.jl:132-184 (update_x! is advect; GPU parity check pending)
+be_find_L(kernel, h, rho0; x = :x, v = :v, m = :m, T = :T, L = :L) = Operator(80, [x, v, m, T, L], [KERNELS[kernel], h, rho0])
+be_update_A(hdt; A = :A, T = :T, L = :L) = Operator(81, [A, T, L], [hdt])
+be_find_J(kernel, h, rho0; x = :x, m = :m, T = :T, J = :J, K = :K) = Operator(82, [x, m, T, J, K], [KERNELS[kernel], h, rho0])
+be_find_T(rho0, c_0, c_s; A = :A, T = :T, P = :P, J = :J) = Operator(83, [A, T, P, J], [rho0, c_0, c_s])
+be_find_f(kernel, h, rho0, c_p; x = :x, m = :m, T = :T, K = :K, f = :f) = Operator(84, [x, m, T, K, f], [KERNELS[kernel], h, rho0, c_p])
+be_reset(; f = :f, L = :L, T = :T, J = :J, K = :K, J0 = :J0, K0 = :K0) = Operator(85, [f, L, T, J, K, J0, K0], Float64[])
+be_update_v(hdt; v = :v, f = :f, m = :m) = Operator(86, [v, f, m], [hdt])
 end # module Operators
 
 # add_new_particles!, examples/cylinder.jl:145-156: particles of `from_type` with x[1] >= x1_min become `to_type`, a new

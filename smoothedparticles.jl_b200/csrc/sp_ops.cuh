@@ -924,6 +924,119 @@ struct OpShtcConvectA {
     }
 };
 
+// ---------------------------------------------------------------- examples/SHTC/beryllium.jl (SHTC solid, 2-D)
+// the script's "structural" kernels wendland2h / rDwendland2h (:44-52): strict x < 1
+__device__ __forceinline__ double sp_wendland2h(double h, double r) {
+    const double x = r / h, u = 1.0 - x;
+    return x < 1.0 ? 14.0 * (u * u * u) * (14.0 * (x * x) - 3.0 * x - 1.0) / (3.141592653589793 * (h * h)) : 0.0;
+}
+__device__ __forceinline__ double sp_rDwendland2h(double h, double r) {
+    const double x = r / h, u = 1.0 - x, h2 = h * h;
+    return x < 1.0 ? 140.0 * (u * u) * (4.0 - 7.0 * x) / (3.141592653589793 * (h2 * h2)) : 0.0;
+}
+
+// find_L!  :140-146 and find_J!  :153-158 share the T accumulation; WITH_L adds L, otherwise J and K
+template <class K, bool WITH_L>
+struct OpBeFindLJBase {
+    static constexpr bool LISTS_ONLY = true;
+    static constexpr int NQ = 3;  // m, vx, vy  (v only read when WITH_L)
+    struct Params {
+        const double* qp[NQ];
+        double *T, *L, *J, *Kf;
+        long long cap;
+        double rho0, h;
+        SpKC kc;
+    };
+    struct PS {
+        double vx, vy;
+    };
+    struct Acc {
+        double t11, t21, t12, t22, a, b, c, d;  // WITH_L: L11 L21 L12 L22; else: J, K, -, -
+    };
+    __device__ static __forceinline__ bool active(const Params&, int) { return true; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
+        const SpM2 T = sp_m2_load(P.T, P.cap, i);
+        a.t11 = T.a11; a.t21 = T.a21; a.t12 = T.a12; a.t22 = T.a22;
+        if (WITH_L) {
+            p.vx = P.qp[1][i]; p.vy = P.qp[2][i];
+            const SpM2 L = sp_m2_load(P.L, P.cap, i);
+            a.a = L.a11; a.b = L.a21; a.c = L.a12; a.d = L.a22;
+        } else {
+            p.vx = p.vy = 0.0;
+            a.a = P.J[i]; a.b = P.Kf[i]; a.c = a.d = 0.0;
+        }
+    }
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, const Q& q, double dx, double dy, double,
+                                                double r, Acc& a) {
+        const double mr = q(0) / P.rho0;
+        const double ker = mr * K::rD(P.kc, r);
+        a.t11 += ker * (dx * dx); a.t21 += ker * (dy * dx); a.t12 += ker * (dx * dy); a.t22 += ker * (dy * dy);
+        if (WITH_L) {
+            const double vx = p.vx - q(1), vy = p.vy - q(2);
+            a.a += ker * (vx * dx); a.b += ker * (vy * dx); a.c += ker * (vx * dy); a.d += ker * (vy * dy);
+        } else {
+            a.a += mr * K::w(P.kc, r);
+            a.b += mr * sp_wendland2h(P.h, r);
+        }
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) {
+        sp_m2_store(P.T, P.cap, i, SpM2{a.t11, a.t21, a.t12, a.t22});
+        if (WITH_L) {
+            sp_m2_store(P.L, P.cap, i, SpM2{a.a, a.b, a.c, a.d});
+        } else {
+            P.J[i] = a.a;
+            P.Kf[i] = a.b;
+        }
+    }
+};
+template <class K>
+struct OpBeFindL : OpBeFindLJBase<K, true> {};
+template <class K>
+struct OpBeFindJ : OpBeFindLJBase<K, false> {};
+
+// find_f!  :166-175
+template <class K>
+struct OpBeFindF {
+    static constexpr bool LISTS_ONLY = true;
+    static constexpr int NQ = 6;  // m, K, T11, T21, T12, T22
+    struct Params {
+        const double* qp[NQ];
+        WV3 f;
+        double rho0, cp2, h;
+        SpKC kc;
+    };
+    struct PS {
+        double m, Kf;
+        SpM2 T;
+    };
+    struct Acc {
+        double x, y, z;
+    };
+    __device__ static __forceinline__ bool active(const Params&, int) { return true; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
+        p.m = P.qp[0][i]; p.Kf = P.qp[1][i];
+        p.T = SpM2{P.qp[2][i], P.qp[3][i], P.qp[4][i], P.qp[5][i]};
+        a.x = P.f.x[i]; a.y = P.f.y[i]; a.z = P.f.z[i];
+    }
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, const Q& q, double dx, double dy,
+                                                double dz, double r, Acc& a) {
+        const double mr = q(0) / P.rho0;
+        const double ker = mr * K::rD(P.kc, r), kerh = mr * sp_rDwendland2h(P.h, r);
+        const double c = -p.m * ker;
+        a.x += c * (p.T.a11 * dx + p.T.a12 * dy); a.y += c * (p.T.a21 * dx + p.T.a22 * dy);
+        a.x += c * (q(2) * dx + q(4) * dy); a.y += c * (q(3) * dx + q(5) * dy);
+        const double g = -p.m * kerh * P.cp2 * (p.Kf + q(1));
+        a.x += g * dx; a.y += g * dy; a.z += g * dz;
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) {
+        P.f.x[i] = a.x; P.f.y[i] = a.y; P.f.z[i] = a.z;
+    }
+};
+
 // ---------------------------------------------------------------- tests/test_collision_2d.jl
 // find_rho! / find_rho0!  :63-69, used with self=true
 template <class K>
@@ -1507,6 +1620,80 @@ struct UShtcMove {
         if (P.type[i] == 0.0) {
             P.x.x[i] += P.v.x[i] * P.dt; P.x.y[i] += P.v.y[i] * P.dt; P.x.z[i] += P.v.z[i] * P.dt;
         }
+    }
+};
+// update_A!  SHTC/beryllium.jl:148-151
+struct UBeUpdateA {
+    struct Params {
+        double *A, *T, *L;
+        long long cap;
+        double hdt;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        const SpM2 L = sp_m2_mul(sp_m2_load(P.L, P.cap, i), sp_m2_inv(sp_m2_load(P.T, P.cap, i)));
+        sp_m2_store(P.L, P.cap, i, L);
+        const SpM2 hL = sp_m2_scale(P.hdt, L);
+        const SpM2 minus{1.0 - hL.a11, 0.0 - hL.a21, 0.0 - hL.a12, 1.0 - hL.a22};
+        const SpM2 plus{1.0 + hL.a11, 0.0 + hL.a21, 0.0 + hL.a12, 1.0 + hL.a22};
+        const SpM2 A = sp_m2_mul(sp_m2_mul(sp_m2_load(P.A, P.cap, i), minus), sp_m2_inv(plus));
+        const double a33 = P.A[8 * P.cap + i];
+        sp_m2_store(P.A, P.cap, i, A);
+        P.A[8 * P.cap + i] = a33;
+    }
+};
+// find_T!  SHTC/beryllium.jl:160-164
+struct UBeFindT {
+    struct Params {
+        const double* A;
+        double *T, *P;
+        const double* J;
+        long long cap;
+        double rho0, c02, cs2;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        const SpM2 A = sp_m2_load(P.A, P.cap, i);
+        const double a33 = P.A[8 * P.cap + i], g33 = a33 * a33;
+        const SpM2 G = sp_m2_mul(sp_m2_trans(A), A);
+        const double J = P.J[i];
+        const double Pr = 0.5 * P.rho0 * P.c02 * ((1.0 - 1.0 / J) / (J * J) + log(J) / J);
+        P.P[i] = Pr;
+        const double tr = 1.0 / 3.0 * (G.a11 + G.a22 + g33);
+        const SpM2 D{G.a11 - tr, G.a21, G.a12, G.a22 - tr};
+        const SpM2 S = sp_m2_mul(sp_m2_mul(sp_m2_scale(P.cs2, G), D), sp_m2_inv(sp_m2_load(P.T, P.cap, i)));
+        const double iso = Pr / P.rho0;
+        sp_m2_store(P.T, P.cap, i, SpM2{iso - S.a11, -S.a21, -S.a12, iso - S.a22});
+        P.T[8 * P.cap + i] = iso - P.cs2 * g33 * (g33 - tr);
+    }
+};
+// reset!  SHTC/beryllium.jl:177-184
+struct UBeReset {
+    struct Params {
+        WV3 f;
+        double *L, *T, *J, *Kf;
+        const double *J0, *K0;
+        long long cap;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        P.f.x[i] = 0.0; P.f.y[i] = 0.0; P.f.z[i] = 0.0;
+        for (int c = 0; c < 9; c++) {
+            P.L[(size_t)c * P.cap + i] = 0.0;
+            P.T[(size_t)c * P.cap + i] = 0.0;
+        }
+        P.J[i] = P.J0[i];
+        P.Kf[i] = P.K0[i];
+    }
+};
+// update_v!  SHTC/beryllium.jl:132-134
+struct UBeUpdateV {
+    struct Params {
+        WV3 v;
+        RV3 f;
+        const double* m;
+        double hdt;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        const double m = P.m[i];
+        P.v.x[i] += P.hdt * P.f.x[i] / m; P.v.y[i] += P.hdt * P.f.y[i] / m; P.v.z[i] += P.hdt * P.f.z[i] / m;
     }
 };
 // find_pressure!  test_collision_2d.jl:71-73

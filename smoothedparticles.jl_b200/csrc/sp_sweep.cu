@@ -1973,6 +1973,92 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
             UShtcMove::Params P{wv3(s, F[0]), rv3(s, F[1]), sc(s, F[2]), Pm[0]};
             return launch_unary<UShtcMove>(s, P);
         }
+        case SP_OP_BE_FIND_L: {
+            NEED(5, 3, 3, 3, 1, 9, 9);
+            NEED_CELLS();
+            sp_wrote(s, F[3]);
+            sp_wrote(s, F[4]);
+            return dispatch_kernel<OpBeFindL>(s, (int)Pm[0], Pm[1], flags, [&](auto& P) {
+                P.qp[0] = sc(s, F[2]);
+                P.qp[1] = sc(s, F[1]);
+                P.qp[2] = sc(s, F[1]) + s->cap;
+                P.T = sc(s, F[3]);
+                P.L = sc(s, F[4]);
+                P.J = nullptr;
+                P.Kf = nullptr;
+                P.cap = s->cap;
+                P.rho0 = Pm[2];
+                P.h = Pm[1];
+            });
+        }
+        case SP_OP_BE_UPDATE_A: {
+            NEED(3, 1, 9, 9, 9);
+            sp_wrote(s, F[0]);
+            sp_wrote(s, F[2]);
+            UBeUpdateA::Params P{sc(s, F[0]), sc(s, F[1]), sc(s, F[2]), s->cap, Pm[0]};
+            return launch_unary<UBeUpdateA>(s, P);
+        }
+        case SP_OP_BE_FIND_J: {
+            NEED(5, 3, 3, 1, 9, 1, 1);
+            NEED_CELLS();
+            sp_wrote(s, F[2]);
+            sp_wrote(s, F[3]);
+            sp_wrote(s, F[4]);
+            return dispatch_kernel<OpBeFindJ>(s, (int)Pm[0], Pm[1], flags, [&](auto& P) {
+                P.qp[0] = sc(s, F[1]);
+                P.qp[1] = sc(s, F[1]);  // velocities are not read by find_J!: any valid plane
+                P.qp[2] = sc(s, F[1]);
+                P.T = sc(s, F[2]);
+                P.L = nullptr;
+                P.J = sc(s, F[3]);
+                P.Kf = sc(s, F[4]);
+                P.cap = s->cap;
+                P.rho0 = Pm[2];
+                P.h = Pm[1];
+            });
+        }
+        case SP_OP_BE_FIND_T: {
+            NEED(4, 3, 9, 9, 1, 1);
+            sp_wrote(s, F[1]);
+            sp_wrote(s, F[2]);
+            UBeFindT::Params P{sc(s, F[0]), sc(s, F[1]), sc(s, F[2]), sc(s, F[3]), s->cap, Pm[0], Pm[1] * Pm[1], Pm[2] * Pm[2]};
+            return launch_unary<UBeFindT>(s, P);
+        }
+        case SP_OP_BE_FIND_F: {
+            NEED(5, 4, 3, 1, 9, 1, 3);
+            NEED_CELLS();
+            sp_wrote(s, F[4]);
+            return dispatch_kernel<OpBeFindF>(s, (int)Pm[0], Pm[1], flags, [&](auto& P) {
+                const double* T = sc(s, F[2]);
+                const long long cap = s->cap;
+                P.qp[0] = sc(s, F[1]);
+                P.qp[1] = sc(s, F[3]);
+                P.qp[2] = T; P.qp[3] = T + cap; P.qp[4] = T + 3 * cap; P.qp[5] = T + 4 * cap;
+                P.f = wv3(s, F[4]);
+                P.rho0 = Pm[2];
+                P.cp2 = Pm[3] * Pm[3];
+                P.h = Pm[1];
+            });
+        }
+        case SP_OP_BE_RESET: {
+            const int ncs[] = {3, 9, 9, 1, 1, 1, 1};
+            int rc2 = sp_check_fields(s, F, nf, ncs, 7);
+            if (rc2) return rc2;
+            if (np != 0) return sp_fail(s, SP_ERR_INVALID, "wrong number of parameters for this operator");
+            sp_zeroed(s, F[0]);
+            sp_zeroed(s, F[1]);
+            sp_zeroed(s, F[2]);
+            sp_wrote(s, F[3]);
+            sp_wrote(s, F[4]);
+            UBeReset::Params P{wv3(s, F[0]), sc(s, F[1]), sc(s, F[2]), sc(s, F[3]), sc(s, F[4]), sc(s, F[5]), sc(s, F[6]), s->cap};
+            return launch_unary<UBeReset>(s, P);
+        }
+        case SP_OP_BE_UPDATE_V: {
+            NEED(3, 1, 3, 3, 1);
+            sp_wrote(s, F[0]);
+            UBeUpdateV::Params P{wv3(s, F[0]), rv3(s, F[1]), sc(s, F[2]), Pm[0]};
+            return launch_unary<UBeUpdateV>(s, P);
+        }
     }
     return sp_fail(s, SP_ERR_INVALID, "unknown operator id");
 }

@@ -139,3 +139,54 @@ def test_device_cell_list_on_random_clouds(dim):
             xs = ora.get("x") + rng.uniform(-0.3, 0.3, (m, 3)) * h * (1.0 if dim == 3 else np.array([1.0, 1.0, 0.0]))
             dev.set("x", xs)
             ora.set("x", xs)
+
+
+def test_shtc_beryllium_operators_and_time_loop():
+    # examples/SHTC/beryllium.jl: SHTC solid in 2-D, structural kernels, J0/K0 calibration
+    from smoothedparticles_jl_b200 import operators as ops
+    from parity import RTOL_STEP, assert_fields_close, neighbour_sets_equal
+    from test_shtc_cpu import beryllium_patch
+    case, ora = beryllium_patch()
+    c = case.consts
+    dev = ParticleSystem(case.fields, case.domain, case.h)
+    dev.add_particles(**{f: ora.get(f) for f in ("x", "v", "m", "A", "J0", "K0")})
+    dev.create_cell_list()
+    assert np.array_equal(dev.cell_keys(), ora.cell_keys()) and neighbour_sets_equal(dev, ora, ordered=True)
+    h, rho0, hdt = c["h"], c["rho0"], 0.5 * c["dt"]
+    for s in (dev, ora):
+        s.apply(ops.be_reset())
+        s.apply(ops.be_find_L("wendland2", h, rho0))
+    assert_fields_close(dev, ora, ["T", "L", "J", "K"], rtol=RTOL_STEP, what="reset!, find_L!")
+    for f in ("T", "L"):
+        ora.set(f, dev.get(f))
+    for s in (dev, ora):
+        s.apply(ops.be_update_A(hdt))
+    assert_fields_close(dev, ora, ["A", "L"], rtol=1e-12, what="update_A!")
+    ora.set("A", dev.get("A"))
+    for s in (dev, ora):
+        s.apply(ops.be_reset())
+        s.apply(ops.be_find_J("wendland2", h, rho0))
+    assert_fields_close(dev, ora, ["T", "J", "K"], rtol=RTOL_STEP, what="find_J!", floors={"K": 1e-3})
+    for f in ("T", "J", "K"):
+        ora.set(f, dev.get(f))
+    for s in (dev, ora):
+        s.apply(ops.be_find_T(rho0, c["c_0"], c["c_s"]))
+    assert_fields_close(dev, ora, ["T", "P"], rtol=1e-11, what="find_T!")
+    ora.set("T", dev.get("T"))
+    for s in (dev, ora):
+        s.apply(ops.be_find_f("wendland2", h, rho0, c["c_p"]))
+        s.apply(ops.be_update_v(hdt))
+    assert_fields_close(dev, ora, ["f", "v"], rtol=RTOL_STEP, what="find_f!, update_v!")
+    # the script's loop on the whole plate: calibration, 100 steps, energy
+    case = configs.shtc_beryllium()
+    dev, ora = case.make(ParticleSystem), case.make(OracleSystem)
+    case.prologue(dev)
+    case.prologue(ora)
+    assert np.max(np.abs(dev.get("J") - 1.0)) < 1e-13 and np.max(np.abs(dev.get("K"))) < 1e-13
+    E0 = configs.beryllium_energy(dev, c)
+    for _ in range(100):
+        case.step(dev)
+        case.step(ora)
+    assert len(dev) == len(ora) == case.n
+    assert_fields_close(dev, ora, ["x", "v", "A"], rtol=1e-8, what="beryllium 100 steps")
+    assert abs(configs.beryllium_energy(dev, c) - E0) < 1e-5 * E0
