@@ -263,8 +263,27 @@ enum {
        f_p += -m_p*ker*(T_p*x_pq) - m_p*ker*(T_q*x_pq) - (m_p*kerh*c_p^2*(K_p + K_q))*x_pq      beryllium.jl:166-175 */
     SP_OP_BE_RESET = 85,
     /* unary. fields {f, L, T, J, K, J0, K0}   f = 0; L = 0; T = 0; J = J0; K = K0                 beryllium.jl:177-184 */
-    SP_OP_BE_UPDATE_V = 86
+    SP_OP_BE_UPDATE_V = 86,
     /* unary. fields {v, f, m}; params {hdt}   v += hdt*f/m                                        beryllium.jl:132-134 */
+
+    /* SHTC solid in 3-D (twisting column) — examples/SHTC/twist3d.jl: the beryllium operators with full 3x3 matrices,
+       StaticArrays' general inverse and the 3-D structural kernels wendland3h / rDwendland3h (:43-51).  ORACLE ONLY so
+       far (pinned in tests/test_shtc_cpu.py): sp_apply rejects these ids until the device operators exist.
+       reset! is SP_OP_BE_RESET, update_x! is SP_OP_ADVECT. */
+    SP_OP_TW_FIND_L = 90,
+    /* binary. fields {x, v, m, T, L}; params {kernel, h, rho0}                                  twist3d.jl:135-141 */
+    SP_OP_TW_UPDATE_A = 91,
+    /* unary. fields {A, T, L}; params {hdt}   L = L*inv(T);  A = A*(I - hdt*L)*inv(I + hdt*L)   twist3d.jl:143-146 */
+    SP_OP_TW_FIND_J = 92,
+    /* binary. fields {x, m, T, J, K}; params {kernel, h, rho0}                                  twist3d.jl:148-153 */
+    SP_OP_TW_FIND_T = 93,
+    /* unary. fields {A, T, P, J}; params {rho0, c_0, c_s}   F = inv(A); B = F*F'; detF = 1/J;
+       P = -rho0*c_0^2*detF^2*(detF - 1);  T = -P/rho0*I - c_s^2*(B - I)*inv(T)                    twist3d.jl:155-161 */
+    SP_OP_TW_FIND_F = 94,
+    /* binary. fields {x, m, T, K, f}; params {kernel, h, rho0, c_p}
+       f_p += m_p*ker*(T_p*x_pq) + m_p*ker*(T_q*x_pq) - (m_p*kerh*c_p^2*(K_p + K_q))*x_pq          twist3d.jl:163-172 */
+    SP_OP_TW_UPDATE_V = 95
+    /* unary. fields {x, v, f, m}; params {hdt}   if x[3] > 0: v += hdt*f/m                        twist3d.jl:125-129 */
 };
 
 /* sp_apply flags */

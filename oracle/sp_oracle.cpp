@@ -466,6 +466,41 @@ inline double rDwendland2h(double h, double r) {
     return x < 1.0 ? 140.0 * pw2(1.0 - x) * (4.0 - 7.0 * x) / (M_PI * pw4(h)) : 0.0;
 }
 
+// ---- examples/SHTC/twist3d.jl:43-51 structural kernels in 3-D, and the general 3x3 inverse (StaticArrays.inv is not
+// vendored; restated as adjugate/det like src/algebra.jl:121-158 — tolerance-level against any other formula)
+inline double wendland3h(double h, double r) {
+    const double x = r / h;
+    return x < 1.0 ? 21.0 * pw3(1.0 - x) * (14.0 * pw2(x) - 3.0 * x - 1.0) / (M_PI * pw3(h)) : 0.0;
+}
+inline double rDwendland3h(double h, double r) {
+    const double x = r / h;
+    return x < 1.0 ? 210.0 * pw2(1.0 - x) * (4.0 - 7.0 * x) / (M_PI * (pw4(h) * h)) : 0.0;
+}
+inline double m3_det(const M3& A) {
+    const double* a = A.a;
+    return a[0] * a[4] * a[8] + a[1] * a[5] * a[6] + a[2] * a[3] * a[7] - a[6] * a[4] * a[2] - a[7] * a[5] * a[0] - a[8] * a[3] * a[1];
+}
+inline M3 m3_inv(const M3& A) {
+    const double* a = A.a;
+    const double id = 1.0 / m3_det(A);
+    M3 C;  // inverse[i,j] = cofactor[j,i]/det, column-major
+    C.a[0] = id * (a[4] * a[8] - a[7] * a[5]);
+    C.a[1] = id * (a[7] * a[2] - a[1] * a[8]);
+    C.a[2] = id * (a[1] * a[5] - a[4] * a[2]);
+    C.a[3] = id * (a[6] * a[5] - a[3] * a[8]);
+    C.a[4] = id * (a[0] * a[8] - a[6] * a[2]);
+    C.a[5] = id * (a[3] * a[2] - a[0] * a[5]);
+    C.a[6] = id * (a[3] * a[7] - a[6] * a[4]);
+    C.a[7] = id * (a[6] * a[1] - a[0] * a[7]);
+    C.a[8] = id * (a[0] * a[4] - a[3] * a[1]);
+    return C;
+}
+inline M3 m3_identity() {
+    M3 I;
+    for (int k = 0; k < 9; k++) I.a[k] = (k % 4 == 0) ? 1.0 : 0.0;
+    return I;
+}
+
 // apply!, core.jl:151-161, specialised to the registered operators (the example closures).
 int apply_op(OSys& s, int op, const int32_t* F, int nf, const double* P, int np, int flags) {
     auto need = [&](int f, int p) { return nf == f && np == p; };
@@ -1131,6 +1166,95 @@ int apply_op(OSys& s, int op, const int32_t* F, int nf, const double* P, int np,
             const double hdt = P[0];
             apply_unary(s, [=](Particle& p) {
                 for (int c = 0; c < 3; c++) p.f[ov + c] += hdt * p.f[of + c] / p.f[om];
+            });
+            return SP_OK;
+        }
+        case SP_OP_TW_FIND_L:    // SHTC/twist3d.jl:135-141
+        case SP_OP_TW_FIND_J: {  // SHTC/twist3d.jl:148-153
+            if (!need(5, 3)) return SP_ERR_INVALID;
+            const bool withL = op == SP_OP_TW_FIND_L;
+            const int ov = withL ? F[1] : 0, om = withL ? F[2] : F[1], oT = withL ? F[3] : F[2];
+            const int oL = withL ? F[4] : 0, oJ = withL ? 0 : F[3], oK = withL ? 0 : F[4];
+            kfn rDw = pick_rD((int)P[0]), w = pick_w((int)P[0]);
+            const double h = P[1], rho0 = P[2];
+            if (!rDw || !w) return SP_ERR_INVALID;
+            apply_binary(s, [=](Particle& p, const Particle& q, const double* xpq, double r) {
+                const double ker = q.f[om] / rho0 * rDw(h, r);
+                for (int j = 0; j < 3; j++)
+                    for (int i = 0; i < 3; i++) p.f[oT + i + 3 * j] += ker * (xpq[i] * xpq[j]);  // outer(x, y)[i,j] = x[i]*y[j]
+                if (withL) {
+                    for (int j = 0; j < 3; j++)
+                        for (int i = 0; i < 3; i++) p.f[oL + i + 3 * j] += ker * ((p.f[ov + i] - q.f[ov + i]) * xpq[j]);
+                } else {
+                    p.f[oJ] += q.f[om] / rho0 * w(h, r);
+                    p.f[oK] += q.f[om] / rho0 * wendland3h(h, r);
+                }
+            });
+            return SP_OK;
+        }
+        case SP_OP_TW_UPDATE_A: {  // SHTC/twist3d.jl:143-146
+            if (!need(3, 1)) return SP_ERR_INVALID;
+            const int oA = F[0], oT = F[1], oL = F[2];
+            const double hdt = P[0];
+            apply_unary(s, [=](Particle& p) {
+                const M3 L = m3_mul(m3_load(p.f + oL), m3_inv(m3_load(p.f + oT)));
+                m3_store(p.f + oL, L);
+                const M3 I = m3_identity(), hL = m3_scale(hdt, L);
+                M3 minus;
+                for (int k = 0; k < 9; k++) minus.a[k] = I.a[k] - hL.a[k];
+                m3_store(p.f + oA, m3_mul(m3_mul(m3_load(p.f + oA), minus), m3_inv(m3_add(I, hL))));
+            });
+            return SP_OK;
+        }
+        case SP_OP_TW_FIND_T: {  // SHTC/twist3d.jl:155-161
+            if (!need(4, 3)) return SP_ERR_INVALID;
+            const int oA = F[0], oT = F[1], oP = F[2], oJ = F[3];
+            const double rho0 = P[0], c_0 = P[1], c_s = P[2];
+            apply_unary(s, [=](Particle& p) {
+                const M3 Fm = m3_inv(m3_load(p.f + oA));
+                M3 B;  // F*F'
+                for (int j = 0; j < 3; j++)
+                    for (int i = 0; i < 3; i++)
+                        B.a[i + 3 * j] = Fm.a[i] * Fm.a[j] + Fm.a[i + 3] * Fm.a[j + 3] + Fm.a[i + 6] * Fm.a[j + 6];
+                const double detF = 1.0 / p.f[oJ];
+                const double Pr = -rho0 * (c_0 * c_0) * (detF * detF) * (detF - 1.0);
+                p.f[oP] = Pr;
+                const M3 I = m3_identity();
+                M3 BmI;
+                for (int k = 0; k < 9; k++) BmI.a[k] = B.a[k] - I.a[k];
+                const M3 S = m3_mul(m3_scale(c_s * c_s, BmI), m3_inv(m3_load(p.f + oT)));
+                M3 T;
+                for (int k = 0; k < 9; k++) T.a[k] = -Pr / rho0 * I.a[k] - S.a[k];
+                m3_store(p.f + oT, T);
+            });
+            return SP_OK;
+        }
+        case SP_OP_TW_FIND_F: {  // SHTC/twist3d.jl:163-172
+            if (!need(5, 4)) return SP_ERR_INVALID;
+            const int om = F[1], oT = F[2], oK = F[3], of = F[4];
+            kfn rDw = pick_rD((int)P[0]);
+            const double h = P[1], rho0 = P[2], c_p = P[3];
+            if (!rDw) return SP_ERR_INVALID;
+            apply_binary(s, [=](Particle& p, const Particle& q, const double* xpq, double r) {
+                const double ker = q.f[om] / rho0 * rDw(h, r);
+                const double kerh = q.f[om] / rho0 * rDwendland3h(h, r);
+                for (int pass = 0; pass < 2; pass++) {
+                    const double* T = (pass == 0 ? p.f : q.f) + oT;
+                    for (int i = 0; i < 3; i++)
+                        p.f[of + i] += p.f[om] * ker * (T[i] * xpq[0] + T[i + 3] * xpq[1] + T[i + 6] * xpq[2]);
+                }
+                const double a = -p.f[om] * kerh * (c_p * c_p) * (p.f[oK] + q.f[oK]);
+                for (int c = 0; c < 3; c++) p.f[of + c] += a * xpq[c];
+            });
+            return SP_OK;
+        }
+        case SP_OP_TW_UPDATE_V: {  // SHTC/twist3d.jl:125-129
+            if (!need(4, 1)) return SP_ERR_INVALID;
+            const int ox = F[0], ov = F[1], of = F[2], om = F[3];
+            const double hdt = P[0];
+            apply_unary(s, [=](Particle& p) {
+                if (p.f[ox + 2] > 0.0)
+                    for (int c = 0; c < 3; c++) p.f[ov + c] += hdt * p.f[of + c] / p.f[om];
             });
             return SP_OK;
         }

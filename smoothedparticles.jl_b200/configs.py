@@ -18,6 +18,7 @@ order as the script.  A Case is backend-agnostic: ``case.make(ParticleSystem)`` 
   rod                    examples/rod.jl                     elastic rod, tensor-valued particle fields
   shtc_ldc               examples/SHTC/ldc.jl                lid-driven cavity with the SHTC model (3x3 distortion field)
   shtc_beryllium         examples/SHTC/beryllium.jl          vibrating beryllium plate, SHTC solid (2-D)
+  shtc_twist3d           examples/SHTC/twist3d.jl            twisting rubber column, SHTC solid (3-D) — oracle only so far
   lattice_box            synthetic S1 block of SURVEY §8(d)  jittered cubic lattice, all fluid
 """
 from __future__ import annotations
@@ -762,6 +763,72 @@ def beryllium_energy(sys, consts) -> float:
     E = (0.5 * m * np.sum(v * v, axis=1) + 0.25 * m * consts["c_0"] ** 2 * ((1.0 - 1.0 / J) ** 2 + np.log(J) ** 2)
          + 0.25 * m * consts["c_s"] ** 2 * np.sum(dev * dev, axis=(1, 2)) + 0.5 * m * consts["c_p"] ** 2 * Kf ** 2)
     return float(np.sum(E))
+
+
+# --------------------------------------------------------------------------- SHTC/twist3d.jl
+def shtc_twist3d(dr: float = None) -> Case:
+    """examples/SHTC/twist3d.jl:13-36 (constants, init_velocity), :102-120 (make_geometry), :242-254 (loop): a rubber
+    column clamped below z = 0 and set spinning about its axis, SHTC solid in 3-D on a body-centred lattice.
+    ORACLE ONLY so far (the device has no operators for it yet)."""
+    H, W = 6.0, 1.0
+    omega = 105.0
+    rho0 = 1100.0
+    Y, nu = 17e6, 0.495
+    c_s = math.sqrt(0.5 / rho0 * Y / (1.0 + nu))
+    c_0 = math.sqrt(nu * Y / (rho0 * (1.0 + nu) * (1.0 - 2 * nu)))
+    c_p = c_0
+    c = math.sqrt(c_0 ** 2 + 4 / 3 * c_s ** 2)
+    if dr is None:
+        dr = W / 24
+    h = 3.0 * dr
+    m0 = rho0 * dr * dr * dr
+    dt = 0.2 * dr / c
+    grid = geo.BodycenteredGrid(dr)
+    column = geo.Box(-0.5 * W, -0.5 * W, -h, 0.5 * W, 0.5 * W, H + 0.1 * dr)
+    domain = geo.Box(column.x1_min - W, column.x2_min - W, column.x3_min - W, column.x1_max + W, column.x2_max + W,
+                     column.x3_max + W)   # boundarybox(column + BoundaryLayer(column, grid, W))
+    x = geo.covering(grid, column)
+    n = len(x)
+    spin = (x[:, 2] > 0.0) * omega * np.sin(0.5 * math.pi * x[:, 2] / H)   # init_velocity :36-38
+    v = np.column_stack([spin * x[:, 1], spin * -x[:, 0], spin * 0.0])
+    fields = {"m": 1, "v": 3, "P": 1, "f": 3, "A": 9, "T": 9, "L": 9, "J": 1, "K": 1, "J0": 1, "K0": 1}
+    init = {"x": x, "m": np.full(n, m0), "v": v, "A": np.tile(np.eye(3).ravel(), (n, 1))}
+    o_L = ops.tw_find_L("wendland3", h, rho0)
+    o_A = ops.tw_update_A(0.5 * dt)
+    o_J = ops.tw_find_J("wendland3", h, rho0)
+    o_T = ops.tw_find_T(rho0, c_0, c_s)
+    o_f = ops.tw_find_f("wendland3", h, rho0, c_p)
+    o_reset = ops.be_reset()
+    o_v = ops.tw_update_v(0.5 * dt)
+    o_x = ops.advect(0.5 * dt)
+
+    def prologue(sys):  # :107-118
+        sys.create_cell_list()
+        sys.apply(o_J)
+        sys.set("J0", 1.0 - sys.get("J"))
+        sys.set("K0", -sys.get("K"))
+        sys.apply(o_reset)
+        sys.apply(o_J)
+        sys.apply(o_T)
+        sys.apply(o_f)
+
+    def step(sys):  # :242-254
+        sys.apply(o_v)
+        sys.apply(o_x)
+        sys.create_cell_list()
+        sys.apply(o_reset)
+        sys.apply(o_L)
+        sys.apply(o_A)
+        sys.apply(o_x)
+        sys.create_cell_list()
+        sys.apply(o_reset)
+        sys.apply(o_J)
+        sys.apply(o_T)
+        sys.apply(o_f)
+        sys.apply(o_v)
+
+    return Case("shtc_twist3d", fields, domain, h, init, step, prologue,
+                consts=dict(dr=dr, h=h, m0=m0, dt=dt, rho0=rho0, c_0=c_0, c_s=c_s, c_p=c_p, H=H, W=W, omega=omega), dim=3)
 
 
 # --------------------------------------------------------------------------- collapse_dry_implicit.jl

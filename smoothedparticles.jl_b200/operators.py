@@ -283,6 +283,37 @@ def be_update_v(hdt, v="v", f="f", m="m"):
     return Operator(K["SP_OP_BE_UPDATE_V"], (v, f, m), (hdt,), False, "update_v!")
 
 
+# ---- examples/SHTC/twist3d.jl (SHTC solid in 3-D) — ORACLE ONLY so far: the device rejects these ids
+def tw_find_L(kernel, h, rho0, x="x", v="v", m="m", T="T", L="L"):
+    """twist3d.jl:135-141."""
+    return Operator(K["SP_OP_TW_FIND_L"], (x, v, m, T, L), (_kid(kernel), h, rho0), True, "find_L! (3-D)")
+
+
+def tw_update_A(hdt, A="A", T="T", L="L"):
+    """twist3d.jl:143-146."""
+    return Operator(K["SP_OP_TW_UPDATE_A"], (A, T, L), (hdt,), False, "update_A! (3-D)")
+
+
+def tw_find_J(kernel, h, rho0, x="x", m="m", T="T", J="J", Kf="K"):
+    """twist3d.jl:148-153."""
+    return Operator(K["SP_OP_TW_FIND_J"], (x, m, T, J, Kf), (_kid(kernel), h, rho0), True, "find_J! (3-D)")
+
+
+def tw_find_T(rho0, c_0, c_s, A="A", T="T", P="P", J="J"):
+    """twist3d.jl:155-161."""
+    return Operator(K["SP_OP_TW_FIND_T"], (A, T, P, J), (rho0, c_0, c_s), False, "find_T! (3-D)")
+
+
+def tw_find_f(kernel, h, rho0, c_p, x="x", m="m", T="T", Kf="K", f="f"):
+    """twist3d.jl:163-172."""
+    return Operator(K["SP_OP_TW_FIND_F"], (x, m, T, Kf, f), (_kid(kernel), h, rho0, c_p), True, "find_f! (3-D)")
+
+
+def tw_update_v(hdt, x="x", v="v", f="f", m="m"):
+    """twist3d.jl:125-129: the part of the column below z = 0 is clamped."""
+    return Operator(K["SP_OP_TW_UPDATE_V"], (x, v, f, m), (hdt,), False, "update_v! (3-D)")
+
+
 # ---- examples/static_container.jl
 def sc_balance_of_mass(kernel, m, h, dt, x="x", v="v", rho="rho"):
     """static_container.jl:102-104: the density is integrated inside the pair loop."""

@@ -246,3 +246,109 @@ def test_beryllium_calibration_and_energy_conservation():
     E1 = configs.beryllium_energy(s, c)
     assert abs(E1 - E0) < 1e-5 * E0                        # measured 7e-7: the symplectic splitting conserves energy
     assert np.max(np.abs(s.get("x") - x0)) > 1e-4          # and the plate does move
+
+
+# ----------------------------------------------------------------------------- SHTC/twist3d.jl (oracle only so far)
+def rDwendland3(h, r):  # kernels.jl:188-195
+    x = r / h
+    return np.where(x <= 1.0, -66.84507609859604 * (1 - x) ** 3 / h ** 5, 0.0)
+
+
+def wendland3(h, r):  # kernels.jl:156-163
+    x = r / h
+    return np.where(x <= 1.0, 3.3422538049298023 * (1 - x) ** 4 * (1 + 4 * x) / h ** 3, 0.0)
+
+
+def wendland3h(h, r):  # twist3d.jl:43-46
+    x = r / h
+    return np.where(x < 1.0, 21.0 * (1.0 - x) ** 3 * (14.0 * x ** 2 - 3.0 * x - 1.0) / (np.pi * h ** 3), 0.0)
+
+
+def rDwendland3h(h, r):  # twist3d.jl:48-51
+    x = r / h
+    return np.where(x < 1.0, 210.0 * (1.0 - x) ** 2 * (4.0 - 7.0 * x) / (np.pi * h ** 5), 0.0)
+
+
+def test_twist3d_operators_against_numpy():
+    case = configs.shtc_twist3d(dr=1 / 6)
+    c = case.consts
+    rng = np.random.default_rng(12)
+    keep = np.flatnonzero(case.init["x"][:, 2] < 1.2)               # the clamped foot and the first layers above it
+    n = len(keep)
+    X = case.init["x"][keep]
+    x = X + rng.uniform(-0.05, 0.05, (n, 3)) * c["dr"]
+    x[:, 0] += 0.05 * X[:, 2] * X[:, 1]
+    x[:, 1] -= 0.05 * X[:, 2] * X[:, 0]
+    v = rng.uniform(-20, 20, (n, 3))
+    m = c["m0"] * rng.uniform(0.9, 1.1, n)
+    A = np.tile(np.eye(3), (n, 1, 1)) + rng.uniform(-0.03, 0.03, (n, 3, 3))
+    s = OracleSystem(case.fields, case.domain, case.h)
+    s.add_particles(x=x, v=v, m=m, A=A.transpose(0, 2, 1).reshape(n, 9), J0=rng.uniform(-0.02, 0.02, n),
+                    K0=rng.uniform(-1e-3, 1e-3, n))
+    s.create_cell_list()
+    assert len(s) == n
+    h, rho0, hdt = c["h"], c["rho0"], 0.5 * c["dt"]
+    d = x[:, None, :] - x[None, :, :]
+    r = np.sqrt(np.sum(d * d, axis=2))
+    nb = (r <= h) & ~np.eye(n, dtype=bool)
+    ker = np.where(nb, m[None, :] / rho0 * rDwendland3(h, r), 0.0)
+    s.apply(ops.be_reset())
+    s.apply(ops.tw_find_L("wendland3", h, rho0))
+    T0 = np.einsum("pq,pqi,pqj->pij", ker, d, d)
+    L0 = np.einsum("pq,pqi,pqj->pij", ker, v[:, None, :] - v[None, :, :], d)
+    assert np.max(np.abs(mat(s.get("T")) - T0)) <= 1e-12 * np.max(np.abs(T0))
+    assert np.max(np.abs(mat(s.get("L")) - L0)) <= 1e-12 * np.max(np.abs(L0))
+    s.apply(ops.tw_update_A(hdt))
+    L = L0 @ np.linalg.inv(T0)
+    I3 = np.eye(3)
+    A1 = A @ (I3 - hdt * L) @ np.linalg.inv(I3 + hdt * L)
+    assert np.max(np.abs(mat(s.get("L")) - L)) <= 1e-9 * np.max(np.abs(L))
+    assert np.max(np.abs(mat(s.get("A")) - A1)) <= 1e-12
+    s.apply(ops.be_reset())
+    s.apply(ops.tw_find_J("wendland3", h, rho0))
+    mr = np.where(nb, m[None, :] / rho0, 0.0)
+    J = s.get("J0") + np.sum(mr * wendland3(h, r), axis=1)
+    Kf = s.get("K0") + np.sum(mr * wendland3h(h, r), axis=1)
+    np.testing.assert_allclose(s.get("J"), J, rtol=1e-13)
+    np.testing.assert_allclose(s.get("K"), Kf, rtol=1e-10, atol=1e-14)
+    s.apply(ops.tw_find_T(rho0, c["c_0"], c["c_s"]))
+    Fm = np.linalg.inv(A1)
+    B = Fm @ Fm.transpose(0, 2, 1)
+    detF = 1.0 / J
+    P = -rho0 * c["c_0"] ** 2 * detF ** 2 * (detF - 1.0)
+    T = (-P / rho0)[:, None, None] * I3 - c["c_s"] ** 2 * (B - I3) @ np.linalg.inv(T0)
+    np.testing.assert_allclose(s.get("P"), P, rtol=1e-10, atol=1e-9 * np.max(np.abs(P)))
+    assert np.max(np.abs(mat(s.get("T")) - T)) <= 1e-9 * np.max(np.abs(T))
+    s.apply(ops.tw_find_f("wendland3", h, rho0, c["c_p"]))
+    Tg, Kg = mat(s.get("T")), s.get("K")
+    kerh = np.where(nb, m[None, :] / rho0 * rDwendland3h(h, r), 0.0)
+    f = ((m[:, None] * ker)[:, :, None] * (np.einsum("pij,pqj->pqi", Tg, d) + np.einsum("qij,pqj->pqi", Tg, d))
+         - (m[:, None] * kerh * c["c_p"] ** 2 * (Kg[:, None] + Kg[None, :]))[:, :, None] * d)
+    want = np.sum(f, axis=1)
+    assert np.max(np.abs(s.get("f") - want)) <= 1e-10 * np.max(np.abs(want))
+    v0, fg = s.get("v"), s.get("f")
+    s.apply(ops.tw_update_v(hdt))
+    assert np.array_equal(s.get("v"), np.where((x[:, 2] > 0.0)[:, None], v0 + hdt * fg / m[:, None], v0))
+
+
+def test_twist3d_time_loop_on_the_oracle():
+    case = configs.shtc_twist3d(dr=1 / 8)
+    c = case.consts
+    s = case.make(OracleSystem)
+    case.prologue(s)
+    assert np.max(np.abs(s.get("J") - 1.0)) < 1e-13 and np.max(np.abs(s.get("K"))) < 1e-13     # calibration :110-113
+    x0 = s.get("x").copy()
+    for _ in range(60):
+        case.step(s)
+    assert len(s) == case.n
+    x, A = s.get("x"), mat(s.get("A"))
+    assert np.all(np.isfinite(x)) and np.all(np.isfinite(A))
+    foot = x0[:, 2] <= 0.0
+    assert np.array_equal(x[foot], x0[foot])                           # the clamped foot (:125-129) never moves
+    top = x0[:, 2] > 0.9 * c["H"]
+    ang0, ang1 = np.arctan2(x0[top, 1], x0[top, 0]), np.arctan2(x[top, 1], x[top, 0])
+    rad = np.hypot(x0[top, 0], x0[top, 1]) > 0.2
+    turn = np.angle(np.exp(1j * (ang1 - ang0)))[rad]
+    assert np.all(turn < 0.0) and np.mean(turn) < -0.05                # the top spins clockwise (init_velocity :36-38)
+    dets = np.linalg.det(A)
+    assert 0.9 < dets.min() and dets.max() < 1.1                       # nearly incompressible rubber (nu = 0.495)
