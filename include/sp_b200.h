@@ -267,8 +267,8 @@ enum {
     /* unary. fields {v, f, m}; params {hdt}   v += hdt*f/m                                        beryllium.jl:132-134 */
 
     /* SHTC solid in 3-D (twisting column) — examples/SHTC/twist3d.jl: the beryllium operators with full 3x3 matrices,
-       StaticArrays' general inverse and the 3-D structural kernels wendland3h / rDwendland3h (:43-51).  ORACLE ONLY so
-       far (pinned in tests/test_shtc_cpu.py): sp_apply rejects these ids until the device operators exist.
+       StaticArrays' general inverse and the 3-D structural kernels wendland3h / rDwendland3h (:43-51).  GPU parity check
+       pending (tests/pending_gpu_round2.py); the oracle side is pinned in tests/test_shtc_cpu.py.
        reset! is SP_OP_BE_RESET, update_x! is SP_OP_ADVECT. */
     SP_OP_TW_FIND_L = 90,
     /* binary. fields {x, v, m, T, L}; params {kernel, h, rho0}                                  twist3d.jl:135-141 */

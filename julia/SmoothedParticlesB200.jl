@@ -201,6 +201,13 @@ be_find_T(rho0, c_0, c_s; A = :A, T = :T, P = :P, J = :J) = Operator(83, [A, T, 
 be_find_f(kernel, h, rho0, c_p; x = :x, m = :m, T = :T, K = :K, f = :f) = Operator(84, [x, m, T, K, f], [KERNELS[kernel], h, rho0, c_p])
 be_reset(; f = :f, L = :L, T = :T, J = :J, K = :K, J0 = :J0, K0 = :K0) = Operator(85, [f, L, T, J, K, J0, K0], Float64[])
 be_update_v(hdt; v = :v, f = :f, m = :m) = Operator(86, [v, f, m], [hdt])
+# examples/SHTC/twist3d.jl:125-172 (reset! is be_reset, update_x! is advect; GPU parity check pending)
+tw_find_L(kernel, h, rho0; x = :x, v = :v, m = :m, T = :T, L = :L) = Operator(90, [x, v, m, T, L], [KERNELS[kernel], h, rho0])
+tw_update_A(hdt; A = :A, T = :T, L = :L) = Operator(91, [A, T, L], [hdt])
+tw_find_J(kernel, h, rho0; x = :x, m = :m, T = :T, J = :J, K = :K) = Operator(92, [x, m, T, J, K], [KERNELS[kernel], h, rho0])
+tw_find_T(rho0, c_0, c_s; A = :A, T = :T, P = :P, J = :J) = Operator(93, [A, T, P, J], [rho0, c_0, c_s])
+tw_find_f(kernel, h, rho0, c_p; x = :x, m = :m, T = :T, K = :K, f = :f) = Operator(94, [x, m, T, K, f], [KERNELS[kernel], h, rho0, c_p])
+tw_update_v(hdt; x = :x, v = :v, f = :f, m = :m) = Operator(95, [x, v, f, m], [hdt])
 end # module Operators
 
 # add_new_particles!, examples/cylinder.jl:145-156: particles of `from_type` with x[1] >= x1_min become `to_type`, a new

@@ -18,7 +18,7 @@ order as the script.  A Case is backend-agnostic: ``case.make(ParticleSystem)`` 
   rod                    examples/rod.jl                     elastic rod, tensor-valued particle fields
   shtc_ldc               examples/SHTC/ldc.jl                lid-driven cavity with the SHTC model (3x3 distortion field)
   shtc_beryllium         examples/SHTC/beryllium.jl          vibrating beryllium plate, SHTC solid (2-D)
-  shtc_twist3d           examples/SHTC/twist3d.jl            twisting rubber column, SHTC solid (3-D) — oracle only so far
+  shtc_twist3d           examples/SHTC/twist3d.jl            twisting rubber column, SHTC solid (3-D)
   lattice_box            synthetic S1 block of SURVEY §8(d)  jittered cubic lattice, all fluid
 """
 from __future__ import annotations
@@ -768,8 +768,7 @@ def beryllium_energy(sys, consts) -> float:
 # --------------------------------------------------------------------------- SHTC/twist3d.jl
 def shtc_twist3d(dr: float = None) -> Case:
     """examples/SHTC/twist3d.jl:13-36 (constants, init_velocity), :102-120 (make_geometry), :242-254 (loop): a rubber
-    column clamped below z = 0 and set spinning about its axis, SHTC solid in 3-D on a body-centred lattice.
-    ORACLE ONLY so far (the device has no operators for it yet)."""
+    column clamped below z = 0 and set spinning about its axis, SHTC solid in 3-D on a body-centred lattice."""
     H, W = 6.0, 1.0
     omega = 105.0
     rho0 = 1100.0

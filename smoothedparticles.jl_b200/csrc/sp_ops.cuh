@@ -1037,6 +1037,151 @@ struct OpBeFindF {
     }
 };
 
+// ---------------------------------------------------------------- examples/SHTC/twist3d.jl (SHTC solid, 3-D)
+__device__ __forceinline__ double sp_wendland3h(double h, double r) {  // :43-46, strict x < 1
+    const double x = r / h, u = 1.0 - x;
+    return x < 1.0 ? 21.0 * (u * u * u) * (14.0 * (x * x) - 3.0 * x - 1.0) / (3.141592653589793 * (h * h * h)) : 0.0;
+}
+__device__ __forceinline__ double sp_rDwendland3h(double h, double r) {  // :48-51
+    const double x = r / h, u = 1.0 - x, h2 = h * h;
+    return x < 1.0 ? 210.0 * (u * u) * (4.0 - 7.0 * x) / (3.141592653589793 * (h2 * h2 * h)) : 0.0;
+}
+__device__ __forceinline__ SpM3 sp_m3_inv(const SpM3& A) {  // adjugate / determinant
+    const double* a = A.a;
+    const double det = a[0] * a[4] * a[8] + a[1] * a[5] * a[6] + a[2] * a[3] * a[7] - a[6] * a[4] * a[2] - a[7] * a[5] * a[0] -
+                       a[8] * a[3] * a[1];
+    const double id = 1.0 / det;
+    SpM3 C;
+    C.a[0] = id * (a[4] * a[8] - a[7] * a[5]);
+    C.a[1] = id * (a[7] * a[2] - a[1] * a[8]);
+    C.a[2] = id * (a[1] * a[5] - a[4] * a[2]);
+    C.a[3] = id * (a[6] * a[5] - a[3] * a[8]);
+    C.a[4] = id * (a[0] * a[8] - a[6] * a[2]);
+    C.a[5] = id * (a[3] * a[2] - a[0] * a[5]);
+    C.a[6] = id * (a[3] * a[7] - a[6] * a[4]);
+    C.a[7] = id * (a[6] * a[1] - a[0] * a[7]);
+    C.a[8] = id * (a[0] * a[4] - a[3] * a[1]);
+    return C;
+}
+
+// find_L!  :135-141 and find_J!  :148-153
+template <class K, bool WITH_L>
+struct OpTwFindLJBase {
+    static constexpr bool LISTS_ONLY = true;
+    static constexpr int NQ = 4;  // m, vx, vy, vz  (v only read when WITH_L)
+    struct Params {
+        const double* qp[NQ];
+        double *T, *L, *J, *Kf;
+        long long cap;
+        double rho0, h;
+        SpKC kc;
+    };
+    struct PS {
+        double vx, vy, vz;
+    };
+    struct Acc {
+        double t[9], l[9];  // WITH_L: L; else l[0] = J, l[1] = K
+    };
+    __device__ static __forceinline__ bool active(const Params&, int) { return true; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
+#pragma unroll
+        for (int c = 0; c < 9; c++) {
+            a.t[c] = P.T[(size_t)c * P.cap + i];
+            a.l[c] = WITH_L ? P.L[(size_t)c * P.cap + i] : 0.0;
+        }
+        if (WITH_L) {
+            p.vx = P.qp[1][i]; p.vy = P.qp[2][i]; p.vz = P.qp[3][i];
+        } else {
+            p.vx = p.vy = p.vz = 0.0;
+            a.l[0] = P.J[i];
+            a.l[1] = P.Kf[i];
+        }
+    }
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, const Q& q, double dx, double dy,
+                                                double dz, double r, Acc& a) {
+        const double mr = q(0) / P.rho0;
+        const double ker = mr * K::rD(P.kc, r);
+        const double x[3] = {dx, dy, dz};
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int i = 0; i < 3; i++) a.t[i + 3 * j] += ker * (x[i] * x[j]);
+        if (WITH_L) {
+            const double v[3] = {p.vx - q(1), p.vy - q(2), p.vz - q(3)};
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+#pragma unroll
+                for (int i = 0; i < 3; i++) a.l[i + 3 * j] += ker * (v[i] * x[j]);
+        } else {
+            a.l[0] += mr * K::w(P.kc, r);
+            a.l[1] += mr * sp_wendland3h(P.h, r);
+        }
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) {
+#pragma unroll
+        for (int c = 0; c < 9; c++) {
+            P.T[(size_t)c * P.cap + i] = a.t[c];
+            if (WITH_L) P.L[(size_t)c * P.cap + i] = a.l[c];
+        }
+        if (!WITH_L) {
+            P.J[i] = a.l[0];
+            P.Kf[i] = a.l[1];
+        }
+    }
+};
+template <class K>
+struct OpTwFindL : OpTwFindLJBase<K, true> {};
+template <class K>
+struct OpTwFindJ : OpTwFindLJBase<K, false> {};
+
+// find_f!  :163-172
+template <class K>
+struct OpTwFindF {
+    static constexpr bool LISTS_ONLY = true;
+    static constexpr int NQ = 11;  // m, K, T (9 planes)
+    struct Params {
+        const double* qp[NQ];
+        WV3 f;
+        double rho0, cp2, h;
+        SpKC kc;
+    };
+    struct PS {
+        double m, Kf;
+        double T[9];
+    };
+    struct Acc {
+        double x, y, z;
+    };
+    __device__ static __forceinline__ bool active(const Params&, int) { return true; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
+        p.m = P.qp[0][i]; p.Kf = P.qp[1][i];
+#pragma unroll
+        for (int c = 0; c < 9; c++) p.T[c] = P.qp[2 + c][i];
+        a.x = P.f.x[i]; a.y = P.f.y[i]; a.z = P.f.z[i];
+    }
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, const Q& q, double dx, double dy,
+                                                double dz, double r, Acc& a) {
+        const double mr = q(0) / P.rho0;
+        const double ker = mr * K::rD(P.kc, r), kerh = mr * sp_rDwendland3h(P.h, r);
+        const double c = p.m * ker;
+        a.x += c * (p.T[0] * dx + p.T[3] * dy + p.T[6] * dz);
+        a.y += c * (p.T[1] * dx + p.T[4] * dy + p.T[7] * dz);
+        a.z += c * (p.T[2] * dx + p.T[5] * dy + p.T[8] * dz);
+        a.x += c * (q(2) * dx + q(5) * dy + q(8) * dz);
+        a.y += c * (q(3) * dx + q(6) * dy + q(9) * dz);
+        a.z += c * (q(4) * dx + q(7) * dy + q(10) * dz);
+        const double g = -p.m * kerh * P.cp2 * (p.Kf + q(1));
+        a.x += g * dx; a.y += g * dy; a.z += g * dz;
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) {
+        P.f.x[i] = a.x; P.f.y[i] = a.y; P.f.z[i] = a.z;
+    }
+};
+
 // ---------------------------------------------------------------- tests/test_collision_2d.jl
 // find_rho! / find_rho0!  :63-69, used with self=true
 template <class K>
@@ -1694,6 +1839,70 @@ struct UBeUpdateV {
     __device__ static __forceinline__ void apply(const Params& P, int i) {
         const double m = P.m[i];
         P.v.x[i] += P.hdt * P.f.x[i] / m; P.v.y[i] += P.hdt * P.f.y[i] / m; P.v.z[i] += P.hdt * P.f.z[i] / m;
+    }
+};
+// update_A!  SHTC/twist3d.jl:143-146
+struct UTwUpdateA {
+    struct Params {
+        double *A, *T, *L;
+        long long cap;
+        double hdt;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        const SpM3 L = sp_m3_mul(sp_m3_load(P.L, P.cap, i), sp_m3_inv(sp_m3_load(P.T, P.cap, i)));
+        sp_m3_store(P.L, P.cap, i, L);
+        SpM3 minus, plus;
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            const double e = (k % 4 == 0) ? 1.0 : 0.0, hl = P.hdt * L.a[k];
+            minus.a[k] = e - hl;
+            plus.a[k] = e + hl;
+        }
+        sp_m3_store(P.A, P.cap, i, sp_m3_mul(sp_m3_mul(sp_m3_load(P.A, P.cap, i), minus), sp_m3_inv(plus)));
+    }
+};
+// find_T!  SHTC/twist3d.jl:155-161
+struct UTwFindT {
+    struct Params {
+        const double* A;
+        double *T, *P;
+        const double* J;
+        long long cap;
+        double rho0, c02, cs2;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        const SpM3 F = sp_m3_inv(sp_m3_load(P.A, P.cap, i));
+        SpM3 BmI;  // F*F' - I
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+                BmI.a[r + 3 * j] = (F.a[r] * F.a[j] + F.a[r + 3] * F.a[j + 3] + F.a[r + 6] * F.a[j + 6]) - (r == j ? 1.0 : 0.0);
+        const double detF = 1.0 / P.J[i];
+        const double Pr = -P.rho0 * P.c02 * (detF * detF) * (detF - 1.0);
+        P.P[i] = Pr;
+        const SpM3 S = sp_m3_mul(sp_m3_scale(P.cs2, BmI), sp_m3_inv(sp_m3_load(P.T, P.cap, i)));
+        const double iso = -Pr / P.rho0;
+        SpM3 T;
+#pragma unroll
+        for (int k = 0; k < 9; k++) T.a[k] = ((k % 4 == 0) ? iso : 0.0) - S.a[k];
+        sp_m3_store(P.T, P.cap, i, T);
+    }
+};
+// update_v!  SHTC/twist3d.jl:125-129
+struct UTwUpdateV {
+    struct Params {
+        const double* z;
+        WV3 v;
+        RV3 f;
+        const double* m;
+        double hdt;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        if (P.z[i] > 0.0) {
+            const double m = P.m[i];
+            P.v.x[i] += P.hdt * P.f.x[i] / m; P.v.y[i] += P.hdt * P.f.y[i] / m; P.v.z[i] += P.hdt * P.f.z[i] / m;
+        }
     }
 };
 // find_pressure!  test_collision_2d.jl:71-73

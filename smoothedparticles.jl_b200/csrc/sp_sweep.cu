@@ -2059,6 +2059,74 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
             UBeUpdateV::Params P{wv3(s, F[0]), rv3(s, F[1]), sc(s, F[2]), Pm[0]};
             return launch_unary<UBeUpdateV>(s, P);
         }
+        case SP_OP_TW_FIND_L: {
+            NEED(5, 3, 3, 3, 1, 9, 9);
+            NEED_CELLS();
+            sp_wrote(s, F[3]);
+            sp_wrote(s, F[4]);
+            return dispatch_kernel<OpTwFindL>(s, (int)Pm[0], Pm[1], flags, [&](auto& P) {
+                P.qp[0] = sc(s, F[2]);
+                set_v3(s, F[1], P.qp + 1);
+                P.T = sc(s, F[3]);
+                P.L = sc(s, F[4]);
+                P.J = nullptr;
+                P.Kf = nullptr;
+                P.cap = s->cap;
+                P.rho0 = Pm[2];
+                P.h = Pm[1];
+            });
+        }
+        case SP_OP_TW_UPDATE_A: {
+            NEED(3, 1, 9, 9, 9);
+            sp_wrote(s, F[0]);
+            sp_wrote(s, F[2]);
+            UTwUpdateA::Params P{sc(s, F[0]), sc(s, F[1]), sc(s, F[2]), s->cap, Pm[0]};
+            return launch_unary<UTwUpdateA>(s, P);
+        }
+        case SP_OP_TW_FIND_J: {
+            NEED(5, 3, 3, 1, 9, 1, 1);
+            NEED_CELLS();
+            sp_wrote(s, F[2]);
+            sp_wrote(s, F[3]);
+            sp_wrote(s, F[4]);
+            return dispatch_kernel<OpTwFindJ>(s, (int)Pm[0], Pm[1], flags, [&](auto& P) {
+                for (int k = 0; k < 4; k++) P.qp[k] = sc(s, F[1]);  // velocities are not read by find_J!: any valid plane
+                P.T = sc(s, F[2]);
+                P.L = nullptr;
+                P.J = sc(s, F[3]);
+                P.Kf = sc(s, F[4]);
+                P.cap = s->cap;
+                P.rho0 = Pm[2];
+                P.h = Pm[1];
+            });
+        }
+        case SP_OP_TW_FIND_T: {
+            NEED(4, 3, 9, 9, 1, 1);
+            sp_wrote(s, F[1]);
+            sp_wrote(s, F[2]);
+            UTwFindT::Params P{sc(s, F[0]), sc(s, F[1]), sc(s, F[2]), sc(s, F[3]), s->cap, Pm[0], Pm[1] * Pm[1], Pm[2] * Pm[2]};
+            return launch_unary<UTwFindT>(s, P);
+        }
+        case SP_OP_TW_FIND_F: {
+            NEED(5, 4, 3, 1, 9, 1, 3);
+            NEED_CELLS();
+            sp_wrote(s, F[4]);
+            return dispatch_kernel<OpTwFindF>(s, (int)Pm[0], Pm[1], flags, [&](auto& P) {
+                P.qp[0] = sc(s, F[1]);
+                P.qp[1] = sc(s, F[3]);
+                for (int c = 0; c < 9; c++) P.qp[2 + c] = sc(s, F[2]) + (size_t)c * s->cap;
+                P.f = wv3(s, F[4]);
+                P.rho0 = Pm[2];
+                P.cp2 = Pm[3] * Pm[3];
+                P.h = Pm[1];
+            });
+        }
+        case SP_OP_TW_UPDATE_V: {
+            NEED(4, 1, 3, 3, 3, 1);
+            sp_wrote(s, F[1]);
+            UTwUpdateV::Params P{sc(s, F[0]) + 2 * s->cap, wv3(s, F[1]), rv3(s, F[2]), sc(s, F[3]), Pm[0]};
+            return launch_unary<UTwUpdateV>(s, P);
+        }
     }
     return sp_fail(s, SP_ERR_INVALID, "unknown operator id");
 }

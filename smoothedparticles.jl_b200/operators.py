@@ -283,7 +283,7 @@ def be_update_v(hdt, v="v", f="f", m="m"):
     return Operator(K["SP_OP_BE_UPDATE_V"], (v, f, m), (hdt,), False, "update_v!")
 
 
-# ---- examples/SHTC/twist3d.jl (SHTC solid in 3-D) — ORACLE ONLY so far: the device rejects these ids
+# ---- examples/SHTC/twist3d.jl (SHTC solid in 3-D; full 3x3 T, L, A)
 def tw_find_L(kernel, h, rho0, x="x", v="v", m="m", T="T", L="L"):
     """twist3d.jl:135-141."""
     return Operator(K["SP_OP_TW_FIND_L"], (x, v, m, T, L), (_kid(kernel), h, rho0), True, "find_L! (3-D)")

@@ -190,3 +190,55 @@ def test_shtc_beryllium_operators_and_time_loop():
     assert len(dev) == len(ora) == case.n
     assert_fields_close(dev, ora, ["x", "v", "A"], rtol=1e-8, what="beryllium 100 steps")
     assert abs(configs.beryllium_energy(dev, c) - E0) < 1e-5 * E0
+
+
+def test_shtc_twist3d_time_loop_and_single_calls():
+    # examples/SHTC/twist3d.jl: SHTC solid in 3-D (full 3x3 T, L, A; h = 3 dr -> ~113 neighbours, the lists grow)
+    from smoothedparticles_jl_b200 import operators as ops
+    from parity import RTOL_STEP, assert_fields_close, neighbour_sets_equal
+    case = configs.shtc_twist3d(dr=1 / 8)
+    c = case.consts
+    dev, ora = case.make(ParticleSystem), case.make(OracleSystem)
+    case.prologue(dev)
+    case.prologue(ora)
+    assert neighbour_sets_equal(dev, ora, ordered=True)
+    assert np.max(np.abs(dev.get("J") - 1.0)) < 1e-13 and np.max(np.abs(dev.get("K"))) < 1e-13
+    assert_fields_close(dev, ora, ["T", "P"], rtol=1e-9, what="twist3d prologue", floors={"P": 1.0})
+    # single calls on a moved state
+    for _ in range(5):
+        case.step(dev)
+        case.step(ora)
+    assert_fields_close(dev, ora, ["x", "v", "A", "J"], rtol=1e-10, what="twist3d 5 steps")
+    h, rho0, hdt = c["h"], c["rho0"], 0.5 * c["dt"]
+    for f in ("x", "v", "A"):
+        ora.set(f, dev.get(f))
+    for s in (dev, ora):
+        s.create_cell_list()
+        s.apply(ops.be_reset())
+        s.apply(ops.tw_find_L("wendland3", h, rho0))
+    assert_fields_close(dev, ora, ["T", "L"], rtol=RTOL_STEP, what="find_L! (3-D)")
+    for f in ("T", "L"):
+        ora.set(f, dev.get(f))
+    for s in (dev, ora):
+        s.apply(ops.tw_update_A(hdt))
+    assert_fields_close(dev, ora, ["A", "L"], rtol=1e-11, what="update_A! (3-D)")
+    ora.set("A", dev.get("A"))
+    for s in (dev, ora):
+        s.apply(ops.be_reset())
+        s.apply(ops.tw_find_J("wendland3", h, rho0))
+    assert_fields_close(dev, ora, ["T", "J", "K"], rtol=RTOL_STEP, what="find_J! (3-D)", floors={"K": 1e-3})
+    for f in ("T", "J", "K"):
+        ora.set(f, dev.get(f))
+    for s in (dev, ora):
+        s.apply(ops.tw_find_T(rho0, c["c_0"], c["c_s"]))
+    assert_fields_close(dev, ora, ["T", "P"], rtol=1e-10, what="find_T! (3-D)", floors={"P": 1.0})
+    ora.set("T", dev.get("T"))
+    for s in (dev, ora):
+        s.apply(ops.tw_find_f("wendland3", h, rho0, c["c_p"]))
+        s.apply(ops.tw_update_v(hdt))
+    assert_fields_close(dev, ora, ["f", "v"], rtol=RTOL_STEP, what="find_f!, update_v! (3-D)")
+    for _ in range(40):
+        case.step(dev)
+        case.step(ora)
+    assert len(dev) == len(ora) == case.n
+    assert_fields_close(dev, ora, ["x", "v", "A"], rtol=1e-7, what="twist3d 45 steps")

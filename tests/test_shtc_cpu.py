@@ -248,7 +248,7 @@ def test_beryllium_calibration_and_energy_conservation():
     assert np.max(np.abs(s.get("x") - x0)) > 1e-4          # and the plate does move
 
 
-# ----------------------------------------------------------------------------- SHTC/twist3d.jl (oracle only so far)
+# ----------------------------------------------------------------------------- SHTC/twist3d.jl
 def rDwendland3(h, r):  # kernels.jl:188-195
     x = r / h
     return np.where(x <= 1.0, -66.84507609859604 * (1 - x) ** 3 / h ** 5, 0.0)
