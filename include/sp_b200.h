@@ -253,8 +253,8 @@ enum {
     SP_OP_BE_UPDATE_A = 81,
     /* unary. fields {A, T, L}; params {hdt}   L = L*inv(T);  A = A*(I - hdt*L)*inv(I + hdt*L)   beryllium.jl:148-151 */
     SP_OP_BE_FIND_J = 82,
-    /* binary. fields {x, m, T, J, K}; params {kernel, h, rho0}   T_p += (m_q/rho0*rDw)*outer(x_pq, x_pq);
-       J_p += m_q/rho0*w(h,r);  K_p += m_q/rho0*w_h(h,r)                                         beryllium.jl:153-158 */
+    /* binary, honours self. fields {x, m, T, J, K}; params {kernel, h, rho0}   T_p += (m_q/rho0*rDw)*outer(x_pq, x_pq);
+       J_p += m_q/rho0*w(h,r);  K_p += m_q/rho0*w_h(h,r)        beryllium.jl:153-158; taco.jl:141-146 (find_rho!, self) */
     SP_OP_BE_FIND_T = 83,
     /* unary. fields {A, T, P, J}; params {rho0, c_0, c_s}   G = A'*A;
        P = 0.5*rho0*c_0^2*((1 - 1/J)/J^2 + log(J)/J);  T = P/rho0*I - c_s^2*G*dev(G)*inv(T)       beryllium.jl:160-164 */
@@ -282,8 +282,24 @@ enum {
     SP_OP_TW_FIND_F = 94,
     /* binary. fields {x, m, T, K, f}; params {kernel, h, rho0, c_p}
        f_p += m_p*ker*(T_p*x_pq) + m_p*ker*(T_q*x_pq) - (m_p*kerh*c_p^2*(K_p + K_q))*x_pq          twist3d.jl:163-172 */
-    SP_OP_TW_UPDATE_V = 95
+    SP_OP_TW_UPDATE_V = 95,
     /* unary. fields {x, v, f, m}; params {hdt}   if x[3] > 0: v += hdt*f/m                        twist3d.jl:125-129 */
+
+    /* SHTC fluid between rotating cylinders (Taylor-Couette) — examples/SHTC/taco.jl.  find_L!, update_A!, reset! and
+       find_rho! (with self) are SP_OP_BE_FIND_L / BE_UPDATE_A / BE_RESET / BE_FIND_J with rho0 = 1 (the same arithmetic:
+       m/1.0 is m), relax_A! is SP_OP_SHTC_RELAX_A.  GPU parity check pending (tests/pending_gpu_round2.py). */
+    SP_OP_TA_FIND_T = 100,
+    /* unary. fields {A, T, P, rho}; params {rho0, c_0, c_s}   G = A'*A;  P = c_0^2*(rho - rho0)*rho0/rho;
+       T = -P/rho^2*I + c_s^2*G*dev(G)*subinv(T)                                                  taco.jl:148-152 */
+    SP_OP_TA_FIND_F = 101,
+    /* binary. fields {x, m, T, lambda, f}; params {kernel, h, cpr2}   ker = m_q*rDw, kerh = m_q*rDw_h:
+       f_p += (m_p*ker*(T_p + T_q))*x_pq - (m_p*kerh*cpr2*(lambda_p + lambda_q))*x_pq,  cpr2 = (c_p/rho0)^2   taco.jl:154-162 */
+    SP_OP_TA_UPDATE_V = 102,
+    /* unary. fields {x, v, f, m, type}; params {hdt, R1, R2, omega}   if type == 0: v += hdt*f/m
+       else v = R2/r*(r/R1 - R1/r)/(R2/R1 - R1/R2)*(-omega*x[2], omega*x[1], 0), r = norm(x)       taco.jl:108-114, 39-42 */
+    SP_OP_TA_UPDATE_X = 103
+    /* unary. fields {x, v, x0, type}; params {hdt, cos_wt, sin_wt, outer_type}   if type == 0: x += hdt*v;
+       if type == outer_type: x = (x0[1]*cos_wt - x0[2]*sin_wt, x0[1]*sin_wt + x0[2]*cos_wt, 0)    taco.jl:116-126 */
 };
 
 /* sp_apply flags */

@@ -1104,6 +1104,11 @@ int apply_op(OSys& s, int op, const int32_t* F, int nf, const double* P, int np,
                 p.f[oJ] += q.f[om] / rho0 * w(h, r);
                 p.f[oK] += q.f[om] / rho0 * wendland2h(h, r);
             });
+            if (self)  // taco.jl:252 find_rho!(p, p, 0.0): x_pq = 0 adds nothing to T
+                apply_unary(s, [=](Particle& p) {
+                    p.f[oJ] += p.f[om] / rho0 * w(h, 0.0);
+                    p.f[oK] += p.f[om] / rho0 * wendland2h(h, 0.0);
+                });
             return SP_OK;
         }
         case SP_OP_BE_FIND_T: {  // SHTC/beryllium.jl:160-164
@@ -1255,6 +1260,85 @@ int apply_op(OSys& s, int op, const int32_t* F, int nf, const double* P, int np,
             apply_unary(s, [=](Particle& p) {
                 if (p.f[ox + 2] > 0.0)
                     for (int c = 0; c < 3; c++) p.f[ov + c] += hdt * p.f[of + c] / p.f[om];
+            });
+            return SP_OK;
+        }
+        case SP_OP_TA_FIND_T: {  // SHTC/taco.jl:148-152 (subinv: tools.jl:45-52, zeros outside the in-plane block)
+            if (!need(4, 3)) return SP_ERR_INVALID;
+            const int oA = F[0], oT = F[1], oP = F[2], orho = F[3];
+            const double rho0 = P[0], c_0 = P[1], c_s = P[2];
+            apply_unary(s, [=](Particle& p) {
+                const M3 A = m3_load(p.f + oA);
+                const M3 G = m3_tmul(A, A);
+                const M3 GD = m3_mul(m3_scale(c_s * c_s, G), m3_dev(G));
+                const double rho = p.f[orho];
+                const double Pr = (c_0 * c_0) * (rho - rho0) * rho0 / rho;
+                p.f[oP] = Pr;
+                const M2 si = m2_inv(m2_load(p.f + oT));
+                M3 S;  // (c_s^2*G*dev(G))*subinv(T): the third column of subinv is zero
+                for (int i = 0; i < 3; i++) {
+                    S.a[i] = GD.a[i] * si.a11 + GD.a[i + 3] * si.a21;
+                    S.a[i + 3] = GD.a[i] * si.a12 + GD.a[i + 3] * si.a22;
+                    S.a[i + 6] = 0.0;
+                }
+                const double iso = -Pr / (rho * rho);
+                S.a[0] = iso + S.a[0];
+                S.a[4] = iso + S.a[4];
+                S.a[8] = iso + S.a[8];
+                m3_store(p.f + oT, S);
+            });
+            return SP_OK;
+        }
+        case SP_OP_TA_FIND_F: {  // SHTC/taco.jl:154-162
+            if (!need(5, 3)) return SP_ERR_INVALID;
+            const int om = F[1], oT = F[2], ol = F[3], of = F[4];
+            kfn rDw = pick_rD((int)P[0]);
+            const double h = P[1], cpr2 = P[2];
+            if (!rDw) return SP_ERR_INVALID;
+            apply_binary(s, [=](Particle& p, const Particle& q, const double* xpq, double r) {
+                const double ker = q.f[om] * rDw(h, r);
+                const double kerh = q.f[om] * rDwendland2h(h, r);
+                const double c = p.f[om] * ker;
+                for (int i = 0; i < 3; i++) {
+                    double row = 0.0;
+                    for (int j = 0; j < 3; j++) row += (c * (p.f[oT + i + 3 * j] + q.f[oT + i + 3 * j])) * xpq[j];
+                    p.f[of + i] += row;
+                }
+                const double a = -p.f[om] * kerh * cpr2 * (p.f[ol] + q.f[ol]);
+                for (int i = 0; i < 3; i++) p.f[of + i] += a * xpq[i];
+            });
+            return SP_OK;
+        }
+        case SP_OP_TA_UPDATE_V: {  // SHTC/taco.jl:108-114 with vexact :39-42
+            if (!need(5, 4)) return SP_ERR_INVALID;
+            const int ox = F[0], ov = F[1], of = F[2], om = F[3], ot = F[4];
+            const double hdt = P[0], R1 = P[1], R2 = P[2], omega = P[3];
+            apply_unary(s, [=](Particle& p) {
+                if (p.f[ot] == 0.0) {
+                    for (int c = 0; c < 3; c++) p.f[ov + c] += hdt * p.f[of + c] / p.f[om];
+                } else {
+                    const double r = std::sqrt(dot3(p.f + ox, p.f + ox));
+                    const double sc = R2 / r * (r / R1 - R1 / r) / (R2 / R1 - R1 / R2);
+                    p.f[ov] = sc * (-omega * p.f[ox + 1]);
+                    p.f[ov + 1] = sc * (omega * p.f[ox]);
+                    p.f[ov + 2] = sc * 0.0;
+                }
+            });
+            return SP_OK;
+        }
+        case SP_OP_TA_UPDATE_X: {  // SHTC/taco.jl:116-126
+            if (!need(4, 4)) return SP_ERR_INVALID;
+            const int ox = F[0], ov = F[1], ox0 = F[2], ot = F[3];
+            const double hdt = P[0], cw = P[1], sw = P[2], outer = P[3];
+            apply_unary(s, [=](Particle& p) {
+                if (p.f[ot] == 0.0) {
+                    for (int c = 0; c < 3; c++) p.f[ox + c] += hdt * p.f[ov + c];
+                } else if (p.f[ot] == outer) {
+                    const double a = p.f[ox0], b = p.f[ox0 + 1];
+                    p.f[ox] = a * cw - b * sw;
+                    p.f[ox + 1] = a * sw + b * cw;
+                    p.f[ox + 2] = 0.0;
+                }
             });
             return SP_OK;
         }

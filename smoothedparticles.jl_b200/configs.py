@@ -19,6 +19,7 @@ order as the script.  A Case is backend-agnostic: ``case.make(ParticleSystem)`` 
   shtc_ldc               examples/SHTC/ldc.jl                lid-driven cavity with the SHTC model (3x3 distortion field)
   shtc_beryllium         examples/SHTC/beryllium.jl          vibrating beryllium plate, SHTC solid (2-D)
   shtc_twist3d           examples/SHTC/twist3d.jl            twisting rubber column, SHTC solid (3-D)
+  shtc_taco              examples/SHTC/taco.jl               Taylor-Couette flow, SHTC fluid on a Vogel spiral
   lattice_box            synthetic S1 block of SURVEY §8(d)  jittered cubic lattice, all fluid
 """
 from __future__ import annotations
@@ -828,6 +829,88 @@ def shtc_twist3d(dr: float = None) -> Case:
 
     return Case("shtc_twist3d", fields, domain, h, init, step, prologue,
                 consts=dict(dr=dr, h=h, m0=m0, dt=dt, rho0=rho0, c_0=c_0, c_s=c_s, c_p=c_p, H=H, W=W, omega=omega), dim=3)
+
+
+# --------------------------------------------------------------------------- SHTC/taco.jl
+def shtc_taco(dr: float = None) -> Case:
+    """examples/SHTC/taco.jl:11-37 (constants), :80-103 (make_geometry with the C_rho/C_lambda calibration),
+    :242-255 (loop): Taylor-Couette flow between a resting inner and a rotating outer cylinder, SHTC fluid on a Vogel
+    spiral.  The step index k (t = k*dt, :228) is kept on the system object as ``step_index``."""
+    R1, R2, omega, Re = 1.0, 2.0, 1.0, 20.0
+    c_s, c_0, rho0 = 30.0, 15.0, 1.0
+    tau = 6 * omega * R2 * (R2 - R1) / (Re * c_s ** 2)
+    if dr is None:
+        dr = (R2 - R1) / 20
+    h = 3.0 * dr
+    wwall = 1.5 * h
+    c_p = 0.01 * c_0
+    c = math.sqrt(c_0 ** 2 + 4 / 3 * c_s ** 2)
+    m0 = rho0 * dr * dr
+    dt = 0.05 * dr / c
+    FLUID, INNER, OUTER = 0.0, 1.0, 2.0
+    grid = geo.VogelGrid(dr)
+    fluid = geo.Circle(0.0, 0.0, R2) - geo.Circle(0.0, 0.0, R1)
+    walls = geo.BoundaryLayer(fluid, grid, wwall)
+    mid = 0.5 * (R1 + R2)
+    inner = geo.Specification(walls, lambda X: np.sqrt(X[:, 0] * X[:, 0] + X[:, 1] * X[:, 1] + X[:, 2] * X[:, 2]) < mid)
+    outer = geo.Specification(walls, lambda X: np.sqrt(X[:, 0] * X[:, 0] + X[:, 1] * X[:, 1] + X[:, 2] * X[:, 2]) > mid)
+    domain = geo.BoundaryLayer(fluid, grid, 10 * wwall).boundarybox()
+    xf, xi, xo = geo.covering(grid, fluid), geo.covering(grid, inner), geo.covering(grid, outer)
+    x = np.concatenate([xf, xi, xo])
+    n = len(x)
+    typ = np.concatenate([np.full(len(xf), FLUID), np.full(len(xi), INNER), np.full(len(xo), OUTER)])
+    fields = {"m": 1, "x0": 3, "v": 3, "P": 1, "f": 3, "A": 9, "T": 9, "L": 9, "rho": 1, "lambda": 1, "C_rho": 1,
+              "C_lambda": 1, "type": 1}
+    init = {"x": x, "x0": x.copy(), "m": np.full(n, m0), "A": np.tile(np.eye(3).ravel(), (n, 1)), "type": typ}
+    o_L = ops.be_find_L("wendland2", h, 1.0)                       # find_L! :128-134 (ker = q.m*rDw)
+    o_A = ops.be_update_A(0.5 * dt)                                # update_A! :136-139
+    o_relax = ops.shtc_relax_A(dt, tau)                            # relax_A! :180-194
+    o_rho = ops.be_find_J("wendland2", h, 1.0, J="rho", Kf="lambda")   # find_rho! :141-146, self = true
+    o_T = ops.ta_find_T(rho0, c_0, c_s)
+    o_f = ops.ta_find_f("wendland2", h, c_p, rho0)
+    o_reset = ops.be_reset(J="rho", Kf="lambda", J0="C_rho", K0="C_lambda")   # reset! :164-170
+    o_v = ops.ta_update_v(0.5 * dt, R1, R2, omega)
+
+    def prologue(sys):  # :90-102
+        sys.create_cell_list()
+        sys.apply(o_rho, self_=True)
+        sys.set("C_rho", rho0 - sys.get("rho"))
+        sys.set("C_lambda", -sys.get("lambda"))
+        sys.apply(o_reset)
+        sys.apply(o_rho, self_=True)
+        sys.apply(o_T)
+        sys.apply(o_f)
+
+    def step(sys):  # :227-228, :242-255
+        k = getattr(sys, "step_index", 0)
+        sys.step_index = k + 1
+        t = k * dt
+        sys.apply(o_v)
+        sys.apply(ops.ta_update_x(0.5 * dt, omega, t + 0.5 * dt, OUTER))
+        sys.create_cell_list()
+        sys.apply(o_reset)
+        sys.apply(o_L)
+        sys.apply(o_A)
+        sys.apply(o_relax)
+        sys.apply(ops.ta_update_x(0.5 * dt, omega, t + dt, OUTER))
+        sys.create_cell_list()
+        sys.apply(o_reset)
+        sys.apply(o_rho, self_=True)
+        sys.apply(o_T)
+        sys.apply(o_f)
+        sys.apply(o_v)
+
+    return Case("shtc_taco", fields, domain, h, init, step, prologue,
+                consts=dict(dr=dr, h=h, m0=m0, dt=dt, rho0=rho0, c_0=c_0, c_s=c_s, c_p=c_p, tau=tau, R1=R1, R2=R2,
+                            omega=omega, OUTER=OUTER), dim=2)
+
+
+def taco_exact_velocity(x, consts):
+    """vexact, taco.jl:39-42: the steady Couette profile."""
+    R1, R2, omega = consts["R1"], consts["R2"], consts["omega"]
+    r = np.sqrt(np.sum(x * x, axis=1))
+    sc = R2 / r * (r / R1 - R1 / r) / (R2 / R1 - R1 / R2)
+    return np.column_stack([sc * (-omega * x[:, 1]), sc * (omega * x[:, 0]), np.zeros(len(x))])
 
 
 # --------------------------------------------------------------------------- collapse_dry_implicit.jl

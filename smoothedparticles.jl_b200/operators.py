@@ -314,6 +314,30 @@ def tw_update_v(hdt, x="x", v="v", f="f", m="m"):
     return Operator(K["SP_OP_TW_UPDATE_V"], (x, v, f, m), (hdt,), False, "update_v! (3-D)")
 
 
+# ---- examples/SHTC/taco.jl (Taylor-Couette flow, SHTC fluid); find_L!/update_A!/reset!/find_rho! are the be_* operators
+# with rho0 = 1, relax_A! is shtc_relax_A
+def ta_find_T(rho0, c_0, c_s, A="A", T="T", P="P", rho="rho"):
+    """taco.jl:148-152."""
+    return Operator(K["SP_OP_TA_FIND_T"], (A, T, P, rho), (rho0, c_0, c_s), False, "find_T! (taco)")
+
+
+def ta_find_f(kernel, h, c_p, rho0, x="x", m="m", T="T", lam="lambda", f="f"):
+    """taco.jl:154-162."""
+    return Operator(K["SP_OP_TA_FIND_F"], (x, m, T, lam, f), (_kid(kernel), h, (c_p / rho0) ** 2), True, "find_f! (taco)")
+
+
+def ta_update_v(hdt, R1, R2, omega, x="x", v="v", f="f", m="m", type="type"):
+    """taco.jl:108-114: the fluid is kicked, wall particles carry the exact Couette velocity (vexact :39-42)."""
+    return Operator(K["SP_OP_TA_UPDATE_V"], (x, v, f, m, type), (hdt, R1, R2, omega), False, "update_v! (taco)")
+
+
+def ta_update_x(hdt, omega, t, outer_type, x="x", v="v", x0="x0", type="type"):
+    """taco.jl:116-126 at time t: the fluid drifts, the outer cylinder is rotated rigidly from its initial position."""
+    import math
+    return Operator(K["SP_OP_TA_UPDATE_X"], (x, v, x0, type), (hdt, math.cos(omega * t), math.sin(omega * t), outer_type),
+                    False, "update_x! (taco)")
+
+
 # ---- examples/static_container.jl
 def sc_balance_of_mass(kernel, m, h, dt, x="x", v="v", rho="rho"):
     """static_container.jl:102-104: the density is integrated inside the pair loop."""

@@ -352,3 +352,96 @@ def test_twist3d_time_loop_on_the_oracle():
     assert np.all(turn < 0.0) and np.mean(turn) < -0.05                # the top spins clockwise (init_velocity :36-38)
     dets = np.linalg.det(A)
     assert 0.9 < dets.min() and dets.max() < 1.1                       # nearly incompressible rubber (nu = 0.495)
+
+
+# ----------------------------------------------------------------------------- SHTC/taco.jl
+def test_taco_operators_against_numpy():
+    case = configs.shtc_taco()
+    c = case.consts
+    rng = np.random.default_rng(21)
+    keep = np.flatnonzero((case.init["x"][:, 0] > 0.6) & (np.abs(case.init["x"][:, 1]) < 0.35))   # a sector with both walls
+    n = len(keep)
+    x = case.init["x"][keep] + rng.uniform(-0.05, 0.05, (n, 3)) * c["dr"] * np.array([1, 1, 0])
+    typ = case.init["type"][keep]
+    assert set(np.unique(typ)) == {0.0, 1.0, 2.0}
+    m = c["m0"] * rng.uniform(0.9, 1.1, n)
+    A = np.tile(np.eye(3), (n, 1, 1))
+    A[:, :2, :2] += rng.uniform(-0.03, 0.03, (n, 2, 2))
+    A[:, 2, 2] += rng.uniform(-0.01, 0.01, n)
+    s = OracleSystem(case.fields, case.domain, case.h)
+    s.add_particles(x=x, x0=case.init["x"][keep], v=rng.uniform(-1, 1, (n, 3)) * np.array([1, 1, 0]), m=m, type=typ,
+                    A=A.transpose(0, 2, 1).reshape(n, 9), C_rho=rng.uniform(-0.02, 0.02, n), C_lambda=rng.uniform(-0.5, 0.5, n))
+    s.create_cell_list()
+    assert len(s) == n
+    h = c["h"]
+    d = x[:, None, :] - x[None, :, :]
+    r = np.sqrt(np.sum(d * d, axis=2))
+    nb = (r <= h) & ~np.eye(n, dtype=bool)
+    d2 = d[:, :, :2]
+    # reset! + find_rho! with self = true  (taco.jl:164-170, 141-146, 252)
+    s.apply(ops.be_reset(J="rho", Kf="lambda", J0="C_rho", K0="C_lambda"))
+    s.apply(ops.be_find_J("wendland2", h, 1.0, J="rho", Kf="lambda"), self_=True)
+    mq = np.where(nb, m[None, :], 0.0)
+    rho = s.get("C_rho") + np.sum(mq * wendland2(h, r), axis=1) + m * float(wendland2(h, 0.0))
+    lam = s.get("C_lambda") + np.sum(mq * wendland2h(h, r), axis=1) + m * float(wendland2h(h, 0.0))
+    T0 = np.einsum("pq,pqi,pqj->pij", mq * rDwendland2(h, r), d2, d2)
+    np.testing.assert_allclose(s.get("rho"), rho, rtol=1e-13)
+    np.testing.assert_allclose(s.get("lambda"), lam, rtol=1e-11, atol=1e-13)
+    assert np.max(np.abs(mat(s.get("T"))[:, :2, :2] - T0)) <= 1e-12 * np.max(np.abs(T0))
+    # find_T!  :148-152
+    s.apply(ops.ta_find_T(c["rho0"], c["c_0"], c["c_s"]))
+    G = A.transpose(0, 2, 1) @ A
+    P = c["c_0"] ** 2 * (rho - c["rho0"]) * c["rho0"] / rho
+    si = np.zeros((n, 3, 3))
+    si[:, :2, :2] = np.linalg.inv(T0)                                # subinv, tools.jl:45-52
+    T = (-P / rho ** 2)[:, None, None] * np.eye(3) + c["c_s"] ** 2 * G @ dev(G) @ si
+    np.testing.assert_allclose(s.get("P"), P, rtol=1e-10, atol=1e-12)
+    assert np.max(np.abs(mat(s.get("T")) - T)) <= 1e-9 * np.max(np.abs(T))
+    # find_f!  :154-162
+    s.apply(ops.ta_find_f("wendland2", h, c["c_p"], c["rho0"]))
+    Tg, lg = mat(s.get("T")), s.get("lambda")
+    ker = mq * rDwendland2(h, r)
+    kerh = mq * rDwendland2h(h, r)
+    f = ((m[:, None] * ker)[:, :, None] * np.einsum("pqij,pqj->pqi", Tg[:, None] + Tg[None, :], d)
+         - (m[:, None] * kerh * (c["c_p"] / c["rho0"]) ** 2 * (lg[:, None] + lg[None, :]))[:, :, None] * d)
+    want = np.sum(f, axis=1)
+    assert np.max(np.abs(s.get("f") - want)) <= 1e-10 * np.max(np.abs(want))
+    # update_v!  :108-114 and update_x!  :116-126
+    v0, fg, x1 = s.get("v"), s.get("f"), s.get("x")
+    hdt = 0.5 * c["dt"]
+    s.apply(ops.ta_update_v(hdt, c["R1"], c["R2"], c["omega"]))
+    want_v = np.where((typ == 0.0)[:, None], v0 + hdt * fg / m[:, None], configs.taco_exact_velocity(x1, c))
+    np.testing.assert_allclose(s.get("v"), want_v, rtol=1e-15, atol=1e-18)
+    t = 0.37
+    s.apply(ops.ta_update_x(hdt, c["omega"], t, c["OUTER"]))
+    X0 = s.get("x0")
+    cw, sw = np.cos(c["omega"] * t), np.sin(c["omega"] * t)
+    rot = np.column_stack([X0[:, 0] * cw - X0[:, 1] * sw, X0[:, 0] * sw + X0[:, 1] * cw, np.zeros(n)])
+    want_x = np.where((typ == 0.0)[:, None], x1 + hdt * s.get("v"), np.where((typ == 2.0)[:, None], rot, x1))
+    np.testing.assert_allclose(s.get("x"), want_x, rtol=1e-15, atol=1e-18)
+
+
+def test_taco_calibration_and_spin_up():
+    case = configs.shtc_taco()
+    c = case.consts
+    s = case.make(OracleSystem)
+    case.prologue(s)
+    # C_rho / C_lambda (:94-97) make the initial state uniform: rho = rho0, lambda = 0, no force
+    assert np.max(np.abs(s.get("rho") - c["rho0"])) < 1e-14 and np.max(np.abs(s.get("lambda"))) < 1e-13
+    assert np.max(np.abs(s.get("f"))) < 1e-12
+    for _ in range(200):
+        case.step(s)
+    assert len(s) == case.n
+    x, v, typ = s.get("x"), s.get("v"), s.get("type")
+    r = np.hypot(x[:, 0], x[:, 1])
+    outer = typ == c["OUTER"]
+    # the outer cylinder turns rigidly: radius kept, angle advanced by omega*t
+    r0 = np.hypot(case.init["x"][outer, 0], case.init["x"][outer, 1])
+    assert np.max(np.abs(r[outer] - r0)) < 1e-12
+    assert np.allclose(v[~(typ == 0.0)], configs.taco_exact_velocity(x, c)[~(typ == 0.0)], rtol=1e-12, atol=1e-14)
+    # and drags the fluid next to it along (anticlockwise), while the fluid at the resting inner cylinder stays slow
+    vphi = (-x[:, 1] * v[:, 0] + x[:, 0] * v[:, 1]) / r
+    near_outer = (typ == 0.0) & (r > 1.93)
+    near_inner = (typ == 0.0) & (r < 1.1)
+    assert np.mean(vphi[near_outer]) > 0.05 and np.mean(vphi[near_outer]) > 3 * abs(np.mean(vphi[near_inner]))
+    assert np.all(np.isfinite(s.get("A")))
