@@ -208,6 +208,14 @@ tw_find_J(kernel, h, rho0; x = :x, m = :m, T = :T, J = :J, K = :K) = Operator(92
 tw_find_T(rho0, c_0, c_s; A = :A, T = :T, P = :P, J = :J) = Operator(93, [A, T, P, J], [rho0, c_0, c_s])
 tw_find_f(kernel, h, rho0, c_p; x = :x, m = :m, T = :T, K = :K, f = :f) = Operator(94, [x, m, T, K, f], [KERNELS[kernel], h, rho0, c_p])
 tw_update_v(hdt; x = :x, v = :v, f = :f, m = :m) = Operator(95, [x, v, f, m], [hdt])
+# examples/SHTC/taco.jl:108-162: find_L!, update_A!, reset!, find_rho! (apply! with self = true) are be_find_L / be_update_A /
+# be_reset / be_find_J with rho0 = 1.0 and the taco field names; relax_A! is shtc_relax_A (GPU parity check pending)
+ta_find_T(rho0, c_0, c_s; A = :A, T = :T, P = :P, rho = :rho) = Operator(100, [A, T, P, rho], [rho0, c_0, c_s])
+ta_find_f(kernel, h, c_p, rho0; x = :x, m = :m, T = :T, lambda = :lambda, f = :f) =
+    Operator(101, [x, m, T, lambda, f], [KERNELS[kernel], h, (c_p / rho0)^2])
+ta_update_v(hdt, R1, R2, omega; x = :x, v = :v, f = :f, m = :m, type = :type) = Operator(102, [x, v, f, m, type], [hdt, R1, R2, omega])
+ta_update_x(hdt, omega, t, outer_type; x = :x, v = :v, x0 = :x0, type = :type) =
+    Operator(103, [x, v, x0, type], [hdt, cos(omega * t), sin(omega * t), outer_type])
 end # module Operators
 
 # add_new_particles!, examples/cylinder.jl:145-156: particles of `from_type` with x[1] >= x1_min become `to_type`, a new

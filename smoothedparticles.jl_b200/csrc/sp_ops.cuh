@@ -948,7 +948,7 @@ struct OpBeFindLJBase {
         SpKC kc;
     };
     struct PS {
-        double vx, vy;
+        double vx, vy, m;
     };
     struct Acc {
         double t11, t21, t12, t22, a, b, c, d;  // WITH_L: L11 L21 L12 L22; else: J, K, -, -
@@ -957,6 +957,7 @@ struct OpBeFindLJBase {
     __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
         const SpM2 T = sp_m2_load(P.T, P.cap, i);
         a.t11 = T.a11; a.t21 = T.a21; a.t12 = T.a12; a.t22 = T.a22;
+        p.m = P.qp[0][i];
         if (WITH_L) {
             p.vx = P.qp[1][i]; p.vy = P.qp[2][i];
             const SpM2 L = sp_m2_load(P.L, P.cap, i);
@@ -980,7 +981,14 @@ struct OpBeFindLJBase {
             a.b += mr * sp_wendland2h(P.h, r);
         }
     }
-    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    // find_rho!(p, p, 0.0) of taco.jl:252 (self = true): x_pq = 0 adds nothing to T
+    __device__ static __forceinline__ void self(const Params& P, const PS& p, Acc& a) {
+        if (!WITH_L) {
+            const double mr = p.m / P.rho0;
+            a.a += mr * K::w(P.kc, 0.0);
+            a.b += mr * sp_wendland2h(P.h, 0.0);
+        }
+    }
     __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) {
         sp_m2_store(P.T, P.cap, i, SpM2{a.t11, a.t21, a.t12, a.t22});
         if (WITH_L) {
@@ -1174,6 +1182,53 @@ struct OpTwFindF {
         a.y += c * (q(3) * dx + q(6) * dy + q(9) * dz);
         a.z += c * (q(4) * dx + q(7) * dy + q(10) * dz);
         const double g = -p.m * kerh * P.cp2 * (p.Kf + q(1));
+        a.x += g * dx; a.y += g * dy; a.z += g * dz;
+    }
+    __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
+    __device__ static __forceinline__ void store(const Params& P, int i, const PS&, const Acc& a) {
+        P.f.x[i] = a.x; P.f.y[i] = a.y; P.f.z[i] = a.z;
+    }
+};
+
+// ---------------------------------------------------------------- examples/SHTC/taco.jl
+// find_f!  :154-162
+template <class K>
+struct OpTaFindF {
+    static constexpr bool LISTS_ONLY = true;
+    static constexpr int NQ = 11;  // m, lambda, T (9 planes)
+    struct Params {
+        const double* qp[NQ];
+        WV3 f;
+        double cpr2, h;
+        SpKC kc;
+    };
+    struct PS {
+        double m, lam;
+        double T[9];
+    };
+    struct Acc {
+        double x, y, z;
+    };
+    __device__ static __forceinline__ bool active(const Params&, int) { return true; }
+    __device__ static __forceinline__ void load(const Params& P, int i, double, double, double, PS& p, Acc& a) {
+        p.m = P.qp[0][i]; p.lam = P.qp[1][i];
+#pragma unroll
+        for (int c = 0; c < 9; c++) p.T[c] = P.qp[2 + c][i];
+        a.x = P.f.x[i]; a.y = P.f.y[i]; a.z = P.f.z[i];
+    }
+    template <class Q>
+    __device__ static __forceinline__ void pair(const Params& P, const PS& p, const Q& q, double dx, double dy,
+                                                double dz, double r, Acc& a) {
+        const double mq = q(0);
+        const double ker = mq * K::rD(P.kc, r), kerh = mq * sp_rDwendland2h(P.h, r);
+        const double c = p.m * ker;
+        double S[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) S[k] = c * (p.T[k] + q(2 + k));
+        a.x += S[0] * dx + S[3] * dy + S[6] * dz;
+        a.y += S[1] * dx + S[4] * dy + S[7] * dz;
+        a.z += S[2] * dx + S[5] * dy + S[8] * dz;
+        const double g = -p.m * kerh * P.cpr2 * (p.lam + q(1));
         a.x += g * dx; a.y += g * dy; a.z += g * dz;
     }
     __device__ static __forceinline__ void self(const Params&, const PS&, Acc&) {}
@@ -1902,6 +1957,76 @@ struct UTwUpdateV {
         if (P.z[i] > 0.0) {
             const double m = P.m[i];
             P.v.x[i] += P.hdt * P.f.x[i] / m; P.v.y[i] += P.hdt * P.f.y[i] / m; P.v.z[i] += P.hdt * P.f.z[i] / m;
+        }
+    }
+};
+// find_T!  SHTC/taco.jl:148-152 (subinv: zeros outside the in-plane block)
+struct UTaFindT {
+    struct Params {
+        const double* A;
+        double *T, *P;
+        const double* rho;
+        long long cap;
+        double rho0, c02, cs2;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        const SpM3 A = sp_m3_load(P.A, P.cap, i);
+        const SpM3 G = sp_m3_tmul(A, A);
+        const SpM3 GD = sp_m3_mul(sp_m3_scale(P.cs2, G), sp_m3_dev(G));
+        const double rho = P.rho[i];
+        const double Pr = P.c02 * (rho - P.rho0) * P.rho0 / rho;
+        P.P[i] = Pr;
+        const SpM2 si = sp_m2_inv(sp_m2_load(P.T, P.cap, i));
+        const double iso = -Pr / (rho * rho);
+        SpM3 S;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            S.a[r] = GD.a[r] * si.a11 + GD.a[r + 3] * si.a21;
+            S.a[r + 3] = GD.a[r] * si.a12 + GD.a[r + 3] * si.a22;
+            S.a[r + 6] = 0.0;
+        }
+        S.a[0] += iso; S.a[4] += iso; S.a[8] += iso;
+        sp_m3_store(P.T, P.cap, i, S);
+    }
+};
+// update_v!  SHTC/taco.jl:108-114 with vexact :39-42
+struct UTaUpdateV {
+    struct Params {
+        RV3 x;
+        WV3 v;
+        RV3 f;
+        const double *m, *type;
+        double hdt, R1, R2, omega;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        if (P.type[i] == 0.0) {
+            const double m = P.m[i];
+            P.v.x[i] += P.hdt * P.f.x[i] / m; P.v.y[i] += P.hdt * P.f.y[i] / m; P.v.z[i] += P.hdt * P.f.z[i] / m;
+        } else {
+            const double x = P.x.x[i], y = P.x.y[i], z = P.x.z[i];
+            const double r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
+            const double sc = P.R2 / r * (r / P.R1 - P.R1 / r) / (P.R2 / P.R1 - P.R1 / P.R2);
+            P.v.x[i] = sc * (-P.omega * y); P.v.y[i] = sc * (P.omega * x); P.v.z[i] = sc * 0.0;
+        }
+    }
+};
+// update_x!  SHTC/taco.jl:116-126
+struct UTaUpdateX {
+    struct Params {
+        WV3 x;
+        RV3 v, x0;
+        const double* type;
+        double hdt, cw, sw, outer;
+    };
+    __device__ static __forceinline__ void apply(const Params& P, int i) {
+        const double t = P.type[i];
+        if (t == 0.0) {
+            P.x.x[i] += P.hdt * P.v.x[i]; P.x.y[i] += P.hdt * P.v.y[i]; P.x.z[i] += P.hdt * P.v.z[i];
+        } else if (t == P.outer) {
+            const double a = P.x0.x[i], b = P.x0.y[i];
+            P.x.x[i] = __dsub_rn(__dmul_rn(a, P.cw), __dmul_rn(b, P.sw));
+            P.x.y[i] = __dadd_rn(__dmul_rn(a, P.sw), __dmul_rn(b, P.cw));
+            P.x.z[i] = 0.0;
         }
     }
 };

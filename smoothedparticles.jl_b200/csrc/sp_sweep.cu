@@ -2127,6 +2127,38 @@ int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const 
             UTwUpdateV::Params P{sc(s, F[0]) + 2 * s->cap, wv3(s, F[1]), rv3(s, F[2]), sc(s, F[3]), Pm[0]};
             return launch_unary<UTwUpdateV>(s, P);
         }
+        case SP_OP_TA_FIND_T: {
+            NEED(4, 3, 9, 9, 1, 1);
+            sp_wrote(s, F[1]);
+            sp_wrote(s, F[2]);
+            UTaFindT::Params P{sc(s, F[0]), sc(s, F[1]), sc(s, F[2]), sc(s, F[3]), s->cap, Pm[0], Pm[1] * Pm[1], Pm[2] * Pm[2]};
+            return launch_unary<UTaFindT>(s, P);
+        }
+        case SP_OP_TA_FIND_F: {
+            NEED(5, 3, 3, 1, 9, 1, 3);
+            NEED_CELLS();
+            sp_wrote(s, F[4]);
+            return dispatch_kernel<OpTaFindF>(s, (int)Pm[0], Pm[1], flags, [&](auto& P) {
+                P.qp[0] = sc(s, F[1]);
+                P.qp[1] = sc(s, F[3]);
+                for (int c = 0; c < 9; c++) P.qp[2 + c] = sc(s, F[2]) + (size_t)c * s->cap;
+                P.f = wv3(s, F[4]);
+                P.cpr2 = Pm[2];
+                P.h = Pm[1];
+            });
+        }
+        case SP_OP_TA_UPDATE_V: {
+            NEED(5, 4, 3, 3, 3, 1, 1);
+            sp_wrote(s, F[1]);
+            UTaUpdateV::Params P{rv3(s, F[0]), wv3(s, F[1]), rv3(s, F[2]), sc(s, F[3]), sc(s, F[4]), Pm[0], Pm[1], Pm[2], Pm[3]};
+            return launch_unary<UTaUpdateV>(s, P);
+        }
+        case SP_OP_TA_UPDATE_X: {
+            NEED(4, 4, 3, 3, 3, 1);
+            sp_wrote(s, F[0]);
+            UTaUpdateX::Params P{wv3(s, F[0]), rv3(s, F[1]), rv3(s, F[2]), sc(s, F[3]), Pm[0], Pm[1], Pm[2], Pm[3]};
+            return launch_unary<UTaUpdateX>(s, P);
+        }
     }
     return sp_fail(s, SP_ERR_INVALID, "unknown operator id");
 }

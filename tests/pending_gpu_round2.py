@@ -242,3 +242,25 @@ def test_shtc_twist3d_time_loop_and_single_calls():
         case.step(ora)
     assert len(dev) == len(ora) == case.n
     assert_fields_close(dev, ora, ["x", "v", "A"], rtol=1e-7, what="twist3d 45 steps")
+
+
+def test_shtc_taco_time_loop():
+    # examples/SHTC/taco.jl: Taylor-Couette flow on a Vogel spiral; find_rho! with self = true, rotating outer wall
+    from parity import assert_fields_close, neighbour_sets_equal
+    case = configs.shtc_taco()
+    c = case.consts
+    dev, ora = case.make(ParticleSystem), case.make(OracleSystem)
+    case.prologue(dev)
+    case.prologue(ora)
+    assert neighbour_sets_equal(dev, ora, ordered=True)
+    assert np.max(np.abs(dev.get("rho") - c["rho0"])) < 1e-13 and np.max(np.abs(dev.get("lambda"))) < 1e-12
+    assert_fields_close(dev, ora, ["C_rho", "C_lambda"], rtol=1e-12, what="taco calibration")
+    for k in range(60):
+        case.step(dev)
+        case.step(ora)
+        if k == 0:
+            assert_fields_close(dev, ora, ["x", "v", "A", "T", "L", "rho", "lambda", "P", "f"], rtol=1e-9, what="taco step 1",
+                                floors={"f": 1e-6, "P": 1e-6, "L": 1e-3, "lambda": 1e-6})
+    assert len(dev) == len(ora) == case.n
+    assert np.array_equal(dev.get("x")[dev.get("type") == c["OUTER"]], ora.get("x")[ora.get("type") == c["OUTER"]])
+    assert_fields_close(dev, ora, ["x", "v", "A", "rho"], rtol=1e-8, what="taco 60 steps")
