@@ -163,14 +163,14 @@ def build(ops):
 class HostFields:
     """Component-major planes of every field of an OracleSystem snapshot (what the device holds, stride n)."""
 
-    def __init__(self, ora, ops):
+    def __init__(self, ora, ops, need_lists=True):
         self.lib = build(ops)
         self.n = len(ora)
         self.planes = {}
         for name, nc in ora.fields.items():
             a = ora.get(name).reshape(self.n, nc if nc > 1 else 1)
             self.planes[name] = np.ascontiguousarray(a.T, dtype=np.float64)   # (ncomp, n)
-        off, ids = ora.neighbour_lists()
+        off, ids = ora.neighbour_lists() if need_lists else (np.zeros(self.n + 1), np.zeros(1))
         self.off = np.ascontiguousarray(off, dtype=np.int64)
         self.ids = np.ascontiguousarray(ids if len(ids) else np.zeros(1), dtype=np.int64)
 
@@ -186,3 +186,40 @@ class HostFields:
     def get(self, name):
         a = self.planes[name].T
         return a[:, 0].copy() if a.shape[1] == 1 else a.copy()
+
+
+def transliterable_ops():
+    """Operator names whose dispatch case is a plain binding (no scratch fields, caches or host-side branches)."""
+    import smoothedparticles_jl_b200 as sp
+    good = []
+    for name in sorted(k for k in sp.K if k.startswith("SP_OP_")):
+        try:
+            _cases([name])
+            good.append(name)
+        except AssertionError:
+            pass
+    return good
+
+
+def host_backed_system():
+    """An OracleSystem whose apply() runs the DEVICE operator body (on the host) for every operator that
+    transliterates, and the oracle's own restatement for the few that do not (scratch-field / cache logic in their
+    dispatch case); everything else — storage, cell list, neighbour lists, reductions, CG — is the oracle's."""
+    import smoothedparticles_jl_b200 as sp
+    from oracle.oracle import OracleSystem
+    names = transliterable_ops()
+    ids = {sp.K[n] for n in names}
+
+    class HostBackedSystem(OracleSystem):
+        host_applied = 0
+
+        def apply(self, op, self_=False, strict_order=False):
+            if op.op not in ids or len(self) == 0:
+                return super().apply(op, self_=self_, strict_order=strict_order)
+            host = HostFields(self, names, need_lists=op.binary)
+            host.apply(op, self_=self_)
+            for f in dict.fromkeys(op.fields):
+                self.set(f, host.get(f))
+            type(self).host_applied += 1
+
+    return HostBackedSystem

@@ -124,3 +124,45 @@ def test_harness_reproduces_an_operator_that_ran_on_the_gpu():
         for name in ora.fields:
             a, b = host.get(name), ora.get(name)
             assert np.max(np.abs(a - b)) <= 1e-11 * max(np.max(np.abs(b)), 1e-300), (op.name, name)
+
+
+def _cylinder_case():
+    from test_cylinder_cpu import cylinder_init
+    return configs.cylinder(cylinder_init())
+
+
+@pytest.mark.parametrize("maker,kw,nsteps", [
+    (configs.collapse_dry, {}, 3), (configs.cavity_flow, {}, 3), (configs.collapse_dry_implicit, {"dr": 2.0e-2}, 2),
+    (configs.collision_2d, {}, 5), (configs.static_container, {}, 3), (configs.drop, {"dr": 1.2e-4}, 2),
+    (configs.collapse_symplectic, {"dr": 4.0e-2}, 4), (configs.kepler_vortex, {"N_rings": 6}, 4), (_cylinder_case, {}, 3),
+    (configs.rod, {}, 4), (configs.shtc_ldc, {}, 3), (configs.shtc_beryllium, {}, 3), (configs.shtc_twist3d, {"dr": 1 / 6}, 2),
+    (configs.shtc_taco, {}, 3), (configs.collapse3d, {"dr": 1.0e-2}, 2)])
+def test_every_config_with_the_device_bodies_on_the_host(maker, kw, nsteps):
+    # every time loop of configs.py, once on the oracle and once on a system whose apply() executes the device operator
+    # bodies (59 of the 66 operators transliterate; the rest fall through to the oracle): a CPU-side guard over the
+    # operator bodies and their bindings that needs no GPU
+    from host_ops import host_backed_system
+    Host = host_backed_system()
+    case = maker(**kw)
+    a, b = case.make(Host), case.make(OracleSystem)
+    before = Host.host_applied
+    case.prologue(a)
+    case.prologue(b)
+    for _ in range(nsteps):
+        case.step(a)
+        case.step(b)
+    assert Host.host_applied > before, "no operator of this config ran through the device body"
+    assert len(a) == len(b)
+    for name in a.fields:
+        u, v = a.get(name), b.get(name)
+        assert np.all(np.isfinite(u) == np.isfinite(v)), (case.name, name)
+        fin = np.isfinite(v)
+        scale = float(np.max(np.abs(v[fin]))) if fin.any() else 0.0
+        err = float(np.max(np.abs(u[fin] - v[fin]))) if fin.any() else 0.0
+        # shtc_ldc: lattice particles sit exactly on the cell face x = 0; a 1e-18 difference in v decides which cell they
+        # fall into after the first move, that changes the visiting order, and convect_A! is order-dependent (3e-9 per
+        # step at the lid corner) — a property of the script, seen between any two implementations
+        rtol = 1e-6 if case.name == "shtc_ldc" else 1e-9
+        # P = c^2*(rho - rho0) of an undisturbed state is c^2 (1e5-1e6) times the rounding noise of the density sums
+        atol = 1e-6 if name == "P" else 1e-10
+        assert err <= rtol * scale + atol, (case.name, name, err, scale)
