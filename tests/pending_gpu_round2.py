@@ -3,7 +3,10 @@ match test_*.py) so that nothing unvalidated can turn the parity gate red.  Run 
 
     python -m pytest tests/pending_gpu_round2.py -q -p no:cacheprovider
 
-and move each test that passes into its test_*_gpu.py home (DESIGN.md §8 lists what is pending)."""
+and move each test that passes into its test_*_gpu.py home (DESIGN.md §8 lists what is pending).  The four SHTC tests
+below have been dry-run with ParticleSystem replaced by tests/host_ops.py's HostBackedSystem (device operator bodies on
+the host), so their own logic and tolerances are known to be sound; the assemble_matrix and random-cloud tests could not
+be (they need CUDA entry points)."""
 import numpy as np
 import pytest
 
@@ -206,7 +209,9 @@ def test_shtc_twist3d_time_loop_and_single_calls():
     case.prologue(ora)
     assert neighbour_sets_equal(dev, ora, ordered=True)
     assert np.max(np.abs(dev.get("J") - 1.0)) < 1e-13 and np.max(np.abs(dev.get("K"))) < 1e-13
-    assert_fields_close(dev, ora, ["T", "P"], rtol=1e-9, what="twist3d prologue", floors={"P": 1.0})
+    # the undeformed column is stress-free: T and P are rounding noise against their natural scales c_s^2 and rho0*c_0^2
+    assert_fields_close(dev, ora, ["T", "P"], rtol=1e-9, what="twist3d prologue",
+                        floors={"P": c["rho0"] * c["c_0"] ** 2, "T": c["c_s"] ** 2})
     # single calls on a moved state
     for _ in range(5):
         case.step(dev)
@@ -234,7 +239,8 @@ def test_shtc_twist3d_time_loop_and_single_calls():
         ora.set(f, dev.get(f))
     for s in (dev, ora):
         s.apply(ops.tw_find_T(rho0, c["c_0"], c["c_s"]))
-    assert_fields_close(dev, ora, ["T", "P"], rtol=1e-10, what="find_T! (3-D)", floors={"P": 1.0})
+    assert_fields_close(dev, ora, ["T", "P"], rtol=1e-10, what="find_T! (3-D)",
+                        floors={"P": c["rho0"] * c["c_0"] ** 2 * 1e-3, "T": c["c_s"] ** 2 * 1e-3})
     ora.set("T", dev.get("T"))
     for s in (dev, ora):
         s.apply(ops.tw_find_f("wendland3", h, rho0, c["c_p"]))
