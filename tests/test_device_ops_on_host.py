@@ -139,7 +139,7 @@ def _cylinder_case():
     (configs.shtc_taco, {}, 3), (configs.collapse3d, {"dr": 1.0e-2}, 2)])
 def test_every_config_with_the_device_bodies_on_the_host(maker, kw, nsteps):
     # every time loop of configs.py, once on the oracle and once on a system whose apply() executes the device operator
-    # bodies (59 of the 66 operators transliterate; the rest fall through to the oracle): a CPU-side guard over the
+    # bodies (63 of the 66 operators transliterate; the rest fall through to the oracle): a CPU-side guard over the
     # operator bodies and their bindings that needs no GPU
     from host_ops import host_backed_system
     Host = host_backed_system()
