@@ -21,6 +21,11 @@
  *                                                                 examples/collapse_dry_implicit.jl:154-163,223-227
  *   sp_reduce                        energy / get_globals loops   examples/collapse_dry.jl:166-187
  *   sp_kernel_eval                   kernel functions             src/kernels.jl
+ *   sp_generate_particles            generate_particles!          src/grids.jl:52-144,253-258, src/geometry.jl:15-258
+ *   sp_respawn                       add_new_particles! (inflow)  examples/cylinder.jl:145-156
+ *   sp_assemble_matrix               assemble_matrix              src/core.jl:196-225
+ *   sp_run_program                   the examples' time loops     examples/collapse3d.jl:134-151, collapse_dry.jl:202-211
+ *   sp_slab_*                        (no counterpart: one process per GPU, slab decomposition over NCCL)
  *
  * Because arbitrary Julia closures cannot run inside CUDA kernels, the per-pair
  * and per-particle actions of the shipped examples are *registered operators*
