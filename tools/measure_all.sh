@@ -5,6 +5,7 @@
 #
 # Writes everything under gpurun_out/<tag>_*; copy what should be judged into profiles/.
 #   1. pytest -m gpu                         (parity gate; the rest is meaningless if it is red)
+#   1b. tests/pending_gpu_round2.py          (checks written when no GPU time was left)
 #   2. bench.py, N = 1                        (value, e2e, roofline, cpu_baseline) and the reference arm
 #   3. ncu launch list of a short bench run   (gpu__time_duration per launch: kernel shares of the step)
 #   4. ncu --set full of the three pair kernels (k_nbr_build, mass replay, force replay) + summary table
@@ -19,6 +20,11 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.acti
 timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider > "$OUT/${TAG}_pytest_gpu.log" 2>&1
 echo "pytest rc=$?" >> "$OUT/${TAG}_pytest_gpu.log"
 tail -3 "$OUT/${TAG}_pytest_gpu.log"
+
+# checks written without a GPU (not collected by the suite above): run them, move the green ones into test_*_gpu.py
+timeout 600 python -m pytest tests/pending_gpu_round2.py -q -p no:cacheprovider > "$OUT/${TAG}_pytest_pending.log" 2>&1
+echo "pending rc=$?" >> "$OUT/${TAG}_pytest_pending.log"
+tail -3 "$OUT/${TAG}_pytest_pending.log"
 
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/${TAG}_bench_reference.json" 2> "$OUT/${TAG}_bench_reference.err"
 timeout 600 python bench.py > "$OUT/${TAG}_bench.json" 2> "$OUT/${TAG}_bench.err"
