@@ -311,8 +311,9 @@ enum {
 enum {
     SP_FLAG_SELF = 1,        /* apply!(...; self=true): add the (p,p,0.0) term after the sweep (core.jl:155-157) */
     SP_FLAG_STRICT_ORDER = 2, /* accumulate in the reference's order: key_diff order x descending index */
-    SP_FLAG_TILE_KERNEL = 4,  /* experimental: shared-memory tile kernel (TMA bulk staging + FP32 pre-filter) */
-    SP_FLAG_PACKED_KERNEL = 8 /* experimental: packed 32-byte records + two-phase compaction through L1 */
+    SP_FLAG_TILE_KERNEL = 4,  /* alternative kernel: shared-memory tile (TMA bulk staging + FP32 pre-filter), no lists */
+    SP_FLAG_UNFUSED_BUILD = 8 /* build the neighbour lists with their own kernel even when the operator has the fused
+                                 build + first-replay kernel (A/B timing, parity of the two-kernel path) */
 };
 
 /* reductions (diagnostic loops of the examples) */

@@ -76,8 +76,6 @@ struct sp_system {
     int* h_counters = nullptr;  // pinned mirror
     double* stage = nullptr;    // upload/download staging + reduction scratch
     long long stage_len = 0;    // in doubles
-    void* pk = nullptr;         // 2 x cap packed 32-byte records (default sweep kernel)
-    long long pk_cap = 0;
     float* ucoord = nullptr;    // 3 planes of FP32 cell-unit coordinates (sweep pre-filter)
     long long ucoord_cap = 0;
     long long x_version = 1;       // bumped whenever positions or the slot order may have changed
@@ -105,6 +103,7 @@ struct sp_system {
     double* h_scal = nullptr;   // pinned mirror of a few scalars
 
     bool have_cells = false;
+    bool capturing = false;   // the stream is being captured into a CUDA graph (sp_program.cu): no host read-backs
     bool in_program = false;  // inside sp_run_program: nested entry points do not touch the per-call timing events
     bool identity_order = true;  // slot s holds reference particle s
     long long n_removed = 0;

@@ -27,6 +27,7 @@ struct WV3 {
 // balance_of_mass!  collapse_dry.jl:112-115, collapse3d.jl:87-90, cavity_flow.jl:92-94 (two_nu = 0)
 template <class K>
 struct OpBalanceOfMass {
+    static constexpr bool FUSED_BUILD = true;  // first pair sweep after a cell-list build: see k_nbr_build_sweep
     static constexpr int NQ = 4;  // vx, vy, vz, rho
     struct Params {
         const double* qp[NQ];
@@ -60,6 +61,7 @@ struct OpBalanceOfMass {
 // internal_force!  collapse_dry.jl:135-141 (3-D: collapse3d.jl:98-104 with the same formula)
 template <class K>
 struct OpInternalForce {
+    static constexpr bool FUSED_BUILD = true;  // first pair sweep after a cell-list build: see k_nbr_build_sweep
     // The per-particle quotient P/rho^2 of both p and q is evaluated ONCE per particle by UPressureOverRho2
     // (same IEEE division as the closure's p.P/p.rho^2, just hoisted out of the pair loop).
     static constexpr int NQ = 4;  // vx, vy, vz, pr = P/rho^2
@@ -108,6 +110,7 @@ struct OpInternalForce {
 // change of x, v, kernel, m or h in between fall back to the plain operator.
 template <class K>
 struct OpBalanceOfMassAux {
+    static constexpr bool FUSED_BUILD = true;  // first pair sweep after a cell-list build: see k_nbr_build_sweep
     static constexpr int NQ = 4;  // vx, vy, vz, rho
     struct Params {
         const double* qp[NQ];
@@ -185,6 +188,7 @@ struct OpInternalForceCached {
 // internal_force!  cavity_flow.jl:102-114 (rDwendland2; lid extrapolation; Monaghan viscosity)
 template <class K>
 struct OpInternalForceCavity {
+    static constexpr bool FUSED_BUILD = true;  // first pair sweep after a cell-list build: see k_nbr_build_sweep
     static constexpr int NQ = 6;  // vx, vy, vz, pr = P/rho^2, rho, type
     struct Params {
         const double* qp[NQ];
@@ -1303,6 +1307,7 @@ struct OpInternalForceSym {
 // viscous_force!  :128-130
 template <class K>
 struct OpIsphViscous {
+    static constexpr bool FUSED_BUILD = true;  // first pair sweep after a cell-list build: see k_nbr_build_sweep
     static constexpr int NQ = 3;  // vx, vy, vz
     struct Params {
         const double* qp[NQ];

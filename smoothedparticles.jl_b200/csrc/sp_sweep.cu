@@ -438,103 +438,6 @@ __global__ void __launch_bounds__(TP, MINB) k_sweep_tile(SpGrid g, SweepCtx c, t
     }
 }
 
-// ---- hit-mask kernel (default path).
-// Same mapping as the reference-order kernel (one thread per target, candidate rows through L1, 16+ warps
-// per SM) but the divergent pair body is taken out of the candidate loop:
-//   phase 1  for a chunk of up to 32 candidates of a stencil row, evaluate the exact un-fused predicate and set
-//            a bit of a 32-bit REGISTER mask — no branch, no shared memory (the unified L1/shared array stays L1);
-//   phase 2  after three chunks (one dk-plane of the stencil) walk the set bits and run the operator body.
-// The body then executes max-over-lanes(hits per 3 rows) ~ 16 times per plane instead of ~72 times (once per
-// candidate iteration at ~15 % lane use in the baseline profile).
-template <class Op>
-__global__ void __launch_bounds__(128, 4) k_sweep_mask(SpGrid g, SweepCtx c, typename Op::Params P, int self_flag) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
-    if (!Op::active(P, i)) return;
-    const double xi = c.x[i], yi = c.y[i], zi = c.z[i];
-    const float ui = c.ux[i], vi = c.uy[i], wi = c.uz[i];
-    typename Op::PS p;
-    typename Op::Acc acc;
-    Op::load(P, i, xi, yi, zi, p, acc);
-    const double T2 = g.T2;
-    const float thr = c.thr;
-    unsigned long long ui2, vi2, wi2;  // own coordinates duplicated into FP32x2 registers
-    asm("mov.b64 %0, {%1,%1};" : "=l"(ui2) : "f"(ui));
-    asm("mov.b64 %0, {%1,%1};" : "=l"(vi2) : "f"(vi));
-    asm("mov.b64 %0, {%1,%1};" : "=l"(wi2) : "f"(wi));
-    unsigned m0 = 0u, m1 = 0u, m2 = 0u;  // pending chunks (newest in m0)
-    int b0 = 0, b1 = 0, b2 = 0;          // first slot of each pending chunk
-    auto run = [&](unsigned m, int base) {
-        while (m) {
-            const int j = base + __ffs(m) - 1;
-            m &= m - 1;
-            const double dx = __dsub_rn(xi, c.x[j]), dy = __dsub_rn(yi, c.y[j]), dz = __dsub_rn(zi, c.z[j]);
-            const double d2 = sp_d2(dx, dy, dz);
-            // the decision itself: (r > h || p == q) && continue (core.jl:105)  <=>  d2 > T2 with r = sqrt_rn(d2)
-            if (d2 > T2 || j == i) continue;
-            QGlobal<Op::NQ> q{P.qp, j};
-            Op::pair(P, p, q, dx, dy, dz, sp_sqrt_fast(d2), acc);
-        }
-    };
-    auto drain = [&]() {
-        run(m2, b2);
-        run(m1, b1);
-        run(m0, b0);
-        m0 = m1 = m2 = 0u;
-    };
-    const long long key = sp_find_key(g, xi, yi, zi);  // core.jl:95 recomputes the key from the current x
-    const long long L1 = g.lim[0], L12 = g.lim[0] * g.lim[1];
-    const int nk = (g.dim == 2) ? 0 : 1;
-    for (int dk = -nk; dk <= nk; dk++) {
-        for (int dj = -1; dj <= 1; dj++) {
-            const long long mid = key + L1 * dj + L12 * dk;
-            long long klo = mid - 1, khi = mid + 1;
-            if (klo < 1) klo = 1;
-            if (khi > g.key_max) khi = g.key_max;
-            if (klo > khi) continue;
-            const int jb = c.cell_start[klo], je = c.cell_start[khi + 1];
-            // chunks of 32 slots starting at an even slot, so two candidates share one 64-bit load per plane and
-            // one packed FP32x2 instruction per operation (FADD2 / FMUL2 / FFMA2 on sm_100)
-            for (int j0 = jb & ~1; j0 < je; j0 += 32) {
-                const int nj = min(32, je - j0);
-                unsigned m = 0u;
-                // phase 1: conservative FP32 pre-filter in cell units (never rejects a true neighbour, see launch)
-#pragma unroll
-                for (int u = 0; u < 16; u++) {
-                    if (2 * u >= nj) break;
-                    const unsigned long long qx = __ldg(reinterpret_cast<const unsigned long long*>(c.ux + j0) + u);
-                    const unsigned long long qy = __ldg(reinterpret_cast<const unsigned long long*>(c.uy + j0) + u);
-                    const unsigned long long qz = __ldg(reinterpret_cast<const unsigned long long*>(c.uz + j0) + u);
-                    unsigned long long dx, dy, dz, dd;
-                    asm("sub.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(ui2), "l"(qx));
-                    asm("sub.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(vi2), "l"(qy));
-                    asm("sub.f32x2 %0, %1, %2;" : "=l"(dz) : "l"(wi2), "l"(qz));
-                    asm("mul.f32x2 %0, %1, %1;" : "=l"(dd) : "l"(dx));
-                    asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(dd) : "l"(dy), "l"(dd));
-                    asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(dd) : "l"(dz), "l"(dd));
-                    float d0, d1;
-                    asm("mov.b64 {%0,%1}, %2;" : "=f"(d0), "=f"(d1) : "l"(dd));
-                    // !(dd > thr) also keeps NaN distances, which the reference lets through as well
-                    if (!(d0 > thr)) m |= 1u << (2 * u);
-                    if (!(d1 > thr)) m |= 2u << (2 * u);
-                }
-                // only slots of this row range count (the aligned chunk may start one slot early / end one late)
-                const int lo_bit = max(jb - j0, 0);
-                unsigned valid = nj >= 32 ? 0xffffffffu : ((1u << nj) - 1u);
-                valid &= ~((1u << lo_bit) - 1u);
-                m &= valid;
-                if (m2) drain();
-                m2 = m1; b2 = b1;
-                m1 = m0; b1 = b0;
-                m0 = m;  b0 = j0;
-            }
-        }
-        drain();
-    }
-    if (self_flag & 1) Op::self(P, p, acc);
-    Op::store(P, i, p, acc);
-}
-
 // ---- neighbour-list cache (default path): build once per position version, replay per operator.
 // Positions do not change between the pair sweeps of one time step (WCSPH: balance_of_mass! and internal_force!;
 // ISPH: viscous_force!, div_L_lambda!, every CG mat-vec, internal_force!), so the op-independent part of
@@ -757,336 +660,155 @@ __global__ void __launch_bounds__(128, 6) k_sweep_list(SpGrid g, SweepCtx c, con
     Op::store(P, i, p, acc);
 }
 
-// ---- hit-mask kernel, two targets per thread.
-// Adjacent slots are almost always in the same cell, so they share their candidate rows: one thread owns the
-// targets 2t and 2t+1, loads every candidate pair once and tests it against both (half the L1 traffic and a
-// quarter fewer instructions per test in phase 1, two independent dependency chains).  Each target keeps its own
-// masks, restricted to its own row range, so the visited set per target is exactly the reference's.  When the two
-// targets are not in the same or adjacent cells (end of a cell row) they are swept one after the other.
+// ---- fused list build + first replay (default for the operators that declare FUSED_BUILD, i.e. the first pair sweep
+// after create_cell_list! in the WCSPH / ISPH time loops).
+// Phase A is the FP32 candidate scan of k_nbr_build with ONE threshold: every candidate that MAY be a neighbour
+// (d2_f32 <= 1 + delta) is appended to the target's own column of the warp-tiled list.  Phase B replays that column
+// exactly like k_sweep_list, and since the pair body needs the exact FP64 d2 anyway, the reference's predicate
+// (r > h) && continue  <=>  d2 > T2  (core.jl:105) is decided THERE, for free: the few false "maybes" of the thin FP32
+// shell are dropped and the column is compacted in place, so what stays in HBM is the exact neighbour list in visiting
+// order — the same lists k_nbr_build writes, for the later sweeps of the step.  Against build + replay as two kernels
+// this saves the second classification (2 of 7.25 instructions per candidate), the three-chunk reject queue, one
+// 1.2 GB read of the lists from HBM and a launch; and the issue-bound scan of some warps overlaps with the
+// L1-bound gathers of others on the same SM.
 template <class Op>
-__global__ void __launch_bounds__(128, 4) k_sweep_mask2(SpGrid g, SweepCtx c, typename Op::Params P, int self_flag) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int iA = 2 * t, iB = 2 * t + 1;
-    if (iA >= c.n) return;
-    const bool actA = Op::active(P, iA);
-    const bool actB = (iB < c.n) && Op::active(P, iB);
-    if (!actA && !actB) return;
-    const double T2 = g.T2;
-    const float thr = c.thr;
-    const long long L1 = g.lim[0], L12 = g.lim[0] * g.lim[1];
-    const int nk = (g.dim == 2) ? 0 : 1;
-
-    double xA = 0, yA = 0, zA = 0, xB = 0, yB = 0, zB = 0;
-    long long keyA = 0, keyB = 0;
-    typename Op::PS pA, pB;
-    typename Op::Acc accA, accB;
-    unsigned long long uA = 0, vA = 0, wA = 0, uB = 0, vB = 0, wB = 0;
-    if (actA) {
-        xA = c.x[iA]; yA = c.y[iA]; zA = c.z[iA];
-        keyA = sp_find_key(g, xA, yA, zA);
-        Op::load(P, iA, xA, yA, zA, pA, accA);
-        const float a = c.ux[iA], b = c.uy[iA], d = c.uz[iA];
-        asm("mov.b64 %0, {%1,%1};" : "=l"(uA) : "f"(a));
-        asm("mov.b64 %0, {%1,%1};" : "=l"(vA) : "f"(b));
-        asm("mov.b64 %0, {%1,%1};" : "=l"(wA) : "f"(d));
-    }
-    if (actB) {
-        xB = c.x[iB]; yB = c.y[iB]; zB = c.z[iB];
-        keyB = sp_find_key(g, xB, yB, zB);
-        Op::load(P, iB, xB, yB, zB, pB, accB);
-        const float a = c.ux[iB], b = c.uy[iB], d = c.uz[iB];
-        asm("mov.b64 %0, {%1,%1};" : "=l"(uB) : "f"(a));
-        asm("mov.b64 %0, {%1,%1};" : "=l"(vB) : "f"(b));
-        asm("mov.b64 %0, {%1,%1};" : "=l"(wB) : "f"(d));
-    }
-    const bool both = actA && actB;
-    const bool near = both && (keyA - keyB <= 1) && (keyB - keyA <= 1);
-    const int npass = (both && !near) ? 2 : 1;
-
-    for (int pass = 0; pass < npass; pass++) {
-        // which targets this pass sweeps
-        const bool onA = actA && (pass == 0);
-        const bool onB = actB && (npass == 1 || pass == 1);
-        unsigned mA0 = 0u, mA1 = 0u, mA2 = 0u, mB0 = 0u, mB1 = 0u, mB2 = 0u;  // pending chunks (newest in *0)
-        int b0 = 0, b1 = 0, b2 = 0;
-        auto runA = [&](unsigned m, int base) {
-            while (m) {
-                const int j = base + __ffs(m) - 1;
-                m &= m - 1;
-                const double dx = __dsub_rn(xA, c.x[j]), dy = __dsub_rn(yA, c.y[j]), dz = __dsub_rn(zA, c.z[j]);
-                const double d2 = sp_d2(dx, dy, dz);
-                // the decision itself: (r > h || p == q) && continue (core.jl:105)  <=>  d2 > T2, r = sqrt_rn(d2)
-                if (d2 > T2 || j == iA) continue;
-                QGlobal<Op::NQ> q{P.qp, j};
-                Op::pair(P, pA, q, dx, dy, dz, sp_sqrt_fast(d2), accA);
-            }
-        };
-        auto runB = [&](unsigned m, int base) {
-            while (m) {
-                const int j = base + __ffs(m) - 1;
-                m &= m - 1;
-                const double dx = __dsub_rn(xB, c.x[j]), dy = __dsub_rn(yB, c.y[j]), dz = __dsub_rn(zB, c.z[j]);
-                const double d2 = sp_d2(dx, dy, dz);
-                if (d2 > T2 || j == iB) continue;
-                QGlobal<Op::NQ> q{P.qp, j};
-                Op::pair(P, pB, q, dx, dy, dz, sp_sqrt_fast(d2), accB);
-            }
-        };
-        auto drain = [&]() {
-            runA(mA2, b2); runA(mA1, b1); runA(mA0, b0);
-            runB(mB2, b2); runB(mB1, b1); runB(mB0, b0);
-            mA0 = mA1 = mA2 = mB0 = mB1 = mB2 = 0u;
-        };
+__global__ void __launch_bounds__(128, 5) k_nbr_build_sweep(SpGrid g, SweepCtx c, int* cnt, int* ids, int* max_cnt,
+                                                            typename Op::Params P, int self_flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    const int capk = c.capk;
+    int* col = ids + ((size_t)(i >> 5) * capk << 5) + (i & 31);
+    const double xi = c.x[i], yi = c.y[i], zi = c.z[i];
+    int n_maybe = 0;
+    {
+        const float ui = c.ux[i], vi = c.uy[i], wi = c.uz[i];
+        unsigned long long ui2, vi2, wi2, thr2;
+        asm("mov.b64 %0, {%1,%1};" : "=l"(ui2) : "f"(ui));
+        asm("mov.b64 %0, {%1,%1};" : "=l"(vi2) : "f"(vi));
+        asm("mov.b64 %0, {%1,%1};" : "=l"(wi2) : "f"(wi));
+        asm("mov.b64 %0, {%1,%1};" : "=l"(thr2) : "f"(c.thr));
+        const long long key = sp_find_key(g, xi, yi, zi);  // core.jl:95
+        const long long L1 = g.lim[0], L12 = g.lim[0] * g.lim[1];
+        const int nk = (g.dim == 2) ? 0 : 1;
         for (int dk = -nk; dk <= nk; dk++) {
             for (int dj = -1; dj <= 1; dj++) {
-                // own row range of each swept target, then their union
-                int jbA = 0, jeA = 0, jbB = 0, jeB = 0;
-                if (onA) {
-                    const long long mid = keyA + L1 * dj + L12 * dk;
-                    long long klo = mid - 1, khi = mid + 1;
-                    if (klo < 1) klo = 1;
-                    if (khi > g.key_max) khi = g.key_max;
-                    if (klo <= khi) {
-                        jbA = c.cell_start[klo];
-                        jeA = c.cell_start[khi + 1];
-                    }
-                }
-                if (onB) {
-                    const long long mid = keyB + L1 * dj + L12 * dk;
-                    long long klo = mid - 1, khi = mid + 1;
-                    if (klo < 1) klo = 1;
-                    if (khi > g.key_max) khi = g.key_max;
-                    if (klo <= khi) {
-                        jbB = c.cell_start[klo];
-                        jeB = c.cell_start[khi + 1];
-                    }
-                }
-                const bool hasA = jeA > jbA, hasB = jeB > jbB;
-                if (!hasA && !hasB) continue;
-                const int jb = hasA && hasB ? min(jbA, jbB) : hasA ? jbA : jbB;
-                const int je = hasA && hasB ? max(jeA, jeB) : hasA ? jeA : jeB;
-                for (int j0 = jb & ~1; j0 < je; j0 += 32) {
+                const long long mid = key + L1 * dj + L12 * dk;
+                long long klo = mid - 1, khi = mid + 1;
+                if (klo < 1) klo = 1;
+                if (khi > g.key_max) khi = g.key_max;
+                if (klo > khi) continue;
+                const int jb = c.cell_start[klo], je = c.cell_start[khi + 1];
+                for (int j0 = jb & ~3; j0 < je; j0 += 32) {
                     const int nj = min(32, je - j0);
-                    unsigned mA = 0u, mB = 0u;
-                    // phase 1: conservative FP32 pre-filter, two candidates per load, both targets per candidate
+                    const int nq = (nj + 3) >> 2;
+                    unsigned not_maybe = 0u;  // candidate k of the chunk lands in bit 4*nq-1-k
+                    const ulonglong2* px = reinterpret_cast<const ulonglong2*>(c.ux + j0);
+                    const ulonglong2* py = reinterpret_cast<const ulonglong2*>(c.uy + j0);
+                    const ulonglong2* pz = reinterpret_cast<const ulonglong2*>(c.uz + j0);
 #pragma unroll
-                    for (int u = 0; u < 16; u++) {
-                        if (2 * u >= nj) break;
-                        const unsigned long long qx = __ldg(reinterpret_cast<const unsigned long long*>(c.ux + j0) + u);
-                        const unsigned long long qy = __ldg(reinterpret_cast<const unsigned long long*>(c.uy + j0) + u);
-                        const unsigned long long qz = __ldg(reinterpret_cast<const unsigned long long*>(c.uz + j0) + u);
-                        unsigned long long dx, dy, dz, dd;
-                        float d0, d1;
-                        asm("sub.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(uA), "l"(qx));
-                        asm("sub.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(vA), "l"(qy));
-                        asm("sub.f32x2 %0, %1, %2;" : "=l"(dz) : "l"(wA), "l"(qz));
-                        asm("mul.f32x2 %0, %1, %1;" : "=l"(dd) : "l"(dx));
-                        asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(dd) : "l"(dy), "l"(dd));
-                        asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(dd) : "l"(dz), "l"(dd));
-                        asm("mov.b64 {%0,%1}, %2;" : "=f"(d0), "=f"(d1) : "l"(dd));
-                        if (!(d0 > thr)) mA |= 1u << (2 * u);
-                        if (!(d1 > thr)) mA |= 2u << (2 * u);
-                        asm("sub.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(uB), "l"(qx));
-                        asm("sub.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(vB), "l"(qy));
-                        asm("sub.f32x2 %0, %1, %2;" : "=l"(dz) : "l"(wB), "l"(qz));
-                        asm("mul.f32x2 %0, %1, %1;" : "=l"(dd) : "l"(dx));
-                        asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(dd) : "l"(dy), "l"(dd));
-                        asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(dd) : "l"(dz), "l"(dd));
-                        asm("mov.b64 {%0,%1}, %2;" : "=f"(d0), "=f"(d1) : "l"(dd));
-                        if (!(d0 > thr)) mB |= 1u << (2 * u);
-                        if (!(d1 > thr)) mB |= 2u << (2 * u);
-                    }
-                    // each target only sees the slots of its OWN row range
-                    auto window = [&](int lo, int hi) -> unsigned {
-                        const int a = max(lo - j0, 0), b = min(hi - j0, 32);
-                        if (b <= a) return 0u;
-                        const unsigned up = b >= 32 ? 0xffffffffu : ((1u << b) - 1u);
-                        return up & ~((1u << a) - 1u);
-                    };
-                    mA &= hasA ? window(jbA, jeA) : 0u;
-                    mB &= hasB ? window(jbB, jeB) : 0u;
-                    if (mA2 | mB2) drain();
-                    mA2 = mA1; mB2 = mB1; b2 = b1;
-                    mA1 = mA0; mB1 = mB0; b1 = b0;
-                    mA0 = mA;  mB0 = mB;  b0 = j0;
-                }
-            }
-            drain();
-        }
-    }
-    if (actA) {
-        if (self_flag & 1) Op::self(P, pA, accA);
-        Op::store(P, iA, pA, accA);
-    }
-    if (actB) {
-        if (self_flag & 1) Op::self(P, pB, accB);
-        Op::store(P, iB, pB, accB);
-    }
-}
-
-// ---- packed-record kernel (experimental, SP_FLAG_PACKED_KERNEL).
-// One thread per target, candidates read through L1 — but from two 32-byte records per particle that a
-// prep pass packs from the SoA planes:  pk0 = {x, y, z, qa}  pk1 = {q0, q1, q2, qb}, so a candidate test costs
-// ONE 256-bit load (LDG.E.256) instead of three 64-bit loads from three planes (the reference-order kernel is
-// bound by L1 wavefronts: 90 % in the round-1 baseline profile).  The sweep is split in two phases:
-//   phase 1  exact un-fused predicate over the 3/9 row ranges; accepted slots are appended to a private
-//            list in shared memory — a short branch-light loop;
-//   phase 2  the operator body (sqrt, kernel, FMAs) over the list, so the expensive part runs with nearly all
-//            lanes active instead of the ~15 % hit rate of the candidate loop.
-// Lanes of one cell share most neighbours, so phase-2 gathers touch only a few 128-byte lines per request.
-struct __align__(32) SpRec {
-    double a, b, c, d;
-};
-__device__ __forceinline__ SpRec sp_ld256(const SpRec* p) {
-    // two 128-bit read-only loads that allocate in L1.  (A single ld.global.nc.v4.f64 = LDG.E.ENL2.256 was
-    // measured to bypass L1 on sm_100a: 7 % L1 hit rate, every candidate a trip to L2 — profiles/r1_notes.md.)
-    const double2 lo = __ldg(reinterpret_cast<const double2*>(p));
-    const double2 hi = __ldg(reinterpret_cast<const double2*>(p) + 1);
-    return SpRec{lo.x, lo.y, hi.x, hi.y};
-}
-// which record component carries q-plane k (see k_pack)
-template <int NQ>
-struct QPacked {
-    const double* const* qp;
-    SpRec r0, r1;
-    int j;
-    __device__ __forceinline__ double operator()(int k) const {
-        if (NQ == 1) return r0.d;
-        if (k < 3) return k == 0 ? r1.a : k == 1 ? r1.b : r1.c;
-        if (k == 3) return r0.d;
-        if (k == 4) return r1.d;
-        return qp[k][j];
-    }
-};
-template <int NQ>
-struct PackPlanes {
-    const double* qp[NQ > 0 ? NQ : 1];
-};
-template <int NQ>
-__global__ void __launch_bounds__(256) k_pack(const double* __restrict__ x, long long cap, PackPlanes<NQ> pl,
-                                              SpRec* __restrict__ pk0, SpRec* __restrict__ pk1, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    SpRec a{x[i], x[cap + i], x[2 * cap + i], 0.0};
-    if (NQ == 1) a.d = pl.qp[0][i];
-    if (NQ >= 4) a.d = pl.qp[3][i];
-    pk0[i] = a;
-    if (NQ >= 2) {
-        SpRec b{pl.qp[0][i], pl.qp[1][i], NQ >= 3 ? pl.qp[2 < NQ ? 2 : 0][i] : 0.0, NQ >= 5 ? pl.qp[4 < NQ ? 4 : 0][i] : 0.0};
-        pk1[i] = b;
-    }
-}
-
-// list replay over packed 32-byte records (experimental, SP_SWEEP_MASK=4): 4 x LDG.128 per pair instead of 7 x LDG.64
-template <class Op>
-__global__ void __launch_bounds__(128, 6) k_sweep_list_pk(SpGrid g, SweepCtx c, const int* __restrict__ cnt,
-                                                          const int* __restrict__ ids, typename Op::Params P,
-                                                          const SpRec* __restrict__ pk0, const SpRec* __restrict__ pk1,
-                                                          int self_flag) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
-    if (!Op::active(P, i)) return;
-    const double xi = c.x[i], yi = c.y[i], zi = c.z[i];
-    typename Op::PS p;
-    typename Op::Acc acc;
-    Op::load(P, i, xi, yi, zi, p, acc);
-    const int n_nb = min(cnt[i], c.capk);
-    const int* col = ids + ((size_t)(i >> 5) * c.capk << 5) + (i & 31);
-#pragma unroll 2
-    for (int k = 0; k < n_nb; k++) {
-        const int j = __ldcs(col + (k << 5));
-        QPacked<Op::NQ> q;
-        q.qp = P.qp;
-        q.j = j;
-        q.r0 = sp_ld256(pk0 + j);
-        if (Op::NQ >= 2) q.r1 = sp_ld256(pk1 + j);
-        const double dx = __dsub_rn(xi, q.r0.a), dy = __dsub_rn(yi, q.r0.b), dz = __dsub_rn(zi, q.r0.c);
-        const double d2 = sp_d2(dx, dy, dz);
-        Op::pair(P, p, q, dx, dy, dz, sp_sqrt_fast(d2), acc);
-    }
-    if (self_flag & 1) Op::self(P, p, acc);
-    Op::store(P, i, p, acc);
-}
-
-template <class Op, int TP, int LCAP>
-__global__ void __launch_bounds__(TP) k_sweep_pk(SpGrid g, SweepCtx c, typename Op::Params P, const SpRec* __restrict__ pk0,
-                                                 const SpRec* __restrict__ pk1, int self_flag) {
-    constexpr int NQ = Op::NQ;
-    extern __shared__ int list[];  // [LCAP][TP]
-    const int tid = threadIdx.x;
-    const int i = blockIdx.x * TP + tid;
-    if (i >= c.n) return;
-    if (!Op::active(P, i)) return;
-    const SpRec me = sp_ld256(pk0 + i);
-    const double xi = me.a, yi = me.b, zi = me.c;
-    typename Op::PS p;
-    typename Op::Acc acc;
-    Op::load(P, i, xi, yi, zi, p, acc);
-    const double T2 = g.T2;
-    int cnt = 0;
-    auto flush = [&]() {
-        for (int k = 0; k < cnt; k += 2) {
-            // two list entries in flight (the second may be padding: computed, then discarded)
-            const bool two = (k + 1) < cnt;
-            QPacked<NQ> q[2];
+                    for (int q = 0; q < 8; q++) {
+                        if (q >= nq) break;
+                        const ulonglong2 qx = __ldg(px + q), qy = __ldg(py + q), qz = __ldg(pz + q);
+                        const unsigned long long cx[2] = {qx.x, qx.y}, cy[2] = {qy.x, qy.y}, cz[2] = {qz.x, qz.y};
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
-                q[u].qp = P.qp;
-                q[u].j = list[((u == 1 && !two) ? k : k + u) * TP + tid];
-                q[u].r0 = sp_ld256(pk0 + q[u].j);
-                if (NQ >= 2) q[u].r1 = sp_ld256(pk1 + q[u].j);
-            }
-            double dx[2], dy[2], dz[2], r[2];
-#pragma unroll
-            for (int u = 0; u < 2; u++) {
-                dx[u] = __dsub_rn(xi, q[u].r0.a);
-                dy[u] = __dsub_rn(yi, q[u].r0.b);
-                dz[u] = __dsub_rn(zi, q[u].r0.c);
-                r[u] = sp_sqrt_fast(sp_d2(dx[u], dy[u], dz[u]));
-            }
-            Op::pair(P, p, q[0], dx[0], dy[0], dz[0], r[0], acc);
-            typename Op::Acc t = acc;
-            Op::pair(P, p, q[1], dx[1], dy[1], dz[1], r[1], t);
-            if (two) acc = t;
-        }
-        cnt = 0;
-    };
-    const long long key = sp_find_key(g, xi, yi, zi);  // core.jl:95 recomputes the key from the current x
-    const long long L1 = g.lim[0], L12 = g.lim[0] * g.lim[1];
-    const int nk = (g.dim == 2) ? 0 : 1;
-    for (int dk = -nk; dk <= nk; dk++)
-        for (int dj = -1; dj <= 1; dj++) {
-            const long long mid = key + L1 * dj + L12 * dk;
-            long long klo = mid - 1, khi = mid + 1;
-            if (klo < 1) klo = 1;
-            if (khi > g.key_max) khi = g.key_max;
-            if (klo > khi) continue;
-            const int jb = c.cell_start[klo], je = c.cell_start[khi + 1];
-            for (int j0 = jb; j0 < je; j0 += LCAP) {
-                const int j1 = min(je, j0 + LCAP);
-                if (cnt + (j1 - j0) > LCAP) flush();
-                for (int j = j0; j < j1; j += 4) {
-                    // 4 independent candidates in flight: all loads first, then the exact tests
-                    SpRec r[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) r[u] = sp_ld256(pk0 + min(j + u, j1 - 1));
-                    bool hit[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const double dx = __dsub_rn(xi, r[u].a), dy = __dsub_rn(yi, r[u].b), dz = __dsub_rn(zi, r[u].c);
-                        // (r > h || p == q) && continue   (core.jl:105)  <=>  d2 > T2 with r = sqrt_rn(d2)
-                        hit[u] = !(sp_d2(dx, dy, dz) > T2) && (j + u) != i && (j + u) < j1;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; u++)
-                        if (hit[u]) {
-                            list[cnt * TP + tid] = j + u;
-                            cnt++;
+                        for (int e = 0; e < 2; e++) {
+                            unsigned long long dx, dy, dz, dd, ta;
+                            asm("sub.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(ui2), "l"(cx[e]));
+                            asm("sub.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(vi2), "l"(cy[e]));
+                            asm("sub.f32x2 %0, %1, %2;" : "=l"(dz) : "l"(wi2), "l"(cz[e]));
+                            asm("mul.f32x2 %0, %1, %1;" : "=l"(dd) : "l"(dx));
+                            asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(dd) : "l"(dy), "l"(dd));
+                            asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(dd) : "l"(dz), "l"(dd));
+                            // sign(thr - dd) = 1  <=>  dd > thr: certainly not a neighbour.  A NaN distance gives the
+                            // canonical positive NaN: it stays a candidate, and the exact test accepts it as the
+                            // reference does (NaN > h is false)
+                            asm("sub.f32x2 %0, %1, %2;" : "=l"(ta) : "l"(thr2), "l"(dd));
+                            unsigned a0, a1;
+                            asm("mov.b64 {%0,%1}, %2;" : "=r"(a0), "=r"(a1) : "l"(ta));
+                            not_maybe = __funnelshift_l(a0, not_maybe, 1);
+                            not_maybe = __funnelshift_l(a1, not_maybe, 1);
                         }
+                    }
+                    unsigned m = __brev(~not_maybe) >> (32 - 4 * nq);
+                    // only slots of this row range count (the aligned chunk may start up to 3 slots early / end late)
+                    const int lo_bit = max(jb - j0, 0);
+                    unsigned valid = nj >= 32 ? 0xffffffffu : ((1u << nj) - 1u);
+                    valid &= ~((1u << lo_bit) - 1u);
+                    m &= valid;
+                    const unsigned self_off = (unsigned)(i - j0);  // p == q (core.jl:105): drop the own slot's bit
+                    if (self_off < 32u) m &= ~(1u << self_off);
+                    while (m) {
+                        const int j = j0 + __ffs(m) - 1;
+                        m &= m - 1;
+                        if (n_maybe < capk) col[n_maybe << 5] = j;
+                        n_maybe++;
+                    }
                 }
             }
         }
-    flush();
+    }
+    // ---- phase B: replay the own column with the exact predicate, compacting it in place
+    const double T2 = g.T2;
+    const bool act = Op::active(P, i);
+    typename Op::PS p;
+    typename Op::Acc acc;
+    if (act) Op::load(P, i, xi, yi, zi, p, acc);
+    int n_out = 0;
+    if (n_maybe <= capk) {
+        constexpr int U = Op::NQ <= 1 ? 4 : 2;
+        int k = 0;
+        for (; k + U <= n_maybe; k += U) {
+            int jj[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) jj[u] = col[(k + u) << 5];
+            double qx[U], qy[U], qz[U];
+            QRegs<Op::NQ> q[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                qx[u] = c.x[jj[u]];
+                qy[u] = c.y[jj[u]];
+                qz[u] = c.z[jj[u]];
+#pragma unroll
+                for (int e = 0; e < Op::NQ; e++) q[u].v[e] = P.qp[e][jj[u]];
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const double dx = __dsub_rn(xi, qx[u]), dy = __dsub_rn(yi, qy[u]), dz = __dsub_rn(zi, qz[u]);
+                const double d2 = sp_d2(dx, dy, dz);
+                if (d2 > T2) continue;  // (r > h) && continue, core.jl:105
+                if (n_out != k + u) col[n_out << 5] = jj[u];
+                n_out++;
+                if (act) Op::pair(P, p, q[u], dx, dy, dz, sp_sqrt_fast(d2), acc);
+            }
+        }
+        for (; k < n_maybe; k++) {
+            const int j = col[k << 5];
+            const double dx = __dsub_rn(xi, c.x[j]), dy = __dsub_rn(yi, c.y[j]), dz = __dsub_rn(zi, c.z[j]);
+            const double d2 = sp_d2(dx, dy, dz);
+            if (d2 > T2) continue;
+            if (n_out != k) col[n_out << 5] = j;
+            n_out++;
+            if (act) {
+                QGlobal<Op::NQ> q{P.qp, j};
+                Op::pair(P, p, q, dx, dy, dz, sp_sqrt_fast(d2), acc);
+            }
+        }
+    } else {
+        // more candidates than the lists hold per target: the exact candidate scan in the same visiting order; the first
+        // capk accepted slots are still recorded, so a target whose TRUE count fits is replayed from its list later
+        sp_for_candidates<false>(g, c, xi, yi, zi, [&](int j, double dx, double dy, double dz, double d2) {
+            if (d2 > T2 || j == i) return;
+            if (n_out < capk) col[n_out << 5] = j;
+            n_out++;
+            if (act) {
+                QGlobal<Op::NQ> q{P.qp, j};
+                Op::pair(P, p, q, dx, dy, dz, sp_sqrt_fast(d2), acc);
+            }
+        });
+    }
+    cnt[i] = n_out;
+    if (n_out > capk) atomicMax(max_cnt, n_out);  // rare: lets the host grow the lists for the next build
+    if (!act) return;
     if (self_flag & 1) Op::self(P, p, acc);
     Op::store(P, i, p, acc);
 }
@@ -1132,17 +854,16 @@ static int launch_tile(sp_system* s, const SweepCtx& c, const typename Op::Param
     return SP_OK;
 }
 
-// 3 (default) = cached neighbour lists; 1 = register hit masks per sweep; 2 = two targets per thread (slower, see
-// profiles/r1_sweep_exploration.md); 4 = lists + packed records; 0 = plain candidate scan
-static int sp_sweep_mode() {
-    static const int mode = getenv("SP_SWEEP_MASK") ? atoi(getenv("SP_SWEEP_MASK")) : 3;
-    return mode;
-}
 // the balance_of_mass -> internal_force cache (OpBalanceOfMassAux) is used on the default path only
 static bool sp_pair_aux_enabled(int flags) {
     static const bool on = !(getenv("SP_PAIR_AUX") && atoi(getenv("SP_PAIR_AUX")) == 0);
-    return on && sp_sweep_mode() == 3 && !(flags & (SP_FLAG_STRICT_ORDER | SP_FLAG_TILE_KERNEL | SP_FLAG_PACKED_KERNEL)) &&
-           !getenv("SP_SWEEP_TILE") && !getenv("SP_SWEEP_VARIANT");
+    return on && !(flags & (SP_FLAG_STRICT_ORDER | SP_FLAG_TILE_KERNEL));
+}
+// SP_FUSED_BUILD=0 builds the lists with k_nbr_build and replays them with k_sweep_list even for the operators that
+// have the fused kernel (A/B timing and the parity tests of the two-kernel path)
+static bool sp_fused_build_enabled() {
+    static const bool on = !(getenv("SP_FUSED_BUILD") && atoi(getenv("SP_FUSED_BUILD")) == 0);
+    return on;
 }
 
 static void sp_sweep_ctx(sp_system* s, SweepCtx& c) {
@@ -1191,8 +912,10 @@ static int sp_ensure_prefilter(sp_system* s, SweepCtx& c) {
     return SP_OK;
 }
 
-// (re)build the cached neighbour lists if positions / slot order changed since they were built
-static int sp_ensure_nbr_cache(sp_system* s, SweepCtx& c) {
+// Make room for the cached neighbour lists and tell whether they have to be (re)built: positions / slot order changed
+// since they were built.  The caller launches the build (k_nbr_build, or the fused k_nbr_build_sweep) and then calls
+// sp_nbr_built.
+static int sp_nbr_prepare(sp_system* s, SweepCtx& c, bool* need_build) {
     int rc = sp_ensure_prefilter(s, c);
     if (rc) return rc;
     const bool rebuild = s->nbr_version != s->x_version || s->nbr_n != s->n || !s->nbr_ids || s->nbr_cap != s->cap;
@@ -1222,16 +945,27 @@ static int sp_ensure_nbr_cache(sp_system* s, SweepCtx& c) {
         s->nbr_version = 0;
     }
     c.capk = s->nbr_capk;
-    if (s->nbr_version != s->x_version || s->nbr_n != s->n) {
-        SP_CUDA(s, cudaMemsetAsync(s->counters + 40, 0, sizeof(int), s->stream));
-        SP_LAUNCH(s, k_nbr_build<1>, sp_blocks(s->n, 128), 128, 0, s->g, c, s->nbr_cnt, s->nbr_ids, s->counters + 40);
+    *need_build = s->nbr_version != s->x_version || s->nbr_n != s->n;
+    if (*need_build) SP_CUDA(s, cudaMemsetAsync(s->counters + 40, 0, sizeof(int), s->stream));
+    return SP_OK;
+}
+static int sp_nbr_built(sp_system* s) {
+    // the longest list of this build travels to the host asynchronously; it is looked at before the NEXT build
+    if (!s->capturing) {
         SP_CUDA(s, cudaMemcpyAsync(s->h_counters + 40, s->counters + 40, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
         SP_CUDA(s, cudaEventRecord(s->ev_nbr, s->stream));
         s->nbr_max_pending = true;
-        s->nbr_version = s->x_version;
-        s->nbr_n = s->n;
     }
+    s->nbr_version = s->x_version;
+    s->nbr_n = s->n;
     return SP_OK;
+}
+static int sp_ensure_nbr_cache(sp_system* s, SweepCtx& c) {
+    bool need = false;
+    int rc = sp_nbr_prepare(s, c, &need);
+    if (rc || !need) return rc;
+    SP_LAUNCH(s, k_nbr_build<1>, sp_blocks(s->n, 128), 128, 0, s->g, c, s->nbr_cnt, s->nbr_ids, s->counters + 40);
+    return sp_nbr_built(s);
 }
 
 // Operators that declare `static constexpr bool LISTS_ONLY = true` (the example zoo beyond the BASELINE configs) are
@@ -1244,93 +978,50 @@ struct SpListsOnly : std::false_type {};
 template <class Op>
 struct SpListsOnly<Op, std::void_t<decltype(Op::LISTS_ONLY)>> : std::true_type {};
 
+template <class Op, class = void>
+struct SpFusedBuild : std::false_type {};
+template <class Op>
+struct SpFusedBuild<Op, std::void_t<decltype(Op::FUSED_BUILD)>> : std::true_type {};
+
 template <class Op>
 static int launch_sweep(sp_system* s, const typename Op::Params& P, int flags) {
     if (s->n == 0) return SP_OK;
     SweepCtx c;
     sp_sweep_ctx(s, c);
-    const double* X = s->fields[0].d;
-    int self_flag = (flags & SP_FLAG_SELF) ? 1 : 0;
-    if (const char* dbg = getenv("SP_DEBUG_SWEEP")) self_flag |= atoi(dbg) << 8;  // profiling switches only
+    const int self_flag = (flags & SP_FLAG_SELF) ? 1 : 0;
     if (flags & SP_FLAG_STRICT_ORDER) {
         SP_LAUNCH(s, (k_sweep<Op, true>), sp_blocks(s->n, 128), 128, 0, s->g, c, P, self_flag);
         return SP_OK;
     }
-    const bool tile = (flags & SP_FLAG_TILE_KERNEL) || getenv("SP_SWEEP_TILE");
-    static const int variant = getenv("SP_SWEEP_VARIANT") ? atoi(getenv("SP_SWEEP_VARIANT")) : 0;
-    const bool packed = (flags & SP_FLAG_PACKED_KERNEL) || variant == 1;
-    if constexpr (SpListsOnly<Op>::value) {
-        (void)X;
-        if (tile || packed || sp_sweep_mode() != 3)
+    if (flags & SP_FLAG_TILE_KERNEL) {
+        // the shared-memory tile kernel (TMA-staged candidate rows), kept as the one alternative to the list path
+        if constexpr (SpListsOnly<Op>::value) {
             return sp_fail(s, SP_ERR_INVALID,
-                           "this operator is built for the cached-list and strict-order kernels only "
-                           "(no SP_FLAG_TILE_KERNEL / SP_FLAG_PACKED_KERNEL / SP_SWEEP_* variants)");
-        int rc = sp_ensure_prefilter(s, c);
-        if (!rc) rc = sp_ensure_nbr_cache(s, c);
-        if (rc) return rc;
-        SP_LAUNCH(s, (k_sweep_list<Op, 1>), sp_blocks(s->n, 128), 128, 0, s->g, c, s->nbr_cnt, s->nbr_ids, P, self_flag);
-        return SP_OK;
-    } else {
-    if (!packed) {
-        int rc = sp_ensure_prefilter(s, c);
-        if (rc) return rc;
-    }
-    if (tile) {
-        // experimental shared-memory tile kernel (TMA-staged): see profiles/r1_sweep_exploration.md
-        if (s->g.dim == 2) return launch_tile<Op, TILE_CAPB2, 3, 1>(s, c, P, self_flag);
-        return launch_tile<Op, TILE_CAPB3, 9, TILE_RPB>(s, c, P, self_flag);
-    }
-    if (!packed) {
-        // default: one thread per target over the sorted SoA planes (L1-resident candidate rows), register hit masks
-        // 3 (default) = cached neighbour lists; 1 = register hit masks per sweep; 2 = two targets per thread
-        // (slower, see profiles/r1_sweep_exploration.md); 0 = plain candidate scan
-        const int mask_mode = sp_sweep_mode();
-        if (mask_mode == 3 || mask_mode == 4) {
-            int rc = sp_ensure_nbr_cache(s, c);
+                           "this operator is built for the cached-list and strict-order kernels only (no SP_FLAG_TILE_KERNEL)");
+        } else {
+            int rc = sp_ensure_prefilter(s, c);
             if (rc) return rc;
-            const unsigned nb = sp_blocks(s->n, 128);
-            if (mask_mode == 3) {
-                SP_LAUNCH(s, (k_sweep_list<Op, 1>), nb, 128, 0, s->g, c, s->nbr_cnt, s->nbr_ids, P, self_flag);
-            } else {
-                if (!s->pk || s->pk_cap != s->cap) {
-                    if (s->pk) SP_CUDA(s, sp_dfree(s, s->pk));
-                    s->pk = nullptr;
-                    SP_CUDA(s, sp_dmalloc(&s->pk, (size_t)2 * s->cap * sizeof(SpRec)));
-                    s->pk_cap = s->cap;
-                }
-                SpRec* pk0 = reinterpret_cast<SpRec*>(s->pk);
-                SpRec* pk1 = pk0 + s->cap;
-                PackPlanes<Op::NQ> pl;
-                for (int k = 0; k < Op::NQ; k++) pl.qp[k] = P.qp[k];
-                SP_LAUNCH(s, (k_pack<Op::NQ>), sp_blocks(s->n, 256), 256, 0, X, s->cap, pl, pk0, pk1, (int)s->n);
-                SP_LAUNCH(s, (k_sweep_list_pk<Op>), nb, 128, 0, s->g, c, s->nbr_cnt, s->nbr_ids, P, pk0, pk1, self_flag);
+            if (s->g.dim == 2) return launch_tile<Op, TILE_CAPB2, 3, 1>(s, c, P, self_flag);
+            return launch_tile<Op, TILE_CAPB3, 9, TILE_RPB>(s, c, P, self_flag);
+        }
+    }
+    // default: cached neighbour lists
+    bool need = false;
+    int rc = sp_nbr_prepare(s, c, &need);
+    if (rc) return rc;
+    const unsigned nb = sp_blocks(s->n, 128);
+    if (need) {
+        if constexpr (SpFusedBuild<Op>::value) {
+            if (sp_fused_build_enabled() && !(flags & SP_FLAG_UNFUSED_BUILD)) {
+                SP_LAUNCH(s, (k_nbr_build_sweep<Op>), nb, 128, 0, s->g, c, s->nbr_cnt, s->nbr_ids, s->counters + 40, P, self_flag);
+                return sp_nbr_built(s);
             }
-        } else if (mask_mode == 0)
-            SP_LAUNCH(s, (k_sweep<Op, false>), sp_blocks(s->n, 128), 128, 0, s->g, c, P, self_flag);
-        else if (mask_mode == 1)
-            SP_LAUNCH(s, (k_sweep_mask<Op>), sp_blocks(s->n, 128), 128, 0, s->g, c, P, self_flag);
-        else
-            SP_LAUNCH(s, (k_sweep_mask2<Op>), sp_blocks((s->n + 1) / 2, 128), 128, 0, s->g, c, P, self_flag);
-        return SP_OK;
+        }
+        SP_LAUNCH(s, k_nbr_build<1>, nb, 128, 0, s->g, c, s->nbr_cnt, s->nbr_ids, s->counters + 40);
+        if ((rc = sp_nbr_built(s))) return rc;
     }
-    // SP_FLAG_PACKED_KERNEL: packed-record two-phase kernel (experimental, see profiles/r1_sweep_exploration.md)
-    if (!s->pk || s->pk_cap != s->cap) {
-        if (s->pk) SP_CUDA(s, sp_dfree(s, s->pk));
-        s->pk = nullptr;
-        SP_CUDA(s, sp_dmalloc(&s->pk, (size_t)2 * s->cap * sizeof(SpRec)));
-        s->pk_cap = s->cap;
-    }
-    SpRec* pk0 = reinterpret_cast<SpRec*>(s->pk);
-    SpRec* pk1 = pk0 + s->cap;
-    PackPlanes<Op::NQ> pl;
-    for (int k = 0; k < Op::NQ; k++) pl.qp[k] = P.qp[k];
-    SP_LAUNCH(s, (k_pack<Op::NQ>), sp_blocks(s->n, 256), 256, 0, X, s->cap, pl, pk0, pk1, (int)s->n);
-    // the hit lists share the 228 KB L1/shared array with the L1 cache the candidate rows live in: keep them small
-    constexpr int TP = 128, LCAP = 20;
-    SP_LAUNCH(s, (k_sweep_pk<Op, TP, LCAP>), sp_blocks(s->n, TP), TP, (size_t)TP * LCAP * sizeof(int), s->g, c, P, pk0, pk1,
-              self_flag);
+    SP_LAUNCH(s, (k_sweep_list<Op, 1>), nb, 128, 0, s->g, c, s->nbr_cnt, s->nbr_ids, P, self_flag);
     return SP_OK;
-    }  // !SpListsOnly
 }
 
 template <template <class> class OpT, class MakeParams>

@@ -331,7 +331,6 @@ int32_t sp_destroy(sp_system* s) {
     sp_dfree(s, s->nbr_ids);
     sp_dfree(s, s->ell_val);
     sp_dfree(s, s->nbr_cnt);
-    sp_dfree(s, s->pk);
     if (s->h_scal) cudaFreeHost(s->h_scal);
     if (s->h_counters) cudaFreeHost(s->h_counters);
     if (s->ev0) cudaEventDestroy(s->ev0);

@@ -190,13 +190,13 @@ class ParticleSystem:
         return np.asarray([self._fid[nm] for nm in names], dtype=np.int32)
 
     def apply(self, op: Operator, self_: bool = False, strict_order: bool = False, tile_kernel: bool = False,
-              packed_kernel: bool = False):
+              unfused_build: bool = False):
         """``apply!(sys, action!; self=false)`` (src/core.jl:151-161) for a registered operator."""
         F = self._bind(op.fields)
         P = _farr(op.params)
         flags = ((K["SP_FLAG_SELF"] if self_ else 0) | (K["SP_FLAG_STRICT_ORDER"] if strict_order else 0)
                  | (K["SP_FLAG_TILE_KERNEL"] if tile_kernel else 0)
-                 | (K["SP_FLAG_PACKED_KERNEL"] if packed_kernel else 0))
+                 | (K["SP_FLAG_UNFUSED_BUILD"] if unfused_build else 0))
         abi.check(self._lib.sp_apply(self._h, op.op, abi.ptr_i32(F), len(F), abi.ptr_f64(P), len(P), flags), self._h)
 
     def sum_at_points(self, sum_op: int, fields: Sequence[str], params: Sequence[float], points) -> np.ndarray:

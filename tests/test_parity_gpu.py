@@ -251,12 +251,13 @@ def _rand_state(case, seed=1):
     return st
 
 
-@pytest.mark.parametrize("mode", ["default", "strict", "tile", "packed"])
+@pytest.mark.parametrize("mode", ["default", "strict", "tile", "unfused"])
 @pytest.mark.parametrize("maker", [configs.collapse_dry, configs.collapse3d])
 def test_wcsph_operators_single_call(maker, mode):
-    # default = packed-record kernel, strict = reference accumulation order, tile = shared-memory tile kernel
+    # default = cached neighbour lists (fused build + first replay), unfused = list build and replay as two kernels,
+    # strict = reference accumulation order, tile = shared-memory tile kernel
     strict = mode == "strict"
-    dev_kw = {"strict": {"strict_order": True}, "tile": {"tile_kernel": True}, "packed": {"packed_kernel": True}}.get(mode, {})
+    dev_kw = {"strict": {"strict_order": True}, "tile": {"tile_kernel": True}, "unfused": {"unfused_build": True}}.get(mode, {})
     case = maker()
     case.init = _rand_state(case)
     dev, ora = _pair(case)
@@ -321,7 +322,7 @@ def test_dense_cluster_list_overflow_all_kernels():
     ora.add_particles(x=x)
     ora.create_cell_list()
     ora.apply(ops.density_sum("wendland3", 1.0, h), self_=True)
-    for kw in ({}, {"strict_order": True}, {"tile_kernel": True}, {"packed_kernel": True}):
+    for kw in ({}, {"strict_order": True}, {"tile_kernel": True}, {"unfused_build": True}):
         dev = ParticleSystem({"rho": 1}, dom, h)
         dev.add_particles(x=x)
         dev.create_cell_list()

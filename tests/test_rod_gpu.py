@@ -66,7 +66,8 @@ def test_rod_time_loop_parity_and_energy():
     assert len(dev) == len(ora) == case.n
     # the stiff shear modulus (c_s = 200) amplifies rounding differences through inv(H) every step
     assert_fields_close(dev, ora, ["x", "v", "A", "B", "f"], rtol=1e-7, what="rod 100 steps",
-                        floors={"v": 1e-4, "f": 1e-3, "B": c["m"] * c["c_s"] ** 2 * 1e-4})
+                        floors={"v": 1e-4, "f": 1e-3, "B": c["m"] * c["c_s"] ** 2 * 1e-4},
+                        etol=1e-6)   # element-wise: the stiff shear modulus amplifies rounding through inv(H) over 100 steps
     Ed, Eo = configs.rod_energy(dev, c), configs.rod_energy(ora, c)
     assert abs(Ed - Eo) <= 1e-6 * abs(Eo) and Eo > 0
     ora.set("x", dev.get("x"))

@@ -174,6 +174,5 @@ def test_zoo_operators_reject_the_experimental_kernels_loudly():
     op = ops.density_sum_fluid("wendland2", c["m"], c["h"], out="rho")
     s.apply(op, self_=True)
     s.apply(op, self_=True, strict_order=True)
-    for kw in ({"tile_kernel": True}, {"packed_kernel": True}):
-        with pytest.raises(sp.SpError):
-            s.apply(op, self_=True, **kw)
+    with pytest.raises(sp.SpError):
+        s.apply(op, self_=True, tile_kernel=True)

@@ -17,6 +17,7 @@ ap.add_argument("--n", type=int, default=128)
 ap.add_argument("--dr", type=float, default=9.04e-4)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--warm", type=int, default=5)
+ap.add_argument("--unfused", action="store_true", help="list build and first replay as two kernels")
 args = ap.parse_args()
 case = configs.collapse3d(args.dr) if args.case == "dambreak" else configs.lattice_box(args.n, jitter=0.1)
 c = case.consts
@@ -38,7 +39,7 @@ def timed(name, fn):
 for _ in range(args.steps):
     timed("move", lambda: s.apply(o_mv))
     timed("cell_list", s.create_cell_list)
-    timed("balance_of_mass", lambda: s.apply(o_bom))
+    timed("balance_of_mass", lambda: s.apply(o_bom, unfused_build=args.unfused))
     timed("find_pressure", lambda: s.apply(o_fp))
     timed("internal_force", lambda: s.apply(o_if))
     timed("accelerate", lambda: s.apply(o_ac))
