@@ -30,6 +30,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+from bench_multi import workload_name  # noqa: E402
 
 METRIC = "particle-updates/s (WCSPH step, FP64)"
 UNIT = "particle-updates/s"
@@ -38,8 +39,8 @@ BYTES_PER_UPDATE_STEP = 736  # algorithmic HBM bytes per particle
 # algorithmic bytes per particle of each kernel class (own fields read + written, 8 B each)
 ALG_BYTES = {"internal_force": 120, "balance_of_mass": 72, "cell_list": 240, "move": 104, "find_pressure": 40,
              "accelerate": 80, "neighbour_lists": 24}
-KERNEL_OF = {"internal_force": "k_sweep_list<OpInternalForceCached>", "balance_of_mass": "k_sweep_list<OpBalanceOfMassAux>",
-             "neighbour_lists": "k_nbr_build"}
+KERNEL_OF = {"internal_force": "k_sweep_list<OpInternalForceCached>",
+             "balance_of_mass": "k_nbr_build_sweep<OpBalanceOfMassAux> (neighbour-list build fused with the mass sweep)"}
 
 
 def _peaks():
@@ -161,8 +162,7 @@ def run_single(args):
     o_if = ops.internal_force("wendland3", c["m"], c["h"], c["mu"], c["rho0"])
     o_mv = ops.move(c["dt"])
     o_ac = ops.accelerate(0.5 * c["dt"], c["g"])
-    acc = {k: 0.0 for k in ("move", "cell_list", "neighbour_lists", "balance_of_mass", "find_pressure", "internal_force",
-                            "accelerate")}
+    acc = {k: 0.0 for k in ("move", "cell_list", "balance_of_mass", "find_pressure", "internal_force", "accelerate")}
 
     def timed(name, fn):
         fn()
@@ -171,7 +171,6 @@ def run_single(args):
     for _ in range(args.steps):
         timed("move", lambda: sysd.apply(o_mv))
         timed("cell_list", sysd.create_cell_list)
-        timed("neighbour_lists", sysd.build_neighbour_lists)   # otherwise done lazily inside the first sweep
         timed("balance_of_mass", lambda: sysd.apply(o_bom))
         timed("find_pressure", lambda: sysd.apply(o_fp))
         timed("internal_force", lambda: sysd.apply(o_if))
@@ -179,7 +178,7 @@ def run_single(args):
         timed("accelerate", lambda: sysd.apply(o_ac))
     clocks = sampler.stop()
     breakdown = {k: v / args.steps for k, v in acc.items()}
-    dominant = max(("internal_force", "balance_of_mass", "neighbour_lists"), key=lambda k: breakdown[k])
+    dominant = max(("internal_force", "balance_of_mass"), key=lambda k: breakdown[k])
     dom_ms = breakdown[dominant]
     hbm_peak, peak_kind = _peaks()
     achieved = ALG_BYTES[dominant] * n / (dom_ms * 1e-3) / 1e9
@@ -222,6 +221,16 @@ def run_single(args):
     # call with a per-step device->host diagnostic (total energy), download of the result fields.
     e2e = run_e2e(case, args, dev_index)
 
+    # ---- BASELINE configs[4] on this one GPU: the periodic box, 292^3 particles, as one slab exchanging ghosts with
+    # itself — the N = 1 point of its weak-scaling curve (the N > 1 lines carry the same key)
+    box = None
+    if not args.no_box:
+        try:
+            from bench_multi import box_line
+            box = box_line(args, UNIT, ClockSampler)
+        except Exception as e:  # noqa: BLE001 - the extra line must not take the headline down
+            box = {"failed": str(e)[:300]}
+
     # ---- CPU baseline on a bounded sample (rank 0 only)
     cpu = cpu_baseline(case, sample_budget_s=args.cpu_budget) if not args.no_cpu else None
 
@@ -229,13 +238,13 @@ def run_single(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "examples/collapse3d.jl dam break scaled to 10 M particles (dr=%g)" % args.dr,
+        "config": {"workload": workload_name("dambreak", 1, args.dr, args.per_gpu),
                    "particles": n, "particles_after": n_after, "h": case.h, "cells": int(np.prod(_key_lim(case))),
                    "l2": "state 1.04 GB >> 126 MB L2, no flush needed", "driver": "sp_run_program (fused step loop)",
                    "setup_s": round(gen_s, 1),
                    "device_setup_s": (round(device_setup_s, 4) if isinstance(device_setup_s, float) else device_setup_s)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
-        "breakdown_ms": breakdown, "cpu_baseline": cpu,
+        "breakdown_ms": breakdown, "cpu_baseline": cpu, "box": box,
     }
     print(json.dumps(line))
 
@@ -329,73 +338,106 @@ def run_e2e(case, args, dev_index):
     phases.update(best_phases)
     h2d = sum(t.numel() * 8 for t in host_in.values())
     d2h = sum(t.numel() * 8 for t in host_out.values())
-    return {"value": n * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
+    return {"value": n * args.steps / dt, "unit": UNIT, "steps": args.steps, "h2d_bytes_per_step": h2d / args.steps,
             "d2h_bytes_per_step": d2h / args.steps + 24, "seconds": dt, "phases": {k: round(v, 4) for k, v in phases.items() if k.endswith("_s")},
-            "what": "one job = sp_create + upload of x,v,rho,type from pinned host memory, K steps driven call by "
-                    "call through the C ABI with a per-step energy read-back, download of x,v,rho,P, sp_destroy; "
-                    "best of 3 jobs",
+            "what": f"one job = sp_create + upload of x,v,rho,type from pinned host memory, K = {args.steps} steps driven "
+                    "call by call through the C ABI with a per-step energy read-back, download of x,v,rho,P, sp_destroy; "
+                    "best of 3 jobs; the bulk upload/download is amortised over K (particles stay resident in HBM), so "
+                    "this value moves with K",
             "energy": energy,
             "energy_drift": ((energy - phases["energy_first"]) / abs(phases["energy_first"])
                              if phases.get("energy_first") else None)}
 
 
-def cpu_baseline(case, sample_budget_s=20.0, steps=None, warmup=1):
-    """The OpenMP restatement of the reference's algorithm (oracle/) on the host cores, same workload."""
+def host_cores() -> int:
+    """All the cores this process may run on (the launcher's OMP_NUM_THREADS=1 under torch.distributed.run is ignored)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def time_oracle(case, warmup, steps):
+    """ONE protocol for both CPU legs: the OpenMP restatement of the reference's algorithm (oracle/) on all host cores,
+    `warmup` untimed steps (first touch of the pages, thread pool start), then `steps` timed steps of the step program."""
     from oracle import oracle
     from oracle.oracle import OracleSystem
 
-    threads = oracle.max_threads()
+    threads = host_cores()
+    oracle.load().so_set_threads(threads)
     s = case.make(OracleSystem)
     n = len(s)
-    t1 = s.run_program(case.program, case.program_fields, case.program_params, warmup)
-    per = t1 / max(warmup, 1)
-    if steps is None:
-        steps = int(max(1, min(5, sample_budget_s / max(per, 1e-3))))
+    if warmup:
+        s.run_program(case.program, case.program_fields, case.program_params, warmup)
     t = s.run_program(case.program, case.program_fields, case.program_params, steps)
     s.close()
-    return {"value": n * steps / t, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{steps} step(s) of the full {n}-particle workload after {warmup} warm-up step(s), "
+    return n, t, threads
+
+
+def cpu_baseline(case, sample_budget_s=20.0):
+    """The reference's algorithm on the host cores, same workload, bounded sample: 2 warm-up steps + as many timed steps
+    as fit the budget (at most 10)."""
+    from oracle import oracle
+    from oracle.oracle import OracleSystem
+
+    threads = host_cores()
+    oracle.load().so_set_threads(threads)
+    s = case.make(OracleSystem)
+    n = len(s)
+    t_warm = s.run_program(case.program, case.program_fields, case.program_params, 2)
+    per = t_warm / 2
+    steps = int(max(2, min(10, sample_budget_s / max(per, 1e-3))))
+    t = s.run_program(case.program, case.program_fields, case.program_params, steps)
+    s.close()
+    return {"value": n * steps / t, "unit": UNIT, "cores": threads, "cpu": cpu_model(), "kind": "port",
+            "sample": f"{steps} step(s) of the full {n}-particle workload after 2 warm-up steps, "
                       f"OpenMP oracle (C++ restatement of the reference; Julia is not installed)",
             "ms_per_step": 1e3 * t / steps}
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU algorithm on all host cores (OpenMP port, see cpu_baseline)."""
+    """--impl reference: the reference's own CPU algorithm on ALL host cores (OpenMP port of it; the Julia original cannot
+    run here).  N > 1: rank 0 alone runs; the weak-scaled workload is N copies of one GPU's share, and the CPU's rate in
+    particle-updates/s does not depend on how many copies it works through (linear-time algorithm), so one share is
+    timed — the bounded sample — and its rate is the whole-job rate of the CPU."""
     rank, local_rank, world = dist_env()
     if rank != 0:
         return
     from smoothedparticles_jl_b200 import configs
-    from oracle import oracle
-    from oracle.oracle import OracleSystem
 
-    case = configs.collapse3d(args.dr) if args.gpus == 1 else _slab_case_for_reference(args)
-    s = case.make(OracleSystem)
-    n = len(s)
-    s.run_program(case.program, case.program_fields, case.program_params, args.warmup)
-    t = s.run_program(case.program, case.program_fields, case.program_params, args.steps)
+    if args.gpus > 1 and args.workload == "box":
+        case = configs.lattice_box(128, jitter=0.1)
+        share = "a 128^3 block of the same lattice"
+    else:
+        case = configs.collapse3d(args.dr)
+        share = "one GPU's share (the 10 M-particle dam break)" if args.gpus > 1 else "the full workload"
+    n, t, threads = time_oracle(case, args.warmup, args.steps)
     value = n * args.steps / t
-    threads = oracle.max_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": case.name + " (%d particles)" % n, "particles": n,
-                   "note": "each step is one full time step of the workload on the host CPU"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} steps of the full {n}-particle workload, OpenMP oracle port "
-                                   "(the Julia reference cannot run here: no Julia runtime)"},
+        "config": {"workload": workload_name(args.workload if args.gpus > 1 else "dambreak", args.gpus, args.dr, args.per_gpu),
+                   "particles": n * (args.gpus if args.gpus > 1 and args.workload != "box" else 1),
+                   "particles_timed": n,
+                   "note": "each step is one full time step of the timed particles on the host CPU"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "cpu": cpu_model(), "kind": "port",
+                         "sample": f"{args.steps} steps of {share} ({n} particles) after {args.warmup} warm-up steps, "
+                                   f"OpenMP oracle port on {threads} threads (the Julia reference cannot run here: no "
+                                   f"Julia runtime); particle-updates/s of the CPU is independent of the number of copies"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
-
-
-def _slab_case_for_reference(args):
-    from smoothedparticles_jl_b200 import configs
-    # bounded sample of the multi-GPU workload: the CPU runs ONE GPU's share (the N = 1 dam break) — the weak-
-    # scaled workload is N copies of it along z; for the periodic box a 2.1 M-particle block of the same lattice
-    if args.workload == "box":
-        return configs.lattice_box(128, jitter=0.1)
-    return configs.collapse3d(args.dr)
 
 
 # ------------------------------------------------------------------------------------------------ N > 1
@@ -417,6 +459,7 @@ def main():
                     help="N > 1: 'dambreak' = collapse3d with the box depth x N (one N=1 workload per GPU); "
                          "'box' = periodic lattice box, --per-gpu^3 particles per GPU (BASELINE configs[4])")
     ap.add_argument("--per-gpu", type=int, default=292, help="lattice side per GPU for --workload box (292^3 = 24.9 M)")
+    ap.add_argument("--no-box", action="store_true", help="skip the extra `box` line (BASELINE configs[4] at this N)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours" and not os.environ.get("SP_BENCH_ALLOW_SHORT"):
         args.warmup = 3

@@ -28,21 +28,40 @@ def make_rank_particles(per_gpu: int, rank: int, world: int, dr: float = 1.0, ji
     return x[perm], v[perm]
 
 
-def run_multi(args, METRIC, UNIT, ClockSampler, peaks):
-    import torch
+def workload_name(workload: str, world: int, dr: float, per: int) -> str:
+    """The `config.workload` string: the same for our arm and for --impl reference at the same N."""
+    if workload == "box":
+        return (f"periodic 3-D lattice box, {per}^3 particles per GPU x {world} GPU(s), slab-decomposed along z "
+                f"(h = 2 dr, jitter 0.1 dr, collapse3d step)")
+    if world == 1:
+        return "examples/collapse3d.jl dam break scaled to 10 M particles (dr=%g)" % dr
+    return (f"examples/collapse3d.jl dam break, dr={dr:g}, box depth x{world} along z (one 10 M-particle copy of "
+            f"the N=1 workload per GPU), slab-decomposed along z")
+
+
+def init_control_plane():
+    """gloo process group for the control plane (NCCL id broadcast, max over ranks); world 1 without torchrun works too."""
     import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29541")
+    if not dist.is_initialized():
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    return dist, rank, world
+
+
+def run_slab_workload(args, workload, UNIT, ClockSampler, e2e=True, breakdown=True):
+    """One weak-scaling workload on `world` slabs: returns a dict (every rank), rank 0's is complete."""
+    import torch
 
     import smoothedparticles_jl_b200 as sp
     from smoothedparticles_jl_b200 import geometry as geo, operators as ops, slab
 
     K = sp.K
-    rank = int(os.environ.get("RANK", 0))
+    dist, rank, world = init_control_plane()
     local = int(os.environ.get("LOCAL_RANK", rank))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    os.environ.setdefault("MASTER_PORT", "29541")
     torch.cuda.set_device(local)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
 
     def fresh_id():
         # one NCCL unique id per communicator: rank 0 draws it, gloo carries the 128 bytes to the others
@@ -54,7 +73,7 @@ def run_multi(args, METRIC, UNIT, ClockSampler, peaks):
     rho0, c, mu, nu = 1000.0, 50.0, 8.4e-4, 1.0e-4
     fields = {"v": 3, "Dv": 3, "P": 1, "rho": 1, "Drho": 1, "type": 1}
     t0 = time.time()
-    if args.workload == "box":
+    if workload == "box":
         # BASELINE.json configs[4]: periodic lattice box, per^3 particles per GPU
         dr = 1.0
         h = 2.0 * dr
@@ -64,8 +83,6 @@ def run_multi(args, METRIC, UNIT, ClockSampler, peaks):
         periodic = True
         x, v = make_rank_particles(per, rank, world, dr)
         typ = np.zeros(len(x))
-        wname = (f"periodic 3-D lattice box, {per}^3 particles per GPU, slab-decomposed along z (h = 2 dr, jitter "
-                 f"0.1 dr, collapse3d step)")
     else:
         # examples/collapse3d.jl at dr = args.dr (10 M particles per unit depth), box depth x N along z — the
         # direction the dam break is invariant in — so every GPU holds one copy of the N = 1 workload
@@ -73,11 +90,8 @@ def run_multi(args, METRIC, UNIT, ClockSampler, peaks):
         dr = args.dr
         h = 2.0 * dr
         g = (0.0, 0.0, -9.8)
-        probe = configs.collapse3d(5e-2, depth_scale=world)          # cheap: only for the global box
-        dom_probe = probe.domain
         wall = 2.5 * dr
         dom = geo.Box(-wall, -wall, -wall, 0.584 + wall, 0.35 + wall, 0.15 * world + wall)
-        del probe, dom_probe
         gphase = int(np.floor(dom.lo[2] / h))
         glim = int(np.floor(dom.hi[2] / h)) - gphase + 1
         c0, c1 = slab.partition_layers(glim, world)[rank]
@@ -92,8 +106,7 @@ def run_multi(args, METRIC, UNIT, ClockSampler, peaks):
         periodic = False
         assert np.allclose(case.domain.lo, dom.lo) and np.allclose(case.domain.hi, dom.hi), (case.domain, dom)
         dom = case.domain
-        wname = (f"examples/collapse3d.jl dam break, dr={dr:g}, box depth x{world} along z (one 10 M-particle copy of "
-                 f"the N=1 workload per GPU), slab-decomposed along z")
+    wname = workload_name(workload, world, args.dr, per)
     m = rho0 * dr ** 3
     dt = 0.1 * h / c
     n_local = len(x)
@@ -102,14 +115,13 @@ def run_multi(args, METRIC, UNIT, ClockSampler, peaks):
              force=ops.internal_force("wendland3", m, h, mu, rho0), move=ops.move(dt), acc=ops.accelerate(0.5 * dt, g))
 
     def make_system():
-        s = slab.SlabSystem(fields, dom, h, rank, world, fresh_id(), periodic=periodic, device=local)
-        return s
+        return slab.SlabSystem(fields, dom, h, rank, world, fresh_id(), periodic=periodic, device=local)
 
     sysd = make_system()
     assert np.all(sysd.owns(x)), "generator and slab partition disagree"
     sysd.add_particles(x=x, v=v, rho=np.full(n_local, rho0), type=typ)
     # the step loop is issued from inside the library (sp_run_program on a slab system: slab rebuild with migration
-    # and ghost halos, sweeps, halo refresh of rho and P) — the same driver as the N = 1 `value`
+    # and ghost halos, sweeps) — the same driver as the N = 1 `value`
     prog = K["SP_PROGRAM_WCSPH_3D"]
     prog_fields = ("x", "v", "Dv", "rho", "Drho", "P", "type")
     prog_params = (float(K["SP_KERNEL_WENDLAND3"]), m, h, 2 * nu, dt, c * c, rho0, mu, *g)
@@ -134,28 +146,34 @@ def run_multi(args, METRIC, UNIT, ClockSampler, peaks):
     n_tot = int(sysd.allreduce([sysd.n_owned])[0])
     n_ghost = len(sysd) - sysd.n_owned
     value = n_tot * args.steps / (ms_max * 1e-3)
+    out = {"workload": wname, "value": value, "ms_per_step": ms_max / args.steps, "particles": n_tot,
+           "particles_per_gpu": n_local, "ghosts_per_gpu": int(n_ghost), "setup_s": round(gen_s, 1), "clocks": clocks,
+           "gpu_launches": int(gpu_launches), "n_slots": n_local + int(n_ghost)}
 
-    # per-kernel breakdown on this rank (same steps, per-call timing)
-    acc = {k: 0.0 for k in ("move", "cell_list+halo", "balance_of_mass", "find_pressure", "halo_refresh", "internal_force",
-                            "accelerate")}
+    if breakdown:
+        # per-kernel breakdown on this rank (same steps, per-call timing)
+        acc = {k: 0.0 for k in ("move", "cell_list+halo", "balance_of_mass", "find_pressure", "halo_refresh",
+                                "internal_force", "accelerate")}
 
-    def timed(name, fn):
-        fn()
-        acc[name] += sysd.last_call_ms()
+        def timed(name, fn):
+            fn()
+            acc[name] += sysd.last_call_ms()
 
-    for _ in range(args.steps):
-        timed("move", lambda: sysd.apply(o["move"]))
-        timed("cell_list+halo", sysd.create_cell_list)
-        timed("balance_of_mass", lambda: sysd.apply(o["bom"]))
-        timed("find_pressure", lambda: sysd.apply(o["fp"]))
-        timed("halo_refresh", lambda: sysd.halo_refresh("rho", "P"))
-        timed("internal_force", lambda: sysd.apply(o["force"]))
-        timed("accelerate", lambda: sysd.apply(o["acc"]))
-        timed("accelerate", lambda: sysd.apply(o["acc"]))
-    breakdown = {k: vv / args.steps for k, vv in acc.items()}
-    E = sysd.reduce(K["SP_RED_ENERGY_WCSPH"], ("x", "v", "rho"), (m, c, rho0, *g))[0]
+        for _ in range(args.steps):
+            timed("move", lambda: sysd.apply(o["move"]))
+            timed("cell_list+halo", sysd.create_cell_list)
+            timed("balance_of_mass", lambda: sysd.apply(o["bom"]))
+            timed("find_pressure", lambda: sysd.apply(o["fp"]))
+            timed("halo_refresh", lambda: sysd.halo_refresh("rho", "P"))
+            timed("internal_force", lambda: sysd.apply(o["force"]))
+            timed("accelerate", lambda: sysd.apply(o["acc"]))
+            timed("accelerate", lambda: sysd.apply(o["acc"]))
+        out["breakdown_ms"] = {k: vv / args.steps for k, vv in acc.items()}
+    out["energy"] = sysd.reduce(K["SP_RED_ENERGY_WCSPH"], ("x", "v", "rho"), (m, c, rho0, *g))[0]
     sysd.close()
     del sysd
+    if not e2e:
+        return out
 
     # end to end: upload from pinned host memory, K steps with a per-step all-reduced energy read-back, download
     host_x = torch.from_numpy(x).pin_memory()
@@ -207,32 +225,53 @@ def run_multi(args, METRIC, UNIT, ClockSampler, peaks):
     d2h = nl * 9 * 8
     tot = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64)
     dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    e2e = {"value": n_tot * args.steps / float(tj[0]), "unit": UNIT, "h2d_bytes_per_step": float(tot[0]) / args.steps,
-           "d2h_bytes_per_step": float(tot[1]) / args.steps + 24 * world, "seconds": float(tj[0]),
-           "what": "every rank: upload of x,v,rho,type from pinned host memory into a fresh slab system, K slab steps "
-                   "driven call by call with a per-step all-reduced energy read-back, download of x,v,rho,P,_ghost "
-                   "(NCCL communicator creation excluded)"}
+    out["e2e"] = {"value": n_tot * args.steps / float(tj[0]), "unit": UNIT, "steps": args.steps,
+                  "h2d_bytes_per_step": float(tot[0]) / args.steps,
+                  "d2h_bytes_per_step": float(tot[1]) / args.steps + 24 * world, "seconds": float(tj[0]),
+                  "what": f"every rank: upload of x,v,rho,type from pinned host memory into a fresh slab system, "
+                          f"K = {args.steps} slab steps driven call by call with a per-step all-reduced energy read-back, "
+                          f"download of x,v,rho,P,_ghost (NCCL communicator creation excluded); the bulk copies are "
+                          f"amortised over K"}
+    return out
 
+
+def box_line(args, UNIT, ClockSampler):
+    """BASELINE configs[4] next to the headline workload: the periodic box at per_gpu^3 particles per GPU on the same
+    N GPUs (N = 1: one slab exchanging ghosts with itself), so that the per-N lines give its weak-scaling curve."""
+    r = run_slab_workload(args, "box", UNIT, ClockSampler, e2e=False, breakdown=False)
+    return {k: r[k] for k in ("workload", "value", "ms_per_step", "particles", "particles_per_gpu", "ghosts_per_gpu",
+                              "gpu_launches")} | {"unit": UNIT, "steps": args.steps, "warmup": args.warmup}
+
+
+def run_multi(args, METRIC, UNIT, ClockSampler, peaks):
+    dist, rank, world = init_control_plane()
+    r = run_slab_workload(args, args.workload, UNIT, ClockSampler)
+    other = None
+    if args.workload != "box" and not args.no_box:
+        other = box_line(args, UNIT, ClockSampler)
     if rank == 0:
         hbm_peak, peak_kind = peaks()
+        breakdown = r["breakdown_ms"]
         dominant = max(("internal_force", "balance_of_mass"), key=lambda k: breakdown[k])
         alg = {"internal_force": 120, "balance_of_mass": 72}[dominant]
-        achieved = alg * (n_local + n_ghost) / (breakdown[dominant] * 1e-3) / 1e9
+        kern = {"internal_force": "k_sweep_list<OpInternalForceCached>",
+                "balance_of_mass": "k_nbr_build_sweep<OpBalanceOfMassAux> (list build fused with the mass sweep)"}[dominant]
+        achieved = alg * r["n_slots"] / (breakdown[dominant] * 1e-3) / 1e9
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wname, "particles": n_tot,
-                       "particles_per_gpu": n_local, "ghosts_per_gpu": int(n_ghost),
-                       "l2": "state >= 1 GB per GPU >> 126 MB L2, no flush needed", "setup_s": round(gen_s, 1),
-                       "parallelism": f"slab{world}", "energy": E},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches),
-            "roofline": {"bound": "hbm", "kernel": f"k_sweep_list<{dominant}> (+ k_nbr_build inside the first sweep of a step)", "achieved": achieved, "peak": hbm_peak,
+            "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": r["workload"], "particles": r["particles"],
+                       "particles_per_gpu": r["particles_per_gpu"], "ghosts_per_gpu": r["ghosts_per_gpu"],
+                       "l2": "state >= 1 GB per GPU >> 126 MB L2, no flush needed", "setup_s": r["setup_s"],
+                       "parallelism": f"slab{world}", "energy": r["energy"]},
+            "clocks": r["clocks"], "e2e": r["e2e"], "gpu_launches": r["gpu_launches"],
+            "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_kind": peak_kind,
                          "alg_bytes_per_particle": alg, "launch_ms": breakdown[dominant],
-                         "step_hbm_frac": 736 * value / world / (hbm_peak * 1e9),
+                         "step_hbm_frac": 736 * r["value"] / world / (hbm_peak * 1e9),
                          "note": "pair sweeps are bound by the L1 data pipe (FP64 gathers), not by HBM"},
-            "breakdown_ms": breakdown, "cpu_baseline": None,
+            "breakdown_ms": breakdown, "cpu_baseline": None, "box": other,
         }
         print(json.dumps(line), flush=True)
     dist.barrier()

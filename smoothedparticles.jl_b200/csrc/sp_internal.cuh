@@ -20,6 +20,13 @@
 #include "../../include/sp_b200.h"
 
 #define SP_MAX_FIELDS 64
+// device counters (ints) of sp_system::counters / the pinned mirror h_counters
+#define SP_CNT_TRASH 0    /* particles in the trash cell of the build in flight (dead tail + newly culled) */
+#define SP_CNT_ALIVE 1    /* alive slots: [0, alive) */
+#define SP_CNT_REMOVED 2  /* particles culled since the last sp_settle (added to n_removed there) */
+#define SP_CNT_CULLED 3   /* particles culled by the last build */
+#define SP_CNT_CGFLAG 32
+#define SP_CNT_NBRMAX 40
 #define SP_FLAG_INTERNAL_PR_READY (1 << 30) /* library-internal: _pr = P/rho^2 is already up to date */
 
 struct SpField {
@@ -60,7 +67,15 @@ struct sp_system {
     int n_key_diff = 0;
     long long key_diff[27]{};
 
-    long long n = 0;    // current particle count (owned + ghosts on a slab system)
+    // Particle count.  `n` is what the host launches with: slots [0, n) exist.  The number of ALIVE slots lives on the
+    // device (counters[SP_CNT_ALIVE]): a cell-list build sorts the particles it culled (outside the domain, NaN) behind
+    // the alive ones and lowers that count without telling the host, so the step loop has no device->host read-back
+    // (and can be captured in a CUDA graph).  Slots [alive, n) are the dead tail: every kernel leaves at `slot >= alive`.
+    // `n_exact` says the host knows alive == n; sp_settle() makes it so (one stream synchronisation) and is called by the
+    // entry points that hand particle counts or particle data to the host.
+    long long n = 0;
+    bool n_exact = true;
+    bool count_pending = false;  // a build's alive count is on its way to h_counters (adopted lazily, without waiting)
     long long cap = 0;  // plane stride
     std::vector<SpField> fields;
     int *ref = nullptr, *ref_alt = nullptr;
@@ -179,6 +194,11 @@ static inline void sp_zeroed(sp_system* s, int fid) {
 }
 void sp_slab_free(sp_system* s);  // sp_slab.cu
 int sp_build_cells(sp_system* s);  // sp_cells.cu
+// make the host's particle count exact (waits for the stream if a build's count has not been fetched yet)
+int sp_settle(sp_system* s);
+// the host changed the particle count itself (resize, slab arrivals): publish it to the device counter
+int sp_publish_count(sp_system* s);
+static inline const int* sp_alive(const sp_system* s) { return s->counters + SP_CNT_ALIVE; }
 void sp_slab_host_touched(sp_system* s);  // positions / particle set changed by the host: full selection next time
 const double* sp_slab_ghost_mask(sp_system* s);  // nullptr unless a slab system: 0 = owned, 1/2 = ghost
 

@@ -613,10 +613,16 @@ __global__ void __launch_bounds__(128, 6) k_sweep_list(SpGrid g, SweepCtx c, con
         // each warp keeps U*(3+NQ) gathers in flight — the kernel is bound by the latency / L1 cost of these loads
         constexpr int U = Op::NQ <= 1 ? 4 : 2;
         int k = 0;
+        // the ids of the next trip are requested one trip ahead (two dependent round trips per trip otherwise)
+        int jn[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) jn[u] = (u < n_it) ? __ldcs(col + (u << 5)) : i;
         for (; k + U <= n_it; k += U) {
             int jj[U];
 #pragma unroll
-            for (int u = 0; u < U; u++) jj[u] = __ldcs(col + ((k + u) << 5));
+            for (int u = 0; u < U; u++) jj[u] = jn[u];
+#pragma unroll
+            for (int u = 0; u < U; u++) jn[u] = (k + U + u < n_it) ? __ldcs(col + ((k + U + u) << 5)) : i;
             double qx[U], qy[U], qz[U];
             QRegs<Op::NQ> q[U];
 #pragma unroll
@@ -633,8 +639,10 @@ __global__ void __launch_bounds__(128, 6) k_sweep_list(SpGrid g, SweepCtx c, con
                 Op::pair(P, p, q[u], dx, dy, dz, sp_sqrt_fast(sp_d2(dx, dy, dz)), acc);
             }
         }
-        for (; k < n_it; k++) {
-            const int j = __ldcs(col + (k << 5));
+#pragma unroll
+        for (int u = 0; u < U - 1; u++) {  // the tail (fewer than U entries) came with the last prefetch
+            if (k + u >= n_it) break;
+            const int j = jn[u];
             const double dx = __dsub_rn(xi, c.x[j]), dy = __dsub_rn(yi, c.y[j]), dz = __dsub_rn(zi, c.z[j]);
             QGlobal<Op::NQ> q{P.qp, j};
             Op::pair(P, p, q, dx, dy, dz, sp_sqrt_fast(sp_d2(dx, dy, dz)), acc);
@@ -671,9 +679,9 @@ __global__ void __launch_bounds__(128, 6) k_sweep_list(SpGrid g, SweepCtx c, con
 // this saves the second classification (2 of 7.25 instructions per candidate), the three-chunk reject queue, one
 // 1.2 GB read of the lists from HBM and a launch; and the issue-bound scan of some warps overlaps with the
 // L1-bound gathers of others on the same SM.
-template <class Op>
-__global__ void __launch_bounds__(128, 5) k_nbr_build_sweep(SpGrid g, SweepCtx c, int* cnt, int* ids, int* max_cnt,
-                                                            typename Op::Params P, int self_flag) {
+template <class Op, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_nbr_build_sweep(SpGrid g, SweepCtx c, int* cnt, int* ids, int* max_cnt,
+                                                               typename Op::Params P, int self_flag) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.n) return;
     const int capk = c.capk;
@@ -757,10 +765,17 @@ __global__ void __launch_bounds__(128, 5) k_nbr_build_sweep(SpGrid g, SweepCtx c
     if (n_maybe <= capk) {
         constexpr int U = Op::NQ <= 1 ? 4 : 2;
         int k = 0;
+        // the ids of the NEXT trip are requested before this trip's gathers are consumed: they come back from L2 (phase A
+        // wrote them through), and two dependent round trips per trip is what this loop would otherwise wait on
+        int jn[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) jn[u] = (u < n_maybe) ? col[u << 5] : i;
         for (; k + U <= n_maybe; k += U) {
             int jj[U];
 #pragma unroll
-            for (int u = 0; u < U; u++) jj[u] = col[(k + u) << 5];
+            for (int u = 0; u < U; u++) jj[u] = jn[u];
+#pragma unroll
+            for (int u = 0; u < U; u++) jn[u] = (k + U + u < n_maybe) ? col[(k + U + u) << 5] : i;
             double qx[U], qy[U], qz[U];
             QRegs<Op::NQ> q[U];
 #pragma unroll
@@ -776,17 +791,21 @@ __global__ void __launch_bounds__(128, 5) k_nbr_build_sweep(SpGrid g, SweepCtx c
                 const double dx = __dsub_rn(xi, qx[u]), dy = __dsub_rn(yi, qy[u]), dz = __dsub_rn(zi, qz[u]);
                 const double d2 = sp_d2(dx, dy, dz);
                 if (d2 > T2) continue;  // (r > h) && continue, core.jl:105
+                // compaction: position n_out <= k + u, and everything up to k + 2U - 1 is already in registers
                 if (n_out != k + u) col[n_out << 5] = jj[u];
                 n_out++;
                 if (act) Op::pair(P, p, q[u], dx, dy, dz, sp_sqrt_fast(d2), acc);
             }
         }
-        for (; k < n_maybe; k++) {
-            const int j = col[k << 5];
+        // the tail entries (fewer than U) were prefetched with the last full trip
+#pragma unroll
+        for (int u = 0; u < U - 1; u++) {
+            if (k + u >= n_maybe) break;
+            const int j = jn[u];
             const double dx = __dsub_rn(xi, c.x[j]), dy = __dsub_rn(yi, c.y[j]), dz = __dsub_rn(zi, c.z[j]);
             const double d2 = sp_d2(dx, dy, dz);
             if (d2 > T2) continue;
-            if (n_out != k) col[n_out << 5] = j;
+            if (n_out != k + u) col[n_out << 5] = j;
             n_out++;
             if (act) {
                 QGlobal<Op::NQ> q{P.qp, j};
@@ -1013,7 +1032,7 @@ static int launch_sweep(sp_system* s, const typename Op::Params& P, int flags) {
     if (need) {
         if constexpr (SpFusedBuild<Op>::value) {
             if (sp_fused_build_enabled() && !(flags & SP_FLAG_UNFUSED_BUILD)) {
-                SP_LAUNCH(s, (k_nbr_build_sweep<Op>), nb, 128, 0, s->g, c, s->nbr_cnt, s->nbr_ids, s->counters + 40, P, self_flag);
+                SP_LAUNCH(s, (k_nbr_build_sweep<Op, 6>), nb, 128, 0, s->g, c, s->nbr_cnt, s->nbr_ids, s->counters + 40, P, self_flag);
                 return sp_nbr_built(s);
             }
         }
