@@ -56,7 +56,9 @@ enum {
     SP_ERR_NO_DEVICE = 3, /* no usable CUDA device: there is NO CPU fallback */
     SP_ERR_STATE = 4,     /* call out of order (e.g. sweep before create_cell_list) */
     SP_ERR_NCCL = 5,
-    SP_ERR_NOT_CONVERGED = 6
+    SP_ERR_NOT_CONVERGED = 6 /* sp_poisson_cg reached maxiter: a SOFT status — P_out holds the last iterate, iters and resid are
+                                filled; IterativeSolvers.cg returns the same iterate without an error, so the host bindings hand
+                                it back to the caller instead of raising */
 };
 
 /* ---- SPH kernel families (src/kernels.jl) -------------------------------- */

@@ -114,6 +114,24 @@ __global__ void k_gen_fill(double* f, long long cap, int ncomp, double value, lo
     for (int c = 0; c < ncomp; c++) f[(size_t)c * cap + s] = value;
 }
 
+// scratch arrays of one call: released on every exit path, the error returns of SP_CUDA / SP_LAUNCH included
+namespace {
+struct ScratchGuard {
+    sp_system* s;
+    void* p[4] = {nullptr, nullptr, nullptr, nullptr};
+    explicit ScratchGuard(sp_system* sys) : s(sys) {}
+    ~ScratchGuard() {
+        bool any = false;
+        for (void* q : p) any = any || q;
+        if (!any) return;
+        if (s->stream) cudaStreamSynchronize(s->stream);
+        for (void* q : p)
+            if (q) sp_dfree_impl(q);
+        cudaGetLastError();
+    }
+};
+}  // namespace
+
 extern "C" int32_t sp_generate_particles(sp_system* s, int32_t grid, double dr, const sp_shape_node* nodes, int32_t n_nodes,
                                          const double* offsets, int32_t n_off, const int64_t irange[6],
                                          const int32_t* fill_fields, const double* fill_values, int32_t n_fill,
@@ -145,14 +163,18 @@ extern "C" int32_t sp_generate_particles(sp_system* s, int32_t grid, double dr, 
     if (i1 < i0 || j1 < j0 || k1 < k0) return SP_OK;
     const long long nj = j1 - j0 + 1, nk = k1 - k0 + 1;
     const double ha = pow(4.0 / 3.0, 0.25) * dr, hb = pow(3.0 / 4.0, 0.25) * dr;  // grids.jl:70-73
-    int rc = sp_time_begin(s);
+    int rc = sp_settle(s);
     if (rc) return rc;
+    if ((rc = sp_time_begin(s))) return rc;
+    ScratchGuard guard(s);
     sp_shape_node* d_nodes = nullptr;
     SP_CUDA(s, sp_dmalloc(&d_nodes, (size_t)n_nodes * sizeof(sp_shape_node)));
+    guard.p[0] = d_nodes;
     SP_CUDA(s, cudaMemcpyAsync(d_nodes, nodes, (size_t)n_nodes * sizeof(sp_shape_node), cudaMemcpyHostToDevice, s->stream));
     double* d_off = nullptr;
     if (n_off > 0) {
         SP_CUDA(s, sp_dmalloc(&d_off, (size_t)3 * n_off * sizeof(double)));
+        guard.p[1] = d_off;
         SP_CUDA(s, cudaMemcpyAsync(d_off, offsets, (size_t)3 * n_off * sizeof(double), cudaMemcpyHostToDevice, s->stream));
     }
     // whole i-slabs per chunk, at most ~64 M lattice points at a time
@@ -161,7 +183,9 @@ extern "C" int32_t sp_generate_particles(sp_system* s, int32_t grid, double dr, 
     const long long chunk_cap = std::min(rows, i1 - i0 + 1) * per_i;
     int *flag = nullptr, *pos = nullptr;
     SP_CUDA(s, sp_dmalloc(&flag, (size_t)chunk_cap * sizeof(int)));
+    guard.p[2] = flag;
     SP_CUDA(s, sp_dmalloc(&pos, (size_t)chunk_cap * sizeof(int)));
+    guard.p[3] = pos;
     const int B = 256;
     long long total = 0;
     for (long long ia = i0; ia <= i1 && !rc; ia += rows) {
@@ -193,11 +217,7 @@ extern "C" int32_t sp_generate_particles(sp_system* s, int32_t grid, double dr, 
         }
         total += add;
     }
-    cudaStreamSynchronize(s->stream);
-    sp_dfree(s, flag);
-    sp_dfree(s, pos);
-    sp_dfree(s, d_off);
-    sp_dfree(s, d_nodes);
+    // (the scratch arrays are released by `guard` on every path)
     if (rc) return rc;
     if (n_added) *n_added = total;
     return sp_time_end(s);
@@ -241,15 +261,19 @@ extern "C" int32_t sp_respawn(sp_system* s, int32_t type_field, double from_type
             return sp_fail(s, SP_ERR_INVALID, "respawn: bad fill field");
     if (s->slab) return sp_fail(s, SP_ERR_STATE, "respawn is not available on a slab system");
     if (n_added) *n_added = 0;
-    if (s->n == 0) return SP_OK;
     SP_CUDA(s, cudaSetDevice(s->device));
-    int rc = sp_time_begin(s);
+    int rc = sp_settle(s);
     if (rc) return rc;
+    if (s->n == 0) return SP_OK;
+    if ((rc = sp_time_begin(s))) return rc;
     const long long n_old = s->n;
     const int B = 256;
+    ScratchGuard guard(s);
     int *flag = nullptr, *pos = nullptr;
     SP_CUDA(s, sp_dmalloc(&flag, (size_t)n_old * sizeof(int)));
+    guard.p[0] = flag;
     SP_CUDA(s, sp_dmalloc(&pos, (size_t)n_old * sizeof(int)));
+    guard.p[1] = pos;
     SP_LAUNCH(s, k_respawn_flags, sp_blocks(n_old, B), B, 0, s->fields[0].d, s->fields[type_field].d, s->ref, n_old,
               from_type, x1_min, flag, pos);
     long long add = 0;
@@ -273,9 +297,6 @@ extern "C" int32_t sp_respawn(sp_system* s, int32_t type_field, double from_type
         }
         SP_LAUNCH(s, k_gen_fill, sp_blocks(add, B), B, 0, s->fields[type_field].d, s->cap, 1, from_type, n_old, n_old + add);
     }
-    cudaStreamSynchronize(s->stream);
-    sp_dfree(s, flag);
-    sp_dfree(s, pos);
     if (rc) return rc;
     if (n_added) *n_added = add;
     return sp_time_end(s);

@@ -23,7 +23,7 @@
 // device counters (ints) of sp_system::counters / the pinned mirror h_counters
 #define SP_CNT_TRASH 0    /* particles in the trash cell of the build in flight (dead tail + newly culled) */
 #define SP_CNT_ALIVE 1    /* alive slots: [0, alive) */
-#define SP_CNT_REMOVED 2  /* particles culled since the last sp_settle (added to n_removed there) */
+#define SP_CNT_REMOVED 2  /* particles culled by all builds so far (sp_num_removed) */
 #define SP_CNT_CULLED 3   /* particles culled by the last build */
 #define SP_CNT_CGFLAG 32
 #define SP_CNT_NBRMAX 40
@@ -117,6 +117,16 @@ struct sp_system {
     double* dscal = nullptr;    // CG scalars + dot partials (3*1024 + 16 doubles)
     double* h_scal = nullptr;   // pinned mirror of a few scalars
 
+    // CUDA graph of a unit of time steps of a step program (sp_program.cu)
+    struct StepGraph {
+        cudaGraphExec_t exec = nullptr;
+        unsigned long long sig = 0;  // signature of everything the captured launches depend on (sp_program.cu)
+        int program = 0, unit = 0;
+        long long launches = 0;      // kernel launches per replay
+        double params[16] = {0};
+        int32_t fields[8] = {0};
+    } graph;
+
     bool have_cells = false;
     bool capturing = false;   // the stream is being captured into a CUDA graph (sp_program.cu): no host read-backs
     bool in_program = false;  // inside sp_run_program: nested entry points do not touch the per-call timing events
@@ -193,6 +203,7 @@ static inline void sp_zeroed(sp_system* s, int fid) {
     s->fields[fid].known_zero = true;
 }
 void sp_slab_free(sp_system* s);  // sp_slab.cu
+void sp_program_free(sp_system* s);  // sp_program.cu: drops the cached step graph
 int sp_build_cells(sp_system* s);  // sp_cells.cu
 // make the host's particle count exact (waits for the stream if a build's count has not been fetched yet)
 int sp_settle(sp_system* s);

@@ -229,6 +229,7 @@ extern "C" int32_t sp_poisson_cg(sp_system* s, const int32_t* F, int32_t nf, con
     if (rc) return rc;
     if (np != 5 || !Pm) return sp_fail(s, SP_ERR_INVALID, "wrong number of parameters");
     if (!s->have_cells) return sp_fail(s, SP_ERR_STATE, "sp_poisson_cg before sp_create_cell_list");
+    if ((rc = sp_settle(s))) return rc;
     const long long n = s->n;
     if (iters) *iters = 0;
     if (resid) *resid = 0.0;
@@ -347,6 +348,7 @@ extern "C" int32_t sp_assemble_matrix(sp_system* s, const int32_t* F, int32_t nf
     const bool fill = I || J || V;
     if (fill && !(I && J && V)) return SP_ERR_INVALID;
     *nnz = 0;
+    if ((rc = sp_settle(s))) return rc;
     const long long n = s->n;
     if (n == 0) return SP_OK;
     int capk = 0;

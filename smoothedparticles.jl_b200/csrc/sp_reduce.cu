@@ -107,8 +107,9 @@ __device__ __forceinline__ void block_reduce3(double v[3], double* out3) {
 }
 
 template <int RED, bool IS_MAX>
-__global__ void __launch_bounds__(RED_B) k_reduce(RedParams R, long long n, double* partial) {
+__global__ void __launch_bounds__(RED_B) k_reduce(RedParams R, const int* __restrict__ alive, double* partial) {
     double acc[3] = {0.0, 0.0, 0.0};
+    const long long n = *alive;  // the dead tail of culled particles takes no part
     for (long long i = blockIdx.x * (long long)RED_B + threadIdx.x; i < n; i += (long long)gridDim.x * RED_B) {
         double v[3] = {0.0, 0.0, 0.0};
         if (R.ghost && R.ghost[i] != 0.0) continue;
@@ -153,7 +154,7 @@ static int run_reduce(sp_system* s, const RedParams& R, int nout, double* out) {
     if (nb < 1) nb = 1;
     double* partial = s->stage;
     double* res = s->stage + 3 * RED_MAXBLOCKS;
-    SP_LAUNCH(s, (k_reduce<RED, IS_MAX>), nb, RED_B, 0, R, (long long)s->n, partial);
+    SP_LAUNCH(s, (k_reduce<RED, IS_MAX>), nb, RED_B, 0, R, sp_alive(s), partial);
     SP_LAUNCH(s, (k_reduce_final<IS_MAX>), 1, RED_B, 0, partial, nb, res);
     if ((rc = sp_slab_allreduce_device(s, res, 3, IS_MAX ? 1 : 0))) return rc;
     double h[3];

@@ -5,15 +5,31 @@
 // slabs of whole cell layers.  Because that axis is the slowest in the linear key, after the local sort a
 // rank's two boundary cell layers and its two ghost layers are contiguous slot ranges.
 //
-// sp_slab_create_cell_list (replaces create_cell_list! on a slab system):
-//   1. drop last step's ghosts; classify owned particles by the cell layer of their CURRENT position
-//   2. MIGRATION: particles whose layer left [c0, c1) are packed (every field) and ncclSend/ncclRecv'd to
-//      the lower / upper neighbour (wrapping, with the coordinate shifted by the period, if periodic)
-//   3. GHOST HALO: copies of the owned particles in layers c0 and c1-1 go to the neighbours, which append
-//      them as ghosts (flag field "_ghost" = 1 from below / 2 from above, "_hidx" = index in the message)
-//   4. the ordinary cell-list build over owned + ghost particles on the LOCAL cell window
-// sp_slab_halo_refresh re-sends chosen fields of the same boundary particles in message order (the senders
-// remember the message index in "_sdn"/"_sup"), e.g. rho and P after find_pressure!.
+// A rank's LOCAL cell window is its owned layers [c0, c1) plus SLAB_W = 2 ghost layers per side.  Two layers, because
+// then the inner ghost layer sees all of its own neighbours: balance_of_mass! integrates its density exactly as the owner
+// does, and the WCSPH step needs ONE exchange per time step (no refresh of rho / P after find_pressure!).
+//
+// sp_slab_create_cell_list (replaces create_cell_list! on a slab system) — ONE exchange round, no host synchronisation
+// in the steady state:
+//   1. last step's ghosts are dropped (they come back fresh);
+//   2. every owned particle whose CURRENT position lies in the rank's first / last two owned layers or beyond them goes
+//      into the message to the lower / upper neighbour — ghost copies and migrants alike, every field, in slot order
+//      (deterministic: block counts, one scan, ordered pack).  Ownership is a function of the position alone: the
+//      receiver owns what falls into its owned layers and keeps the rest of its window as ghosts; the sender keeps
+//      its copy of a particle that migrated away as a ghost (it is bit-identical to what the new owner holds);
+//   3. both messages travel in one ncclGroup at a CAPACITY known to both ends without talking: the count that went over
+//      the same link two rebuilds ago (both ends have it) plus 25 %; the actual count rides in the message header and
+//      stays on the device; unused entries arrive as NaN positions and are culled by the build;
+//   4. arrivals are appended behind the alive slots, the ordinary cell-list build (sp_cells.cu, no read-back) sorts
+//      everything, "_ghost" is set from the cell layer.
+// The host runs at most two rebuilds ahead of the device: rebuild b waits for the counts of rebuild b-2 (an event that
+// has long completed when the device is busy), takes the message capacities and the slot bound from them, and never
+// waits for anything younger.  The first two rebuilds after sp_slab_init or after the host changed particles exchange
+// their counts explicitly (one host synchronisation each).
+// In-cell order on a slab system is by descending "_gid" (a global id given at insertion), which is the same on every
+// rank: a rank's two boundary layers and its neighbour's two ghost layers are then IDENTICAL slot sequences, and
+// sp_slab_halo_refresh (needed by the ISPH CG, whose search vector changes every iteration) is a plain copy of slot
+// ranges: pack, one ncclGroup, unpack — no index fields.
 // Reductions and CG dot products skip ghosts and are summed with ncclAllReduce.
 //
 // NCCL is loaded lazily with dlopen, so the single-GPU library has no NCCL dependency.
@@ -72,27 +88,32 @@ bool nccl_load() {
 
 }  // namespace
 
+#define SLAB_W 2        /* ghost layers per side */
+#define SLAB_NB 512     /* blocks of the selection passes */
+#define SLAB_HDR 8      /* doubles in front of a message: [0] = particle count */
+#define SLAB_RING 4
+
 struct SlabState {
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1, periodic = 0, axis = 2;
     long long gphase = 0, glim = 1;  // global key_phase / key_lim along the axis
     long long c0 = 0, c1 = 1;        // owned global cell layers [c0, c1), 0-based from gphase
     double period = 0.0;
-    int f_ghost = -1, f_hidx = -1, f_sdn = -1, f_sup = -1;
+    int f_ghost = -1, f_gid = -1;
     double* sendbuf[2] = {nullptr, nullptr};
     double* recvbuf[2] = {nullptr, nullptr};
     long long buf_len = 0;  // doubles per buffer
-    int* d_cnt = nullptr;   // [0],[1] send counts down/up, [2],[3] received counts from below/above
-    int* h_cnt = nullptr;
-    long long n_send[2] = {0, 0};   // ghost message sizes sent down / up at the last rebuild
-    long long n_ghost[2] = {0, 0};  // ghosts received from below / above
-    long long n_owned = 0;
-    // slot window of the selection passes: after a rebuild the slots are sorted by cell layer, and a particle moves
-    // less than one cell per step, so only slots [0, sel_a) and [sel_b, n) (three cell layers per side) can hold
-    // old ghosts, migrants or new boundary particles.  sel_valid is dropped whenever the host touched positions.
-    long long sel_a = 0, sel_b = 0;
-    bool sel_valid = false;
-    // SP_SLAB_TRACE=1: host wall-clock of the phases of sp_slab_create_cell_list (each ends in a stream sync)
+    // device ints: [0],[1] particles sent down / up, [2],[3] received from below / above, [4] overflow flag,
+    // [5] refresh mismatch flag, [8] owned count, [16 ..] block counts / offsets of the selection passes
+    int* d_cnt = nullptr;
+    int* h_cnt = nullptr;                 // pinned: SLAB_RING x 16 ints (counts of the last rebuilds) + scratch
+    cudaEvent_t ring_ev[SLAB_RING] = {nullptr, nullptr, nullptr, nullptr};
+    long long build_no = 0;               // rebuilds so far
+    int history = 0;                      // consecutive rebuilds whose counts are in the ring (steady state from 2 on)
+    long long cap_send[2] = {0, 0};       // message capacities of the last rebuild: down / up
+    long long cap_recv[2] = {0, 0};       // ... from below / from above
+    long long gid_base = 0;
+    bool fresh_particles = true;          // the host added particles: they have no "_gid" yet
     double trace_s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long trace_calls = 0;
 };
@@ -124,17 +145,25 @@ void sp_slab_free(sp_system* s) {
     }
     sp_dfree(s, sl->d_cnt);
     if (sl->h_cnt) cudaFreeHost(sl->h_cnt);
+    for (int r = 0; r < SLAB_RING; r++)
+        if (sl->ring_ev[r]) cudaEventDestroy(sl->ring_ev[r]);
     delete sl;
     s->slab = nullptr;
 }
 
 void sp_slab_host_touched(sp_system* s) {
-    if (s->slab) s->slab->sel_valid = false;
+    if (!s->slab) return;
+    s->slab->history = 0;  // the next two rebuilds exchange their counts explicitly and select over all slots
+    s->slab->fresh_particles = true;
 }
 
 const double* sp_slab_ghost_mask(sp_system* s) {
     if (!s->slab) return nullptr;
     return s->fields[s->slab->f_ghost].d;
+}
+const double* sp_slab_gid(sp_system* s) {
+    if (!s->slab) return nullptr;
+    return s->fields[s->slab->f_gid].d;
 }
 
 int sp_slab_allreduce_device(sp_system* s, double* d_inout, int count, int is_max) {
@@ -150,136 +179,238 @@ struct SlabPlanes {
     double* p[SLAB_PLANES];
     int count;
     int axis_plane;  // index of the plane holding the slab-axis coordinate, or -1
+    int x_plane;     // index of the plane holding x[0] (a NaN there kills a slot), or -1
 };
 
-// selection passes run over t in [0, n_sel): slot = t below sel_a, sel_b + (t - sel_a) above
-struct SlabSel {
-    long long a, b, n_sel;
-    __host__ __device__ long long slot(long long t) const { return t < a ? t : b + (t - a); }
-};
-
-// flags: dn[t] = 1 if the particle migrates to the lower neighbour, up[t] likewise; old ghosts are killed (x = NaN)
-__global__ void k_slab_classify(SpGrid g, int rank, int nranks, long long gphase, long long c0, long long c1,
-                                double* x, long long cap, const double* ghost, SlabSel sel, int* dn, int* up) {
-    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (t >= sel.n_sel) return;
-    const long long s = sel.slot(t);
-    int fd = 0, fu = 0;
-    if (ghost[s] != 0.0) {
-        x[s] = nan("");  // dropped by the build
-    } else {
-        const double xa = x[(size_t)g.slab_axis * cap + s];
-        const double q = floor(__ddiv_rn(xa, g.h));
-        if (q == q && fabs(q) < 9.0e18) {
-            const long long ca = (long long)q - gphase;
-            if (ca < c0) fd = (g.slab_periodic || rank > 0) ? 1 : 0;          // else: left the global domain, culled
-            else if (ca >= c1) fu = (g.slab_periodic || rank < nranks - 1) ? 1 : 0;
+// Where things are in the slot order of the LAST build (slots are sorted by cell, the slab axis is the slowest key axis,
+// so a cell layer is one slot range).  `full` = the host touched the particles: no valid cell list, look at every slot.
+struct SlabWin {
+    const int* cell_start;
+    const int* counters;   // sp_system::counters
+    long long L;           // cells per layer
+    int nl;                // layers of the local window (owned + 2 * SLAB_W)
+    int full;
+    __device__ long long layer_begin(int l) const { return cell_start[(long long)l * L + 1]; }
+    __device__ long long alive() const { return counters[SP_CNT_ALIVE]; }
+    // slots that may have to be sent in direction dir (0 = down, 1 = up): the three owned layers next to that side
+    __device__ void send_window(int dir, long long* lo, long long* hi) const {
+        if (full) {
+            *lo = 0;
+            *hi = alive();
+            return;
+        }
+        if (dir == 0) {
+            *lo = layer_begin(SLAB_W);
+            *hi = layer_begin(min(SLAB_W + 3, nl - SLAB_W));
+        } else {
+            *lo = layer_begin(max(SLAB_W, nl - SLAB_W - 3));
+            *hi = layer_begin(nl - SLAB_W);
         }
     }
-    dn[t] = fd;
-    up[t] = fu;
+};
+
+__device__ __forceinline__ bool slab_layer_of(const SpGrid& g, double xa, long long* layer) {
+    const double q = floor(__ddiv_rn(xa, g.h));
+    if (!(q == q) || !(fabs(q) < 9.0e18)) return false;
+    *layer = (long long)q - g.phase[g.slab_axis];
+    return true;
 }
-// owned, alive particles in the first / last owned layer are sent as ghosts down / up
-__global__ void k_slab_boundary(SpGrid g, int rank, int nranks, long long gphase, long long c0, long long c1,
-                                const double* x, long long cap, const double* ghost, SlabSel sel, int* dn, int* up) {
-    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (t >= sel.n_sel) return;
-    const long long s = sel.slot(t);
-    int fd = 0, fu = 0;
+// is slot s part of the message in direction dir?  owned, alive, and its CURRENT layer within the first (last) two owned
+// layers or beyond
+__device__ __forceinline__ bool slab_selected(const SpGrid& g, const double* x, long long cap, const double* ghost, int nl,
+                                              int dir, long long s) {
+    if (ghost[s] != 0.0) return false;
     const double x0 = x[s];
-    if (ghost[s] == 0.0 && x0 == x0) {
-        const double q = floor(__ddiv_rn(x[(size_t)g.slab_axis * cap + s], g.h));
-        if (q == q && fabs(q) < 9.0e18) {
-            const long long ca = (long long)q - gphase;
-            if (ca == c0) fd = (g.slab_periodic || rank > 0) ? 1 : 0;
-            if (ca == c1 - 1) fu = (g.slab_periodic || rank < nranks - 1) ? 1 : 0;
+    if (!(x0 == x0)) return false;
+    long long l;
+    if (!slab_layer_of(g, x[(size_t)g.slab_axis * cap + s], &l)) return false;
+    return dir == 0 ? (l < 2 * SLAB_W) : (l >= nl - 2 * SLAB_W);
+}
+
+// old ghosts die: x = NaN (the build culls them)
+__global__ void k_slab_kill_ghosts(SlabWin w, double* x, const double* ghost) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (w.full) {
+        const long long n = w.alive();
+        for (long long s = t0; s < n; s += stride)
+            if (ghost[s] != 0.0) x[s] = nan("");
+        return;
+    }
+    const long long a0 = w.layer_begin(0), a1 = w.layer_begin(SLAB_W);
+    const long long b0 = w.layer_begin(w.nl - SLAB_W), b1 = w.layer_begin(w.nl);
+    for (long long s = a0 + t0; s < a1; s += stride) x[s] = nan("");
+    for (long long s = b0 + t0; s < b1; s += stride) x[s] = nan("");
+}
+
+// pass 1: how many selected slots in the chunk of block b (blockIdx.y = direction)
+__global__ void __launch_bounds__(256) k_slab_sel_count(SpGrid g, SlabWin w, const double* x, long long cap, const double* ghost,
+                                                        int* blk) {
+    const int dir = blockIdx.y;
+    long long lo, hi;
+    w.send_window(dir, &lo, &hi);
+    const long long len = max(hi - lo, 0LL);
+    const long long chunk = (len + gridDim.x - 1) / gridDim.x;
+    const long long b = lo + (long long)blockIdx.x * chunk, e = min(b + chunk, hi);
+    int mine = 0;
+    for (long long s = b + threadIdx.x; s < e; s += blockDim.x) mine += slab_selected(g, x, cap, ghost, w.nl, dir, s) ? 1 : 0;
+    const int total = __syncthreads_count(0) * 0 + 0;  // (placeholder to keep the barrier structure simple)
+    (void)total;
+    __shared__ int sm[256];
+    sm[threadIdx.x] = mine;
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) {
+        if (threadIdx.x < d) sm[threadIdx.x] += sm[threadIdx.x + d];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) blk[dir * SLAB_NB + blockIdx.x] = sm[0];
+}
+// pass 2 (one block): exclusive scan of the block counts, totals, overflow against the message capacity
+__global__ void __launch_bounds__(SLAB_NB) k_slab_sel_scan(int* blk, int* d_cnt, long long cap_dn, long long cap_up) {
+    __shared__ int sm[SLAB_NB];
+    for (int dir = 0; dir < 2; dir++) {
+        const int v = blk[dir * SLAB_NB + threadIdx.x];
+        sm[threadIdx.x] = v;
+        __syncthreads();
+        for (int d = 1; d < SLAB_NB; d <<= 1) {
+            int t = threadIdx.x >= d ? sm[threadIdx.x - d] : 0;
+            __syncthreads();
+            sm[threadIdx.x] += t;
+            __syncthreads();
         }
-    }
-    dn[t] = fd;
-    up[t] = fu;
-}
-// message index of every selected slot (exclusive scans in posd/posu), -1 otherwise, as Float64 fields
-__global__ void k_slab_fill2(double* a, double* b, double v, long long n) {
-    const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (s < n) {
-        a[s] = v;
-        b[s] = v;
-    }
-}
-__global__ void k_slab_record(const int* fd, const int* fu, const int* posd, const int* posu, double* sdn, double* sup,
-                              SlabSel sel) {
-    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (t >= sel.n_sel) return;
-    const long long s = sel.slot(t);
-    sdn[s] = fd[t] ? (double)posd[t] : -1.0;
-    sup[s] = fu[t] ? (double)posu[t] : -1.0;
-}
-__global__ void k_slab_pack(SlabPlanes tab, const int* flag, const int* pos, SlabSel sel, double* buf, long long count) {
-    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (t >= sel.n_sel || !flag[t]) return;
-    const long long s = sel.slot(t);
-    const long long m = pos[t];
-    for (int c = 0; c < tab.count; c++) buf[(size_t)c * count + m] = tab.p[c][s];
-}
-__global__ void k_slab_kill(const int* fd, const int* fu, double* x, SlabSel sel) {
-    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (t < sel.n_sel && (fd[t] | fu[t])) x[sel.slot(t)] = nan("");
-}
-__global__ void k_slab_unpack(SlabPlanes tab, const double* buf, long long count, long long base, double shift, int* ref) {
-    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (t >= count) return;
-    for (int c = 0; c < tab.count; c++) {
-        double v = buf[(size_t)c * count + t];
-        if (c == tab.axis_plane) v += shift;
-        tab.p[c][base + t] = v;
-    }
-    if (ref) ref[base + t] = (int)(base + t);
-}
-__global__ void k_slab_mark(double* ghost, double* hidx, double* sdn, double* sup, long long base, long long count,
-                            double side) {
-    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (t >= count) return;
-    ghost[base + t] = side;
-    hidx[base + t] = (double)t;
-    sdn[base + t] = -1.0;
-    sup[base + t] = -1.0;
-}
-// halo refresh: boundary owners write the field into message order; ghosts read it back by message index
-__global__ void k_slab_refresh_pack(const double* f, long long cap, int ncomp, const double* sel, long long n, double* buf,
-                                    long long count) {
-    const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    const double v = sel[s];
-    if (!(v >= 0.0)) return;
-    const long long t = (long long)v;
-    for (int c = 0; c < ncomp; c++) buf[(size_t)c * count + t] = f[(size_t)c * cap + s];
-}
-__global__ void k_slab_refresh_unpack(double* f, long long cap, int ncomp, const double* ghost, const double* hidx,
-                                      long long n, const double* buf_lo, long long cnt_lo, const double* buf_hi,
-                                      long long cnt_hi, int axis_comp, double shift_lo, double shift_hi) {
-    const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    const double gflag = ghost[s];
-    if (gflag == 0.0) return;
-    const long long t = (long long)hidx[s];
-    const bool lo = gflag == 1.0;
-    const double* buf = lo ? buf_lo : buf_hi;
-    const long long cnt = lo ? cnt_lo : cnt_hi;
-    for (int c = 0; c < ncomp; c++) {
-        double v = buf[(size_t)c * cnt + t];
-        if (c == axis_comp) v += lo ? shift_lo : shift_hi;
-        f[(size_t)c * cap + s] = v;
+        blk[dir * SLAB_NB + threadIdx.x] = sm[threadIdx.x] - v;  // exclusive
+        if (threadIdx.x == SLAB_NB - 1) {
+            const long long capd = dir == 0 ? cap_dn : cap_up;
+            const int total = sm[threadIdx.x];
+            if (capd >= 0 && total > capd) {
+                d_cnt[4] = 1;  // overflow: the message cannot hold the boundary particles (reported by a later rebuild)
+                d_cnt[dir] = (int)capd;
+            } else
+                d_cnt[dir] = total;
+        }
+        __syncthreads();
     }
 }
-__global__ void k_slab_iota(int* ref, long long n) {
-    const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (s < n) ref[s] = (int)s;
+// pass 3: ordered pack of every plane of the selected slots into the message (plane c at SLAB_HDR + c*msg_cap)
+__global__ void __launch_bounds__(256) k_slab_sel_pack(SpGrid g, SlabWin w, const double* x, long long cap, const double* ghost,
+                                                       const int* blk, const int* d_cnt, SlabPlanes tab, int plane0,
+                                                       double* buf_dn, long long cap_dn, double* buf_up, long long cap_up) {
+    const int dir = blockIdx.y;
+    double* buf = dir == 0 ? buf_dn : buf_up;
+    const long long mcap = dir == 0 ? cap_dn : cap_up;
+    if (!buf) return;
+    long long lo, hi;
+    w.send_window(dir, &lo, &hi);
+    const long long len = max(hi - lo, 0LL);
+    const long long chunk = (len + gridDim.x - 1) / gridDim.x;
+    const long long b = lo + (long long)blockIdx.x * chunk, e = min(b + chunk, hi);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && plane0 == 0) buf[0] = (double)d_cnt[dir];
+    __shared__ int warp_tot[8];
+    __shared__ int run_sm;
+    if (threadIdx.x == 0) run_sm = blk[dir * SLAB_NB + blockIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long base = b; base < e; base += blockDim.x) {
+        const long long s = base + threadIdx.x;
+        const bool sel = s < e && slab_selected(g, x, cap, ghost, w.nl, dir, s);
+        const unsigned bal = __ballot_sync(0xffffffffu, sel);
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        int off = run_sm;
+        for (int q = 0; q < warp; q++) off += warp_tot[q];
+        const long long m = off + __popc(bal & ((1u << lane) - 1u));
+        if (sel && m < mcap)
+            for (int c = 0; c < tab.count; c++) buf[SLAB_HDR + (size_t)(plane0 + c) * mcap + m] = tab.p[c][s];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int q = 0; q < 8; q++) t += warp_tot[q];
+            run_sm += t;
+        }
+        __syncthreads();
+    }
 }
-__global__ void k_slab_count_owned(const double* ghost, long long n, int* out) {
+// arrivals go behind the alive slots: slot = alive + off + t; entries beyond the message's count become dead slots
+__global__ void k_slab_unpack(SlabPlanes tab, int plane0, const double* buf, long long mcap, long long off, double shift,
+                              const int* counters, int* ref, int* d_cnt, int which) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= mcap) return;
+    const long long count = (long long)buf[0];
+    const long long slot = (long long)counters[SP_CNT_ALIVE] + off + t;
+    if (t == 0 && plane0 == 0) d_cnt[2 + which] = (int)count;
+    if (t < count) {
+        for (int c = 0; c < tab.count; c++) {
+            double v = buf[SLAB_HDR + (size_t)(plane0 + c) * mcap + t];
+            if (c == tab.axis_plane) v += shift;
+            tab.p[c][slot] = v;
+        }
+    } else if (tab.x_plane >= 0)
+        tab.p[tab.x_plane][slot] = nan("");
+    if (plane0 == 0) ref[slot] = (int)slot;
+}
+__global__ void k_slab_add_alive(int* counters, int add) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) counters[SP_CNT_ALIVE] += add;
+}
+__global__ void k_slab_clear(int* d_cnt) {
+    if (threadIdx.x < 4 && blockIdx.x == 0) d_cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 8 && blockIdx.x == 0) d_cnt[8] = 0;
+}
+// particles the host added have no global id yet: rank * 2^44 + base + slot (unique, deterministic)
+__global__ void k_slab_assign_gid(double* gid, const int* counters, double base) {
     const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const int owned = (s < n && ghost[s] == 0.0) ? 1 : 0;
-    const int total = __syncthreads_count(owned);  // one atomic per CTA: 300 k same-address atomics cost 0.15 ms
-    if (threadIdx.x == 0 && total) atomicAdd(out, total);
+    if (s < counters[SP_CNT_ALIVE] && gid[s] == 0.0) gid[s] = base + (double)s;
+}
+// after the build: "_ghost" from the cell layer (1 = below the owned layers, 2 = above), ref = slot, owned count
+__global__ void __launch_bounds__(256) k_slab_post(const int* key, double* ghost, int* ref, long long L, int nl,
+                                                   const int* counters, int* d_cnt) {
+    const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    int owned = 0;
+    if (s < counters[SP_CNT_ALIVE]) {
+        const long long l = ((long long)key[s] - 1) / L;
+        const double gflag = l < SLAB_W ? 1.0 : (l >= nl - SLAB_W ? 2.0 : 0.0);
+        ghost[s] = gflag;
+        ref[s] = (int)s;
+        owned = gflag == 0.0;
+    }
+    const int total = __syncthreads_count(owned);  // one atomic per CTA
+    if (threadIdx.x == 0 && total) atomicAdd(d_cnt + 8, total);
+}
+// halo refresh: the two boundary layers of the owner and the two ghost layers of its neighbour are the same slot
+// sequence (see the header comment), so a refresh is a copy of slot ranges
+__global__ void k_slab_refresh_pack(SlabWin w, const double* f, long long cap, int ncomp, int comp0, double* buf_dn,
+                                    long long cap_dn, double* buf_up, long long cap_up) {
+    const int dir = blockIdx.y;
+    double* buf = dir == 0 ? buf_dn : buf_up;
+    if (!buf) return;
+    const long long mcap = dir == 0 ? cap_dn : cap_up;
+    const long long lo = dir == 0 ? w.layer_begin(SLAB_W) : w.layer_begin(w.nl - 2 * SLAB_W);
+    const long long hi = dir == 0 ? w.layer_begin(2 * SLAB_W) : w.layer_begin(w.nl - SLAB_W);
+    const long long len = min(hi - lo, mcap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) buf[0] = (double)(hi - lo);
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < len; t += (long long)gridDim.x * blockDim.x)
+        for (int c = 0; c < ncomp; c++) buf[SLAB_HDR + (size_t)(comp0 + c) * mcap + t] = f[(size_t)c * cap + lo + t];
+}
+__global__ void k_slab_refresh_unpack(SlabWin w, double* f, long long cap, int ncomp, int comp0, const double* buf_lo,
+                                      long long cap_lo, const double* buf_hi, long long cap_hi, int axis_comp,
+                                      double shift_lo, double shift_hi, int* d_cnt) {
+    const int side = blockIdx.y;  // 0: from below into the lower ghost layers, 1: from above into the upper ones
+    const double* buf = side == 0 ? buf_lo : buf_hi;
+    if (!buf) return;
+    const long long mcap = side == 0 ? cap_lo : cap_hi;
+    const long long lo = side == 0 ? w.layer_begin(0) : w.layer_begin(w.nl - SLAB_W);
+    const long long hi = side == 0 ? w.layer_begin(SLAB_W) : w.layer_begin(w.nl);
+    const long long count = (long long)buf[0];
+    if (count != hi - lo) {  // the two ends disagree about the boundary set: never expected, reported by the next rebuild
+        if (blockIdx.x == 0 && threadIdx.x == 0) d_cnt[5] = 1;
+        return;
+    }
+    const double shift = side == 0 ? shift_lo : shift_hi;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < count; t += (long long)gridDim.x * blockDim.x)
+        for (int c = 0; c < ncomp; c++) {
+            double v = buf[SLAB_HDR + (size_t)(comp0 + c) * mcap + t];
+            if (c == axis_comp) v += shift;
+            f[(size_t)c * cap + lo + t] = v;
+        }
 }
 
 // ------------------------------------------------------------------ host helpers
@@ -287,19 +418,20 @@ static int slab_planes(sp_system* s, std::vector<SlabPlanes>& tabs, int* nplanes
     tabs.clear();
     SlabPlanes cur;
     cur.count = 0;
-    cur.axis_plane = -1;
+    cur.axis_plane = cur.x_plane = -1;
     int total = 0;
     for (size_t f = 0; f < s->fields.size(); f++) {
         SpField& fl = s->fields[f];
         if (fl.transient) continue;
         for (int c = 0; c < fl.ncomp; c++) {
             if (f == 0 && c == s->slab->axis) cur.axis_plane = cur.count;
+            if (f == 0 && c == 0) cur.x_plane = cur.count;
             cur.p[cur.count++] = fl.d + (size_t)c * s->cap;
             total++;
             if (cur.count == SLAB_PLANES) {
                 tabs.push_back(cur);
                 cur.count = 0;
-                cur.axis_plane = -1;
+                cur.axis_plane = cur.x_plane = -1;
             }
         }
     }
@@ -338,153 +470,216 @@ static void slab_peers(const SlabState* sl, int* below, int* above) {
     }
 }
 
-// totals of the two selections on the device: d_cnt[0] = to send down, d_cnt[1] = to send up (last exclusive-scan
-// value + last flag), d_cnt[2], d_cnt[3] cleared for the receive counts
-__global__ void k_slab_totals(const int* fd, const int* fu, const int* posd, const int* posu, long long ns, int* d_cnt) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        d_cnt[0] = ns > 0 ? posd[ns - 1] + fd[ns - 1] : 0;
-        d_cnt[1] = ns > 0 ? posu[ns - 1] + fu[ns - 1] : 0;
-        d_cnt[2] = 0;
-        d_cnt[3] = 0;
-    }
+static SlabWin slab_win(sp_system* s, bool full) {
+    SlabWin w;
+    w.cell_start = s->cell_start;
+    w.counters = s->counters;
+    w.L = s->g.lim[0] * (s->slab->axis == 2 ? s->g.lim[1] : 1);
+    w.nl = (int)s->g.lim[s->slab->axis];
+    w.full = full ? 1 : 0;
+    return w;
 }
 
-// exchange the send counts (already in d_cnt[0], d_cnt[1]) with both neighbours and bring all four numbers to the
-// host with ONE synchronisation: h_cnt[0],[1] = my counts down/up, h_cnt[2],[3] = counts arriving from below / above
+// The bootstrap rebuilds exchange the send counts (already in d_cnt[0], d_cnt[1]) with both neighbours and bring all
+// four numbers to the host with ONE synchronisation: h[0],[1] = my counts down/up, h[2],[3] = counts arriving from
+// below / above.
 static int slab_exchange_counts(sp_system* s, long long* n_dn, long long* n_up, long long* from_below, long long* from_above) {
     SlabState* sl = s->slab;
     int below, above;
     slab_peers(sl, &below, &above);
+    int* scratch = sl->d_cnt + 12;  // [12],[13] receive slots
+    int* h = sl->h_cnt + SLAB_RING * 16;
     // Call order matters when below == above (1 or 2 ranks, periodic): messages between one pair of ranks are
     // matched in issue order, and what I send DOWN arrives at my lower neighbour FROM ABOVE.  So: send down,
     // send up, then receive from above, receive from below.
     SP_NCCL(s, g_nccl.GroupStart());
     if (below >= 0) SP_NCCL(s, g_nccl.Send(sl->d_cnt + 0, 1, ncclInt32, below, sl->comm, s->stream));
     if (above >= 0) SP_NCCL(s, g_nccl.Send(sl->d_cnt + 1, 1, ncclInt32, above, sl->comm, s->stream));
-    if (above >= 0) SP_NCCL(s, g_nccl.Recv(sl->d_cnt + 3, 1, ncclInt32, above, sl->comm, s->stream));
-    if (below >= 0) SP_NCCL(s, g_nccl.Recv(sl->d_cnt + 2, 1, ncclInt32, below, sl->comm, s->stream));
+    if (above >= 0) SP_NCCL(s, g_nccl.Recv(scratch + 1, 1, ncclInt32, above, sl->comm, s->stream));
+    if (below >= 0) SP_NCCL(s, g_nccl.Recv(scratch + 0, 1, ncclInt32, below, sl->comm, s->stream));
     SP_NCCL(s, g_nccl.GroupEnd());
-    SP_CUDA(s, cudaMemcpyAsync(sl->h_cnt, sl->d_cnt, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    SP_CUDA(s, cudaMemcpyAsync(h, sl->d_cnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    SP_CUDA(s, cudaMemcpyAsync(h + 2, scratch, 2 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     SP_CUDA(s, cudaStreamSynchronize(s->stream));
-    *n_dn = sl->h_cnt[0];
-    *n_up = sl->h_cnt[1];
-    *from_below = below >= 0 ? sl->h_cnt[2] : 0;
-    *from_above = above >= 0 ? sl->h_cnt[3] : 0;
+    *n_dn = below >= 0 ? h[0] : 0;
+    *n_up = above >= 0 ? h[1] : 0;
+    *from_below = below >= 0 ? h[2] : 0;
+    *from_above = above >= 0 ? h[3] : 0;
     return SP_OK;
 }
 
-static int slab_exchange_payload(sp_system* s, long long send_dn, long long send_up, long long recv_lo, long long recv_hi,
-                                 int nplanes) {
+static int slab_exchange_payload(sp_system* s, long long send_dn, long long send_up, long long recv_lo, long long recv_hi) {
     SlabState* sl = s->slab;
     int below, above;
     slab_peers(sl, &below, &above);
-    // same call order as slab_exchange_counts; empty messages are skipped on both sides (counts are known)
+    // same call order as slab_exchange_counts; sizes in doubles, header included; a link without traffic is skipped on
+    // both sides (size 0)
     SP_NCCL(s, g_nccl.GroupStart());
-    if (below >= 0 && send_dn)
-        SP_NCCL(s, g_nccl.Send(sl->sendbuf[0], (size_t)send_dn * nplanes, ncclFloat64, below, sl->comm, s->stream));
-    if (above >= 0 && send_up)
-        SP_NCCL(s, g_nccl.Send(sl->sendbuf[1], (size_t)send_up * nplanes, ncclFloat64, above, sl->comm, s->stream));
-    if (above >= 0 && recv_hi)
-        SP_NCCL(s, g_nccl.Recv(sl->recvbuf[1], (size_t)recv_hi * nplanes, ncclFloat64, above, sl->comm, s->stream));
-    if (below >= 0 && recv_lo)
-        SP_NCCL(s, g_nccl.Recv(sl->recvbuf[0], (size_t)recv_lo * nplanes, ncclFloat64, below, sl->comm, s->stream));
+    if (below >= 0 && send_dn) SP_NCCL(s, g_nccl.Send(sl->sendbuf[0], (size_t)send_dn, ncclFloat64, below, sl->comm, s->stream));
+    if (above >= 0 && send_up) SP_NCCL(s, g_nccl.Send(sl->sendbuf[1], (size_t)send_up, ncclFloat64, above, sl->comm, s->stream));
+    if (above >= 0 && recv_hi) SP_NCCL(s, g_nccl.Recv(sl->recvbuf[1], (size_t)recv_hi, ncclFloat64, above, sl->comm, s->stream));
+    if (below >= 0 && recv_lo) SP_NCCL(s, g_nccl.Recv(sl->recvbuf[0], (size_t)recv_lo, ncclFloat64, below, sl->comm, s->stream));
     SP_NCCL(s, g_nccl.GroupEnd());
     return SP_OK;
 }
 
-// select (flags fd/fu) -> scan -> pack all planes -> exchange -> append; returns counts
-static int slab_round(sp_system* s, bool ghosts, long long* n_recv_lo, long long* n_recv_hi, long long* n_sent_dn,
-                      long long* n_sent_up) {
+// message capacity for a link over which `count` particles went two rebuilds ago (both ends evaluate this)
+static long long slab_capacity(long long count) {
+    long long c = count + count / 4 + 2048;
+    return (c + 1023) / 1024 * 1024;
+}
+
+static int slab_rebuild(sp_system* s) {
     SlabState* sl = s->slab;
     const int B = 256;
-    const long long n = s->n;
-    int* fd = s->flags;
-    int* fu = s->key_alt;
-    int* posd = s->perm;
-    int* posu = s->tmp_slot;
-    double* X = s->fields[0].d;
-    const double* ghost = s->fields[sl->f_ghost].d;
-    SlabSel sel;
-    if (sl->sel_valid && sl->sel_a < sl->sel_b && sl->sel_b <= n) {
-        sel.a = sl->sel_a;
-        sel.b = sl->sel_b;
+    int rc;
+    int below, above;
+    slab_peers(sl, &below, &above);
+    const bool trace = slab_trace_on();
+    double t0 = 0, t1 = 0, t2 = 0;
+    if (trace) {
+        cudaStreamSynchronize(s->stream);
+        t0 = slab_now();
+    }
+    const bool steady = sl->history >= 2 && s->have_cells;
+    long long cap_send[2] = {0, 0}, cap_recv[2] = {0, 0};
+    if (steady) {
+        // counts of rebuild b-2: long finished unless the host is more than two steps ahead of the device
+        const int slot = (int)((sl->build_no - 2) % SLAB_RING);
+        SP_CUDA(s, cudaEventSynchronize(sl->ring_ev[slot]));
+        const int* h = sl->h_cnt + slot * 16;
+        if (h[4]) return sp_fail(s, SP_ERR_STATE, "slab exchange overflow: the number of particles in a boundary layer grew by "
+                                                  "more than 25 % within two rebuilds; particles were lost");
+        if (h[5]) return sp_fail(s, SP_ERR_STATE, "slab halo refresh: owner and ghost layers disagree");
+        cap_send[0] = below >= 0 ? slab_capacity(h[0]) : 0;
+        cap_send[1] = above >= 0 ? slab_capacity(h[1]) : 0;
+        cap_recv[0] = below >= 0 ? slab_capacity(h[2]) : 0;
+        cap_recv[1] = above >= 0 ? slab_capacity(h[3]) : 0;
+        // slot bound before this rebuild: alive after rebuild b-2 plus everything rebuild b-1 may have appended
+        s->n = (long long)h[9] + sl->cap_recv[0] + sl->cap_recv[1];
+        s->n_exact = false;
+        s->count_pending = false;
     } else {
-        sel.a = n;  // everything
-        sel.b = n;
+        if ((rc = sp_settle(s))) return rc;
     }
-    sel.n_sel = sel.a + (n - sel.b);
-    const long long ns = sel.n_sel;
-    if (ns > 0) {
-        if (!ghosts)
-            SP_LAUNCH(s, k_slab_classify, sp_blocks(ns, B), B, 0, s->g, sl->rank, sl->nranks, sl->gphase, sl->c0, sl->c1, X,
-                      s->cap, ghost, sel, fd, fu);
-        else
-            SP_LAUNCH(s, k_slab_boundary, sp_blocks(ns, B), B, 0, s->g, sl->rank, sl->nranks, sl->gphase, sl->c0, sl->c1, X,
-                      s->cap, ghost, sel, fd, fu);
-        SP_CUDA(s, cudaMemcpyAsync(posd, fd, (size_t)ns * sizeof(int), cudaMemcpyDeviceToDevice, s->stream));
-        SP_CUDA(s, cudaMemcpyAsync(posu, fu, (size_t)ns * sizeof(int), cudaMemcpyDeviceToDevice, s->stream));
-        int rc = sp_exclusive_scan_i32(s, posd, ns);
-        if (rc) return rc;
-        if ((rc = sp_exclusive_scan_i32(s, posu, ns))) return rc;
+    const SlabWin w = slab_win(s, !steady);
+    double* X = s->fields[0].d;
+    double* ghost = s->fields[sl->f_ghost].d;
+    SP_LAUNCH(s, k_slab_clear, 1, 32, 0, sl->d_cnt);
+    if (s->n > 0) {
+        if (sl->fresh_particles) {
+            SP_LAUNCH(s, k_slab_assign_gid, sp_blocks(s->n, B), B, 0, s->fields[sl->f_gid].d, s->counters,
+                      (double)sl->rank * 17592186044416.0 + (double)sl->gid_base);
+            sl->gid_base += s->n;
+            sl->fresh_particles = false;
+        }
+        // 1: old ghosts die
+        SP_LAUNCH(s, k_slab_kill_ghosts, 1184, B, 0, w, X, ghost);
+        // 2: selection: counts per block, one scan
+        SP_LAUNCH(s, k_slab_sel_count, dim3(SLAB_NB, 2), B, 0, s->g, w, X, s->cap, ghost, sl->d_cnt + 16);
+        SP_LAUNCH(s, k_slab_sel_scan, 1, SLAB_NB, 0, sl->d_cnt + 16, sl->d_cnt, steady ? cap_send[0] : -1LL,
+                  steady ? cap_send[1] : -1LL);
     }
-    // totals stay on the device: they go to the neighbours from there, and one synchronisation brings the send and
-    // receive counts to the host together
-    SP_LAUNCH(s, k_slab_totals, 1, 32, 0, fd, fu, posd, posu, ns, sl->d_cnt);
-    long long send_dn = 0, send_up = 0, recv_lo = 0, recv_hi = 0;
-    int rc = slab_exchange_counts(s, &send_dn, &send_up, &recv_lo, &recv_hi);
-    if (rc) return rc;
-    if (ghosts && n > 0) {
-        SP_LAUNCH(s, k_slab_fill2, sp_blocks(n, B), B, 0, s->fields[sl->f_sdn].d, s->fields[sl->f_sup].d, -1.0, n);
-        if (ns > 0)
-            SP_LAUNCH(s, k_slab_record, sp_blocks(ns, B), B, 0, fd, fu, posd, posu, s->fields[sl->f_sdn].d,
-                      s->fields[sl->f_sup].d, sel);
+    if (!steady) {
+        long long n_dn = 0, n_up = 0, fb = 0, fa = 0;
+        if ((rc = slab_exchange_counts(s, &n_dn, &n_up, &fb, &fa))) return rc;
+        cap_send[0] = below >= 0 ? std::max<long long>(n_dn, 1) : 0;
+        cap_send[1] = above >= 0 ? std::max<long long>(n_up, 1) : 0;
+        cap_recv[0] = below >= 0 ? std::max<long long>(fb, 1) : 0;
+        cap_recv[1] = above >= 0 ? std::max<long long>(fa, 1) : 0;
     }
     std::vector<SlabPlanes> tabs;
     int nplanes = 0;
     slab_planes(s, tabs, &nplanes);
-    const long long biggest = std::max(std::max(send_dn, send_up), std::max(recv_lo, recv_hi));
-    if ((rc = slab_ensure_buffers(s, biggest * nplanes + 16))) return rc;
-    // pack
-    int plane0 = 0;
-    for (SlabPlanes& t : tabs) {
-        if (send_dn) SP_LAUNCH(s, k_slab_pack, sp_blocks(ns, B), B, 0, t, fd, posd, sel, sl->sendbuf[0] + (size_t)plane0 * send_dn, send_dn);
-        if (send_up) SP_LAUNCH(s, k_slab_pack, sp_blocks(ns, B), B, 0, t, fu, posu, sel, sl->sendbuf[1] + (size_t)plane0 * send_up, send_up);
-        plane0 += t.count;
-    }
-    if (!ghosts && (send_dn || send_up)) SP_LAUNCH(s, k_slab_kill, sp_blocks(ns, B), B, 0, fd, fu, X, sel);
-    if ((rc = slab_exchange_payload(s, send_dn, send_up, recv_lo, recv_hi, nplanes))) return rc;
-    // append arrivals after the current particles
-    const long long n_new = n + recv_lo + recv_hi;
+    const long long biggest = std::max(std::max(cap_send[0], cap_send[1]), std::max(cap_recv[0], cap_recv[1]));
+    if ((rc = slab_ensure_buffers(s, SLAB_HDR + biggest * nplanes + 16))) return rc;
+    // room for the arrivals (growing reallocates every plane: rare, and it waits for the stream)
+    const long long n_new = s->n + cap_recv[0] + cap_recv[1];
     if (n_new > s->cap) {
-        // growing reallocates every plane: finish the exchange first, then rebuild the plane tables
-        SP_CUDA(s, cudaStreamSynchronize(s->stream));
-        if ((rc = sp_ensure_capacity(s, n_new))) return rc;
+        if ((rc = sp_ensure_capacity(s, n_new + n_new / 8))) return rc;
         slab_planes(s, tabs, &nplanes);
+        X = s->fields[0].d;
+        ghost = s->fields[sl->f_ghost].d;
     }
-    // a particle that crossed the periodic boundary is shifted by one period on arrival
+    // 3: ordered pack (all planes), headers
+    if (s->n > 0 && (cap_send[0] || cap_send[1])) {
+        int plane0 = 0;
+        for (SlabPlanes& t : tabs) {
+            SP_LAUNCH(s, k_slab_sel_pack, dim3(SLAB_NB, 2), B, 0, s->g, w, X, s->cap, ghost, sl->d_cnt + 16, sl->d_cnt, t, plane0,
+                      cap_send[0] ? sl->sendbuf[0] : (double*)nullptr, cap_send[0], cap_send[1] ? sl->sendbuf[1] : (double*)nullptr,
+                      cap_send[1]);
+            plane0 += t.count;
+        }
+    } else {
+        // nothing selected on an empty system: the headers still have to say so
+        for (int d = 0; d < 2; d++)
+            if (cap_send[d]) SP_CUDA(s, cudaMemsetAsync(sl->sendbuf[d], 0, SLAB_HDR * sizeof(double), s->stream));
+    }
+    if (trace) {
+        cudaStreamSynchronize(s->stream);
+        t1 = slab_now();
+    }
+    // 4: one exchange
+    if ((rc = slab_exchange_payload(s, cap_send[0] ? SLAB_HDR + cap_send[0] * nplanes : 0,
+                                    cap_send[1] ? SLAB_HDR + cap_send[1] * nplanes : 0,
+                                    cap_recv[0] ? SLAB_HDR + cap_recv[0] * nplanes : 0,
+                                    cap_recv[1] ? SLAB_HDR + cap_recv[1] * nplanes : 0)))
+        return rc;
+    // 5: arrivals behind the alive slots; a particle that crossed the periodic boundary is shifted by one period
     const double shift_lo = (sl->periodic && sl->rank == 0) ? -sl->period : 0.0;              // came from the top rank
     const double shift_hi = (sl->periodic && sl->rank == sl->nranks - 1) ? sl->period : 0.0;  // came from rank 0
-    plane0 = 0;
-    for (SlabPlanes& t : tabs) {
-        int* ref = plane0 == 0 ? s->ref : nullptr;  // arrivals are numbered by their slot
-        if (recv_lo) SP_LAUNCH(s, k_slab_unpack, sp_blocks(recv_lo, B), B, 0, t, sl->recvbuf[0] + (size_t)plane0 * recv_lo, recv_lo, n, shift_lo, ref);
-        if (recv_hi) SP_LAUNCH(s, k_slab_unpack, sp_blocks(recv_hi, B), B, 0, t, sl->recvbuf[1] + (size_t)plane0 * recv_hi, recv_hi, n + recv_lo, shift_hi, ref);
-        plane0 += t.count;
+    {
+        int plane0 = 0;
+        for (SlabPlanes& t : tabs) {
+            if (cap_recv[0])
+                SP_LAUNCH(s, k_slab_unpack, sp_blocks(cap_recv[0], B), B, 0, t, plane0, sl->recvbuf[0], cap_recv[0], 0LL, shift_lo,
+                          s->counters, s->ref, sl->d_cnt, 0);
+            if (cap_recv[1])
+                SP_LAUNCH(s, k_slab_unpack, sp_blocks(cap_recv[1], B), B, 0, t, plane0, sl->recvbuf[1], cap_recv[1], cap_recv[0],
+                          shift_hi, s->counters, s->ref, sl->d_cnt, 1);
+            plane0 += t.count;
+        }
     }
-    if (ghosts) {
-        double* gh = s->fields[sl->f_ghost].d;
-        double* hx = s->fields[sl->f_hidx].d;
-        double* sd = s->fields[sl->f_sdn].d;
-        double* su = s->fields[sl->f_sup].d;
-        if (recv_lo) SP_LAUNCH(s, k_slab_mark, sp_blocks(recv_lo, B), B, 0, gh, hx, sd, su, n, recv_lo, 1.0);
-        if (recv_hi) SP_LAUNCH(s, k_slab_mark, sp_blocks(recv_hi, B), B, 0, gh, hx, sd, su, n + recv_lo, recv_hi, 2.0);
-    }
+    if (cap_recv[0] + cap_recv[1]) SP_LAUNCH(s, k_slab_add_alive, 1, 32, 0, s->counters, (int)(cap_recv[0] + cap_recv[1]));
     s->n = n_new;
+    s->n_exact = false;
+    s->count_pending = false;
     s->x_version++;
-    *n_recv_lo = recv_lo;
-    *n_recv_hi = recv_hi;
-    *n_sent_dn = send_dn;
-    *n_sent_up = send_up;
+    for (int d = 0; d < 2; d++) {
+        sl->cap_send[d] = cap_send[d];
+        sl->cap_recv[d] = cap_recv[d];
+    }
+    if (trace) {
+        cudaStreamSynchronize(s->stream);
+        t2 = slab_now();
+    }
+    // 6: the ordinary build on the local window (in-cell order by descending "_gid"), then ghost flags
+    if ((rc = sp_build_cells(s))) return rc;
+    if (s->n)
+        SP_LAUNCH(s, k_slab_post, sp_blocks(s->n, B), B, 0, s->key, s->fields[sl->f_ghost].d, s->ref, w.L, w.nl, s->counters,
+                  sl->d_cnt);
+    s->identity_order = true;
+    // 7: this rebuild's counts go to the ring: [0..8] slab counts, [9] alive
+    {
+        const int slot = (int)(sl->build_no % SLAB_RING);
+        int* h = sl->h_cnt + slot * 16;
+        SP_CUDA(s, cudaMemcpyAsync(h, sl->d_cnt, 9 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        SP_CUDA(s, cudaMemcpyAsync(h + 9, s->counters + SP_CNT_ALIVE, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        SP_CUDA(s, cudaEventRecord(sl->ring_ev[slot], s->stream));
+    }
+    sl->build_no++;
+    sl->history++;
+    if (trace) {
+        cudaStreamSynchronize(s->stream);
+        const double t3 = slab_now();
+        sl->trace_s[0] += t1 - t0;
+        sl->trace_s[1] += t2 - t1;
+        sl->trace_s[2] += t3 - t2;
+        if (++sl->trace_calls % 20 == 0)
+            fprintf(stderr, "[slab trace rank %d] calls=%lld select+pack=%.3f ms exchange+unpack=%.3f ms build=%.3f ms (bound n=%lld, caps %lld %lld | %lld %lld)\n",
+                    sl->rank, sl->trace_calls, 1e3 * sl->trace_s[0] / sl->trace_calls, 1e3 * sl->trace_s[1] / sl->trace_calls,
+                    1e3 * sl->trace_s[2] / sl->trace_calls, (long long)s->n, cap_send[0], cap_send[1], cap_recv[0], cap_recv[1]);
+    }
     return SP_OK;
 }
 
@@ -612,6 +807,7 @@ int32_t sp_slab_create_cell_list(sp_system* s) {
     // (ref is already the slot order unless the host added or re-ordered particles since the last rebuild)
     if (s->n && !sl->sel_valid) SP_LAUNCH(s, k_slab_iota, sp_blocks(s->n, 256), 256, 0, s->ref, s->n);
     if ((rc = sp_build_cells(s))) return rc;
+    if ((rc = sp_settle(s))) return rc;
     if (s->n) SP_LAUNCH(s, k_slab_iota, sp_blocks(s->n, 256), 256, 0, s->ref, s->n);
     s->identity_order = true;
     if (trace) {

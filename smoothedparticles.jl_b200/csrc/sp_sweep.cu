@@ -25,7 +25,8 @@ struct SweepCtx {
     float thr;                  // pre-filter threshold on the FP32 squared distance in cell units: above = not a neighbour
     float thr_lo;               // at or below = certainly a neighbour (k_nbr_build)
     int capk;                   // entries per target in the cached neighbour lists (multiple of 32)
-    int n;
+    int n;                      // slots the launch covers
+    const int* alive;           // device: slots [0, *alive) are alive, [*alive, n) is the dead tail of culled particles
 };
 
 // Visit every candidate slot j of particle (xi,yi,zi): f(j, dx, dy, dz, d2).
@@ -86,7 +87,7 @@ __device__ __forceinline__ double sp_sqrt_fast(double a);
 template <class Op, bool STRICT>
 __global__ void __launch_bounds__(128) k_sweep(SpGrid g, SweepCtx c, typename Op::Params P, int self_flag) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= *c.alive) return;  // the dead tail [alive, n) takes no part (sp_internal.cuh)
     if (!Op::active(P, i)) return;
     const double xi = c.x[i], yi = c.y[i], zi = c.z[i];
     typename Op::PS p;
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(TP, MINB) k_sweep_tile(SpGrid g, SweepCtx c, t
 
     const int tid = threadIdx.x;
     const int i = blockIdx.x * TP + tid;
-    const bool act = (i < c.n) && Op::active(P, i);
+    const bool act = (i < *c.alive) && Op::active(P, i);
     double xi = 0.0, yi = 0.0, zi = 0.0;
     float ui = 0.f, vi = 0.f, wi = 0.f;
     long long key = 0;
@@ -460,7 +461,7 @@ template <int G>
 __global__ void __launch_bounds__(128, 5) k_nbr_build(SpGrid g, SweepCtx c, int* __restrict__ cnt, int* __restrict__ ids,
                                                       int* __restrict__ max_cnt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= *c.alive) return;  // the dead tail [alive, n) takes no part (sp_internal.cuh)
     const float ui = c.ux[i], vi = c.uy[i], wi = c.uz[i];
     const double T2 = g.T2;
     unsigned long long ui2, vi2, wi2, thr2, thr_lo2;
@@ -593,7 +594,7 @@ __global__ void __launch_bounds__(128, 6) k_sweep_list(SpGrid g, SweepCtx c, con
     const int i = (int)(gt / G);
     const int sub = (int)(gt % G);
     // whole groups leave together (i is uniform within a group), so the group shuffles below are safe
-    if (i >= c.n) return;
+    if (i >= *c.alive) return;  // the dead tail [alive, n) takes no part (sp_internal.cuh)
     if (!Op::active(P, i)) return;
     const double xi = c.x[i], yi = c.y[i], zi = c.z[i];
     typename Op::PS p;
@@ -683,7 +684,7 @@ template <class Op, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_nbr_build_sweep(SpGrid g, SweepCtx c, int* cnt, int* ids, int* max_cnt,
                                                                typename Op::Params P, int self_flag) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= *c.alive) return;  // the dead tail [alive, n) takes no part (sp_internal.cuh)
     const int capk = c.capk;
     int* col = ids + ((size_t)(i >> 5) * capk << 5) + (i & 31);
     const double xi = c.x[i], yi = c.y[i], zi = c.z[i];
@@ -833,9 +834,9 @@ __global__ void __launch_bounds__(128, MINB) k_nbr_build_sweep(SpGrid g, SweepCt
 }
 
 template <class U>
-__global__ void __launch_bounds__(256) k_unary(typename U::Params P, int n) {
+__global__ void __launch_bounds__(256) k_unary(typename U::Params P, const int* __restrict__ alive) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) U::apply(P, i);
+    if (i < *alive) U::apply(P, i);
 }
 
 #define TILE_TP 128
@@ -895,6 +896,7 @@ static void sp_sweep_ctx(sp_system* s, SweepCtx& c) {
     c.thr = c.thr_lo = 0.f;
     c.capk = s->nbr_capk;
     c.n = (int)s->n;
+    c.alive = sp_alive(s);
 }
 
 // FP32 pre-filter inputs: coordinates in cell units u = (x - lo)/h and thresholds that can never misclassify.
@@ -938,7 +940,7 @@ static int sp_nbr_prepare(sp_system* s, SweepCtx& c, bool* need_build) {
     int rc = sp_ensure_prefilter(s, c);
     if (rc) return rc;
     const bool rebuild = s->nbr_version != s->x_version || s->nbr_n != s->n || !s->nbr_ids || s->nbr_cap != s->cap;
-    if (rebuild && s->nbr_max_pending && cudaEventQuery(s->ev_nbr) == cudaSuccess) {
+    if (rebuild && !s->capturing && s->nbr_max_pending && cudaEventQuery(s->ev_nbr) == cudaSuccess) {
         // the previous build met targets with more neighbours than the lists hold (they were swept by the exact scan):
         // give the lists room before building them again
         s->nbr_max_pending = false;
@@ -1075,7 +1077,7 @@ static int dispatch_kernel(sp_system* s, int kernel, double h, int flags, MakePa
 template <class U>
 static int launch_unary(sp_system* s, const typename U::Params& P) {
     if (s->n == 0) return SP_OK;
-    SP_LAUNCH(s, (k_unary<U>), sp_blocks(s->n, 256), 256, 0, P, (int)s->n);
+    SP_LAUNCH(s, (k_unary<U>), sp_blocks(s->n, 256), 256, 0, P, sp_alive(s));
     return SP_OK;
 }
 
@@ -1884,7 +1886,7 @@ __global__ void __launch_bounds__(128) k_poisson_coeffs(SweepCtx c, const int* _
                                                         double C_free, SpKC kc, double* __restrict__ aval,
                                                         double* __restrict__ diag, int* __restrict__ overflow) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= *c.alive) return;  // the dead tail [alive, n) takes no part (sp_internal.cuh)
     double Aii = h2 * L[i];
     if (type[i] == 0.0) Aii += C_free * fmax(lambda[i], 0.0);
     diag[i] = Aii;
@@ -1990,7 +1992,7 @@ int sp_poisson_apply_impl(sp_system* s, const int32_t* F, int32_t nf, const doub
 // ------------------------------------------------------------------ neighbour-list export (parity view)
 __global__ void k_nbr_count(SpGrid g, SweepCtx c, const int* ref, long long* counts) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= *c.alive) return;  // the dead tail [alive, n) takes no part (sp_internal.cuh)
     int cnt = 0;
     sp_for_candidates<true>(g, c, c.x[i], c.y[i], c.z[i], [&](int j, double, double, double, double d2) {
         if (d2 > g.T2 || j == i) return;
@@ -2000,7 +2002,7 @@ __global__ void k_nbr_count(SpGrid g, SweepCtx c, const int* ref, long long* cou
 }
 __global__ void k_nbr_fill(SpGrid g, SweepCtx c, const int* ref, const long long* offsets, long long* ids) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= *c.alive) return;  // the dead tail [alive, n) takes no part (sp_internal.cuh)
     long long o = offsets[ref[i]];
     sp_for_candidates<true>(g, c, c.x[i], c.y[i], c.z[i], [&](int j, double, double, double, double d2) {
         if (d2 > g.T2 || j == i) return;
@@ -2011,13 +2013,13 @@ __global__ void k_nbr_fill(SpGrid g, SweepCtx c, const int* ref, const long long
 // the lists the default sweeps replay (cached), in their visiting order
 __global__ void k_cache_count(SpGrid g, SweepCtx c, const int* cnt, const int* ref, long long* counts) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= *c.alive) return;  // the dead tail [alive, n) takes no part (sp_internal.cuh)
     counts[ref[i]] = cnt[i];
 }
 __global__ void k_cache_fill(SpGrid g, SweepCtx c, const int* cnt, const int* lists, const int* ref,
                              const long long* offsets, long long* ids) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    if (i >= *c.alive) return;  // the dead tail [alive, n) takes no part (sp_internal.cuh)
     long long o = offsets[ref[i]];
     const int n_nb = cnt[i];
     if (n_nb <= c.capk) {
@@ -2094,6 +2096,7 @@ int32_t sp_get_sweep_neighbour_lists(sp_system* s, int64_t* offsets, int64_t* id
     if (!s || !offsets) return SP_ERR_INVALID;
     if (!s->have_cells) return sp_fail(s, SP_ERR_STATE, "no cell list: call sp_create_cell_list first");
     SP_CUDA(s, cudaSetDevice(s->device));
+    if (int rcs = sp_settle(s)) return rcs;
     const long long n = s->n;
     offsets[0] = 0;
     if (n == 0) return SP_OK;
@@ -2132,6 +2135,7 @@ int32_t sp_get_neighbour_lists(sp_system* s, int64_t* offsets, int64_t* ids, int
     if (!s || !offsets) return SP_ERR_INVALID;
     if (!s->have_cells) return sp_fail(s, SP_ERR_STATE, "no cell list: call sp_create_cell_list first");
     SP_CUDA(s, cudaSetDevice(s->device));
+    if (int rcs = sp_settle(s)) return rcs;
     const long long n = s->n;
     offsets[0] = 0;
     if (n == 0) return SP_OK;

@@ -309,6 +309,7 @@ int32_t sp_destroy(sp_system* s) {
     if (!s) return SP_OK;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    sp_program_free(s);
     sp_slab_free(s);
     for (SpField& f : s->fields) {
         sp_dfree(s, f.d);
@@ -398,17 +399,19 @@ int32_t sp_resize(sp_system* s, int64_t n) {
     if (!s || n < 0) return SP_ERR_INVALID;
     if (n >= (1LL << 31) - 256) return sp_fail(s, SP_ERR_INVALID, "particle count exceeds 31 bits");
     SP_CUDA(s, cudaSetDevice(s->device));
+    int rc = sp_settle(s);
+    if (rc) return rc;
     if (n == s->n) return SP_OK;
     sp_slab_host_touched(s);
     s->x_version++;
     if (n < s->n) {
-        int rc = restore_reference_order(s);
+        rc = restore_reference_order(s);
         if (rc) return rc;
         s->n = n;
         s->have_cells = false;
-        return SP_OK;
+        return sp_publish_count(s);
     }
-    int rc = sp_ensure_capacity(s, n);
+    rc = sp_ensure_capacity(s, n);
     if (rc) return rc;
     for (SpField& f : s->fields)
         for (int c = 0; c < f.ncomp; c++)
@@ -416,17 +419,23 @@ int32_t sp_resize(sp_system* s, int64_t n) {
     SP_LAUNCH(s, k_iota_ref, sp_blocks(n - s->n, 256), 256, 0, s->ref, (long long)s->n, (long long)n);
     s->n = n;
     s->have_cells = false;
-    return SP_OK;
+    return sp_publish_count(s);
 }
 
 int32_t sp_num_particles(sp_system* s, int64_t* n) {
     if (!s || !n) return SP_ERR_INVALID;
+    SP_CUDA(s, cudaSetDevice(s->device));
+    int rc = sp_settle(s);
+    if (rc) return rc;
     *n = s->n;
     return SP_OK;
 }
 
 int32_t sp_num_removed(sp_system* s, int64_t* n_removed) {
     if (!s || !n_removed) return SP_ERR_INVALID;
+    SP_CUDA(s, cudaSetDevice(s->device));
+    int rc = sp_settle(s);
+    if (rc) return rc;
     *n_removed = s->n_removed;
     return SP_OK;
 }
@@ -434,6 +443,8 @@ int32_t sp_num_removed(sp_system* s, int64_t* n_removed) {
 int32_t sp_upload(sp_system* s, int32_t fid, const double* host, int64_t n, int32_t layout) {
     if (!s || !host) return SP_ERR_INVALID;
     if (fid < 0 || fid >= (int)s->fields.size()) return sp_fail(s, SP_ERR_INVALID, "bad field id");
+    SP_CUDA(s, cudaSetDevice(s->device));
+    if (int rcs = sp_settle(s)) return rcs;
     if (n != s->n) return sp_fail(s, SP_ERR_INVALID, "upload: n differs from the particle count");
     if (layout != SP_LAYOUT_AOS && layout != SP_LAYOUT_SOA) return sp_fail(s, SP_ERR_INVALID, "bad layout");
     if (n == 0) return SP_OK;
@@ -461,6 +472,8 @@ int32_t sp_upload(sp_system* s, int32_t fid, const double* host, int64_t n, int3
 int32_t sp_download(sp_system* s, int32_t fid, double* host, int64_t n, int32_t layout) {
     if (!s || !host) return SP_ERR_INVALID;
     if (fid < 0 || fid >= (int)s->fields.size()) return sp_fail(s, SP_ERR_INVALID, "bad field id");
+    SP_CUDA(s, cudaSetDevice(s->device));
+    if (int rcs = sp_settle(s)) return rcs;
     if (n != s->n) return sp_fail(s, SP_ERR_INVALID, "download: n differs from the particle count");
     if (layout != SP_LAYOUT_AOS && layout != SP_LAYOUT_SOA) return sp_fail(s, SP_ERR_INVALID, "bad layout");
     if (n == 0) return SP_OK;
@@ -521,6 +534,8 @@ int32_t sp_launch_count(sp_system* s, int64_t* launches) {
 int32_t sp_get_cell_keys(sp_system* s, int64_t* keys, int64_t n) {
     if (!s || !keys) return SP_ERR_INVALID;
     if (!s->have_cells) return sp_fail(s, SP_ERR_STATE, "no cell list: call sp_create_cell_list first");
+    SP_CUDA(s, cudaSetDevice(s->device));
+    if (int rcs = sp_settle(s)) return rcs;
     if (n != s->n) return sp_fail(s, SP_ERR_INVALID, "n differs from the particle count");
     if (n == 0) return SP_OK;
     SP_CUDA(s, cudaSetDevice(s->device));
@@ -536,6 +551,7 @@ int32_t sp_get_cell_list(sp_system* s, int64_t* offsets, int64_t* members) {
     if (!s || !offsets || !members) return SP_ERR_INVALID;
     if (!s->have_cells) return sp_fail(s, SP_ERR_STATE, "no cell list: call sp_create_cell_list first");
     SP_CUDA(s, cudaSetDevice(s->device));
+    if (int rcs = sp_settle(s)) return rcs;
     const long long K = s->g.key_max;
     std::vector<int> cs(K + 1), rf(s->n);
     SP_CUDA(s, cudaMemcpyAsync(cs.data(), s->cell_start + 1, (size_t)(K + 1) * sizeof(int), cudaMemcpyDeviceToHost, s->stream));

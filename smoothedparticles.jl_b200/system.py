@@ -254,8 +254,14 @@ class ParticleSystem:
         P = _farr(A.params)
         iters = C.c_int64()
         resid = C.c_double()
-        abi.check(self._lib.sp_poisson_cg(self._h, abi.ptr_i32(F), len(F), abi.ptr_f64(P), len(P), float(reltol),
-                                          float(abstol), int(maxiter), C.byref(iters), C.byref(resid)), self._h)
+        rc = self._lib.sp_poisson_cg(self._h, abi.ptr_i32(F), len(F), abi.ptr_f64(P), len(P), float(reltol),
+                                     float(abstol), int(maxiter), C.byref(iters), C.byref(resid))
+        # IterativeSolvers.cg hands back its last iterate when maxiter is reached, without an error, and the script keeps
+        # stepping (collapse_dry_implicit.jl:223-227): SP_ERR_NOT_CONVERGED is a soft status here, P_out holds that
+        # iterate, and the caller reads `last_cg_converged`
+        self.last_cg_converged = rc != K["SP_ERR_NOT_CONVERGED"]
+        if rc != K["SP_ERR_NOT_CONVERGED"]:
+            abi.check(rc, self._h)
         return iters.value, resid.value
 
     def run_program(self, program: int, fields: Sequence[str], params: Sequence[float], nsteps: int):

@@ -14,6 +14,7 @@ from parity import RTOL_STEP, assert_fields_close, neighbour_sets_equal, rel_err
 
 pytestmark = pytest.mark.gpu
 K = sp.K
+RTOL_LOOP = 1e-9   # N-step runs: bounded drift of the per-step 1e-10
 
 
 def _pair(case):
@@ -451,15 +452,80 @@ def test_collision_2d_reference_assertions_on_device():
     assert x_mid < 1e-5
 
 
-def test_run_program_equals_per_call_path():
+@pytest.mark.parametrize("nsteps", [5, 13, 14])
+def test_run_program_equals_per_call_path(nsteps):
+    # 5 steps: the program issues the launches one by one; 13 / 14 steps: steps 2.. are replayed from a CUDA graph of two
+    # steps (odd and even numbers of graph units + eager remainder).  Same kernels, same order: bit-identical.
     case = configs.collapse3d()
     a = case.make(ParticleSystem)
     b = case.make(ParticleSystem)
-    for _ in range(5):
+    for _ in range(nsteps):
         case.step(a)
-    b.run_program(case.program, case.program_fields, case.program_params, 5)
+    b.run_program(case.program, case.program_fields, case.program_params, nsteps)
+    assert len(a) == len(b) == case.n
     for nm in ("x", "v", "rho", "P", "Dv"):
         assert np.array_equal(a.get(nm), b.get(nm)), nm
+    # a second batch on the same system re-uses (or re-captures) the graph and continues exactly
+    for _ in range(9):
+        case.step(a)
+    b.run_program(case.program, case.program_fields, case.program_params, 9)
+    for nm in ("x", "v", "rho", "P", "Dv"):
+        assert np.array_equal(a.get(nm), b.get(nm)), nm
+
+
+@pytest.mark.parametrize("nsteps", [4, 12])
+def test_run_program_2d_equals_per_call_path_and_oracle(nsteps):
+    # SP_PROGRAM_WCSPH_2D = the loop of examples/collapse_dry.jl:203-211 (two cell lists per step); 12 steps go through
+    # the CUDA graph.  Bit-identical to the per-call path, <= 1e-9 to the oracle running the same loop.
+    case = configs.collapse_dry()
+    a, ora = _pair(case)
+    b = case.make(ParticleSystem)
+    for s_ in (a, b, ora):
+        case.prologue(s_)
+    for _ in range(nsteps):
+        case.step(a)
+        case.step(ora)
+    b.run_program(case.program, case.program_fields, case.program_params, nsteps)
+    assert len(a) == len(b) == len(ora)
+    for nm in ("x", "v", "rho", "P", "Dv", "Drho"):
+        assert np.array_equal(a.get(nm), b.get(nm)), nm
+    assert_fields_close(b, ora, ["x", "v", "rho", "P", "Dv"], rtol=RTOL_LOOP, what=f"2-D program, {nsteps} steps")
+    ora2 = case.make(OracleSystem)
+    case.prologue(ora2)
+    ora2.run_program(case.program, case.program_fields, case.program_params, nsteps)
+    for nm in ("x", "v", "rho", "P"):
+        assert np.array_equal(ora.get(nm), ora2.get(nm)), nm
+
+
+@pytest.mark.parametrize("shape", [(22, 20, 18), (48, 44, 36)])   # below / above the single-CTA renumbering limit (65 536)
+def test_particles_leaving_the_domain_inside_a_graph_run(shape):
+    # removal (core.jl:64-81) with the culled count kept on the device: the outer shell of a lattice block flies apart and
+    # leaves the domain (lattice bounds +- h) a few particles per step while the step loop is replayed from a CUDA graph.
+    # Count, post-removal numbering and fields must equal the oracle's, which removes particle by particle with the
+    # swap-with-tail rule.  (The shell moves AWAY from the block: no violent collisions that would amplify rounding.)
+    case = configs.lattice_box(shape, jitter=0.1, dr=5e-3, seed=3)
+    c = case.consts
+    x, v = case.init["x"], case.init["v"].copy()
+    rng = np.random.default_rng(11)
+    speed = case.h / c["dt"]                                   # one cell per step
+    lo, hi = x.min(axis=0), x.max(axis=0)
+    for a in range(3):
+        for side, sgn in ((lo[a], -1.0), (hi[a], 1.0)):
+            shell = np.abs(x[:, a] - side) < 0.6 * c["dr"]
+            v[shell, a] = sgn * speed * rng.uniform(0.08, 0.6, int(shell.sum()))   # out after 2-13 of the 14 steps
+    case.init["v"] = v
+    dev, ora = _pair(case)
+    n0 = len(dev)
+    dev.run_program(case.program, case.program_fields, case.program_params, 14)
+    for _ in range(14):
+        case.step(ora)
+    assert len(dev) == len(ora)
+    assert dev.n_removed == n0 - len(dev) and dev.n_removed > 1000
+    # the survivors carry the reference's post-removal numbering: compare in reference order
+    dev.create_cell_list()
+    ora.create_cell_list()
+    _check_cells(dev, ora)
+    assert_fields_close(dev, ora, ["x", "v", "rho", "P"], rtol=RTOL_LOOP, what="removal inside a graph run")
 
 
 def test_energy_and_front_reductions():
