@@ -152,8 +152,8 @@ def run_slab_workload(args, workload, UNIT, ClockSampler, e2e=True, breakdown=Tr
 
     if breakdown:
         # per-kernel breakdown on this rank (same steps, per-call timing)
-        acc = {k: 0.0 for k in ("move", "cell_list+halo", "balance_of_mass", "find_pressure", "halo_refresh",
-                                "internal_force", "accelerate")}
+        acc = {k: 0.0 for k in ("move", "cell_list+halo", "balance_of_mass", "find_pressure", "internal_force",
+                                "accelerate")}
 
         def timed(name, fn):
             fn()
@@ -164,7 +164,6 @@ def run_slab_workload(args, workload, UNIT, ClockSampler, e2e=True, breakdown=Tr
             timed("cell_list+halo", sysd.create_cell_list)
             timed("balance_of_mass", lambda: sysd.apply(o["bom"]))
             timed("find_pressure", lambda: sysd.apply(o["fp"]))
-            timed("halo_refresh", lambda: sysd.halo_refresh("rho", "P"))
             timed("internal_force", lambda: sysd.apply(o["force"]))
             timed("accelerate", lambda: sysd.apply(o["acc"]))
             timed("accelerate", lambda: sysd.apply(o["acc"]))

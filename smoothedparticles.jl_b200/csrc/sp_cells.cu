@@ -240,16 +240,29 @@ __global__ void k_scatter(const int* __restrict__ key, const int* __restrict__ o
 
 // Order every cell by descending reference index: perm[cell_start + rank] = slot.  Only the n - trash kept slots; the
 // trash cell (last in the scatter order) is left alone.
+// On a slab system (gid != nullptr) the order inside a cell is by descending GLOBAL id instead — the reference numbering
+// has no meaning across ranks, and an order that every rank agrees on makes a rank's boundary layers and its
+// neighbour's ghost layers identical slot sequences (sp_slab.cu).
 __global__ void k_rank(const int* __restrict__ key, const int* __restrict__ ref, const int* __restrict__ cell_start,
-                       const int* __restrict__ member, int* __restrict__ perm, long long n, const int* __restrict__ counters) {
+                       const int* __restrict__ member, int* __restrict__ perm, long long n, const int* __restrict__ counters,
+                       const double* __restrict__ gid) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n - counters[SP_CNT_TRASH]) return;
     const int s = member[t];
     const int k = key[s];
-    const int mine = ref[s];
     const int b = cell_start[k], e = cell_start[k + 1];
     int rank = 0;
-    for (int u = b; u < e; u++) rank += (ref[member[u]] > mine);
+    if (gid) {
+        const double mine = gid[s];
+        for (int u = b; u < e; u++) {
+            const int o = member[u];
+            const double g = gid[o];
+            rank += (g > mine) || (g == mine && ref[o] > ref[s]);  // equal ids cannot happen; keep it a total order anyway
+        }
+    } else {
+        const int mine = ref[s];
+        for (int u = b; u < e; u++) rank += (ref[member[u]] > mine);
+    }
     perm[b + rank] = s;
 }
 // close the build: publish the new alive count and the removal statistics
@@ -396,7 +409,8 @@ int sp_build_cells(sp_system* s) {
             SP_LAUNCH(s, k_apply_newref, G, B, 0, s->key, (int)K + 1, s->ref, newref, N, s->counters);
         }
     }
-    SP_LAUNCH(s, k_rank, sp_blocks(N, B), B, 0, s->key, s->ref, s->cell_start, s->tmp_slot, s->perm, N, s->counters);
+    SP_LAUNCH(s, k_rank, sp_blocks(N, B), B, 0, s->key, s->ref, s->cell_start, s->tmp_slot, s->perm, N, s->counters,
+              sp_slab_gid(s));
     rc = sp_permute_all(s, N);
     if (rc) return rc;
     SP_LAUNCH(s, k_finish_build, 1, 32, 0, s->counters, N);

@@ -299,6 +299,10 @@ extern "C" int32_t sp_poisson_cg(sp_system* s, const int32_t* F, int32_t nf, con
         residual = std::sqrt(res2);
         it++;
     }
+    if (s->slab) {  // the ghost copies of the solution come from their owners (internal_force! reads them next)
+        const int32_t fp[1] = {F[5]};
+        if ((rc = sp_slab_halo_refresh(s, fp, 1))) return rc;
+    }
     if ((rc = sp_time_end(s))) return rc;
     if (iters) *iters = it;
     if (resid) *resid = residual;

@@ -128,8 +128,8 @@ extern "C" int32_t sp_run_program(sp_system* s, int32_t program, const int32_t* 
 
 // One time step.  `first`: the step opens a run (3-D: the run's first move! is its own kernel); `last`: it closes one
 // (3-D: the two accelerate! are not fused with the next step's move!).
-// On a slab system (sp_slab.cu) the cell-list build is the slab rebuild (migration + ghost halos + local build) and
-// the ghost copies of rho and P are refreshed after find_pressure! (ghosts cannot integrate their own Drho).
+// On a slab system (sp_slab.cu) the cell-list build is the slab rebuild (one exchange: migration + two ghost layers per
+// side + local build).
 static int run_step(sp_system* s, int32_t program, const int32_t* F, const double* P, bool first, bool last) {
     int rc;
     const bool slab = s->slab != nullptr;
@@ -139,7 +139,6 @@ static int run_step(sp_system* s, int32_t program, const int32_t* F, const doubl
                   f_mv[4] = {x, v, Dv, ty}, f_ac[3] = {v, Dv, ty};
     const double p_bom[4] = {kernel, m, h, two_nu}, p_fp[4] = {dt, c2, rho0, 0.0}, p_if[5] = {kernel, m, h, mu, rho0},
                  p_ac[4] = {0.5 * dt, P[8], P[9], P[10]};
-    const int32_t f_halo[2] = {rho, Pr};
 #define STEP(call) \
     if ((rc = (call))) return rc;
     if (program == SP_PROGRAM_WCSPH_3D) {  // examples/collapse3d.jl:136-150
@@ -156,15 +155,10 @@ static int run_step(sp_system* s, int32_t program, const int32_t* F, const doubl
             STEP(sp_build_cells(s));
         }
         STEP(sp_apply_impl(s, SP_OP_BALANCE_OF_MASS, f_bom, 4, p_bom, 4, 0));
-        if (slab) {
-            // the ghosts' rho and P come from their owners, so P/rho^2 is evaluated after the refresh
-            STEP(sp_apply_impl(s, SP_OP_FIND_PRESSURE, f_fp, 3, p_fp, 4, 0));
-            STEP(sp_slab_halo_refresh(s, f_halo, 2));
-            STEP(sp_apply_impl(s, SP_OP_INTERNAL_FORCE, f_if, 6, p_if, 5, 0));
-        } else {
-            STEP(sp_find_pressure_pr_impl(s, f_fp, p_fp));
-            STEP(sp_apply_impl(s, SP_OP_INTERNAL_FORCE, f_if, 6, p_if, 5, SP_FLAG_INTERNAL_PR_READY));
-        }
+        // (slab systems: the two ghost layers per side make the inner one integrate its own density — same neighbours,
+        // same order as on its owner — so rho and P of every ghost a force sum reads are already right: no refresh)
+        STEP(sp_find_pressure_pr_impl(s, f_fp, p_fp));
+        STEP(sp_apply_impl(s, SP_OP_INTERNAL_FORCE, f_if, 6, p_if, 5, SP_FLAG_INTERNAL_PR_READY));
         if (!last) {
             STEP(sp_kick_kick_move_impl(s, f_kkm, p_kkm));
         } else {

@@ -254,8 +254,6 @@ __global__ void __launch_bounds__(256) k_slab_sel_count(SpGrid g, SlabWin w, con
     const long long b = lo + (long long)blockIdx.x * chunk, e = min(b + chunk, hi);
     int mine = 0;
     for (long long s = b + threadIdx.x; s < e; s += blockDim.x) mine += slab_selected(g, x, cap, ghost, w.nl, dir, s) ? 1 : 0;
-    const int total = __syncthreads_count(0) * 0 + 0;  // (placeholder to keep the barrier structure simple)
-    (void)total;
     __shared__ int sm[256];
     sm[threadIdx.x] = mine;
     __syncthreads();
@@ -344,8 +342,12 @@ __global__ void k_slab_unpack(SlabPlanes tab, int plane0, const double* buf, lon
             if (c == tab.axis_plane) v += shift;
             tab.p[c][slot] = v;
         }
-    } else if (tab.x_plane >= 0)
-        tab.p[tab.x_plane][slot] = nan("");
+    } else {
+        // padding: a dead slot (NaN position, culled by the build).  Its other planes are cleared: a field the library
+        // knows to be zero everywhere is not permuted by the build, so no stale value may sit in a slot below the new
+        // alive count
+        for (int c = 0; c < tab.count; c++) tab.p[c][slot] = c == tab.x_plane ? nan("") : 0.0;
+    }
     if (plane0 == 0) ref[slot] = (int)slot;
 }
 __global__ void k_slab_add_alive(int* counters, int add) {
@@ -577,8 +579,10 @@ static int slab_rebuild(sp_system* s) {
         SP_LAUNCH(s, k_slab_kill_ghosts, 1184, B, 0, w, X, ghost);
         // 2: selection: counts per block, one scan
         SP_LAUNCH(s, k_slab_sel_count, dim3(SLAB_NB, 2), B, 0, s->g, w, X, s->cap, ghost, sl->d_cnt + 16);
-        SP_LAUNCH(s, k_slab_sel_scan, 1, SLAB_NB, 0, sl->d_cnt + 16, sl->d_cnt, steady ? cap_send[0] : -1LL,
-                  steady ? cap_send[1] : -1LL);
+        // (no capacity to check in the bootstrap rebuilds — they size the messages from the counts — nor towards a side
+        // without a neighbour, whose selection is never sent)
+        SP_LAUNCH(s, k_slab_sel_scan, 1, SLAB_NB, 0, sl->d_cnt + 16, sl->d_cnt, steady && below >= 0 ? cap_send[0] : -1LL,
+                  steady && above >= 0 ? cap_send[1] : -1LL);
     }
     if (!steady) {
         long long n_dn = 0, n_up = 0, fb = 0, fa = 0;
@@ -706,7 +710,12 @@ int32_t sp_slab_init(sp_system* s, const uint8_t id[128], int32_t rank, int32_t 
     if (!nccl_load()) return sp_fail(s, SP_ERR_NCCL, g_nccl.err);
     SpGrid& g = s->g;
     const int axis = g.dim == 2 ? 1 : 2;  // slowest key axis
-    if (g.lim[axis] < nranks) return sp_fail(s, SP_ERR_INVALID, "fewer cell layers along the slab axis than ranks");
+    // three owned layers per rank: the two boundary layers facing one neighbour must not receive migrants from the other
+    // (that is what makes a rank's boundary layers and its neighbour's ghost layers the same particle sets)
+    if (nranks > 1 || periodic) {
+        if (g.lim[axis] < 3LL * nranks)
+            return sp_fail(s, SP_ERR_INVALID, "fewer than three cell layers per rank along the slab axis");
+    }
     SlabState* sl = new SlabState();
     sl->rank = rank;
     sl->nranks = nranks;
@@ -727,19 +736,28 @@ int32_t sp_slab_init(sp_system* s, const uint8_t id[128], int32_t rank, int32_t 
         delete sl;
         return sp_fail(s, SP_ERR_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
     }
-    SP_CUDA(s, sp_dmalloc(&sl->d_cnt, 16 * sizeof(int)));
-    SP_CUDA(s, cudaHostAlloc(&sl->h_cnt, 16 * sizeof(int), cudaHostAllocDefault));
-    // local cell window: owned layers [c0, c1) plus one ghost layer per side
-    g.phase[axis] = sl->gphase + sl->c0 - 1;
-    g.lim[axis] = (sl->c1 - sl->c0) + 2;
+    SP_CUDA(s, sp_dmalloc(&sl->d_cnt, (16 + 2 * SLAB_NB) * sizeof(int)));
+    SP_CUDA(s, cudaMemset(sl->d_cnt, 0, (16 + 2 * SLAB_NB) * sizeof(int)));
+    SP_CUDA(s, cudaHostAlloc(&sl->h_cnt, (SLAB_RING * 16 + 16) * sizeof(int), cudaHostAllocDefault));
+    memset(sl->h_cnt, 0, (SLAB_RING * 16 + 16) * sizeof(int));
+    for (int k = 0; k < SLAB_RING; k++) SP_CUDA(s, cudaEventCreateWithFlags(&sl->ring_ev[k], cudaEventDisableTiming));
+    // local cell window: owned layers [c0, c1) plus SLAB_W ghost layers per side
+    g.phase[axis] = sl->gphase + sl->c0 - SLAB_W;
+    g.lim[axis] = (sl->c1 - sl->c0) + 2 * SLAB_W;
     g.key_max = g.lim[0] * g.lim[1] * g.lim[2];
-    // the local window (with its two ghost layers) can be larger than the global grid when nranks is small
+    // the local window (with its ghost layers) can be larger than the global grid when nranks is small
     SP_CUDA(s, sp_dfree(s, s->cell_start));
     SP_CUDA(s, sp_dfree(s, s->cell_fill));
     s->cell_start = s->cell_fill = nullptr;
     SP_CUDA(s, sp_dmalloc(&s->cell_start, (size_t)(g.key_max + 3) * sizeof(int)));
     SP_CUDA(s, sp_dmalloc(&s->cell_fill, (size_t)(g.key_max + 3) * sizeof(int)));
     SP_CUDA(s, cudaMemset(s->cell_start, 0, (size_t)(g.key_max + 3) * sizeof(int)));
+    if (s->scan_tmp_len < (g.key_max + 3) / 1024 + 1024) {
+        SP_CUDA(s, sp_dfree(s, s->scan_tmp));
+        s->scan_tmp = nullptr;
+        s->scan_tmp_len = (g.key_max + 3) / 1024 + 2048;
+        SP_CUDA(s, sp_dmalloc(&s->scan_tmp, (size_t)s->scan_tmp_len * sizeof(int)));
+    }
     g.slab_axis = axis;
     g.slab_periodic = sl->periodic;
     if (g.dim == 3) {
@@ -752,12 +770,8 @@ int32_t sp_slab_init(sp_system* s, const uint8_t id[128], int32_t rank, int32_t 
     int rc;
     if ((rc = sp_add_field(s, "_ghost", 1, &fid))) return rc;
     sl->f_ghost = fid;
-    if ((rc = sp_add_field(s, "_hidx", 1, &fid))) return rc;
-    sl->f_hidx = fid;
-    if ((rc = sp_add_field(s, "_sdn", 1, &fid))) return rc;
-    sl->f_sdn = fid;
-    if ((rc = sp_add_field(s, "_sup", 1, &fid))) return rc;
-    sl->f_sup = fid;
+    if ((rc = sp_add_field(s, "_gid", 1, &fid))) return rc;
+    sl->f_gid = fid;
     return SP_OK;
 }
 
@@ -777,71 +791,9 @@ int32_t sp_slab_create_cell_list(sp_system* s) {
     if (!s) return SP_ERR_INVALID;
     if (!s->slab) return sp_fail(s, SP_ERR_STATE, "not a slab system");
     SP_CUDA(s, cudaSetDevice(s->device));
-    SlabState* sl = s->slab;
     int rc = sp_time_begin(s);
     if (rc) return rc;
-    long long rl, rh, sd, su;
-    const bool trace = slab_trace_on();
-    double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
-    if (trace) {
-        cudaStreamSynchronize(s->stream);
-        t0 = slab_now();
-    }
-    // 1+2: drop old ghosts, migrate
-    if ((rc = slab_round(s, false, &rl, &rh, &sd, &su))) return rc;
-    if (trace) {
-        cudaStreamSynchronize(s->stream);
-        t1 = slab_now();
-    }
-    // 3: ghost halo
-    if ((rc = slab_round(s, true, &rl, &rh, &sd, &su))) return rc;
-    if (trace) {
-        cudaStreamSynchronize(s->stream);
-        t2 = slab_now();
-    }
-    sl->n_ghost[0] = rl;
-    sl->n_ghost[1] = rh;
-    sl->n_send[0] = sd;
-    sl->n_send[1] = su;
-    // 4: local build; the reference numbering has no meaning across ranks: slots are renumbered in place
-    // (ref is already the slot order unless the host added or re-ordered particles since the last rebuild)
-    if (s->n && !sl->sel_valid) SP_LAUNCH(s, k_slab_iota, sp_blocks(s->n, 256), 256, 0, s->ref, s->n);
-    if ((rc = sp_build_cells(s))) return rc;
-    if ((rc = sp_settle(s))) return rc;
-    if (s->n) SP_LAUNCH(s, k_slab_iota, sp_blocks(s->n, 256), 256, 0, s->ref, s->n);
-    s->identity_order = true;
-    if (trace) {
-        cudaStreamSynchronize(s->stream);
-        t3 = slab_now();
-    }
-    // owned count, and the slot window of the next rebuild's selection passes (three cell layers per side)
-    SP_CUDA(s, cudaMemsetAsync(sl->d_cnt + 8, 0, sizeof(int), s->stream));
-    if (s->n)
-        SP_LAUNCH(s, k_slab_count_owned, sp_blocks(s->n, 256), 256, 0, s->fields[sl->f_ghost].d, s->n, sl->d_cnt + 8);
-    SP_CUDA(s, cudaMemcpyAsync(sl->h_cnt + 8, sl->d_cnt + 8, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-    const long long layer = s->g.lim[0] * (sl->axis == 2 ? s->g.lim[1] : 1);  // cells per layer
-    const long long nl = s->g.lim[sl->axis];
-    const bool window = nl >= 8;
-    if (window) {
-        SP_CUDA(s, cudaMemcpyAsync(sl->h_cnt + 9, s->cell_start + 3 * layer + 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-        SP_CUDA(s, cudaMemcpyAsync(sl->h_cnt + 10, s->cell_start + (nl - 3) * layer + 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-    }
-    SP_CUDA(s, cudaStreamSynchronize(s->stream));
-    sl->sel_valid = window;
-    sl->sel_a = sl->h_cnt[9];
-    sl->sel_b = sl->h_cnt[10];
-    sl->n_owned = sl->h_cnt[8];
-    if (trace) {
-        const double t4 = slab_now();
-        sl->trace_s[0] += t1 - t0;
-        sl->trace_s[1] += t2 - t1;
-        sl->trace_s[2] += t3 - t2;
-        sl->trace_s[3] += t4 - t3;
-        if (++sl->trace_calls % 20 == 0)
-            fprintf(stderr, "[slab trace rank %d] calls=%lld migrate=%.3f ms ghosts=%.3f ms build=%.3f ms tail=%.3f ms (n=%lld ghosts=%lld+%lld)\n",
-                    sl->rank, sl->trace_calls, 1e3 * sl->trace_s[0] / sl->trace_calls, 1e3 * sl->trace_s[1] / sl->trace_calls,
-                    1e3 * sl->trace_s[2] / sl->trace_calls, 1e3 * sl->trace_s[3] / sl->trace_calls, (long long)s->n, rl, rh);
-    }
+    if ((rc = slab_rebuild(s))) return rc;
     return sp_time_end(s);
 }
 
@@ -858,33 +810,38 @@ int32_t sp_slab_halo_refresh(sp_system* s, const int32_t* fields, int32_t nfield
         if (fields[k] < 0 || fields[k] >= (int)s->fields.size()) return sp_fail(s, SP_ERR_INVALID, "bad field id");
         ncomp_total += s->fields[fields[k]].ncomp;
     }
-    const long long sd = sl->n_send[0], su = sl->n_send[1], rl = sl->n_ghost[0], rh = sl->n_ghost[1];
-    const long long biggest = std::max(std::max(sd, su), std::max(rl, rh));
-    if ((rc = slab_ensure_buffers(s, biggest * ncomp_total + 16))) return rc;
+    int below, above;
+    slab_peers(sl, &below, &above);
+    // the boundary layers hold at most what the last rebuild sent (that message also carried the migrants), the ghost
+    // layers at most what it received: the capacities of that rebuild fit, and both ends know them
+    const long long cs0 = below >= 0 ? sl->cap_send[0] : 0, cs1 = above >= 0 ? sl->cap_send[1] : 0;
+    const long long cr0 = below >= 0 ? sl->cap_recv[0] : 0, cr1 = above >= 0 ? sl->cap_recv[1] : 0;
+    const long long biggest = std::max(std::max(cs0, cs1), std::max(cr0, cr1));
+    if (biggest == 0) return sp_time_end(s);
+    if ((rc = slab_ensure_buffers(s, SLAB_HDR + biggest * ncomp_total + 16))) return rc;
+    const SlabWin w = slab_win(s, false);
     const int B = 256;
-    const long long n = s->n;
-    const double* sdn = s->fields[sl->f_sdn].d;
-    const double* sup = s->fields[sl->f_sup].d;
     int c0 = 0;
-    for (int k = 0; k < nfields && n > 0; k++) {
+    for (int k = 0; k < nfields; k++) {
         SpField& f = s->fields[fields[k]];
-        if (sd) SP_LAUNCH(s, k_slab_refresh_pack, sp_blocks(n, B), B, 0, f.d, s->cap, f.ncomp, sdn, n, sl->sendbuf[0] + (size_t)c0 * sd, sd);
-        if (su) SP_LAUNCH(s, k_slab_refresh_pack, sp_blocks(n, B), B, 0, f.d, s->cap, f.ncomp, sup, n, sl->sendbuf[1] + (size_t)c0 * su, su);
+        SP_LAUNCH(s, k_slab_refresh_pack, dim3(296, 2), B, 0, w, f.d, s->cap, f.ncomp, c0, cs0 ? sl->sendbuf[0] : (double*)nullptr,
+                  cs0, cs1 ? sl->sendbuf[1] : (double*)nullptr, cs1);
         c0 += f.ncomp;
     }
-    if ((rc = slab_exchange_payload(s, sd, su, rl, rh, ncomp_total))) return rc;
+    if ((rc = slab_exchange_payload(s, cs0 ? SLAB_HDR + cs0 * ncomp_total : 0, cs1 ? SLAB_HDR + cs1 * ncomp_total : 0,
+                                    cr0 ? SLAB_HDR + cr0 * ncomp_total : 0, cr1 ? SLAB_HDR + cr1 * ncomp_total : 0)))
+        return rc;
     const double shift_lo = (sl->periodic && sl->rank == 0) ? -sl->period : 0.0;
     const double shift_hi = (sl->periodic && sl->rank == sl->nranks - 1) ? sl->period : 0.0;
     c0 = 0;
-    for (int k = 0; k < nfields && n > 0; k++) {
+    for (int k = 0; k < nfields; k++) {
         SpField& f = s->fields[fields[k]];
         const int axis_comp = fields[k] == 0 ? sl->axis : -1;
         f.version++;  // ghost values change (a field that is zero everywhere stays zero: known_zero is kept)
         if (fields[k] == 0) s->x_version++;
-        if (rl || rh)
-            SP_LAUNCH(s, k_slab_refresh_unpack, sp_blocks(n, B), B, 0, f.d, s->cap, f.ncomp, s->fields[sl->f_ghost].d,
-                      s->fields[sl->f_hidx].d, n, sl->recvbuf[0] + (size_t)c0 * rl, rl, sl->recvbuf[1] + (size_t)c0 * rh, rh,
-                      axis_comp, shift_lo, shift_hi);
+        SP_LAUNCH(s, k_slab_refresh_unpack, dim3(296, 2), B, 0, w, f.d, s->cap, f.ncomp, c0,
+                  cr0 ? sl->recvbuf[0] : (const double*)nullptr, cr0, cr1 ? sl->recvbuf[1] : (const double*)nullptr, cr1, axis_comp,
+                  shift_lo, shift_hi, sl->d_cnt);
         c0 += f.ncomp;
     }
     return sp_time_end(s);
@@ -893,7 +850,12 @@ int32_t sp_slab_halo_refresh(sp_system* s, const int32_t* fields, int32_t nfield
 int32_t sp_slab_num_owned(sp_system* s, int64_t* n_owned) {
     if (!s || !n_owned) return SP_ERR_INVALID;
     if (!s->slab) return sp_fail(s, SP_ERR_STATE, "not a slab system");
-    *n_owned = s->slab->n_owned;
+    SP_CUDA(s, cudaSetDevice(s->device));
+    SlabState* sl = s->slab;
+    int* h = sl->h_cnt + SLAB_RING * 16 + 8;
+    SP_CUDA(s, cudaMemcpyAsync(h, sl->d_cnt + 8, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    SP_CUDA(s, cudaStreamSynchronize(s->stream));
+    *n_owned = sl->build_no ? *h : s->n;  // before the first rebuild everything the host added is owned
     return SP_OK;
 }
 

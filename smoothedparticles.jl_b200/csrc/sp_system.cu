@@ -106,7 +106,7 @@ static int regrow(sp_system* s, T** p, long long old_cap, long long new_cap, int
 
 int sp_ensure_capacity(sp_system* s, long long n) {
     if (n <= s->cap) return SP_OK;
-    long long nc = n + n / 16 + 8;  // head room: migrants/ghosts on slab systems; the tile kernel's aligned
+    long long nc = n + n / (s->slab ? 6 : 16) + 8;  // head room: arrivals on slab systems; the tile kernel's aligned
                                     // bulk copies may read one slot past n
     nc = (nc + 127) / 128 * 128;
     int rc;

@@ -60,7 +60,7 @@ class SlabSystem(ParticleSystem):
         self.rank, self.nranks, self.periodic = rank, nranks, periodic
         idbuf = (C.c_uint8 * 128).from_buffer_copy(nccl_id)
         abi.check(self._lib.sp_slab_init(self._h, idbuf, rank, nranks, 1 if periodic else 0), self._h)
-        for hidden in ("_ghost", "_hidx", "_sdn", "_sup"):
+        for hidden in ("_ghost", "_gid"):
             fid = C.c_int32()
             abi.check(self._lib.sp_find_field(self._h, hidden.encode(), C.byref(fid)), self._h)
             self.fields[hidden] = 1
@@ -111,13 +111,13 @@ class SlabSystem(ParticleSystem):
 
 
 def wcsph3d_slab_step(sys: SlabSystem, ops: dict):
-    """examples/collapse3d.jl:136-150 on a slab system: the rebuild migrates and exchanges ghosts, and the ghost
-    copies of rho and P are refreshed after find_pressure! (ghosts cannot integrate their own Drho)."""
+    """examples/collapse3d.jl:136-150 on a slab system: the rebuild migrates particles and exchanges two ghost layers per
+    side in one round; the inner ghost layer integrates its own density (it sees all of its neighbours), so no field has
+    to be refreshed between the sweeps."""
     sys.apply(ops["move"])
     sys.create_cell_list()
     sys.apply(ops["bom"])
     sys.apply(ops["fp"])
-    sys.halo_refresh("rho", "P")
     sys.apply(ops["force"])
     sys.apply(ops["acc"])
     sys.apply(ops["acc"])

@@ -88,6 +88,95 @@ def main():
             dt_o = sp.cfl_time_step(ora, 0.1, case.h, c["c"])
             ok = ok and abs(dt_cfl - dt_o) <= 1e-9 * dt_o and dt_o < 0.1 * case.h / c["c"]
             msg += f" dt_cfl {dt_cfl:.12e} vs {dt_o:.12e}"
+    elif case_name == "box_lists":
+        # SURVEY 8(e) "parity under sharding": neighbour sets per GLOBAL id, bit-exact, after 12 steps with migration.
+        # The oracle gets the device positions (bit-exactness is a statement about identical inputs).
+        case = configs.lattice_box((20, 18, 26), jitter=0.15, dr=5e-3, seed=7)
+        n = case.n
+        fields = dict(case.fields)
+        fields["gid"] = 1
+        sysd = slab.SlabSystem(fields, case.domain, case.h, rank, world, ids[0], periodic=False, device=device)
+        mine = sysd.owns(case.init["x"])
+        init = {k: v[mine] for k, v in case.init.items()}
+        init["gid"] = np.arange(n, dtype=float)[mine]
+        sysd.add_particles(**init)
+        for _ in range(12):
+            slab.wcsph3d_slab_step(sysd, case.ops)
+        off, idx = sysd.neighbour_lists()                 # local 1-based indices, device order
+        gid_loc = sysd.get("gid").astype(np.int64)
+        own = sysd.owned_mask()
+        nb = {}
+        for i in np.nonzero(own)[0]:
+            nb[int(gid_loc[i])] = np.sort(gid_loc[idx[off[i]:off[i + 1]] - 1])
+        res = gather_by_gid(sysd, ["x"], rank, world)
+        allnb = [None] * world
+        dist.all_gather_object(allnb, nb)
+        if rank == 0:
+            from oracle.oracle import OracleSystem
+            ora = OracleSystem({"gid": 1}, case.domain, case.h)
+            ora.add_particles(x=res["x"], gid=res["gid"])
+            ora.create_cell_list()
+            oo, oi = ora.neighbour_lists()
+            merged = {}
+            for d in allnb:
+                merged.update(d)
+            ok = len(merged) == n == len(ora)
+            bad = 0
+            for g in range(n):
+                ref = np.sort(oi[oo[g]:oo[g + 1]] - 1)
+                if not np.array_equal(ref, merged.get(g, np.array([-1]))):
+                    bad += 1
+            ok = ok and bad == 0
+            msg = f"neighbour sets by global id: {n} particles, {int(oo[-1])} pairs, {bad} mismatching lists"
+    elif case_name == "isph_cg":
+        # ISPH on slabs (2-D: the slab axis is y): pre-solve operators, matrix-free CG with NCCL all-reduced dot products
+        # and a halo refresh of the search vector per iteration, against the oracle's assembled matrix + CG
+        # (collapse_dry_implicit.jl:218-233)
+        case = configs.collapse_dry_implicit(dr=2.0e-2)
+        rng = np.random.default_rng(2)
+        case.init["v"] = rng.uniform(-1, 1, size=(case.n, 3)) * np.array([1.0, 1.0, 0.0])
+        n = case.n
+        o = case.ops
+        fields = dict(case.fields)
+        fields["gid"] = 1
+        sysd = slab.SlabSystem(fields, case.domain, case.h, rank, world, ids[0], periodic=False, device=device)
+        mine = sysd.owns(case.init["x"])
+        init = {k: v[mine] for k, v in case.init.items()}
+        init["gid"] = np.arange(n, dtype=float)[mine]
+        sysd.add_particles(**init)
+        case.prologue(sysd)
+        sysd.apply(o["init"])
+        sysd.create_cell_list()
+        sysd.apply(o["visc"])
+        sysd.apply(o["dll"])
+        sysd.apply(o["b"])
+        it_d, res_d = sysd.poisson_cg(o["A"], "b", "P")
+        sysd.apply(o["force"])
+        sysd.apply(o["acc"])
+        res = gather_by_gid(sysd, ["b", "P", "v", "L", "lambda"], rank, world)
+        if rank == 0:
+            from oracle.oracle import OracleSystem
+            ora = case.make(OracleSystem)
+            case.prologue(ora)
+            ora.apply(o["init"])
+            ora.create_cell_list()
+            ora.apply(o["visc"])
+            ora.apply(o["dll"])
+            ora.apply(o["b"])
+            I, J, V = ora.assemble_matrix(o["A"])
+            x_ref, it_o, res_o = ora.cg(I, J, V, ora.get("b"))
+            ora.set("P", x_ref)
+            ora.apply(o["force"])
+            ora.apply(o["acc"])
+            ok = len(res["gid"]) == n == len(ora)
+            errs = {}
+            for nm, tol in (("L", 1e-10), ("lambda", 1e-10), ("b", 1e-10), ("P", 1e-5), ("v", 1e-6)):
+                a, b_ = res[nm], ora.get(nm)
+                errs[nm] = np.max(np.abs(a - b_)) / max(np.max(np.abs(b_)), 1e-300)
+                ok = ok and errs[nm] <= tol
+            ok = ok and abs(it_d - it_o) <= max(3, it_o // 20)
+            ok = ok and res_d <= np.sqrt(np.finfo(float).eps) * np.linalg.norm(ora.get("b"))
+            msg = f"iters {it_d} vs {it_o}; " + " ".join(f"{k}:{v:.2e}" for k, v in errs.items())
     elif case_name == "box_periodic":
         # periodic along z: compare with an oracle run on the same particles plus explicit periodic images
         nx, ny, nz = 14, 12, 24

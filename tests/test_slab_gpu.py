@@ -33,14 +33,22 @@ def _run(case, world):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     out = r.stdout + r.stderr
     assert r.returncode == 0 and "SLAB-OK" in out, out[-3000:]
+    # keep the worker's verdict line (profiles/ keeps the ones of the multi-GPU runs)
+    log = os.environ.get("SP_SLAB_LOG")
+    if log:
+        with open(log, "a") as f:
+            f.write("".join(l + "\n" for l in out.splitlines() if l.startswith("SLAB-")))
 
 
-@pytest.mark.parametrize("case", ["box_nonperiodic", "box_steps", "box_program", "box_periodic"])
+CASES = ["box_nonperiodic", "box_steps", "box_program", "box_periodic", "box_lists", "isph_cg"]
+
+
+@pytest.mark.parametrize("case", CASES)
 def test_slab_single_rank(case):
     _run(case, 1)
 
 
-@pytest.mark.parametrize("case", ["box_nonperiodic", "box_steps", "box_program", "box_periodic"])
+@pytest.mark.parametrize("case", CASES)
 def test_slab_two_ranks(case):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
@@ -52,3 +60,4 @@ def test_slab_four_ranks():
         pytest.skip("needs 4 GPUs")
     _run("box_steps", 4)
     _run("box_periodic", 4)
+    _run("box_lists", 4)
