@@ -447,6 +447,10 @@ def run_multi(args):
 
 
 def main():
+    wd = os.environ.get("SP_BENCH_WATCHDOG")   # debugging aid: dump every thread's Python stack and exit after N seconds
+    if wd:
+        import faulthandler
+        faulthandler.dump_traceback_later(float(wd), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
@@ -468,7 +472,15 @@ def main():
     elif args.gpus == 1:
         run_single(args)
     else:
-        run_multi(args)
+        try:
+            run_multi(args)
+        except BaseException:
+            # a rank that fails must not sit in a destructor waiting for a collective its peers will never join
+            import traceback
+            traceback.print_exc()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(1)
 
 
 if __name__ == "__main__":

@@ -124,6 +124,15 @@ __global__ void k_cull_key(SpGrid g, const double* __restrict__ x, long long cap
         if (s < alive) {
             double px = x[s], py = x[cap + s], pz = x[2 * cap + s];
             if (sp_inside(g, px, py, pz)) k = (int)sp_find_key(g, px, py, pz);
+            else if (g.slab_axis >= 0 && px == px) {
+                // slab system: inside the global box but outside this rank's window = the particle outran the exchange
+                // (more than the ghost width in one step); counted, and reported by a later rebuild (sp_slab.cu)
+                bool in_box = true;
+                const double p[3] = {px, py, pz};
+                for (int a = 0; a < 3; a++)
+                    if (a != g.slab_axis || !g.slab_periodic) in_box = in_box && g.lo[a] <= p[a] && p[a] <= g.hi[a];
+                if (in_box) atomicAdd(&counters[SP_CNT_LOST], 1);
+            }
         }
     }
     const unsigned peers = __match_any_sync(0xffffffffu, k);

@@ -25,6 +25,8 @@
 #define SP_CNT_ALIVE 1    /* alive slots: [0, alive) */
 #define SP_CNT_REMOVED 2  /* particles culled by all builds so far (sp_num_removed) */
 #define SP_CNT_CULLED 3   /* particles culled by the last build */
+#define SP_CNT_LOST 4     /* slab systems: particles that left the local cell window although they are inside the global
+                             box, i.e. moved more than the ghost width between two rebuilds (cumulative) */
 #define SP_CNT_CGFLAG 32
 #define SP_CNT_NBRMAX 40
 #define SP_FLAG_INTERNAL_PR_READY (1 << 30) /* library-internal: _pr = P/rho^2 is already up to date */

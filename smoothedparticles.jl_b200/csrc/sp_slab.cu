@@ -18,7 +18,7 @@
 //      receiver owns what falls into its owned layers and keeps the rest of its window as ghosts; the sender keeps
 //      its copy of a particle that migrated away as a ghost (it is bit-identical to what the new owner holds);
 //   3. both messages travel in one ncclGroup at a CAPACITY known to both ends without talking: the count that went over
-//      the same link two rebuilds ago (both ends have it) plus 25 %; the actual count rides in the message header and
+//      the same link two rebuilds ago (both ends have it) times two; the actual count rides in the message header and
 //      stays on the device; unused entries arrive as NaN positions and are culled by the build;
 //   4. arrivals are appended behind the alive slots, the ordinary cell-list build (sp_cells.cu, no read-back) sorts
 //      everything, "_ghost" is set from the cell layer.
@@ -350,6 +350,12 @@ __global__ void k_slab_unpack(SlabPlanes tab, int plane0, const double* buf, lon
     }
     if (plane0 == 0) ref[slot] = (int)slot;
 }
+__global__ void k_slab_zero_tail(SlabPlanes tab, long long count, const int* counters) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const long long slot = (long long)counters[SP_CNT_ALIVE] + t;
+    for (int c = 0; c < tab.count; c++) tab.p[c][slot] = 0.0;
+}
 __global__ void k_slab_add_alive(int* counters, int add) {
     if (threadIdx.x == 0 && blockIdx.x == 0) counters[SP_CNT_ALIVE] += add;
 }
@@ -416,7 +422,7 @@ __global__ void k_slab_refresh_unpack(SlabWin w, double* f, long long cap, int n
 }
 
 // ------------------------------------------------------------------ host helpers
-static int slab_planes(sp_system* s, std::vector<SlabPlanes>& tabs, int* nplanes) {
+static int slab_planes(sp_system* s, std::vector<SlabPlanes>& tabs, int* nplanes, bool skip_zero = true, bool only_zero = false) {
     tabs.clear();
     SlabPlanes cur;
     cur.count = 0;
@@ -425,6 +431,11 @@ static int slab_planes(sp_system* s, std::vector<SlabPlanes>& tabs, int* nplanes
     for (size_t f = 0; f < s->fields.size(); f++) {
         SpField& fl = s->fields[f];
         if (fl.transient) continue;
+        // a field that is +0.0 in every slot (the operators that reset a field say so: Dv after move!, Drho after
+        // find_pressure!) does not travel: the receiver's copy is zero as well — every rank runs the same call sequence —
+        // and the dead tail the arrivals land in is kept zero for such fields (see k_slab_unpack / zero_tabs)
+        if (skip_zero && fl.known_zero) continue;
+        if (only_zero && !fl.known_zero) continue;
         for (int c = 0; c < fl.ncomp; c++) {
             if (f == 0 && c == s->slab->axis) cur.axis_plane = cur.count;
             if (f == 0 && c == 0) cur.x_plane = cur.count;
@@ -526,8 +537,11 @@ static int slab_exchange_payload(sp_system* s, long long send_dn, long long send
 }
 
 // message capacity for a link over which `count` particles went two rebuilds ago (both ends evaluate this)
+// A boundary zone is two cell layers = about four lattice planes at h = 2 dr, and on an aligned lattice a whole plane
+// can cross a cell boundary in one step (measured on the 10 M dam break: 216 808 -> 165 458 -> 216 808 particles in three
+// consecutive rebuilds), so the head room is a factor of two over the larger of the last two known counts.
 static long long slab_capacity(long long count) {
-    long long c = count + count / 4 + 2048;
+    long long c = 2 * count + 4096;
     return (c + 1023) / 1024 * 1024;
 }
 
@@ -550,13 +564,36 @@ static int slab_rebuild(sp_system* s) {
         const int slot = (int)((sl->build_no - 2) % SLAB_RING);
         SP_CUDA(s, cudaEventSynchronize(sl->ring_ev[slot]));
         const int* h = sl->h_cnt + slot * 16;
-        if (h[4]) return sp_fail(s, SP_ERR_STATE, "slab exchange overflow: the number of particles in a boundary layer grew by "
-                                                  "more than 25 % within two rebuilds; particles were lost");
+        if (h[4]) {
+            char buf[400];
+            snprintf(buf, sizeof buf,
+                     "slab exchange overflow at rebuild %lld (rank %d): a boundary message outgrew its capacity (sent %d down / %d "
+                     "up with capacities %lld / %lld, i.e. the boundary population more than doubled within three rebuilds); particles "
+                     "were lost",
+                     sl->build_no - 2, sl->rank, h[0], h[1], (long long)h[10], (long long)h[11]);
+            return sp_fail(s, SP_ERR_STATE, buf);
+        }
         if (h[5]) return sp_fail(s, SP_ERR_STATE, "slab halo refresh: owner and ghost layers disagree");
-        cap_send[0] = below >= 0 ? slab_capacity(h[0]) : 0;
-        cap_send[1] = above >= 0 ? slab_capacity(h[1]) : 0;
-        cap_recv[0] = below >= 0 ? slab_capacity(h[2]) : 0;
-        cap_recv[1] = above >= 0 ? slab_capacity(h[3]) : 0;
+        if (h[12]) {
+            char buf[300];
+            snprintf(buf, sizeof buf,
+                     "slab exchange (rank %d): %d particle(s) moved more than the two ghost layers between two rebuilds and "
+                     "left this rank's window inside the global box; they were culled (time step too large?)", sl->rank, h[12]);
+            return sp_fail(s, SP_ERR_STATE, buf);
+        }
+        if (trace)
+            fprintf(stderr, "[slab trace rank %d] rebuild %lld: sent %d dn / %d up, received %d lo / %d hi, owned %d, alive %d\n",
+                    sl->rank, sl->build_no - 2, h[0], h[1], h[2], h[3], h[8], h[9]);
+        // both ends of a link hold the counts that went over it in rebuilds b-2 and b-3
+        int big[4] = {h[0], h[1], h[2], h[3]};
+        if (sl->history >= 3) {
+            const int* h3 = sl->h_cnt + (int)((sl->build_no - 3) % SLAB_RING) * 16;
+            for (int i = 0; i < 4; i++) big[i] = std::max(big[i], h3[i]);
+        }
+        cap_send[0] = below >= 0 ? slab_capacity(big[0]) : 0;
+        cap_send[1] = above >= 0 ? slab_capacity(big[1]) : 0;
+        cap_recv[0] = below >= 0 ? slab_capacity(big[2]) : 0;
+        cap_recv[1] = above >= 0 ? slab_capacity(big[3]) : 0;
         // slot bound before this rebuild: alive after rebuild b-2 plus everything rebuild b-1 may have appended
         s->n = (long long)h[9] + sl->cap_recv[0] + sl->cap_recv[1];
         s->n_exact = false;
@@ -644,7 +681,15 @@ static int slab_rebuild(sp_system* s) {
             plane0 += t.count;
         }
     }
-    if (cap_recv[0] + cap_recv[1]) SP_LAUNCH(s, k_slab_add_alive, 1, 32, 0, s->counters, (int)(cap_recv[0] + cap_recv[1]));
+    if (cap_recv[0] + cap_recv[1]) {
+        // fields that did not travel (zero everywhere): the arrival slots must hold zero too
+        std::vector<SlabPlanes> ztabs;
+        int nz = 0;
+        slab_planes(s, ztabs, &nz, false, true);
+        for (SlabPlanes& t : ztabs)
+            SP_LAUNCH(s, k_slab_zero_tail, sp_blocks(cap_recv[0] + cap_recv[1], B), B, 0, t, cap_recv[0] + cap_recv[1], s->counters);
+        SP_LAUNCH(s, k_slab_add_alive, 1, 32, 0, s->counters, (int)(cap_recv[0] + cap_recv[1]));
+    }
     s->n = n_new;
     s->n_exact = false;
     s->count_pending = false;
@@ -669,6 +714,9 @@ static int slab_rebuild(sp_system* s) {
         int* h = sl->h_cnt + slot * 16;
         SP_CUDA(s, cudaMemcpyAsync(h, sl->d_cnt, 9 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
         SP_CUDA(s, cudaMemcpyAsync(h + 9, s->counters + SP_CNT_ALIVE, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        SP_CUDA(s, cudaMemcpyAsync(h + 12, s->counters + SP_CNT_LOST, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        h[10] = (int)cap_send[0];  // (host-side notes for the error message; written before the event can complete)
+        h[11] = (int)cap_send[1];
         SP_CUDA(s, cudaEventRecord(sl->ring_ev[slot], s->stream));
     }
     sl->build_no++;

@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(128, 5) k_nbr_build(SpGrid g, SweepCtx c, int*
             for (int j0 = jb & ~3; j0 < je; j0 += 32) {
                 const int nj = min(32, je - j0);
                 const int nq = (nj + 3) >> 2;
-                unsigned not_maybe = 0u, not_sure = 0u;  // candidate k of the chunk lands in bit 4*nq-1-k
+                unsigned not_maybe = 0u, is_sure = 0u;  // candidate k of the chunk lands in bit 4*nq-1-k
                 const ulonglong2* px = reinterpret_cast<const ulonglong2*>(c.ux + j0);
                 const ulonglong2* py = reinterpret_cast<const ulonglong2*>(c.uy + j0);
                 const ulonglong2* pz = reinterpret_cast<const ulonglong2*>(c.uz + j0);
@@ -549,19 +549,22 @@ __global__ void __launch_bounds__(128, 5) k_nbr_build(SpGrid g, SweepCtx c, int*
                         // sign(thr - dd) = 1  <=>  dd > thr  (certainly not a neighbour); a NaN distance gives the
                         // canonical positive NaN: it stays a candidate and the reference accepts it as well
                         asm("sub.f32x2 %0, %1, %2;" : "=l"(ta) : "l"(thr2), "l"(dd));
-                        asm("sub.f32x2 %0, %1, %2;" : "=l"(tb) : "l"(thr_lo2), "l"(dd));
+                        // sign(dd - thr_lo) = 1  <=>  dd < thr_lo: certainly a neighbour.  A NaN distance (a coordinate
+                        // outside the range the rounding bound covers, k_prefilter_coords) has sign 0 in both tests: it is
+                        // neither certainly outside nor certainly inside and goes to the exact predicate
+                        asm("sub.f32x2 %0, %1, %2;" : "=l"(tb) : "l"(dd), "l"(thr_lo2));
                         unsigned a0, a1, c0, c1;
                         asm("mov.b64 {%0,%1}, %2;" : "=r"(a0), "=r"(a1) : "l"(ta));
                         asm("mov.b64 {%0,%1}, %2;" : "=r"(c0), "=r"(c1) : "l"(tb));
                         not_maybe = __funnelshift_l(a0, not_maybe, 1);
                         not_maybe = __funnelshift_l(a1, not_maybe, 1);
-                        not_sure = __funnelshift_l(c0, not_sure, 1);
-                        not_sure = __funnelshift_l(c1, not_sure, 1);
+                        is_sure = __funnelshift_l(c0, is_sure, 1);
+                        is_sure = __funnelshift_l(c1, is_sure, 1);
                     }
                 }
                 const int sh = 32 - 4 * nq;
                 unsigned m = __brev(~not_maybe) >> sh;
-                unsigned sure = __brev(~not_sure) >> sh;
+                unsigned sure = __brev(is_sure) >> sh;
                 // only slots of this row range count (the aligned chunk may start up to 3 slots early / end late)
                 const int lo_bit = max(jb - j0, 0);
                 unsigned valid = nj >= 32 ? 0xffffffffu : ((1u << nj) - 1u);
@@ -846,14 +849,22 @@ __global__ void __launch_bounds__(256) k_unary(typename U::Params P, const int* 
 #define TILE_CAPB2 (TILE_TP + 96)       /* slots per buffer, 2-D (rows are ~3x longer per cell) */
 
 // FP32 cell-unit coordinates u = (x - lo)/h of every slot, the input of the tile kernel's pre-filter.
+// The rounding bound delta of the pre-filter holds for |u| <= U (sp_ensure_prefilter).  A particle that has drifted
+// further out since the last create_cell_list! (several move! calls without a rebuild, a runaway particle) gets NaN
+// coordinates instead: a NaN distance is never "certainly outside" nor "certainly inside", so every pair it takes part
+// in is decided by the exact FP64 predicate from its true position, as the reference decides all of them.
 __global__ void __launch_bounds__(256) k_prefilter_coords(SpGrid g, const double* __restrict__ x, long long cap,
-                                                          float* __restrict__ u, long long n) {
+                                                          float* __restrict__ u, long long n, float U) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double ih = 1.0 / g.h;
-    u[i] = (float)((x[i] - g.lo[0]) * ih);
-    u[cap + i] = (float)((x[cap + i] - g.lo[1]) * ih);
-    u[2 * cap + i] = (float)((x[2 * cap + i] - g.lo[2]) * ih);
+    float a = (float)((x[i] - g.lo[0]) * ih);
+    float b = (float)((x[cap + i] - g.lo[1]) * ih);
+    float c = (float)((x[2 * cap + i] - g.lo[2]) * ih);
+    if (!(fabsf(a) <= U) || !(fabsf(b) <= U) || !(fabsf(c) <= U)) a = b = c = nanf("");
+    u[i] = a;
+    u[cap + i] = b;
+    u[2 * cap + i] = c;
 }
 
 template <class Op, int CAPB, int NROWS, int RPB>
@@ -914,17 +925,17 @@ static int sp_ensure_prefilter(sp_system* s, SweepCtx& c) {
         s->ucoord_cap = s->cap;
         s->ucoord_version = 0;
     }
+    // U bounds |u| from the GLOBAL box (on a slab system key_lim is only the local window along the slab axis)
+    double U = (double)std::max(std::max(s->g.lim[0], s->g.lim[1]), s->g.lim[2]);
+    for (int a = 0; a < 3; a++) U = std::max(U, std::ceil((s->g.hi[a] - s->g.lo[a]) / s->g.h) + 1.0);
+    U += 2.0;
     if (s->ucoord_version != s->x_version) {  // positions unchanged since the last sweep: keep the planes
-        SP_LAUNCH(s, k_prefilter_coords, sp_blocks(s->n, 256), 256, 0, s->g, s->fields[0].d, s->cap, s->ucoord, s->n);
+        SP_LAUNCH(s, k_prefilter_coords, sp_blocks(s->n, 256), 256, 0, s->g, s->fields[0].d, s->cap, s->ucoord, s->n, (float)U);
         s->ucoord_version = s->x_version;
     }
     c.ux = s->ucoord;
     c.uy = s->ucoord + s->cap;
     c.uz = s->ucoord + 2 * s->cap;
-    // U bounds |u| from the GLOBAL box (on a slab system key_lim is only the local window along the slab axis)
-    double U = (double)std::max(std::max(s->g.lim[0], s->g.lim[1]), s->g.lim[2]);
-    for (int a = 0; a < 3; a++) U = std::max(U, std::ceil((s->g.hi[a] - s->g.lo[a]) / s->g.h) + 1.0);
-    U += 2.0;
     c.thr = (float)(1.0 + 8.0 * U / 8388608.0 + 1e-6);
     c.thr = std::nextafter(c.thr, 2.0f);
     // 1e-6 more for the FP64 rounding of d2 and of T2 itself

@@ -110,6 +110,37 @@ def test_cached_sweep_lists_are_the_reference_sets(maker):
     assert np.array_equal(_sorted_segments(od, idd), _sorted_segments(oo, ido))
 
 
+def test_runaway_particles_between_rebuilds_do_not_break_the_prefilter():
+    # The FP32 pre-filter's rounding bound holds for coordinates within the box (+2 cells).  Particles that drift far out
+    # between rebuilds (several move! calls without create_cell_list!, a runaway) get NaN pre-filter coordinates and are
+    # decided by the exact FP64 predicate alone: lists and sums must still equal the reference's, which works from the
+    # current x with the cells of the last build (core.jl:95-110).
+    case = configs.lattice_box(14, jitter=0.2, dr=5e-3, seed=5)
+    dev, ora = _pair(case)
+    dev.create_cell_list()
+    ora.create_cell_list()
+    x = ora.get("x").copy()
+    rng = np.random.default_rng(4)
+    far = rng.choice(len(x), 40, replace=False)
+    x[far[:20]] += rng.uniform(40.0, 3000.0, size=(20, 3)) * case.h                  # far outside, all axes
+    x[far[20:], 0] -= rng.uniform(20.0, 1.0e6, size=20) * case.h                     # far outside along -x only
+    near = np.setdiff1d(np.arange(len(x)), far)
+    x[near] += rng.uniform(-0.3, 0.3, size=(len(near), 3)) * case.h                 # everybody else moves a little
+    for s_ in (dev, ora):
+        s_.set("x", x)
+        s_.apply(ops.density_sum("wendland3", case.consts["m"], case.h), self_=True)
+    od, idd = dev.sweep_neighbour_lists()
+    oo, ido = ora.neighbour_lists()
+    assert np.array_equal(od, oo)
+    assert np.array_equal(_sorted_segments(od, idd), _sorted_segments(oo, ido))
+    assert_fields_close(dev, ora, ["rho"], what="density after runaway particles")
+    # the fused build + sweep path sees the same state (balance_of_mass is the first sweep after a position change)
+    for s_ in (dev, ora):
+        s_.set("x", x)
+        s_.apply(case.ops["bom"])
+    assert_fields_close(dev, ora, ["Drho"], what="balance_of_mass after runaway particles")
+
+
 def test_cached_sweep_lists_overflow_cluster():
     # more neighbours than the cache holds per target (64): those targets are swept by the exact scan
     rng = np.random.default_rng(8)
@@ -607,6 +638,44 @@ def test_isph_operators_matvec_and_cg():
     dev.apply(o["force"])
     dev.apply(o["acc"])
     assert_fields_close(dev, ora, ["v"], rtol=1e-6, what="ISPH post-solve")
+
+
+def test_isph_full_size_fields_and_ten_steps():
+    # BASELINE configs[2] as shipped: examples/collapse_dry_implicit.jl at dr = 1e-2, 23 172 particles.
+    # (a) the pre-solve operators of one step (initialize!, viscous_force!, div_L_lambda!, projection_vector) <= 1e-10;
+    # (b) the matrix-free operator against the oracle's assembled matrix <= 1e-10;
+    # (c) ten full time steps (each with its own CG solve to sqrt(eps)) against the oracle running the same loop:
+    #     the solver tolerance, not rounding, sets the bar — P to 1e-4 of its maximum, v to 1e-5, x to 1e-8.
+    case = configs.collapse_dry_implicit()
+    assert case.n == 23172
+    dev, ora = _pair(case)
+    o = case.ops
+    for s_ in (dev, ora):
+        case.prologue(s_)
+        s_.apply(o["init"])
+        s_.create_cell_list()
+        s_.apply(o["visc"])
+        s_.apply(o["dll"])
+        s_.apply(o["b"])
+    _check_cells(dev, ora)
+    assert_fields_close(dev, ora, ["x", "v", "Dv", "div", "L", "lambda", "b"], what="ISPH pre-solve, 23 172 particles")
+    I, J, V = ora.assemble_matrix(o["A"])
+    p = np.random.default_rng(9).uniform(-1, 1, case.n)
+    dev.set("P", p)
+    dev.add_field("y", 1)
+    dev.poisson_apply(o["A"], "P", "y")
+    assert rel_err(dev.get("y"), ora.coo_matvec(I, J, V, p)) <= RTOL_STEP
+    # (c) fresh systems, the script's loop
+    dev, ora = _pair(case)
+    case.prologue(dev)
+    case.prologue(ora)
+    for _ in range(10):
+        case.step(dev)
+        case.step(ora)
+    assert len(dev) == len(ora) == case.n
+    assert_fields_close(dev, ora, ["x"], rtol=1e-8, what="ISPH 10 steps", etol=1e-8)
+    assert_fields_close(dev, ora, ["v"], rtol=1e-5, what="ISPH 10 steps", etol=1e-4)
+    assert_fields_close(dev, ora, ["P"], rtol=1e-4, what="ISPH 10 steps", etol=1e-3)
 
 
 def test_isph_time_loop_runs_and_conserves_count():
