@@ -79,7 +79,38 @@ __global__ void k_scan_add(int* data, long long len, const int* block_offsets, S
     }
 }
 
+// short arrays (the cell counts of the 2-D configs, ~6 k cells): the whole scan in ONE block and one launch — the small
+// configs are bound by their launch count
+#define SCAN_SMALL_MAX 32768
+__global__ void __launch_bounds__(1024) k_scan_small(int* data, int len, ScanGate gate) {
+    if (scan_gated_off(gate)) return;
+    __shared__ int part[1024];
+    const int t = threadIdx.x, T = blockDim.x;
+    const int chunk = (len + T - 1) / T;
+    const int b = min(t * chunk, len), e = min(b + chunk, len);
+    int sum = 0;
+    for (int i = b; i < e; i++) sum += data[i];
+    part[t] = sum;
+    __syncthreads();
+    for (int d = 1; d < T; d <<= 1) {  // inclusive Hillis-Steele over the 1024 chunk sums
+        const int v = t >= d ? part[t - d] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    int run = part[t] - sum;
+    for (int i = b; i < e; i++) {
+        const int v = data[i];
+        data[i] = run;
+        run += v;
+    }
+}
+
 static int scan_rec(sp_system* s, int* data, long long len, int* tmp, long long tmp_len, ScanGate gate) {
+    if (len <= SCAN_SMALL_MAX) {
+        SP_LAUNCH(s, k_scan_small, 1, 1024, 0, data, (int)len, gate);
+        return SP_OK;
+    }
     const long long nb = (len + SCAN_TILE - 1) / SCAN_TILE;
     if (nb <= 1) {
         SP_LAUNCH(s, k_scan_tile, 1, SCAN_B, 0, data, len, (int*)nullptr, gate);
@@ -282,6 +313,7 @@ __global__ void k_finish_build(int* counters, long long n) {
         counters[SP_CNT_CULLED] = alive_old - alive_new;
         counters[SP_CNT_REMOVED] += alive_old - alive_new;
         counters[SP_CNT_ALIVE] = alive_new;
+        counters[SP_CNT_TRASH] = 0;  // ready for the next build (saves it a memset)
     }
 }
 __global__ void k_set_count(int* counters, int n) {
@@ -293,8 +325,14 @@ struct PlaneTable {
     const double* in[PERM_PLANES];
     double* out[PERM_PLANES];
     int count;
+    // the launch that moves the three position planes (planes 0-2 of the first table) also writes the FP32 cell-unit
+    // coordinates u = (x - lo)/h of the pre-filter for the new slot order (sp_sweep.cu: k_prefilter_coords) — one pass
+    // over the positions and one launch less per step
+    float* ucoord;  // nullptr: not this launch
+    long long ucap;
+    float U;
 };
-__global__ void k_permute(PlaneTable tab, const int* __restrict__ perm, const int* __restrict__ ref_in,
+__global__ void k_permute(SpGrid g, PlaneTable tab, const int* __restrict__ perm, const int* __restrict__ ref_in,
                           int* __restrict__ ref_out, const int* __restrict__ key_in, int* __restrict__ key_out,
                           long long n, const int* __restrict__ counters) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -313,6 +351,14 @@ __global__ void k_permute(PlaneTable tab, const int* __restrict__ perm, const in
 #pragma unroll
         for (int u = 0; u < 12; u++)
             if (c0 + u < tab.count) tab.out[c0 + u][t] = v[u];
+        if (c0 == 0 && tab.ucoord) {  // same arithmetic as k_prefilter_coords
+            const double ih = 1.0 / g.h;
+            float a = (float)((v[0] - g.lo[0]) * ih), b = (float)((v[1] - g.lo[1]) * ih), c = (float)((v[2] - g.lo[2]) * ih);
+            if (!(fabsf(a) <= tab.U) || !(fabsf(b) <= tab.U) || !(fabsf(c) <= tab.U)) a = b = c = nanf("");
+            tab.ucoord[t] = a;
+            tab.ucoord[tab.ucap + t] = b;
+            tab.ucoord[2 * tab.ucap + t] = c;
+        }
     }
 }
 
@@ -320,10 +366,22 @@ int sp_permute_all(sp_system* s, long long n_keep) {
     const int B = 256;
     PlaneTable tab;
     tab.count = 0;
+    tab.ucoord = nullptr;
+    tab.ucap = 0;
+    tab.U = 0.f;
     bool first = true;
+    // the position planes are planes 0-2 of the first launch (field 0 is x and is never known-zero in a system with
+    // particles in a domain; if it were, the separate pass of sp_sweep.cu computes the coordinates as before)
+    const bool with_u = s->ucoord && s->ucoord_cap == s->cap && !s->fields[0].known_zero && !s->fields[0].transient;
     auto flush = [&]() -> int {
         if (tab.count == 0 && !first) return SP_OK;
-        SP_LAUNCH(s, k_permute, sp_blocks(n_keep, B), B, 0, tab, s->perm, s->ref, first ? s->ref_alt : (int*)nullptr,
+        if (first && with_u) {
+            tab.ucoord = s->ucoord;
+            tab.ucap = s->cap;
+            tab.U = sp_prefilter_range(s);
+        } else
+            tab.ucoord = nullptr;
+        SP_LAUNCH(s, k_permute, sp_blocks(n_keep, B), B, 0, s->g, tab, s->perm, s->ref, first ? s->ref_alt : (int*)nullptr,
                   s->key, s->key_alt, n_keep, s->counters);
         first = false;
         tab.count = 0;
@@ -345,6 +403,7 @@ int sp_permute_all(sp_system* s, long long n_keep) {
         if (!f.transient && !f.known_zero) std::swap(f.d, f.alt);
     std::swap(s->ref, s->ref_alt);
     std::swap(s->key, s->key_alt);
+    if (with_u) s->ucoord_version = s->x_version;  // valid until the next position write
     return SP_OK;
 }
 
@@ -393,7 +452,7 @@ int sp_build_cells(sp_system* s) {
     const long long N = s->n;
     const long long K = g.key_max;
     SP_CUDA(s, cudaMemsetAsync(s->cell_start, 0, (size_t)(K + 3) * sizeof(int), s->stream));
-    SP_CUDA(s, cudaMemsetAsync(s->counters + SP_CNT_TRASH, 0, sizeof(int), s->stream));
+    // (counters[SP_CNT_TRASH] is zero between builds: k_finish_build leaves it so)
     if (N == 0) {
         s->have_cells = true;
         return SP_OK;

@@ -916,6 +916,12 @@ static void sp_sweep_ctx(sp_system* s, SweepCtx& c) {
 //   d2_f32 > 1 + delta   certainly not a neighbour        (thr)
 //   d2_f32 <= 1 - delta  certainly a neighbour            (thr_lo, used by k_nbr_build only)
 // Everything in between is decided by the exact FP64 predicate, so the neighbour set is the reference's bit for bit.
+// U bounds |u| from the GLOBAL box (on a slab system key_lim is only the local window along the slab axis)
+float sp_prefilter_range(const sp_system* s) {
+    double U = (double)std::max(std::max(s->g.lim[0], s->g.lim[1]), s->g.lim[2]);
+    for (int a = 0; a < 3; a++) U = std::max(U, std::ceil((s->g.hi[a] - s->g.lo[a]) / s->g.h) + 1.0);
+    return (float)(U + 2.0);
+}
 static int sp_ensure_prefilter(sp_system* s, SweepCtx& c) {
     if (!s->ucoord || s->ucoord_cap != s->cap) {
         if (s->ucoord) SP_CUDA(s, sp_dfree(s, s->ucoord));
@@ -925,10 +931,7 @@ static int sp_ensure_prefilter(sp_system* s, SweepCtx& c) {
         s->ucoord_cap = s->cap;
         s->ucoord_version = 0;
     }
-    // U bounds |u| from the GLOBAL box (on a slab system key_lim is only the local window along the slab axis)
-    double U = (double)std::max(std::max(s->g.lim[0], s->g.lim[1]), s->g.lim[2]);
-    for (int a = 0; a < 3; a++) U = std::max(U, std::ceil((s->g.hi[a] - s->g.lo[a]) / s->g.h) + 1.0);
-    U += 2.0;
+    const double U = (double)sp_prefilter_range(s);
     if (s->ucoord_version != s->x_version) {  // positions unchanged since the last sweep: keep the planes
         SP_LAUNCH(s, k_prefilter_coords, sp_blocks(s->n, 256), 256, 0, s->g, s->fields[0].d, s->cap, s->ucoord, s->n, (float)U);
         s->ucoord_version = s->x_version;
@@ -978,7 +981,7 @@ static int sp_nbr_prepare(sp_system* s, SweepCtx& c, bool* need_build) {
     }
     c.capk = s->nbr_capk;
     *need_build = s->nbr_version != s->x_version || s->nbr_n != s->n;
-    if (*need_build) SP_CUDA(s, cudaMemsetAsync(s->counters + 40, 0, sizeof(int), s->stream));
+    // (counters[SP_CNT_NBRMAX] is a running maximum over all builds: the lists only ever grow)
     return SP_OK;
 }
 static int sp_nbr_built(sp_system* s) {
