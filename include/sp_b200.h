@@ -25,6 +25,7 @@
  *   sp_respawn                       add_new_particles! (inflow)  examples/cylinder.jl:145-156
  *   sp_assemble_matrix               assemble_matrix              src/core.jl:196-225
  *   sp_run_program                   the examples' time loops     examples/collapse3d.jl:134-151, collapse_dry.jl:202-211
+ *   sp_graph_*                       (no counterpart: a host loop body recorded once, replayed as one CUDA graph launch)
  *   sp_slab_*                        (no counterpart: one process per GPU, slab decomposition over NCCL)
  *
  * Because arbitrary Julia closures cannot run inside CUDA kernels, the per-pair
@@ -460,6 +461,26 @@ enum {
 /* fields {x, v, Dv, rho, Drho, P, type}; params {kernel, m, h, two_nu, dt, c2, rho0, mu, gx, gy, gz} */
 int32_t sp_run_program(sp_system* sys, int32_t program, const int32_t* fields, int32_t nfields,
                        const double* params, int32_t nparams, int64_t nsteps);
+
+/* ---- step graphs: any host loop body as ONE launch -------------------------------------------------------------
+ * No counterpart in the reference; the device analogue of "the loop body is cheap to call".  The cell-list build keeps
+ * its counts on the device, so a time step of ANY example is a fixed sequence of kernel launches.  Between
+ * sp_graph_begin and sp_graph_end the asynchronous entry points (sp_apply, sp_create_cell_list, sp_poisson_apply,
+ * sp_run_program without its own graphs, ...) are recorded into a CUDA graph instead of being executed; sp_graph_end
+ * executes the recorded body ONCE — so begin/end behaves like the calls it encloses — and returns a handle;
+ * sp_graph_launch(id, times) replays it.  A 10 k-particle 2-D step costs ~25 launches of ~3 us each when issued call
+ * by call and one graph launch when replayed.
+ * Rules: (1) run the body once the ordinary way first (lazy allocations happen then); (2) the body must leave the
+ * library's ping-pong buffers where it found them, which means an EVEN number of cell-list builds — record two time
+ * steps if a step has one; otherwise sp_graph_end executes the body, keeps no graph and returns SP_ERR_STATE;
+ * (3) calls that hand data or counts to the host (sp_download, sp_reduce, sp_num_particles, sp_poisson_cg, ...) are
+ * refused inside a recording (SP_ERR_STATE); (4) a graph is replayed only while everything its launches depend on is
+ * unchanged (field storage, slot bound, list capacity): sp_graph_launch returns SP_ERR_STATE otherwise and the host
+ * records again.  Particles leaving the domain inside a replay are handled on the device as in the ordinary path. */
+int32_t sp_graph_begin(sp_system* sys);
+int32_t sp_graph_end(sp_system* sys, int32_t* graph_id);
+int32_t sp_graph_launch(sp_system* sys, int32_t graph_id, int64_t times);
+int32_t sp_graph_destroy(sp_system* sys, int32_t graph_id);
 
 /* ---- kernel functions on the device (tests/test_kernels.jl parity) ------- */
 int32_t sp_kernel_eval(int32_t kernel, int32_t kfun, double h, const double* r, double* out, int64_t n,

@@ -11,7 +11,7 @@
 #   * the closures passed to apply! are registered operators (Operators.balance_of_mass(...), ...).
 module SmoothedParticlesB200
 
-export ParticleSystem, create_cell_list!, build_neighbour_lists!, apply!, respawn!, upload!, download, add_particles!, ParticleField,
+export ParticleSystem, record!, replay!, destroy_graph!, create_cell_list!, build_neighbour_lists!, apply!, respawn!, upload!, download, add_particles!, ParticleField,
        assemble_vector, assemble_matrix, Operators, poisson_cg!, reduce_energy_wcsph, sum_at_points, run_program!, front, cfl_time_step, positions, sp_reduce,
        kernel_eval, wendland1, Dwendland1, rDwendland1, wendland2, Dwendland2, rDwendland2, wendland3, Dwendland3, rDwendland3,
        DDwendland3, spline23, Dspline23, rDspline23, spline24, Dspline24, rDspline24, synchronize, num_removed, key_params,
@@ -277,6 +277,30 @@ function run_program!(sys::ParticleSystem, program::Integer, kernel, m, h, nu, d
     check(ccall((:sp_run_program, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{Float64}, Int32, Int64),
                 sys.handle, Int32(program), F, length(F), prm, length(prm), Int64(nsteps)), sys.handle)
 end
+
+# A loop body recorded once and replayed as one CUDA graph launch (sp_graph_* of include/sp_b200.h):
+#     g = record!(sys, 2) do; step!(sys); end      # runs the body twice as one unit, returns the graph
+#     replay!(sys, g, 500)                          # 1000 more time steps, 500 graph launches
+# The body may only contain apply! / create_cell_list! style calls (nothing that hands data to the host), and the unit
+# must contain an even number of cell-list builds.
+function record!(body::Function, sys::ParticleSystem, repeat::Integer = 2)
+    check(ccall((:sp_graph_begin, LIB), Int32, (Ptr{Cvoid},), sys.handle), sys.handle)
+    gid = Ref{Int32}(-1)
+    try
+        for _ in 1:repeat
+            body()
+        end
+    catch
+        ccall((:sp_graph_end, LIB), Int32, (Ptr{Cvoid}, Ref{Int32}), sys.handle, gid)
+        rethrow()
+    end
+    check(ccall((:sp_graph_end, LIB), Int32, (Ptr{Cvoid}, Ref{Int32}), sys.handle, gid), sys.handle)
+    return gid[]
+end
+replay!(sys::ParticleSystem, graph::Integer, times::Integer = 1) =
+    check(ccall((:sp_graph_launch, LIB), Int32, (Ptr{Cvoid}, Int32, Int64), sys.handle, Int32(graph), Int64(times)), sys.handle)
+destroy_graph!(sys::ParticleSystem, graph::Integer) =
+    check(ccall((:sp_graph_destroy, LIB), Int32, (Ptr{Cvoid}, Int32), sys.handle, Int32(graph)), sys.handle)
 
 # A = assemble_matrix(sys, projection_matrix), src/core.jl:196-225, for hosts that want the matrix itself:
 # returns (I, J, V) — feed them to SparseArrays.sparse(I, J, V, N, N) exactly as the reference does

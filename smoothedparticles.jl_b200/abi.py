@@ -68,6 +68,10 @@ SIGNATURES = {
     "sp_poisson_cg": (_i32, [_p, _pi32, _i32, _pf64, _i32, _f64, _f64, _i64, _pi64, _pf64]),
     "sp_assemble_matrix": (_i32, [_p, _pi32, _i32, _pf64, _i32, _pi64, _pi64, _pf64, _i64, _pi64]),
     "sp_run_program": (_i32, [_p, _i32, _pi32, _i32, _pf64, _i32, _i64]),
+    "sp_graph_begin": (_i32, [_p]),
+    "sp_graph_end": (_i32, [_p, _pi32]),
+    "sp_graph_launch": (_i32, [_p, _i32, _i64]),
+    "sp_graph_destroy": (_i32, [_p, _i32]),
     "sp_kernel_eval": (_i32, [_i32, _i32, _f64, _pf64, _pf64, _i64, _i32]),
     "sp_get_cell_keys": (_i32, [_p, _pi64, _i64]),
     "sp_get_cell_list": (_i32, [_p, _pi64, _pi64]),

@@ -423,8 +423,10 @@ static void sp_adopt_count(sp_system* s) {
 }
 
 int sp_settle(sp_system* s) {
+    // every entry point that hands counts or data to the host comes through here: none of them can be part of a graph
+    if (s->capturing)
+        return sp_fail(s, SP_ERR_STATE, "this call hands data or counts to the host and cannot be recorded into a step graph");
     if (s->n_exact) return SP_OK;
-    if (s->capturing) return sp_fail(s, SP_ERR_STATE, "particle count requested while a step graph is being captured");
     SP_CUDA(s, cudaMemcpyAsync(s->h_counters, s->counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     SP_CUDA(s, cudaStreamSynchronize(s->stream));
     s->count_pending = false;

@@ -128,6 +128,11 @@ struct sp_system {
         double params[16] = {0};
         int32_t fields[8] = {0};
     } graph;
+    // graphs recorded by the host (sp_graph_begin / sp_graph_end)
+    std::vector<StepGraph> user_graphs;
+    unsigned long long rec_sig = 0;  // signature at sp_graph_begin
+    long long rec_launches = 0;
+    bool recording = false;
 
     bool have_cells = false;
     bool capturing = false;   // the stream is being captured into a CUDA graph (sp_program.cu): no host read-backs
@@ -150,6 +155,13 @@ int sp_fail_cuda(sp_system* s, cudaError_t e, const char* what, const char* file
     do {                                                                               \
         cudaError_t _e = (call);                                                       \
         if (_e != cudaSuccess) return sp_fail_cuda((sys), _e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+// entry points that wait for the device cannot be recorded into a step graph
+#define SP_NOT_WHILE_RECORDING(sys)                                                                              \
+    do {                                                                                                         \
+        if ((sys)->capturing)                                                                                    \
+            return sp_fail((sys), SP_ERR_STATE, "this call waits for the device and cannot be recorded into a step graph"); \
     } while (0)
 
 // launch + count + check

@@ -1,6 +1,8 @@
 // sp_program.cu — fused step programs: the time loops of the examples issued from inside the library,
 // so a Julia/Python host pays one FFI crossing per batch of steps instead of 7-9 per step.
 // Same kernels, same order, same arithmetic as the per-call path.
+#include <cstdint>
+
 #include "sp_internal.cuh"
 
 int sp_apply_impl(sp_system* s, int32_t op, const int32_t* F, int32_t nf, const double* Pm, int32_t np, int32_t flags);
@@ -54,7 +56,109 @@ static void drop_graph(sp_system* s) {
     s->graph.exec = nullptr;
     s->graph.sig = 0;
 }
-void sp_program_free(sp_system* s) { drop_graph(s); }
+void sp_program_free(sp_system* s) {
+    drop_graph(s);
+    for (auto& g : s->user_graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    s->user_graphs.clear();
+}
+
+// ------------------------------------------------------------------ host-recorded graphs
+extern "C" int32_t sp_graph_begin(sp_system* s) {
+    if (!s) return SP_ERR_INVALID;
+    if (s->capturing) return sp_fail(s, SP_ERR_STATE, "a recording is already in progress");
+    if (s->slab) return sp_fail(s, SP_ERR_STATE, "step graphs are not available on a slab system");
+    SP_CUDA(s, cudaSetDevice(s->device));
+    s->rec_sig = state_signature(s);
+    s->rec_launches = s->launches;
+    SP_CUDA(s, cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeRelaxed));
+    s->capturing = true;
+    s->recording = true;
+    return SP_OK;
+}
+
+extern "C" int32_t sp_graph_end(sp_system* s, int32_t* graph_id) {
+    if (!s || !graph_id) return SP_ERR_INVALID;
+    *graph_id = -1;
+    if (!s->recording) return sp_fail(s, SP_ERR_STATE, "sp_graph_end without sp_graph_begin");
+    SP_CUDA(s, cudaSetDevice(s->device));
+    s->capturing = false;
+    s->recording = false;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+    if (e != cudaSuccess || !graph) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        return sp_fail(s, SP_ERR_CUDA, std::string("recording failed: ") + cudaGetErrorString(e) +
+                                            " — the recorded calls were NOT executed; the system's state is undefined");
+    }
+    const bool periodic = state_signature(s) == s->rec_sig;
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess || !exec) {
+        cudaGetLastError();
+        return sp_fail(s, SP_ERR_CUDA, "cudaGraphInstantiate failed — the recorded calls were NOT executed");
+    }
+    // the body runs once now: begin/end behaves like the calls it encloses
+    SP_CUDA(s, cudaGraphLaunch(exec, s->stream));
+    s->n_exact = false;
+    s->count_pending = false;
+    if (!periodic) {
+        cudaGraphExecDestroy(exec);
+        return sp_fail(s, SP_ERR_STATE,
+                       "the recorded body was executed once but cannot be replayed: it does not leave the ping-pong buffers "
+                       "where it found them (record an even number of cell-list builds, e.g. two time steps)");
+    }
+    sp_system::StepGraph g;
+    g.exec = exec;
+    g.sig = s->rec_sig;
+    g.launches = s->launches - s->rec_launches;
+    int id = -1;
+    for (size_t i = 0; i < s->user_graphs.size(); i++)
+        if (!s->user_graphs[i].exec) id = (int)i;
+    if (id < 0) {
+        s->user_graphs.push_back(g);
+        id = (int)s->user_graphs.size() - 1;
+    } else
+        s->user_graphs[id] = g;
+    *graph_id = id;
+    return SP_OK;
+}
+
+extern "C" int32_t sp_graph_launch(sp_system* s, int32_t graph_id, int64_t times) {
+    if (!s || times < 0) return SP_ERR_INVALID;
+    if (graph_id < 0 || graph_id >= (int)s->user_graphs.size() || !s->user_graphs[graph_id].exec)
+        return sp_fail(s, SP_ERR_INVALID, "unknown graph id");
+    if (s->capturing) return sp_fail(s, SP_ERR_STATE, "sp_graph_launch inside a recording");
+    SP_CUDA(s, cudaSetDevice(s->device));
+    sp_system::StepGraph& g = s->user_graphs[graph_id];
+    if (g.sig != state_signature(s))
+        return sp_fail(s, SP_ERR_STATE, "the system changed since this graph was recorded (field storage, particle bound or "
+                                        "list capacity): record it again");
+    int rc = sp_time_begin(s);
+    if (rc) return rc;
+    for (int64_t k = 0; k < times; k++) {
+        SP_CUDA(s, cudaGraphLaunch(g.exec, s->stream));
+        s->launches += g.launches;
+    }
+    if (times > 0) {
+        s->n_exact = false;
+        s->count_pending = false;
+    }
+    return sp_time_end(s);
+}
+
+extern "C" int32_t sp_graph_destroy(sp_system* s, int32_t graph_id) {
+    if (!s) return SP_ERR_INVALID;
+    if (graph_id < 0 || graph_id >= (int)s->user_graphs.size() || !s->user_graphs[graph_id].exec)
+        return sp_fail(s, SP_ERR_INVALID, "unknown graph id");
+    SP_CUDA(s, cudaSetDevice(s->device));
+    SP_CUDA(s, cudaStreamSynchronize(s->stream));
+    cudaGraphExecDestroy(s->user_graphs[graph_id].exec);
+    s->user_graphs[graph_id].exec = nullptr;
+    return SP_OK;
+}
 
 // capture `unit` middle steps; on success the graph is instantiated and NOT yet launched (the capture executes nothing)
 static int capture_unit(sp_system* s, int32_t program, const int32_t* F, const double* P, int unit, bool* ok) {
@@ -197,7 +301,7 @@ static int run_program(sp_system* s, int32_t program, const int32_t* F, int32_t 
     // steps [0, nsteps): step 0 opens the run, step nsteps-1 closes it; the steps in between are all alike and are
     // what a graph unit holds.  Two eager steps come first (lazy allocations, list capacity), so a graph pays off
     // from about 8 steps on.
-    const bool use_graph = graphs_enabled() && !slab && nsteps >= 8;
+    const bool use_graph = graphs_enabled() && !slab && nsteps >= 8 && !s->capturing;
     int64_t k = 0;
     auto eager = [&](int64_t upto) -> int {
         for (; k < upto; k++)

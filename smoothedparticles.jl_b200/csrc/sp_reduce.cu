@@ -219,6 +219,7 @@ extern "C" {
 
 int32_t sp_reduce(sp_system* s, int32_t red, const int32_t* F, int32_t nf, const double* Pm, int32_t np, double* out) {
     if (!s || !out) return SP_ERR_INVALID;
+    SP_NOT_WHILE_RECORDING(s);
     SP_CUDA(s, cudaSetDevice(s->device));
     RedParams R{};
     R.cap = s->cap;
@@ -282,6 +283,7 @@ int32_t sp_reduce(sp_system* s, int32_t red, const int32_t* F, int32_t nf, const
 int32_t sp_sum_at_points(sp_system* s, int32_t sum_op, const int32_t* F, int32_t nf, const double* Pm, int32_t np,
                          const double* xyz, int64_t m_pts, double* out) {
     if (!s || !xyz || !out || m_pts < 0) return SP_ERR_INVALID;
+    SP_NOT_WHILE_RECORDING(s);
     SP_CUDA(s, cudaSetDevice(s->device));
     if (!s->have_cells) return sp_fail(s, SP_ERR_STATE, "no cell list: call sp_create_cell_list first");
     int rc;

@@ -21,12 +21,12 @@ int sp_fail_cuda(sp_system* s, cudaError_t e, const char* what, const char* file
 }
 
 int sp_time_begin(sp_system* s) {
-    if (s->in_program) return SP_OK;  // the step program times itself as one call
+    if (s->in_program || s->capturing) return SP_OK;  // the step program times itself as one call; a recording is not timed
     SP_CUDA(s, cudaEventRecord(s->ev0, s->stream));
     return SP_OK;
 }
 int sp_time_end(sp_system* s) {
-    if (s->in_program) return SP_OK;
+    if (s->in_program || s->capturing) return SP_OK;
     SP_CUDA(s, cudaEventRecord(s->ev1, s->stream));
     return SP_OK;
 }
@@ -497,6 +497,7 @@ int32_t sp_download(sp_system* s, int32_t fid, double* host, int64_t n, int32_t 
 
 int32_t sp_synchronize(sp_system* s) {
     if (!s) return SP_ERR_INVALID;
+    SP_NOT_WHILE_RECORDING(s);
     SP_CUDA(s, cudaSetDevice(s->device));
     SP_CUDA(s, cudaStreamSynchronize(s->stream));
     return SP_OK;
@@ -504,6 +505,7 @@ int32_t sp_synchronize(sp_system* s) {
 
 int32_t sp_last_call_ms(sp_system* s, float* ms) {
     if (!s || !ms) return SP_ERR_INVALID;
+    SP_NOT_WHILE_RECORDING(s);
     SP_CUDA(s, cudaSetDevice(s->device));
     SP_CUDA(s, cudaEventSynchronize(s->ev1));
     SP_CUDA(s, cudaEventElapsedTime(ms, s->ev0, s->ev1));
@@ -512,12 +514,14 @@ int32_t sp_last_call_ms(sp_system* s, float* ms) {
 
 int32_t sp_timer_start(sp_system* s) {
     if (!s) return SP_ERR_INVALID;
+    SP_NOT_WHILE_RECORDING(s);
     SP_CUDA(s, cudaSetDevice(s->device));
     SP_CUDA(s, cudaEventRecord(s->tev0, s->stream));
     return SP_OK;
 }
 int32_t sp_timer_stop(sp_system* s, float* ms) {
     if (!s || !ms) return SP_ERR_INVALID;
+    SP_NOT_WHILE_RECORDING(s);
     SP_CUDA(s, cudaSetDevice(s->device));
     SP_CUDA(s, cudaEventRecord(s->tev1, s->stream));
     SP_CUDA(s, cudaEventSynchronize(s->tev1));

@@ -270,6 +270,25 @@ class ParticleSystem:
         abi.check(self._lib.sp_run_program(self._h, program, abi.ptr_i32(F), len(F), abi.ptr_f64(P), len(P),
                                            int(nsteps)), self._h)
 
+    # -- step graphs: a loop body recorded once, replayed as one CUDA graph launch (sp_graph_* of include/sp_b200.h)
+    def record(self, body, repeat: int = 2) -> "StepGraph":
+        """Run ``body()`` ``repeat`` times as ONE recorded unit and return a replayable graph.
+
+        ``body`` is the host's loop body (``lambda: case.step(sys)``): apply / create_cell_list calls only.  The unit is
+        executed once by this call (like the calls it encloses).  ``repeat`` must make the number of cell-list builds in
+        the unit even (2 time steps when a step builds once).  Run the body the ordinary way at least once before."""
+        abi.check(self._lib.sp_graph_begin(self._h), self._h)
+        try:
+            for _ in range(repeat):
+                body()
+        except BaseException:
+            gid = C.c_int32()
+            self._lib.sp_graph_end(self._h, C.byref(gid))   # close the recording; its status is secondary here
+            raise
+        gid = C.c_int32()
+        abi.check(self._lib.sp_graph_end(self._h, C.byref(gid)), self._h)
+        return StepGraph(self, gid.value, repeat)
+
     # -- parity / debug views (1-based, reference order)
     def cell_keys(self) -> np.ndarray:
         n = len(self)
@@ -434,3 +453,19 @@ def kernel_eval(kernel, kfun: int, h: float, r, device: int = 0) -> np.ndarray:
     kid = abi.KERNEL_IDS[kernel] if isinstance(kernel, str) else int(kernel)
     abi.check(lib.sp_kernel_eval(kid, int(kfun), float(h), abi.ptr_f64(r), abi.ptr_f64(out), r.size, device), None)
     return out
+
+
+class StepGraph:
+    """Handle of a recorded loop body (``ParticleSystem.record``): ``replay(k)`` runs the unit k times, one CUDA graph
+    launch each; ``steps_per_replay`` says how many executions of the body one replay is."""
+
+    def __init__(self, system: "ParticleSystem", gid: int, steps_per_replay: int):
+        self._sys, self._gid, self.steps_per_replay = system, gid, steps_per_replay
+
+    def replay(self, times: int = 1):
+        abi.check(self._sys._lib.sp_graph_launch(self._sys._h, self._gid, int(times)), self._sys._h)
+
+    def close(self):
+        if self._gid >= 0 and self._sys._h:
+            self._sys._lib.sp_graph_destroy(self._sys._h, self._gid)
+        self._gid = -1

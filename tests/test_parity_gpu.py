@@ -528,6 +528,38 @@ def test_run_program_2d_equals_per_call_path_and_oracle(nsteps):
         assert np.array_equal(ora.get(nm), ora2.get(nm)), nm
 
 
+@pytest.mark.parametrize("maker", [configs.cavity_flow, configs.collapse_dry, configs.static_container,
+                                   configs.collapse_symplectic])
+def test_recorded_step_graph_equals_the_call_by_call_loop(maker):
+    # sp_graph_begin / sp_graph_end / sp_graph_launch: the loop body of an example recorded once (two steps = an even number
+    # of cell-list builds) and replayed as one CUDA graph launch per unit must be the same computation, bit for bit
+    case = maker()
+    a = case.make(ParticleSystem)
+    b = case.make(ParticleSystem)
+    for s_ in (a, b):
+        case.prologue(s_)
+        for _ in range(2):
+            case.step(s_)                                 # the ordinary way first: lazy allocations happen here
+    g = b.record(lambda: case.step(b), repeat=2)          # executes steps 3-4 and keeps them as a graph
+    g.replay(4)                                           # steps 5-12
+    for _ in range(10):
+        case.step(a)
+    assert len(a) == len(b)
+    names = [nm for nm in ("x", "v", "rho", "P", "Dv", "a") if nm in case.fields or nm == "x"]
+    for nm in names:
+        assert np.array_equal(a.get(nm), b.get(nm)), nm
+    # what cannot be part of a recording is refused, and the system stays usable
+    with pytest.raises(sp.SpError):
+        b.record(lambda: b.get("x"), repeat=1)
+    # an odd number of builds leaves the ping-pong planes swapped: the body is executed once, but there is no graph
+    with pytest.raises(sp.SpError):
+        b.record(lambda: b.create_cell_list(), repeat=1)
+    a.create_cell_list()                                             # ... it DID execute once
+    for nm in names:
+        assert np.array_equal(a.get(nm), b.get(nm)), nm
+    g.close()
+
+
 @pytest.mark.parametrize("shape", [(22, 20, 18), (48, 44, 36)])   # below / above the single-CTA renumbering limit (65 536)
 def test_particles_leaving_the_domain_inside_a_graph_run(shape):
     # removal (core.jl:64-81) with the culled count kept on the device: the outer shell of a lattice block flies apart and

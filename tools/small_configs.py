@@ -55,6 +55,18 @@ def main():
         s, sec, launches = rate(case, ParticleSystem, nsteps, 5 if isph else 20)
         rec = {"config": case.name, "particles": len(s), "device_ms_per_step": 1e3 * sec,
                "device_updates_per_s": len(s) / sec, "launches_per_step": launches}
+        if not isph and case.name != "cylinder":   # (ISPH: the CG reads back; cylinder: respawn reads back)
+            try:
+                g = s.record(lambda: case.step(s), repeat=2)
+                s.synchronize()
+                t0 = time.perf_counter()
+                g.replay(100)
+                s.synchronize()
+                rec["graph_ms_per_step"] = 1e3 * (time.perf_counter() - t0) / 200
+                rec["graph_updates_per_s"] = len(s) / (rec["graph_ms_per_step"] * 1e-3)
+                g.close()
+            except Exception as e:  # noqa: BLE001
+                rec["graph_failed"] = str(e)[:200]
         if case.program:
             s.run_program(case.program, case.program_fields, case.program_params, 20)
             s.synchronize()
@@ -70,6 +82,10 @@ def main():
             rec["oracle_updates_per_s"] = len(so) / sec_o
             rec["oracle_threads"] = oracle.max_threads() if hasattr(oracle, "max_threads") else os.cpu_count()
             rec["speedup_per_call"] = sec_o / sec
+            if "graph_ms_per_step" in rec:
+                rec["speedup_graph"] = 1e3 * sec_o / rec["graph_ms_per_step"]
+            if "program_ms_per_step" in rec:
+                rec["speedup_program"] = 1e3 * sec_o / rec["program_ms_per_step"]
         out.append(rec)
         print(json.dumps(rec), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
