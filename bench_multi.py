@@ -35,8 +35,8 @@ def workload_name(workload: str, world: int, dr: float, per: int) -> str:
                 f"(h = 2 dr, jitter 0.1 dr, collapse3d step)")
     if world == 1:
         return "examples/collapse3d.jl dam break scaled to 10 M particles (dr=%g)" % dr
-    return (f"examples/collapse3d.jl dam break, dr={dr:g}, box depth x{world} along z (one 10 M-particle copy of "
-            f"the N=1 workload per GPU), slab-decomposed along z")
+    return (f"examples/collapse3d.jl dam break, dr={dr:g}, box extruded along z to {world} x the particle count of the N=1 "
+            f"workload, slab-decomposed along z with count-balanced cuts")
 
 
 def init_control_plane():
@@ -91,12 +91,43 @@ def run_slab_workload(args, workload, UNIT, ClockSampler, e2e=True, breakdown=Tr
         h = 2.0 * dr
         g = (0.0, 0.0, -9.8)
         wall = 2.5 * dr
-        dom = geo.Box(-wall, -wall, -wall, 0.584 + wall, 0.35 + wall, 0.15 * world + wall)
+        # WEAK scaling: every GPU gets the particle count of the N = 1 workload.  The two end walls exist once per job,
+        # not once per GPU, so the box is a little deeper than N x 0.15, and the slabs are cut by particle count, not by
+        # layer count (the end layers are full planes of wall particles, ~4x as dense as a fluid layer).  Both follow
+        # from two numbers every rank measures on a thin slice of the lattice: particles per interior cell layer (f)
+        # and per end-wall layer (w).
+        probe = configs.collapse3d(dr, depth_scale=1.0, z_range=(-wall - dr, 3.0 * h + 0.5 * dr))
+        pl = np.floor(probe.init["x"][:, 2] / h).astype(np.int64) - int(np.floor(-wall / h))
+        head = np.bincount(pl, minlength=5)[:5]          # layers 0..4 from the lower domain face
+        f_layer = float(head[4])                          # an interior layer (two lattice planes of fluid + side walls)
+        end_layers = head[:2].astype(float)               # the layers that hold the end wall
+        del probe
+        n_wall_end = float(end_layers.sum())
+
+        def total_for(depth):
+            gl = int(np.floor((depth + wall) / h)) - int(np.floor(-wall / h)) + 1
+            return 2.0 * n_wall_end + f_layer * (gl - 4), gl
+
+        n1, _ = total_for(0.15)
+        depth = 0.15 * world
+        if world > 1:
+            # the depth at which the job holds world x n1 particles (whole cell layers)
+            gl_target = 4 + int(round((world * n1 - 2.0 * n_wall_end) / f_layer))
+            depth = (gl_target - 1 + int(np.floor(-wall / h))) * h - wall + 0.5 * h
+        dom = geo.Box(-wall, -wall, -wall, 0.584 + wall, 0.35 + wall, depth + wall)
         gphase = int(np.floor(dom.lo[2] / h))
         glim = int(np.floor(dom.hi[2] / h)) - gphase + 1
-        c0, c1 = slab.partition_layers(glim, world)[rank]
+        layer_counts = np.full(glim, f_layer)
+        layer_counts[:2] = end_layers
+        # the far end: how the wall falls onto the cell layers depends on the depth, so it is measured as well
+        probe = configs.collapse3d(dr, depth_scale=depth / 0.15, z_range=((gphase + glim - 4) * h, depth + wall + dr))
+        tl = np.floor(probe.init["x"][:, 2] / h).astype(np.int64) - gphase
+        layer_counts[glim - 4:] = np.bincount(tl, minlength=glim)[glim - 4:]
+        del probe
+        cuts = slab.balanced_cuts(layer_counts, world) if world > 1 else None
+        c0, c1 = (cuts[rank], cuts[rank + 1]) if cuts else (0, glim)
         zlo, zhi = (gphase + c0) * h - dr, (gphase + c1) * h + dr      # generous: ownership is decided below
-        case = configs.collapse3d(dr, depth_scale=world, z_range=(zlo, zhi))
+        case = configs.collapse3d(dr, depth_scale=depth / 0.15, z_range=(zlo, zhi))
         x = case.init["x"]
         cell = np.floor(x[:, 2] / h).astype(np.int64) - gphase
         mine = (cell >= c0) & (cell < c1)
@@ -106,6 +137,7 @@ def run_slab_workload(args, workload, UNIT, ClockSampler, e2e=True, breakdown=Tr
         periodic = False
         assert np.allclose(case.domain.lo, dom.lo) and np.allclose(case.domain.hi, dom.hi), (case.domain, dom)
         dom = case.domain
+    slab_cuts = cuts if workload != "box" else None
     wname = workload_name(workload, world, args.dr, per)
     m = rho0 * dr ** 3
     dt = 0.1 * h / c
@@ -115,7 +147,7 @@ def run_slab_workload(args, workload, UNIT, ClockSampler, e2e=True, breakdown=Tr
              force=ops.internal_force("wendland3", m, h, mu, rho0), move=ops.move(dt), acc=ops.accelerate(0.5 * dt, g))
 
     def make_system():
-        return slab.SlabSystem(fields, dom, h, rank, world, fresh_id(), periodic=periodic, device=local)
+        return slab.SlabSystem(fields, dom, h, rank, world, fresh_id(), periodic=periodic, device=local, cuts=slab_cuts)
 
     sysd = make_system()
     assert np.all(sysd.owns(x)), "generator and slab partition disagree"
@@ -144,10 +176,14 @@ def run_slab_workload(args, workload, UNIT, ClockSampler, e2e=True, breakdown=Tr
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t[0])
     n_tot = int(sysd.allreduce([sysd.n_owned])[0])
+    cnts = np.zeros(world)
+    cnts[rank] = sysd.n_owned
+    sysd_counts = sysd.allreduce(cnts)
     n_ghost = len(sysd) - sysd.n_owned
     value = n_tot * args.steps / (ms_max * 1e-3)
     out = {"workload": wname, "value": value, "ms_per_step": ms_max / args.steps, "particles": n_tot,
            "particles_per_gpu": n_local, "ghosts_per_gpu": int(n_ghost), "setup_s": round(gen_s, 1), "clocks": clocks,
+           "particles_per_gpu_all": [int(v) for v in sysd_counts],
            "gpu_launches": int(gpu_launches), "n_slots": n_local + int(n_ghost)}
 
     if breakdown:
@@ -261,7 +297,8 @@ def run_multi(args, METRIC, UNIT, ClockSampler, peaks):
             "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": r["workload"], "particles": r["particles"],
-                       "particles_per_gpu": r["particles_per_gpu"], "ghosts_per_gpu": r["ghosts_per_gpu"],
+                       "particles_per_gpu": r["particles_per_gpu"], "particles_per_gpu_all": r["particles_per_gpu_all"],
+                       "ghosts_per_gpu": r["ghosts_per_gpu"],
                        "l2": "state >= 1 GB per GPU >> 126 MB L2, no flush needed", "setup_s": r["setup_s"],
                        "parallelism": f"slab{world}", "energy": r["energy"]},
             "clocks": r["clocks"], "e2e": r["e2e"], "gpu_launches": r["gpu_launches"],

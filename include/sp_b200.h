@@ -530,6 +530,11 @@ int32_t sp_launch_count(sp_system* sys, int64_t* launches);
  * the global box must then start and end on cell faces along that axis. */
 int32_t sp_slab_unique_id(uint8_t id[128]);
 int32_t sp_slab_init(sp_system* sys, const uint8_t id[128], int32_t rank, int32_t nranks, int32_t periodic);
+/* The same with the caller's cut planes instead of equal layer counts: rank r owns the cell layers [cuts[r], cuts[r+1])
+ * (0-based from the global key_phase of the slab axis; cuts[0] = 0, cuts[nranks] = key_lim[axis]; at least three layers
+ * per rank).  A host that knows how many particles each layer holds balances the particle counts with it. */
+int32_t sp_slab_init_cuts(sp_system* sys, const uint8_t id[128], int32_t rank, int32_t nranks, int32_t periodic,
+                          const int64_t* cuts);
 /* Owned cell layers [cell_lo, cell_hi) (0-based from the global key_phase) and their coordinate interval. */
 int32_t sp_slab_range(sp_system* sys, int64_t* cell_lo, int64_t* cell_hi, double* coord_lo, double* coord_hi,
                       int32_t* axis);

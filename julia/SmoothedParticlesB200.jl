@@ -480,9 +480,17 @@ function slab_unique_id()
     check(ccall((:sp_slab_unique_id, LIB), Int32, (Ptr{UInt8},), id))
     return id                                     # rank 0 sends these 128 bytes to the other ranks (MPI.jl / sockets)
 end
-slab_init!(sys::ParticleSystem, id::Vector{UInt8}, rank::Integer, nranks::Integer; periodic::Bool = false) =
-    check(ccall((:sp_slab_init, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32, Int32), sys.handle, id, Int32(rank),
-                Int32(nranks), Int32(periodic)), sys.handle)
+# cuts (optional): rank r owns the cell layers cuts[r+1] .. cuts[r+2]-1 (0-based layer numbers; count-balanced slabs)
+function slab_init!(sys::ParticleSystem, id::Vector{UInt8}, rank::Integer, nranks::Integer; periodic::Bool = false,
+                    cuts::Union{Nothing, Vector{Int64}} = nothing)
+    if cuts === nothing
+        check(ccall((:sp_slab_init, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32, Int32), sys.handle, id, Int32(rank),
+                    Int32(nranks), Int32(periodic)), sys.handle)
+    else
+        check(ccall((:sp_slab_init_cuts, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32, Int32, Ptr{Int64}), sys.handle, id,
+                    Int32(rank), Int32(nranks), Int32(periodic), cuts), sys.handle)
+    end
+end
 function slab_range(sys::ParticleSystem)          # the cell layers [cell_lo, cell_hi) and coordinates this rank owns
     clo = Ref{Int64}(0); chi = Ref{Int64}(0); xlo = Ref{Float64}(0.0); xhi = Ref{Float64}(0.0); axis = Ref{Int32}(0)
     check(ccall((:sp_slab_range, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Float64}, Ref{Float64}, Ref{Int32}),

@@ -89,6 +89,7 @@ SIGNATURES = {
     "sp_launch_count": (_i32, [_p, _pi64]),
     "sp_slab_unique_id": (_i32, [C.POINTER(C.c_uint8)]),
     "sp_slab_init": (_i32, [_p, C.POINTER(C.c_uint8), _i32, _i32, _i32]),
+    "sp_slab_init_cuts": (_i32, [_p, C.POINTER(C.c_uint8), _i32, _i32, _i32, _pi64]),
     "sp_slab_range": (_i32, [_p, _pi64, _pi64, _pf64, _pf64, _pi32]),
     "sp_slab_create_cell_list": (_i32, [_p]),
     "sp_slab_halo_refresh": (_i32, [_p, _pi32, _i32]),

@@ -750,6 +750,11 @@ int32_t sp_slab_unique_id(uint8_t id[128]) {
 }
 
 int32_t sp_slab_init(sp_system* s, const uint8_t id[128], int32_t rank, int32_t nranks, int32_t periodic) {
+    return sp_slab_init_cuts(s, id, rank, nranks, periodic, nullptr);
+}
+
+int32_t sp_slab_init_cuts(sp_system* s, const uint8_t id[128], int32_t rank, int32_t nranks, int32_t periodic,
+                          const int64_t* cuts) {
     if (!s || !id) return SP_ERR_INVALID;
     if (nranks < 1 || rank < 0 || rank >= nranks) return sp_fail(s, SP_ERR_INVALID, "bad rank / nranks");
     if (s->slab) return sp_fail(s, SP_ERR_STATE, "slab already initialised");
@@ -758,11 +763,28 @@ int32_t sp_slab_init(sp_system* s, const uint8_t id[128], int32_t rank, int32_t 
     if (!nccl_load()) return sp_fail(s, SP_ERR_NCCL, g_nccl.err);
     SpGrid& g = s->g;
     const int axis = g.dim == 2 ? 1 : 2;  // slowest key axis
+    // owned layers [c0, c1): equal layer counts, or the caller's cut planes (count-balanced slabs: SURVEY 8(e))
+    long long c0, c1;
+    if (cuts) {
+        if (cuts[0] != 0 || cuts[nranks] != g.lim[axis]) return sp_fail(s, SP_ERR_INVALID, "cuts must start at 0 and end at key_lim");
+        for (int r = 0; r < nranks; r++)
+            if (cuts[r + 1] <= cuts[r]) return sp_fail(s, SP_ERR_INVALID, "cuts must be increasing");
+        c0 = cuts[rank];
+        c1 = cuts[rank + 1];
+    } else {
+        const long long base = g.lim[axis] / nranks, rem = g.lim[axis] % nranks;
+        c0 = rank * base + std::min<long long>(rank, rem);
+        c1 = c0 + base + (rank < rem ? 1 : 0);
+    }
     // three owned layers per rank: the two boundary layers facing one neighbour must not receive migrants from the other
     // (that is what makes a rank's boundary layers and its neighbour's ghost layers the same particle sets)
     if (nranks > 1 || periodic) {
-        if (g.lim[axis] < 3LL * nranks)
-            return sp_fail(s, SP_ERR_INVALID, "fewer than three cell layers per rank along the slab axis");
+        bool ok = true;
+        if (cuts)
+            for (int r = 0; r < nranks; r++) ok = ok && cuts[r + 1] - cuts[r] >= 3;
+        else
+            ok = g.lim[axis] >= 3LL * nranks;
+        if (!ok) return sp_fail(s, SP_ERR_INVALID, "fewer than three cell layers per rank along the slab axis");
     }
     SlabState* sl = new SlabState();
     sl->rank = rank;
@@ -771,9 +793,8 @@ int32_t sp_slab_init(sp_system* s, const uint8_t id[128], int32_t rank, int32_t 
     sl->axis = axis;
     sl->gphase = g.phase[axis];
     sl->glim = g.lim[axis];
-    const long long base = sl->glim / nranks, rem = sl->glim % nranks;
-    sl->c0 = rank * base + std::min<long long>(rank, rem);
-    sl->c1 = sl->c0 + base + (rank < rem ? 1 : 0);
+    sl->c0 = c0;
+    sl->c1 = c1;
     sl->period = (double)sl->glim * g.h;
     s->slab = sl;
     ncclUniqueId u;

@@ -31,6 +31,25 @@ def partition_layers(n_layers: int, nranks: int) -> list:
     return out
 
 
+def balanced_cuts(layer_counts: Sequence[int], nranks: int, min_layers: int = 3) -> list:
+    """Cut planes that balance the particle counts: ``layer_counts[l]`` particles in cell layer l -> nranks + 1 layer
+    numbers, every slab at least ``min_layers`` layers thick (sp_slab_init_cuts).  Greedy on the cumulative count: the
+    r-th cut goes where the running total is closest to r/nranks of all particles."""
+    cnt = np.asarray(layer_counts, dtype=np.float64)
+    nl = len(cnt)
+    assert nl >= min_layers * nranks, "too few cell layers for this many ranks"
+    cum = np.concatenate([[0.0], np.cumsum(cnt)])
+    cuts = [0]
+    for r in range(1, nranks):
+        target = cum[-1] * r / nranks
+        lo = cuts[-1] + min_layers
+        hi = nl - min_layers * (nranks - r)
+        c = int(np.argmin(np.abs(cum[lo:hi + 1] - target))) + lo
+        cuts.append(c)
+    cuts.append(nl)
+    return cuts
+
+
 def owner_of(x_axis: np.ndarray, h: float, key_phase_axis: int, layers: list) -> np.ndarray:
     """Rank owning each coordinate along the slab axis (same floor(x/h) as find_key, src/structs.jl:99-101).
     Returns -1 for coordinates outside every slab."""
@@ -53,13 +72,21 @@ class SlabSystem(ParticleSystem):
     domain and h, then adds only the particles it owns (``owner_of``)."""
 
     def __init__(self, particle_fields, domain, h, rank: int, nranks: int, nccl_id: bytes, periodic: bool = False,
-                 device: int = 0):
+                 device: int = 0, cuts: Sequence[int] | None = None):
+        """cuts: optional ``nranks + 1`` cell-layer numbers (0 .. key_lim[axis]); rank r owns layers [cuts[r], cuts[r+1]).
+        Default: equal layer counts (``partition_layers``); ``balanced_cuts`` balances particle counts instead."""
         super().__init__(particle_fields, domain, h, device=device)
         self.global_key_phase = self.key_phase
         self.global_key_lim = self.key_lim
         self.rank, self.nranks, self.periodic = rank, nranks, periodic
         idbuf = (C.c_uint8 * 128).from_buffer_copy(nccl_id)
-        abi.check(self._lib.sp_slab_init(self._h, idbuf, rank, nranks, 1 if periodic else 0), self._h)
+        if cuts is None:
+            abi.check(self._lib.sp_slab_init(self._h, idbuf, rank, nranks, 1 if periodic else 0), self._h)
+        else:
+            carr = np.ascontiguousarray(cuts, dtype=np.int64)
+            assert carr.size == nranks + 1
+            abi.check(self._lib.sp_slab_init_cuts(self._h, idbuf, rank, nranks, 1 if periodic else 0, abi.ptr_i64(carr)),
+                      self._h)
         for hidden in ("_ghost", "_gid"):
             fid = C.c_int32()
             abi.check(self._lib.sp_find_field(self._h, hidden.encode(), C.byref(fid)), self._h)
