@@ -226,6 +226,7 @@ int sp_publish_count(sp_system* s);
 static inline const int* sp_alive(const sp_system* s) { return s->counters + SP_CNT_ALIVE; }
 // |u| bound of the FP32 pre-filter coordinates (sp_sweep.cu: sp_ensure_prefilter), also used by the cell-list permute
 float sp_prefilter_range(const sp_system* s);
+int sp_self_visits(const sp_system* s);  // sp_sweep.cu: visits of the own cell by the stencil (diagonal multiplicity)
 void sp_slab_host_touched(sp_system* s);  // positions / particle set changed by the host: full selection next time
 const double* sp_slab_ghost_mask(sp_system* s);  // nullptr unless a slab system: 0 = owned, 1/2 = ghost
 const double* sp_slab_gid(sp_system* s);         // nullptr unless a slab system: the global id plane (in-cell order)

@@ -311,23 +311,24 @@ extern "C" int32_t sp_poisson_cg(sp_system* s, const int32_t* F, int32_t nf, con
 }
 
 // ------------------------------------------------------------------ assemble_matrix as COO triplets
-__global__ void __launch_bounds__(256) k_coo_counts(const int* __restrict__ cnt, int* __restrict__ off, long long n) {
+__global__ void __launch_bounds__(256) k_coo_counts(const int* __restrict__ cnt, int* __restrict__ off, long long n, int mult) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i < n) off[i] = cnt[i] + 1;  // the neighbours and the diagonal
+    if (i < n) off[i] = cnt[i] + mult;  // the neighbours and the diagonal (once per visit of the own cell)
 }
 __global__ void __launch_bounds__(128) k_coo_export(long long n, int capk, const int* __restrict__ cnt,
                                                     const int* __restrict__ ids, const double* __restrict__ aval,
                                                     const double* __restrict__ diag, const int* __restrict__ ref,
                                                     const int* __restrict__ off, long long* __restrict__ I,
-                                                    long long* __restrict__ J, double* __restrict__ V) {
+                                                    long long* __restrict__ J, double* __restrict__ V, int mult) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     long long o = off[i];
     const long long row = (long long)ref[i] + 1;  // 1-based index in the reference's sys.particles
-    I[o] = row;
-    J[o] = row;
-    V[o] = diag[i];
-    o++;
+    for (int v = 0; v < mult; v++, o++) {  // diag[i] is the sum over the visits; the reference pushes one triplet per visit
+        I[o] = row;
+        J[o] = row;
+        V[o] = diag[i] / (double)mult;
+    }
     const size_t base = ((size_t)(i >> 5) * capk << 5) + (i & 31);
     const int n_nb = cnt[i];
     for (int k = 0; k < n_nb; k++, o++) {
@@ -379,7 +380,7 @@ extern "C" int32_t sp_assemble_matrix(sp_system* s, const int32_t* F, int32_t nf
     } while (0)
     SP_TRY(sp_dmalloc(&d_off, (size_t)(n + 1) * sizeof(int)));
     {
-        k_coo_counts<<<sp_blocks(n, 256), 256, 0, s->stream>>>(s->nbr_cnt, d_off, n);
+        k_coo_counts<<<sp_blocks(n, 256), 256, 0, s->stream>>>(s->nbr_cnt, d_off, n, sp_self_visits(s));
         s->launches++;
         SP_TRY(cudaGetLastError());
     }
@@ -426,7 +427,7 @@ extern "C" int32_t sp_assemble_matrix(sp_system* s, const int32_t* F, int32_t nf
     SP_TRY(sp_dmalloc(&dJ, (size_t)total * sizeof(long long)));
     SP_TRY(sp_dmalloc(&dV, (size_t)total * sizeof(double)));
     {
-        k_coo_export<<<sp_blocks(n, 128), 128, 0, s->stream>>>(n, capk, cnt, ids, aval, diag, s->ref, d_off, dI, dJ, dV);
+        k_coo_export<<<sp_blocks(n, 128), 128, 0, s->stream>>>(n, capk, cnt, ids, aval, diag, s->ref, d_off, dI, dJ, dV, sp_self_visits(s));
         s->launches++;
         SP_TRY(cudaGetLastError());
     }

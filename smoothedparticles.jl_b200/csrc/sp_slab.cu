@@ -34,7 +34,23 @@
 //
 // NCCL is loaded lazily with dlopen, so the single-GPU library has no NCCL dependency.
 #include <dlfcn.h>
+#if defined(__has_include)
+#if __has_include(<nccl.h>)
 #include <nccl.h>
+#define SP_HAVE_NCCL_H 1
+#endif
+#endif
+#ifndef SP_HAVE_NCCL_H
+// Building without the NCCL headers: the few declarations this file uses (NCCL is only ever reached through dlopen, so
+// a machine without NCCL builds and runs the single-GPU library; sp_slab_* then fails with SP_ERR_NCCL at run time).
+extern "C" {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef enum { ncclSuccess = 0 } ncclResult_t;
+typedef enum { ncclInt32 = 2, ncclFloat64 = 8 } ncclDataType_t;
+typedef enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3 } ncclRedOp_t;
+}
+#endif
 
 #include <cmath>
 #include <cstdio>

@@ -1918,6 +1918,14 @@ __global__ void __launch_bounds__(128) k_poisson_coeffs(SweepCtx c, const int* _
     }
 }
 
+// how many of the 9/27 stencil offsets are zero = how often the reference visits a particle's own cell (1, except on
+// domains with fewer than three cells along an axis: the double-visit quirk of the linear key offsets)
+int sp_self_visits(const sp_system* s) {
+    int m = 0;
+    for (int k = 0; k < s->n_key_diff; k++) m += s->key_diff[k] == 0;
+    return m < 1 ? 1 : m;
+}
+
 // fields {x, L, lambda, type}; params {kernel, m, h, rho, C_free}; aval: cap*capk doubles, diag: n doubles
 int sp_poisson_ell_build(sp_system* s, const int32_t* F, const double* Pm, double* aval, double* diag, int* d_overflow,
                          const int** ids_out, const int** cnt_out) {
@@ -1928,7 +1936,8 @@ int sp_poisson_ell_build(sp_system* s, const int32_t* F, const double* Pm, doubl
     SpKC kc;
     const int kernel = (int)Pm[0];
     if (!sp_make_kc(kernel, Pm[2], &kc)) return sp_fail(s, SP_ERR_INVALID, "unknown SPH kernel id");
-    const double off_coef = 2.0 * (Pm[2] * Pm[2]) * Pm[1] / Pm[3], h2 = Pm[2] * Pm[2], C_free = Pm[4];
+    const double mult = (double)sp_self_visits(s);  // the diagonal is the SUM over the visits of the own cell
+    const double off_coef = 2.0 * (Pm[2] * Pm[2]) * Pm[1] / Pm[3], h2 = Pm[2] * Pm[2] * mult, C_free = Pm[4] * mult;
     const double *L = sc(s, F[1]), *lam = sc(s, F[2]), *ty = sc(s, F[3]);
     const unsigned nb = sp_blocks(s->n, 128);
     switch (kernel) {
@@ -1996,8 +2005,11 @@ int sp_poisson_apply_impl(sp_system* s, const int32_t* F, int32_t nf, const doub
         P.qp[0] = sc(s, F[4]);
         P.y = sc(s, F[5]);
         P.off_coef = 2.0 * (Pm[2] * Pm[2]) * Pm[1] / Pm[3];
-        P.h2 = Pm[2] * Pm[2];
-        P.C_free = Pm[4];
+        // assemble_matrix does not skip p == q (core.jl:196-225): the diagonal entry is pushed once per visit of the own
+        // cell and sparse() sums them — more than once only on domains with fewer than three cells along an axis
+        const double mult = (double)sp_self_visits(s);
+        P.h2 = Pm[2] * Pm[2] * mult;
+        P.C_free = Pm[4] * mult;
     });
 }
 #undef NEED

@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 
 #include "sp_internal.cuh"
 
@@ -38,11 +39,13 @@ struct PoolState {
     cudaStream_t stream = nullptr;
 };
 PoolState g_pool[64];
+std::once_flag g_pool_once[64];
 PoolState& pool_for_current_device() {
     int dev = 0;
     cudaGetDevice(&dev);
     PoolState& ps = g_pool[dev & 63];
-    if (!ps.tried) {
+    // handles are not thread-safe, but two threads may create their first handles on one device at the same time
+    std::call_once(g_pool_once[dev & 63], [&ps, dev]() {
         ps.tried = true;
         int supported = 0;
         cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, dev);
@@ -56,7 +59,7 @@ PoolState& pool_for_current_device() {
                 ps.use_pool = true;
         }
         cudaGetLastError();
-    }
+    });
     return ps;
 }
 }  // namespace

@@ -197,16 +197,33 @@ def read_pvd(path: str) -> Sequence[Tuple[float, str]]:
     return [(float(t), f) for t, f in re.findall(r'<DataSet[^>]*timestep="([^"]*)"[^>]*file="([^"]*)"', text)]
 
 
-def import_particles(sys, path: str) -> int:
-    """``import_particles!(sys, path, constructor)``: the points of the file become new particles at the end of the
-    reference order, and every point-data array whose name and width match a field of the system is copied into
-    it; other fields of the new particles are zero (the constructor's defaults in the reference's usage)."""
+def import_particles(sys, path: str, constructor=None, **constants) -> int:
+    """``import_particles!(sys, path, particle_constructor)`` (src/IO.jl): the points of the file become new particles at
+    the end of the reference order.  The reference builds every particle with the caller's constructor — which sets
+    non-zero defaults such as ``rho0`` or ``m`` — and then overwrites the fields present in the file.  Here the defaults
+    come either as ``**constants`` (field name -> scalar or per-component tuple, as in ``generate_particles``) or from
+    ``constructor(x)``, a callable that gets the (n, 3) positions and returns a ``{field: array or scalar}`` dict; every
+    point-data array of the file whose name and width match a field of the system is then laid over them.  Fields named
+    by neither stay zero."""
     pts, fields = read_vtp(path)
-    arrays = {"x": pts}
+    n = pts.shape[0]
+    arrays = {}
+    defaults = dict(constants)
+    if constructor is not None:
+        defaults.update(constructor(pts))
+    for name, val in defaults.items():
+        if name == "x":
+            continue
+        if name not in sys.fields:
+            raise KeyError(f"import_particles: the system has no field '{name}'")
+        nc = sys.fields[name]
+        a = np.asarray(val, dtype=np.float64)
+        arrays[name] = np.broadcast_to(a, (n,) if nc == 1 else (n, nc)).copy()
     for name, a in fields.items():
         if name in sys.fields and name != "x":
             nc = sys.fields[name]
             if (a.ndim == 1 and nc == 1) or (a.ndim == 2 and a.shape[1] == nc):
                 arrays[name] = a
+    arrays["x"] = pts
     sys.add_particles(**arrays)
-    return pts.shape[0]
+    return n

@@ -44,3 +44,25 @@ def test_save_and_import_round_trip(tmp_path):
         if len(new) == len(sys_):
             spio.import_particles(new, str(tmp_path / "test_IO" / "frame0.vtp"))   # "import even more particles"
             assert len(new) == 2 * len(sys_)
+
+
+def test_import_keeps_the_constructor_defaults(tmp_path):
+    # import_particles!(sys, path, constructor): fields the file does not carry keep what the constructor sets
+    # (src/IO.jl; examples/cylinder.jl relies on it for rho0 and m)
+    dr = 1 / 40
+    src = _make_sys()
+    x = geo.covering(geo.Hexagrid(dr), geo.Circle(0.0, 0.0, 1.0))
+    s, v, M = _get_vars(x)
+    src.add_particles(x=x, s=s, v=v, M=M)
+    out = spio.new_pvd_file(str(tmp_path / "defaults"))
+    spio.save_frame(out, src, "s", "v")                          # M is NOT in the file
+    dst = ParticleSystem({"s": 1, "v": 3, "M": 9, "m": 1, "w": 3}, geo.Circle(0.0, 0.0, 1.0), 0.1)
+    n = spio.import_particles(dst, str(tmp_path / "defaults" / "frame0.vtp"), m=2.5, w=(1.0, 2.0, 3.0), s=-7.0)
+    assert n == len(x) == len(dst)
+    assert np.array_equal(dst.get("s"), s) and np.array_equal(dst.get("v"), v)      # the file wins over the default
+    assert np.all(dst.get("m") == 2.5) and np.all(dst.get("w") == np.array([1.0, 2.0, 3.0]))
+    assert np.all(dst.get("M") == 0.0)
+    n2 = spio.import_particles(dst, str(tmp_path / "defaults" / "frame0.vtp"),
+                               constructor=lambda X: {"m": X[:, 0] ** 2, "M": np.eye(3).ravel()})
+    assert np.array_equal(dst.get("m")[n:], dst.get("x")[n:, 0] ** 2)
+    assert np.all(dst.get("M")[n:] == np.eye(3).ravel()) and len(dst) == n + n2

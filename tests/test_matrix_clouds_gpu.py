@@ -100,3 +100,35 @@ def test_device_cell_list_on_random_clouds(dim):
             xs = ora.get("x") + rng.uniform(-0.3, 0.3, (m, 3)) * h * (1.0 if dim == 3 else np.array([1.0, 1.0, 0.0]))
             dev.set("x", xs)
             ora.set("x", xs)
+
+
+def test_assemble_matrix_on_a_narrow_domain_counts_the_diagonal_per_visit():
+    # core.jl:196-225 does not skip p == q: on a domain with fewer than three cells along an axis the linear key offsets
+    # visit a particle's own cell more than once, the diagonal triplet is pushed once per visit and sparse() sums them.
+    # Export, matrix-free operator and CG operator must all be that matrix.
+    import scipy.sparse as sps
+    from smoothedparticles_jl_b200 import geometry as geo, operators as ops
+    rng = np.random.default_rng(12)
+    h = 0.1
+    box = geo.Box(0.0, 0.0, 0.0, 0.05, 1.0, 0.0)            # 1 x 11 x 1 cells: offsets di + 1*dj, three of them zero
+    n = 70                                                  # ~14 distinct neighbours, each visited three times
+    x = np.column_stack([rng.uniform(0.0, 0.05, n), rng.uniform(0.0, 1.0, n), np.zeros(n)])
+    fields = {"L": 1, "lambda": 1, "type": 1, "P": 1, "y": 1}
+    vals = dict(L=rng.uniform(0.5, 2.0, n), type=(rng.uniform(size=n) < 0.3).astype(float))
+    vals["lambda"] = rng.uniform(-1.0, 1.0, n)
+    dev, ora = ParticleSystem(fields, box, h), OracleSystem(fields, box, h)
+    for s in (dev, ora):
+        s.add_particles(x=x, **vals)
+        s.create_cell_list()
+    assert sum(1 for d in ora.key_diff if d == 0) > 1, "the test needs a domain with repeated visits of the own cell"
+    A = ops.isph_projection_matrix("spline23", 1.0e-3, h, 1.0, 0.7)
+    Io, Jo, Vo = ora.assemble_matrix(A)
+    Id, Jd, Vd = dev.assemble_matrix(A)
+    assert len(Id) == len(Io)
+    Ao = sps.coo_matrix((Vo, (Io - 1, Jo - 1)), shape=(n, n)).tocsr()
+    Ad = sps.coo_matrix((Vd, (Id - 1, Jd - 1)), shape=(n, n)).tocsr()
+    assert abs(Ao - Ad).max() <= 1e-10 * np.max(np.abs(Ao.data))
+    p = rng.uniform(-1, 1, n)
+    dev.set("P", p)
+    dev.poisson_apply(A, "P", "y")
+    assert np.max(np.abs(dev.get("y") - Ao @ p)) <= 1e-10 * np.max(np.abs(Ao @ p))
