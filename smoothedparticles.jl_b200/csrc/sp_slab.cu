@@ -56,7 +56,6 @@ typedef enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3 } ncclRedOp_t
 #include <cstdio>
 #include <cstring>
 
-#include <time.h>
 #include <cstdio>
 
 #include "sp_internal.cuh"
@@ -138,12 +137,6 @@ static bool slab_trace_on() {
     static const bool on = getenv("SP_SLAB_TRACE") && atoi(getenv("SP_SLAB_TRACE"));
     return on;
 }
-static double slab_now() {
-    timespec ts;
-    clock_gettime(CLOCK_MONOTONIC, &ts);
-    return ts.tv_sec + 1e-9 * ts.tv_nsec;
-}
-
 #define SP_NCCL(s, call)                                                                                  \
     do {                                                                                                  \
         ncclResult_t _r = (call);                                                                         \
@@ -568,10 +561,12 @@ static int slab_rebuild(sp_system* s) {
     int below, above;
     slab_peers(sl, &below, &above);
     const bool trace = slab_trace_on();
-    double t0 = 0, t1 = 0, t2 = 0;
+    // SP_SLAB_TRACE=1: device time of the phases from events on the stream (one synchronisation at the end of the call)
+    static thread_local cudaEvent_t tev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     if (trace) {
-        cudaStreamSynchronize(s->stream);
-        t0 = slab_now();
+        for (auto& e : tev)
+            if (!e) cudaEventCreate(&e);
+        cudaEventRecord(tev[0], s->stream);
     }
     const bool steady = sl->history >= 2 && s->have_cells;
     long long cap_send[2] = {0, 0}, cap_recv[2] = {0, 0};
@@ -672,16 +667,14 @@ static int slab_rebuild(sp_system* s) {
         for (int d = 0; d < 2; d++)
             if (cap_send[d]) SP_CUDA(s, cudaMemsetAsync(sl->sendbuf[d], 0, SLAB_HDR * sizeof(double), s->stream));
     }
-    if (trace) {
-        cudaStreamSynchronize(s->stream);
-        t1 = slab_now();
-    }
+    if (trace) cudaEventRecord(tev[1], s->stream);
     // 4: one exchange
     if ((rc = slab_exchange_payload(s, cap_send[0] ? SLAB_HDR + cap_send[0] * nplanes : 0,
                                     cap_send[1] ? SLAB_HDR + cap_send[1] * nplanes : 0,
                                     cap_recv[0] ? SLAB_HDR + cap_recv[0] * nplanes : 0,
                                     cap_recv[1] ? SLAB_HDR + cap_recv[1] * nplanes : 0)))
         return rc;
+    if (trace) cudaEventRecord(tev[2], s->stream);
     // 5: arrivals behind the alive slots; a particle that crossed the periodic boundary is shifted by one period
     const double shift_lo = (sl->periodic && sl->rank == 0) ? -sl->period : 0.0;              // came from the top rank
     const double shift_hi = (sl->periodic && sl->rank == sl->nranks - 1) ? sl->period : 0.0;  // came from rank 0
@@ -714,10 +707,7 @@ static int slab_rebuild(sp_system* s) {
         sl->cap_send[d] = cap_send[d];
         sl->cap_recv[d] = cap_recv[d];
     }
-    if (trace) {
-        cudaStreamSynchronize(s->stream);
-        t2 = slab_now();
-    }
+    if (trace) cudaEventRecord(tev[3], s->stream);
     // 6: the ordinary build on the local window (in-cell order by descending "_gid"), then ghost flags
     if ((rc = sp_build_cells(s))) return rc;
     if (s->n)
@@ -738,15 +728,18 @@ static int slab_rebuild(sp_system* s) {
     sl->build_no++;
     sl->history++;
     if (trace) {
-        cudaStreamSynchronize(s->stream);
-        const double t3 = slab_now();
-        sl->trace_s[0] += t1 - t0;
-        sl->trace_s[1] += t2 - t1;
-        sl->trace_s[2] += t3 - t2;
-        if (++sl->trace_calls % 20 == 0)
-            fprintf(stderr, "[slab trace rank %d] calls=%lld select+pack=%.3f ms exchange+unpack=%.3f ms build=%.3f ms (bound n=%lld, caps %lld %lld | %lld %lld)\n",
-                    sl->rank, sl->trace_calls, 1e3 * sl->trace_s[0] / sl->trace_calls, 1e3 * sl->trace_s[1] / sl->trace_calls,
-                    1e3 * sl->trace_s[2] / sl->trace_calls, (long long)s->n, cap_send[0], cap_send[1], cap_recv[0], cap_recv[1]);
+        cudaEventRecord(tev[4], s->stream);
+        cudaEventSynchronize(tev[4]);
+        float ms[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 4; k++) cudaEventElapsedTime(&ms[k], tev[k], tev[k + 1]);
+        for (int k = 0; k < 4; k++) sl->trace_s[k] += ms[k];
+        if (++sl->trace_calls % 10 == 0) {
+            fprintf(stderr, "[slab trace rank %d] calls=%lld (last 10) select+pack=%.3f ms exchange=%.3f ms unpack=%.3f ms build+post=%.3f ms "
+                            "(bound n=%lld, caps %lld %lld | %lld %lld)\n",
+                    sl->rank, sl->trace_calls, sl->trace_s[0] / 10, sl->trace_s[1] / 10, sl->trace_s[2] / 10, sl->trace_s[3] / 10,
+                    (long long)s->n, cap_send[0], cap_send[1], cap_recv[0], cap_recv[1]);
+            for (int k = 0; k < 4; k++) sl->trace_s[k] = 0;
+        }
     }
     return SP_OK;
 }

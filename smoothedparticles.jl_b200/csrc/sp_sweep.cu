@@ -27,7 +27,15 @@ struct SweepCtx {
     int capk;                   // entries per target in the cached neighbour lists (multiple of 32)
     int n;                      // slots the launch covers
     const int* alive;           // device: slots [0, *alive) are alive, [*alive, n) is the dead tail of culled particles
+    // slab systems: the outermost ghost layer on either side only FEEDS sums (its own neighbourhood is incomplete), so its
+    // particles are not swept as targets: targets are the slots of the cells [tgt_key_lo, tgt_key_hi) (0, 0 = all)
+    int tgt_key_lo, tgt_key_hi;
 };
+__device__ __forceinline__ bool sp_is_target(const SweepCtx& c, int i) {
+    if (i >= *c.alive) return false;  // the dead tail [alive, n) takes no part (sp_internal.cuh)
+    if (c.tgt_key_hi && (i < c.cell_start[c.tgt_key_lo] || i >= c.cell_start[c.tgt_key_hi])) return false;
+    return true;
+}
 
 // Visit every candidate slot j of particle (xi,yi,zi): f(j, dx, dy, dz, d2).
 template <bool STRICT, class F>
@@ -87,7 +95,7 @@ __device__ __forceinline__ double sp_sqrt_fast(double a);
 template <class Op, bool STRICT>
 __global__ void __launch_bounds__(128) k_sweep(SpGrid g, SweepCtx c, typename Op::Params P, int self_flag) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *c.alive) return;  // the dead tail [alive, n) takes no part (sp_internal.cuh)
+    if (!sp_is_target(c, i)) return;
     if (!Op::active(P, i)) return;
     const double xi = c.x[i], yi = c.y[i], zi = c.z[i];
     typename Op::PS p;
@@ -462,6 +470,10 @@ __global__ void __launch_bounds__(128, 5) k_nbr_build(SpGrid g, SweepCtx c, int*
                                                       int* __restrict__ max_cnt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= *c.alive) return;  // the dead tail [alive, n) takes no part (sp_internal.cuh)
+    if (!sp_is_target(c, i)) {  // outermost ghost layer of a slab: no list
+        cnt[i] = 0;
+        return;
+    }
     const float ui = c.ux[i], vi = c.uy[i], wi = c.uz[i];
     const double T2 = g.T2;
     unsigned long long ui2, vi2, wi2, thr2, thr_lo2;
@@ -597,7 +609,7 @@ __global__ void __launch_bounds__(128, 6) k_sweep_list(SpGrid g, SweepCtx c, con
     const int i = (int)(gt / G);
     const int sub = (int)(gt % G);
     // whole groups leave together (i is uniform within a group), so the group shuffles below are safe
-    if (i >= *c.alive) return;  // the dead tail [alive, n) takes no part (sp_internal.cuh)
+    if (!sp_is_target(c, i)) return;
     if (!Op::active(P, i)) return;
     const double xi = c.x[i], yi = c.y[i], zi = c.z[i];
     typename Op::PS p;
@@ -688,6 +700,10 @@ __global__ void __launch_bounds__(128, MINB) k_nbr_build_sweep(SpGrid g, SweepCt
                                                                typename Op::Params P, int self_flag) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= *c.alive) return;  // the dead tail [alive, n) takes no part (sp_internal.cuh)
+    if (!sp_is_target(c, i)) {  // outermost ghost layer of a slab: no list, no sweep
+        cnt[i] = 0;
+        return;
+    }
     const int capk = c.capk;
     int* col = ids + ((size_t)(i >> 5) * capk << 5) + (i & 31);
     const double xi = c.x[i], yi = c.y[i], zi = c.z[i];
@@ -908,6 +924,13 @@ static void sp_sweep_ctx(sp_system* s, SweepCtx& c) {
     c.capk = s->nbr_capk;
     c.n = (int)s->n;
     c.alive = sp_alive(s);
+    c.tgt_key_lo = c.tgt_key_hi = 0;
+    if (s->g.slab_axis >= 0 && s->have_cells) {
+        const long long L = s->g.lim[0] * (s->g.slab_axis == 2 ? s->g.lim[1] : 1);  // cells per layer
+        const long long nl = s->g.lim[s->g.slab_axis];
+        c.tgt_key_lo = (int)(1 * L + 1);
+        c.tgt_key_hi = (int)((nl - 1) * L + 1);
+    }
 }
 
 // FP32 pre-filter inputs: coordinates in cell units u = (x - lo)/h and thresholds that can never misclassify.
