@@ -47,7 +47,7 @@ extern "C" {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef enum { ncclSuccess = 0 } ncclResult_t;
-typedef enum { ncclInt32 = 2, ncclFloat64 = 8 } ncclDataType_t;
+typedef enum { ncclInt8 = 0, ncclInt32 = 2, ncclInt64 = 4, ncclFloat64 = 8 } ncclDataType_t;
 typedef enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3 } ncclRedOp_t;
 }
 #endif
@@ -129,6 +129,17 @@ struct SlabState {
     long long cap_recv[2] = {0, 0};       // ... from below / from above
     long long gid_base = 0;
     bool fresh_particles = true;          // the host added particles: they have no "_gid" yet
+    // ---- peer-to-peer exchange over NVLink (default when CUDA IPC works; SP_SLAB_P2P=0 keeps every link on NCCL).
+    // One cudaMalloc'ed block per rank: [64 flag words][receive buffer "from below"][receive buffer "from above"]; the
+    // neighbours map it through CUDA IPC and WRITE their messages straight into it from the pack kernel (no staging
+    // buffer, no padding: the exact count is in the header), then raise a flag word; acknowledgements come back the same way.
+    unsigned long long* p2p_block = nullptr;       // my block (device memory)
+    unsigned long long* p2p_peer[2] = {nullptr, nullptr};  // the block of the rank below / above as mapped here
+    bool p2p_mapped[2] = {false, false};           // p2p_peer[d] came from cudaIpcOpenMemHandle (close it when done)
+    long long p2p_cap = 0, p2p_planes = 0;         // my receive buffers: entries per plane, planes
+    long long p2p_peer_cap[2] = {0, 0}, p2p_peer_planes[2] = {0, 0};
+    long long p2p_send_seq[2] = {0, 0}, p2p_recv_seq[2] = {0, 0};
+    int p2p_state = 0;                             // 0 = not tried, 1 = ready, -1 = unavailable (NCCL only)
     double trace_s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long trace_calls = 0;
 };
@@ -153,6 +164,13 @@ void sp_slab_free(sp_system* s) {
         sp_dfree(s, sl->recvbuf[d]);
     }
     sp_dfree(s, sl->d_cnt);
+    for (int d = 0; d < 2; d++)
+        if (sl->p2p_mapped[d] && sl->p2p_peer[d] && !(d == 1 && sl->p2p_peer[1] == sl->p2p_peer[0])) cudaIpcCloseMemHandle(sl->p2p_peer[d]);
+    if (sl->p2p_block) {
+        if (s->stream) cudaStreamSynchronize(s->stream);
+        cudaFree(sl->p2p_block);
+    }
+    cudaGetLastError();
     if (sl->h_cnt) cudaFreeHost(sl->h_cnt);
     for (int r = 0; r < SLAB_RING; r++)
         if (sl->ring_ev[r]) cudaEventDestroy(sl->ring_ev[r]);
@@ -301,11 +319,14 @@ __global__ void __launch_bounds__(SLAB_NB) k_slab_sel_scan(int* blk, int* d_cnt,
 // pass 3: ordered pack of every plane of the selected slots into the message (plane c at SLAB_HDR + c*msg_cap)
 __global__ void __launch_bounds__(256) k_slab_sel_pack(SpGrid g, SlabWin w, const double* x, long long cap, const double* ghost,
                                                        const int* blk, const int* d_cnt, SlabPlanes tab, int plane0,
-                                                       double* buf_dn, long long cap_dn, double* buf_up, long long cap_up) {
+                                                       double* buf_dn, long long stride_dn, double* buf_up, long long stride_up) {
+    // buf_*: the NCCL staging buffer, or — on a peer-to-peer link — the neighbour's receive buffer itself (remote stores
+    // over NVLink); stride_* = entries per plane of that buffer
     const int dir = blockIdx.y;
     double* buf = dir == 0 ? buf_dn : buf_up;
-    const long long mcap = dir == 0 ? cap_dn : cap_up;
+    const long long stride = dir == 0 ? stride_dn : stride_up;
     if (!buf) return;
+    const long long mcap = d_cnt[dir];  // the (clamped) message count
     long long lo, hi;
     w.send_window(dir, &lo, &hi);
     const long long len = max(hi - lo, 0LL);
@@ -327,7 +348,7 @@ __global__ void __launch_bounds__(256) k_slab_sel_pack(SpGrid g, SlabWin w, cons
         for (int q = 0; q < warp; q++) off += warp_tot[q];
         const long long m = off + __popc(bal & ((1u << lane) - 1u));
         if (sel && m < mcap)
-            for (int c = 0; c < tab.count; c++) buf[SLAB_HDR + (size_t)(plane0 + c) * mcap + m] = tab.p[c][s];
+            for (int c = 0; c < tab.count; c++) buf[SLAB_HDR + (size_t)(plane0 + c) * stride + m] = tab.p[c][s];
         __syncthreads();
         if (threadIdx.x == 0) {
             int t = 0;
@@ -337,40 +358,86 @@ __global__ void __launch_bounds__(256) k_slab_sel_pack(SpGrid g, SlabWin w, cons
         __syncthreads();
     }
 }
-// arrivals go behind the alive slots: slot = alive + off + t; entries beyond the message's count become dead slots
-__global__ void k_slab_unpack(SlabPlanes tab, int plane0, const double* buf, long long mcap, long long off, double shift,
-                              const int* counters, int* ref, int* d_cnt, int which) {
+// Arrival layout, decided on the device from the two message headers: d_cnt[2], d_cnt[3] = particles from below / above
+// (clamped to what the unpack launches cover: an excess raises the overflow flag), d_cnt[13] = slot offset of the second
+// message, d_cnt[14] = slots appended in total.  A message that came through NCCL occupies its full capacity (padding
+// becomes dead slots), a peer-to-peer message exactly its count.
+__global__ void k_slab_arrival_layout(const double* hdr_lo, long long cap_lo, int lo_padded, const double* hdr_hi, long long cap_hi,
+                                      int hi_padded, int* d_cnt) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    long long c_lo = hdr_lo ? (long long)hdr_lo[0] : 0, c_hi = hdr_hi ? (long long)hdr_hi[0] : 0;
+    if (c_lo > cap_lo || c_hi > cap_hi || c_lo < 0 || c_hi < 0) d_cnt[4] = 1;
+    c_lo = max(0LL, min(c_lo, cap_lo));
+    c_hi = max(0LL, min(c_hi, cap_hi));
+    d_cnt[2] = (int)c_lo;
+    d_cnt[3] = (int)c_hi;
+    const long long span_lo = hdr_lo ? (lo_padded ? cap_lo : c_lo) : 0;
+    const long long span_hi = hdr_hi ? (hi_padded ? cap_hi : c_hi) : 0;
+    d_cnt[13] = (int)span_lo;
+    d_cnt[14] = (int)(span_lo + span_hi);
+}
+// arrivals go behind the alive slots: slot = alive + off + t; in a padded (NCCL) message the entries beyond the count
+// become dead slots
+__global__ void k_slab_unpack(SlabPlanes tab, int plane0, const double* buf, long long stride, long long launch_cap, int padded,
+                              double shift, const int* counters, int* ref, const int* d_cnt, int which) {
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (t >= mcap) return;
-    const long long count = (long long)buf[0];
-    const long long slot = (long long)counters[SP_CNT_ALIVE] + off + t;
-    if (t == 0 && plane0 == 0) d_cnt[2 + which] = (int)count;
+    if (t >= launch_cap) return;
+    const long long count = d_cnt[2 + which];
+    const long long slot = (long long)counters[SP_CNT_ALIVE] + (which ? d_cnt[13] : 0) + t;
     if (t < count) {
         for (int c = 0; c < tab.count; c++) {
-            double v = buf[SLAB_HDR + (size_t)(plane0 + c) * mcap + t];
+            double v = buf[SLAB_HDR + (size_t)(plane0 + c) * stride + t];
             if (c == tab.axis_plane) v += shift;
             tab.p[c][slot] = v;
         }
-    } else {
+    } else if (padded) {
         // padding: a dead slot (NaN position, culled by the build).  Its other planes are cleared: a field the library
         // knows to be zero everywhere is not permuted by the build, so no stale value may sit in a slot below the new
         // alive count
         for (int c = 0; c < tab.count; c++) tab.p[c][slot] = c == tab.x_plane ? nan("") : 0.0;
-    }
+    } else
+        return;
     if (plane0 == 0) ref[slot] = (int)slot;
 }
-__global__ void k_slab_zero_tail(SlabPlanes tab, long long count, const int* counters) {
+// ---- peer-to-peer flags.  Flag words (unsigned long long) at the head of a rank's block:
+//   [0] sequence number of the newest message in my "from below" buffer   (written by the rank below)
+//   [1] ... in my "from above" buffer                                      (written by the rank above)
+//   [2] newest message of mine the rank below has consumed                 (written by the rank below)
+//   [3] ... the rank above has consumed                                    (written by the rank above)
+#define SLAB_P2P_FLAGS 64
+// one thread waits until *flag >= value; gives up after ~4 s of device clocks and raises d_cnt[6] (reported by a later
+// rebuild) instead of hanging the GPU
+__global__ void k_slab_wait(const volatile unsigned long long* flag, unsigned long long value, int* d_cnt) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const long long t0 = clock64();
+    while (*flag < value) {
+        __nanosleep(200);
+        if (clock64() - t0 > 8000000000LL) {
+            d_cnt[6] = 1;
+            break;
+        }
+    }
+    __threadfence_system();
+}
+__global__ void k_slab_signal(volatile unsigned long long* flag, unsigned long long value) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    __threadfence_system();
+    *flag = value;
+    __threadfence_system();
+}
+__global__ void k_slab_zero_tail(SlabPlanes tab, long long launch_count, const int* d_cnt, const int* counters) {
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (t >= count) return;
+    if (t >= launch_count || t >= d_cnt[14]) return;
     const long long slot = (long long)counters[SP_CNT_ALIVE] + t;
     for (int c = 0; c < tab.count; c++) tab.p[c][slot] = 0.0;
 }
-__global__ void k_slab_add_alive(int* counters, int add) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) counters[SP_CNT_ALIVE] += add;
+__global__ void k_slab_add_alive(int* counters, const int* d_cnt) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) counters[SP_CNT_ALIVE] += d_cnt[14];
 }
 __global__ void k_slab_clear(int* d_cnt) {
     if (threadIdx.x < 4 && blockIdx.x == 0) d_cnt[threadIdx.x] = 0;
     if (threadIdx.x == 8 && blockIdx.x == 0) d_cnt[8] = 0;
+    if ((threadIdx.x == 13 || threadIdx.x == 14) && blockIdx.x == 0) d_cnt[threadIdx.x] = 0;
 }
 // particles the host added have no global id yet: rank * 2^44 + base + slot (unique, deterministic)
 __global__ void k_slab_assign_gid(double* gid, const int* counters, double base) {
@@ -554,6 +621,106 @@ static long long slab_capacity(long long count) {
     return (c + 1023) / 1024 * 1024;
 }
 
+// (Re)create this rank's peer-to-peer block and map the neighbours' blocks.  Collective over the slab communicator
+// (every rank calls it in the same rebuild: a bootstrap rebuild, whose counts size the buffers).  The handles travel over
+// NCCL like the bootstrap counts; afterwards the message payload never touches NCCL on a link both ends mapped.
+struct SlabP2PHello {
+    cudaIpcMemHandle_t handle;
+    long long cap, planes, ok, pid_rank;
+};
+static int slab_p2p_setup(sp_system* s, long long want_cap, long long planes) {
+    SlabState* sl = s->slab;
+    static const bool off = getenv("SP_SLAB_P2P") && atoi(getenv("SP_SLAB_P2P")) == 0;
+    int below, above;
+    slab_peers(sl, &below, &above);
+    SP_CUDA(s, cudaStreamSynchronize(s->stream));
+    // drop the old mappings and block
+    for (int d = 0; d < 2; d++) {
+        if (sl->p2p_mapped[d] && sl->p2p_peer[d] && !(d == 1 && sl->p2p_peer[1] == sl->p2p_peer[0])) cudaIpcCloseMemHandle(sl->p2p_peer[d]);
+        sl->p2p_peer[d] = nullptr;
+        sl->p2p_mapped[d] = false;
+        sl->p2p_peer_cap[d] = sl->p2p_peer_planes[d] = 0;
+        sl->p2p_send_seq[d] = sl->p2p_recv_seq[d] = 0;
+    }
+    if (sl->p2p_block) cudaFree(sl->p2p_block);
+    sl->p2p_block = nullptr;
+    cudaGetLastError();
+    SlabP2PHello mine;
+    memset(&mine, 0, sizeof mine);
+    mine.cap = want_cap;
+    mine.planes = planes;
+    mine.pid_rank = sl->rank;
+    mine.ok = 0;
+    if (!off) {
+        const size_t bytes = SLAB_P2P_FLAGS * sizeof(unsigned long long) + 2 * (size_t)(SLAB_HDR + want_cap * planes) * sizeof(double);
+        if (cudaMalloc(&sl->p2p_block, bytes) == cudaSuccess && cudaMemset(sl->p2p_block, 0, bytes) == cudaSuccess &&
+            cudaIpcGetMemHandle(&mine.handle, sl->p2p_block) == cudaSuccess)
+            mine.ok = 1;
+        else {
+            cudaGetLastError();
+            if (sl->p2p_block) cudaFree(sl->p2p_block);
+            sl->p2p_block = nullptr;
+        }
+    }
+    sl->p2p_cap = mine.ok ? want_cap : 0;
+    sl->p2p_planes = mine.ok ? planes : 0;
+    // exchange the hellos with both neighbours (same order rule as every exchange here)
+    int rc = sp_ensure_stage(s, (long long)(3 * sizeof(SlabP2PHello) / sizeof(double)) + 8);
+    if (rc) return rc;
+    char* d_buf = reinterpret_cast<char*>(s->stage);
+    SlabP2PHello theirs[2];
+    memset(theirs, 0, sizeof theirs);
+    SP_CUDA(s, cudaMemcpyAsync(d_buf, &mine, sizeof mine, cudaMemcpyHostToDevice, s->stream));
+    SP_NCCL(s, g_nccl.GroupStart());
+    if (below >= 0) SP_NCCL(s, g_nccl.Send(d_buf, sizeof mine, ncclInt8, below, sl->comm, s->stream));
+    if (above >= 0) SP_NCCL(s, g_nccl.Send(d_buf, sizeof mine, ncclInt8, above, sl->comm, s->stream));
+    if (above >= 0) SP_NCCL(s, g_nccl.Recv(d_buf + 2 * sizeof mine, sizeof mine, ncclInt8, above, sl->comm, s->stream));
+    if (below >= 0) SP_NCCL(s, g_nccl.Recv(d_buf + sizeof mine, sizeof mine, ncclInt8, below, sl->comm, s->stream));
+    SP_NCCL(s, g_nccl.GroupEnd());
+    SP_CUDA(s, cudaMemcpyAsync(theirs, d_buf + sizeof mine, 2 * sizeof mine, cudaMemcpyDeviceToHost, s->stream));
+    SP_CUDA(s, cudaStreamSynchronize(s->stream));
+    const int peer[2] = {below, above};
+    for (int d = 0; d < 2; d++) {
+        if (peer[d] < 0 || !mine.ok || !theirs[d].ok) continue;  // this link stays on NCCL
+        if (peer[d] == sl->rank) {
+            sl->p2p_peer[d] = sl->p2p_block;  // a periodic slab exchanging with itself
+        } else if (d == 1 && peer[1] == peer[0] && sl->p2p_peer[0]) {
+            sl->p2p_peer[1] = sl->p2p_peer[0];  // two ranks, periodic: the same neighbour on both sides
+            sl->p2p_mapped[1] = sl->p2p_mapped[0];
+        } else {
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, theirs[d].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                continue;  // (the other end cannot know: see the agreement round below)
+            }
+            sl->p2p_peer[d] = reinterpret_cast<unsigned long long*>(ptr);
+            sl->p2p_mapped[d] = true;
+        }
+        sl->p2p_peer_cap[d] = theirs[d].cap;
+        sl->p2p_peer_planes[d] = theirs[d].planes;
+    }
+    // agreement: a link is peer-to-peer only if BOTH ends mapped the other's block.  One more tiny exchange.
+    long long mapped[2] = {sl->p2p_peer[0] ? 1 : 0, sl->p2p_peer[1] ? 1 : 0}, other[2] = {0, 0};
+    SP_CUDA(s, cudaMemcpyAsync(d_buf, mapped, sizeof mapped, cudaMemcpyHostToDevice, s->stream));
+    long long* d_l = reinterpret_cast<long long*>(d_buf);
+    SP_NCCL(s, g_nccl.GroupStart());
+    if (below >= 0) SP_NCCL(s, g_nccl.Send(d_l + 0, 1, ncclInt64, below, sl->comm, s->stream));
+    if (above >= 0) SP_NCCL(s, g_nccl.Send(d_l + 1, 1, ncclInt64, above, sl->comm, s->stream));
+    if (above >= 0) SP_NCCL(s, g_nccl.Recv(d_l + 3, 1, ncclInt64, above, sl->comm, s->stream));
+    if (below >= 0) SP_NCCL(s, g_nccl.Recv(d_l + 2, 1, ncclInt64, below, sl->comm, s->stream));
+    SP_NCCL(s, g_nccl.GroupEnd());
+    SP_CUDA(s, cudaMemcpyAsync(other, d_l + 2, sizeof other, cudaMemcpyDeviceToHost, s->stream));
+    SP_CUDA(s, cudaStreamSynchronize(s->stream));
+    for (int d = 0; d < 2; d++)
+        if (sl->p2p_peer[d] && !other[d]) {
+            if (sl->p2p_mapped[d] && !(d == 1 && sl->p2p_peer[1] == sl->p2p_peer[0])) cudaIpcCloseMemHandle(sl->p2p_peer[d]);
+            sl->p2p_peer[d] = nullptr;
+            sl->p2p_mapped[d] = false;
+        }
+    sl->p2p_state = 1;
+    return SP_OK;
+}
+
 static int slab_rebuild(sp_system* s) {
     SlabState* sl = s->slab;
     const int B = 256;
@@ -585,6 +752,8 @@ static int slab_rebuild(sp_system* s) {
             return sp_fail(s, SP_ERR_STATE, buf);
         }
         if (h[5]) return sp_fail(s, SP_ERR_STATE, "slab halo refresh: owner and ghost layers disagree");
+        if (h[6]) return sp_fail(s, SP_ERR_STATE, "slab exchange: a peer-to-peer message or acknowledgement did not arrive within "
+                                                  "the time limit (a neighbouring rank stopped, or the ranks do not issue the same calls)");
         if (h[12]) {
             char buf[300];
             snprintf(buf, sizeof buf,
@@ -643,8 +812,24 @@ static int slab_rebuild(sp_system* s) {
     std::vector<SlabPlanes> tabs;
     int nplanes = 0;
     slab_planes(s, tabs, &nplanes);
-    const long long biggest = std::max(std::max(cap_send[0], cap_send[1]), std::max(cap_recv[0], cap_recv[1]));
-    if ((rc = slab_ensure_buffers(s, SLAB_HDR + biggest * nplanes + 16))) return rc;
+    // peer-to-peer blocks: (re)created in the first bootstrap rebuild after the host touched the particles, sized from
+    // its counts (4x head room) — every rank is in that rebuild at the same time, so the handshake is collective
+    if (!steady && sl->history == 0) {
+        const long long most = std::max(std::max(cap_send[0], cap_send[1]), std::max(cap_recv[0], cap_recv[1]));
+        if ((rc = slab_p2p_setup(s, std::max<long long>(4 * most, 65536), nplanes + 4))) return rc;
+    }
+    // which links carry this rebuild's messages peer to peer: both ends evaluate the same numbers
+    bool p2p_send[2], p2p_recv[2];
+    for (int d = 0; d < 2; d++) {
+        p2p_send[d] = cap_send[d] && sl->p2p_peer[d] && cap_send[d] <= sl->p2p_peer_cap[d] && nplanes <= sl->p2p_peer_planes[d];
+        p2p_recv[d] = cap_recv[d] && sl->p2p_peer[d] && cap_recv[d] <= sl->p2p_cap && nplanes <= sl->p2p_planes;
+    }
+    long long nccl_most = 0;
+    for (int d = 0; d < 2; d++) {
+        if (!p2p_send[d]) nccl_most = std::max(nccl_most, cap_send[d]);
+        if (!p2p_recv[d]) nccl_most = std::max(nccl_most, cap_recv[d]);
+    }
+    if (nccl_most && (rc = slab_ensure_buffers(s, SLAB_HDR + nccl_most * nplanes + 16))) return rc;
     // room for the arrivals (growing reallocates every plane: rare, and it waits for the stream)
     const long long n_new = s->n + cap_recv[0] + cap_recv[1];
     if (n_new > s->cap) {
@@ -653,51 +838,94 @@ static int slab_rebuild(sp_system* s) {
         X = s->fields[0].d;
         ghost = s->fields[sl->f_ghost].d;
     }
+    // a rank's block: [flags][buffer "from below"][buffer "from above"]
+    auto p2p_buffer = [](unsigned long long* block, long long cap, long long planes, int which) -> double* {
+        return reinterpret_cast<double*>(block + SLAB_P2P_FLAGS) + (size_t)which * (size_t)(SLAB_HDR + cap * planes);
+    };
+    // what I send DOWN lands in the lower neighbour's "from above" buffer (1), what I send UP in the upper one's (0)
+    double* dst[2] = {nullptr, nullptr};
+    long long dst_stride[2] = {0, 0};
+    for (int d = 0; d < 2; d++) {
+        if (!cap_send[d]) continue;
+        if (p2p_send[d]) {
+            dst[d] = p2p_buffer(sl->p2p_peer[d], sl->p2p_peer_cap[d], sl->p2p_peer_planes[d], d == 0 ? 1 : 0);
+            dst_stride[d] = sl->p2p_peer_cap[d];
+            // the neighbour must have consumed my previous message before I overwrite it: it writes my flag 2 (below) / 3 (above)
+            SP_LAUNCH(s, k_slab_wait, 1, 32, 0, sl->p2p_block + 2 + d, (unsigned long long)sl->p2p_send_seq[d], sl->d_cnt);
+        } else {
+            dst[d] = sl->sendbuf[d];
+            dst_stride[d] = cap_send[d];
+        }
+    }
     // 3: ordered pack (all planes), headers
     if (s->n > 0 && (cap_send[0] || cap_send[1])) {
         int plane0 = 0;
         for (SlabPlanes& t : tabs) {
             SP_LAUNCH(s, k_slab_sel_pack, dim3(SLAB_NB, 2), B, 0, s->g, w, X, s->cap, ghost, sl->d_cnt + 16, sl->d_cnt, t, plane0,
-                      cap_send[0] ? sl->sendbuf[0] : (double*)nullptr, cap_send[0], cap_send[1] ? sl->sendbuf[1] : (double*)nullptr,
-                      cap_send[1]);
+                      dst[0], dst_stride[0], dst[1], dst_stride[1]);
             plane0 += t.count;
         }
     } else {
         // nothing selected on an empty system: the headers still have to say so
         for (int d = 0; d < 2; d++)
-            if (cap_send[d]) SP_CUDA(s, cudaMemsetAsync(sl->sendbuf[d], 0, SLAB_HDR * sizeof(double), s->stream));
+            if (dst[d]) SP_CUDA(s, cudaMemsetAsync(dst[d], 0, SLAB_HDR * sizeof(double), s->stream));
     }
+    for (int d = 0; d < 2; d++)
+        if (p2p_send[d]) {
+            sl->p2p_send_seq[d]++;
+            SP_LAUNCH(s, k_slab_signal, 1, 32, 0, sl->p2p_peer[d] + (d == 0 ? 1 : 0), (unsigned long long)sl->p2p_send_seq[d]);
+        }
     if (trace) cudaEventRecord(tev[1], s->stream);
-    // 4: one exchange
-    if ((rc = slab_exchange_payload(s, cap_send[0] ? SLAB_HDR + cap_send[0] * nplanes : 0,
-                                    cap_send[1] ? SLAB_HDR + cap_send[1] * nplanes : 0,
-                                    cap_recv[0] ? SLAB_HDR + cap_recv[0] * nplanes : 0,
-                                    cap_recv[1] ? SLAB_HDR + cap_recv[1] * nplanes : 0)))
+    // 4: one exchange: NCCL for the links that are not peer to peer, flag waits for those that are
+    if ((rc = slab_exchange_payload(s, cap_send[0] && !p2p_send[0] ? SLAB_HDR + cap_send[0] * nplanes : 0,
+                                    cap_send[1] && !p2p_send[1] ? SLAB_HDR + cap_send[1] * nplanes : 0,
+                                    cap_recv[0] && !p2p_recv[0] ? SLAB_HDR + cap_recv[0] * nplanes : 0,
+                                    cap_recv[1] && !p2p_recv[1] ? SLAB_HDR + cap_recv[1] * nplanes : 0)))
         return rc;
+    const double* src[2] = {nullptr, nullptr};
+    long long src_stride[2] = {0, 0};
+    for (int d = 0; d < 2; d++) {
+        if (!cap_recv[d]) continue;
+        if (p2p_recv[d]) {
+            sl->p2p_recv_seq[d]++;
+            SP_LAUNCH(s, k_slab_wait, 1, 32, 0, sl->p2p_block + d, (unsigned long long)sl->p2p_recv_seq[d], sl->d_cnt);
+            src[d] = p2p_buffer(sl->p2p_block, sl->p2p_cap, sl->p2p_planes, d);
+            src_stride[d] = sl->p2p_cap;
+        } else {
+            src[d] = sl->recvbuf[d];
+            src_stride[d] = cap_recv[d];
+        }
+    }
     if (trace) cudaEventRecord(tev[2], s->stream);
     // 5: arrivals behind the alive slots; a particle that crossed the periodic boundary is shifted by one period
     const double shift_lo = (sl->periodic && sl->rank == 0) ? -sl->period : 0.0;              // came from the top rank
     const double shift_hi = (sl->periodic && sl->rank == sl->nranks - 1) ? sl->period : 0.0;  // came from rank 0
-    {
+    if (cap_recv[0] + cap_recv[1]) {
+        SP_LAUNCH(s, k_slab_arrival_layout, 1, 32, 0, src[0], cap_recv[0], p2p_recv[0] ? 0 : 1, src[1], cap_recv[1], p2p_recv[1] ? 0 : 1,
+                  sl->d_cnt);
         int plane0 = 0;
         for (SlabPlanes& t : tabs) {
             if (cap_recv[0])
-                SP_LAUNCH(s, k_slab_unpack, sp_blocks(cap_recv[0], B), B, 0, t, plane0, sl->recvbuf[0], cap_recv[0], 0LL, shift_lo,
-                          s->counters, s->ref, sl->d_cnt, 0);
+                SP_LAUNCH(s, k_slab_unpack, sp_blocks(cap_recv[0], B), B, 0, t, plane0, src[0], src_stride[0], cap_recv[0],
+                          p2p_recv[0] ? 0 : 1, shift_lo, s->counters, s->ref, sl->d_cnt, 0);
             if (cap_recv[1])
-                SP_LAUNCH(s, k_slab_unpack, sp_blocks(cap_recv[1], B), B, 0, t, plane0, sl->recvbuf[1], cap_recv[1], cap_recv[0],
-                          shift_hi, s->counters, s->ref, sl->d_cnt, 1);
+                SP_LAUNCH(s, k_slab_unpack, sp_blocks(cap_recv[1], B), B, 0, t, plane0, src[1], src_stride[1], cap_recv[1],
+                          p2p_recv[1] ? 0 : 1, shift_hi, s->counters, s->ref, sl->d_cnt, 1);
             plane0 += t.count;
         }
-    }
-    if (cap_recv[0] + cap_recv[1]) {
         // fields that did not travel (zero everywhere): the arrival slots must hold zero too
         std::vector<SlabPlanes> ztabs;
         int nz = 0;
         slab_planes(s, ztabs, &nz, false, true);
         for (SlabPlanes& t : ztabs)
-            SP_LAUNCH(s, k_slab_zero_tail, sp_blocks(cap_recv[0] + cap_recv[1], B), B, 0, t, cap_recv[0] + cap_recv[1], s->counters);
-        SP_LAUNCH(s, k_slab_add_alive, 1, 32, 0, s->counters, (int)(cap_recv[0] + cap_recv[1]));
+            SP_LAUNCH(s, k_slab_zero_tail, sp_blocks(cap_recv[0] + cap_recv[1], B), B, 0, t, cap_recv[0] + cap_recv[1], sl->d_cnt,
+                      s->counters);
+        SP_LAUNCH(s, k_slab_add_alive, 1, 32, 0, s->counters, sl->d_cnt);
+        // tell the senders their buffers are free again: the message from below was the lower neighbour's UP message
+        // (its flag 3), the one from above the upper neighbour's DOWN message (its flag 2)
+        for (int d = 0; d < 2; d++)
+            if (p2p_recv[d])
+                SP_LAUNCH(s, k_slab_signal, 1, 32, 0, sl->p2p_peer[d] + (d == 0 ? 3 : 2), (unsigned long long)sl->p2p_recv_seq[d]);
     }
     s->n = n_new;
     s->n_exact = false;
