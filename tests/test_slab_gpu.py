@@ -26,11 +26,11 @@ def _free_port():
     return p
 
 
-def _run(case, world):
+def _run(case, world, env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "slab_worker.py"),
            case]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, **(env or {})))
     out = r.stdout + r.stderr
     assert r.returncode == 0 and "SLAB-OK" in out, out[-3000:]
     # keep the worker's verdict line (profiles/ keeps the ones of the multi-GPU runs)
@@ -53,6 +53,20 @@ def test_slab_two_ranks(case):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
     _run(case, 2)
+
+
+@pytest.mark.parametrize("case", ["box_steps", "box_periodic", "isph_cg"])
+def test_slab_nccl_links_single_rank(case):
+    # SP_SLAB_P2P=0: every link stays on NCCL (padded messages at the agreed capacity) — the path a rank takes when a
+    # neighbour's block cannot be mapped through CUDA IPC
+    _run(case, 1, env={"SP_SLAB_P2P": "0"})
+
+
+def test_slab_nccl_links_two_ranks():
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    _run("box_steps", 2, env={"SP_SLAB_P2P": "0"})
+    _run("box_periodic", 2, env={"SP_SLAB_P2P": "0"})
 
 
 def test_slab_four_ranks():
