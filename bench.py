@@ -182,19 +182,23 @@ def run_single(args):
     dom_ms = breakdown[dominant]
     hbm_peak, peak_kind = _peaks()
     achieved = ALG_BYTES[dominant] * n / (dom_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, l1 = None, None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(dominant)
+            tj = json.load(open(tpath))
+            traffic = tj.get(dominant)
+            l1 = (tj.get("l1") or {}).get(dominant)     # ncu: what actually bounds the kernel (committed capture, not live)
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": KERNEL_OF[dominant], "achieved": achieved, "peak": hbm_peak,
                 "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_kind": peak_kind,
                 "alg_bytes_per_particle": ALG_BYTES[dominant], "launch_ms": dom_ms,
-                "note": "pair sweeps are bound by the L1 data pipe (FP64 gathers of the neighbours), not by HBM: "
-                        "see fp64, step_hbm_frac and profiles/"}
+                "note": "pair sweeps are bound by the L1 line-touch rate (FP64 gathers of the neighbours: one distinct 128-byte "
+                        "line per clock and SM), not by HBM: see l1_ncu, fp64, step_hbm_frac and profiles/"}
     roofline["step_hbm_frac"] = BYTES_PER_UPDATE_STEP * value / (hbm_peak * 1e9)
+    if l1:
+        roofline["l1_ncu"] = l1
     pk = fp64_peak()
     if pk:
         roofline["fp64"] = {"peak_dfma_per_s": pk["dfma_per_s"], "peak_dadd_per_s": pk["dadd_per_s"],

@@ -253,10 +253,14 @@ static int run_step(sp_system* s, int32_t program, const int32_t* F, const doubl
         const int32_t f_kkm[4] = {v, Dv, x, ty};
         const double p_kkm[5] = {0.5 * dt, P[8], P[9], P[10], dt};
         if (first) STEP(sp_apply_impl(s, SP_OP_MOVE, f_mv, 4, p_mv, 1, 0));
-        if (slab) {
-            STEP(sp_slab_create_cell_list(s));
-        } else {
-            STEP(sp_build_cells(s));
+        {
+            // P is dead here: find_pressure! rewrites it for every particle before anything reads it (collapse3d.jl:140-141),
+            // so the build need not carry it along (one plane less to permute, and to send on a slab system)
+            const bool was = s->fields[Pr].transient;
+            s->fields[Pr].transient = true;
+            rc = slab ? sp_slab_create_cell_list(s) : sp_build_cells(s);
+            s->fields[Pr].transient = was;
+            if (rc) return rc;
         }
         STEP(sp_apply_impl(s, SP_OP_BALANCE_OF_MASS, f_bom, 4, p_bom, 4, 0));
         // (slab systems: the two ghost layers per side make the inner one integrate its own density — same neighbours,
