@@ -407,22 +407,30 @@ __global__ void k_slab_unpack(SlabPlanes tab, int plane0, const double* buf, lon
 #define SLAB_P2P_FLAGS 64
 // one thread waits until *flag >= value; gives up after ~4 s of device clocks and raises d_cnt[6] (reported by a later
 // rebuild) instead of hanging the GPU
-__global__ void k_slab_wait(const volatile unsigned long long* flag, unsigned long long value, int* d_cnt) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const long long t0 = clock64();
-    while (*flag < value) {
-        __nanosleep(200);
-        if (clock64() - t0 > 8000000000LL) {
-            d_cnt[6] = 1;
-            break;
+// (two flags per launch — one per direction; a null pointer is skipped)
+__global__ void k_slab_wait(const volatile unsigned long long* flag_a, unsigned long long value_a,
+                            const volatile unsigned long long* flag_b, unsigned long long value_b, int* d_cnt) {
+    if (threadIdx.x > 1 || blockIdx.x != 0) return;
+    const volatile unsigned long long* flag = threadIdx.x == 0 ? flag_a : flag_b;
+    const unsigned long long value = threadIdx.x == 0 ? value_a : value_b;
+    if (flag) {
+        const long long t0 = clock64();
+        while (*flag < value) {
+            __nanosleep(200);
+            if (clock64() - t0 > 8000000000LL) {
+                d_cnt[6] = 1;
+                break;
+            }
         }
     }
     __threadfence_system();
 }
-__global__ void k_slab_signal(volatile unsigned long long* flag, unsigned long long value) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void k_slab_signal(volatile unsigned long long* flag_a, unsigned long long value_a, volatile unsigned long long* flag_b,
+                              unsigned long long value_b) {
+    if (threadIdx.x > 1 || blockIdx.x != 0) return;
+    volatile unsigned long long* flag = threadIdx.x == 0 ? flag_a : flag_b;
     __threadfence_system();
-    *flag = value;
+    if (flag) *flag = threadIdx.x == 0 ? value_a : value_b;
     __threadfence_system();
 }
 __global__ void k_slab_zero_tail(SlabPlanes tab, long long launch_count, const int* d_cnt, const int* counters) {
@@ -850,13 +858,16 @@ static int slab_rebuild(sp_system* s) {
         if (p2p_send[d]) {
             dst[d] = p2p_buffer(sl->p2p_peer[d], sl->p2p_peer_cap[d], sl->p2p_peer_planes[d], d == 0 ? 1 : 0);
             dst_stride[d] = sl->p2p_peer_cap[d];
-            // the neighbour must have consumed my previous message before I overwrite it: it writes my flag 2 (below) / 3 (above)
-            SP_LAUNCH(s, k_slab_wait, 1, 32, 0, sl->p2p_block + 2 + d, (unsigned long long)sl->p2p_send_seq[d], sl->d_cnt);
         } else {
             dst[d] = sl->sendbuf[d];
             dst_stride[d] = cap_send[d];
         }
     }
+    // the neighbour must have consumed my previous message before I overwrite it: it writes my flag 2 (below) / 3 (above)
+    if (p2p_send[0] || p2p_send[1])
+        SP_LAUNCH(s, k_slab_wait, 1, 32, 0, p2p_send[0] ? sl->p2p_block + 2 : (unsigned long long*)nullptr,
+                  (unsigned long long)sl->p2p_send_seq[0], p2p_send[1] ? sl->p2p_block + 3 : (unsigned long long*)nullptr,
+                  (unsigned long long)sl->p2p_send_seq[1], sl->d_cnt);
     // 3: ordered pack (all planes), headers
     if (s->n > 0 && (cap_send[0] || cap_send[1])) {
         int plane0 = 0;
@@ -871,10 +882,11 @@ static int slab_rebuild(sp_system* s) {
             if (dst[d]) SP_CUDA(s, cudaMemsetAsync(dst[d], 0, SLAB_HDR * sizeof(double), s->stream));
     }
     for (int d = 0; d < 2; d++)
-        if (p2p_send[d]) {
-            sl->p2p_send_seq[d]++;
-            SP_LAUNCH(s, k_slab_signal, 1, 32, 0, sl->p2p_peer[d] + (d == 0 ? 1 : 0), (unsigned long long)sl->p2p_send_seq[d]);
-        }
+        if (p2p_send[d]) sl->p2p_send_seq[d]++;
+    if (p2p_send[0] || p2p_send[1])  // "message k is in your buffer": flag 1 of the rank below (from above), flag 0 of the rank above
+        SP_LAUNCH(s, k_slab_signal, 1, 32, 0, p2p_send[0] ? sl->p2p_peer[0] + 1 : (unsigned long long*)nullptr,
+                  (unsigned long long)sl->p2p_send_seq[0], p2p_send[1] ? sl->p2p_peer[1] + 0 : (unsigned long long*)nullptr,
+                  (unsigned long long)sl->p2p_send_seq[1]);
     if (trace) cudaEventRecord(tev[1], s->stream);
     // 4: one exchange: NCCL for the links that are not peer to peer, flag waits for those that are
     if ((rc = slab_exchange_payload(s, cap_send[0] && !p2p_send[0] ? SLAB_HDR + cap_send[0] * nplanes : 0,
@@ -888,7 +900,6 @@ static int slab_rebuild(sp_system* s) {
         if (!cap_recv[d]) continue;
         if (p2p_recv[d]) {
             sl->p2p_recv_seq[d]++;
-            SP_LAUNCH(s, k_slab_wait, 1, 32, 0, sl->p2p_block + d, (unsigned long long)sl->p2p_recv_seq[d], sl->d_cnt);
             src[d] = p2p_buffer(sl->p2p_block, sl->p2p_cap, sl->p2p_planes, d);
             src_stride[d] = sl->p2p_cap;
         } else {
@@ -896,6 +907,10 @@ static int slab_rebuild(sp_system* s) {
             src_stride[d] = cap_recv[d];
         }
     }
+    if (p2p_recv[0] || p2p_recv[1])
+        SP_LAUNCH(s, k_slab_wait, 1, 32, 0, p2p_recv[0] ? sl->p2p_block + 0 : (unsigned long long*)nullptr,
+                  (unsigned long long)sl->p2p_recv_seq[0], p2p_recv[1] ? sl->p2p_block + 1 : (unsigned long long*)nullptr,
+                  (unsigned long long)sl->p2p_recv_seq[1], sl->d_cnt);
     if (trace) cudaEventRecord(tev[2], s->stream);
     // 5: arrivals behind the alive slots; a particle that crossed the periodic boundary is shifted by one period
     const double shift_lo = (sl->periodic && sl->rank == 0) ? -sl->period : 0.0;              // came from the top rank
@@ -923,9 +938,10 @@ static int slab_rebuild(sp_system* s) {
         SP_LAUNCH(s, k_slab_add_alive, 1, 32, 0, s->counters, sl->d_cnt);
         // tell the senders their buffers are free again: the message from below was the lower neighbour's UP message
         // (its flag 3), the one from above the upper neighbour's DOWN message (its flag 2)
-        for (int d = 0; d < 2; d++)
-            if (p2p_recv[d])
-                SP_LAUNCH(s, k_slab_signal, 1, 32, 0, sl->p2p_peer[d] + (d == 0 ? 3 : 2), (unsigned long long)sl->p2p_recv_seq[d]);
+        if (p2p_recv[0] || p2p_recv[1])
+            SP_LAUNCH(s, k_slab_signal, 1, 32, 0, p2p_recv[0] ? sl->p2p_peer[0] + 3 : (unsigned long long*)nullptr,
+                      (unsigned long long)sl->p2p_recv_seq[0], p2p_recv[1] ? sl->p2p_peer[1] + 2 : (unsigned long long*)nullptr,
+                      (unsigned long long)sl->p2p_recv_seq[1]);
     }
     s->n = n_new;
     s->n_exact = false;
