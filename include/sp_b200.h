@@ -538,13 +538,20 @@ int32_t sp_slab_init_cuts(sp_system* sys, const uint8_t id[128], int32_t rank, i
 /* Owned cell layers [cell_lo, cell_hi) (0-based from the global key_phase) and their coordinate interval. */
 int32_t sp_slab_range(sp_system* sys, int64_t* cell_lo, int64_t* cell_hi, double* coord_lo, double* coord_hi,
                       int32_t* axis);
-/* create_cell_list! for a slab system: migration of owned particles that left the slab (ncclSend/ncclRecv of
- * every field), ghost halo of the two boundary cell layers, then the local cell-list build.  Afterwards the
- * particle count includes the ghosts; field "_ghost" is 0 for owned particles, 1 / 2 for ghosts received from
- * the lower / upper neighbour.  Particle order on a slab system is the device order (no reference numbering
- * exists across ranks): identify particles by a field of your own (e.g. a global id). */
+/* create_cell_list! for a slab system: ONE exchange round — every owned particle whose current position lies in the
+ * rank's first / last two owned cell layers or beyond goes to the lower / upper neighbour (ghost copies and migrants
+ * alike, every non-zero field); ownership afterwards follows from the position; then the local cell-list build on the
+ * owned layers plus two ghost layers per side.  The ranks of a node write these messages straight into each other's
+ * receive buffers (CUDA IPC over NVLink; SP_SLAB_P2P=0 or an unmappable link: NCCL send/recv); no host synchronisation
+ * in the steady state, all ranks must issue the same calls.  Afterwards the particle count includes the ghosts; field
+ * "_ghost" is 0 for owned particles, 1 / 2 for ghosts below / above the owned layers.  Particle order on a slab system
+ * is the device order (no reference numbering exists across ranks): identify particles by a field of your own (e.g. a
+ * global id).  With two ghost layers the inner one integrates its own density in the WCSPH loops, so those need no
+ * further exchange inside a step.  At least three cell layers per rank. */
 int32_t sp_slab_create_cell_list(sp_system* sys);
-/* Refresh the ghost copies of the listed fields from their owners (e.g. rho, P after find_pressure!). */
+/* Refresh the ghost copies of the listed fields from their owners — for solvers whose vectors change between rebuilds
+ * (the CG search direction; sp_poisson_cg does it itself).  A copy of slot ranges: boundary layers and ghost layers hold
+ * the same particles in the same order. */
 int32_t sp_slab_halo_refresh(sp_system* sys, const int32_t* fields, int32_t nfields);
 /* Owned (non-ghost) particle count on this rank after the last sp_slab_create_cell_list. */
 int32_t sp_slab_num_owned(sp_system* sys, int64_t* n_owned);
