@@ -250,7 +250,7 @@ def run_single(args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
         "breakdown_ms": breakdown, "cpu_baseline": cpu, "box": box,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def _key_lim(case):
@@ -441,16 +441,35 @@ def run_reference(args):
                                    f"Julia runtime); particle-updates/s of the CPU is independent of the number of copies"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ N > 1
 def run_multi(args):
     from bench_multi import run_multi as _run
-    _run(args, METRIC, UNIT, ClockSampler, _peaks)
+    _run(args, METRIC, UNIT, ClockSampler, _peaks, emit)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line of the contract, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    # Libraries write to fd 1 on their own (NCCL prints its version banner there when NCCL_DEBUG asks for it): everything
+    # but the JSON line goes to stderr, so stdout carries exactly one line.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     wd = os.environ.get("SP_BENCH_WATCHDOG")   # debugging aid: dump every thread's Python stack and exit after N seconds
     if wd:
         import faulthandler

@@ -278,7 +278,7 @@ def box_line(args, UNIT, ClockSampler):
                               "gpu_launches")} | {"unit": UNIT, "steps": args.steps, "warmup": args.warmup}
 
 
-def run_multi(args, METRIC, UNIT, ClockSampler, peaks):
+def run_multi(args, METRIC, UNIT, ClockSampler, peaks, emit):
     dist, rank, world = init_control_plane()
     r = run_slab_workload(args, args.workload, UNIT, ClockSampler)
     other = None
@@ -309,6 +309,6 @@ def run_multi(args, METRIC, UNIT, ClockSampler, peaks):
                          "note": "pair sweeps are bound by the L1 data pipe (FP64 gathers), not by HBM"},
             "breakdown_ms": breakdown, "cpu_baseline": None, "box": other,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     dist.barrier()
     dist.destroy_process_group()
