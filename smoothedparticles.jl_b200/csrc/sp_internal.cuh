@@ -102,7 +102,6 @@ struct sp_system {
     long long nbr_cap = 0;
     long long nbr_version = 0;     // x_version the lists were built for
     long long nbr_n = 0;
-    int nbr_group = 0;             // lanes per target the list layout was written for
     int nbr_capk = 64;             // list entries per target (multiple of 32; grows when a build reports more)
     bool nbr_max_pending = false;  // a build's longest-list report is on its way to h_counters[40]
     cudaEvent_t ev_nbr = nullptr;

@@ -465,7 +465,6 @@ __global__ void __launch_bounds__(TP, MINB) k_sweep_tile(SpGrid g, SweepCtx c, t
 // symmetric (see launch_sweep): dd <= 1 - delta is certainly a neighbour, dd > 1 + delta certainly is not, and only
 // the thin shell in between (~0.1 % of the candidates) needs the exact FP64 predicate.  So the build kernel reads
 // FP64 positions only for those few.
-template <int G>
 __global__ void __launch_bounds__(128, 5) k_nbr_build(SpGrid g, SweepCtx c, int* __restrict__ cnt, int* __restrict__ ids,
                                                       int* __restrict__ max_cnt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -482,10 +481,9 @@ __global__ void __launch_bounds__(128, 5) k_nbr_build(SpGrid g, SweepCtx c, int*
     asm("mov.b64 %0, {%1,%1};" : "=l"(wi2) : "f"(wi));
     asm("mov.b64 %0, {%1,%1};" : "=l"(thr2) : "f"(c.thr));
     asm("mov.b64 %0, {%1,%1};" : "=l"(thr_lo2) : "f"(c.thr_lo));
-    // entry k of target i lives at ((i / TPW) * (CAPK / G) + k / G) * 32 + (i % TPW) * G + k % G, TPW = 32 / G
-    const int TPW = 32 / G;
+    // entry k of target i lives at ((i / 32) * CAPK + k) * 32 + i % 32
     const int capk = c.capk;
-    int* col = ids + ((size_t)(i / TPW) * (capk / G) << 5) + (i % TPW) * G;
+    int* col = ids + ((size_t)(i >> 5) * capk << 5) + (i & 31);
     int n_out = 0;
     unsigned m0 = 0u, m1 = 0u, m2 = 0u;  // pending chunks: candidates that may be neighbours (newest in m0)
     unsigned s0 = 0u, s1 = 0u, s2 = 0u;  // ... of which certainly neighbours
@@ -508,7 +506,7 @@ __global__ void __launch_bounds__(128, 5) k_nbr_build(SpGrid g, SweepCtx c, int*
         while (m) {
             const int j = base + __ffs(m) - 1;
             m &= m - 1;
-            if (n_out < capk) col[((n_out / G) << 5) + (n_out % G)] = j;
+            if (n_out < capk) col[n_out << 5] = j;
             n_out++;
         }
     };
@@ -596,35 +594,22 @@ __global__ void __launch_bounds__(128, 5) k_nbr_build(SpGrid g, SweepCtx c, int*
     if (n_out > capk) atomicMax(max_cnt, n_out);  // rare: lets the host grow the lists for the next build
 }
 
-// Replay: G adjacent lanes share one target and take every G-th entry of its list, so a warp covers 32/G
-// consecutive slots (about one cell for G = 4): the G lanes of a target read neighbouring slots and the targets of
-// one cell walk the same candidate rows, which cuts the distinct cache lines per gather (the L1 data pipe is what
-// bounds this kernel).  Partial sums are combined by a fixed xor-butterfly, so results are deterministic.
-template <class Op, int G>
+// Replay: one thread per target walks its list column (the k-th entries of a warp are one 128-byte line).  (Several
+// lanes per target, combined by a butterfly, were measured in round 1: same L1 wavefronts, more requests — removed.)
+template <class Op>
 __global__ void __launch_bounds__(128, 6) k_sweep_list(SpGrid g, SweepCtx c, const int* __restrict__ cnt,
                                                        const int* __restrict__ ids, typename Op::Params P, int self_flag) {
-    constexpr int NACC = (int)(sizeof(typename Op::Acc) / sizeof(double));
-    static_assert(sizeof(typename Op::Acc) == NACC * sizeof(double), "Acc must be plain doubles");
-    const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const int i = (int)(gt / G);
-    const int sub = (int)(gt % G);
-    // whole groups leave together (i is uniform within a group), so the group shuffles below are safe
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (!sp_is_target(c, i)) return;
     if (!Op::active(P, i)) return;
     const double xi = c.x[i], yi = c.y[i], zi = c.z[i];
     typename Op::PS p;
     typename Op::Acc acc;
     Op::load(P, i, xi, yi, zi, p, acc);
-    double* av = reinterpret_cast<double*>(&acc);
-    if (G > 1 && sub != 0) {
-#pragma unroll
-        for (int a = 0; a < NACC; a++) av[a] = 0.0;
-    }
     const int n_nb = cnt[i];
     if (n_nb <= c.capk) {
-        constexpr int TPW = 32 / G;  // targets per warp tile
-        const int* col = ids + ((size_t)(i / TPW) * (c.capk / G) << 5) + (i % TPW) * G + sub;
-        const int n_it = (n_nb - sub + G - 1) / G;  // entries sub, sub+G, ...
+        const int* col = ids + ((size_t)(i >> 5) * c.capk << 5) + (i & 31);
+        const int n_it = n_nb;
         // U pairs per trip: all their loads (ids first, then the gathers) are issued before the first pair body, so
         // each warp keeps U*(3+NQ) gathers in flight — the kernel is bound by the latency / L1 cost of these loads
         constexpr int U = Op::NQ <= 1 ? 4 : 2;
@@ -663,22 +648,13 @@ __global__ void __launch_bounds__(128, 6) k_sweep_list(SpGrid g, SweepCtx c, con
             QGlobal<Op::NQ> q{P.qp, j};
             Op::pair(P, p, q, dx, dy, dz, sp_sqrt_fast(sp_d2(dx, dy, dz)), acc);
         }
-    } else if (sub == 0) {
+    } else {
         // more neighbours than the cache holds per target: the exact candidate scan, same visiting order
         sp_for_candidates<false>(g, c, xi, yi, zi, [&](int j, double dx, double dy, double dz, double d2) {
             if (d2 > g.T2 || j == i) return;
             QGlobal<Op::NQ> q{P.qp, j};
             Op::pair(P, p, q, dx, dy, dz, sp_sqrt_fast(d2), acc);
         });
-    }
-    if (G > 1) {
-        const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << ((threadIdx.x & 31) / G * G);
-#pragma unroll
-        for (int a = 0; a < NACC; a++) {
-#pragma unroll
-            for (int d = 1; d < G; d <<= 1) av[a] += __shfl_xor_sync(gmask, av[a], d);
-        }
-        if (sub != 0) return;
     }
     if (self_flag & 1) Op::self(P, p, acc);
     Op::store(P, i, p, acc);
@@ -1022,7 +998,7 @@ static int sp_ensure_nbr_cache(sp_system* s, SweepCtx& c) {
     bool need = false;
     int rc = sp_nbr_prepare(s, c, &need);
     if (rc || !need) return rc;
-    SP_LAUNCH(s, k_nbr_build<1>, sp_blocks(s->n, 128), 128, 0, s->g, c, s->nbr_cnt, s->nbr_ids, s->counters + 40);
+    SP_LAUNCH(s, k_nbr_build, sp_blocks(s->n, 128), 128, 0, s->g, c, s->nbr_cnt, s->nbr_ids, s->counters + 40);
     return sp_nbr_built(s);
 }
 
@@ -1075,10 +1051,10 @@ static int launch_sweep(sp_system* s, const typename Op::Params& P, int flags) {
                 return sp_nbr_built(s);
             }
         }
-        SP_LAUNCH(s, k_nbr_build<1>, nb, 128, 0, s->g, c, s->nbr_cnt, s->nbr_ids, s->counters + 40);
+        SP_LAUNCH(s, k_nbr_build, nb, 128, 0, s->g, c, s->nbr_cnt, s->nbr_ids, s->counters + 40);
         if ((rc = sp_nbr_built(s))) return rc;
     }
-    SP_LAUNCH(s, (k_sweep_list<Op, 1>), nb, 128, 0, s->g, c, s->nbr_cnt, s->nbr_ids, P, self_flag);
+    SP_LAUNCH(s, (k_sweep_list<Op>), nb, 128, 0, s->g, c, s->nbr_cnt, s->nbr_ids, P, self_flag);
     return SP_OK;
 }
 
