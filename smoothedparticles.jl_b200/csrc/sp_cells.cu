@@ -206,7 +206,7 @@ __global__ void k_mark_victims(const int* key, const int* ref, int trash, int* V
 // For a hole r (victim with r < n_new): i0 = number of victims with a larger index; the particle that lands
 // in r is the one at tail position t = N-1-i0, following the chain while t is itself a victim
 // (its content was overwritten earlier by the same rule).  Verified against the literal swap-with-tail loop of
-// core.jl:72-81 in tests/test_oracle_pins.py (host restatement of this rule) and on the device by the removal tests of
+// core.jl:72-81 in tests/test_oracle_pins.py::test_device_chain_rule_equals_the_literal_swap_with_tail_loop (host restatement of this rule) and on the device by the removal tests of
 // tests/test_parity_gpu.py.
 __global__ void k_chain(const int* V, const int* Vexcl, long long n, const int* counters, int* newref) {
     const int n_out = sp_new_victims(counters, n);

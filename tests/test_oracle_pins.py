@@ -321,3 +321,43 @@ def test_oracle_against_a_literal_python_port_on_random_inputs(dim):
                     p["x"] = tuple(map(float, row))
                 n = m
     assert checked_pairs > 5000 and removed > 100
+
+
+def _chain_rule_renumbering(victim):
+    """Host restatement of the DEVICE's parallel renumbering (csrc/sp_cells.cu: k_mark_victims / k_chain / k_apply_newref,
+    k_renumber_small): for a hole r (a victim with r < n_new) the particle that lands in it is the one at tail position
+    t = N-1-i0, i0 = number of victims with a larger index, following the chain while t is itself a victim."""
+    victim = np.asarray(victim, dtype=bool)
+    N = len(victim)
+    n_out = int(victim.sum())
+    n_new = N - n_out
+    excl = np.concatenate([[0], np.cumsum(victim)[:-1]])        # victims with a smaller index
+    newref = np.arange(N)
+    for r in range(n_new):
+        if not victim[r]:
+            continue
+        t = N - 1 - (n_out - (excl[r] + 1))
+        while victim[t]:
+            t = N - 1 - (n_out - (excl[t] + 1))
+        newref[t] = r
+    # survivors in their new numbering: result[new index] = old index
+    out = np.full(n_new, -1)
+    for old in range(N):
+        if not victim[old]:
+            out[newref[old] if old >= n_new else old] = old
+    return out
+
+
+def test_device_chain_rule_equals_the_literal_swap_with_tail_loop():
+    # core.jl:72-81 removes victims in descending index order, each hole taking the CURRENT last particle; the device
+    # computes the same permutation in parallel.  Random victim sets, dense and sparse, including victims at the tail.
+    rng = np.random.default_rng(77)
+    for trial in range(300):
+        n = int(rng.integers(1, 60))
+        p = rng.choice([0.05, 0.3, 0.7, 0.95])
+        victim = rng.uniform(size=n) < p
+        if trial % 7 == 0:
+            victim[-int(rng.integers(1, n + 1)):] = True       # a run of victims at the tail
+        expect = _literal_removal(range(n), ~victim)
+        got = _chain_rule_renumbering(victim)
+        assert list(got) == list(expect), (victim, got, expect)

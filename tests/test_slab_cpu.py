@@ -40,3 +40,20 @@ def test_partition_layers_and_owner():
     own = slab.owner_of(z, h, -1, slab.partition_layers(11, 2))   # cells -1..9 -> layers 0..10
     cells = np.floor(z / h).astype(int) + 1
     assert np.array_equal(own, np.where(cells < 6, 0, np.where(cells < 11, 1, -1)))
+
+
+def test_balanced_cuts():
+    # count-balanced slabs (sp_slab_init_cuts): dense end layers (walls) get thinner slabs, every slab >= 3 layers
+    counts = np.array([0, 500, 120, 120] + [120] * 60 + [120, 120, 500, 0])
+    for nranks in (2, 3, 4, 8):
+        cuts = slab.balanced_cuts(counts, nranks)
+        assert cuts[0] == 0 and cuts[-1] == len(counts) and len(cuts) == nranks + 1
+        widths = np.diff(cuts)
+        assert widths.min() >= 3
+        per = [counts[a:b].sum() for a, b in zip(cuts, cuts[1:])]
+        assert max(per) - min(per) <= 2 * counts.max()                  # within the granularity of whole layers
+        if nranks >= 3:
+            assert widths[0] < widths[1] and widths[-1] < widths[-2]    # the wall layers make the end slabs thinner
+    assert slab.balanced_cuts(np.ones(24), 8) == list(range(0, 25, 3))
+    with pytest.raises(AssertionError):
+        slab.balanced_cuts(np.ones(8), 4)
