@@ -499,7 +499,7 @@ function slab_range(sys::ParticleSystem)          # the cell layers [cell_lo, ce
 end
 slab_create_cell_list!(sys::ParticleSystem) =     # migration + ghost layers + the local create_cell_list!
     check(ccall((:sp_slab_create_cell_list, LIB), Int32, (Ptr{Cvoid},), sys.handle), sys.handle)
-function slab_halo_refresh!(sys::ParticleSystem, names::Symbol...)   # e.g. (:rho, :P) after find_pressure!
+function slab_halo_refresh!(sys::ParticleSystem, names::Symbol...)   # ghost copies of fields that change between rebuilds (a CG search vector); the WCSPH loops need none
     F = Int32[sys.fields[f][1] for f in names]
     check(ccall((:sp_slab_halo_refresh, LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}, Int32), sys.handle, F, length(F)), sys.handle)
 end
