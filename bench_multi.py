@@ -187,7 +187,13 @@ def run_slab_workload(args, workload, UNIT, ClockSampler, e2e=True, breakdown=Tr
            "gpu_launches": int(gpu_launches), "n_slots": n_local + int(n_ghost)}
 
     if breakdown:
-        # per-kernel breakdown on this rank (same steps, per-call timing)
+        # per-kernel breakdown on this rank (same steps, per-call timing) — on a fresh system: with the script's constants
+        # the dam break at this resolution is only stable for ~45 steps (profiles/r2_drift.md)
+        sysd.close()
+        sysd = make_system()
+        sysd.add_particles(x=x, v=v, rho=np.full(n_local, rho0), type=typ)
+        sysd.run_program(prog, prog_fields, prog_params, 3)
+        sysd.synchronize()
         acc = {k: 0.0 for k in ("move", "cell_list+halo", "balance_of_mass", "find_pressure", "internal_force",
                                 "accelerate")}
 
