@@ -6,6 +6,8 @@
 // and bench.py's cpu_baseline / `--impl reference` leg may load this library; the product
 // (smoothedparticles.jl_b200/) never does.
 //
+// PARITY UNPINNED against output of the Julia package itself (no Julia runtime here or on the GPU box, no network, and
+// the reference ships no golden vectors for this path) — what follows is the strongest pin obtainable without it.
 // PARITY PINNING.  The reference ships no golden vectors for this path.  What pins this
 // restatement to the Julia code is (1) the reference's own assertions, ported 1:1 and run
 // against this file in tests/test_oracle_pins.py: tests/test_kernels.jl:20-61 (kernel
