@@ -596,8 +596,8 @@ __global__ void __launch_bounds__(128, 5) k_nbr_build(SpGrid g, SweepCtx c, int*
 
 // Replay: one thread per target walks its list column (the k-th entries of a warp are one 128-byte line).  (Several
 // lanes per target, combined by a butterfly, were measured in round 1: same L1 wavefronts, more requests — removed.)
-template <class Op>
-__global__ void __launch_bounds__(128, 6) k_sweep_list(SpGrid g, SweepCtx c, const int* __restrict__ cnt,
+template <class Op, int MINB = 6>
+__global__ void __launch_bounds__(128, MINB) k_sweep_list(SpGrid g, SweepCtx c, const int* __restrict__ cnt,
                                                        const int* __restrict__ ids, typename Op::Params P, int self_flag) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (!sp_is_target(c, i)) return;
@@ -1047,12 +1047,22 @@ static int launch_sweep(sp_system* s, const typename Op::Params& P, int flags) {
     if (need) {
         if constexpr (SpFusedBuild<Op>::value) {
             if (sp_fused_build_enabled() && !(flags & SP_FLAG_UNFUSED_BUILD)) {
+                // 80 registers / 6 CTAs per SM; 72 and 64 registers spill and were measured slower (3.23 / 3.79 vs 3.00 ms)
                 SP_LAUNCH(s, (k_nbr_build_sweep<Op, 6>), nb, 128, 0, s->g, c, s->nbr_cnt, s->nbr_ids, s->counters + 40, P, self_flag);
                 return sp_nbr_built(s);
             }
         }
         SP_LAUNCH(s, k_nbr_build, nb, 128, 0, s->g, c, s->nbr_cnt, s->nbr_ids, s->counters + 40);
         if ((rc = sp_nbr_built(s))) return rc;
+    }
+    if constexpr (Op::NQ <= 1) {
+        // operators that gather one plane besides the position (the cached force sweep): 64 registers, 8 CTAs per SM —
+        // measured 1.21 -> 1.06 ms on the 10 M dam break (7 CTAs: 1.11 ms); SP_LIST_MINB=6 for the A/B comparison
+        static const int minb = getenv("SP_LIST_MINB") ? atoi(getenv("SP_LIST_MINB")) : 8;
+        if (minb == 8) {
+            SP_LAUNCH(s, (k_sweep_list<Op, 8>), nb, 128, 0, s->g, c, s->nbr_cnt, s->nbr_ids, P, self_flag);
+            return SP_OK;
+        }
     }
     SP_LAUNCH(s, (k_sweep_list<Op>), nb, 128, 0, s->g, c, s->nbr_cnt, s->nbr_ids, P, self_flag);
     return SP_OK;
