@@ -543,7 +543,8 @@ int32_t sp_slab_range(sp_system* sys, int64_t* cell_lo, int64_t* cell_hi, double
  * alike, every non-zero field); ownership afterwards follows from the position; then the local cell-list build on the
  * owned layers plus two ghost layers per side.  The ranks of a node write these messages straight into each other's
  * receive buffers (CUDA IPC over NVLink; SP_SLAB_P2P=0 or an unmappable link: NCCL send/recv); no host synchronisation
- * in the steady state, all ranks must issue the same calls.  Afterwards the particle count includes the ghosts; field
+ * in the steady state, all ranks must issue the same calls (a rank whose neighbour stops answering reports SP_ERR_STATE
+ * from a later rebuild, after SP_SLAB_TIMEOUT_S seconds — default 30 — of waiting on the device).  Afterwards the particle count includes the ghosts; field
  * "_ghost" is 0 for owned particles, 1 / 2 for ghosts below / above the owned layers.  Particle order on a slab system
  * is the device order (no reference numbering exists across ranks): identify particles by a field of your own (e.g. a
  * global id).  With two ghost layers the inner one integrates its own density in the WCSPH loops, so those need no

@@ -17,9 +17,11 @@
 //      (deterministic: block counts, one scan, ordered pack).  Ownership is a function of the position alone: the
 //      receiver owns what falls into its owned layers and keeps the rest of its window as ghosts; the sender keeps
 //      its copy of a particle that migrated away as a ghost (it is bit-identical to what the new owner holds);
-//   3. both messages travel in one ncclGroup at a CAPACITY known to both ends without talking: the count that went over
-//      the same link two rebuilds ago (both ends have it) times two; the actual count rides in the message header and
-//      stays on the device; unused entries arrive as NaN positions and are culled by the build;
+//   3. both messages travel at a CAPACITY known to both ends without talking: twice the larger of the counts that went
+//      over the same link two and three rebuilds ago (both ends have them); the actual count rides in the message header
+//      and stays on the device.  On a link both ends mapped through CUDA IPC the pack kernel stores straight into the
+//      neighbour's receive buffer over NVLink and flag words say "message k is there" / "message k is consumed"; any
+//      other link goes through one ncclGroup of send/recv at the full capacity (unused entries become dead slots);
 //   4. arrivals are appended behind the alive slots, the ordinary cell-list build (sp_cells.cu, no read-back) sorts
 //      everything, "_ghost" is set from the cell layer.
 // The host runs at most two rebuilds ahead of the device: rebuild b waits for the counts of rebuild b-2 (an event that
@@ -54,9 +56,8 @@ typedef enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3 } ncclRedOp_t
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
-
-#include <cstdio>
 
 #include "sp_internal.cuh"
 
@@ -144,6 +145,20 @@ struct SlabState {
     long long trace_calls = 0;
 };
 
+// how long a flag wait may spin, in SM clocks.  Generous on purpose: a neighbour that is merely late (module loading, a
+// host thread descheduled) must not be mistaken for one that stopped.
+static long long slab_wait_limit(const sp_system* s) {
+    static long long clocks = 0;
+    if (!clocks) {
+        double seconds = 30.0;
+        if (const char* e = getenv("SP_SLAB_TIMEOUT_S"))
+            if (atof(e) > 0.0) seconds = atof(e);
+        int khz = 0;
+        if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, s->device) != cudaSuccess || khz <= 0) khz = 2000000;
+        clocks = (long long)(seconds * 1000.0 * (double)khz);
+    }
+    return clocks;
+}
 static bool slab_trace_on() {
     static const bool on = getenv("SP_SLAB_TRACE") && atoi(getenv("SP_SLAB_TRACE"));
     return on;
@@ -405,11 +420,11 @@ __global__ void k_slab_unpack(SlabPlanes tab, int plane0, const double* buf, lon
 //   [2] newest message of mine the rank below has consumed                 (written by the rank below)
 //   [3] ... the rank above has consumed                                    (written by the rank above)
 #define SLAB_P2P_FLAGS 64
-// one thread waits until *flag >= value; gives up after ~4 s of device clocks and raises d_cnt[6] (reported by a later
-// rebuild) instead of hanging the GPU
+// one thread waits until *flag >= value; gives up after `limit` device clocks (slab_wait_limit: 30 s unless
+// SP_SLAB_TIMEOUT_S says otherwise) and raises d_cnt[6] (reported by a later rebuild) instead of hanging the GPU
 // (two flags per launch — one per direction; a null pointer is skipped)
 __global__ void k_slab_wait(const volatile unsigned long long* flag_a, unsigned long long value_a,
-                            const volatile unsigned long long* flag_b, unsigned long long value_b, int* d_cnt) {
+                            const volatile unsigned long long* flag_b, unsigned long long value_b, int* d_cnt, long long limit) {
     if (threadIdx.x > 1 || blockIdx.x != 0) return;
     const volatile unsigned long long* flag = threadIdx.x == 0 ? flag_a : flag_b;
     const unsigned long long value = threadIdx.x == 0 ? value_a : value_b;
@@ -417,7 +432,7 @@ __global__ void k_slab_wait(const volatile unsigned long long* flag_a, unsigned 
         const long long t0 = clock64();
         while (*flag < value) {
             __nanosleep(200);
-            if (clock64() - t0 > 8000000000LL) {
+            if (clock64() - t0 > limit) {
                 d_cnt[6] = 1;
                 break;
             }
@@ -867,7 +882,7 @@ static int slab_rebuild(sp_system* s) {
     if (p2p_send[0] || p2p_send[1])
         SP_LAUNCH(s, k_slab_wait, 1, 32, 0, p2p_send[0] ? sl->p2p_block + 2 : (unsigned long long*)nullptr,
                   (unsigned long long)sl->p2p_send_seq[0], p2p_send[1] ? sl->p2p_block + 3 : (unsigned long long*)nullptr,
-                  (unsigned long long)sl->p2p_send_seq[1], sl->d_cnt);
+                  (unsigned long long)sl->p2p_send_seq[1], sl->d_cnt, slab_wait_limit(s));
     // 3: ordered pack (all planes), headers
     if (s->n > 0 && (cap_send[0] || cap_send[1])) {
         int plane0 = 0;
@@ -910,7 +925,7 @@ static int slab_rebuild(sp_system* s) {
     if (p2p_recv[0] || p2p_recv[1])
         SP_LAUNCH(s, k_slab_wait, 1, 32, 0, p2p_recv[0] ? sl->p2p_block + 0 : (unsigned long long*)nullptr,
                   (unsigned long long)sl->p2p_recv_seq[0], p2p_recv[1] ? sl->p2p_block + 1 : (unsigned long long*)nullptr,
-                  (unsigned long long)sl->p2p_recv_seq[1], sl->d_cnt);
+                  (unsigned long long)sl->p2p_recv_seq[1], sl->d_cnt, slab_wait_limit(s));
     if (trace) cudaEventRecord(tev[2], s->stream);
     // 5: arrivals behind the alive slots; a particle that crossed the periodic boundary is shifted by one period
     const double shift_lo = (sl->periodic && sl->rank == 0) ? -sl->period : 0.0;              // came from the top rank
