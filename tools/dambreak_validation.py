@@ -14,6 +14,7 @@ normalisation, pressure law, wall treatment or time scheme does not land on thes
     python tools/dambreak_validation.py oracle            # CPU oracle (here or on the GPU box)
     python tools/dambreak_validation.py device            # CUDA path through the C ABI (GPU box)
     python tools/dambreak_validation.py oracle device     # both, and the difference between them
+    python tools/dambreak_validation.py --isph oracle     # the ISPH dam break (collapse_dry_implicit.jl) against the same tables
 Writes gpurun_out/dambreak_validation_<backends>.json."""
 import json
 import math
@@ -57,9 +58,13 @@ def globals_of(sys_, c):
     return X, H
 
 
-def run(system_cls, every=50, t_star_end=3.0):
-    case = configs.collapse_dry()
-    c = case.consts
+def run(system_cls, every=50, t_star_end=3.0, isph=False):
+    """WCSPH: collapse_dry.jl as shipped.  isph=True: collapse_dry_implicit.jl as shipped (dr = 1e-2, 23 172 particles, loop
+    :205-233 with the matrix-free CG in place of assemble_matrix + cg), whose make_plot (:242-255) uses the same tables."""
+    case = configs.collapse_dry_implicit() if isph else configs.collapse_dry()
+    c = dict(case.consts)
+    c.setdefault("width", 1.0)
+    c.setdefault("height", 2.0)
     scale = math.sqrt(2.0 * abs(c["g"][1]))
     nsteps = int(math.ceil(t_star_end / scale / c["dt"])) + every
     s = case.make(system_cls)
@@ -67,12 +72,15 @@ def run(system_cls, every=50, t_star_end=3.0):
     ts, Xs, Hs = [], [], []
     t0 = time.perf_counter()
     for k in range(nsteps + 1):
-        case.step(s)
-        if k % every == 0:   # the script samples after the step with index k and labels it k*dt (:212-222)
+        if not isph:
+            case.step(s)
+        if k % every == 0:   # collapse_dry.jl samples after the step with index k (:212-222), the ISPH script before it (:206-217)
             X, H = globals_of(s, c)
             ts.append(k * c["dt"] * scale)
             Xs.append(X)
             Hs.append(H)
+        if isph:
+            case.step(s)
     wall = time.perf_counter() - t0
     return {"t": ts, "X": Xs, "H": Hs, "steps": nsteps + 1, "particles": len(s), "wall_s": wall}
 
@@ -102,12 +110,17 @@ def main():
     res = {"config": "collapse_dry.jl as shipped (dr = 1.5e-2), loop :203-211, to t*sqrt(2g) = 3.0",
            "tables": "examples/reference/dambreak_{X,H}_{Violeau,Koshizuka}.csv (collapse_dry.jl:232-249)"}
     curves = {}
+    isph = "--isph" in sys.argv
+    if isph:
+        res["config"] = "collapse_dry_implicit.jl as shipped (dr = 1e-2), loop :205-233, to t*sqrt(2g) = 3.0"
+        res["tables"] = "examples/reference/dambreak_{X,H}_{Violeau,Koshizuka}.csv (collapse_dry_implicit.jl:242-255)"
+    every = 10 if isph else 50
     if "oracle" in sys.argv:
         from oracle.oracle import OracleSystem
-        curves["oracle"] = run(OracleSystem)
+        curves["oracle"] = run(OracleSystem, every=every, isph=isph)
     if "device" in sys.argv:
         from smoothedparticles_jl_b200 import ParticleSystem
-        curves["device"] = run(ParticleSystem)
+        curves["device"] = run(ParticleSystem, every=every, isph=isph)
     for who, cv in curves.items():
         res[who] = {"steps": cv["steps"], "particles": cv["particles"], "wall_s": cv["wall_s"], "vs_tables": compare(cv, tables),
                     "curve": {"t": cv["t"], "X": cv["X"], "H": cv["H"]}}
@@ -118,7 +131,7 @@ def main():
                                       "max_abs_dH": float(np.max(np.abs(np.asarray(a["H"]) - np.asarray(b["H"]))))}
         print("device - oracle", json.dumps(res["device_minus_oracle"]), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    name = "dambreak_validation_" + "_".join(curves) + ".json"
+    name = "dambreak_validation_" + ("isph_" if isph else "") + "_".join(curves) + ".json"
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", name), "w"))
 
 
