@@ -126,8 +126,24 @@ def collapse_dry(dr: float = 1.5e-2) -> Case:
 
 
 # --------------------------------------------------------------------------- collapse3d.jl
-def collapse3d(dr: float = 5.0e-3, depth_scale: float = 1.0, z_range=None) -> Case:
+def relabel_axes(axis: int):
+    """Cyclic relabelling of the coordinate axes that makes physical axis ``axis`` the third one: column k of a relabelled
+    vector is column ``perm[k]`` of the physical one (cyclic, so handedness is kept).  The slab decomposition cuts along the
+    slowest axis of the cell key (z in 3-D, csrc/sp_slab.cu); a host that wants to cut along x or y hands the library
+    relabelled coordinates — every registered pair operator depends on positions through differences and distances only,
+    and vector parameters (gravity) are relabelled with them — and relabels vector fields back after a download
+    (``inverse``: physical[:, perm] = relabelled)."""
+    assert axis in (0, 1, 2)
+    return [(axis + 1) % 3, (axis + 2) % 3, axis]
+
+
+def collapse3d(dr: float = 5.0e-3, depth_scale: float = 1.0, z_range=None, slab_axis: int = 2) -> Case:
     """examples/collapse3d.jl:28-84 and :134-151.
+
+    ``slab_axis`` (0, 1 or 2): the physical axis a slab decomposition should cut along.  2 (default) is the script as it
+    stands; 0 / 1 hand the library cyclically relabelled coordinates (``relabel_axes``) so that axis becomes the slowest
+    axis of the cell key — same physics, same neighbour sets, sums in a different visiting order (``case.consts["perm"]``
+    maps back).  The device recipe is dropped for a relabelled case (host generation + upload).
 
     ``depth_scale`` extrudes the box (and the water column) along z — the direction the dam break is invariant
     in — for weak scaling over slabs; ``z_range=(lo, hi)`` generates only the lattice points with lo <= z < hi
@@ -171,6 +187,13 @@ def collapse3d(dr: float = 5.0e-3, depth_scale: float = 1.0, z_range=None) -> Ca
     o_fp = ops.find_pressure(dt, c, rho0)
     o_if = ops.internal_force("wendland3", m, h, mu, rho0)
     o_mv = ops.move(dt)
+    perm = relabel_axes(slab_axis)
+    recipe = ((grid, fluid_g, {"rho": rho0, "type": 0.0}), (grid, walls_g, {"rho": rho0, "type": 1.0}))
+    if slab_axis != 2:
+        init["x"] = np.ascontiguousarray(x[:, perm])
+        g = tuple(g[k] for k in perm)
+        domain = geo.Box(*(domain.lo[k] for k in perm), *(domain.hi[k] for k in perm))
+        recipe = ()
     o_ac = ops.accelerate(0.5 * dt, g)
 
     def step(sys):  # :136-150
@@ -183,10 +206,9 @@ def collapse3d(dr: float = 5.0e-3, depth_scale: float = 1.0, z_range=None) -> Ca
         sys.apply(o_ac)
 
     return Case("collapse3d", fields, domain, h, init, step,
-                consts=dict(dr=dr, h=h, rho0=rho0, m=m, c=c, mu=mu, nu=nu, dt=dt, g=g),
+                consts=dict(dr=dr, h=h, rho0=rho0, m=m, c=c, mu=mu, nu=nu, dt=dt, g=g, perm=perm),
                 program=K["SP_PROGRAM_WCSPH_3D"], program_fields=("x", "v", "Dv", "rho", "Drho", "P", "type"),
-                program_params=(float(K["SP_KERNEL_WENDLAND3"]), m, h, 2 * nu, dt, c * c, rho0, mu, *g), dim=3,
-                recipe=((grid, fluid_g, {"rho": rho0, "type": 0.0}), (grid, walls_g, {"rho": rho0, "type": 1.0})))
+                program_params=(float(K["SP_KERNEL_WENDLAND3"]), m, h, 2 * nu, dt, c * c, rho0, mu, *g), dim=3, recipe=recipe)
 
 
 def collapse3d_dr_for(n_target: float) -> float:
