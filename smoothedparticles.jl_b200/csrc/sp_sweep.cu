@@ -10,6 +10,21 @@
 // contiguous slot range; the default order walks those 3 (2-D) / 9 (3-D) ranges, SP_FLAG_STRICT_ORDER
 // walks the 9/27 cells in key_diff order (di outermost), which with the descending in-cell order is
 // exactly the reference's accumulation order.
+//
+// Kernels in this file, in the order a time step meets them (DESIGN.md §4 has the measurements):
+//   k_prefilter_coords       FP32 cell-unit coordinates for the conservative pre-filter (also written by the cell-list permute)
+//   k_nbr_build_sweep<Op>    DEFAULT for the first pair sweep after a position change: FP32x2 candidate scan with one
+//                            conservative threshold -> the "maybe" slots go to the target's own column of the warp-tiled list ->
+//                            replay of that column with the exact FP64 predicate (d2 > T2) inside the pair body, compacted in
+//                            place: leaves the exact neighbour list in visiting order AND the operator's result
+//   k_nbr_build              the list alone (operators without FUSED_BUILD, SP_FLAG_UNFUSED_BUILD): two thresholds, only the
+//                            thin shell between them takes the FP64 test
+//   k_sweep_list<Op>         every later sweep of the same position version: replay of the cached list (ids prefetched one
+//                            trip ahead)
+//   k_sweep<Op,STRICT>       no lists: the candidate scan with the exact predicate per candidate; STRICT = reference
+//                            accumulation order (SP_FLAG_STRICT_ORDER), also the fallback for targets whose list overflowed
+//   k_sweep_tile<Op>         the one alternative kept (SP_FLAG_TILE_KERNEL): shared-memory tile staged by TMA bulk copies
+//   k_unary<Op>              apply_unary! (core.jl:138-142)
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
