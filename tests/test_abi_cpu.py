@@ -136,3 +136,24 @@ def test_every_entry_point_is_documented_and_bound_for_julia():
     assert {s for s in syms if ":" + s not in shim} <= instrumentation
     # and the Python binding table covers the header exactly
     assert sorted(sp.abi.SIGNATURES) == syms
+
+
+def test_header_is_plain_c_and_a_c_program_links(tmp_path):
+    """include/sp_b200.h is the drop-in boundary: it must compile as C99 (pedantic) and as C++, and a C program must link
+    against libsp_b200.so and see the documented error behaviour (tests/c_abi_consumer.c; with a GPU it also runs one tiny
+    system through create / resize / upload / create_cell_list / destroy)."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    inc = os.path.join(root, "include")
+    src = os.path.join(root, "tests", "c_abi_consumer.c")
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, src], check=True)
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-pedantic", "-fsyntax-only", "-x", "c++", "-I", inc, src], check=True)
+    libdir = os.path.dirname(sp.abi.library_path()) if hasattr(sp.abi, "library_path") else os.path.join(root, "smoothedparticles.jl_b200")
+    exe = str(tmp_path / "consumer")
+    subprocess.run(["gcc", "-std=c99", "-I", inc, src, "-o", exe, "-L", libdir, "-lsp_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, (p.returncode, p.stdout, p.stderr)
+    assert "c-abi consumer ok" in p.stdout
