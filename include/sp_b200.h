@@ -231,8 +231,8 @@ enum {
     SP_OP_ROD_FIND_E = 66,
     /* binary. fields {x, X, A, e}; params {h}   eta = inv(A_p)*X_pq - x_pq;  e_p += dot(eta, eta)   rod.jl:185-188 */
 
-    /* SHTC fluid (full 3x3 distortion field A, stress tensor) — examples/SHTC/ldc.jl.  GPU parity check pending
-       (tests/pending_gpu_round2.py); the oracle side is pinned in tests/test_shtc_cpu.py. */
+    /* SHTC fluid (full 3x3 distortion field A, stress tensor) — examples/SHTC/ldc.jl.  Parity on B200:
+       tests/test_shtc_gpu.py; the oracle side is pinned in tests/test_shtc_cpu.py. */
     SP_OP_SHTC_FIND_STRESS = 70,
     /* unary. fields {A, rho, stress}; params {c_l, c_s, rho_ref}   G = A'*A;
        stress = c_l^2*(rho - rho_ref)*I + c_s^2*rho*G*dev(G),  rho_ref = rho0/(1 + acf)        ldc.jl:118-121 */
@@ -253,8 +253,8 @@ enum {
 
     /* SHTC solid in 2-D (vibrating beryllium plate) — examples/SHTC/beryllium.jl.  T, L, A are RealMatrix fields; the
        script's own outer/det/inv/dev (:79-103) are the 2-D ones (inv sets [3,3] = 1).  w_h / rDw_h are the script's
-       "structural" kernels wendland2h / rDwendland2h (:44-52, strict x < 1).  GPU parity check pending
-       (tests/pending_gpu_round2.py); the oracle side is pinned in tests/test_shtc_cpu.py.  update_x! is SP_OP_ADVECT. */
+       "structural" kernels wendland2h / rDwendland2h (:44-52, strict x < 1).  Parity on B200:
+       tests/test_shtc_gpu.py; the oracle side is pinned in tests/test_shtc_cpu.py.  update_x! is SP_OP_ADVECT. */
     SP_OP_BE_FIND_L = 80,
     /* binary. fields {x, v, m, T, L}; params {kernel, h, rho0}   ker = m_q/rho0*rDw(h,r):
        T_p += ker*outer(x_pq, x_pq);  L_p += ker*outer(v_pq, x_pq)                              beryllium.jl:140-146 */
@@ -275,8 +275,8 @@ enum {
     /* unary. fields {v, f, m}; params {hdt}   v += hdt*f/m                                        beryllium.jl:132-134 */
 
     /* SHTC solid in 3-D (twisting column) — examples/SHTC/twist3d.jl: the beryllium operators with full 3x3 matrices,
-       StaticArrays' general inverse and the 3-D structural kernels wendland3h / rDwendland3h (:43-51).  GPU parity check
-       pending (tests/pending_gpu_round2.py); the oracle side is pinned in tests/test_shtc_cpu.py.
+       StaticArrays' general inverse and the 3-D structural kernels wendland3h / rDwendland3h (:43-51).  Parity on B200:
+       tests/test_shtc_gpu.py; the oracle side is pinned in tests/test_shtc_cpu.py.
        reset! is SP_OP_BE_RESET, update_x! is SP_OP_ADVECT. */
     SP_OP_TW_FIND_L = 90,
     /* binary. fields {x, v, m, T, L}; params {kernel, h, rho0}                                  twist3d.jl:135-141 */
@@ -295,7 +295,7 @@ enum {
 
     /* SHTC fluid between rotating cylinders (Taylor-Couette) — examples/SHTC/taco.jl.  find_L!, update_A!, reset! and
        find_rho! (with self) are SP_OP_BE_FIND_L / BE_UPDATE_A / BE_RESET / BE_FIND_J with rho0 = 1 (the same arithmetic:
-       m/1.0 is m), relax_A! is SP_OP_SHTC_RELAX_A.  GPU parity check pending (tests/pending_gpu_round2.py). */
+       m/1.0 is m), relax_A! is SP_OP_SHTC_RELAX_A.  Parity on B200: tests/test_shtc_gpu.py. */
     SP_OP_TA_FIND_T = 100,
     /* unary. fields {A, T, P, rho}; params {rho0, c_0, c_s}   G = A'*A;  P = c_0^2*(rho - rho0)*rho0/rho;
        T = -P/rho^2*I + c_s^2*G*dev(G)*subinv(T)                                                  taco.jl:148-152 */

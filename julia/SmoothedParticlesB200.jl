@@ -185,7 +185,7 @@ rod_pull(X1_min, fy; X = :X, f = :f) = Operator(63, [X, f], [X1_min, fy])
 rod_update_v(hdt, m, X1_clamp; v = :v, f = :f, X = :X) = Operator(64, [v, f, X], [hdt, m, X1_clamp])
 rod_update_x(dt; x = :x, v = :v, A = :A, H = :H, f = :f, e = :e) = Operator(65, [x, v, A, H, f, e], [dt])
 rod_find_e(h; x = :x, X = :X, A = :A, e = :e) = Operator(66, [x, X, A, e], [h])
-# examples/SHTC/ldc.jl:90-133 (A and stress are 9-component RealMatrix fields; GPU parity check pending)
+# examples/SHTC/ldc.jl:90-133 (A and stress are 9-component RealMatrix fields; parity on B200: tests/test_shtc_gpu.py)
 shtc_find_stress(c_l, c_s, rho0, acf; A = :A, rho = :rho, stress = :stress) = Operator(70, [A, rho, stress], [c_l, c_s, rho0 / (1.0 + acf)])
 shtc_update_v(kernel, h, dt, m; x = :x, v = :v, rho = :rho, stress = :stress, type = :type) =
     Operator(71, [x, v, rho, stress, type], [KERNELS[kernel], h, dt * m])
@@ -194,7 +194,7 @@ shtc_convect_A(kernel, h, dt, m, skip_type; x = :x, v = :v, rho = :rho, A = :A, 
     Operator(73, [x, v, rho, A, type], [KERNELS[kernel], h, dt * m, skip_type])
 shtc_relax_A(dt, tau; A = :A) = Operator(74, [A], [dt, tau])
 shtc_move(dt; x = :x, v = :v, type = :type) = Operator(75, [x, v, type], [dt])
-# examples/SHTC/beryllium.jl:132-184 (update_x! is advect; GPU parity check pending)
+# examples/SHTC/beryllium.jl:132-184 (update_x! is advect; parity on B200: tests/test_shtc_gpu.py)
 be_find_L(kernel, h, rho0; x = :x, v = :v, m = :m, T = :T, L = :L) = Operator(80, [x, v, m, T, L], [KERNELS[kernel], h, rho0])
 be_update_A(hdt; A = :A, T = :T, L = :L) = Operator(81, [A, T, L], [hdt])
 be_find_J(kernel, h, rho0; x = :x, m = :m, T = :T, J = :J, K = :K) = Operator(82, [x, m, T, J, K], [KERNELS[kernel], h, rho0])
@@ -202,7 +202,7 @@ be_find_T(rho0, c_0, c_s; A = :A, T = :T, P = :P, J = :J) = Operator(83, [A, T, 
 be_find_f(kernel, h, rho0, c_p; x = :x, m = :m, T = :T, K = :K, f = :f) = Operator(84, [x, m, T, K, f], [KERNELS[kernel], h, rho0, c_p])
 be_reset(; f = :f, L = :L, T = :T, J = :J, K = :K, J0 = :J0, K0 = :K0) = Operator(85, [f, L, T, J, K, J0, K0], Float64[])
 be_update_v(hdt; v = :v, f = :f, m = :m) = Operator(86, [v, f, m], [hdt])
-# examples/SHTC/twist3d.jl:125-172 (reset! is be_reset, update_x! is advect; GPU parity check pending)
+# examples/SHTC/twist3d.jl:125-172 (reset! is be_reset, update_x! is advect; parity on B200: tests/test_shtc_gpu.py)
 tw_find_L(kernel, h, rho0; x = :x, v = :v, m = :m, T = :T, L = :L) = Operator(90, [x, v, m, T, L], [KERNELS[kernel], h, rho0])
 tw_update_A(hdt; A = :A, T = :T, L = :L) = Operator(91, [A, T, L], [hdt])
 tw_find_J(kernel, h, rho0; x = :x, m = :m, T = :T, J = :J, K = :K) = Operator(92, [x, m, T, J, K], [KERNELS[kernel], h, rho0])
@@ -210,7 +210,7 @@ tw_find_T(rho0, c_0, c_s; A = :A, T = :T, P = :P, J = :J) = Operator(93, [A, T, 
 tw_find_f(kernel, h, rho0, c_p; x = :x, m = :m, T = :T, K = :K, f = :f) = Operator(94, [x, m, T, K, f], [KERNELS[kernel], h, rho0, c_p])
 tw_update_v(hdt; x = :x, v = :v, f = :f, m = :m) = Operator(95, [x, v, f, m], [hdt])
 # examples/SHTC/taco.jl:108-162: find_L!, update_A!, reset!, find_rho! (apply! with self = true) are be_find_L / be_update_A /
-# be_reset / be_find_J with rho0 = 1.0 and the taco field names; relax_A! is shtc_relax_A (GPU parity check pending)
+# be_reset / be_find_J with rho0 = 1.0 and the taco field names; relax_A! is shtc_relax_A (parity on B200: tests/test_shtc_gpu.py)
 ta_find_T(rho0, c_0, c_s; A = :A, T = :T, P = :P, rho = :rho) = Operator(100, [A, T, P, rho], [rho0, c_0, c_s])
 ta_find_f(kernel, h, c_p, rho0; x = :x, m = :m, T = :T, lambda = :lambda, f = :f) =
     Operator(101, [x, m, T, lambda, f], [KERNELS[kernel], h, (c_p / rho0)^2])

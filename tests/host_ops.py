@@ -1,4 +1,4 @@
-"""Runs the DEVICE operator bodies on the host.  Test infrastructure for operators whose GPU run is still pending.
+"""Runs the DEVICE operator bodies on the host: a second look at the operators without a GPU (every operator also has a B200 parity test).
 
 The operator structs of csrc/sp_ops.cuh (and the kernel families of csrc/sp_kernels.cuh) are plain C++ apart from the
 CUDA qualifiers and a handful of rounding intrinsics, so they are compiled for the host with those mapped to their
